@@ -1,0 +1,101 @@
+"""The oracle restatement must reproduce the unmodified reference (golden vectors)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusesg_b200.utils.synthetic import CONFIGS, state_dict_spec, synthetic_inputs, synthetic_state_dict
+from oracle import denoiser_oracle as O
+from oracle import edm_oracle as E
+
+
+def _net(cfg, sd):
+    def f(adj, node, flags, labels, sa, sn):
+        return O.denoiser_forward(sd, img=cfg["img"], embed=cfg["embed"], depths=cfg["depths"], heads=cfg["heads"],
+                                  window=cfg["window"], self_condition=cfg["self_cond"], adj=adj, node=node,
+                                  flags=flags, noise_labels=labels, sc_adj=sa, sc_node=sn)
+    return f
+
+
+@pytest.mark.parametrize("name", ["vg", "coco", "tiny", "n64w16"])
+def test_state_dict_layout_matches_reference(name, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, f"layout_{name}.json")))
+    spec = state_dict_spec(CONFIGS[name])
+    assert [k for k, _, _ in ref["layout"]] == list(spec.keys())
+    for (k, shape, _), (shape2, _) in zip(ref["layout"], spec.values()):
+        assert tuple(shape) == tuple(shape2), k
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 3), ("vg", 2), ("coco", 2)])
+def test_forward_matches_reference(name, batch, golden_dir):
+    torch.set_num_threads(8)
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"forward_{name}.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    adj, node, flags, sigmas, sc_adj, sc_node = synthetic_inputs(cfg, batch, seed=7)
+    labels = torch.from_numpy(g["labels"])
+    net = _net(cfg, sd)
+    with torch.no_grad():
+        a, n = net(adj, node, flags, labels, sc_adj, sc_node)
+        a0, n0 = net(adj, node, flags, labels, None, None)
+    # identical op sequence in fp32; the only slack is GEMM blocking order
+    for got, key in ((a, "adj_sc"), (n, "node_sc"), (a0, "adj_nosc"), (n0, "node_nosc")):
+        want = torch.from_numpy(g[key])
+        rel = (got - want).norm() / want.norm()
+        assert rel < 2e-6, (key, float(rel))
+    assert float(torch.from_numpy(g["adj_sc"]).abs().mean()) > 1e-2   # stress init makes the output visible
+
+
+def test_precond_matches_reference(golden_dir):
+    cfg = CONFIGS["tiny"]
+    g = np.load(os.path.join(golden_dir, "precond_tiny.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    adj, node, flags, _, _, _ = synthetic_inputs(cfg, 3, seed=7)
+    coins = iter(g["coins"])
+    sa = sn = None
+    with torch.no_grad():
+        for k, s in enumerate((40.0, 3.0, 0.4, 0.01)):
+            sa, sn = O.precond_forward(_net(cfg, sd), adj * s, node * s, flags, torch.full((3,), s), sa, sn,
+                                       coin=lambda: next(coins))
+            for got, key in ((sa, f"adj_{k}"), (sn, f"node_{k}")):
+                want = torch.from_numpy(g[key])
+                assert (got - want).norm() / want.norm() < 2e-6, key
+
+
+def test_sampler_matches_reference(golden_dir):
+    cfg = CONFIGS["tiny"]
+    g = np.load(os.path.join(golden_dir, "sampler_tiny.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, 3, seed=7)
+    flags = flags[:2]
+    np.testing.assert_array_equal(E.t_steps_fp32(8).numpy(), g["t_steps"])
+    np.testing.assert_array_equal(E.sigma_grid(256).numpy(), g["sigma_steps_256"])
+
+    def model(a, n, f, sig, sa, sn):
+        return O.precond_forward(_net(cfg, sd), a, n, f, sig, sa, sn, coin=np.random.rand)
+
+    torch.manual_seed(11)
+    np.random.seed(11)
+    trace = []
+    with torch.no_grad():
+        a, n = E.sample(model, flags, cfg["c_e"], cfg["c_n"], num_steps=8, trace=trace)
+    assert (a - torch.from_numpy(g["adjs"])).abs().max() < 2e-4
+    assert (n - torch.from_numpy(g["nodes"])).abs().max() < 2e-4
+    # interim snapshots of the reference: init + steps linspace(0, 8, 4).astype(int).clip(max=7) = 0, 2, 5, 7
+    for slot, step in zip(range(1, 5), (0, 2, 5, 7)):
+        assert (trace[step][1] - torch.from_numpy(g["nodes_ls"][slot])).abs().max() < 2e-4
+
+
+def test_sampler_known_answer(golden_dir):
+    """The reference's own KAT (sanity_check_gt_*): the last Euler step returns the ground truth."""
+    g = np.load(os.path.join(golden_dir, "sampler_tiny.npz"))
+    cfg = CONFIGS["tiny"]
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, 3, seed=7)
+    gt = (torch.from_numpy(g["kat_gt_adjs"]), torch.from_numpy(g["kat_gt_nodes"]))
+    torch.manual_seed(12)
+    a, n = E.sample(None, flags[:2], cfg["c_e"], cfg["c_n"], num_steps=8, gt=gt)
+    np.testing.assert_array_equal(a.numpy(), g["kat_adjs"])
+    np.testing.assert_array_equal(n.numpy(), g["kat_nodes"])
+    assert (a - gt[0]).abs().max() < 1e-6 and (n - gt[1]).abs().max() < 1e-6
