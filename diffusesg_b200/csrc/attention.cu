@@ -1,0 +1,244 @@
+// Shifted-window multi-head self-attention over the N x N pair grid (head_dim = 32).
+//
+// One CTA per (sample, window, head).  The cyclic shift, window partition and window reverse of the
+// reference (model/diffusesg/diffusesg.py:246-271, :28-57) never touch memory: they are index arithmetic
+// on the token gather/scatter of this kernel.  softmax(q k^T + rel_pos_bias[h] (+ shift mask[window])) v
+// restates WindowAttention.forward (:108-139); q arrives pre-scaled (the 32^-0.5 factor is folded into the
+// packed qkv weights).  Scores, softmax statistics and the output accumulator are fp32; q/k/v/p are bf16
+// tensor-core operands (warp-level mma.sync m16n8k16: each warp owns a 16-query slab; the window tile is
+// far below the 128-row tcgen05 atom).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+constexpr int HD = 32;        // head dim
+constexpr int QK_PITCH = 40;  // bf16 per q/k smem row (80 B: conflict-free fragment loads)
+
+template <int T_PAD>
+__global__ void __launch_bounds__((T_PAD / 16) * 32)
+window_attention_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
+                        bf16* __restrict__ out, int res, int w, int shift, int heads) {
+  constexpr int NWARP = T_PAD / 16;
+  constexpr int VT_PITCH = T_PAD + 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(att_smem);
+  bf16* sK = sQ + T_PAD * QK_PITCH;
+  bf16* sVt = sK + T_PAD * QK_PITCH;
+  int* sRow = reinterpret_cast<int*>(sVt + HD * VT_PITCH);
+
+  const int T = w * w;
+  const int nwx = res / w;
+  const int nW = nwx * nwx;
+  int bid = blockIdx.x;
+  const int h = bid % heads; bid /= heads;
+  const int win = bid % nW;
+  const int b = bid / nW;
+  const int wy = win / nwx, wx = win % nwx;
+  const int C = heads * HD;
+  const int tid = threadIdx.x;
+
+  for (int t = tid; t < T_PAD; t += NWARP * 32) {
+    int row = -1;
+    if (t < T) {
+      const int ty = t / w, tx = t - ty * w;
+      int oy = wy * w + ty + shift; if (oy >= res) oy -= res;
+      int ox = wx * w + tx + shift; if (ox >= res) ox -= res;
+      row = (b * res + oy) * res + ox;
+    }
+    sRow[t] = row;
+  }
+  __syncthreads();
+
+  // gather q, k (row-major) and v (transposed) for this head; padded tokens are zero
+  for (int idx = tid; idx < T_PAD * 12; idx += NWARP * 32) {
+    const int t = idx / 12;
+    const int rem = idx - t * 12;
+    const int part = rem >> 2, chunk = rem & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int row = sRow[t];
+    if (row >= 0)
+      v = __ldg(reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(row) * (3 * C) + part * C + h * HD + chunk * 8));
+    if (part == 0) {
+      *reinterpret_cast<uint4*>(&sQ[t * QK_PITCH + chunk * 8]) = v;
+    } else if (part == 1) {
+      *reinterpret_cast<uint4*>(&sK[t * QK_PITCH + chunk * 8]) = v;
+    } else {
+      const bf16* e = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sVt[(chunk * 8 + i) * VT_PITCH + t] = e[i];
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int r0 = warp * 16 + g;  // this thread's two query rows: r0 and r0 + 8
+  const int r1 = r0 + 8;
+
+  uint32_t qa[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    qa[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4]);
+    qa[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4]);
+    qa[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+    qa[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+  }
+
+  const float* bias_h = bias + static_cast<size_t>(h) * T * T;
+  const float* mask_w = mask ? mask + static_cast<size_t>(win) * T * T : nullptr;
+  const bool ok0 = r0 < T, ok1 = r1 < T;
+
+  float o[4][4];
+#pragma unroll
+  for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+#pragma unroll
+  for (int kc = 0; kc < T_PAD; kc += 64) {
+    constexpr int NT_MAX = 8;
+    float s[NT_MAX][4];
+#pragma unroll
+    for (int nt = 0; nt < NT_MAX; ++nt) {
+      if (kc + nt * 8 < T_PAD) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const int key = kc + nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t kb[2];
+          kb[0] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4]);
+          kb[1] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+          mma_m16n8k16_bf16(s[nt], qa[ks], kb);
+        }
+        const int c = kc + nt * 8 + 2 * t4;  // columns c, c + 1 (T is even, so both are valid or both padded)
+        if (c < T) {
+          if (ok0) {
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(bias_h + static_cast<size_t>(r0) * T + c));
+            s[nt][0] += bv.x; s[nt][1] += bv.y;
+            if (mask_w) {
+              const float2 mv = __ldg(reinterpret_cast<const float2*>(mask_w + static_cast<size_t>(r0) * T + c));
+              s[nt][0] += mv.x; s[nt][1] += mv.y;
+            }
+          }
+          if (ok1) {
+            const float2 bv = __ldg(reinterpret_cast<const float2*>(bias_h + static_cast<size_t>(r1) * T + c));
+            s[nt][2] += bv.x; s[nt][3] += bv.y;
+            if (mask_w) {
+              const float2 mv = __ldg(reinterpret_cast<const float2*>(mask_w + static_cast<size_t>(r1) * T + c));
+              s[nt][2] += mv.x; s[nt][3] += mv.y;
+            }
+          }
+        } else {
+          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
+        }
+      }
+    }
+    // online softmax over this chunk of keys
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT_MAX; ++nt) {
+      if (kc + nt * 8 < T_PAD) {
+        cm0 = fmaxf(cm0, fmaxf(s[nt][0], s[nt][1]));
+        cm1 = fmaxf(cm1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1));
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);  // finite: every chunk holds >= 1 real key
+    const float f0 = __expf(m0 - nm0), f1 = __expf(m1 - nm1);
+    m0 = nm0; m1 = nm1;
+    l0 *= f0; l1 *= f1;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      o[nd][0] *= f0; o[nd][1] *= f0; o[nd][2] *= f1; o[nd][3] *= f1;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT_MAX; ++nt) {
+      if (kc + nt * 8 < T_PAD) {
+        s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+        s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+    }
+    // o += p . v  (p: bf16 A fragments straight from the score registers)
+#pragma unroll
+    for (int kt = 0; kt < NT_MAX / 2; ++kt) {
+      if (kc + kt * 16 < T_PAD) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
+        pa[1] = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
+        pa[2] = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+        const int key = kc + kt * 16 + 2 * t4;
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd) {
+          uint32_t vb[2];
+          vb[0] = *reinterpret_cast<const uint32_t*>(&sVt[(nd * 8 + g) * VT_PITCH + key]);
+          vb[1] = *reinterpret_cast<const uint32_t*>(&sVt[(nd * 8 + g) * VT_PITCH + key + 8]);
+          mma_m16n8k16_bf16(o[nd], pa, vb);
+        }
+      }
+    }
+  }
+
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (ok0) {
+    bf16* dst = out + static_cast<size_t>(sRow[r0]) * C + h * HD + 2 * t4;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd)
+      *reinterpret_cast<uint32_t*>(dst + nd * 8) = pack_bf16x2(o[nd][0] * i0, o[nd][1] * i0);
+  }
+  if (ok1) {
+    bf16* dst = out + static_cast<size_t>(sRow[r1]) * C + h * HD + 2 * t4;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd)
+      *reinterpret_cast<uint32_t*>(dst + nd * 8) = pack_bf16x2(o[nd][2] * i1, o[nd][3] * i1);
+  }
+}
+
+template <int T_PAD>
+int launch_t(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res, int window,
+             int shift, int heads, cudaStream_t st) {
+  const int nW = (res / window) * (res / window);
+  const long long grid = static_cast<long long>(batch) * nW * heads;
+  DSG_REQUIRE(grid > 0 && grid < 2147483647LL, "attention: grid out of range");
+  constexpr int smem = (2 * T_PAD * QK_PITCH + HD * (T_PAD + 8)) * 2 + T_PAD * 4;
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel<T_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  window_attention_kernel<T_PAD><<<static_cast<unsigned>(grid), (T_PAD / 16) * 32, smem, st>>>(qkv, bias, mask, out, res,
+                                                                                            window, shift, heads);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+}  // namespace
+
+int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
+                            int window, int shift, int heads, cudaStream_t st) {
+  DSG_REQUIRE(res % window == 0 && shift >= 0 && shift < window, "attention: res %d window %d shift %d", res, window,
+              shift);
+  DSG_REQUIRE((shift > 0) == (mask != nullptr), "attention: a shifted block needs its mask (and only it)");
+  const int T = window * window;
+  DSG_REQUIRE(T % 2 == 0, "attention: odd window token count %d", T);
+  if (T <= 16) return launch_t<16>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
+  if (T <= 64) return launch_t<64>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
+  if (T <= 112) return launch_t<112>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
+  if (T <= 256) return launch_t<256>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
+  set_last_error("attention: windows of %d tokens are not supported (max 256)", T);
+  return DSG_ERR_INVALID;
+}
+
+}  // namespace dsg

@@ -1,0 +1,140 @@
+// Fused elementwise kernels of the EDM stochastic-Heun sampler (runner/mcmc_sampler/edm.py:350-434 of the
+// reference; ~113 ATen launches per step there, two here).
+//
+// State layout: adj [B, C_e, N, N] and node [B, N, C_n], fp32, exactly the reference's tensors.  Pure
+// HBM-bound streaming: 128-bit loads/stores over the adjacency tensor (N % 4 == 0), grid-stride with a grid
+// that is a multiple of the SM count.  Arithmetic is written with explicit round-to-nearest intrinsics in
+// the reference's operation order (no FMA contraction) so that, given the same inputs, the results are
+// bit-identical to the fp32 torch expressions:
+//
+//   pre :  x_hat  = mask(x + c * eps)                      c = sqrt(t_hat^2 - t_cur^2) * S_noise     (:361-366)
+//   post:  k      = mask(inv_t * x_hat - inv_t * D1)                                                  (:384-387)
+//          x'     = x_hat + h * k                                                                    (:389-390)
+//          x_next = mask(x_hat + h * (0.5 k + 0.5 (inv_tp * x' - inv_tp * D2)))     (Heun, :414-422)
+//          x_next = mask(x')                                                        (last step, :395-396)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+struct EdmShape {
+  int batch, c_e, n, c_n;
+};
+
+DSG_DEVICE float pre_one(float x, float e, float c) { return __fadd_rn(x, __fmul_rn(c, e)); }
+
+DSG_DEVICE float post_one(float xh, float d1, float d2, float inv_t, float h, float inv_tp, bool heun) {
+  const float k = __fsub_rn(__fmul_rn(inv_t, xh), __fmul_rn(inv_t, d1));
+  const float xp = __fadd_rn(xh, __fmul_rn(h, k));
+  if (!heun) return xp;
+  const float kp = __fsub_rn(__fmul_rn(inv_tp, xp), __fmul_rn(inv_tp, d2));
+  return __fadd_rn(xh, __fmul_rn(h, __fadd_rn(__fmul_rn(0.5f, k), __fmul_rn(0.5f, kp))));
+}
+
+// MODE 0: pre-step, 1: post-step (heun), 2: post-step (euler / last), 3: x = mask(x * scale)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+edm_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ a2,
+           float* __restrict__ a_out, const float* __restrict__ n0, const float* __restrict__ n1,
+           const float* __restrict__ n2, float* __restrict__ n_out, const uint8_t* __restrict__ flags, float s0,
+           float s1, float s2, EdmShape sh) {
+  const int n = sh.n, n4 = sh.n >> 2;
+  const long long adj_vec = static_cast<long long>(sh.batch) * sh.c_e * n * n4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (long long v = tid; v < adj_vec; v += stride) {
+    const int j4 = static_cast<int>(v % n4);
+    const long long r = v / n4;
+    const int i = static_cast<int>(r % n);
+    const int b = static_cast<int>(r / (static_cast<long long>(n) * sh.c_e));
+    const uint8_t* f = flags + static_cast<size_t>(b) * n;
+    const bool fi = f[i] != 0;
+    const uchar4 fj = *reinterpret_cast<const uchar4*>(f + 4 * j4);
+    float4 x = reinterpret_cast<const float4*>(a0)[v];
+    float4 o;
+    if (MODE == 0) {
+      const float4 e = reinterpret_cast<const float4*>(a1)[v];
+      o = make_float4(pre_one(x.x, e.x, s0), pre_one(x.y, e.y, s0), pre_one(x.z, e.z, s0), pre_one(x.w, e.w, s0));
+    } else if (MODE == 1 || MODE == 2) {
+      const float4 d1 = reinterpret_cast<const float4*>(a1)[v];
+      float4 d2 = d1;
+      if (MODE == 1) d2 = reinterpret_cast<const float4*>(a2)[v];
+      o = make_float4(post_one(x.x, d1.x, d2.x, s0, s1, s2, MODE == 1), post_one(x.y, d1.y, d2.y, s0, s1, s2, MODE == 1),
+                      post_one(x.z, d1.z, d2.z, s0, s1, s2, MODE == 1), post_one(x.w, d1.w, d2.w, s0, s1, s2, MODE == 1));
+    } else {
+      o = make_float4(__fmul_rn(x.x, s0), __fmul_rn(x.y, s0), __fmul_rn(x.z, s0), __fmul_rn(x.w, s0));
+    }
+    o.x = (fi && fj.x) ? o.x : 0.f;
+    o.y = (fi && fj.y) ? o.y : 0.f;
+    o.z = (fi && fj.z) ? o.z : 0.f;
+    o.w = (fi && fj.w) ? o.w : 0.f;
+    reinterpret_cast<float4*>(a_out)[v] = o;
+  }
+  const long long node_el = static_cast<long long>(sh.batch) * n * sh.c_n;
+  for (long long v = tid; v < node_el; v += stride) {
+    const long long bi = v / sh.c_n;
+    const bool ok = flags[bi] != 0;
+    const float x = n0[v];
+    float o;
+    if (MODE == 0) {
+      o = pre_one(x, n1[v], s0);
+    } else if (MODE == 1) {
+      o = post_one(x, n1[v], n2[v], s0, s1, s2, true);
+    } else if (MODE == 2) {
+      o = post_one(x, n1[v], 0.f, s0, s1, s2, false);
+    } else {
+      o = __fmul_rn(x, s0);
+    }
+    n_out[v] = ok ? o : 0.f;
+  }
+}
+
+template <int MODE>
+int launch_mode(const float* a0, const float* a1, const float* a2, float* a_out, const float* n0, const float* n1,
+                const float* n2, float* n_out, const uint8_t* flags, float s0, float s1, float s2, int batch, int c_e,
+                int n, int c_n, cudaStream_t st) {
+  DSG_REQUIRE(batch > 0 && c_e > 0 && n > 0 && c_n > 0 && n % 4 == 0, "edm step: bad shape B=%d C_e=%d N=%d C_n=%d",
+              batch, c_e, n, c_n);
+  DSG_REQUIRE(((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(a_out) | reinterpret_cast<uintptr_t>(a1) |
+                reinterpret_cast<uintptr_t>(a2)) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0,
+              "edm step: adjacency tensors must be 16-byte aligned (flags 4-byte)");
+  const long long vec = static_cast<long long>(batch) * c_e * n * (n / 4);
+  long long blocks = (vec + 255) / 256;
+  const long long cap = 148LL * 8;  // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  EdmShape sh{batch, c_e, n, c_n};
+  edm_kernel<MODE><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a0, a1, a2, a_out, n0, n1, n2, n_out, flags, s0, s1,
+                                                                  s2, sh);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+}  // namespace
+
+int launch_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
+                        const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch, int c_e,
+                        int n, int c_n, cudaStream_t st) {
+  return launch_mode<0>(adj, eps_adj, nullptr, adj_hat, node, eps_node, nullptr, node_hat, flags, noise_coef, 0.f, 0.f,
+                        batch, c_e, n, c_n, st);
+}
+
+int launch_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                         const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat, float h,
+                         float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e, int n, int c_n,
+                         cudaStream_t st) {
+  if (d2_adj != nullptr)
+    return launch_mode<1>(adj_hat, d1_adj, d2_adj, adj_next, node_hat, d1_node, d2_node, node_next, flags, inv_t_hat, h,
+                          inv_t_prime, batch, c_e, n, c_n, st);
+  return launch_mode<2>(adj_hat, d1_adj, nullptr, adj_next, node_hat, d1_node, nullptr, node_next, flags, inv_t_hat, h,
+                        0.f, batch, c_e, n, c_n, st);
+}
+
+int launch_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
+                      float* node_out, int batch, int c_e, int n, int c_n, cudaStream_t st) {
+  return launch_mode<3>(adj, nullptr, nullptr, adj_out, node, nullptr, nullptr, node_out, flags, scale, 0.f, 0.f, batch,
+                        c_e, n, c_n, st);
+}
+
+}  // namespace dsg

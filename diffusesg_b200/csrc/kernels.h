@@ -1,0 +1,135 @@
+// Host-side launchers of every kernel in libdsg_b200.so (internal header).
+//
+// Conventions: all pointers are device pointers unless stated; "tokens" are the pixels of the
+// N x N node-pair grid flattened row-major (token = i * res + j) and batched sample-major, so an
+// activation is a row-major [B*L, C] matrix with the channel contiguous.  Launchers never allocate
+// and never synchronise; they return 0 or a DSG_ERR_* code (see common.cuh).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dsg {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM:  out[M, N] = epilogue(A[M, K] . W[N, K]^T)          (gemm.cu)
+// ---------------------------------------------------------------------------------------------
+enum GemmEpi : int {
+  EPI_BF16 = 0,       // out bf16 = acc + bias
+  EPI_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
+  EPI_RES_F32 = 2,    // out f32  = acc + bias + res            (res may alias out)
+  EPI_F32 = 3,        // out f32  = acc + bias
+  EPI_ADJ_HEAD = 4,   // h = gelu(acc + bias) [N == 96]; y = W2 h + b2; masked (+ EDM precond) -> [B, Ce, n, n]
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;   // [N] or nullptr
+  const float* res;    // [M, ldo] fp32 (EPI_RES_F32)
+  void* out;           // [M, ldo] bf16 / fp32; EPI_ADJ_HEAD: float [B, c_e, n, n]
+  int ldo;
+  // EPI_ADJ_HEAD only
+  const float* w2t;    // [96][8]: second layer of the adj read-out MLP, transposed and zero padded
+  const float* b2;     // [8]
+  int c_e;             // real output channels (<= 8)
+  int n_img;           // N; a GEMM row m is pixel (b, i, j) = (m / N^2, (m / N) % N, m % N)
+  const uint8_t* flags;  // [B, N] node validity
+  const float* x_adj;    // preconditioning: D = c_skip * x + c_out * F; nullptr -> raw F
+  const float* c_skip;   // [B]
+  const float* c_out;    // [B]
+};
+
+// Encode a TMA descriptor for a row-major bf16 matrix [rows, cols] (cols contiguous), box = 64 cols x
+// box_rows rows, 128-byte swizzle.  Pure host work (driver entry point), no stream interaction.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows);
+
+// N must be a multiple of 96; K a multiple of 32; rows beyond M are neither read as valid nor written.
+// box_rows of the W descriptor must equal gemm_block_n(N).
+int gemm_block_n(int N);
+int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, int epi, const GemmParams& p, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// shifted-window attention                                             (attention.cu)
+// ---------------------------------------------------------------------------------------------
+// qkv [B*res*res, 3*C] bf16 (q pre-scaled through the packed weights), layout per token [3][heads][32];
+// bias [heads, T, T] fp32 = gathered relative-position bias; mask [nW, T, T] fp32 (0 / -100) for shifted blocks,
+// nullptr otherwise; out [B*res*res, C] bf16 at the un-shifted token positions.
+int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
+                            int window, int shift, int heads, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// row kernels: LayerNorm / FiLM / merge / breakup / embed / heads       (rowops.cu)
+// ---------------------------------------------------------------------------------------------
+// x_out = silu(shift_b + x_in * (1 + scale_b)); y = LN(x_out) * g + b  (bf16).  film [n_cond, film_ld]
+// holds (scale[C], shift[C]) at column film_off; sample s uses row (cond_uniform ? 0 : s).
+int launch_film_ln(const float* x_in, float* x_out, bf16* y, const float* film, int film_ld, int film_off,
+                   int cond_uniform, const float* gamma, const float* beta, int batch, int tokens_per_sample,
+                   int C, cudaStream_t st);
+int launch_ln(const float* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, cudaStream_t st);
+// PatchMerging front half: gather the 2x2 neighbourhood (order (0,0),(1,0),(0,1),(1,1)), LN(4C) -> bf16
+int launch_merge_ln(const float* x, bf16* y, const float* gamma, const float* beta, int batch, int res, int C,
+                    cudaStream_t st);
+// PatchBreakup input: y[m, 0:C] = bf16(x[m]), y[m, C:2C] = bf16(skip[m])
+int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st);
+// PatchBreakup middle: LN(D) over each row of t [B*res*res, D], split into 4 chunks of D/4, chunk k goes to
+// pixel (2y + k%2, 2x + k/2) of the 2res x 2res grid, LN(D/4) -> bf16 [B*4*res*res, D/4]
+int launch_breakup_ln(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
+                      int batch, int res, int D, cudaStream_t st);
+
+// sigma conditioning: noise_labels [n_cond] -> emb [n_cond, 512] -> film [n_cond, film_total]
+// scratch: emb0 [n_cond, embed], emb1 [n_cond, 512], emb [n_cond, 512]
+int launch_cond(const float* noise_labels, long long label_stride, int n_cond, const float* w0, const float* b0, const float* w1,
+                const float* b1, const float* w_film, const float* b_film, int film_total, float* emb0, float* emb1,
+                float* emb, float* film, int embed, cudaStream_t st);
+
+// per-sample EDM coefficients from sigma: coef[0..3][B] = c_in, c_skip, c_out, c_noise
+int launch_precond_coef(const float* sigmas, int sigma_stride, float* coef, int batch, cudaStream_t st);
+
+// node row/col projections of the patch embedding: rc[b, i, 0:E] = W_row . nodecat[b, i], rc[b, i, E:2E] = W_col . nodecat
+int launch_node_proj(const float* node, const float* sc_node, const float* in_scale, const float* w_rc,
+                     float* rc, int batch, int n, int c_n, int self_cond, int embed, cudaStream_t st);
+// patch embed + LN + FiLM-SiLU -> x0 [B*n*n, E] fp32
+int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_scale, const uint8_t* flags,
+                       const float* rc, const float* w_adj, const float* bias, const float* gamma,
+                       const float* beta, const float* film, int film_ld, int film_off, int cond_uniform,
+                       float* x0, int batch, int n, int c_e, int self_cond, int embed, cudaStream_t st);
+// node head: masked row mean of rep [B*n*n, E] bf16 -> MLP -> (precond) -> out_node [B, n, c_n]
+// w1t [E][E] and w2t [E][c_n] are the transposed nn.Linear weights (input-channel major)
+int launch_node_head(const bf16* rep, const uint8_t* flags, const float* w1t, const float* b1, const float* w2t,
+                     const float* b2, const float* x_node, const float* c_skip, const float* c_out,
+                     float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// fused EDM step kernels                                               (edm.cu)
+// ---------------------------------------------------------------------------------------------
+int launch_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
+                        const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch,
+                        int c_e, int n, int c_n, cudaStream_t st);
+int launch_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                         const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat,
+                         float h, float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e,
+                         int n, int c_n, cudaStream_t st);
+int launch_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
+                      float* node_out, int batch, int c_e, int n, int c_n, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// weight packing helpers (run once per weight update)                  (pack.cu)
+// ---------------------------------------------------------------------------------------------
+// dst bf16 = src * (i < n_scaled ? scale : 1)
+int launch_pack_bf16(const float* src, bf16* dst, int64_t numel, int64_t n_scaled, float scale, cudaStream_t st);
+int launch_scale_copy(const float* src, float* dst, int64_t numel, int64_t n_scaled, float scale, cudaStream_t st);
+// dst[c * dst_pitch + r] = src[r * ld + col0 + c], r < R, c < ncols   (dst is NOT cleared)
+int launch_transpose(const float* src, float* dst, int R, int ld, int col0, int ncols, int dst_pitch, cudaStream_t st);
+// out[h, p, q] = table[index[p, q], h]                              (diffusesg.py:121-124)
+int launch_bias_expand(const float* table, const int64_t* index, float* out, int T, int heads, int table_rows,
+                       cudaStream_t st);
+// C[o][i] = sum_k A[o][k] * (trans_b ? B[i][k] : B[k][i]), n x n fp32
+int launch_small_mm(const float* A, const float* B, float* C, int n, int trans_b, cudaStream_t st);
+// y = A x + b
+int launch_small_mv(const float* A, const float* x, const float* b, float* y, int n, cudaStream_t st);
+
+}  // namespace dsg

@@ -1,0 +1,668 @@
+// dsg_model: configuration, weight arena, packing and the kernel schedule of one denoiser forward.
+//
+// The schedule restates DiffuseSG.forward / forward_features (model/diffusesg/diffusesg.py:739-830 of the
+// reference) as ~110 launches of the kernels in gemm.cu / attention.cu / rowops.cu on one stream.  All shapes
+// are static per (model, batch), so the whole forward is CUDA-graph capturable (no host sync, no allocation).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/dsg_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+
+// ------------------------------------------------------------------------------------------------
+// error / launch bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static unsigned long long g_launches = 0;
+static int g_stop_after = -1;  // test hook: leave the forward schedule after this many stages (-1: run all)
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct TensorSpec {
+  std::string key;
+  int64_t numel = 0;
+  int dtype = 0;  // 0 fp32, 1 int64
+  size_t offset = 0;
+  bool loaded = false;
+  size_t bytes() const { return static_cast<size_t>(numel) * (dtype == 1 ? 8 : 4); }
+};
+
+struct Weight {       // packed bf16 [N, K] + its TMA descriptor
+  size_t offset = 0;  // into the arena
+  int N = 0, K = 0;
+  CUtensorMap tmap;
+};
+
+struct Block {
+  std::string prefix;
+  int dim, res, heads, window, shift, stage;
+  int film_off;        // column of (scale, shift) in the film row
+  Weight qkv, proj, fc1, fc2;
+  size_t qkv_bias_off;  // fp32 [3C], q part pre-scaled
+  size_t attn_bias_off; // fp32 [heads, T, T]
+};
+
+struct Merge { std::string prefix; int C, res; Weight reduction; };
+struct Breakup { std::string prefix; int D, res; Weight pre, post; };
+
+}  // namespace
+}  // namespace dsg
+
+using namespace dsg;
+
+struct dsg_model {
+  dsg_config cfg;
+  int nl, N, E;
+  int planes_adj, planes_node, cin;
+  std::vector<TensorSpec> tensors;           // state_dict order
+  std::map<std::string, int> index;          // key -> tensors[]
+  std::vector<Block> blocks;                 // execution order
+  std::vector<int> down_first, up_first;     // index of the first block of each down / up layer
+  std::vector<Merge> merges;                 // after down layer s (s < nl - 1)
+  std::vector<Breakup> breakups;             // before up layer u (u >= 1), index u - 1
+  int film_total = 0;
+  size_t film_w_off = 0, film_b_off = 0;     // contiguous [film_total, 512] and [film_total]
+  // packed extras
+  size_t w_adj_off = 0, w_rc_off = 0, fold_t1_off = 0, fold_f_off = 0, fold_b_off = 0, fold_tv_off = 0;
+  size_t adj_w2t_off = 0, adj_b2_off = 0, node_w1t_off = 0, node_w2t_off = 0;
+  Weight fold_w, adj_fc1;
+  size_t arena_bytes = 0;
+  uint8_t* arena = nullptr;
+  bool finalized = false;
+  std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
+
+  const float* f32(const std::string& key) const {
+    return reinterpret_cast<const float*>(arena + tensors[index.at(key)].offset);
+  }
+  template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(arena + off); }
+};
+
+namespace {
+
+void add_tensor(dsg_model* m, const std::string& key, int64_t numel, int dtype = 0) {
+  TensorSpec t;
+  t.key = key;
+  t.numel = numel;
+  t.dtype = dtype;
+  m->index[key] = static_cast<int>(m->tensors.size());
+  m->tensors.push_back(t);
+}
+void add_linear(dsg_model* m, const std::string& p, int out, int in, bool bias = true) {
+  add_tensor(m, p + ".weight", static_cast<int64_t>(out) * in);
+  if (bias) add_tensor(m, p + ".bias", out);
+}
+void add_ln(dsg_model* m, const std::string& p, int c) {
+  add_tensor(m, p + ".weight", c);
+  add_tensor(m, p + ".bias", c);
+}
+
+// Registration order of the reference module tree (model/diffusesg/diffusesg.py:611-720; blocks :158-230).
+void add_block(dsg_model* m, const std::string& p, int dim, int res, int heads, int j, int stage) {
+  const int window = m->cfg.window_size;
+  Block b;
+  b.prefix = p;
+  b.dim = dim; b.res = res; b.heads = heads; b.stage = stage;
+  if (res <= window) { b.window = res; b.shift = 0; }              // :189-192
+  else { b.window = window; b.shift = (j % 2 == 0) ? 0 : window / 2; }  // :459
+  const int T = b.window * b.window;
+  if (b.shift > 0) {
+    const int nw = (res / b.window) * (res / b.window);
+    add_tensor(m, p + ".attn_mask", static_cast<int64_t>(nw) * T * T);
+  }
+  add_linear(m, p + ".affine", 2 * dim, 512);
+  add_ln(m, p + ".norm1", dim);
+  add_tensor(m, p + ".attn.relative_position_bias_table",
+             static_cast<int64_t>(2 * b.window - 1) * (2 * b.window - 1) * heads);
+  add_tensor(m, p + ".attn.relative_position_index", static_cast<int64_t>(T) * T, 1);
+  add_linear(m, p + ".attn.qkv", 3 * dim, dim);
+  add_linear(m, p + ".attn.proj", dim, dim);
+  add_ln(m, p + ".norm2", dim);
+  add_linear(m, p + ".mlp.fc1", 4 * dim, dim);
+  add_linear(m, p + ".mlp.fc2", dim, 4 * dim);
+  m->blocks.push_back(b);
+}
+
+size_t reserve(size_t& cursor, size_t bytes) {
+  const size_t off = cursor;
+  cursor = align_up(cursor + bytes);
+  return off;
+}
+
+void reserve_weight(size_t& cursor, Weight& w, int N, int K) {
+  w.N = N; w.K = K;
+  w.offset = reserve(cursor, static_cast<size_t>(N) * K * 2);
+}
+
+int build(dsg_model* m) {
+  const dsg_config& c = m->cfg;
+  DSG_REQUIRE(c.num_stages >= 1 && c.num_stages <= 4, "config: num_stages %d", c.num_stages);
+  DSG_REQUIRE(c.embed_dim == 96, "config: embed_dim %d (this build supports 96)", c.embed_dim);
+  DSG_REQUIRE(c.c_e >= 1 && c.c_e <= 8 && c.c_n >= 1 && c.c_n <= 64, "config: c_e %d c_n %d", c.c_e, c.c_n);
+  DSG_REQUIRE(c.img_size > 0 && c.img_size % (1 << (c.num_stages - 1)) == 0 && c.img_size % 4 == 0,
+              "config: img_size %d is not divisible by the %d-stage pyramid (and by 4)", c.img_size, c.num_stages);
+  m->nl = c.num_stages; m->N = c.img_size; m->E = c.embed_dim;
+  const int sc = c.self_condition ? 2 : 1;
+  m->planes_adj = c.c_e * sc;
+  m->planes_node = c.c_n * sc;
+  m->cin = m->planes_adj + 2 * m->planes_node;
+  for (int s = 0; s < m->nl; ++s) {
+    const int dim = m->E << s, res = m->N >> s;
+    DSG_REQUIRE(c.depths[s] >= 1, "config: depth of stage %d", s);
+    DSG_REQUIRE(c.num_heads[s] * 32 == dim, "config: stage %d needs %d heads of 32 channels", s, dim / 32);
+    const int w = res <= c.window_size ? res : c.window_size;
+    DSG_REQUIRE(res % w == 0 && (w * w) % 2 == 0 && w * w <= 256, "config: window %d on a %d-grid", w, res);
+  }
+  // ---- state_dict enumeration ------------------------------------------------------------------
+  add_linear(m, "patch_embed.affine", 2 * m->E, 512);
+  add_tensor(m, "patch_embed.proj.weight", static_cast<int64_t>(m->E) * m->cin);
+  add_tensor(m, "patch_embed.proj.bias", m->E);
+  add_ln(m, "patch_embed.norm", m->E);
+  char buf[128];
+  for (int s = 0; s < m->nl; ++s) {
+    const int dim = m->E << s, res = m->N >> s;
+    m->down_first.push_back(static_cast<int>(m->blocks.size()));
+    for (int j = 0; j < c.depths[s]; ++j) {
+      snprintf(buf, sizeof(buf), "down_layers.%d.blocks.%d", s, j);
+      add_block(m, buf, dim, res, c.num_heads[s], j, s);
+    }
+    if (s < m->nl - 1) {
+      snprintf(buf, sizeof(buf), "down_layers.%d.downsample", s);
+      Merge mg; mg.prefix = buf; mg.C = dim; mg.res = res;
+      add_linear(m, mg.prefix + ".reduction", 2 * dim, 4 * dim, false);
+      add_ln(m, mg.prefix + ".norm", 4 * dim);
+      m->merges.push_back(mg);
+    }
+  }
+  for (int u = 0; u < m->nl; ++u) {
+    const int s = m->nl - 1 - u;
+    const int dim = m->E << s, res = m->N >> s;
+    if (u > 0) {
+      snprintf(buf, sizeof(buf), "up_layers.%d.upsample", u);
+      Breakup bu; bu.prefix = buf; bu.D = 4 * dim; bu.res = res / 2;
+      add_linear(m, bu.prefix + ".pre_linear", bu.D, bu.D, false);
+      add_ln(m, bu.prefix + ".norm", bu.D);
+      add_linear(m, bu.prefix + ".post_linear", bu.D / 4, bu.D / 4, false);
+      add_ln(m, bu.prefix + ".post_norm", bu.D / 4);
+      m->breakups.push_back(bu);
+    }
+    m->up_first.push_back(static_cast<int>(m->blocks.size()));
+    for (int j = 0; j < c.depths[s]; ++j) {
+      snprintf(buf, sizeof(buf), "up_layers.%d.blocks.%d", u, j);
+      add_block(m, buf, dim, res, c.num_heads[s], j, s);
+    }
+  }
+  for (int k = 0; k < 3; ++k) {
+    snprintf(buf, sizeof(buf), "read_out.%d", k);
+    add_linear(m, buf, m->E, m->E);
+  }
+  add_linear(m, "map_layer0", 512, m->E);
+  add_linear(m, "map_layer1", 512, 512);
+  add_ln(m, "norm", m->E);
+  add_linear(m, "readout_adj_mlp.fc1", m->E, m->E);
+  add_linear(m, "readout_adj_mlp.fc2", c.c_e, m->E);
+  add_linear(m, "readout_node_mlp.fc1", m->E, m->E);
+  add_linear(m, "readout_node_mlp.fc2", c.c_n, m->E);
+
+  // ---- arena layout ------------------------------------------------------------------------------
+  size_t cur = 0;
+  // all FiLM generators back to back: one [film_total, 512] matrix, one [film_total] bias
+  std::vector<std::string> film_keys;
+  film_keys.push_back("patch_embed.affine");
+  for (const Block& b : m->blocks) film_keys.push_back(b.prefix + ".affine");
+  m->film_w_off = cur;
+  int off = 0;
+  for (size_t i = 0; i < film_keys.size(); ++i) {
+    TensorSpec& t = m->tensors[m->index[film_keys[i] + ".weight"]];
+    t.offset = cur;
+    cur += t.bytes();
+    if (i > 0) m->blocks[i - 1].film_off = off;
+    off += static_cast<int>(t.numel / 512);
+  }
+  m->film_total = off;
+  cur = align_up(cur);
+  m->film_b_off = cur;
+  for (const std::string& k : film_keys) {
+    TensorSpec& t = m->tensors[m->index[k + ".bias"]];
+    t.offset = cur;
+    cur += t.bytes();
+  }
+  cur = align_up(cur);
+  for (TensorSpec& t : m->tensors) {
+    if (t.key.size() > 7 && t.key.find(".affine.") != std::string::npos) continue;
+    t.offset = reserve(cur, t.bytes());
+  }
+  // packed forms
+  for (Block& b : m->blocks) {
+    const int C = b.dim, T = b.window * b.window;
+    reserve_weight(cur, b.qkv, 3 * C, C);
+    reserve_weight(cur, b.proj, C, C);
+    reserve_weight(cur, b.fc1, 4 * C, C);
+    reserve_weight(cur, b.fc2, C, 4 * C);
+    b.qkv_bias_off = reserve(cur, static_cast<size_t>(3 * C) * 4);
+    b.attn_bias_off = reserve(cur, static_cast<size_t>(b.heads) * T * T * 4);
+  }
+  for (Merge& g : m->merges) reserve_weight(cur, g.reduction, 2 * g.C, 4 * g.C);
+  for (Breakup& u : m->breakups) {
+    reserve_weight(cur, u.pre, u.D, u.D);
+    reserve_weight(cur, u.post, u.D / 4, u.D / 4);
+  }
+  const int E = m->E;
+  m->w_adj_off = reserve(cur, static_cast<size_t>(m->planes_adj) * E * 4);
+  m->w_rc_off = reserve(cur, static_cast<size_t>(2) * m->planes_node * E * 4);
+  m->fold_t1_off = reserve(cur, static_cast<size_t>(E) * E * 4);
+  m->fold_f_off = reserve(cur, static_cast<size_t>(E) * E * 4);
+  m->fold_b_off = reserve(cur, static_cast<size_t>(E) * 4);
+  m->fold_tv_off = reserve(cur, static_cast<size_t>(E) * 4);
+  reserve_weight(cur, m->fold_w, E, E);
+  reserve_weight(cur, m->adj_fc1, E, E);
+  m->adj_w2t_off = reserve(cur, static_cast<size_t>(E) * 8 * 4);
+  m->adj_b2_off = reserve(cur, 8 * 4);
+  m->node_w1t_off = reserve(cur, static_cast<size_t>(E) * E * 4);
+  m->node_w2t_off = reserve(cur, static_cast<size_t>(E) * c.c_n * 4);
+  m->arena_bytes = cur;
+  return DSG_OK;
+}
+
+int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st, int64_t n_scaled = 0,
+                float scale = 1.f) {
+  int rc = launch_pack_bf16(m->f32(key), m->at<bf16>(w.offset), static_cast<int64_t>(w.N) * w.K, n_scaled, scale, st);
+  if (rc) return rc;
+  return make_tmap_bf16(&w.tmap, m->arena + w.offset, w.N, w.K, gemm_block_n(w.N));
+}
+
+struct Workspace {
+  float *X, *T, *coef, *emb0, *emb1, *emb, *film, *rc;
+  std::vector<float*> skip;
+  bf16 *Y, *QKV, *ATT, *H, *REP;
+  size_t bytes;
+};
+
+Workspace carve(const dsg_model* m, int batch, int n_cond, void* base) {
+  Workspace w;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t cur = 0;
+  const size_t tok0 = static_cast<size_t>(batch) * m->N * m->N;
+  const size_t full = tok0 * m->E;  // elements of a stage-0 activation; later stages hold full / 2^s
+  auto take = [&](size_t bytes) { void* r = p ? p + cur : nullptr; cur = align_up(cur + bytes); return r; };
+  w.X = static_cast<float*>(take(full * 4));
+  w.T = static_cast<float*>(take(full * 4));
+  w.Y = static_cast<bf16*>(take(full * 2));
+  w.QKV = static_cast<bf16*>(take(full * 3 * 2));
+  w.ATT = static_cast<bf16*>(take(full * 2));
+  w.H = static_cast<bf16*>(take(full * 4 * 2));
+  w.REP = static_cast<bf16*>(take(full * 2));
+  for (int s = 0; s + 1 < m->nl; ++s) w.skip.push_back(static_cast<float*>(take((full >> (s + 1)) * 4)));
+  w.coef = static_cast<float*>(take(static_cast<size_t>(4) * batch * 4));
+  w.emb0 = static_cast<float*>(take(static_cast<size_t>(n_cond) * m->E * 4));
+  w.emb1 = static_cast<float*>(take(static_cast<size_t>(n_cond) * 512 * 4));
+  w.emb = static_cast<float*>(take(static_cast<size_t>(n_cond) * 512 * 4));
+  w.film = static_cast<float*>(take(static_cast<size_t>(n_cond) * m->film_total * 4));
+  w.rc = static_cast<float*>(take(static_cast<size_t>(batch) * m->N * 2 * m->E * 4));
+  w.bytes = cur;
+  return w;
+}
+
+int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, const float* bias, const float* res,
+         void* out, cudaStream_t st, const GemmParams* extra = nullptr) {
+  DSG_REQUIRE(rows > 0 && rows < 2147483647LL, "gemm: %lld rows", rows);
+  auto key = std::make_tuple(static_cast<const void*>(A), rows, W.K);
+  auto it = m->a_maps.find(key);
+  if (it == m->a_maps.end()) {
+    CUtensorMap tm;
+    int rc = make_tmap_bf16(&tm, A, rows, W.K, 128);
+    if (rc) return rc;
+    if (m->a_maps.size() > 4096) m->a_maps.clear();
+    it = m->a_maps.emplace(key, tm).first;
+  }
+  GemmParams p;
+  if (extra) p = *extra; else memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(rows); p.N = W.N; p.K = W.K;
+  p.bias = bias; p.res = res; p.out = out; p.ldo = W.N;
+  return launch_gemm(&it->second, &W.tmap, epi, p, st);
+}
+
+#define DSG_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
+              cudaStream_t st) {
+  const int C = b.dim;
+  const int L = b.res * b.res;
+  const long long rows = static_cast<long long>(batch) * L;
+  const std::string& p = b.prefix;
+  // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
+  DSG_TRY(launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform, m->f32(p + ".norm1.weight"),
+                         m->f32(p + ".norm1.bias"), batch, L, C, st));
+  DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
+  const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
+  DSG_TRY(launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
+                                  b.heads, st));
+  // x = x + proj(attn)                                                   (:137, :272)
+  DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
+  // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
+  DSG_TRY(launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
+  DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));
+  DSG_TRY(gemm(m, w.H, rows, b.fc2, EPI_RES_F32, m->f32(p + ".mlp.fc2.bias"), w.X, w.X, st));
+  return DSG_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int dsg_abi_version(void) { return DSG_ABI_VERSION; }
+const char* dsg_last_error(void) { return g_err; }
+uint64_t dsg_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
+  DSG_REQUIRE(cfg != nullptr && out != nullptr, "dsg_model_create: null argument");
+  dsg_model* m = new dsg_model();
+  m->cfg = *cfg;
+  const int rc = build(m);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return DSG_OK;
+}
+
+void dsg_model_destroy(dsg_model* m) { delete m; }
+
+size_t dsg_model_arena_bytes(const dsg_model* m) { return m ? m->arena_bytes : 0; }
+
+int dsg_model_bind_arena(dsg_model* m, void* arena, size_t bytes) {
+  DSG_REQUIRE(m != nullptr && arena != nullptr, "bind_arena: null argument");
+  if (bytes < m->arena_bytes || (reinterpret_cast<uintptr_t>(arena) & (kAlign - 1)) != 0) {
+    set_last_error("bind_arena: need %zu bytes aligned to %zu, got %zu at %p", m->arena_bytes, kAlign, bytes, arena);
+    return DSG_ERR_WORKSPACE;
+  }
+  m->arena = static_cast<uint8_t*>(arena);
+  m->finalized = false;
+  for (TensorSpec& t : m->tensors) t.loaded = false;
+  return DSG_OK;
+}
+
+int dsg_model_num_tensors(const dsg_model* m) { return m ? static_cast<int>(m->tensors.size()) : 0; }
+
+int dsg_model_tensor_info(const dsg_model* m, int i, const char** key, int64_t* numel, int32_t* dtype) {
+  DSG_REQUIRE(m != nullptr && i >= 0 && i < static_cast<int>(m->tensors.size()), "tensor_info: index %d", i);
+  if (key) *key = m->tensors[i].key.c_str();
+  if (numel) *numel = m->tensors[i].numel;
+  if (dtype) *dtype = m->tensors[i].dtype;
+  return DSG_OK;
+}
+
+int dsg_model_set_tensor(dsg_model* m, const char* key, const void* src, int64_t bytes, int src_is_host,
+                         dsg_stream_t stream) {
+  DSG_REQUIRE(m != nullptr && key != nullptr && src != nullptr, "set_tensor: null argument");
+  if (m->arena == nullptr) { set_last_error("set_tensor: no arena bound"); return DSG_ERR_STATE; }
+  auto it = m->index.find(key);
+  if (it == m->index.end()) { set_last_error("set_tensor: unknown key '%s'", key); return DSG_ERR_UNKNOWN_KEY; }
+  TensorSpec& t = m->tensors[it->second];
+  DSG_REQUIRE(static_cast<size_t>(bytes) == t.bytes(), "set_tensor: '%s' expects %zu bytes, got %lld", key, t.bytes(),
+              static_cast<long long>(bytes));
+  DSG_CUDA_CHECK(cudaMemcpyAsync(m->arena + t.offset, src, t.bytes(),
+                                 src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+  t.loaded = true;
+  m->finalized = false;
+  return DSG_OK;
+}
+
+int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
+  DSG_REQUIRE(m != nullptr, "finalize: null model");
+  if (m->arena == nullptr) { set_last_error("finalize: no arena bound"); return DSG_ERR_STATE; }
+  for (const TensorSpec& t : m->tensors)
+    if (!t.loaded) { set_last_error("finalize: tensor '%s' was never set", t.key.c_str()); return DSG_ERR_STATE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float qscale = 0.17677669529663687f;  // head_dim ** -0.5 with head_dim = 32 (diffusesg.py:76, :118)
+  for (Block& b : m->blocks) {
+    const int C = b.dim, T = b.window * b.window;
+    const std::string& p = b.prefix;
+    DSG_TRY(pack_weight(m, b.qkv, p + ".attn.qkv.weight", st, static_cast<int64_t>(C) * C, qscale));
+    DSG_TRY(launch_scale_copy(m->f32(p + ".attn.qkv.bias"), m->at<float>(b.qkv_bias_off), 3 * C, C, qscale, st));
+    DSG_TRY(pack_weight(m, b.proj, p + ".attn.proj.weight", st));
+    DSG_TRY(pack_weight(m, b.fc1, p + ".mlp.fc1.weight", st));
+    DSG_TRY(pack_weight(m, b.fc2, p + ".mlp.fc2.weight", st));
+    const TensorSpec& idx = m->tensors[m->index[p + ".attn.relative_position_index"]];
+    DSG_TRY(launch_bias_expand(m->f32(p + ".attn.relative_position_bias_table"),
+                               reinterpret_cast<const int64_t*>(m->arena + idx.offset), m->at<float>(b.attn_bias_off), T,
+                               b.heads, (2 * b.window - 1) * (2 * b.window - 1), st));
+  }
+  for (Merge& g : m->merges) DSG_TRY(pack_weight(m, g.reduction, g.prefix + ".reduction.weight", st));
+  for (Breakup& u : m->breakups) {
+    DSG_TRY(pack_weight(m, u.pre, u.prefix + ".pre_linear.weight", st));
+    DSG_TRY(pack_weight(m, u.post, u.prefix + ".post_linear.weight", st));
+  }
+  const int E = m->E;
+  // patch embedding: split the 1x1 conv into its adjacency and node row / column parts, input-channel major
+  const float* wp = m->f32("patch_embed.proj.weight");  // [E, cin]
+  DSG_TRY(launch_transpose(wp, m->at<float>(m->w_adj_off), E, m->cin, 0, m->planes_adj, E, st));
+  DSG_TRY(launch_transpose(wp, m->at<float>(m->w_rc_off), E, m->cin, m->planes_adj, m->planes_node, E, st));
+  DSG_TRY(launch_transpose(wp, m->at<float>(m->w_rc_off) + static_cast<size_t>(m->planes_node) * E, E, m->cin,
+                           m->planes_adj + m->planes_node, m->planes_node, E, st));
+  // read_out = ConvTranspose2d(1x1) -> Conv2d(1x1) -> Conv2d(1x1) with no activation between (:705-709): one
+  // 96x96 map.  ConvTranspose2d stores its weight as [in, out].
+  float* t1 = m->at<float>(m->fold_t1_off);
+  float* ff = m->at<float>(m->fold_f_off);
+  float* tv = m->at<float>(m->fold_tv_off);
+  DSG_TRY(launch_small_mm(m->f32("read_out.1.weight"), m->f32("read_out.0.weight"), t1, E, 1, st));
+  DSG_TRY(launch_small_mm(m->f32("read_out.2.weight"), t1, ff, E, 0, st));
+  DSG_TRY(launch_small_mv(m->f32("read_out.1.weight"), m->f32("read_out.0.bias"), m->f32("read_out.1.bias"), tv, E, st));
+  DSG_TRY(launch_small_mv(m->f32("read_out.2.weight"), tv, m->f32("read_out.2.bias"), m->at<float>(m->fold_b_off), E, st));
+  DSG_TRY(launch_pack_bf16(ff, m->at<bf16>(m->fold_w.offset), static_cast<int64_t>(E) * E, 0, 1.f, st));
+  DSG_TRY(make_tmap_bf16(&m->fold_w.tmap, m->arena + m->fold_w.offset, E, E, gemm_block_n(E)));
+  // heads
+  DSG_TRY(pack_weight(m, m->adj_fc1, "readout_adj_mlp.fc1.weight", st));
+  DSG_CUDA_CHECK(cudaMemsetAsync(m->at<float>(m->adj_w2t_off), 0, static_cast<size_t>(E) * 8 * 4, st));
+  DSG_CUDA_CHECK(cudaMemsetAsync(m->at<float>(m->adj_b2_off), 0, 8 * 4, st));
+  DSG_TRY(launch_transpose(m->f32("readout_adj_mlp.fc2.weight"), m->at<float>(m->adj_w2t_off), m->cfg.c_e, E, 0, E, 8, st));
+  DSG_CUDA_CHECK(cudaMemcpyAsync(m->at<float>(m->adj_b2_off), m->f32("readout_adj_mlp.fc2.bias"), m->cfg.c_e * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+  DSG_TRY(launch_transpose(m->f32("readout_node_mlp.fc1.weight"), m->at<float>(m->node_w1t_off), E, E, 0, E, E, st));
+  DSG_TRY(launch_transpose(m->f32("readout_node_mlp.fc2.weight"), m->at<float>(m->node_w2t_off), m->cfg.c_n, E, 0, E,
+                           m->cfg.c_n, st));
+  m->finalized = true;
+  return DSG_OK;
+}
+
+size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond) {
+  if (m == nullptr || batch <= 0 || n_cond <= 0) return 0;
+  return carve(m, batch, n_cond, nullptr).bytes;
+}
+
+int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t stream) {
+  DSG_REQUIRE(m != nullptr && a != nullptr, "forward: null argument");
+  DSG_REQUIRE(a->struct_size == sizeof(dsg_forward_args), "forward: dsg_forward_args size %u, library expects %zu",
+              a->struct_size, sizeof(dsg_forward_args));
+  if (!m->finalized) { set_last_error("forward: dsg_model_finalize has not been called since the last weight update"); return DSG_ERR_STATE; }
+  DSG_REQUIRE(a->batch > 0 && (a->n_cond == 1 || a->n_cond == a->batch), "forward: batch %d n_cond %d", a->batch, a->n_cond);
+  DSG_REQUIRE(a->mode == 0 || a->mode == 1, "forward: mode %d", a->mode);
+  DSG_REQUIRE(a->adj && a->node && a->flags && a->noise && a->out_adj && a->out_node, "forward: null tensor");
+  DSG_REQUIRE((reinterpret_cast<uintptr_t>(a->flags) & 3) == 0, "forward: node_flags must be 4-byte aligned");
+  DSG_REQUIRE(static_cast<long long>(a->batch) * m->N * m->N < 2147483647LL, "forward: batch %d too large", a->batch);
+  const int B = a->batch, N = m->N, E = m->E;
+  Workspace w = carve(m, B, a->n_cond, a->workspace);
+  if (a->workspace == nullptr || a->workspace_bytes < w.bytes ||
+      (reinterpret_cast<uintptr_t>(a->workspace) & (kAlign - 1)) != 0) {
+    set_last_error("forward: workspace needs %zu bytes aligned to %zu (got %zu at %p)", w.bytes, kAlign,
+                   a->workspace_bytes, a->workspace);
+    return DSG_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int uniform = a->n_cond == 1 ? 1 : 0;
+  const float *c_in = nullptr, *c_skip = nullptr, *c_out = nullptr;
+  const float* labels = a->noise;
+  long long label_stride = a->noise_stride;
+  if (a->mode == 1) {
+    // coefficients for every sample (a shared sigma is broadcast), c_noise doubles as the noise labels
+    DSG_TRY(launch_precond_coef(a->noise, uniform ? 0 : static_cast<int>(a->noise_stride), w.coef, B, st));
+    c_in = w.coef; c_skip = w.coef + B; c_out = w.coef + 2 * B;
+    labels = w.coef + 3 * B;
+    label_stride = 1;
+  }
+  DSG_TRY(launch_cond(labels, label_stride, a->n_cond, m->f32("map_layer0.weight"),
+                      m->f32("map_layer0.bias"), m->f32("map_layer1.weight"), m->f32("map_layer1.bias"),
+                      m->at<float>(m->film_w_off), m->at<float>(m->film_b_off), m->film_total, w.emb0, w.emb1, w.emb,
+                      w.film, E, st));
+  // patch embedding straight from (adj, node): the [B, cin, N, N] grid of :784-802 is never built
+  DSG_TRY(launch_node_proj(a->node, a->sc_node, c_in, m->at<float>(m->w_rc_off), w.rc, B, N, m->cfg.c_n,
+                           m->cfg.self_condition, E, st));
+  DSG_TRY(launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
+                             m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
+                             m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
+                             m->cfg.self_condition, E, st));
+  int stage_no = 0;
+#define DSG_STAGE_DONE() do { if (g_stop_after >= 0 && stage_no++ == g_stop_after) return DSG_OK; } while (0)
+  DSG_STAGE_DONE();
+  // encoder                                                                  (:746-748)
+  for (int s = 0; s < m->nl; ++s) {
+    const float* x_in = s == 0 ? w.X : w.skip[s - 1];
+    for (int j = 0; j < m->cfg.depths[s]; ++j) {
+      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st));
+      x_in = w.X;
+      DSG_STAGE_DONE();
+    }
+    if (s < m->nl - 1) {
+      const Merge& g = m->merges[s];
+      const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
+      DSG_TRY(launch_merge_ln(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), B, g.res, g.C, st));
+      DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
+      DSG_STAGE_DONE();
+    }
+  }
+  // decoder                                                                  (:751-756)
+  for (int u = 0; u < m->nl; ++u) {
+    const int s = m->nl - 1 - u;
+    // u == 0 continues on the last encoder stage's output: X for a multi-block stage, or the merge output
+    const float* x_in = w.X;
+    if (u > 0) {
+      const Breakup& bu = m->breakups[u - 1];
+      const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
+      // the low-resolution stream lives in X unless no block ran since the last merge (cannot happen: depth >= 1)
+      DSG_TRY(launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+      DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
+      DSG_TRY(launch_breakup_ln(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"), B, bu.res,
+                                bu.D, st));
+      DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
+      DSG_STAGE_DONE();
+    }
+    for (int j = 0; j < m->cfg.depths[s]; ++j) {
+      DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st));
+      DSG_STAGE_DONE();
+    }
+  }
+  // read-out                                                                 (:758-761, :806-825)
+  const long long pixels = static_cast<long long>(B) * N * N;
+  DSG_TRY(launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
+  DSG_TRY(gemm(m, w.Y, pixels, m->fold_w, EPI_BF16, m->at<float>(m->fold_b_off), nullptr, w.REP, st));
+  GemmParams hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.w2t = m->at<float>(m->adj_w2t_off);
+  hp.b2 = m->at<float>(m->adj_b2_off);
+  hp.c_e = m->cfg.c_e;
+  hp.n_img = N;
+  hp.flags = a->flags;
+  hp.x_adj = a->mode == 1 ? a->adj : nullptr;
+  hp.c_skip = c_skip;
+  hp.c_out = c_out;
+  DSG_TRY(gemm(m, w.REP, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->f32("readout_adj_mlp.fc1.bias"), nullptr, a->out_adj, st, &hp));
+  DSG_TRY(launch_node_head(w.REP, a->flags, m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
+                           m->at<float>(m->node_w2t_off), m->f32("readout_node_mlp.fc2.bias"),
+                           a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st));
+  return DSG_OK;
+}
+
+void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
+
+int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name, size_t* offset, size_t* bytes) {
+  DSG_REQUIRE(m && name && offset && bytes && batch > 0 && n_cond > 0, "debug_buffer: bad argument");
+  uint8_t* base = reinterpret_cast<uint8_t*>(kAlign);  // fake non-null base: only offsets are wanted
+  Workspace w = carve(m, batch, n_cond, base);
+  const size_t full = static_cast<size_t>(batch) * m->N * m->N * m->E;
+  struct { const char* n; const void* p; size_t b; } tab[] = {
+      {"X", w.X, full * 4}, {"T", w.T, full * 4}, {"Y", w.Y, full * 2}, {"QKV", w.QKV, full * 6},
+      {"ATT", w.ATT, full * 2}, {"H", w.H, full * 8}, {"REP", w.REP, full * 2},
+      {"skip0", w.skip.size() > 0 ? w.skip[0] : nullptr, full * 2}, {"skip1", w.skip.size() > 1 ? w.skip[1] : nullptr, full},
+      {"skip2", w.skip.size() > 2 ? w.skip[2] : nullptr, full / 2}, {"coef", w.coef, static_cast<size_t>(16) * batch},
+      {"emb", w.emb, static_cast<size_t>(n_cond) * 2048}, {"film", w.film, static_cast<size_t>(n_cond) * m->film_total * 4},
+      {"rc", w.rc, static_cast<size_t>(batch) * m->N * 2 * m->E * 4}};
+  for (auto& t : tab)
+    if (strcmp(t.n, name) == 0 && t.p != nullptr) {
+      *offset = static_cast<size_t>(static_cast<const uint8_t*>(t.p) - base);
+      *bytes = t.b;
+      return DSG_OK;
+    }
+  set_last_error("debug_buffer: no buffer named '%s'", name);
+  return DSG_ERR_INVALID;
+}
+
+int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
+                     const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch, int c_e, int n,
+                     int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && eps_adj && eps_node && flags && adj_hat && node_hat, "edm_pre_step: null tensor");
+  return launch_edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef, adj_hat, node_hat, batch, c_e, n, c_n,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                      const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat, float h,
+                      float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e, int n, int c_n,
+                      dsg_stream_t stream) {
+  DSG_REQUIRE(adj_hat && node_hat && d1_adj && d1_node && flags && adj_next && node_next, "edm_post_step: null tensor");
+  DSG_REQUIRE((d2_adj == nullptr) == (d2_node == nullptr), "edm_post_step: d2_adj / d2_node must both be given or both NULL");
+  return launch_edm_post_step(adj_hat, node_hat, d1_adj, d1_node, d2_adj, d2_node, flags, inv_t_hat, h, inv_t_prime,
+                              adj_next, node_next, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
+                       float* node_out, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && flags && adj_out && node_out, "edm_mask_scale: null tensor");
+  return launch_mask_scale(adj, node, flags, scale, adj_out, node_out, batch, c_e, n, c_n,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
+                  int epi, dsg_stream_t stream) {
+  DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");
+  CUtensorMap ta, tw;
+  DSG_TRY(make_tmap_bf16(&ta, a, M, K, 128));
+  DSG_TRY(make_tmap_bf16(&tw, w, N, K, gemm_block_n(N)));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N;
+  return launch_gemm(&ta, &tw, epi, p, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,
+                         int shift, int heads, dsg_stream_t stream) {
+  DSG_REQUIRE(qkv && bias && out, "window_attention: null tensor");
+  return launch_window_attention(static_cast<const bf16*>(qkv), bias, mask, static_cast<bf16*>(out), batch, res, window,
+                                 shift, heads, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

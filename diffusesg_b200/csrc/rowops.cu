@@ -1,0 +1,546 @@
+// Row kernels of the denoiser: everything that is not a GEMM or attention.
+//
+// HBM-bound by construction: each kernel reads its fp32 rows once with 128-bit loads (one warp per row, the
+// whole row in registers), does LayerNorm / FiLM / gather / scatter in registers and writes once.  The
+// window / merge / breakup reshuffles of the reference (model/diffusesg/diffusesg.py:28-57, :314-335, :374-403)
+// are index arithmetic on the row addresses of these kernels; the 60-channel input grid (:784-802) is never
+// materialised.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+constexpr int kRowThreads = 256;  // 8 rows per CTA
+constexpr float kLnEps = 1e-5f;   // nn.LayerNorm default (diffusesg.py:175 etc.)
+
+DSG_DEVICE uint2 pack4_bf16(float a, float b, float c, float d) { return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d)); }
+
+// A row of C fp32 values spread over a warp: float4 number (lane + 32 i) lives in v[i].
+template <int NV>
+struct Row {
+  float4 v[NV];
+  DSG_DEVICE void load(const float* p, int C, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = (lane + 32 * i) * 4;
+      v[i] = (e < C) ? *reinterpret_cast<const float4*>(p + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  DSG_DEVICE void store(float* p, int C, int lane) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = (lane + 32 * i) * 4;
+      if (e < C) *reinterpret_cast<float4*>(p + e) = v[i];
+    }
+  }
+  // (x - mean) * rstd over the C valid entries, in place
+  DSG_DEVICE void normalize(int C, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = (lane + 32 * i) * 4;
+      if (e < C) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd; }
+  }
+  DSG_DEVICE void affine(const float* g, const float* b, int C, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = (lane + 32 * i) * 4;
+      if (e < C) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + e));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + e));
+        v[i].x = fmaf(v[i].x, gg.x, bb.x); v[i].y = fmaf(v[i].y, gg.y, bb.y);
+        v[i].z = fmaf(v[i].z, gg.z, bb.z); v[i].w = fmaf(v[i].w, gg.w, bb.w);
+      }
+    }
+  }
+  DSG_DEVICE void store_bf16(bf16* p, int C, int lane) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = (lane + 32 * i) * 4;
+      if (e < C) *reinterpret_cast<uint2*>(p + e) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// FiLM + SiLU (+ shortcut write) + LayerNorm            (SwinTransformerBlock.forward :238-243)
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+film_ln_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, bf16* __restrict__ y,
+               const float* __restrict__ film, int film_ld, int cond_uniform, const float* __restrict__ gamma,
+               const float* __restrict__ beta, long long rows, int tokens_per_sample, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = cond_uniform ? 0 : static_cast<int>(row / tokens_per_sample);
+  const float* sc = film + static_cast<size_t>(b) * film_ld;  // scale[C] then shift[C]
+  Row<NV> r;
+  r.load(x_in + row * C, C, lane);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    if (e < C) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(sc + e));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(sc + C + e));
+      r.v[i].x = silu_f(fmaf(r.v[i].x, s.x + 1.f, t.x));
+      r.v[i].y = silu_f(fmaf(r.v[i].y, s.y + 1.f, t.y));
+      r.v[i].z = silu_f(fmaf(r.v[i].z, s.z + 1.f, t.z));
+      r.v[i].w = silu_f(fmaf(r.v[i].w, s.w + 1.f, t.w));
+    }
+  }
+  r.store(x_out + row * C, C, lane);
+  r.normalize(C, lane);
+  r.affine(gamma, beta, C, lane);
+  r.store_bf16(y + row * C, C, lane);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+ln_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+          const float* __restrict__ beta, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  Row<NV> r;
+  r.load(x + row * C, C, lane);
+  r.normalize(C, lane);
+  r.affine(gamma, beta, C, lane);
+  r.store_bf16(y + row * C, C, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PatchMerging front half: 2x2 gather + LN(4C)                                   (:314-333)
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+merge_ln_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, long long rows_out, int res, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows_out) return;
+  const int half = res >> 1;
+  const int ox = static_cast<int>(row % half);
+  const int oy = static_cast<int>((row / half) % half);
+  const long long b = row / (static_cast<long long>(half) * half);
+  const int C4 = 4 * C;
+  Row<NV> r;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < C4) {
+      const int q = e / C, c = e - q * C;  // channel block q holds pixel (2y + q % 2, 2x + q / 2)
+      const long long src = (b * res + (2 * oy + (q & 1))) * res + (2 * ox + (q >> 1));
+      r.v[i] = *reinterpret_cast<const float4*>(x + src * C + c);
+    }
+  }
+  r.normalize(C4, lane);
+  r.affine(gamma, beta, C4, lane);
+  r.store_bf16(y + row * C4, C4, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PatchBreakup middle: LN(D) -> depth-to-space -> LN(D/4)                          (:386-400)
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+breakup_ln_kernel(const float* __restrict__ t, bf16* __restrict__ y, const float* __restrict__ g1,
+                  const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
+                  long long rows_in, int res, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows_in) return;
+  const int ix = static_cast<int>(row % res);
+  const int iy = static_cast<int>((row / res) % res);
+  const long long b = row / (static_cast<long long>(res) * res);
+  const int Dq = D >> 2;
+  Row<NV> r;
+  r.load(t + row * D, D, lane);
+  r.normalize(D, lane);
+  r.affine(g1, b1, D, lane);
+  // per-chunk LayerNorm: chunk k = elements [k Dq, (k + 1) Dq)
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    if (e < D) {
+      const int k = e / Dq;
+      const float a = (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) s[kk] += (k == kk) ? a : 0.f;
+    }
+  }
+  float mean[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) mean[kk] = warp_sum(s[kk]) / Dq;
+  float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    if (e < D) {
+      const int k = e / Dq;
+      const float m = (k == 0) ? mean[0] : (k == 1) ? mean[1] : (k == 2) ? mean[2] : mean[3];
+      r.v[i].x -= m; r.v[i].y -= m; r.v[i].z -= m; r.v[i].w -= m;
+      const float a = (r.v[i].x * r.v[i].x + r.v[i].y * r.v[i].y) + (r.v[i].z * r.v[i].z + r.v[i].w * r.v[i].w);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) q[kk] += (k == kk) ? a : 0.f;
+    }
+  }
+  float rstd[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) rstd[kk] = rsqrtf(warp_sum(q[kk]) / Dq + kLnEps);
+  const int res2 = 2 * res;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    if (e < D) {
+      const int k = e / Dq, c = e - k * Dq;
+      const float rs = (k == 0) ? rstd[0] : (k == 1) ? rstd[1] : (k == 2) ? rstd[2] : rstd[3];
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g2 + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c));
+      // chunk k lands on pixel (2y + k % 2, 2x + k / 2) of the up-sampled grid
+      const long long dst = (b * res2 + (2 * iy + (k & 1))) * res2 + (2 * ix + (k >> 1));
+      *reinterpret_cast<uint2*>(y + dst * Dq + c) =
+          pack4_bf16(fmaf(r.v[i].x * rs, gg.x, bb.x), fmaf(r.v[i].y * rs, gg.y, bb.y),
+                     fmaf(r.v[i].z * rs, gg.z, bb.z), fmaf(r.v[i].w * rs, gg.w, bb.w));
+    }
+  }
+}
+
+// y[m] = bf16([x[m], skip[m]])                                                    (:753 torch.cat)
+__global__ void __launch_bounds__(256)
+concat_bf16_kernel(const float* __restrict__ x, const float* __restrict__ skip, bf16* __restrict__ y, long long rows,
+                   int C) {
+  const int c4 = C >> 2;
+  const long long total = rows * 2 * c4;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx / (2 * c4);
+    const int e = static_cast<int>(idx - row * (2 * c4));
+    const float* src = (e < c4) ? x + row * C + e * 4 : skip + row * C + (e - c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src);
+    *reinterpret_cast<uint2*>(y + row * (2 * C) + e * 4) = pack4_bf16(v.x, v.y, v.z, v.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sigma conditioning                                                   (:507-513, :768-771, affine layers)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ labels, long long label_stride, float* __restrict__ e0,
+                                int n_cond, int embed) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = embed >> 1;
+  if (idx >= n_cond * half) return;
+  const int r = idx / half, k = idx - r * half;
+  const float f = powf(1.0f / 10000.0f, static_cast<float>(k) / static_cast<float>(half));
+  const float a = labels[r * label_stride] * f;
+  e0[r * embed + k] = cosf(a);
+  e0[r * embed + half + k] = sinf(a);
+}
+
+// y[r, o] = act(W[o, :] . x[r, :] + b[o]); one warp per output
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                    float* __restrict__ y, int n, int K, int O, int act_silu) {
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= static_cast<long long>(n) * O) return;
+  const int r = static_cast<int>(wid / O), o = static_cast<int>(wid - static_cast<long long>(r) * O);
+  const float* xr = x + static_cast<size_t>(r) * K;
+  const float* wr = W + static_cast<size_t>(o) * K;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(__ldg(wr + k), xr[k], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += bias ? bias[o] : 0.f;
+    y[static_cast<size_t>(r) * O + o] = act_silu ? silu_f(s) : s;
+  }
+}
+
+// coef[0..3][n] = c_in, c_skip, c_out, c_noise                    (runner/objectives/edm.py:122-126, sigma_data 0.5)
+__global__ void precond_coef_kernel(const float* __restrict__ sigmas, int sigma_stride, float* __restrict__ coef,
+                                    int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = sigmas[static_cast<size_t>(i) * sigma_stride];
+  const float s2 = __fadd_rn(__fmul_rn(s, s), 0.25f);
+  coef[i] = __fdiv_rn(1.0f, __fsqrt_rn(s2));
+  coef[n + i] = __fdiv_rn(0.25f, s2);
+  coef[2 * n + i] = __fdiv_rn(__fmul_rn(s, 0.5f), __fsqrt_rn(s2));
+  coef[3 * n + i] = __fdiv_rn(logf(s), 4.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// patch embedding without the 60-channel grid                                   (:784-802, :569-577)
+// ---------------------------------------------------------------------------------------------------------
+// rc[b, i, 0:E]  = sum_c W[:, row-plane c] * nodecat[b, i, c]      nodecat = [self-cond node, c_in * node]
+// rc[b, i, E:2E] = sum_c W[:, col-plane c] * nodecat[b, i, c]
+// w_rc is [2, 2 c_n(self_cond) or c_n, E] (input-channel major so that lanes read consecutive e).
+__global__ void node_proj_kernel(const float* __restrict__ node, const float* __restrict__ sc_node,
+                                 const float* __restrict__ in_scale, const float* __restrict__ w_rc,
+                                 float* __restrict__ rc, int batch, int n, int c_n, int self_cond, int embed) {
+  const int bi = blockIdx.x;  // (b, i)
+  const int b = bi / n;
+  const int e2 = threadIdx.x;  // 0 .. 2E-1
+  if (e2 >= 2 * embed) return;
+  const int which = e2 / embed, e = e2 - which * embed;
+  const int cin = self_cond ? 2 * c_n : c_n;
+  const float sc = in_scale ? in_scale[b] : 1.f;
+  const float* w = w_rc + static_cast<size_t>(which) * cin * embed + e;
+  float acc = 0.f;
+  int ch = 0;
+  if (self_cond) {
+    for (int c = 0; c < c_n; ++c, ++ch) {
+      const float v = sc_node ? sc_node[static_cast<size_t>(bi) * c_n + c] : 0.f;
+      acc = fmaf(w[ch * embed], v, acc);
+    }
+  }
+  for (int c = 0; c < c_n; ++c, ++ch) {
+    const float v = __fmul_rn(sc, node[static_cast<size_t>(bi) * c_n + c]);
+    acc = fmaf(w[ch * embed], v, acc);
+  }
+  rc[static_cast<size_t>(bi) * 2 * embed + e2] = acc;
+}
+
+// One warp per pixel (b, i, j); lane l owns channels l, l + 32, l + 64 of the 96-wide embedding.
+// x0 = silu(shift + LN(conv1x1(input)) * (1 + scale))
+template <int EPL>  // embed / 32
+__global__ void __launch_bounds__(kRowThreads)
+patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_adj, const float* __restrict__ in_scale,
+                   const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
+                   const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ film, int film_ld, int cond_uniform, float* __restrict__ x0,
+                   long long pixels, int n, int c_e, int self_cond) {
+  constexpr int E = EPL * 32;
+  const int lane = threadIdx.x & 31;
+  const long long pix = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (pix >= pixels) return;
+  const int nn = n * n;
+  const int b = static_cast<int>(pix / nn);
+  const int ij = static_cast<int>(pix - static_cast<long long>(b) * nn);
+  const int i = ij / n, j = ij - i * n;
+  const bool pair_ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+  const float sc = in_scale ? in_scale[b] : 1.f;
+  float v[EPL];
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) v[k] = bias[lane + 32 * k];
+  // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]; w_adj is [planes, E]
+  int ch = 0;
+  if (self_cond) {
+    for (int c = 0; c < c_e; ++c, ++ch) {
+      const float a = sc_adj ? sc_adj[(static_cast<size_t>(b) * c_e + c) * nn + ij] : 0.f;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) v[k] = fmaf(w_adj[ch * E + lane + 32 * k], a, v[k]);
+    }
+  }
+  for (int c = 0; c < c_e; ++c, ++ch) {
+    const float a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) v[k] = fmaf(w_adj[ch * E + lane + 32 * k], a, v[k]);
+  }
+  if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)
+    const float* rrow = rc + (static_cast<size_t>(b) * n + i) * 2 * E;
+    const float* rcol = rc + (static_cast<size_t>(b) * n + j) * 2 * E + E;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) v[k] += rrow[lane + 32 * k] + rcol[lane + 32 * k];
+  }
+  // LayerNorm(E)
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) s += v[k];
+  const float mean = warp_sum(s) / E;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) { v[k] -= mean; q += v[k] * v[k]; }
+  const float rstd = rsqrtf(warp_sum(q) / E + kLnEps);
+  const float* fs = film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int e = lane + 32 * k;
+    const float y = fmaf(v[k] * rstd, gamma[e], beta[e]);
+    x0[pix * E + e] = silu_f(fmaf(y, fs[e] + 1.f, fs[E + e]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// node read-out: masked row mean -> MLP -> mask (-> EDM output preconditioning)   (:812-822, precond.py:103-105)
+// ---------------------------------------------------------------------------------------------------------
+// One CTA (128 threads) per (b, i).  rep is the shared representation [B n n, E] (bf16).
+__global__ void __launch_bounds__(128)
+node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags, const float* __restrict__ w1t,
+                 const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                 const float* __restrict__ x_node, const float* __restrict__ c_skip, const float* __restrict__ c_out,
+                 float* __restrict__ out_node, int n, int c_n, int embed) {
+  __shared__ float pooled[128];
+  __shared__ float hidden[128];
+  const int bi = blockIdx.x;
+  const int b = bi / n;
+  const int e = threadIdx.x;
+  const bool row_ok = flags[bi] != 0;
+  if (!row_ok) {  // masked node: output row is zero regardless of the features
+    if (e < c_n) out_node[static_cast<size_t>(bi) * c_n + e] = 0.f;
+    return;
+  }
+  if (e < embed) {
+    const bf16* p = rep + static_cast<size_t>(bi) * n * embed + e;
+    float s = 0.f;
+    for (int j = 0; j < n; ++j)
+      if (flags[b * n + j]) s += __bfloat162float(p[static_cast<size_t>(j) * embed]);
+    pooled[e] = s / n;  // mean over the full row length N, not over the valid count (:813)
+  }
+  __syncthreads();
+  if (e < embed) {
+    float s = b1[e];
+    for (int k = 0; k < embed; ++k) s = fmaf(w1t[k * embed + e], pooled[k], s);
+    hidden[e] = gelu_erf(s);
+  }
+  __syncthreads();
+  if (e < c_n) {
+    float s = b2[e];
+    for (int k = 0; k < embed; ++k) s = fmaf(w2t[k * c_n + e], hidden[k], s);
+    const size_t o = static_cast<size_t>(bi) * c_n + e;
+    if (x_node != nullptr) s = __fadd_rn(__fmul_rn(c_skip[b], x_node[o]), __fmul_rn(c_out[b], s));
+    out_node[o] = s;
+  }
+}
+
+int nv_of(int C) {
+  switch (C) {
+    case 96: return 1;
+    case 192: return 2;
+    case 384: return 3;
+    case 768: return 6;
+    case 1536: return 12;
+    default: return 0;
+  }
+}
+
+inline unsigned row_grid(long long rows) { return static_cast<unsigned>((rows + kRowThreads / 32 - 1) / (kRowThreads / 32)); }
+
+}  // namespace
+
+#define DSG_DISPATCH_NV(C, CALL)                                                          \
+  switch (nv_of(C)) {                                                                     \
+    case 1: { constexpr int NV = 1; CALL; break; }                                        \
+    case 2: { constexpr int NV = 2; CALL; break; }                                        \
+    case 3: { constexpr int NV = 3; CALL; break; }                                        \
+    case 6: { constexpr int NV = 6; CALL; break; }                                        \
+    case 12: { constexpr int NV = 12; CALL; break; }                                      \
+    default:                                                                              \
+      set_last_error("row kernel: unsupported width %d (96/192/384/768/1536)", C);        \
+      return DSG_ERR_INVALID;                                                             \
+  }
+
+int launch_film_ln(const float* x_in, float* x_out, bf16* y, const float* film, int film_ld, int film_off,
+                   int cond_uniform, const float* gamma, const float* beta, int batch, int tokens_per_sample, int C,
+                   cudaStream_t st) {
+  const long long rows = static_cast<long long>(batch) * tokens_per_sample;
+  DSG_DISPATCH_NV(C, (film_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(
+                         x_in, x_out, y, film + film_off, film_ld, cond_uniform, gamma, beta, rows, tokens_per_sample, C)));
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_ln(const float* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, cudaStream_t st) {
+  DSG_DISPATCH_NV(C, (ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(x, y, gamma, beta, rows, C)));
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_merge_ln(const float* x, bf16* y, const float* gamma, const float* beta, int batch, int res, int C,
+                    cudaStream_t st) {
+  DSG_REQUIRE(res % 2 == 0, "merge: odd resolution %d", res);
+  const long long rows = static_cast<long long>(batch) * (res / 2) * (res / 2);
+  DSG_DISPATCH_NV(4 * C, (merge_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res, C)));
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st) {
+  DSG_REQUIRE(C % 4 == 0, "concat: width %d", C);
+  const long long total = rows * 2 * (C / 4);
+  const unsigned grid = static_cast<unsigned>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  concat_bf16_kernel<<<grid, 256, 0, st>>>(x, skip, y, rows, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_breakup_ln(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
+                      int batch, int res, int D, cudaStream_t st) {
+  const long long rows = static_cast<long long>(batch) * res * res;
+  DSG_REQUIRE(D % 16 == 0, "breakup: width %d", D);
+  DSG_DISPATCH_NV(D, (breakup_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, D)));
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_cond(const float* noise_labels, long long label_stride, int n_cond, const float* w0, const float* b0, const float* w1,
+                const float* b1, const float* w_film, const float* b_film, int film_total, float* emb0, float* emb1,
+                float* emb, float* film, int embed, cudaStream_t st) {
+  const int half = embed / 2;
+  sinusoid_kernel<<<(n_cond * half + 127) / 128, 128, 0, st>>>(noise_labels, label_stride, emb0, n_cond, embed);
+  DSG_LAUNCH_CHECK();
+  auto lin = [&](const float* x, const float* W, const float* b, float* y, int K, int O, int act) {
+    const long long warps = static_cast<long long>(n_cond) * O;
+    small_linear_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, st>>>(x, W, b, y, n_cond, K, O, act);
+  };
+  lin(emb0, w0, b0, emb1, embed, 512, 1);
+  DSG_LAUNCH_CHECK();
+  lin(emb1, w1, b1, emb, 512, 512, 1);
+  DSG_LAUNCH_CHECK();
+  lin(emb, w_film, b_film, film, 512, film_total, 0);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_precond_coef(const float* sigmas, int sigma_stride, float* coef, int n, cudaStream_t st) {
+  precond_coef_kernel<<<(n + 127) / 128, 128, 0, st>>>(sigmas, sigma_stride, coef, n);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_node_proj(const float* node, const float* sc_node, const float* in_scale, const float* w_rc, float* rc,
+                     int batch, int n, int c_n, int self_cond, int embed, cudaStream_t st) {
+  DSG_REQUIRE(2 * embed <= 1024, "node_proj: embed %d", embed);
+  node_proj_kernel<<<batch * n, 2 * embed, 0, st>>>(node, sc_node, in_scale, w_rc, rc, batch, n, c_n, self_cond, embed);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_scale, const uint8_t* flags,
+                       const float* rc, const float* w_adj, const float* bias, const float* gamma, const float* beta,
+                       const float* film, int film_ld, int film_off, int cond_uniform, float* x0, int batch, int n,
+                       int c_e, int self_cond, int embed, cudaStream_t st) {
+  DSG_REQUIRE(embed == 96, "patch_embed: embed_dim %d (only 96 is built)", embed);
+  const long long pixels = static_cast<long long>(batch) * n * n;
+  patch_embed_kernel<3><<<row_grid(pixels), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj, bias, gamma,
+                                                                 beta, film + film_off, film_ld, cond_uniform, x0,
+                                                                 pixels, n, c_e, self_cond);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_node_head(const bf16* rep, const uint8_t* flags, const float* w1t, const float* b1, const float* w2t,
+                     const float* b2, const float* x_node, const float* c_skip, const float* c_out, float* out_node,
+                     int batch, int n, int c_n, int embed, cudaStream_t st) {
+  DSG_REQUIRE(embed <= 128 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
+  node_head_kernel<<<batch * n, 128, 0, st>>>(rep, flags, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, n, c_n,
+                                              embed);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+}  // namespace dsg

@@ -1,0 +1,347 @@
+"""Drop-in ``DiffuseSG`` denoiser backed by libdsg_b200 (hand-written sm_100a CUDA).
+
+Mirrors the reference interface (model/diffusesg/diffusesg.py:587-830 of ubc-vision/DiffuseSG):
+
+* the same constructor keywords as used by ``get_network`` (utils/learning_utils.py:47-64);
+* the same ``state_dict()`` keys, order, shapes and dtypes (247 entries for the Visual Genome config,
+  including the persistent ``relative_position_index`` / ``attn_mask`` buffers), so reference checkpoints load
+  with ``strict=True`` and ``ema_pytorch.EMA`` / DDP can wrap the module;
+* ``forward(adj, node, node_flags, noise_labels, self_cond_x=None, self_cond_feat=None) -> (adj_out, node_out)``.
+
+The module holds ordinary fp32 ``nn.Parameter`` masters.  The native side keeps its own arena with the packed
+bf16 / transposed / folded copies; it is refreshed lazily whenever a parameter's version counter moved.  There
+is no PyTorch implementation of the forward in this file: without the shared library or a CUDA device the call
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from ... import native
+from .geometry import relative_position_index, shifted_window_mask
+
+
+class _Tree(nn.Module):
+    """Anonymous container node: gives parameters the dotted names of the reference module tree."""
+
+
+def _spec(img: int, cin: int, embed: int, depths: Sequence[int], heads: Sequence[int], window: int, c_e: int, c_n: int):
+    """Ordered [(key, shape, kind)] in the registration order of the reference (diffusesg.py:611-720)."""
+    out: List[tuple] = []
+
+    def lin(p, o, i, bias=True, kind="w"):
+        out.append((p + ".weight", (o, i), kind))
+        if bias:
+            out.append((p + ".bias", (o,), "zero"))
+
+    def ln(p, c):
+        out.append((p + ".weight", (c,), "one"))
+        out.append((p + ".bias", (c,), "zero"))
+
+    def block(p, dim, res, nh, j):
+        w, s = (res, 0) if res <= window else (window, 0 if j % 2 == 0 else window // 2)
+        if s > 0:
+            out.append((p + ".attn_mask", ((res // w) ** 2, w * w, w * w), ("mask", res, w, s)))
+        lin(p + ".affine", 2 * dim, 512)
+        ln(p + ".norm1", dim)
+        out.append((p + ".attn.relative_position_bias_table", ((2 * w - 1) ** 2, nh), "table"))
+        out.append((p + ".attn.relative_position_index", (w * w, w * w), ("index", w)))
+        lin(p + ".attn.qkv", 3 * dim, dim)
+        lin(p + ".attn.proj", dim, dim)
+        ln(p + ".norm2", dim)
+        lin(p + ".mlp.fc1", 4 * dim, dim)
+        lin(p + ".mlp.fc2", dim, 4 * dim)
+
+    nl = len(depths)
+    lin("patch_embed.affine", 2 * embed, 512)
+    out.append(("patch_embed.proj.weight", (embed, cin, 1, 1), "conv"))
+    out.append(("patch_embed.proj.bias", (embed,), ("conv_bias", cin)))
+    ln("patch_embed.norm", embed)
+    for s in range(nl):
+        dim, res = embed * 2 ** s, img // 2 ** s
+        for j in range(depths[s]):
+            block(f"down_layers.{s}.blocks.{j}", dim, res, heads[s], j)
+        if s < nl - 1:
+            lin(f"down_layers.{s}.downsample.reduction", 2 * dim, 4 * dim, bias=False)
+            ln(f"down_layers.{s}.downsample.norm", 4 * dim)
+    for u in range(nl):
+        s = nl - 1 - u
+        dim, res = embed * 2 ** s, img // 2 ** s
+        if u > 0:
+            d = 4 * dim
+            lin(f"up_layers.{u}.upsample.pre_linear", d, d, bias=False)
+            ln(f"up_layers.{u}.upsample.norm", d)
+            lin(f"up_layers.{u}.upsample.post_linear", d // 4, d // 4, bias=False)
+            ln(f"up_layers.{u}.upsample.post_norm", d // 4)
+        for j in range(depths[s]):
+            block(f"up_layers.{u}.blocks.{j}", dim, res, heads[s], j)
+    for k in range(3):
+        out.append((f"read_out.{k}.weight", (embed, embed, 1, 1), "conv"))
+        out.append((f"read_out.{k}.bias", (embed,), ("conv_bias", embed)))
+    lin("map_layer0", 512, embed)
+    lin("map_layer1", 512, 512)
+    ln("norm", embed)
+    lin("readout_adj_mlp.fc1", embed, embed)
+    lin("readout_adj_mlp.fc2", c_e, embed)
+    lin("readout_node_mlp.fc1", embed, embed)
+    lin("readout_node_mlp.fc2", c_n, embed)
+    return out
+
+
+class DiffuseSG(nn.Module):
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, depths=(2, 2, 6, 2),
+                 num_heads=(3, 6, 12, 24), window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, out_chans_adj=1, out_chans_node=1, norm_layer=nn.LayerNorm,
+                 patch_norm=True, use_checkpoint=False, self_condition=False, symmetric_noise=True, **kwargs):
+        super().__init__()
+        img_size = int(img_size[0] if isinstance(img_size, (tuple, list)) else img_size)
+        unsupported = []
+        if int(patch_size) != 1:
+            unsupported.append(f"patch_size={patch_size} (the scene-graph configs use 1)")
+        if float(mlp_ratio) != 4.0:
+            unsupported.append(f"mlp_ratio={mlp_ratio}")
+        if not qkv_bias or qk_scale is not None or not patch_norm or norm_layer is not nn.LayerNorm:
+            unsupported.append("non-default qkv_bias / qk_scale / patch_norm / norm_layer")
+        if drop_rate or attn_drop_rate or drop_path_rate:
+            unsupported.append("non-zero dropout / stochastic depth (get_network passes 0 for all three)")
+        if symmetric_noise:
+            unsupported.append("symmetric_noise=True (scene graphs use non-symmetric noise, learning_utils.py:62)")
+        if unsupported:
+            raise NotImplementedError("DiffuseSG (B200): " + "; ".join(unsupported))
+        depths, num_heads = list(depths), list(num_heads)[:len(depths)]
+        self.num_layers = len(depths)
+        self.embed_dim = int(embed_dim)
+        self.img_size = img_size
+        self.depths, self.num_heads, self.window_size = depths, num_heads, int(window_size)
+        self.self_condition = bool(self_condition)
+        self.symmetric_noise = False
+        self.out_chans_adj, self.out_chans_node = int(out_chans_adj), int(out_chans_node)
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+        self.mlp_ratio = mlp_ratio
+        self.patches_resolution = [img_size, img_size]
+        cin = in_chans * 2 if self_condition else in_chans
+        if cin != (self.out_chans_adj + 2 * self.out_chans_node) * (2 if self_condition else 1):
+            raise NotImplementedError(f"in_chans={in_chans} is not out_chans_adj + 2 * out_chans_node "
+                                      "(utils/sg_utils.py:412-430 always builds it that way)")
+        self._spec = _spec(img_size, cin, self.embed_dim, depths, num_heads, self.window_size, self.out_chans_adj,
+                           self.out_chans_node)
+        for key, shape, kind in self._spec:
+            *path, leaf = key.split(".")
+            node = self
+            for name in path:
+                node = DiffuseSG._child(node, name)
+            if isinstance(kind, tuple) and kind[0] == "index":
+                node.register_buffer(leaf, relative_position_index(kind[1]))
+            elif isinstance(kind, tuple) and kind[0] == "mask":
+                node.register_buffer(leaf, shifted_window_mask(kind[1], kind[2], kind[3]))
+            else:
+                node.register_parameter(leaf, nn.Parameter(self._init(shape, kind)))
+        # native state (never part of state_dict, never deep-copied)
+        self.__dict__["_nat"] = None
+
+    @staticmethod
+    def _child(module: nn.Module, name: str) -> _Tree:
+        if name not in module._modules:
+            module.add_module(name, _Tree())
+        return module._modules[name]
+
+    @staticmethod
+    def _init(shape, kind) -> torch.Tensor:
+        """Same distributions as the reference init (diffusesg.py:722-729 and nn.Conv2d defaults)."""
+        t = torch.empty(shape)
+        if kind in ("w", "table"):
+            nn.init.trunc_normal_(t, std=.02)
+        elif kind == "zero":
+            t.zero_()
+        elif kind == "one":
+            t.fill_(1.0)
+        elif kind == "conv":
+            nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+        elif isinstance(kind, tuple) and kind[0] == "conv_bias":
+            bound = 1 / math.sqrt(kind[1])
+            nn.init.uniform_(t, -bound, bound)
+        else:  # pragma: no cover
+            raise AssertionError(kind)
+        return t
+
+    # ------------------------------------------------------------------------------------------------------
+    # native model management
+    # ------------------------------------------------------------------------------------------------------
+    def __deepcopy__(self, memo):
+        # ema_pytorch.EMA deep-copies the online model (utils/learning_utils.py:160): copy the parameters,
+        # give the copy its own (lazily created) native state
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        import copy
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_nat" else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_nat"] = None
+        return d
+
+    def _versions(self):
+        # (version counter, storage address) of every parameter / buffer: moves on optimizer steps,
+        # load_state_dict, .to(device) and EMA copies alike
+        return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
+
+    def _native(self, device: torch.device) -> "_NativeModel":
+        nat = self.__dict__.get("_nat")
+        if nat is None or nat.device != device:
+            nat = _NativeModel(self, device)
+            self.__dict__["_nat"] = nat
+        ver = self._versions()
+        if nat.versions != ver:
+            nat.upload(self.state_dict(keep_vars=True))
+            nat.versions = ver
+        return nat
+
+    def forward(self, adj, node, node_flags, noise_labels, self_cond_x=None, self_cond_feat=None):
+        """Raw network F(adj, node | node_flags, c_noise)  (reference diffusesg.py:765-830).
+
+        adj [B, C_e, N, N], node [B, N, C_n], node_flags [B, N] bool, noise_labels [B] (or a stride-0 expand of
+        one value) -> (adj_out [B, C_e, N, N], node_out [B, N, C_n]), fp32, masked like the reference.
+        """
+        return self._run(0, adj, node, node_flags, noise_labels, self_cond_x, self_cond_feat)
+
+    def denoise(self, adjs, nodes, node_flags, sigmas, self_cond_adjs=None, self_cond_nodes=None):
+        """EDM-preconditioned call D(x; sigma) = mask(c_skip x + c_out F(c_in x, ln(sigma)/4, self_cond)):
+        the body of NodeAdjPrecond.forward after the coin flip (model/precond/precond.py:100-105) in one
+        native schedule (the scalings ride inside the patch-embedding and read-out kernels)."""
+        return self._run(1, adjs, nodes, node_flags, sigmas, self_cond_adjs, self_cond_nodes)
+
+    def _run(self, mode, adj, node, flags, noise, sc_adj, sc_node):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
+                (adj.requires_grad or self.training):
+            raise NotImplementedError("DiffuseSG (B200): backward through the native kernels is not built yet; "
+                                      "call under torch.no_grad() / model.eval() (training step = SURVEY 8f-2)")
+        if adj.dim() != 4 or node.dim() != 3 or flags.dim() != 2:
+            raise NotImplementedError("DiffuseSG (B200): expects adj [B,C,N,N], node [B,N,C], node_flags [B,N] "
+                                      "(the scene-graph path of the reference)")
+        dev = adj.device
+        adj = native.require_cuda(adj, "adj")
+        node = native.require_cuda(node.to(dev), "node")
+        b, ce, n, _ = adj.shape
+        if (ce, n, node.shape[-1]) != (self.out_chans_adj, self.img_size, self.out_chans_node):
+            raise ValueError(f"input shapes {tuple(adj.shape)}, {tuple(node.shape)} do not match the model "
+                             f"(C_e={self.out_chans_adj}, N={self.img_size}, C_n={self.out_chans_node})")
+        flags = native.require_cuda(flags.to(dev), "node_flags", torch.bool)
+        noise = noise.to(dev)
+        if noise.dim() == 0:
+            noise = noise.view(1)
+        if noise.dtype != torch.float32:
+            noise = noise.float()
+        if noise.numel() == 1 or (noise.dim() == 1 and noise.stride(0) == 0):
+            n_cond, stride = 1, 0
+        else:
+            if noise.numel() != b:
+                raise ValueError(f"noise conditioning has {noise.numel()} entries for batch {b}")
+            noise = noise.reshape(b)
+            n_cond, stride = b, noise.stride(0)
+        if self.self_condition:
+            sc_adj = None if sc_adj is None else native.require_cuda(sc_adj, "self_cond_x")
+            sc_node = None if sc_node is None else native.require_cuda(sc_node, "self_cond_feat")
+        else:
+            sc_adj = sc_node = None
+        nat = self._native(dev)
+        out_adj = torch.empty_like(adj)
+        out_node = torch.empty_like(node)
+        nat.forward(mode, b, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node)
+        return out_adj, out_node
+
+
+class _NativeModel:
+    """Owns the dsg_model handle, its weight arena and the activation workspace (torch tensors = device memory)."""
+
+    def __init__(self, module: DiffuseSG, device: torch.device):
+        if device.type != "cuda":
+            raise native.NativeError("DiffuseSG (B200) runs on CUDA devices only; there is no CPU fallback")
+        self.lib = native.lib()
+        self.device = device
+        cfg = native.DsgConfig()
+        cfg.img_size, cfg.embed_dim, cfg.num_stages = module.img_size, module.embed_dim, module.num_layers
+        for i in range(module.num_layers):
+            cfg.depths[i] = module.depths[i]
+            cfg.num_heads[i] = module.num_heads[i]
+        cfg.window_size, cfg.c_e, cfg.c_n = module.window_size, module.out_chans_adj, module.out_chans_node
+        cfg.self_condition = int(module.self_condition)
+        handle = C.c_void_p()
+        native.check(self.lib.dsg_model_create(C.byref(cfg), C.byref(handle)), "dsg_model_create")
+        self.handle = handle
+        with torch.cuda.device(device):
+            self.arena = torch.empty(self.lib.dsg_model_arena_bytes(handle) + 256, dtype=torch.uint8, device=device)
+            off = (-self.arena.data_ptr()) % 256
+            native.check(self.lib.dsg_model_bind_arena(handle, self.arena.data_ptr() + off,
+                                                       self.arena.numel() - off), "dsg_model_bind_arena")
+        self.versions = None
+        self.workspace = None
+        self.ws_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dsg_model_destroy(self.handle)
+        except Exception:  # interpreter shutdown
+            pass
+
+    def keys(self):
+        out = []
+        key, numel, dtype = C.c_char_p(), C.c_int64(), C.c_int32()
+        for i in range(self.lib.dsg_model_num_tensors(self.handle)):
+            native.check(self.lib.dsg_model_tensor_info(self.handle, i, C.byref(key), C.byref(numel), C.byref(dtype)),
+                         "dsg_model_tensor_info")
+            out.append((key.value.decode(), numel.value, dtype.value))
+        return out
+
+    def upload(self, state):
+        st = native.stream_ptr(self.device)
+        keep = []
+        for key, numel, dtype in self.keys():
+            t = state[key].detach()
+            want = torch.int64 if dtype == 1 else torch.float32
+            if t.numel() != numel:
+                raise native.NativeError(f"{key}: {t.numel()} elements, native model expects {numel}")
+            t = t.to(device=self.device, dtype=want).contiguous()
+            keep.append(t)
+            native.check(self.lib.dsg_model_set_tensor(self.handle, key.encode(), t.data_ptr(),
+                                                       t.numel() * t.element_size(), 0, st), "dsg_model_set_tensor")
+        native.check(self.lib.dsg_model_finalize(self.handle, st), "dsg_model_finalize")
+        del keep  # stream-ordered: the caching allocator keeps the blocks alive until the copies ran
+
+    def forward(self, mode, batch, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node):
+        key = (batch, n_cond)
+        if self.ws_key != key:
+            need = self.lib.dsg_workspace_bytes(self.handle, batch, n_cond)
+            self.workspace = None
+            with torch.cuda.device(self.device):
+                self.workspace = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            self.ws_key = key
+        off = (-self.workspace.data_ptr()) % 256
+        a = native.DsgForwardArgs()
+        a.struct_size = C.sizeof(native.DsgForwardArgs)
+        a.batch, a.n_cond, a.mode = batch, n_cond, mode
+        a.adj, a.node, a.flags, a.noise = adj.data_ptr(), node.data_ptr(), flags.data_ptr(), noise.data_ptr()
+        a.noise_stride = stride
+        a.sc_adj, a.sc_node = native.ptr(sc_adj), native.ptr(sc_node)
+        a.out_adj, a.out_node = out_adj.data_ptr(), out_node.data_ptr()
+        a.workspace = self.workspace.data_ptr() + off
+        a.workspace_bytes = self.workspace.numel() - off
+        native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
+                     "dsg_denoiser_forward")
+
+    def debug_buffer(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        """Test hook: flat view of a named activation buffer of the last forward's workspace."""
+        off, nbytes = C.c_size_t(), C.c_size_t()
+        batch, n_cond = self.ws_key
+        native.check(self.lib.dsg_debug_buffer(self.handle, batch, n_cond, name.encode(), C.byref(off), C.byref(nbytes)),
+                     "dsg_debug_buffer")
+        base = (-self.workspace.data_ptr()) % 256
+        return self.workspace[base + off.value: base + off.value + nbytes.value].view(dtype)

@@ -1,0 +1,165 @@
+"""ctypes binding of libdsg_b200.so (the C ABI declared in include/dsg_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a ``NativeError`` is raised.  PyTorch is
+used only as the owner of device memory and streams; every pointer crossing the ABI is a raw device pointer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdsg_b200.so")
+ABI_VERSION = 1
+
+EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_F32 = 0, 1, 2, 3
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class DsgConfig(C.Structure):
+    _fields_ = [("img_size", C.c_int32), ("embed_dim", C.c_int32), ("num_stages", C.c_int32),
+                ("depths", C.c_int32 * 4), ("num_heads", C.c_int32 * 4), ("window_size", C.c_int32),
+                ("c_e", C.c_int32), ("c_n", C.c_int32), ("self_condition", C.c_int32)]
+
+
+class DsgForwardArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("batch", C.c_int32), ("n_cond", C.c_int32), ("mode", C.c_int32),
+                ("adj", C.c_void_p), ("node", C.c_void_p), ("flags", C.c_void_p), ("noise", C.c_void_p),
+                ("noise_stride", C.c_int64), ("sc_adj", C.c_void_p), ("sc_node", C.c_void_p),
+                ("out_adj", C.c_void_p), ("out_node", C.c_void_p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
+_SIGNATURES = {
+    "dsg_abi_version": (C.c_int, []),
+    "dsg_last_error": (C.c_char_p, []),
+    "dsg_launch_count": (C.c_uint64, []),
+    "dsg_model_create": (C.c_int, [C.POINTER(DsgConfig), C.POINTER(C.c_void_p)]),
+    "dsg_model_destroy": (None, [C.c_void_p]),
+    "dsg_model_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "dsg_model_bind_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dsg_model_num_tensors": (C.c_int, [C.c_void_p]),
+    "dsg_model_tensor_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int32)]),
+    "dsg_model_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "dsg_model_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dsg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "dsg_denoiser_forward": (C.c_int, [C.c_void_p, C.POINTER(DsgForwardArgs), C.c_void_p]),
+    "dsg_edm_pre_step": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_post_step": (C.c_int, [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_debug_set_stop_after": (None, [C.c_int]),
+    "dsg_debug_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def exported_symbols():
+    """Every entry point include/dsg_b200.h declares."""
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Never builds, never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} is missing: build it with `python -m diffusesg_b200.build_native` "
+                              "(there is no CPU / PyTorch fallback for this path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.dsg_abi_version() != ABI_VERSION:
+            raise NativeError(f"libdsg_b200 ABI {handle.dsg_abi_version()} != binding ABI {ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().dsg_last_error()
+        raise NativeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(lib().dsg_launch_count())
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise NativeError(f"{name} must live on a CUDA device: the B200 path has no CPU implementation")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# thin functional wrappers (used by the kernel-level parity tests)
+# ---------------------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias=None, res=None, epi: int = EPI_F32) -> torch.Tensor:
+    """epilogue(a [M,K] @ w [N,K]^T + bias) on the tcgen05 kernel.  a, w: bf16 CUDA."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    a, w = a.contiguous(), w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty(m, n, device=a.device, dtype=torch.bfloat16 if epi in (EPI_BF16, EPI_GELU_BF16) else torch.float32)
+    check(lib().dsg_gemm_bf16(ptr(a), ptr(w), ptr(bias), ptr(res), ptr(out), m, n, k, epi, stream_ptr(a.device)),
+          "dsg_gemm_bf16")
+    return out
+
+
+def window_attention(qkv: torch.Tensor, bias: torch.Tensor, mask, batch: int, res: int, window: int, shift: int,
+                     heads: int) -> torch.Tensor:
+    assert qkv.is_cuda and qkv.dtype == torch.bfloat16
+    out = torch.empty(qkv.shape[0], heads * 32, device=qkv.device, dtype=torch.bfloat16)
+    check(lib().dsg_window_attention(ptr(qkv.contiguous()), ptr(bias.contiguous()), ptr(mask), ptr(out), batch, res,
+                                     window, shift, heads, stream_ptr(qkv.device)), "dsg_window_attention")
+    return out
+
+
+def edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef: float):
+    b, ce, n, _ = adj.shape
+    cn = node.shape[-1]
+    adj_hat, node_hat = torch.empty_like(adj), torch.empty_like(node)
+    check(lib().dsg_edm_pre_step(ptr(adj), ptr(node), ptr(eps_adj), ptr(eps_node), ptr(flags), float(noise_coef),
+                                 ptr(adj_hat), ptr(node_hat), b, ce, n, cn, stream_ptr(adj.device)), "dsg_edm_pre_step")
+    return adj_hat, node_hat
+
+
+def edm_post_step(adj_hat, node_hat, d1, d2, flags, inv_t_hat: float, h: float, inv_t_prime: float):
+    b, ce, n, _ = adj_hat.shape
+    cn = node_hat.shape[-1]
+    adj_next, node_next = torch.empty_like(adj_hat), torch.empty_like(node_hat)
+    d2a, d2n = (None, None) if d2 is None else d2
+    check(lib().dsg_edm_post_step(ptr(adj_hat), ptr(node_hat), ptr(d1[0]), ptr(d1[1]), ptr(d2a), ptr(d2n), ptr(flags),
+                                  float(inv_t_hat), float(h), float(inv_t_prime), ptr(adj_next), ptr(node_next), b, ce,
+                                  n, cn, stream_ptr(adj_hat.device)), "dsg_edm_post_step")
+    return adj_next, node_next
+
+
+def edm_mask_scale(adj, node, flags, scale: float):
+    b, ce, n, _ = adj.shape
+    cn = node.shape[-1]
+    adj_out, node_out = torch.empty_like(adj), torch.empty_like(node)
+    check(lib().dsg_edm_mask_scale(ptr(adj), ptr(node), ptr(flags), float(scale), ptr(adj_out), ptr(node_out), b, ce, n,
+                                   cn, stream_ptr(adj.device)), "dsg_edm_mask_scale")
+    return adj_out, node_out

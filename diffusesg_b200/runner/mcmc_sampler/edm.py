@@ -1,0 +1,180 @@
+"""Drop-in ``NodeAdjEDMSampler``: the 256-step stochastic Heun loop on fused native kernels.
+
+Interface of runner/mcmc_sampler/edm.py:231-445 of the reference: keyword-only constructor with the same names
+and defaults, ``sample(model, node_flags, init_adjs=None, init_nodes=None, sanity_check_gt_adjs=None, ...)`` with
+the same return convention ((adjs, nodes) on the CPU, or the 4-tuple with interim snapshots), the same consumption
+order of the global torch RNGs (CPU generator for the initial sample, device generator per step, adjacency
+before nodes) and of the numpy RNG (through the model's coin flip).
+
+What changed underneath:
+* the sigma grid and every per-step scalar (gamma, t_hat, noise coefficient, h, 1/t) are evaluated once on the
+  host with the reference's own fp32/fp64 tensor expressions - no 0-d device tensors, no per-step host sync
+  (the reference syncs twice per step: edm.py:355 and :433);
+* each step is two fused elementwise launches (libdsg_b200: dsg_edm_pre_step / dsg_edm_post_step) around the
+  denoiser calls instead of ~113 ATen launches; masking is part of those kernels;
+* interim snapshots are copied to pinned host memory asynchronously.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import native
+from ..objectives.edm import get_edm_params, get_edm_sigma_deriv_t, get_edm_sigma_from_t, get_edm_t_from_sigma
+
+
+class NodeAdjEDMSampler:
+    def __init__(self, *, sigma_min=None, sigma_max=None, solver="heun", discretization="edm", schedule="linear",
+                 scaling="none", C_1=0.001, C_2=0.008, M=1000, alpha=1, num_steps=256, S_churn=40, S_min=0.05,
+                 S_max=50, S_noise=1.003, clip_samples, clip_samples_min, clip_samples_max, clip_samples_scope,
+                 self_condition, dev, objective="edm", symmetric_noise=True):
+        if (solver, discretization, schedule, scaling) != ("heun", "edm", "linear", "none") or alpha != 1:
+            raise NotImplementedError("NodeAdjEDMSampler (B200): only solver='heun', discretization='edm', "
+                                      "schedule='linear', scaling='none', alpha=1 (the reference defaults, "
+                                      "edm.py:239-245) are built")
+        if objective != "edm":
+            raise NotImplementedError("objective must be 'edm'")
+        if symmetric_noise:
+            raise NotImplementedError("symmetric_noise=True: get_mc_sampler always passes False "
+                                      "(utils/sampling_utils.py:23)")
+        if clip_samples:
+            assert clip_samples_scope == "x_0"  # parsed and asserted, never applied by the reference (edm.py:30)
+        self.objective = objective
+        self.clip_samples, self.clip_samples_min, self.clip_samples_max = clip_samples, clip_samples_min, clip_samples_max
+        self.clip_samples_scope = clip_samples_scope
+        self.self_condition = self_condition
+        self.symmetric_noise = symmetric_noise
+        self.dev = torch.device(dev) if not isinstance(dev, torch.device) else dev
+        self.edm_params = get_edm_params()
+        self.num_steps, self.S_churn, self.S_min, self.S_max, self.S_noise = num_steps, S_churn, S_min, S_max, S_noise
+        self.solver, self.alpha = solver, alpha
+        sigma_min = self.edm_params.sigma_min_sampling if sigma_min is None else sigma_min
+        sigma_max = self.edm_params.sigma_max_sampling if sigma_max is None else sigma_max
+        self.sigma_min, self.sigma_max = sigma_min, sigma_max
+        # Karras grid in fp64 (edm.py:70, :84-88); kept on the host
+        rho = self.edm_params.rho
+        step_indices = torch.arange(num_steps, dtype=torch.float64)
+        self.sigma_steps = (sigma_max ** (1 / rho) + step_indices / (num_steps - 1) *
+                            (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+        self.sigma, self.sigma_deriv, self.sigma_inv = get_edm_sigma_from_t, get_edm_sigma_deriv_t, get_edm_t_from_sigma
+        self.s = lambda t: 1
+        self.s_deriv = lambda t: 0
+        self.last_raw_passes = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    def step_scalars(self, t_cur: torch.Tensor, t_next: torch.Tensor) -> dict:
+        """Every scalar one loop iteration derives from (t_cur, t_next), with the reference's expressions on
+        0-d CPU tensors (edm.py:355-356, :361, :369, :384-391, :414), returned as python floats."""
+        gamma = min(self.S_churn / self.num_steps, np.sqrt(2) - 1) if self.S_min <= self.sigma(t_cur) <= self.S_max else 0
+        t_hat = self.sigma_inv(torch.as_tensor(self.sigma(t_cur) + gamma * self.sigma(t_cur)))
+        noise_coef = (self.sigma(t_hat) ** 2 - self.sigma(t_cur) ** 2).clip(min=0).sqrt() * self.s(t_hat) * self.S_noise
+        h = t_next - t_hat
+        inv_t_hat = self.sigma_deriv(t_hat) / self.sigma(t_hat) + self.s_deriv(t_hat) / self.s(t_hat)
+        t_prime = t_hat + self.alpha * h
+        inv_t_prime = (self.sigma_deriv(t_prime) / self.sigma(t_prime)) if float(t_prime) != 0.0 else torch.zeros(())
+        return dict(gamma=float(gamma), t_hat=t_hat, noise_coef=float(noise_coef), h=float(h),
+                    inv_t_hat=float(inv_t_hat), inv_t_prime=float(inv_t_prime))
+
+    def gen_init_sample(self, node_flags, folded_norm=False, flag_node_multi_channel=False,
+                        flag_adj_multi_channel=False, num_node_chan=150, num_edge_chan=51):
+        """Unit-variance start drawn on the CPU generator, adjacency first (edm.py:257-289), masked on device."""
+        batch_size, max_node_num = node_flags.shape[:2]
+        init_adjs = torch.randn((batch_size, num_edge_chan, max_node_num, max_node_num)).to(self.dev, non_blocking=True)
+        init_nodes = torch.randn((batch_size, max_node_num, num_node_chan)).to(self.dev, non_blocking=True)
+        flags = node_flags.to(self.dev).contiguous()
+        return native.edm_mask_scale(init_adjs, init_nodes, flags, 1.0)
+
+    @torch.no_grad()
+    def sample(self, model, node_flags, init_adjs=None, init_nodes=None, sanity_check_gt_adjs=None,
+               sanity_check_gt_nodes=None, flag_interim_adjs=False, max_num_interim_adjs=None, flag_use_double=False,
+               flag_node_multi_channel=False, flag_adj_multi_channel=False, num_node_chan=150, num_edge_chan=51):
+        if flag_use_double:
+            raise NotImplementedError("flag_use_double: the native state is fp32 (the reference default)")
+        if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
+            func_round_sigma = model.module.round_sigma
+        else:
+            func_round_sigma = model.round_sigma
+        t_steps = self.sigma_inv(func_round_sigma(self.sigma_steps))
+        t_steps = torch.cat([t_steps, torch.zeros_like(t_steps[:1])]).to(torch.float32)  # t_N = 0 (edm.py:318-323)
+
+        dev = self.dev
+        flags = node_flags.to(dev).to(torch.bool).contiguous()
+        if init_adjs is None or init_nodes is None:
+            init_adjs, init_nodes = self.gen_init_sample(node_flags, num_node_chan=num_node_chan,
+                                                         num_edge_chan=num_edge_chan)
+        adjs = native.require_cuda(init_adjs.to(dev), "init_adjs")
+        nodes = native.require_cuda(init_nodes.to(dev), "init_nodes")
+        if adjs.dim() != 4 or nodes.dim() != 3:
+            raise NotImplementedError("single-channel ([B,N,N] / [B,N]) states are not part of the scene-graph path")
+        snaps_a: List[torch.Tensor] = [self._snapshot(adjs)] if flag_interim_adjs and not flag_adj_multi_channel else []
+        snaps_n: List[torch.Tensor] = [self._snapshot(nodes)] if flag_interim_adjs else []
+        if max_num_interim_adjs is None:
+            timesteps_snapshot = set(np.arange(self.num_steps).tolist())
+        else:
+            timesteps_snapshot = set(np.linspace(0, self.num_steps, max_num_interim_adjs).astype(int)
+                                     .clip(max=self.num_steps - 1).tolist())
+        gt = None
+        if sanity_check_gt_adjs is not None:
+            gt = native.edm_mask_scale(native.require_cuda(sanity_check_gt_adjs.to(dev), "sanity_check_gt_adjs"),
+                                       native.require_cuda(sanity_check_gt_nodes.to(dev), "sanity_check_gt_nodes"),
+                                       flags, 1.0)
+        passes0 = getattr(model, "raw_passes", 0)
+
+        # x_0 = init * sigma(t_0) s(t_0)                                     (edm.py:343-347)
+        adjs, nodes = native.edm_mask_scale(adjs, nodes, flags, float(self.sigma(t_steps[0]) * self.s(t_steps[0])))
+        sc_a = sc_n = None
+        # all per-step scalars up front (host), the noise levels uploaded once: no per-step H2D copy or sync
+        scalars = [self.step_scalars(t_steps[i], t_steps[i + 1]) for i in range(self.num_steps)]
+        t_hat_dev = torch.stack([s["t_hat"] for s in scalars]).to(torch.float32).to(dev)
+        for i in range(self.num_steps):
+            sc = scalars[i]
+            # temporary noise increase; adjacency noise is drawn first        (edm.py:355-366)
+            eps_a = torch.randn_like(adjs)
+            eps_n = torch.randn_like(nodes)
+            adjs_hat, nodes_hat = native.edm_pre_step(adjs, nodes, eps_a, eps_n, flags, sc["noise_coef"])
+            sigma_tensors = t_hat_dev[i].view(-1).expand(flags.size(0))
+            d1 = gt if gt is not None else model(adjs_hat, nodes_hat, flags, sigma_tensors, sc_a, sc_n)
+            if i == self.num_steps - 1:
+                adjs, nodes = native.edm_post_step(adjs_hat, nodes_hat, d1, None, flags, sc["inv_t_hat"], sc["h"], 0.0)
+                d2 = d1
+            else:
+                # second evaluation at (x_hat, t_hat) again, self-conditioned on D1 (edm.py:400-405)
+                if gt is None:
+                    if self.self_condition:
+                        sc_a, sc_n = d1
+                    else:
+                        sc_a = sc_n = None
+                    d2 = model(adjs_hat, nodes_hat, flags, sigma_tensors, sc_a, sc_n)
+                else:
+                    d2 = gt
+                adjs, nodes = native.edm_post_step(adjs_hat, nodes_hat, d1, d2, flags, sc["inv_t_hat"], sc["h"],
+                                                   sc["inv_t_prime"])
+            sc_a, sc_n = d2 if self.self_condition else (None, None)
+            if flag_interim_adjs and i in timesteps_snapshot:
+                if not flag_adj_multi_channel:
+                    snaps_a.append(self._snapshot(adjs))
+                snaps_n.append(self._snapshot(nodes))
+        self.last_raw_passes = getattr(model, "raw_passes", 0) - passes0
+        logging.info("Done with EDM-NodeAdj MCMC.")
+        adjs_cpu, nodes_cpu = adjs.cpu(), nodes.cpu()  # synchronises the stream: snapshots are complete too
+        if flag_interim_adjs:
+            if flag_adj_multi_channel:
+                return adjs_cpu, nodes_cpu, [None], torch.stack(snaps_n)
+            return adjs_cpu, nodes_cpu, torch.stack(snaps_a), torch.stack(snaps_n)
+        return adjs_cpu, nodes_cpu
+
+    @staticmethod
+    def _snapshot(t: torch.Tensor) -> torch.Tensor:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        return host
+
+    @staticmethod
+    def get_num_edges(adjs, node_flags, threshold=0.0):
+        """runner/mcmc_sampler/__init__.py:50 (diagnostic only; no longer called inside the loop)."""
+        valid = node_flags[:, None, :, None] & node_flags[:, None, None, :]
+        return ((adjs > threshold) & valid).flatten(1).sum(-1).float()

@@ -1,0 +1,158 @@
+/* libdsg_b200 — C ABI of the B200-native DiffuseSG denoising hot path.
+ *
+ * The reference (ubc-vision/DiffuseSG) is pure Python/PyTorch and has no FFI of its own; its seam for this
+ * path is the pair of Python objects built by utils/learning_utils.py:33 get_network() and
+ * utils/sampling_utils.py:8 get_mc_sampler().  This header is what the drop-in Python classes in
+ * diffusesg_b200/ bind through ctypes.  Each entry point cites the reference code it
+ * replaces; paths are relative to DiffuseSG/ in the reference repository.
+ *
+ * Conventions
+ *   - plain C, no exceptions: every function returns 0 (DSG_OK) or a DSG_ERR_* code; dsg_last_error() gives
+ *     the message of the last failure on the calling thread.
+ *   - all tensor pointers are DEVICE pointers (fp32 unless stated) owned by the caller; nothing is allocated
+ *     behind the caller's back: weights live in a caller-provided arena, activations in a caller-provided
+ *     workspace.  Calls are asynchronous on the given CUDA stream and never synchronise it.
+ *   - one host thread per dsg_model; different models may be used from different threads.
+ *   - there is no CPU path: without an sm_100 device every compute call fails with DSG_ERR_CUDA.
+ */
+#ifndef DSG_B200_H_
+#define DSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DSG_API __attribute__((visibility("default")))
+#else
+#define DSG_API
+#endif
+
+enum {
+  DSG_OK = 0,
+  DSG_ERR_INVALID = 1,     /* bad argument / shape */
+  DSG_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed (includes: no device) */
+  DSG_ERR_STATE = 3,       /* call order violated (e.g. forward before finalize) */
+  DSG_ERR_UNKNOWN_KEY = 4, /* set_tensor with a key the configuration does not define */
+  DSG_ERR_WORKSPACE = 5    /* arena / workspace too small or not bound */
+};
+
+typedef void* dsg_stream_t;          /* cudaStream_t */
+typedef struct dsg_model dsg_model;  /* opaque: configuration + packed weights + TMA descriptors */
+
+/* Constructor arguments of the reference denoiser, DiffuseSG.__init__ (model/diffusesg/diffusesg.py:587-720) as
+ * called from utils/learning_utils.py:47-64.  patch_size is 1, mlp_ratio 4, head_dim 32 and all drop rates 0 there. */
+typedef struct dsg_config {
+  int32_t img_size;       /* N: dataset.max_node_num */
+  int32_t embed_dim;      /* model.feature_dims[-1]; 96 */
+  int32_t num_stages;     /* len(model.depths), <= 4 */
+  int32_t depths[4];
+  int32_t num_heads[4];   /* [3, 6, 12, 24]; dim / heads must be 32 */
+  int32_t window_size;
+  int32_t c_e;            /* out_chans_adj: edge channels (<= 8) */
+  int32_t c_n;            /* out_chans_node: node channels */
+  int32_t self_condition; /* train.self_cond */
+} dsg_config;
+
+DSG_API int dsg_abi_version(void);
+DSG_API const char* dsg_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (all models). */
+DSG_API uint64_t dsg_launch_count(void);
+
+/* ---- model life cycle -------------------------------------------------------------------------------------- */
+DSG_API int dsg_model_create(const dsg_config* cfg, dsg_model** out);
+DSG_API void dsg_model_destroy(dsg_model* m);
+
+/* The arena holds the fp32 master copy of every state_dict tensor plus the packed bf16 / transposed / folded
+ * forms the kernels read.  Bind once; rebinding invalidates loaded tensors. */
+DSG_API size_t dsg_model_arena_bytes(const dsg_model* m);
+DSG_API int dsg_model_bind_arena(dsg_model* m, void* arena, size_t bytes);
+
+/* Enumerate the state_dict of the reference module (same keys, shapes and dtypes as
+ * DiffuseSG(...).state_dict(); strict checkpoint loading at utils/sampling_utils.py:34-60 relies on it).
+ * dtype: 0 = float32, 1 = int64 (the relative_position_index buffers). */
+DSG_API int dsg_model_num_tensors(const dsg_model* m);
+DSG_API int dsg_model_tensor_info(const dsg_model* m, int index, const char** key, int64_t* numel, int32_t* dtype);
+
+/* Copy one state_dict tensor (contiguous, dtype as reported above) into the arena.  src may be a device or a
+ * host pointer (src_is_host != 0). */
+DSG_API int dsg_model_set_tensor(dsg_model* m, const char* key, const void* src, int64_t bytes, int src_is_host,
+                         dsg_stream_t stream);
+/* Build the packed forms (bf16 weights with the q scale folded in, gathered relative-position bias, folded
+ * read_out chain, transposed head weights) and the weight TMA descriptors.  Call after all tensors are set and
+ * again whenever any of them changed. */
+DSG_API int dsg_model_finalize(dsg_model* m, dsg_stream_t stream);
+
+/* ---- denoiser forward --------------------------------------------------------------------------------------- */
+/* n_cond = 1 when every sample shares one noise level (sampling: runner/mcmc_sampler/edm.py:371 expands a
+ * scalar), = batch otherwise (training). */
+DSG_API size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond);
+
+typedef struct dsg_forward_args {
+  uint32_t struct_size;     /* sizeof(dsg_forward_args) */
+  int32_t batch;
+  int32_t n_cond;           /* 1 or batch */
+  /* mode 0: raw network, DiffuseSG.forward(adj, node, node_flags, noise_labels, self_cond_x, self_cond_feat)
+   *         (model/diffusesg/diffusesg.py:765); `noise` holds noise_labels (c_noise = ln(sigma) / 4).
+   * mode 1: EDM-preconditioned denoiser, the non-coin-flip body of NodeAdjPrecond.forward
+   *         (model/precond/precond.py:100-105): `noise` holds sigmas; inputs are scaled by c_in inside the
+   *         patch embedding, outputs are c_skip * x + c_out * F, masked. */
+  int32_t mode;
+  const float* adj;         /* [B, c_e, N, N] */
+  const float* node;        /* [B, N, c_n] */
+  const uint8_t* flags;     /* [B, N] bool (node_flags), 4-byte aligned */
+  const float* noise;       /* n_cond values, element stride noise_stride */
+  int64_t noise_stride;
+  const float* sc_adj;      /* self-conditioning inputs or NULL (zeros), same shapes as adj / node */
+  const float* sc_node;
+  float* out_adj;           /* [B, c_e, N, N] */
+  float* out_node;          /* [B, N, c_n] */
+  void* workspace;
+  size_t workspace_bytes;
+} dsg_forward_args;
+
+DSG_API int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* args, dsg_stream_t stream);
+
+/* ---- EDM stochastic-Heun sampler steps (runner/mcmc_sampler/edm.py:350-434) ------------------------------- */
+/* x_hat = mask(x + noise_coef * eps), noise_coef = sqrt(t_hat^2 - t_cur^2) * S_noise          (:361-366) */
+DSG_API int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
+                     const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch, int c_e,
+                     int n, int c_n, dsg_stream_t stream);
+/* Heun update from (x_hat, D1, D2); pass d2_* = NULL for the Euler update of the last step     (:384-422).
+ * inv_t_hat = 1 / t_hat, h = t_next - t_hat, inv_t_prime = 1 / (t_hat + h), all evaluated in fp32 by the caller
+ * exactly as the reference does. */
+DSG_API int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                      const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat, float h,
+                      float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e, int n, int c_n,
+                      dsg_stream_t stream);
+/* x_out = mask(x * scale): masking of the initial noise and its scaling by sigma(t_0)         (:276-289, :346-347) */
+DSG_API int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
+                       float* node_out, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
+
+/* ---- building blocks, exported for the kernel-level parity tests ------------------------------------------- */
+/* out[M, N] = epilogue(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major.  epi: 0 bf16, 1 gelu->bf16,
+ * 2 fp32 + residual (res may alias out), 3 fp32.  tcgen05/TMEM/TMA kernel (nn.Linear of the reference). */
+DSG_API int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
+                  int epi, dsg_stream_t stream);
+/* qkv [B*res*res, 3*heads*32] bf16 -> out [B*res*res, heads*32] bf16 (WindowAttention.forward, :108-139, q
+ * pre-scaled); bias [heads, T, T] fp32, mask [nW, T, T] fp32 or NULL (shift == 0). */
+DSG_API int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
+                         int window, int shift, int heads, dsg_stream_t stream);
+
+/* ---- test hooks (used by tests/ to localise a parity failure; not part of the product path) ------------------- */
+/* Leave dsg_denoiser_forward after n_stages schedule stages (0: patch embedding, then one per Swin block /
+ * PatchMerging / PatchBreakup in execution order); -1 restores the full schedule.  Process-global. */
+DSG_API void dsg_debug_set_stop_after(int n_stages);
+/* Byte offset and size of a named activation buffer ("X", "Y", "QKV", "ATT", "H", "T", "REP", "skip0".."skip2",
+ * "film", "rc", "emb", "coef") inside a workspace laid out for (batch, n_cond). */
+DSG_API int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name, size_t* offset, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSG_B200_H_ */

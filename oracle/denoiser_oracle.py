@@ -233,12 +233,16 @@ def denoiser_forward(sd: Dict[str, Tensor], *, img: int, embed: int, depths: Seq
             x = swin_block(sd, next(it), x, emb, capture)
         if s < nl - 1:
             x = patch_merging(sd, f"down_layers.{s}.downsample", x, img // 2 ** s)
+            if capture is not None:
+                capture[f"down_layers.{s}.downsample"] = x
         skips.append(x)
     for u in range(nl):                                                      # decoder (:751-756)
         s = nl - 1 - u
         skip = skips.pop()
         if u > 0:                                                            # first decoder stage drops its skip
             x = patch_breakup(sd, f"up_layers.{u}.upsample", torch.cat([x, skip], dim=-1), img // 2 ** (s + 1))
+            if capture is not None:
+                capture[f"up_layers.{u}.upsample"] = x
         for _ in range(depths[s]):
             x = swin_block(sd, next(it), x, emb, capture)
 

@@ -1,0 +1,152 @@
+"""Kernel-level parity on the B200 (run with -m gpu): every check goes through the C ABI of libdsg_b200.so."""
+import numpy as np
+import pytest
+import torch
+
+from diffusesg_b200 import native
+from diffusesg_b200.model.diffusesg.geometry import relative_position_index, shifted_window_mask
+from oracle import edm_oracle as E
+from oracle.denoiser_oracle import mask_pairs, mask_rows
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ---------------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    # (M, N, K): tails in M (TMA zero fill + predicated stores), K = 96 (half-empty second k-block), both tile widths
+    (128, 96, 64), (128, 192, 64), (256, 96, 96), (300, 288, 96), (1000, 384, 192), (4096, 1152, 384),
+    (777, 768, 3072), (512, 1536, 1536), (48, 96, 384), (20000, 96, 96), (33000, 576, 192),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [native.EPI_BF16, native.EPI_GELU_BF16, native.EPI_RES_F32, native.EPI_F32])
+def test_gemm_matches_torch(M, N, K, epi):
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K + epi)
+    a = (torch.randn(M, K, device=DEV, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g) if epi == native.EPI_RES_F32 else None
+    want = a.float() @ w.float().t() + bias
+    if epi == native.EPI_GELU_BF16:
+        want = torch.nn.functional.gelu(want)
+    if res is not None:
+        want = want + res
+    got = native.gemm_bf16(a, w, bias, res, epi).float()
+    torch.cuda.synchronize()
+    err = (got - want).abs()
+    tol = 2e-2 if epi in (native.EPI_BF16, native.EPI_GELU_BF16) else 2e-3   # bf16 output rounding vs fp32 output
+    bad = (err > tol * (1 + want.abs())).nonzero()
+    assert bad.numel() == 0, (f"{bad.shape[0]} bad of {M * N}; first {bad[:5].tolist()}; max err {float(err.max())}; "
+                              f"bad rows {sorted(set(bad[:, 0].tolist()))[:10]} cols {sorted(set(bad[:, 1].tolist()))[:10]}")
+    assert _rel(got, want) < (5e-3 if tol > 1e-2 else 1e-5 + 2e-6 * K ** 0.5)
+
+
+def test_gemm_residual_in_place():
+    M, N, K = 1000, 192, 384
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).to(torch.bfloat16)
+    x = torch.randn(M, N, device=DEV)
+    want = x + a.float() @ w.float().t()
+    native.check(native.lib().dsg_gemm_bf16(a.data_ptr(), w.data_ptr(), None, x.data_ptr(), x.data_ptr(), M, N, K,
+                                            native.EPI_RES_F32, native.stream_ptr()), "gemm")
+    assert _rel(x, want) < 1e-4
+
+
+def test_gemm_rejects_bad_shapes():
+    a = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(100, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(native.NativeError):
+        native.gemm_bf16(a, w)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# window attention
+# ---------------------------------------------------------------------------------------------------------
+def _attention_reference(qkv, bias, mask, batch, res, w, shift, heads):
+    c = heads * 32
+    x = qkv.float().view(batch, res, res, 3 * c)
+    if shift:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    nw = res // w
+    t = w * w
+    xw = x.view(batch, nw, w, nw, w, 3 * c).permute(0, 1, 3, 2, 4, 5).reshape(batch * nw * nw, t, 3, heads, 32)
+    q, k, v = xw.permute(2, 0, 3, 1, 4)
+    att = q @ k.transpose(-1, -2) + bias[None]
+    if mask is not None:
+        att = (att.view(batch, nw * nw, heads, t, t) + mask[None, :, None]).view(-1, heads, t, t)
+    out = (att.softmax(-1) @ v).transpose(1, 2).reshape(batch, nw, nw, w, w, c).permute(0, 1, 3, 2, 4, 5)
+    out = out.reshape(batch, res, res, c)
+    if shift:
+        out = torch.roll(out, shifts=(shift, shift), dims=(1, 2))
+    return out.reshape(batch * res * res, c)
+
+
+@pytest.mark.parametrize("batch,res,w,shift,heads", [
+    (3, 16, 4, 0, 3), (3, 8, 4, 2, 6), (2, 64, 8, 0, 3), (5, 16, 8, 4, 12), (2, 8, 8, 0, 24),
+    (2, 20, 10, 5, 6), (3, 10, 10, 0, 12), (1, 32, 16, 8, 6), (2, 16, 16, 0, 12)])
+def test_window_attention_matches_torch(batch, res, w, shift, heads):
+    g = torch.Generator(device=DEV).manual_seed(res * 100 + w + shift)
+    c = heads * 32
+    t = w * w
+    qkv = torch.randn(batch * res * res, 3 * c, device=DEV, generator=g)
+    qkv[:, :c] *= 32 ** -0.5
+    qkv = qkv.to(torch.bfloat16)
+    table = torch.randn((2 * w - 1) ** 2, heads, device=DEV, generator=g) * 0.5
+    bias = table[relative_position_index(w).to(DEV).reshape(-1)].view(t, t, heads).permute(2, 0, 1).contiguous()
+    mask = shifted_window_mask(res, w, shift).to(DEV) if shift else None
+    want = _attention_reference(qkv, bias, mask, batch, res, w, shift, heads)
+    got = native.window_attention(qkv, bias, mask, batch, res, w, shift, heads).float()
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert _rel(got, want) < 1e-2, _rel(got, want)   # p is rounded to bf16 before p.v, output stored as bf16
+    assert float((got - want).abs().max()) < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused EDM step kernels: bit-exact against the fp32 expressions of the reference sampler
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,ce,n,cn", [(3, 3, 16, 5), (8, 6, 64, 12), (5, 3, 40, 12), (1, 1, 4, 1)])
+def test_edm_steps_bit_exact(b, ce, n, cn):
+    g = torch.Generator().manual_seed(b + n)
+    flags = torch.arange(n)[None, :] < torch.randint(1, n + 1, (b, 1), generator=g)
+    adj = mask_pairs(torch.randn(b, ce, n, n, generator=g) * 3, flags)
+    node = mask_rows(torch.randn(b, n, cn, generator=g) * 3, flags)
+    eps_a, eps_n = torch.randn(b, ce, n, n, generator=g), torch.randn(b, n, cn, generator=g)
+    d1 = (mask_pairs(torch.randn(b, ce, n, n, generator=g), flags), mask_rows(torch.randn(b, n, cn, generator=g), flags))
+    d2 = (mask_pairs(torch.randn(b, ce, n, n, generator=g), flags), mask_rows(torch.randn(b, n, cn, generator=g), flags))
+    ts = E.t_steps_fp32(256)
+    cu = lambda t: t.to(DEV)
+    for i in (0, 40, 130, 254, 255):
+        s = E.step_scalars(ts[i], ts[i + 1], 256)
+        t_hat, h, t_prime = s["t_hat"], s["h"], s["t_prime"]
+        # oracle (CPU fp32 torch)
+        a_hat = mask_pairs(adj + s["noise_coef"] * eps_a, flags)
+        n_hat = mask_rows(node + s["noise_coef"] * eps_n, flags)
+        inv = 1.0 / t_hat
+        ka, kn = inv * a_hat - inv * d1[0], inv * n_hat - inv * d1[1]
+        pa, pn = a_hat + h * ka, n_hat + h * kn
+        if i == 255:
+            na, nn_ = mask_pairs(pa, flags), mask_rows(pn, flags)
+        else:
+            ip = 1.0 / t_prime
+            na = mask_pairs(a_hat + h * (0.5 * ka + 0.5 * (ip * pa - ip * d2[0])), flags)
+            nn_ = mask_rows(n_hat + h * (0.5 * kn + 0.5 * (ip * pn - ip * d2[1])), flags)
+        # device
+        ga_hat, gn_hat = native.edm_pre_step(cu(adj), cu(node), cu(eps_a), cu(eps_n), cu(flags), float(s["noise_coef"]))
+        np.testing.assert_array_equal(ga_hat.cpu().numpy(), a_hat.numpy())
+        np.testing.assert_array_equal(gn_hat.cpu().numpy(), n_hat.numpy())
+        ga, gn = native.edm_post_step(ga_hat, gn_hat, (cu(d1[0]), cu(d1[1])), None if i == 255 else (cu(d2[0]), cu(d2[1])),
+                                      cu(flags), float(inv), float(h), 0.0 if i == 255 else float(1.0 / t_prime))
+        np.testing.assert_array_equal(ga.cpu().numpy(), na.numpy())
+        np.testing.assert_array_equal(gn.cpu().numpy(), nn_.numpy())
+    sa, sn = native.edm_mask_scale(cu(torch.randn(b, ce, n, n, generator=g)), cu(node), cu(flags), 80.0)
+    assert float(sa[~(flags[:, None, :, None] & flags[:, None, None, :]).expand_as(sa).to(DEV)].abs().sum()) == 0.0
+    np.testing.assert_array_equal(sn.cpu().numpy(), (node * 80.0).numpy())
