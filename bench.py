@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffuseSG sampling hot path: sampled scene graphs / second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config vg] [--batch 512]
+
+A "step" is one pass of the hot path over one batch of synthetic input: one full NodeAdjEDMSampler run (256
+stochastic-Heun steps, 511 preconditioned-denoiser calls plus the data-dependent self-conditioning passes) over
+`--batch` Visual-Genome-shaped graphs per GPU with seeded random-init weights (no dataset or checkpoint is
+available offline).  N > 1 is launched by torchrun, one rank per GPU; the batch is sharded by sample with no
+per-step communication (weak scaling: every rank samples its own `--batch` graphs).
+
+Two numbers per step:
+  value  device-resident: node flags and the initial noise are already in HBM, the result stays in HBM;
+  e2e    the reference-facing call `sampler.sample(model, node_flags)` with HOST node flags: the initial noise
+         is drawn on the CPU generator and uploaded (as the reference does), the samples come back as CPU tensors.
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port of the unmodified
+PyTorch modules: same ATen CPU kernels, all host threads) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from diffusesg_b200.utils.synthetic import CONFIGS, in_chans, synthetic_node_flags, synthetic_state_dict  # noqa: E402
+
+METRIC = "sampled scene graphs/sec"
+UNIT = "graphs/s"
+EXPECTED_PASSES_256 = 766.5  # 511 precond calls + E[#coins < 0.5] (model/precond/precond.py:90)
+GFLOP_PER_PASS = {"vg": 13.30, "coco": 7.36, "n64w16": 14.66}  # GEMM + bmm + conv, per sample
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_sustained=p["bf16_tflops_sustained"], tensor_burst=p["bf16_tflops"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_sustained=1400.0, tensor_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 4:]  # drop idle samples at the edges
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_native_model(cfg, device):
+    from diffusesg_b200.model.diffusesg.diffusesg import DiffuseSG
+    from diffusesg_b200.model.precond.precond import NodeAdjPrecond
+    net = DiffuseSG(img_size=cfg["img"], in_chans=in_chans(cfg), patch_size=1, embed_dim=cfg["embed"],
+                    depths=cfg["depths"], num_heads=[3, 6, 12, 24], window_size=cfg["window"], mlp_ratio=4.,
+                    drop_rate=0., attn_drop_rate=0., drop_path_rate=0.0, self_condition=cfg["self_cond"],
+                    symmetric_noise=False, out_chans_adj=cfg["c_e"], out_chans_node=cfg["c_n"])
+    net.load_state_dict(synthetic_state_dict(cfg, seed=1234, stress=False), strict=True)
+    return NodeAdjPrecond(precond="edm", model=net.to(device), self_condition=cfg["self_cond"],
+                          symmetric_noise=False).eval()
+
+
+def make_sampler(cfg, device, num_steps):
+    from diffusesg_b200.runner.mcmc_sampler.edm import NodeAdjEDMSampler
+    return NodeAdjEDMSampler(num_steps=num_steps, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                             clip_samples_scope="x_0", dev=device, objective="edm", self_condition=cfg["self_cond"],
+                             symmetric_noise=False)
+
+
+# -----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# -----------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(cfg, batch, num_steps, repeats, warmup):
+    """(graphs/s extrapolated to 256 steps, ms per repeat, raw passes per repeat, seconds per raw pass)."""
+    from oracle import denoiser_oracle as O
+    from oracle import edm_oracle as E
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic_state_dict(cfg, seed=1234, stress=False)
+    flags = synthetic_node_flags(cfg, batch, seed=1234)
+    passes = [0]
+
+    def net(adj, node, f, labels, sa, sn):
+        passes[0] += 1
+        return O.denoiser_forward(sd, img=cfg["img"], embed=cfg["embed"], depths=cfg["depths"], heads=cfg["heads"],
+                                  window=cfg["window"], self_condition=cfg["self_cond"], adj=adj, node=node, flags=f,
+                                  noise_labels=labels, sc_adj=sa, sc_node=sn)
+
+    model = lambda a, n, f, sig, sa, sn: O.precond_forward(net, a, n, f, sig, sa, sn, coin=np.random.rand)
+    times, counts = [], []
+    torch.manual_seed(1234)
+    np.random.seed(1234)
+    with torch.no_grad():
+        for it in range(warmup + repeats):
+            passes[0] = 0
+            t0 = time.perf_counter()
+            E.sample(model, flags, cfg["c_e"], cfg["c_n"], num_steps=num_steps)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+                counts.append(passes[0])
+    sec_per_pass = sum(times) / max(1, sum(counts))
+    rate = batch / (sec_per_pass * EXPECTED_PASSES_256)
+    return rate, 1e3 * sum(times) / len(times), sum(counts) / len(counts), sec_per_pass
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    b, ns = args.cpu_batch, args.cpu_steps
+    rate, ms, passes, spp = cpu_reference_rate(cfg, b, ns, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    sample = (f"{args.config} geometry, batch {b}, {ns} Heun steps per timed step ({passes:.1f} raw denoiser passes, "
+              f"{spp:.3f} s/pass), extrapolated to 256 steps = {EXPECTED_PASSES_256} expected passes per graph batch")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, cfg, world),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, world):
+    return {"workload": f"DiffuseSG EDM sampling, {cfg['dataset']}-shaped synthetic graphs (N={cfg['img']}, "
+                        f"C_e={cfg['c_e']}, C_n={cfg['c_n']}, window {cfg['window']}, depths {cfg['depths']}), "
+                        f"{args.num_steps} stochastic Heun steps, self-conditioning coin flip on",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "num_steps": args.num_steps,
+            "parallelism": f"sample-sharded x{world}, no per-step collective",
+            "l2": "working set per step (>= 6 GB of activations at batch 512) exceeds the 126 MB L2; no flush needed"}
+
+
+# -----------------------------------------------------------------------------------------------------------
+# native arm
+# -----------------------------------------------------------------------------------------------------------
+def run_native(args, cfg, rank, local_rank, world):
+    from diffusesg_b200 import native
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the native path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    native.lib()
+    torch.manual_seed(1234 + rank)   # the reference offsets the seed by the rank (utils/arg_parser.py:293-294)
+    np.random.seed(1234 + rank)
+    model = build_native_model(cfg, device)
+    sampler = make_sampler(cfg, device, args.num_steps)
+    B, N, ce, cn = args.batch, cfg["img"], cfg["c_e"], cfg["c_n"]
+    flags_host = synthetic_node_flags(cfg, B, seed=1234 + rank)
+    flags_dev = flags_host.to(device)
+    elems = B * (ce * N * N + N * cn)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # device-resident step: initial noise pre-generated in HBM, result left in HBM
+    init = [(torch.randn(B, ce, N, N, device=device), torch.randn(B, N, cn, device=device))
+            for _ in range(2)]
+    k = [0]
+
+    def step_device():
+        a, n = init[k[0] % 2]
+        k[0] += 1
+        sampler.sample_on_device(model, flags_dev, init_adjs=a, init_nodes=n, num_node_chan=cn, num_edge_chan=ce)
+
+    def step_e2e():
+        sampler.sample(model=model, node_flags=flags_host, num_node_chan=cn, num_edge_chan=ce)
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    passes0, launches0 = model.raw_passes, native.launch_count()
+    native.profile_begin(args.profile_stride)
+    with ClockSampler(local_rank) as clocks:
+        ms_total = timed(step_device, args.steps)
+    prof = native.profile_read()
+    native.profile_stop()
+    passes = (model.raw_passes - passes0) / args.steps
+    launches = native.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # end-to-end through the reference-facing API with host inputs / outputs
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    step_e2e()
+    ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
+    e2e_value = world * B / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    g = prof.get("gemm_tcgen05", dict(ms=0, flops=0, bytes=0, launches=0))
+    total_prof_ms = sum(c["ms"] for c in prof.values()) or 1.0
+    gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05/TMEM/TMA GEMM, all nn.Linear of the denoiser)",
+                "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic": None, "launches_timed": g["launches"],
+                "avg_launch_ms": g["ms"] / g["launches"] if g["launches"] else None,
+                "share_of_profiled_time": g["ms"] / total_prof_ms,
+                "how": f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region"}
+    classes = {}
+    for name, c in prof.items():
+        sec = c["ms"] * 1e-3
+        classes[name] = {"launches": c["launches"], "ms": round(c["ms"], 3), "share": round(c["ms"] / total_prof_ms, 4),
+                         "tflops": round(c["flops"] / sec / 1e12, 2) if sec and c["flops"] else None,
+                         "gbs": round(c["bytes"] / sec / 1e9, 1) if sec and c["bytes"] else None}
+    edm = prof.get("edm_step")
+    edm_roof = None
+    if edm and edm["ms"]:
+        gbs = edm["bytes"] / (edm["ms"] * 1e-3) / 1e9
+        edm_roof = {"bound": "hbm", "kernel": "edm_kernel<MODE> (fused pre / post step)", "achieved": gbs, "peak": pk["hbm"],
+                    "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None}
+    flops_step = passes * GFLOP_PER_PASS.get(args.config, 0.0) * 1e9 * B
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args, cfg, world),
+            "raw_denoiser_passes_per_step": passes,
+            "denoiser_tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12 if flops_step else None,
+            "denoiser_frac_of_sustained_peak": (flops_step / (ms_step * 1e-3) / 1e12 / pk["tensor_sustained"]) if flops_step else None,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(flags_host.numel() + elems * 4), "d2h_bytes_per_step": int(elems * 4)},
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_edm_step": edm_roof, "kernel_classes": classes,
+            "clocks": clocks.summary()}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, ms, p, spp = cpu_reference_rate(cfg, args.cpu_batch, args.cpu_steps, 1, 0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"oracle port of the reference PyTorch CPU path, {args.config} geometry, batch "
+                                          f"{args.cpu_batch}, {args.cpu_steps} Heun steps ({p:.0f} raw passes, {spp:.3f} "
+                                          f"s/pass), extrapolated to {EXPECTED_PASSES_256} passes per 256-step batch"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="vg", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=512, help="graphs per GPU per step")
+    ap.add_argument("--num-steps", type=int, default=256, help="EDM sampler steps (mcmc.num_steps)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--profile-stride", type=int, default=16)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+    else:
+        run_native(args, cfg, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,10 +97,10 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
                        const float* rc, const float* w_adj, const float* bias, const float* gamma,
                        const float* beta, const float* film, int film_ld, int film_off, int cond_uniform,
                        float* x0, int batch, int n, int c_e, int self_cond, int embed, cudaStream_t st);
-// node head: masked row mean of rep [B*n*n, E] bf16 -> MLP -> (precond) -> out_node [B, n, c_n]
-// w1t [E][E] and w2t [E][c_n] are the transposed nn.Linear weights (input-channel major)
-int launch_node_head(const bf16* rep, const uint8_t* flags, const float* w1t, const float* b1, const float* w2t,
-                     const float* b2, const float* x_node, const float* c_skip, const float* c_out,
+// node head: masked row mean of y = LN(x) [B*n*n, E] bf16 -> folded read_out -> MLP -> (precond) -> out_node [B, n, c_n]
+// fold_t [E][E], w1t [E][E] and w2t [E][c_n] are transposed (input-channel major)
+int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
+                     const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip, const float* c_out,
                      float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------

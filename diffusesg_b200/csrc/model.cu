@@ -32,6 +32,43 @@ void set_last_error(const char* fmt, ...) {
 }
 void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
 
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
+// ------------------------------------------------------------------------------------------------
+enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"gemm_tcgen05", "window_attention", "row_ln_film", "embed_heads_cond", "edm_step"};
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;        // between dsg_profile_begin and dsg_profile_stop
+static bool g_prof_pass = false;      // the current denoiser pass is being bracketed
+static int g_prof_stride = 1, g_prof_counter = 0;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static dsg_profile_class g_prof_tot[PC_COUNT];
+
+static cudaEvent_t prof_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+
+struct ProfScope {
+  bool active = false;
+  ProfRec rec;
+  cudaStream_t st;
+  ProfScope(bool enabled, int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+    if (!enabled) return;
+    rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
+    rec.e0 = prof_event(); rec.e1 = prof_event();
+    if (rec.e0 == nullptr || rec.e1 == nullptr) return;
+    active = cudaEventRecord(rec.e0, st) == cudaSuccess;
+  }
+  ~ProfScope() {
+    if (!active) return;
+    if (cudaEventRecord(rec.e1, st) == cudaSuccess) g_prof_recs.push_back(rec);
+  }
+};
+
 namespace {
 
 constexpr size_t kAlign = 256;
@@ -83,8 +120,8 @@ struct dsg_model {
   size_t film_w_off = 0, film_b_off = 0;     // contiguous [film_total, 512] and [film_total]
   // packed extras
   size_t w_adj_off = 0, w_rc_off = 0, fold_t1_off = 0, fold_f_off = 0, fold_b_off = 0, fold_tv_off = 0;
-  size_t adj_w2t_off = 0, adj_b2_off = 0, node_w1t_off = 0, node_w2t_off = 0;
-  Weight fold_w, adj_fc1;
+  size_t adj_w2t_off = 0, adj_b2_off = 0, adj_b1_off = 0, node_w1t_off = 0, node_w2t_off = 0, fold_ft_off = 0;
+  Weight adj_fc1;  // readout_adj_mlp.fc1 composed with the folded read_out chain
   size_t arena_bytes = 0;
   uint8_t* arena = nullptr;
   bool finalized = false;
@@ -272,7 +309,8 @@ int build(dsg_model* m) {
   m->fold_f_off = reserve(cur, static_cast<size_t>(E) * E * 4);
   m->fold_b_off = reserve(cur, static_cast<size_t>(E) * 4);
   m->fold_tv_off = reserve(cur, static_cast<size_t>(E) * 4);
-  reserve_weight(cur, m->fold_w, E, E);
+  m->fold_ft_off = reserve(cur, static_cast<size_t>(E) * E * 4);
+  m->adj_b1_off = reserve(cur, static_cast<size_t>(E) * 4);
   reserve_weight(cur, m->adj_fc1, E, E);
   m->adj_w2t_off = reserve(cur, static_cast<size_t>(E) * 8 * 4);
   m->adj_b2_off = reserve(cur, 8 * 4);
@@ -292,7 +330,7 @@ int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st
 struct Workspace {
   float *X, *T, *coef, *emb0, *emb1, *emb, *film, *rc;
   std::vector<float*> skip;
-  bf16 *Y, *QKV, *ATT, *H, *REP;
+  bf16 *Y, *QKV, *ATT, *H;
   size_t bytes;
 };
 
@@ -309,7 +347,6 @@ Workspace carve(const dsg_model* m, int batch, int n_cond, void* base) {
   w.QKV = static_cast<bf16*>(take(full * 3 * 2));
   w.ATT = static_cast<bf16*>(take(full * 2));
   w.H = static_cast<bf16*>(take(full * 4 * 2));
-  w.REP = static_cast<bf16*>(take(full * 2));
   for (int s = 0; s + 1 < m->nl; ++s) w.skip.push_back(static_cast<float*>(take((full >> (s + 1)) * 4)));
   w.coef = static_cast<float*>(take(static_cast<size_t>(4) * batch * 4));
   w.emb0 = static_cast<float*>(take(static_cast<size_t>(n_cond) * m->E * 4));
@@ -337,6 +374,12 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   if (extra) p = *extra; else memset(&p, 0, sizeof(p));
   p.M = static_cast<int>(rows); p.N = W.N; p.K = W.K;
   p.bias = bias; p.res = res; p.out = out; p.ldo = W.N;
+  const double mn = static_cast<double>(rows) * W.N;
+  const double out_bytes = epi == EPI_ADJ_HEAD ? static_cast<double>(rows) * (extra ? extra->c_e : 0) * 4
+                                               : mn * ((epi == EPI_BF16 || epi == EPI_GELU_BF16) ? 2 : 4);
+  ProfScope ps(g_prof_pass, PC_GEMM, 2.0 * mn * W.K,
+               static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
+                   (epi == EPI_RES_F32 ? mn * 4 : 0), st);
   return launch_gemm(&it->second, &W.tmap, epi, p, st);
 }
 
@@ -346,6 +389,14 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
     if (_rc) return _rc;     \
   } while (0)
 
+// same, bracketed by a pair of CUDA events when this pass is being profiled (algorithmic flops / bytes attached)
+#define DSG_TRY_P(cls, flops, bytes, expr)                                    \
+  do {                                                                        \
+    ProfScope _ps(g_prof_pass, cls, flops, bytes, st);                        \
+    int _rc = (expr);                                                         \
+    if (_rc) return _rc;                                                      \
+  } while (0)
+
 int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
               cudaStream_t st) {
   const int C = b.dim;
@@ -353,16 +404,18 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   const long long rows = static_cast<long long>(batch) * L;
   const std::string& p = b.prefix;
   // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
-  DSG_TRY(launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform, m->f32(p + ".norm1.weight"),
-                         m->f32(p + ".norm1.bias"), batch, L, C, st));
+  const double rc = static_cast<double>(rows) * C;
+  DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
+                                               m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"), batch, L, C, st));
   DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
-  DSG_TRY(launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
-                                  b.heads, st));
+  DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
+            launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
+                                    b.heads, st));
   // x = x + proj(attn)                                                   (:137, :272)
   DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
   // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
-  DSG_TRY(launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
+  DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
   DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));
   DSG_TRY(gemm(m, w.H, rows, b.fc2, EPI_RES_F32, m->f32(p + ".mlp.fc2.bias"), w.X, w.X, st));
   return DSG_OK;
@@ -473,10 +526,15 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
   DSG_TRY(launch_small_mm(m->f32("read_out.2.weight"), t1, ff, E, 0, st));
   DSG_TRY(launch_small_mv(m->f32("read_out.1.weight"), m->f32("read_out.0.bias"), m->f32("read_out.1.bias"), tv, E, st));
   DSG_TRY(launch_small_mv(m->f32("read_out.2.weight"), tv, m->f32("read_out.2.bias"), m->at<float>(m->fold_b_off), E, st));
-  DSG_TRY(launch_pack_bf16(ff, m->at<bf16>(m->fold_w.offset), static_cast<int64_t>(E) * E, 0, 1.f, st));
-  DSG_TRY(make_tmap_bf16(&m->fold_w.tmap, m->arena + m->fold_w.offset, E, E, gemm_block_n(E)));
-  // heads
-  DSG_TRY(pack_weight(m, m->adj_fc1, "readout_adj_mlp.fc1.weight", st));
+  // adj head: fc1 composed with the folded read_out (fp32 composition, one bf16 rounding of the product), so the
+  // shared representation [B, 96, N, N] of :761 is never written; the node head pools LN(x) and applies the
+  // fold after the (linear) masked row mean
+  DSG_TRY(launch_small_mm(m->f32("readout_adj_mlp.fc1.weight"), ff, t1, E, 0, st));
+  DSG_TRY(launch_pack_bf16(t1, m->at<bf16>(m->adj_fc1.offset), static_cast<int64_t>(E) * E, 0, 1.f, st));
+  DSG_TRY(make_tmap_bf16(&m->adj_fc1.tmap, m->arena + m->adj_fc1.offset, E, E, gemm_block_n(E)));
+  DSG_TRY(launch_small_mv(m->f32("readout_adj_mlp.fc1.weight"), m->at<float>(m->fold_b_off),
+                          m->f32("readout_adj_mlp.fc1.bias"), m->at<float>(m->adj_b1_off), E, st));
+  DSG_TRY(launch_transpose(ff, m->at<float>(m->fold_ft_off), E, E, 0, E, E, st));
   DSG_CUDA_CHECK(cudaMemsetAsync(m->at<float>(m->adj_w2t_off), 0, static_cast<size_t>(E) * 8 * 4, st));
   DSG_CUDA_CHECK(cudaMemsetAsync(m->at<float>(m->adj_b2_off), 0, 8 * 4, st));
   DSG_TRY(launch_transpose(m->f32("readout_adj_mlp.fc2.weight"), m->at<float>(m->adj_w2t_off), m->cfg.c_e, E, 0, E, 8, st));
@@ -524,14 +582,17 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     labels = w.coef + 3 * B;
     label_stride = 1;
   }
-  DSG_TRY(launch_cond(labels, label_stride, a->n_cond, m->f32("map_layer0.weight"),
+  g_prof_pass = g_prof_on && (g_prof_counter++ % g_prof_stride == 0);
+  struct ProfPassGuard { ~ProfPassGuard() { g_prof_pass = false; } } prof_pass_guard;
+  const double px = static_cast<double>(B) * N * N;
+  DSG_TRY_P(PC_EMBED_HEAD, 0, 0, launch_cond(labels, label_stride, a->n_cond, m->f32("map_layer0.weight"),
                       m->f32("map_layer0.bias"), m->f32("map_layer1.weight"), m->f32("map_layer1.bias"),
                       m->at<float>(m->film_w_off), m->at<float>(m->film_b_off), m->film_total, w.emb0, w.emb1, w.emb,
                       w.film, E, st));
   // patch embedding straight from (adj, node): the [B, cin, N, N] grid of :784-802 is never built
-  DSG_TRY(launch_node_proj(a->node, a->sc_node, c_in, m->at<float>(m->w_rc_off), w.rc, B, N, m->cfg.c_n,
+  DSG_TRY_P(PC_EMBED_HEAD, 0, 0, launch_node_proj(a->node, a->sc_node, c_in, m->at<float>(m->w_rc_off), w.rc, B, N, m->cfg.c_n,
                            m->cfg.self_condition, E, st));
-  DSG_TRY(launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
+  DSG_TRY_P(PC_EMBED_HEAD, 0, px * (m->planes_adj * 4 + E * 4), launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
                              m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
                              m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
                              m->cfg.self_condition, E, st));
@@ -549,7 +610,8 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     if (s < m->nl - 1) {
       const Merge& g = m->merges[s];
       const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
-      DSG_TRY(launch_merge_ln(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), B, g.res, g.C, st));
+      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows) * 4 * g.C * 6,
+                launch_merge_ln(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), B, g.res, g.C, st));
       DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
       DSG_STAGE_DONE();
     }
@@ -563,9 +625,9 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
       const Breakup& bu = m->breakups[u - 1];
       const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
       // the low-resolution stream lives in X unless no block ran since the last merge (cannot happen: depth >= 1)
-      DSG_TRY(launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
       DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
-      DSG_TRY(launch_breakup_ln(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_breakup_ln(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
                                 m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"), B, bu.res,
                                 bu.D, st));
       DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
@@ -578,8 +640,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   }
   // read-out                                                                 (:758-761, :806-825)
   const long long pixels = static_cast<long long>(B) * N * N;
-  DSG_TRY(launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
-  DSG_TRY(gemm(m, w.Y, pixels, m->fold_w, EPI_BF16, m->at<float>(m->fold_b_off), nullptr, w.REP, st));
+  DSG_TRY_P(PC_ROW, 0, px * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
   GemmParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.w2t = m->at<float>(m->adj_w2t_off);
@@ -590,14 +651,46 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   hp.x_adj = a->mode == 1 ? a->adj : nullptr;
   hp.c_skip = c_skip;
   hp.c_out = c_out;
-  DSG_TRY(gemm(m, w.REP, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->f32("readout_adj_mlp.fc1.bias"), nullptr, a->out_adj, st, &hp));
-  DSG_TRY(launch_node_head(w.REP, a->flags, m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
+  DSG_TRY(gemm(m, w.Y, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->at<float>(m->adj_b1_off), nullptr, a->out_adj, st, &hp));
+  DSG_TRY_P(PC_EMBED_HEAD, 0, px * E * 2, launch_node_head(w.Y, a->flags, m->at<float>(m->fold_ft_off), m->at<float>(m->fold_b_off),
+                           m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
                            m->at<float>(m->node_w2t_off), m->f32("readout_node_mlp.fc2.bias"),
                            a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st));
   return DSG_OK;
 }
 
 void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
+
+int dsg_profile_begin(int pass_stride) {
+  DSG_REQUIRE(pass_stride >= 1, "profile_begin: stride %d", pass_stride);
+  for (int c = 0; c < PC_COUNT; ++c) {
+    memset(&g_prof_tot[c], 0, sizeof(g_prof_tot[c]));
+    strncpy(g_prof_tot[c].name, kProfNames[c], sizeof(g_prof_tot[c].name) - 1);
+  }
+  g_prof_stride = pass_stride;
+  g_prof_counter = 0;
+  g_prof_on = true;
+  return DSG_OK;
+}
+
+int dsg_profile_read(dsg_profile_class* out, int max_classes, int* n_classes) {
+  for (ProfRec& r : g_prof_recs) {
+    float ms = 0.f;
+    DSG_CUDA_CHECK(cudaEventSynchronize(r.e1));
+    DSG_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    dsg_profile_class& t = g_prof_tot[r.cls];
+    t.launches += 1; t.ms += ms; t.flops += r.flops; t.bytes += r.bytes;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  if (out != nullptr)
+    for (int c = 0; c < PC_COUNT && c < max_classes; ++c) out[c] = g_prof_tot[c];
+  if (n_classes) *n_classes = PC_COUNT;
+  return DSG_OK;
+}
+
+void dsg_profile_stop(void) { g_prof_on = false; g_prof_pass = false; }
 
 int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name, size_t* offset, size_t* bytes) {
   DSG_REQUIRE(m && name && offset && bytes && batch > 0 && n_cond > 0, "debug_buffer: bad argument");
@@ -606,7 +699,7 @@ int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name
   const size_t full = static_cast<size_t>(batch) * m->N * m->N * m->E;
   struct { const char* n; const void* p; size_t b; } tab[] = {
       {"X", w.X, full * 4}, {"T", w.T, full * 4}, {"Y", w.Y, full * 2}, {"QKV", w.QKV, full * 6},
-      {"ATT", w.ATT, full * 2}, {"H", w.H, full * 8}, {"REP", w.REP, full * 2},
+      {"ATT", w.ATT, full * 2}, {"H", w.H, full * 8},
       {"skip0", w.skip.size() > 0 ? w.skip[0] : nullptr, full * 2}, {"skip1", w.skip.size() > 1 ? w.skip[1] : nullptr, full},
       {"skip2", w.skip.size() > 2 ? w.skip[2] : nullptr, full / 2}, {"coef", w.coef, static_cast<size_t>(16) * batch},
       {"emb", w.emb, static_cast<size_t>(n_cond) * 2048}, {"film", w.film, static_cast<size_t>(n_cond) * m->film_total * 4},
@@ -625,6 +718,8 @@ int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, 
                      const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch, int c_e, int n,
                      int c_n, dsg_stream_t stream) {
   DSG_REQUIRE(adj && node && eps_adj && eps_node && flags && adj_hat && node_hat, "edm_pre_step: null tensor");
+  const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
+  ProfScope ps(g_prof_on, PC_EDM, 2 * el, 12 * el, static_cast<cudaStream_t>(stream));
   return launch_edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef, adj_hat, node_hat, batch, c_e, n, c_n,
                              static_cast<cudaStream_t>(stream));
 }
@@ -635,6 +730,8 @@ int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* 
                       dsg_stream_t stream) {
   DSG_REQUIRE(adj_hat && node_hat && d1_adj && d1_node && flags && adj_next && node_next, "edm_post_step: null tensor");
   DSG_REQUIRE((d2_adj == nullptr) == (d2_node == nullptr), "edm_post_step: d2_adj / d2_node must both be given or both NULL");
+  const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
+  ProfScope ps(g_prof_on, PC_EDM, (d2_adj ? 11 : 4) * el, (d2_adj ? 16 : 12) * el, static_cast<cudaStream_t>(stream));
   return launch_edm_post_step(adj_hat, node_hat, d1_adj, d1_node, d2_adj, d2_node, flags, inv_t_hat, h, inv_t_prime,
                               adj_next, node_next, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
 }

@@ -378,9 +378,11 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
 // ---------------------------------------------------------------------------------------------------------
 // node read-out: masked row mean -> MLP -> mask (-> EDM output preconditioning)   (:812-822, precond.py:103-105)
 // ---------------------------------------------------------------------------------------------------------
-// One CTA (128 threads) per (b, i).  rep is the shared representation [B n n, E] (bf16).
+// One CTA (128 threads) per (b, i).  y is LN(x) of the last stage [B n n, E] (bf16); the folded read_out map
+// (fold_t [E][E] input-major, fold_b) is applied after pooling: mean_j m_ij (F y_ij + f) = F mean_j(m_ij y_ij) + f cnt/n.
 __global__ void __launch_bounds__(128)
-node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags, const float* __restrict__ w1t,
+node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags, const float* __restrict__ fold_t,
+                 const float* __restrict__ fold_b, const float* __restrict__ w1t,
                  const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                  const float* __restrict__ x_node, const float* __restrict__ c_skip, const float* __restrict__ c_out,
                  float* __restrict__ out_node, int n, int c_n, int embed) {
@@ -397,9 +399,17 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
   if (e < embed) {
     const bf16* p = rep + static_cast<size_t>(bi) * n * embed + e;
     float s = 0.f;
+    int cnt = 0;
     for (int j = 0; j < n; ++j)
-      if (flags[b * n + j]) s += __bfloat162float(p[static_cast<size_t>(j) * embed]);
-    pooled[e] = s / n;  // mean over the full row length N, not over the valid count (:813)
+      if (flags[b * n + j]) { s += __bfloat162float(p[static_cast<size_t>(j) * embed]); ++cnt; }
+    hidden[e] = s / n;  // mean over the full row length N, not over the valid count (:813)
+    pooled[e] = fold_b[e] * (static_cast<float>(cnt) / n);
+  }
+  __syncthreads();
+  if (e < embed) {
+    float s = pooled[e];
+    for (int k = 0; k < embed; ++k) s = fmaf(fold_t[k * embed + e], hidden[k], s);
+    pooled[e] = s;
   }
   __syncthreads();
   if (e < embed) {
@@ -533,12 +543,12 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
   return DSG_OK;
 }
 
-int launch_node_head(const bf16* rep, const uint8_t* flags, const float* w1t, const float* b1, const float* w2t,
-                     const float* b2, const float* x_node, const float* c_skip, const float* c_out, float* out_node,
-                     int batch, int n, int c_n, int embed, cudaStream_t st) {
+int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
+                     const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip,
+                     const float* c_out, float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st) {
   DSG_REQUIRE(embed <= 128 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
-  node_head_kernel<<<batch * n, 128, 0, st>>>(rep, flags, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, n, c_n,
-                                              embed);
+  node_head_kernel<<<batch * n, 128, 0, st>>>(rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out,
+                                              out_node, n, c_n, embed);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

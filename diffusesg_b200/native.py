@@ -36,6 +36,11 @@ class DsgForwardArgs(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class DsgProfileClass(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 _SIGNATURES = {
     "dsg_abi_version": (C.c_int, []),
     "dsg_last_error": (C.c_char_p, []),
@@ -56,6 +61,9 @@ _SIGNATURES = {
     "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_profile_begin": (C.c_int, [C.c_int]),
+    "dsg_profile_read": (C.c_int, [C.POINTER(DsgProfileClass), C.c_int, C.POINTER(C.c_int)]),
+    "dsg_profile_stop": (None, []),
     "dsg_debug_set_stop_after": (None, [C.c_int]),
     "dsg_debug_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
@@ -94,6 +102,23 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().dsg_launch_count())
+
+
+def profile_begin(pass_stride: int = 1) -> None:
+    check(lib().dsg_profile_begin(pass_stride), "dsg_profile_begin")
+
+
+def profile_read() -> dict:
+    """{class name: dict(launches, ms, flops, bytes)} accumulated since profile_begin (waits for the events)."""
+    arr = (DsgProfileClass * 8)()
+    n = C.c_int()
+    check(lib().dsg_profile_read(arr, 8, C.byref(n)), "dsg_profile_read")
+    return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=arr[i].ms, flops=arr[i].flops,
+                                       bytes=arr[i].bytes) for i in range(n.value)}
+
+
+def profile_stop() -> None:
+    lib().dsg_profile_stop()
 
 
 def stream_ptr(device=None) -> int:

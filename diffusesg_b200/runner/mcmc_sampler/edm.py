@@ -92,6 +92,24 @@ class NodeAdjEDMSampler:
     def sample(self, model, node_flags, init_adjs=None, init_nodes=None, sanity_check_gt_adjs=None,
                sanity_check_gt_nodes=None, flag_interim_adjs=False, max_num_interim_adjs=None, flag_use_double=False,
                flag_node_multi_channel=False, flag_adj_multi_channel=False, num_node_chan=150, num_edge_chan=51):
+        """Reference entry point (edm.py:291-445): returns CPU tensors."""
+        out = self.sample_on_device(model, node_flags, init_adjs, init_nodes, sanity_check_gt_adjs,
+                                    sanity_check_gt_nodes, flag_interim_adjs, max_num_interim_adjs, flag_use_double,
+                                    flag_adj_multi_channel, num_node_chan, num_edge_chan)
+        adjs, nodes, snaps_a, snaps_n = out
+        adjs_cpu, nodes_cpu = adjs.cpu(), nodes.cpu()  # synchronises the stream: the pinned snapshots are complete too
+        if flag_interim_adjs:
+            if flag_adj_multi_channel:
+                return adjs_cpu, nodes_cpu, [None], torch.stack(snaps_n)
+            return adjs_cpu, nodes_cpu, torch.stack(snaps_a), torch.stack(snaps_n)
+        return adjs_cpu, nodes_cpu
+
+    @torch.no_grad()
+    def sample_on_device(self, model, node_flags, init_adjs=None, init_nodes=None, sanity_check_gt_adjs=None,
+                         sanity_check_gt_nodes=None, flag_interim_adjs=False, max_num_interim_adjs=None,
+                         flag_use_double=False, flag_adj_multi_channel=False, num_node_chan=150, num_edge_chan=51):
+        """The sampling loop proper; the final state stays on the device (no host sync anywhere inside).
+        Returns (adjs, nodes, pinned adjacency snapshots, pinned node snapshots)."""
         if flag_use_double:
             raise NotImplementedError("flag_use_double: the native state is fp32 (the reference default)")
         if isinstance(model, (nn.DataParallel, nn.parallel.DistributedDataParallel)):
@@ -160,12 +178,7 @@ class NodeAdjEDMSampler:
                 snaps_n.append(self._snapshot(nodes))
         self.last_raw_passes = getattr(model, "raw_passes", 0) - passes0
         logging.info("Done with EDM-NodeAdj MCMC.")
-        adjs_cpu, nodes_cpu = adjs.cpu(), nodes.cpu()  # synchronises the stream: snapshots are complete too
-        if flag_interim_adjs:
-            if flag_adj_multi_channel:
-                return adjs_cpu, nodes_cpu, [None], torch.stack(snaps_n)
-            return adjs_cpu, nodes_cpu, torch.stack(snaps_a), torch.stack(snaps_n)
-        return adjs_cpu, nodes_cpu
+        return adjs, nodes, snaps_a, snaps_n
 
     @staticmethod
     def _snapshot(t: torch.Tensor) -> torch.Tensor:

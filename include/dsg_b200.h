@@ -144,6 +144,22 @@ DSG_API int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const
 DSG_API int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
                          int window, int shift, int heads, dsg_stream_t stream);
 
+/* ---- per-kernel-class timing (bench.py roofline numbers) ------------------------------------------------------- */
+/* While enabled, every pass_stride-th dsg_denoiser_forward and every dsg_edm_* call brackets each of its kernel
+ * launches with a pair of CUDA events on the launching stream.  dsg_profile_read waits for the recorded events
+ * and returns per-class totals since dsg_profile_begin: launches, device milliseconds, ALGORITHMIC flops and
+ * bytes (2MNK per GEMM; each distinct tensor touched once per elementwise kernel).  Process-global, one thread. */
+typedef struct dsg_profile_class {
+  char name[24];
+  uint64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} dsg_profile_class;
+DSG_API int dsg_profile_begin(int pass_stride);
+DSG_API int dsg_profile_read(dsg_profile_class* out, int max_classes, int* n_classes);
+DSG_API void dsg_profile_stop(void);
+
 /* ---- test hooks (used by tests/ to localise a parity failure; not part of the product path) ------------------- */
 /* Leave dsg_denoiser_forward after n_stages schedule stages (0: patch embedding, then one per Swin block /
  * PatchMerging / PatchBreakup in execution order); -1 restores the full schedule.  Process-global. */
