@@ -206,6 +206,193 @@ window_attention_kernel(const bf16* __restrict__ qkv, const float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast path for 64-token windows (every block of the Visual Genome geometry).
+//
+// One CTA = 4 warps, one head, a run of kWPC consecutive windows.  The relative-position bias of the head sits in
+// registers for the whole run (32 floats per thread: exactly the score fragment layout), q/k/v of the next
+// window stream into the other shared-memory buffer with cp.async while the current one is computed, v is
+// consumed row-major through ldmatrix.trans, and the output tile is staged through the (already consumed) q
+// buffer so that every token receives one 64-byte store.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWPC = 8;
+
+DSG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+DSG_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+DSG_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+DSG_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+
+DSG_DEVICE int window_token_row(int gw, int t, int res, int shift, int nwx_log_free_nW, int nwx) {
+  // gw = b * nW + win; token t = ty * 8 + tx of the (rolled) window -> row of the un-rolled [B*res*res] token matrix
+  const int b = gw / nwx_log_free_nW, win = gw - b * nwx_log_free_nW;
+  const int wy = win / nwx, wx = win - wy * nwx;
+  int oy = wy * 8 + (t >> 3) + shift; if (oy >= res) oy -= res;
+  int ox = wx * 8 + (t & 7) + shift; if (ox >= res) ox -= res;
+  return (b * res + oy) * res + ox;
+}
+
+__global__ void __launch_bounds__(128)
+window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
+                          bf16* __restrict__ out, int res, int shift, int heads, int total_windows) {
+  constexpr int T = 64;
+  __shared__ __align__(16) bf16 sbuf[2][3][T * QK_PITCH];  // [buffer][q, k, v][token][40]
+  const int nwx = res >> 3;
+  const int nW = nwx * nwx;
+  const int h = blockIdx.x % heads;
+  const int w_begin = (blockIdx.x / heads) * kWPC;
+  const int w_end = min(total_windows, w_begin + kWPC);
+  const int C = heads * HD;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+
+  auto issue_loads = [&](int gw, int buf) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int idx = tid + 128 * k;  // 64 tokens x 3 parts x 4 chunks of 16 bytes
+      const int t = idx / 12;
+      const int rem = idx - t * 12;
+      const int part = rem >> 2, chunk = rem & 3;
+      const int row = window_token_row(gw, t, res, shift, nW, nwx);
+      cp_async16(&sbuf[buf][part][t * QK_PITCH + chunk * 8],
+                 qkv + static_cast<size_t>(row) * (3 * C) + part * C + h * HD + chunk * 8);
+    }
+    cp_async_commit();
+  };
+
+  issue_loads(w_begin, 0);
+
+  // relative-position bias of this head, in score-fragment layout
+  float bia[8][4];
+  {
+    const float* bh = bias + static_cast<size_t>(h) * T * T;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(bh + r0 * T + nt * 8 + 2 * t4));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bh + r1 * T + nt * 8 + 2 * t4));
+      bia[nt][0] = a.x; bia[nt][1] = a.y; bia[nt][2] = b.x; bia[nt][3] = b.y;
+    }
+  }
+
+  for (int gw = w_begin; gw < w_end; ++gw) {
+    const int buf = (gw - w_begin) & 1;
+    if (gw + 1 < w_end) {
+      issue_loads(gw + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    bf16* sQ = sbuf[buf][0];
+    const bf16* sK = sbuf[buf][1];
+    const bf16* sV = sbuf[buf][2];
+
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4]);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4]);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = bia[nt][0]; s[nt][1] = bia[nt][1]; s[nt][2] = bia[nt][2]; s[nt][3] = bia[nt][3];
+      const int key = nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t kb[2];
+        kb[0] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4]);
+        kb[1] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4 + 8]);
+        mma_m16n8k16_bf16(s[nt], qa[ks], kb);
+      }
+    }
+    if (mask != nullptr) {
+      const float* mw = mask + static_cast<size_t>(gw % nW) * T * T;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(mw + r0 * T + nt * 8 + 2 * t4));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(mw + r1 * T + nt * 8 + 2 * t4));
+        s[nt][0] += a.x; s[nt][1] += a.y; s[nt][2] += b.x; s[nt][3] += b.y;
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float m0s = m0 * kLog2e, m1s = m1 * kLog2e;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(fmaf(s[nt][0], kLog2e, -m0s)); s[nt][1] = exp2f(fmaf(s[nt][1], kLog2e, -m0s));
+      s[nt][2] = exp2f(fmaf(s[nt][2], kLog2e, -m1s)); s[nt][3] = exp2f(fmaf(s[nt][3], kLog2e, -m1s));
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    float o[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
+      pa[1] = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
+      pa[2] = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      // lanes 0-7 / 8-15 address keys kt*16 + 0..7 / 8..15 at dims n0, lanes 16-31 the same keys at dims n0 + 8
+      const int krow = kt * 16 + (lane & 15);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, &sV[krow * QK_PITCH + np * 16 + ((lane >> 4) << 3)]);
+        mma_m16n8k16_bf16(o[2 * np], pa, reinterpret_cast<const uint32_t(&)[2]>(vb[0]));
+        mma_m16n8k16_bf16(o[2 * np + 1], pa, reinterpret_cast<const uint32_t(&)[2]>(vb[2]));
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // stage the 16 x 32 output slab of this warp in its own (consumed) q rows, then one 64-byte store per token
+    __syncwarp();
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      *reinterpret_cast<uint32_t*>(&sQ[r0 * QK_PITCH + nd * 8 + 2 * t4]) = pack_bf16x2(o[nd][0] * i0, o[nd][1] * i0);
+      *reinterpret_cast<uint32_t*>(&sQ[r1 * QK_PITCH + nd * 8 + 2 * t4]) = pack_bf16x2(o[nd][2] * i1, o[nd][3] * i1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = lane + 32 * k;  // 16 tokens x 4 chunks
+      const int t = warp * 16 + (idx >> 2), chunk = idx & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(&sQ[t * QK_PITCH + chunk * 8]);
+      const int row = window_token_row(gw, t, res, shift, nW, nwx);
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * C + h * HD + chunk * 8) = v;
+    }
+    __syncthreads();  // everyone is done with this buffer before the loads of window gw + 2 overwrite it
+  }
+}
+
 template <int T_PAD>
 int launch_t(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res, int window,
              int shift, int heads, cudaStream_t st) {
@@ -233,6 +420,15 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
   DSG_REQUIRE((shift > 0) == (mask != nullptr), "attention: a shifted block needs its mask (and only it)");
   const int T = window * window;
   DSG_REQUIRE(T % 2 == 0, "attention: odd window token count %d", T);
+  if (window == 8) {
+    const long long total = static_cast<long long>(batch) * (res / 8) * (res / 8);
+    const long long grid = ((total + kWPC - 1) / kWPC) * heads;
+    DSG_REQUIRE(grid > 0 && grid < 2147483647LL, "attention: grid out of range");
+    window_attention64_kernel<<<static_cast<unsigned>(grid), 128, 0, st>>>(qkv, bias, mask, out, res, shift, heads,
+                                                                         static_cast<int>(total));
+    DSG_LAUNCH_CHECK();
+    return DSG_OK;
+  }
   if (T <= 16) return launch_t<16>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
   if (T <= 64) return launch_t<64>(qkv, bias, mask, out, batch, res, window, shift, heads, st);
   if (T <= 112) return launch_t<112>(qkv, bias, mask, out, batch, res, window, shift, heads, st);

@@ -62,8 +62,20 @@ DSG_DEVICE float warp_sum(float v) {
 
 DSG_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-// exact (erf) GELU, the reference's nn.GELU() default (model/diffusesg/diffusesg.py:10,15)
-DSG_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact (erf) GELU, the reference's nn.GELU() default (model/diffusesg/diffusesg.py:10,15).
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result):
+// 2 MUFU + ~12 FP32 ops instead of the ~30-instruction branchy erff().
+DSG_DEVICE float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * exp2f(-1.4426950408889634f * z * z);  // 1 - erf(z)
+  const float erf_abs = 1.0f - e;
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 DSG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -6,8 +6,10 @@
 //   warp 0      TMA producer: 128 x 64 A box + BN x 64 W box per stage (128-byte swizzle), kStages ring
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per stage; accumulators
 //               live in TMEM, double buffered so the epilogue of tile i overlaps the main loop of i+1
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / GELU / residual /
-//               fused adj read-out head, vectorised global stores
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / GELU, staged through a swizzled
+//               shared-memory chunk (128 rows x 32 columns) and written with TMA bulk stores; the residual
+//               epilogue x += acc + bias is a TMA reduce-add (the L2 does the read-modify-write, the tile of x is
+//               never loaded by the SM); the adj read-out head epilogue writes its c_e planes directly
 //
 // Replaces the cuBLAS sgemm behind every nn.Linear / 1x1 conv of the reference denoiser
 // (model/diffusesg/diffusesg.py:20-24 Mlp, :115 qkv, :137 proj, :334 reduction, :385/:402 breakup linears,
@@ -20,7 +22,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;        // TMA warp, MMA warp, 2 epilogue groups of 4 warps
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN>
@@ -30,19 +32,22 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int ACC_STRIDE = (BN == 192) ? 256 : 128;  // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;       // 512 / 256
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int OUT_CHUNK_BYTES = 128 * 32 * 4;  // 128 rows x 32 fp32 columns (bf16 uses half of it)
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + 4 * OUT_CHUNK_BYTES + 256 /*barriers*/;
 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+            const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::STAGE_BYTES);
+  uint8_t* sOut = smem + kStages * C::STAGE_BYTES;  // 2 groups x 2 x 16 KB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 4 * C::OUT_CHUNK_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -62,6 +67,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if (EPI != EPI_ADJ_HEAD) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -130,106 +136,134 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (acc == 0) acc_ph ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (2 groups x 4 warps)
+    // group g drains accumulator g, i.e. every other tile of this CTA, with its own staging buffers
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int acc = 0;
+    const int grp = (warp - 2) >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    constexpr bool kOutBf16 = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
+    uint8_t* sOutG = sOut + grp * 2 * C::OUT_CHUNK_BYTES;
+    const int acc = grp;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int chunk_no = 0;  // running count of staged chunks -> staging buffer parity
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tcgen05_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
-      float y[8];
       if (EPI == EPI_ADJ_HEAD) {
+        const int row = m_blk * BM + r_in_tile;
+        float y[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) y[c] = s_b2[c];
-      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c0, r);
-        tmem_ld_wait();
-        const int col = n_blk * BN + c0;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (EPI == EPI_GELU_BF16 || EPI == EPI_ADJ_HEAD) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-          if (row_ok) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack_bf16x2(v[j], v[j + 1]);
-              w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = w;
-            }
-          }
-        } else if (EPI == EPI_RES_F32 || EPI == EPI_F32) {
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
-            if (EPI == EPI_RES_F32) {
-              const float* rs = p.res + static_cast<size_t>(row) * p.ldo + col;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(rs + j);
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        } else {  // EPI_ADJ_HEAD: second linear of the read-out MLP, 96 -> c_e (padded to 8)
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
+            const float v = gelu_erf(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j));
             const float4 wa = *reinterpret_cast<const float4*>(&s_w2t[(c0 + j) * 8]);
             const float4 wb = *reinterpret_cast<const float4*>(&s_w2t[(c0 + j) * 8 + 4]);
-            y[0] = fmaf(wa.x, v[j], y[0]); y[1] = fmaf(wa.y, v[j], y[1]);
-            y[2] = fmaf(wa.z, v[j], y[2]); y[3] = fmaf(wa.w, v[j], y[3]);
-            y[4] = fmaf(wb.x, v[j], y[4]); y[5] = fmaf(wb.y, v[j], y[5]);
-            y[6] = fmaf(wb.z, v[j], y[6]); y[7] = fmaf(wb.w, v[j], y[7]);
+            y[0] = fmaf(wa.x, v, y[0]); y[1] = fmaf(wa.y, v, y[1]);
+            y[2] = fmaf(wa.z, v, y[2]); y[3] = fmaf(wa.w, v, y[3]);
+            y[4] = fmaf(wb.x, v, y[4]); y[5] = fmaf(wb.y, v, y[5]);
+            y[6] = fmaf(wb.z, v, y[6]); y[7] = fmaf(wb.w, v, y[7]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (row < p.M) {
+          // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
+          // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
+          const int n = p.n_img;
+          const int nn = n * n;
+          const int b = row / nn;
+          const int ij = row - b * nn;
+          const int i = ij / n, j = ij - i * n;
+          const bool ok = p.flags[b * n + i] != 0 && p.flags[b * n + j] != 0;
+          float cs = 0.f, co = 1.f;
+          if (p.x_adj != nullptr) { cs = p.c_skip[b]; co = p.c_out[b]; }
+          for (int c = 0; c < p.c_e; ++c) {
+            const size_t o = (static_cast<size_t>(b) * p.c_e + c) * nn + ij;
+            float val = y[c];
+            if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs, p.x_adj[o]), __fmul_rn(co, val));
+            reinterpret_cast<float*>(p.out)[o] = ok ? val : 0.f;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_no) {
+          uint8_t* buf = sOutG + (chunk_no & 1) * C::OUT_CHUNK_BYTES;
+          // the bulk store that last read this staging buffer (two chunks ago) must have drained it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 >= BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          const int col = n_blk * BN + c0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (kOutBf16) {
+            // 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+            uint8_t* rowp = buf + r_in_tile * 64;
+            const int sw = (r_in_tile >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 w;
+              w.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+              w.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+              w.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+              w.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+              *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = w;
+            }
+          } else {
+            // 128-byte rows, CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk index ^= row & 7
+            uint8_t* rowp = buf + r_in_tile * 128;
+            const int sw = r_in_tile & 7;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          if (issuer) {
+            if (EPI == EPI_RES_F32) {
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(buf)), "r"(col), "r"(m_blk * BM)
+                           : "memory");
+            } else {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(buf)), "r"(col), "r"(m_blk * BM)
+                           : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (EPI == EPI_ADJ_HEAD && row_ok) {
-        // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
-        // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
-        const int n = p.n_img;
-        const int nn = n * n;
-        const int b = row / nn;
-        const int ij = row - b * nn;
-        const int i = ij / n, j = ij - i * n;
-        const bool ok = p.flags[b * n + i] != 0 && p.flags[b * n + j] != 0;
-        float cs = 0.f, co = 1.f;
-        if (p.x_adj != nullptr) { cs = p.c_skip[b]; co = p.c_out[b]; }
-        for (int c = 0; c < p.c_e; ++c) {
-          const size_t o = (static_cast<size_t>(b) * p.c_e + c) * nn + ij;
-          float val = y[c];
-          if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs, p.x_adj[o]), __fmul_rn(co, val));
-          reinterpret_cast<float*>(p.out)[o] = ok ? val : 0.f;
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_ph ^= 1;
+      acc_ph ^= 1;
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -267,7 +301,8 @@ int num_sms() {
 }
 
 template <int BN, int EPI>
-int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const GemmParams& p, cudaStream_t st) {
+int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, const GemmParams& p,
+             cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -276,40 +311,56 @@ int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const GemmParams& p
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, p);
+  gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
 
 }  // namespace
 
-int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes, int box_cols,
+                 int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return DSG_ERR_CUDA;
   }
-  DSG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (cols * 2) % 16 == 0 && box_rows > 0 && box_rows <= 256,
-              "make_tmap_bf16: unaligned base/pitch or bad box (rows=%lld cols=%lld box=%d)", (long long)rows,
+  const int inner = box_cols * elem_bytes;
+  DSG_REQUIRE((elem_bytes == 2 || elem_bytes == 4) && (inner == 64 || inner == 128),
+              "make_tmap_2d: box of %d x %d-byte elements (inner extent must be 64 or 128 bytes)", box_cols, elem_bytes);
+  DSG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (cols * elem_bytes) % 16 == 0 && box_rows > 0 &&
+                  box_rows <= 256,
+              "make_tmap_2d: unaligned base/pitch or bad box (rows=%lld cols=%lld box_rows=%d)", (long long)rows,
               (long long)cols, box_rows);
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box_rows=%d)", (int)r,
-                   (long long)rows, (long long)cols, box_rows);
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box=%dx%d)", (int)r,
+                   (long long)rows, (long long)cols, box_cols, box_rows);
     return DSG_ERR_CUDA;
   }
   return DSG_OK;
 }
 
+int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  return make_tmap_2d(map, base, rows, cols, 2, BK, box_rows);
+}
+
+int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int epi) {
+  const bool bf = (epi == EPI_BF16 || epi == EPI_GELU_BF16);
+  return make_tmap_2d(map, base, rows, cols, bf ? 2 : 4, 32, BM);
+}
+
 int gemm_block_n(int N) { return (N % 192 == 0) ? 192 : 96; }
 
-int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, int epi, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,
+                cudaStream_t st) {
   DSG_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.N % 96 == 0 && p.K % 16 == 0,
               "gemm: unsupported shape M=%d N=%d K=%d (N %% 96 == 0 and K %% 16 == 0 required)", p.M, p.N, p.K);
   DSG_REQUIRE(p.out != nullptr, "gemm: null output");
@@ -317,23 +368,25 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, int epi, const G
   if (epi == EPI_ADJ_HEAD) {
     DSG_REQUIRE(p.N == 96 && p.c_e >= 1 && p.c_e <= 8 && p.w2t && p.b2 && p.flags && p.n_img > 0,
                 "gemm: adj-head epilogue needs N == 96, c_e <= 8 and the head tensors");
-    return launch_t<96, EPI_ADJ_HEAD>(tmA, tmW, p, st);
+    return launch_t<96, EPI_ADJ_HEAD>(tmA, tmW, tmO, p, st);
   }
   DSG_REQUIRE(p.ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
-  if (epi == EPI_RES_F32) DSG_REQUIRE(p.res != nullptr, "gemm: residual epilogue without residual");
+  DSG_REQUIRE(tmO != nullptr && p.ldo == p.N, "gemm: output tensor map missing or ldo != N");
+  if (epi == EPI_RES_F32)
+    DSG_REQUIRE(p.res == p.out, "gemm: the residual epilogue accumulates in place (res must alias out)");
   if (bn == 192) {
     switch (epi) {
-      case EPI_BF16: return launch_t<192, EPI_BF16>(tmA, tmW, p, st);
-      case EPI_GELU_BF16: return launch_t<192, EPI_GELU_BF16>(tmA, tmW, p, st);
-      case EPI_RES_F32: return launch_t<192, EPI_RES_F32>(tmA, tmW, p, st);
-      case EPI_F32: return launch_t<192, EPI_F32>(tmA, tmW, p, st);
+      case EPI_BF16: return launch_t<192, EPI_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_GELU_BF16: return launch_t<192, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_RES_F32: return launch_t<192, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+      case EPI_F32: return launch_t<192, EPI_F32>(tmA, tmW, tmO, p, st);
     }
   } else {
     switch (epi) {
-      case EPI_BF16: return launch_t<96, EPI_BF16>(tmA, tmW, p, st);
-      case EPI_GELU_BF16: return launch_t<96, EPI_GELU_BF16>(tmA, tmW, p, st);
-      case EPI_RES_F32: return launch_t<96, EPI_RES_F32>(tmA, tmW, p, st);
-      case EPI_F32: return launch_t<96, EPI_F32>(tmA, tmW, p, st);
+      case EPI_BF16: return launch_t<96, EPI_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_GELU_BF16: return launch_t<96, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_RES_F32: return launch_t<96, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+      case EPI_F32: return launch_t<96, EPI_F32>(tmA, tmW, tmO, p, st);
     }
   }
   set_last_error("gemm: unknown epilogue %d", epi);

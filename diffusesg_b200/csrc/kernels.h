@@ -21,7 +21,7 @@ typedef __nv_bfloat16 bf16;
 enum GemmEpi : int {
   EPI_BF16 = 0,       // out bf16 = acc + bias
   EPI_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
-  EPI_RES_F32 = 2,    // out f32  = acc + bias + res            (res may alias out)
+  EPI_RES_F32 = 2,    // out f32 += acc + bias                  (in place: res == out)
   EPI_F32 = 3,        // out f32  = acc + bias
   EPI_ADJ_HEAD = 4,   // h = gelu(acc + bias) [N == 96]; y = W2 h + b2; masked (+ EDM precond) -> [B, Ce, n, n]
 };
@@ -46,11 +46,16 @@ struct GemmParams {
 // Encode a TMA descriptor for a row-major bf16 matrix [rows, cols] (cols contiguous), box = 64 cols x
 // box_rows rows, 128-byte swizzle.  Pure host work (driver entry point), no stream interaction.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows);
+// Output descriptor of a GEMM with epilogue `epi`: [rows, cols] bf16 / fp32, box = 32 cols x 128 rows
+// (64-byte swizzle for bf16, 128-byte for fp32).  Not used by EPI_ADJ_HEAD.
+int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int epi);
 
 // N must be a multiple of 96; K a multiple of 32; rows beyond M are neither read as valid nor written.
 // box_rows of the W descriptor must equal gemm_block_n(N).
 int gemm_block_n(int N);
-int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, int epi, const GemmParams& p, cudaStream_t st);
+// EPI_RES_F32 accumulates in place with a TMA reduce-add: p.res must alias p.out.
+int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,
+                cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // shifted-window attention                                             (attention.cu)

@@ -370,6 +370,18 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
     if (m->a_maps.size() > 4096) m->a_maps.clear();
     it = m->a_maps.emplace(key, tm).first;
   }
+  const CUtensorMap* tmo = &it->second;  // placeholder for the adj-head epilogue, which stores directly
+  if (epi != EPI_ADJ_HEAD) {
+    auto okey = std::make_tuple(static_cast<const void*>(out), rows, -(W.N * 8 + epi));
+    auto ot = m->a_maps.find(okey);
+    if (ot == m->a_maps.end()) {
+      CUtensorMap tm;
+      int rc = make_tmap_out(&tm, out, rows, W.N, epi);
+      if (rc) return rc;
+      ot = m->a_maps.emplace(okey, tm).first;
+    }
+    tmo = &ot->second;
+  }
   GemmParams p;
   if (extra) p = *extra; else memset(&p, 0, sizeof(p));
   p.M = static_cast<int>(rows); p.N = W.N; p.K = W.K;
@@ -380,7 +392,7 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   ProfScope ps(g_prof_pass, PC_GEMM, 2.0 * mn * W.K,
                static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
                    (epi == EPI_RES_F32 ? mn * 4 : 0), st);
-  return launch_gemm(&it->second, &W.tmap, epi, p, st);
+  return launch_gemm(&it->second, &W.tmap, tmo, epi, p, st);
 }
 
 #define DSG_TRY(expr)        \
@@ -746,13 +758,21 @@ int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags
 int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
                   int epi, dsg_stream_t stream) {
   DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, to;
   DSG_TRY(make_tmap_bf16(&ta, a, M, K, 128));
   DSG_TRY(make_tmap_bf16(&tw, w, N, K, gemm_block_n(N)));
+  DSG_TRY(make_tmap_out(&to, out, M, N, epi));
+  if (epi == EPI_RES_F32) {
+    DSG_REQUIRE(res != nullptr, "gemm_bf16: residual epilogue without residual");
+    if (res != out)  // the kernel accumulates in place: seed the output with the residual
+      DSG_CUDA_CHECK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToDevice,
+                                     static_cast<cudaStream_t>(stream)));
+    res = static_cast<const float*>(out);
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N;
-  return launch_gemm(&ta, &tw, epi, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream));
 }
 
 int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,

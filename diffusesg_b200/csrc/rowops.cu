@@ -16,21 +16,30 @@ constexpr float kLnEps = 1e-5f;   // nn.LayerNorm default (diffusesg.py:175 etc.
 
 DSG_DEVICE uint2 pack4_bf16(float a, float b, float c, float d) { return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d)); }
 
-// A row of C fp32 values spread over a warp: float4 number (lane + 32 i) lives in v[i].
-template <int NV>
+// Sum over the LPR consecutive lanes that share a row.
+template <int LPR>
+DSG_DEVICE float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// A row of C fp32 values spread over LPR lanes (32 = a whole warp): float4 number (sub + LPR i) lives in v[i],
+// sub = lane % LPR.  Narrow rows (C = 96, 192) use 8 / 16 lanes per row so that no lane idles.
+template <int NV, int LPR = 32>
 struct Row {
   float4 v[NV];
   DSG_DEVICE void load(const float* p, int C, int lane) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e = (lane + 32 * i) * 4;
+      const int e = (lane + LPR * i) * 4;
       v[i] = (e < C) ? *reinterpret_cast<const float4*>(p + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   DSG_DEVICE void store(float* p, int C, int lane) const {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e = (lane + 32 * i) * 4;
+      const int e = (lane + LPR * i) * 4;
       if (e < C) *reinterpret_cast<float4*>(p + e) = v[i];
     }
   }
@@ -39,24 +48,24 @@ struct Row {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) / C;
+    const float mean = group_sum<LPR>(s) / C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e = (lane + 32 * i) * 4;
+      const int e = (lane + LPR * i) * 4;
       if (e < C) {
         v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
         q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
+    const float rstd = rsqrtf(group_sum<LPR>(q) / C + kLnEps);
 #pragma unroll
     for (int i = 0; i < NV; ++i) { v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd; }
   }
   DSG_DEVICE void affine(const float* g, const float* b, int C, int lane) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e = (lane + 32 * i) * 4;
+      const int e = (lane + LPR * i) * 4;
       if (e < C) {
         const float4 gg = __ldg(reinterpret_cast<const float4*>(g + e));
         const float4 bb = __ldg(reinterpret_cast<const float4*>(b + e));
@@ -68,7 +77,7 @@ struct Row {
   DSG_DEVICE void store_bf16(bf16* p, int C, int lane) const {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e = (lane + 32 * i) * 4;
+      const int e = (lane + LPR * i) * 4;
       if (e < C) *reinterpret_cast<uint2*>(p + e) = pack4_bf16(v[i].x, v[i].y, v[i].z, v[i].w);
     }
   }
@@ -77,21 +86,22 @@ struct Row {
 // ---------------------------------------------------------------------------------------------------------
 // FiLM + SiLU (+ shortcut write) + LayerNorm            (SwinTransformerBlock.forward :238-243)
 // ---------------------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, int LPR>
 __global__ void __launch_bounds__(kRowThreads)
 film_ln_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, bf16* __restrict__ y,
                const float* __restrict__ film, int film_ld, int cond_uniform, const float* __restrict__ gamma,
                const float* __restrict__ beta, long long rows, int tokens_per_sample, int C) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int lane = threadIdx.x % LPR;
+  long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / LPR) + threadIdx.x / LPR;
+  const bool valid = row < rows;  // surplus lane groups stay for the shuffles but never store
+  if (!valid) row = rows - 1;
   const int b = cond_uniform ? 0 : static_cast<int>(row / tokens_per_sample);
   const float* sc = film + static_cast<size_t>(b) * film_ld;  // scale[C] then shift[C]
-  Row<NV> r;
+  Row<NV, LPR> r;
   r.load(x_in + row * C, C, lane);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int e = (lane + 32 * i) * 4;
+    const int e = (lane + LPR * i) * 4;
     if (e < C) {
       const float4 s = __ldg(reinterpret_cast<const float4*>(sc + e));
       const float4 t = __ldg(reinterpret_cast<const float4*>(sc + C + e));
@@ -101,24 +111,25 @@ film_ln_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, bf16* 
       r.v[i].w = silu_f(fmaf(r.v[i].w, s.w + 1.f, t.w));
     }
   }
-  r.store(x_out + row * C, C, lane);
+  if (valid) r.store(x_out + row * C, C, lane);
   r.normalize(C, lane);
   r.affine(gamma, beta, C, lane);
-  r.store_bf16(y + row * C, C, lane);
+  if (valid) r.store_bf16(y + row * C, C, lane);
 }
 
-template <int NV>
+template <int NV, int LPR>
 __global__ void __launch_bounds__(kRowThreads)
 ln_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
           const float* __restrict__ beta, long long rows, int C) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  Row<NV> r;
+  const int lane = threadIdx.x % LPR;
+  long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / LPR) + threadIdx.x / LPR;
+  const bool valid = row < rows;
+  if (!valid) row = rows - 1;
+  Row<NV, LPR> r;
   r.load(x + row * C, C, lane);
   r.normalize(C, lane);
   r.affine(gamma, beta, C, lane);
-  r.store_bf16(y + row * C, C, lane);
+  if (valid) r.store_bf16(y + row * C, C, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -315,63 +326,99 @@ __global__ void node_proj_kernel(const float* __restrict__ node, const float* __
   rc[static_cast<size_t>(bi) * 2 * embed + e2] = acc;
 }
 
-// One warp per pixel (b, i, j); lane l owns channels l, l + 32, l + 64 of the 96-wide embedding.
+// One thread per pixel (b, i, j), a warp covers 32 consecutive pixels: the c_e (x2) adjacency planes are read
+// coalesced, the 96 output channels of the pixel live in registers (1x1-conv weights broadcast from shared
+// memory), LayerNorm and FiLM are thread-local, and the [32 pixels x 96] tile leaves through a padded
+// shared-memory transpose so that every store instruction writes one full 128-byte line.
 // x0 = silu(shift + LN(conv1x1(input)) * (1 + scale))
-template <int EPL>  // embed / 32
-__global__ void __launch_bounds__(kRowThreads)
+constexpr int kPE = 96;
+__global__ void __launch_bounds__(kRowThreads, 2)
 patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_adj, const float* __restrict__ in_scale,
                    const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ film, int film_ld, int cond_uniform, float* __restrict__ x0,
                    long long pixels, int n, int c_e, int self_cond) {
-  constexpr int E = EPL * 32;
-  const int lane = threadIdx.x & 31;
-  const long long pix = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
-  if (pix >= pixels) return;
+  constexpr int E = kPE;
+  __shared__ __align__(16) float sW[16 * E];
+  __shared__ __align__(16) float sB[E], sG[E], sBe[E];
+  __shared__ float sT[kRowThreads / 32][32][33];
+  const int planes = self_cond ? 2 * c_e : c_e;
+  for (int i = threadIdx.x; i < planes * E; i += kRowThreads) sW[i] = w_adj[i];
+  for (int i = threadIdx.x; i < E; i += kRowThreads) { sB[i] = bias[i]; sG[i] = gamma[i]; sBe[i] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nn = n * n;
-  const int b = static_cast<int>(pix / nn);
-  const int ij = static_cast<int>(pix - static_cast<long long>(b) * nn);
-  const int i = ij / n, j = ij - i * n;
-  const bool pair_ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
-  const float sc = in_scale ? in_scale[b] : 1.f;
-  float v[EPL];
+  const long long groups = (pixels + 31) / 32;
+  for (long long grp = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + warp; grp < groups;
+       grp += static_cast<long long>(gridDim.x) * (kRowThreads / 32)) {
+    const long long pix0 = grp * 32;
+    const long long pix = pix0 + lane;
+    const bool valid = pix < pixels;
+    const long long pc = valid ? pix : pixels - 1;
+    const int b = static_cast<int>(pc / nn);
+    const int ij = static_cast<int>(pc - static_cast<long long>(b) * nn);
+    const int i = ij / n, j = ij - i * n;
+    const bool pair_ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+    const float sc = in_scale ? in_scale[b] : 1.f;
+    float v[E];
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) v[k] = bias[lane + 32 * k];
-  // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]; w_adj is [planes, E]
-  int ch = 0;
-  if (self_cond) {
-    for (int c = 0; c < c_e; ++c, ++ch) {
-      const float a = sc_adj ? sc_adj[(static_cast<size_t>(b) * c_e + c) * nn + ij] : 0.f;
+    for (int e = 0; e < E; ++e) v[e] = sB[e];
+    // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]
+    for (int ch = 0; ch < planes; ++ch) {
+      float a;
+      if (self_cond && ch < c_e) {
+        a = sc_adj ? sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij] : 0.f;
+      } else {
+        const int c = self_cond ? ch - c_e : ch;
+        a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+      }
+      const float4* w4 = reinterpret_cast<const float4*>(&sW[ch * E]);
 #pragma unroll
-      for (int k = 0; k < EPL; ++k) v[k] = fmaf(w_adj[ch * E + lane + 32 * k], a, v[k]);
+      for (int e4 = 0; e4 < E / 4; ++e4) {
+        const float4 w = w4[e4];
+        v[4 * e4] = fmaf(w.x, a, v[4 * e4]); v[4 * e4 + 1] = fmaf(w.y, a, v[4 * e4 + 1]);
+        v[4 * e4 + 2] = fmaf(w.z, a, v[4 * e4 + 2]); v[4 * e4 + 3] = fmaf(w.w, a, v[4 * e4 + 3]);
+      }
     }
-  }
-  for (int c = 0; c < c_e; ++c, ++ch) {
-    const float a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+    if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)
+      const float4* rrow = reinterpret_cast<const float4*>(rc + (static_cast<size_t>(b) * n + i) * 2 * E);
+      const float4* rcol = reinterpret_cast<const float4*>(rc + (static_cast<size_t>(b) * n + j) * 2 * E + E);
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) v[k] = fmaf(w_adj[ch * E + lane + 32 * k], a, v[k]);
-  }
-  if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)
-    const float* rrow = rc + (static_cast<size_t>(b) * n + i) * 2 * E;
-    const float* rcol = rc + (static_cast<size_t>(b) * n + j) * 2 * E + E;
+      for (int e4 = 0; e4 < E / 4; ++e4) {
+        const float4 r1 = __ldg(rrow + e4), r2 = __ldg(rcol + e4);
+        v[4 * e4] += r1.x + r2.x; v[4 * e4 + 1] += r1.y + r2.y;
+        v[4 * e4 + 2] += r1.z + r2.z; v[4 * e4 + 3] += r1.w + r2.w;
+      }
+    }
+    float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) v[k] += rrow[lane + 32 * k] + rcol[lane + 32 * k];
-  }
-  // LayerNorm(E)
-  float s = 0.f;
+    for (int e = 0; e < E; ++e) sum += v[e];
+    const float mean = sum / E;
+    float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) s += v[k];
-  const float mean = warp_sum(s) / E;
-  float q = 0.f;
+    for (int e = 0; e < E; ++e) { v[e] -= mean; q = fmaf(v[e], v[e], q); }
+    const float rstd = rsqrtf(q / E + kLnEps);
+    const float4* fs4 = reinterpret_cast<const float4*>(film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld);
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) { v[k] -= mean; q += v[k] * v[k]; }
-  const float rstd = rsqrtf(warp_sum(q) / E + kLnEps);
-  const float* fs = film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld;
+    for (int e4 = 0; e4 < E / 4; ++e4) {
+      const float4 fsc = __ldg(fs4 + e4), fsh = __ldg(fs4 + E / 4 + e4);
+      const float s4[4] = {fsc.x, fsc.y, fsc.z, fsc.w}, t4[4] = {fsh.x, fsh.y, fsh.z, fsh.w};
 #pragma unroll
-  for (int k = 0; k < EPL; ++k) {
-    const int e = lane + 32 * k;
-    const float y = fmaf(v[k] * rstd, gamma[e], beta[e]);
-    x0[pix * E + e] = silu_f(fmaf(y, fs[e] + 1.f, fs[E + e]));
+      for (int k = 0; k < 4; ++k) {
+        const int e = 4 * e4 + k;
+        const float y = fmaf(v[e] * rstd, sG[e], sBe[e]);
+        v[e] = silu_f(fmaf(y, s4[k] + 1.f, t4[k]));
+      }
+    }
+#pragma unroll
+    for (int gq = 0; gq < E / 32; ++gq) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) sT[warp][lane][k] = v[32 * gq + k];
+      __syncwarp();
+      for (int p = 0; p < 32; ++p)
+        if (pix0 + p < pixels) x0[(pix0 + p) * E + 32 * gq + lane] = sT[warp][p][lane];
+    }
   }
 }
 
@@ -438,9 +485,25 @@ int nv_of(int C) {
   }
 }
 
-inline unsigned row_grid(long long rows) { return static_cast<unsigned>((rows + kRowThreads / 32 - 1) / (kRowThreads / 32)); }
+inline unsigned row_grid(long long rows, int lpr = 32) {
+  const int per_cta = kRowThreads / lpr;
+  return static_cast<unsigned>((rows + per_cta - 1) / per_cta);
+}
 
 }  // namespace
+
+// (float4 per lane, lanes per row): 96 -> (3, 8), 192 -> (3, 16), 384 -> (3, 32), 768 -> (6, 32), 1536 -> (12, 32)
+#define DSG_DISPATCH_ROW(C, CALL)                                                         \
+  switch (C) {                                                                            \
+    case 96: { constexpr int NV = 3, LPR = 8; CALL; break; }                              \
+    case 192: { constexpr int NV = 3, LPR = 16; CALL; break; }                            \
+    case 384: { constexpr int NV = 3, LPR = 32; CALL; break; }                            \
+    case 768: { constexpr int NV = 6, LPR = 32; CALL; break; }                            \
+    case 1536: { constexpr int NV = 12, LPR = 32; CALL; break; }                          \
+    default:                                                                              \
+      set_last_error("row kernel: unsupported width %d (96/192/384/768/1536)", C);        \
+      return DSG_ERR_INVALID;                                                             \
+  }
 
 #define DSG_DISPATCH_NV(C, CALL)                                                          \
   switch (nv_of(C)) {                                                                     \
@@ -458,14 +521,14 @@ int launch_film_ln(const float* x_in, float* x_out, bf16* y, const float* film, 
                    int cond_uniform, const float* gamma, const float* beta, int batch, int tokens_per_sample, int C,
                    cudaStream_t st) {
   const long long rows = static_cast<long long>(batch) * tokens_per_sample;
-  DSG_DISPATCH_NV(C, (film_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(
-                         x_in, x_out, y, film + film_off, film_ld, cond_uniform, gamma, beta, rows, tokens_per_sample, C)));
+  DSG_DISPATCH_ROW(C, (film_ln_kernel<NV, LPR><<<row_grid(rows, LPR), kRowThreads, 0, st>>>(
+                          x_in, x_out, y, film + film_off, film_ld, cond_uniform, gamma, beta, rows, tokens_per_sample, C)));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
 
 int launch_ln(const float* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, cudaStream_t st) {
-  DSG_DISPATCH_NV(C, (ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(x, y, gamma, beta, rows, C)));
+  DSG_DISPATCH_ROW(C, (ln_kernel<NV, LPR><<<row_grid(rows, LPR), kRowThreads, 0, st>>>(x, y, gamma, beta, rows, C)));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -536,9 +599,12 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
                        int c_e, int self_cond, int embed, cudaStream_t st) {
   DSG_REQUIRE(embed == 96, "patch_embed: embed_dim %d (only 96 is built)", embed);
   const long long pixels = static_cast<long long>(batch) * n * n;
-  patch_embed_kernel<3><<<row_grid(pixels), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj, bias, gamma,
-                                                                 beta, film + film_off, film_ld, cond_uniform, x0,
-                                                                 pixels, n, c_e, self_cond);
+  DSG_REQUIRE((self_cond ? 2 : 1) * c_e <= 16, "patch_embed: %d adjacency planes (max 16)", (self_cond ? 2 : 1) * c_e);
+  long long blocks = (pixels + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  patch_embed_kernel<<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj,
+                                                                           bias, gamma, beta, film + film_off, film_ld,
+                                                                           cond_uniform, x0, pixels, n, c_e, self_cond);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

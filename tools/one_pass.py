@@ -1,0 +1,35 @@
+"""Run a few preconditioned denoiser passes (VG geometry) - the unit ncu profiles.
+
+    python tools/one_pass.py [--batch 512] [--passes 2] [--config vg]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import build_native_model  # noqa: E402
+from diffusesg_b200.utils.synthetic import CONFIGS, synthetic_inputs  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=512)
+ap.add_argument("--passes", type=int, default=2)
+ap.add_argument("--config", default="vg")
+args = ap.parse_args()
+cfg = CONFIGS[args.config]
+dev = torch.device("cuda:0")
+model = build_native_model(cfg, dev)
+adj, node, flags, sigmas, sc_adj, sc_node = [t.to(dev) for t in synthetic_inputs(cfg, args.batch, seed=7)]
+sig = torch.tensor(1.5, device=dev).view(-1).expand(args.batch)
+with torch.no_grad():
+    for _ in range(args.passes):
+        a, n = model.model.denoise(adj, node, flags, sig, sc_adj, sc_node)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+with torch.no_grad():
+    a, n = model.model.denoise(adj, node, flags, sig, sc_adj, sc_node)
+e1.record()
+torch.cuda.synchronize()
+print("pass ms", e0.elapsed_time(e1), "finite", bool(torch.isfinite(a).all() and torch.isfinite(n).all()))
