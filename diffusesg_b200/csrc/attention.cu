@@ -150,7 +150,7 @@ window_attention_kernel(const bf16* __restrict__ qkv, const float* __restrict__ 
     cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
     cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
     const float nm0 = fmaxf(m0, cm0), nm1 = fmaxf(m1, cm1);  // finite: every chunk holds >= 1 real key
-    const float f0 = __expf(m0 - nm0), f1 = __expf(m1 - nm1);
+    const float f0 = ex2_approx((m0 - nm0) * 1.4426950408889634f), f1 = ex2_approx((m1 - nm1) * 1.4426950408889634f);
     m0 = nm0; m1 = nm1;
     l0 *= f0; l1 *= f1;
 #pragma unroll
@@ -160,8 +160,8 @@ window_attention_kernel(const bf16* __restrict__ qkv, const float* __restrict__ 
 #pragma unroll
     for (int nt = 0; nt < NT_MAX; ++nt) {
       if (kc + nt * 8 < T_PAD) {
-        s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
-        s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+        s[nt][0] = ex2_approx((s[nt][0] - m0) * 1.4426950408889634f); s[nt][1] = ex2_approx((s[nt][1] - m0) * 1.4426950408889634f);
+        s[nt][2] = ex2_approx((s[nt][2] - m1) * 1.4426950408889634f); s[nt][3] = ex2_approx((s[nt][3] - m1) * 1.4426950408889634f);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }
@@ -342,8 +342,8 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
     const float m0s = m0 * kLog2e, m1s = m1 * kLog2e;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(fmaf(s[nt][0], kLog2e, -m0s)); s[nt][1] = exp2f(fmaf(s[nt][1], kLog2e, -m0s));
-      s[nt][2] = exp2f(fmaf(s[nt][2], kLog2e, -m1s)); s[nt][3] = exp2f(fmaf(s[nt][3], kLog2e, -m1s));
+      s[nt][0] = ex2_approx(fmaf(s[nt][0], kLog2e, -m0s)); s[nt][1] = ex2_approx(fmaf(s[nt][1], kLog2e, -m0s));
+      s[nt][2] = ex2_approx(fmaf(s[nt][2], kLog2e, -m1s)); s[nt][3] = ex2_approx(fmaf(s[nt][3], kLog2e, -m1s));
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }

@@ -60,21 +60,34 @@ DSG_DEVICE float warp_sum(float v) {
   return v;
 }
 
-DSG_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// MUFU-backed approximations (1-2 ulp): the IEEE-rounded expf / division sequences cost ~10x more issue slots
+DSG_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+DSG_DEVICE float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+DSG_DEVICE float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 // exact (erf) GELU, the reference's nn.GELU() default (model/diffusesg/diffusesg.py:10,15).
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result):
-// 2 MUFU + ~12 FP32 ops instead of the ~30-instruction branchy erff().
+// erfc by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result):
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2),  erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z)
+// 12 FP32 ops + 2 MUFU per element instead of the ~40-instruction branchy erff().
 DSG_DEVICE float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * exp2f(-1.4426950408889634f * z * z);  // 1 - erf(z)
-  const float erf_abs = 1.0f - e;
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float e = (p * t) * ex2_approx(-1.4426950408889634f * (z * z));
+  return fmaf(-0.5f * ax, e, fmaxf(x, 0.0f));
 }
 
 DSG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {

@@ -27,7 +27,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = (BN == 192) ? 4 : 6;
+  static constexpr int kStages = (BN == 192) ? 4 : 5;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int ACC_STRIDE = (BN == 192) ? 256 : 128;  // TMEM columns between the two accumulators
@@ -35,6 +35,8 @@ struct Cfg {
   static constexpr int OUT_CHUNK_BYTES = 128 * 32 * 4;  // 128 rows x 32 fp32 columns (bf16 uses half of it)
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + 4 * OUT_CHUNK_BYTES + 256 /*barriers*/;
 };
+
+static_assert(Cfg<96>::SMEM_BYTES <= 227 * 1024 && Cfg<192>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
