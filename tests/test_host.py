@@ -1,0 +1,261 @@
+"""CPU-only checks: the C ABI library loads and exports what include/dsg_b200.h declares, host-side logic of the
+drop-in classes, and the world_size-2 sharded sampling path over gloo.  No compute call needs a GPU here."""
+import copy
+import ctypes as C
+import json
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from diffusesg_b200 import native
+from diffusesg_b200.model.diffusesg.diffusesg import DiffuseSG
+from diffusesg_b200.model.precond.precond import NodeAdjPrecond
+from diffusesg_b200.runner.mcmc_sampler.edm import NodeAdjEDMSampler
+from diffusesg_b200.runner.objectives.edm import get_preconditioning_params
+from diffusesg_b200.runner.sampler.sharded import per_gpu_batch, shard_bounds
+from diffusesg_b200.utils.synthetic import CONFIGS, in_chans, synthetic_inputs, synthetic_state_dict
+from oracle import denoiser_oracle as O
+from oracle import edm_oracle as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _module(cfg):
+    return DiffuseSG(img_size=cfg["img"], in_chans=in_chans(cfg), patch_size=1, embed_dim=cfg["embed"],
+                     depths=cfg["depths"], num_heads=[3, 6, 12, 24], window_size=cfg["window"], mlp_ratio=4.,
+                     drop_rate=0., attn_drop_rate=0., drop_path_rate=0.0, self_condition=cfg["self_cond"],
+                     symmetric_noise=False, out_chans_adj=cfg["c_e"], out_chans_node=cfg["c_n"])
+
+
+def _native_cfg(cfg):
+    c = native.DsgConfig()
+    c.img_size, c.embed_dim, c.num_stages = cfg["img"], cfg["embed"], len(cfg["depths"])
+    for i, (d, h) in enumerate(zip(cfg["depths"], cfg["heads"])):
+        c.depths[i], c.num_heads[i] = d, h
+    c.window_size, c.c_e, c.c_n, c.self_condition = cfg["window"], cfg["c_e"], cfg["c_n"], int(cfg["self_cond"])
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C ABI
+# ---------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "dsg_b200.h")).read()
+    declared = sorted(set(re.findall(r"DSG_API[^;]*?\b(dsg_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = native.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/dsg_b200.h but not exported"
+    assert declared == native.exported_symbols()
+    assert lib.dsg_abi_version() == 1
+
+
+@pytest.mark.parametrize("name", ["vg", "coco", "tiny", "n64w16"])
+def test_native_tensor_table_matches_reference_state_dict(name, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, f"layout_{name}.json")))["layout"]
+    lib = native.lib()
+    h = C.c_void_p()
+    native.check(lib.dsg_model_create(C.byref(_native_cfg(CONFIGS[name])), C.byref(h)), "create")
+    try:
+        assert lib.dsg_model_num_tensors(h) == len(ref)
+        key, numel, dtype = C.c_char_p(), C.c_int64(), C.c_int32()
+        for i, (k, shape, dt) in enumerate(ref):
+            native.check(lib.dsg_model_tensor_info(h, i, C.byref(key), C.byref(numel), C.byref(dtype)), "info")
+            assert key.value.decode() == k
+            assert numel.value == int(np.prod(shape))
+            assert dtype.value == (1 if dt == "int64" else 0)
+        assert lib.dsg_model_arena_bytes(h) > 4 * sum(int(np.prod(s)) for _, s, _ in ref)
+        small, big = lib.dsg_workspace_bytes(h, 2, 1), lib.dsg_workspace_bytes(h, 8, 1)
+        assert 0 < small < big
+    finally:
+        lib.dsg_model_destroy(h)
+
+
+def test_native_error_paths_without_gpu():
+    lib = native.lib()
+    bad = _native_cfg(CONFIGS["vg"])
+    bad.num_heads[0] = 4                                   # 96 channels need 3 heads of 32
+    h = C.c_void_p()
+    assert lib.dsg_model_create(C.byref(bad), C.byref(h)) == 1
+    assert b"heads" in lib.dsg_last_error()
+    h = C.c_void_p()
+    native.check(lib.dsg_model_create(C.byref(_native_cfg(CONFIGS["tiny"])), C.byref(h)), "create")
+    try:
+        buf = (C.c_float * 4)()
+        assert lib.dsg_model_set_tensor(h, b"norm.weight", buf, 16, 1, None) == 3        # no arena bound
+        assert lib.dsg_model_finalize(h, None) == 3
+        args = native.DsgForwardArgs()
+        args.struct_size = C.sizeof(native.DsgForwardArgs)
+        assert lib.dsg_denoiser_forward(h, C.byref(args), None) == 3                     # not finalized
+        assert lib.dsg_model_bind_arena(h, C.c_void_p(256), 16) == 5                     # arena too small
+    finally:
+        lib.dsg_model_destroy(h)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# drop-in module
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vg", "coco", "tiny", "n64w16"])
+def test_module_state_dict_is_the_reference_layout(name, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, f"layout_{name}.json")))
+    m = _module(CONFIGS[name])
+    sd = m.state_dict()
+    assert list(sd) == [k for k, _, _ in ref["layout"]]
+    for (k, shape, dt), v in zip(ref["layout"], sd.values()):
+        assert list(v.shape) == shape and str(v.dtype) == "torch." + dt, k
+    assert sum(p.numel() for p in m.parameters()) == ref["n_params"]
+    m.load_state_dict(synthetic_state_dict(CONFIGS[name]), strict=True)
+    wrapped = NodeAdjPrecond(precond="edm", model=m, self_condition=True, symmetric_noise=False)
+    assert list(wrapped.state_dict()) == ["model." + k for k in sd]
+
+
+def test_module_buffers_match_reference_init(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "layout_vg.json")))["init_sums"]
+    sd = _module(CONFIGS["vg"]).state_dict()
+    for k, v in sd.items():
+        if k.endswith("relative_position_index") or k.endswith("attn_mask"):
+            assert float(v.double().sum()) == ref[k][0] and float(v.double().abs().sum()) == ref[k][1], k
+
+
+def test_module_deepcopy_and_unsupported_options():
+    m = _module(CONFIGS["tiny"])
+    m2 = copy.deepcopy(m)                                  # ema_pytorch.EMA does this (learning_utils.py:160)
+    assert m2._nat is None and list(m2.state_dict()) == list(m.state_dict())
+    with pytest.raises(NotImplementedError):
+        DiffuseSG(img_size=16, in_chans=13, patch_size=4, depths=[1], num_heads=[3], window_size=4, drop_path_rate=0.,
+                  symmetric_noise=False, out_chans_adj=3, out_chans_node=5)
+    with pytest.raises(NotImplementedError):
+        NodeAdjPrecond(precond="vp", model=m, self_condition=True, symmetric_noise=False)
+
+
+def test_forward_refuses_cpu_tensors():
+    cfg = CONFIGS["tiny"]
+    m = _module(cfg).eval()
+    adj, node, flags, sigmas, _, _ = synthetic_inputs(cfg, 2, seed=7)
+    with torch.no_grad(), pytest.raises(native.NativeError):
+        m(adj, node, flags, sigmas.log() / 4)
+
+
+def test_preconditioning_params_match_oracle():
+    s = torch.tensor([80.0, 3.0, 0.5, 0.002])
+    for a, b in zip(get_preconditioning_params("edm", s), O.precond_coefficients(s)):
+        assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sampler host logic
+# ---------------------------------------------------------------------------------------------------------
+def _sampler(steps=256):
+    return NodeAdjEDMSampler(num_steps=steps, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                             clip_samples_scope="x_0", dev="cpu", objective="edm", self_condition=True,
+                             symmetric_noise=False)
+
+
+def test_sampler_schedule_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sampler_tiny.npz"))
+    np.testing.assert_array_equal(_sampler(256).sigma_steps.numpy(), g["sigma_steps_256"])
+    s8 = _sampler(8)
+    t = torch.cat([s8.sigma_steps, torch.zeros(1, dtype=torch.float64)]).to(torch.float32)
+    np.testing.assert_array_equal(t.numpy(), g["t_steps"])
+
+
+def test_sampler_step_scalars_match_oracle_bit_for_bit():
+    s = _sampler(256)
+    ts = E.t_steps_fp32(256)
+    for i in range(256):
+        got, want = s.step_scalars(ts[i], ts[i + 1]), E.step_scalars(ts[i], ts[i + 1], 256)
+        assert got["noise_coef"] == float(want["noise_coef"]) and got["h"] == float(want["h"])
+        assert got["inv_t_hat"] == float(1.0 / want["t_hat"]) and float(got["t_hat"]) == float(want["t_hat"])
+        if i < 255:
+            assert got["inv_t_prime"] == float(1.0 / want["t_prime"])
+    assert s.step_scalars(ts[0], ts[1])["gamma"] == 0.0          # sigma = 80 is outside [S_min, S_max]
+    assert s.step_scalars(ts[100], ts[101])["gamma"] == pytest.approx(40 / 256)
+
+
+def test_sampler_rejects_unbuilt_variants():
+    with pytest.raises(NotImplementedError):
+        NodeAdjEDMSampler(num_steps=8, solver="euler", clip_samples=False, clip_samples_min=None, clip_samples_max=None,
+                          clip_samples_scope="x_0", dev="cpu", self_condition=True, symmetric_noise=False)
+    with pytest.raises(NotImplementedError):
+        NodeAdjEDMSampler(num_steps=8, clip_samples=False, clip_samples_min=None, clip_samples_max=None,
+                          clip_samples_scope="x_0", dev="cpu", self_condition=True, symmetric_noise=True)
+
+
+class _Cfg(dict):
+    """ml_collections.ConfigDict stand-in: attribute access + `in`."""
+    __getattr__ = dict.__getitem__
+
+
+def test_factories_take_the_reference_config_keys():
+    from diffusesg_b200.utils.learning_utils import get_network
+    from diffusesg_b200.utils.sampling_utils import get_mc_sampler, load_model
+    cfg = _Cfg(dev="cpu", flag_sg=True, logdir="/tmp", dataset=_Cfg(name="visual_genome_sg", max_node_num=64),
+               model=_Cfg(name="diffuse_sg", feature_dims=[96], depths=[1, 1, 3, 1], window_size=8, patch_size=1),
+               train=_Cfg(self_cond=True, node_encoding="bits", edge_encoding="bits", resume=None),
+               mcmc=_Cfg(name="edm", precond="edm", sigma_dist="edm", num_steps=256,
+                         sample_clip=_Cfg(min=-1.0, max=1.0, scope="x_0")))
+    model = get_network(cfg, None)
+    assert isinstance(model, NodeAdjPrecond) and len(model.state_dict()) == 247
+    assert sum(p.numel() for p in model.parameters()) == 35813660
+    sampler = get_mc_sampler(cfg)
+    assert sampler.num_steps == 256 and sampler.S_churn == 40 and sampler.S_noise == 1.003
+    ckpt = {"model": {"module." + k: v.clone() for k, v in model.state_dict().items()}}   # DDP-prefixed checkpoint
+    load_model(ckpt, model, "model")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU host path: world_size 2 over gloo
+# ---------------------------------------------------------------------------------------------------------
+def test_shard_bounds_cover_everything():
+    for total in (0, 1, 7, 512, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+    assert per_gpu_batch(512, 4) == 128 and per_gpu_batch(2, 8) == 1
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from diffusesg_b200.runner.sampler.sharded import sample_sharded, seed_everything
+    from diffusesg_b200.utils.dist_training import gather_tensors
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        seed_everything(1234, rank)
+        n, ce, cn = 8, 2, 3
+        flags = torch.arange(n)[None, :] < torch.arange(2, 9)[:, None]       # 7 graphs: uneven split 4 + 3
+
+        class FakeSampler:                                                   # stands in for the GPU sampler
+            dev = "cpu"
+
+            def sample(self, model, node_flags, num_node_chan, num_edge_chan):
+                b = node_flags.shape[0]
+                cnt = node_flags.sum(1).float()
+                return (cnt.view(b, 1, 1, 1).expand(b, num_edge_chan, n, n).clone(),
+                        (cnt * 10 + rank).view(b, 1, 1).expand(b, n, num_node_chan).clone())
+
+        a, nd = sample_sharded(FakeSampler(), None, flags, batch_size=4, num_node_chan=cn, num_edge_chan=ce)
+        g = gather_tensors(torch.full((2, 3), float(rank)), 0, "cpu")
+        torch.save(dict(a=a, n=nd, g=g, draw=torch.randn(2)), os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sampling_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert torch.equal(r0["a"], r1["a"]) and torch.equal(r0["n"], r1["n"])       # every rank holds the full result
+    assert r0["a"].shape == (7, 2, 8, 8) and r0["n"].shape == (7, 8, 3)
+    assert r0["a"][:, 0, 0, 0].tolist() == [2, 3, 4, 5, 6, 7, 8]                 # rank order, padding trimmed
+    assert r0["n"][:, 0, 0].tolist() == [20, 30, 40, 50, 61, 71, 81]             # rows 0-3 from rank 0, 4-6 from rank 1
+    assert r0["g"][:, 0].tolist() == [0, 0, 1, 1]
+    assert not torch.equal(r0["draw"], r1["draw"])                               # seed + rank
