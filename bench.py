@@ -253,10 +253,11 @@ def run_native(args, cfg, rank, local_rank, world):
     if rank != 0:
         return
     pk = peaks()
-    g = prof.get("gemm_tcgen05", dict(ms=0, flops=0, bytes=0, launches=0))
+    g0, g1 = prof.get("gemm_tcgen05", {}), prof.get("fused_mlp_tcgen05", {})
+    g = {k: g0.get(k, 0) + g1.get(k, 0) for k in ("ms", "flops", "bytes", "launches")}  # every tcgen05 launch
     total_prof_ms = sum(c["ms"] for c in prof.values()) or 1.0
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> (tcgen05/TMEM/TMA GEMM, all nn.Linear of the denoiser)",
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> + fused_mlp_kernel<C> (tcgen05/TMEM/TMA: every nn.Linear of the denoiser)",
                 "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": gemm_tflops / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "traffic": None, "launches_timed": g["launches"],

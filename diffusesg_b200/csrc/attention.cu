@@ -231,16 +231,21 @@ DSG_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
                : "r"(smem_u32(smem_row)));
 }
 
-DSG_DEVICE int window_token_row(int gw, int t, int res, int shift, int nwx_log_free_nW, int nwx) {
-  // gw = b * nW + win; token t = ty * 8 + tx of the (rolled) window -> row of the un-rolled [B*res*res] token matrix
-  const int b = gw / nwx_log_free_nW, win = gw - b * nwx_log_free_nW;
+// Window gw = b * nW + wy * nwx + wx of the (rolled) grid: row of its token (0, 0) before wrapping, as (b, y0, x0).
+struct WinOrigin { int b_row0, y0, x0; };
+DSG_DEVICE WinOrigin window_origin(int gw, int res, int shift, int nW, int nwx) {
+  const int b = gw / nW, win = gw - b * nW;
   const int wy = win / nwx, wx = win - wy * nwx;
-  int oy = wy * 8 + (t >> 3) + shift; if (oy >= res) oy -= res;
-  int ox = wx * 8 + (t & 7) + shift; if (ox >= res) ox -= res;
-  return (b * res + oy) * res + ox;
+  return WinOrigin{b * res * res, wy * 8 + shift, wx * 8 + shift};
+}
+// token t = ty * 8 + tx of the window -> row of the un-rolled [B*res*res] token matrix (cyclic shift undone)
+DSG_DEVICE int window_token_row(const WinOrigin& o, int t, int res) {
+  int oy = o.y0 + (t >> 3); if (oy >= res) oy -= res;
+  int ox = o.x0 + (t & 7); if (ox >= res) ox -= res;
+  return o.b_row0 + oy * res + ox;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
                           bf16* __restrict__ out, int res, int shift, int heads, int total_windows) {
   constexpr int T = 64;
@@ -257,13 +262,14 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
   const int r0 = warp * 16 + g, r1 = r0 + 8;
 
   auto issue_loads = [&](int gw, int buf) {
+    const WinOrigin org = window_origin(gw, res, shift, nW, nwx);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int idx = tid + 128 * k;  // 64 tokens x 3 parts x 4 chunks of 16 bytes
       const int t = idx / 12;
       const int rem = idx - t * 12;
       const int part = rem >> 2, chunk = rem & 3;
-      const int row = window_token_row(gw, t, res, shift, nW, nwx);
+      const int row = window_token_row(org, t, res);
       cp_async16(&sbuf[buf][part][t * QK_PITCH + chunk * 8],
                  qkv + static_cast<size_t>(row) * (3 * C) + part * C + h * HD + chunk * 8);
     }
@@ -372,7 +378,8 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
         mma_m16n8k16_bf16(o[2 * np + 1], pa, reinterpret_cast<const uint32_t(&)[2]>(vb[2]));
       }
     }
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
+    const WinOrigin org_out = window_origin(gw, res, shift, nW, nwx);
     // stage the 16 x 32 output slab of this warp in its own (consumed) q rows, then one 64-byte store per token
     __syncwarp();
 #pragma unroll
@@ -386,7 +393,7 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
       const int idx = lane + 32 * k;  // 16 tokens x 4 chunks
       const int t = warp * 16 + (idx >> 2), chunk = idx & 3;
       const uint4 v = *reinterpret_cast<const uint4*>(&sQ[t * QK_PITCH + chunk * 8]);
-      const int row = window_token_row(gw, t, res, shift, nW, nwx);
+      const int row = window_token_row(org_out, t, res);
       *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * C + h * HD + chunk * 8) = v;
     }
     __syncthreads();  // everyone is done with this buffer before the loads of window gw + 2 overwrite it

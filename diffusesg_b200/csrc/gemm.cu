@@ -22,7 +22,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                    // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 320;        // TMA warp, MMA warp, 2 epilogue groups of 4 warps
+// Epilogue groups (4 warps each): group g drains accumulator (g & 1); for the ALU-heavy epilogues (bf16 output,
+// GELU, adj head) two groups share an accumulator and split its columns, so 16 warps hide the MUFU / load latency.
+__host__ __device__ constexpr int epi_groups(int epi) { return (epi == EPI_RES_F32 || epi == EPI_F32) ? 2 : 4; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * epi_groups(epi); }
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN>
@@ -32,24 +35,28 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int ACC_STRIDE = (BN == 192) ? 256 : 128;  // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;       // 512 / 256
-  static constexpr int OUT_CHUNK_BYTES = 128 * 32 * 4;  // 128 rows x 32 fp32 columns (bf16 uses half of it)
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + 4 * OUT_CHUNK_BYTES + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 64 * 1024;  // 2 groups x 2 x 16 KB (fp32 chunks) or 4 groups x 2 x 8 KB (bf16)
+  static constexpr int BIAS_BYTES = 2 * BN * 4;     // bias slice of the current tile, per accumulator
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + kStages * STAGE_BYTES + STAGING_BYTES + BIAS_BYTES + 256 /*barriers*/;
 };
 
 static_assert(Cfg<96>::SMEM_BYTES <= 227 * 1024 && Cfg<192>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // round up to 1024 bytes (128-byte swizzle atoms) without casting through an integer, so that the compiler
+  // keeps the shared address space and emits LDS / STS instead of generic loads and stores
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * A_STAGE_BYTES;
-  uint8_t* sOut = smem + kStages * C::STAGE_BYTES;  // 2 groups x 2 x 16 KB, 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 4 * C::OUT_CHUNK_BYTES);
+  uint8_t* sOut = smem + kStages * C::STAGE_BYTES;  // staging chunks, 1024-byte aligned
+  float* sBias = reinterpret_cast<float*>(sOut + C::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + C::STAGING_BYTES + C::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -76,13 +83,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 2 * epi_groups(EPI));  // one arrival per epilogue warp reading accumulator a
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   if (EPI == EPI_ADJ_HEAD) {
-    for (int i = threadIdx.x; i < 96 * 8; i += kGemmThreads) s_w2t[i] = p.w2t[i];
+    for (int i = threadIdx.x; i < 96 * 8; i += gemm_threads(EPI)) s_w2t[i] = p.w2t[i];
     if (threadIdx.x < 8) s_b2[threadIdx.x] = p.b2[threadIdx.x];
   }
   tcgen05_fence_before();
@@ -138,37 +145,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (acc == 0) acc_ph ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (2 groups x 4 warps)
-    // group g drains accumulator g, i.e. every other tile of this CTA, with its own staging buffers
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;
-    const int r_in_tile = q * 32 + lane;
-    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    // ------------------------------------------------------------------ epilogue groups
+    constexpr int kGroups = epi_groups(EPI);
+    constexpr int kHalves = kGroups / 2;           // groups sharing one accumulator
     constexpr bool kOutBf16 = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
-    uint8_t* sOutG = sOut + grp * 2 * C::OUT_CHUNK_BYTES;
-    const int acc = grp;
+    constexpr int kChunkBytes = kOutBf16 ? 128 * 64 : 128 * 128;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;
+    const int acc = grp & 1;
+    const int half = grp >> 1;
+    const int r_in_tile = q * 32 + lane;
+    const int tig = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group
+    const bool issuer = tig == 0;
+    const int bar_id = grp + 1;
+    uint8_t* sOutG = sOut + grp * 2 * kChunkBytes;
+    float* sBiasA = sBias + acc * BN;
     uint32_t acc_ph = 0;
     int chunk_no = 0;  // running count of staged chunks -> staging buffer parity
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
+    for (int tile = blockIdx.x + acc * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
       if (EPI == EPI_ADJ_HEAD) {
+        // columns [48 half, 48 half + 48) of the hidden layer; partial sums of the 96 -> c_e linear are combined
+        // through shared memory (reusing the staging area)
+        float* sPart = reinterpret_cast<float*>(sOut) + acc * 128 * 8;
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // previous tile's bias reads are done
+        if (tig < 48) sBiasA[half * 48 + tig] = p.bias[half * 48 + tig];
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tcgen05_fence_after();
         const int row = m_blk * BM + r_in_tile;
         float y[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = s_b2[c];
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + c0, r);
+        for (int c = 0; c < 8; ++c) y[c] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 48; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x16(t_row + half * 48 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = gelu_erf(__uint_as_float(r[j]) + __ldg(p.bias + c0 + j));
-            const float4 wa = *reinterpret_cast<const float4*>(&s_w2t[(c0 + j) * 8]);
-            const float4 wb = *reinterpret_cast<const float4*>(&s_w2t[(c0 + j) * 8 + 4]);
+          for (int j = 0; j < 16; ++j) {
+            const int col = half * 48 + c0 + j;
+            const float v = gelu_erf(__uint_as_float(r[j]) + sBiasA[col]);
+            const float4 wa = *reinterpret_cast<const float4*>(&s_w2t[col * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&s_w2t[col * 8 + 4]);
             y[0] = fmaf(wa.x, v, y[0]); y[1] = fmaf(wa.y, v, y[1]);
             y[2] = fmaf(wa.z, v, y[2]); y[3] = fmaf(wa.w, v, y[3]);
             y[4] = fmaf(wb.x, v, y[4]); y[5] = fmaf(wb.y, v, y[5]);
@@ -178,35 +198,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (row < p.M) {
-          // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
-          // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
-          const int n = p.n_img;
-          const int nn = n * n;
-          const int b = row / nn;
-          const int ij = row - b * nn;
-          const int i = ij / n, j = ij - i * n;
-          const bool ok = p.flags[b * n + i] != 0 && p.flags[b * n + j] != 0;
-          float cs = 0.f, co = 1.f;
-          if (p.x_adj != nullptr) { cs = p.c_skip[b]; co = p.c_out[b]; }
-          for (int c = 0; c < p.c_e; ++c) {
-            const size_t o = (static_cast<size_t>(b) * p.c_e + c) * nn + ij;
-            float val = y[c];
-            if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs, p.x_adj[o]), __fmul_rn(co, val));
-            reinterpret_cast<float*>(p.out)[o] = ok ? val : 0.f;
+        if (half == 1) {
+          *reinterpret_cast<float4*>(&sPart[r_in_tile * 8]) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(&sPart[r_in_tile * 8 + 4]) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(5 + acc) : "memory");  // both halves of this accumulator
+        if (half == 0) {
+          const float4 pa = *reinterpret_cast<const float4*>(&sPart[r_in_tile * 8]);
+          const float4 pb = *reinterpret_cast<const float4*>(&sPart[r_in_tile * 8 + 4]);
+          y[0] += pa.x + s_b2[0]; y[1] += pa.y + s_b2[1]; y[2] += pa.z + s_b2[2]; y[3] += pa.w + s_b2[3];
+          y[4] += pb.x + s_b2[4]; y[5] += pb.y + s_b2[5]; y[6] += pb.z + s_b2[6]; y[7] += pb.w + s_b2[7];
+          if (row < p.M) {
+            // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
+            // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
+            const int n = p.n_img;
+            const int nn = n * n;
+            const int b = row / nn;
+            const int ij = row - b * nn;
+            const int i = ij / n, j = ij - i * n;
+            const bool ok = p.flags[b * n + i] != 0 && p.flags[b * n + j] != 0;
+            float cs = 0.f, co = 1.f;
+            if (p.x_adj != nullptr) { cs = p.c_skip[b]; co = p.c_out[b]; }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c < p.c_e) {
+                const size_t o = (static_cast<size_t>(b) * p.c_e + c) * nn + ij;
+                float val = y[c];
+                if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs, p.x_adj[o]), __fmul_rn(co, val));
+                reinterpret_cast<float*>(p.out)[o] = ok ? val : 0.f;
+              }
+            }
           }
         }
+        asm volatile("bar.sync %0, 256;" ::"r"(5 + acc) : "memory");  // sPart may be overwritten by the next tile
       } else {
+        // this group's share of the bias slice (its own column chunks), visible after the first chunk barrier
+        if (p.bias != nullptr) {
+          for (int i = tig; i < BN; i += 128)
+            if (((i >> 5) % kHalves) == half) sBiasA[i] = p.bias[n_blk * BN + i];
+        }
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tcgen05_fence_after();
+        constexpr int kChunks = BN / 32;
+        constexpr int kLast = ((kChunks - 1) % kHalves);  // which half owns the last chunk is irrelevant: each half
+        (void)kLast;                                       // signals after ITS last chunk
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk_no) {
-          uint8_t* buf = sOutG + (chunk_no & 1) * C::OUT_CHUNK_BYTES;
+        for (int ci = half; ci < kChunks; ci += kHalves, ++chunk_no) {
+          const int c0 = ci * 32;
+          uint8_t* buf = sOutG + (chunk_no & 1) * kChunkBytes;
           // the bulk store that last read this staging buffer (two chunks ago) must have drained it
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           uint32_t r[32];
           tmem_ld_32x32(t_row + c0, r);
           tmem_ld_wait();
-          if (c0 + 32 >= BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          if (ci + kHalves >= kChunks) {  // this group's last chunk: its warps are done with the accumulator
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -218,7 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+              const float4 b = *reinterpret_cast<const float4*>(&sBiasA[c0 + j]);
               v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
@@ -248,7 +294,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (issuer) {
             if (EPI == EPI_RES_F32) {
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
@@ -313,7 +359,7 @@ int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* 
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
+  gemm_kernel<BN, EPI><<<grid, gemm_threads(EPI), Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

@@ -5,6 +5,7 @@
 // are static per (model, batch), so the whole forward is CUDA-graph capturable (no host sync, no allocation).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -35,8 +36,9 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned 
 // ------------------------------------------------------------------------------------------------
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
 // ------------------------------------------------------------------------------------------------
-enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"gemm_tcgen05", "window_attention", "row_ln_film", "embed_heads_cond", "edm_step"};
+enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_MLP, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"gemm_tcgen05", "window_attention", "row_ln_film", "embed_heads_cond", "edm_step",
+                                           "fused_mlp_tcgen05"};
 struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;        // between dsg_profile_begin and dsg_profile_stop
 static bool g_prof_pass = false;      // the current denoiser pass is being bracketed
@@ -94,6 +96,7 @@ struct Block {
   int dim, res, heads, window, shift, stage;
   int film_off;        // column of (scale, shift) in the film row
   Weight qkv, proj, fc1, fc2;
+  CUtensorMap mlp_w1, mlp_w2;  // descriptors of fc1 / fc2 with the fused-MLP box shapes (C = 96, 192)
   size_t qkv_bias_off;  // fp32 [3C], q part pre-scaled
   size_t attn_bias_off; // fp32 [heads, T, T]
 };
@@ -125,6 +128,7 @@ struct dsg_model {
   size_t arena_bytes = 0;
   uint8_t* arena = nullptr;
   bool finalized = false;
+  bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -427,6 +431,20 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   // x = x + proj(attn)                                                   (:137, :272)
   DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
   // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
+  if (m->use_fused_mlp && fused_mlp_supported(C)) {
+    auto okey = std::make_tuple(static_cast<const void*>(w.X), rows, -(C * 8 + EPI_RES_F32));
+    auto ot = m->a_maps.find(okey);
+    if (ot == m->a_maps.end()) {
+      CUtensorMap tm;
+      DSG_TRY(make_tmap_out(&tm, w.X, rows, C, EPI_RES_F32));
+      ot = m->a_maps.emplace(okey, tm).first;
+    }
+    DSG_TRY_P(PC_MLP, 16.0 * rc * C, rc * 12,
+              launch_fused_mlp(&b.mlp_w1, &b.mlp_w2, &ot->second, w.X, m->f32(p + ".norm2.weight"),
+                               m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"), m->f32(p + ".mlp.fc2.bias"),
+                               rows, C, st));
+    return DSG_OK;
+  }
   DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
   DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));
   DSG_TRY(gemm(m, w.H, rows, b.fc2, EPI_RES_F32, m->f32(p + ".mlp.fc2.bias"), w.X, w.X, st));
@@ -448,6 +466,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   DSG_REQUIRE(cfg != nullptr && out != nullptr, "dsg_model_create: null argument");
   dsg_model* m = new dsg_model();
   m->cfg = *cfg;
+  const char* no_fuse = getenv("DSG_NO_FUSED_MLP");
+  m->use_fused_mlp = !(no_fuse != nullptr && no_fuse[0] == '1');
   const int rc = build(m);
   if (rc) { delete m; return rc; }
   *out = m;
@@ -512,6 +532,10 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
     DSG_TRY(pack_weight(m, b.proj, p + ".attn.proj.weight", st));
     DSG_TRY(pack_weight(m, b.fc1, p + ".mlp.fc1.weight", st));
     DSG_TRY(pack_weight(m, b.fc2, p + ".mlp.fc2.weight", st));
+    if (fused_mlp_supported(C)) {
+      DSG_TRY(make_tmap_bf16(&b.mlp_w1, m->arena + b.fc1.offset, 4 * C, C, fused_mlp_w1_box_rows(C)));
+      DSG_TRY(make_tmap_bf16(&b.mlp_w2, m->arena + b.fc2.offset, C, 4 * C, C));
+    }
     const TensorSpec& idx = m->tensors[m->index[p + ".attn.relative_position_index"]];
     DSG_TRY(launch_bias_expand(m->f32(p + ".attn.relative_position_bias_table"),
                                reinterpret_cast<const int64_t*>(m->arena + idx.offset), m->at<float>(b.attn_bias_off), T,

@@ -363,21 +363,30 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
     float v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = sB[e];
-    // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]
-    for (int ch = 0; ch < planes; ++ch) {
-      float a;
-      if (self_cond && ch < c_e) {
-        a = sc_adj ? sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij] : 0.f;
-      } else {
-        const int c = self_cond ? ch - c_e : ch;
-        a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
-      }
-      const float4* w4 = reinterpret_cast<const float4*>(&sW[ch * E]);
+    // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]; all loads are issued before the first use
+    float a[16];
 #pragma unroll
-      for (int e4 = 0; e4 < E / 4; ++e4) {
-        const float4 w = w4[e4];
-        v[4 * e4] = fmaf(w.x, a, v[4 * e4]); v[4 * e4 + 1] = fmaf(w.y, a, v[4 * e4 + 1]);
-        v[4 * e4 + 2] = fmaf(w.z, a, v[4 * e4 + 2]); v[4 * e4 + 3] = fmaf(w.w, a, v[4 * e4 + 3]);
+    for (int ch = 0; ch < 16; ++ch) {
+      a[ch] = 0.f;
+      if (ch < planes) {
+        if (self_cond && ch < c_e) {
+          if (sc_adj) a[ch] = sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij];
+        } else {
+          const int c = self_cond ? ch - c_e : ch;
+          a[ch] = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      if (ch < planes) {
+        const float4* w4 = reinterpret_cast<const float4*>(&sW[ch * E]);
+#pragma unroll
+        for (int e4 = 0; e4 < E / 4; ++e4) {
+          const float4 w = w4[e4];
+          v[4 * e4] = fmaf(w.x, a[ch], v[4 * e4]); v[4 * e4 + 1] = fmaf(w.y, a[ch], v[4 * e4 + 1]);
+          v[4 * e4 + 2] = fmaf(w.z, a[ch], v[4 * e4 + 2]); v[4 * e4 + 3] = fmaf(w.w, a[ch], v[4 * e4 + 3]);
+        }
       }
     }
     if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)

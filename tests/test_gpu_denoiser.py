@@ -113,6 +113,27 @@ def test_forward_matches_golden(name, batch, golden_dir):
     assert float(a[~pair].abs().sum()) == 0.0 and float(n[~flags].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("name,batch", [("tiny", 5), ("vg", 3)])
+def test_fused_mlp_matches_unfused_schedule(name, batch):
+    """The fused LN + fc1 + GELU + fc2 kernel against the LayerNorm kernel + two GEMMs it replaces (same bf16
+    roundings of the LN output and of the hidden activation; only the fp32 accumulation order differs)."""
+    cfg = CONFIGS[name]
+    inputs = [t.to(DEV) for t in synthetic_inputs(cfg, batch, seed=11)]
+    adj, node, flags, sigmas, sc_adj, sc_node = inputs
+    outs = []
+    for no_fuse in ("0", "1"):
+        os.environ["DSG_NO_FUSED_MLP"] = no_fuse
+        try:
+            model, _ = build(cfg)
+            with torch.no_grad():
+                outs.append(model(adj, node, flags, sigmas.log() / 4, sc_adj, sc_node))
+        finally:
+            os.environ.pop("DSG_NO_FUSED_MLP", None)
+    (fa, fn), (ua, un) = outs
+    assert torch.isfinite(fa).all() and torch.isfinite(fn).all()
+    assert rel(fa, ua) < 3e-3 and rel(fn, un) < 3e-3, (rel(fa, ua), rel(fn, un))
+
+
 def test_forward_uniform_vs_per_sample_sigma():
     cfg = CONFIGS["tiny"]
     model, _ = build(cfg)
