@@ -58,15 +58,15 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
                 cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
-// fused MLP:  x += fc2(gelu(fc1(LN(x))))                                 (mlp.cu)
+// fused MLP:  x += fc2(gelu(fc1(y))), y = LN(x) in bf16                 (mlp.cu)
 // ---------------------------------------------------------------------------------------------
-// Built for C = 96 and 192 (hidden 4C).  tmW1: fc1.weight [4C, C] bf16, box 64 x fused_mlp_w1_box_rows(C);
-// tmW2: fc2.weight [C, 4C] bf16, box 64 x C; tmX: x [rows, C] fp32 output descriptor (make_tmap_out, EPI_RES_F32).
+// Built for C = 96 and 192 (hidden 4C).  tmY: y [rows, C] bf16, box 64 x 128 (make_tmap_bf16); tmW1: fc1.weight
+// [4C, C] bf16, box 64 x fused_mlp_w1_box_rows(C); tmW2: fc2.weight [C, 4C] bf16, box 64 x C; tmX: x [rows, C] fp32
+// output descriptor (make_tmap_out, EPI_RES_F32).
 bool fused_mlp_supported(int C);
 int fused_mlp_w1_box_rows(int C);
-int launch_fused_mlp(const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX, float* x,
-                     const float* gamma, const float* beta, const float* b1, const float* b2, long long rows, int C,
-                     cudaStream_t st);
+int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
+                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // shifted-window attention                                             (attention.cu)

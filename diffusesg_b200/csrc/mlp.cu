@@ -1,18 +1,16 @@
-// Fused transformer MLP for sm_100a:   x += fc2(gelu(fc1(LayerNorm(x))))          (one kernel per Swin block)
+// Fused transformer MLP for sm_100a:   x += fc2(gelu(fc1(y))),  y = LayerNorm(x) in bf16   (one kernel per Swin block)
 //
 // Restates `x = x + self.mlp(self.norm2(x))` (model/diffusesg/diffusesg.py:275 with Mlp.forward :19-25) of the
-// reference.  Unfused this is a LayerNorm kernel and two GEMMs whose 4C-wide hidden activation makes two round
-// trips through HBM (26 C bytes per token); here the hidden activation never leaves the SM (10 C bytes per token:
-// read x once, reduce-add once).
+// reference.  Unfused this is two GEMMs whose 4C-wide hidden activation makes two round trips through HBM
+// (16 C bytes per token); here the hidden activation never leaves the SM.
 //
-// Per persistent CTA and 128-token tile:
-//   worker warps (16)  LayerNorm of the tile (rows prefetched into registers during the previous tile) -> bf16
-//                      A operand written straight into the 128-byte-swizzled K-major layout tcgen05 expects
-//   MMA warp           acc1[j&1] = A . W1[chunk j]^T          (TMEM, double buffered, hidden chunks of HC columns)
-//   worker warps       tcgen05.ld acc1 -> + b1 -> exact-erf GELU -> bf16 -> swizzled smem H chunk
-//   MMA warp           acc2     += H[chunk j] . W2[:, chunk j]^T   (TMEM, C columns)
-//   worker warps       tcgen05.ld acc2 -> + b2 -> swizzled fp32 staging -> TMA reduce-add into x
-//   TMA warp           streams the W1 / W2 k-blocks of every chunk through a 4-stage mbarrier ring (L2 resident)
+// The hidden dimension is cut into chunks of HC columns that form ONE stream across the tiles of a persistent CTA
+// (global chunk index g): fc1 of chunk g + 2 is issued right after fc2 of chunk g, also across a tile boundary, so
+// the tensor pipe never waits for the workers and the workers never wait for the tensor pipe.
+//   TMA warp           y tile [128 x C] (once per tile) and the W1 / W2 k-blocks of every chunk (4-stage ring)
+//   MMA warp           acc1[g&1] = y . W1[chunk]^T  (TMEM, double buffered);  acc2 += H[chunk] . W2[:, chunk]^T
+//   worker warps (16)  tcgen05.ld acc1 -> + b1 -> exact-erf GELU -> bf16 -> 128-byte-swizzled K-major smem H chunk;
+//                      after the last chunk of a tile: tcgen05.ld acc2 -> + b2 -> fp32 staging -> TMA reduce-add into x
 #include "common.cuh"
 #include "kernels.h"
 
@@ -34,22 +32,16 @@ struct MlpCfg {
   static constexpr int STAGE_BYTES = ((HC > C) ? HC : C) * 128;  // one weight k-block: [rows x 64] bf16
   static constexpr int kStages = 4;
   static constexpr int STG_BYTES = 2 * 16384;           // fp32 output staging, 2 x [128 x 32]
-  static constexpr int PAR_FLOATS = HID + 3 * C;        // b1, b2, gamma, beta
+  static constexpr int PAR_FLOATS = HID + C;            // b1, b2
   static constexpr int SMEM_BYTES = 1024 + A_BYTES + H_BYTES + kStages * STAGE_BYTES + STG_BYTES + PAR_FLOATS * 4 + 256;
   static constexpr int ACC2_COL = 2 * HC;               // TMEM: acc1[0] @0, acc1[1] @HC, acc2 @2HC
-  static constexpr int LPR = C / 12;                    // lanes per LayerNorm row (12 floats per lane)
-  static constexpr int ROWS_PER_PASS = kWorkers / LPR;  // 64 / 32
-  static constexpr int PASSES = 128 / ROWS_PER_PASS;    // 2 / 4
   static constexpr int CQ = HC / 4;                     // GELU columns per warp: 48 / 32
   static_assert(NCH % 2 == 0 && ACC2_COL + C <= 512 && SMEM_BYTES <= 227 * 1024, "fused MLP budget");
 };
 
 struct MlpParams {
-  float* x;            // [M, C] fp32, updated in place through the reduce-add descriptor
-  const float* gamma;  // norm2
-  const float* beta;
-  const float* b1;     // [4C]
-  const float* b2;     // [C]
+  const float* b1;  // [4C]
+  const float* b2;  // [C]
   int M;
 };
 
@@ -62,8 +54,8 @@ DSG_DEVICE uint32_t sw128_offset(int r, int k) {
 template <int C>
 // 18 warps -> 5 on the fullest SM sub-partition (16K registers each): at most 96 registers per thread
 __global__ void __launch_bounds__(kMlpThreads, 1)
-fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmX, const MlpParams p) {
+fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX, const MlpParams p) {
   using G = MlpCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   // round up to 1024 bytes (128-byte swizzle atoms) without casting through an integer, so that the compiler
@@ -76,12 +68,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   float* sPar = reinterpret_cast<float*>(sStg + G::STG_BYTES);
   float* sB1 = sPar;
   float* sB2 = sPar + G::HID;
-  float* sGam = sB2 + C;
-  float* sBet = sGam + C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + G::PAR_FLOATS);
   uint64_t* w_full = bars;                    // [kStages]
   uint64_t* w_empty = bars + G::kStages;      // [kStages]
-  uint64_t* a_full = bars + 2 * G::kStages;   // workers -> MMA: LN tile written
+  uint64_t* a_full = bars + 2 * G::kStages;   // TMA -> MMA: y tile landed
   uint64_t* a_empty = a_full + 1;             // MMA -> workers: every fc1 MMA of the tile has read sA
   uint64_t* acc1_full = a_full + 2;           // [2]
   uint64_t* acc1_empty = a_full + 4;          // [2]
@@ -96,11 +86,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   const int num_tiles = (p.M + 127) / 128;
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < G::kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, 16); mbar_init(a_empty, 1);
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], 16); }
     mbar_init(h_full, 16); mbar_init(h_empty, 1);
     mbar_init(acc2_full, 1); mbar_init(acc2_empty, 8);
@@ -108,18 +99,28 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   for (int i = threadIdx.x; i < G::HID; i += kMlpThreads) sB1[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += kMlpThreads) { sB2[i] = p.b2[i]; sGam[i] = p.gamma[i]; sBet[i] = p.beta[i]; }
+  for (int i = threadIdx.x; i < C; i += kMlpThreads) sB2[i] = p.b2[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x)) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int n_chunks = my_tiles * G::NCH;  // global chunk stream of this CTA
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer: weight k-blocks
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
-      auto load_w1 = [&](int j) {
+      uint32_t ph = 0, n_tile = 0;
+      auto load_fc1 = [&](int g) {  // operands of fc1 of chunk g: (the y tile, once per tile,) W1[chunk]
+        const int j = g % G::NCH;
+        if (j == 0) {
+          const int tile = blockIdx.x + (g / G::NCH) * gridDim.x;
+          mbar_wait(a_empty, (n_tile & 1) ^ 1);  // every fc1 MMA of the previous tile has read sA
+          ++n_tile;
+          mbar_expect_tx(a_full, G::A_BYTES);
+          for (int kb = 0; kb < G::KB1; ++kb) tma_load_2d(sA + kb * 16384, &tmY, a_full, kb * 64, tile * 128);
+        }
         for (int kb = 0; kb < G::KB1; ++kb) {
           mbar_wait(&w_empty[s], ph ^ 1);
           mbar_expect_tx(&w_full[s], G::HC * 128);
@@ -127,7 +128,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           if (++s == G::kStages) { s = 0; ph ^= 1; }
         }
       };
-      auto load_w2 = [&](int j) {
+      auto load_w2 = [&](int g) {
+        const int j = g % G::NCH;
         for (int kb = 0; kb < G::KB2; ++kb) {
           mbar_wait(&w_empty[s], ph ^ 1);
           mbar_expect_tx(&w_full[s], C * 128);
@@ -135,13 +137,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           if (++s == G::kStages) { s = 0; ph ^= 1; }
         }
       };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        load_w1(0);
-        load_w1(1);
-        for (int j = 0; j < G::NCH; ++j) {
-          load_w2(j);
-          if (j + 2 < G::NCH) load_w1(j + 2);
-        }
+      if (n_chunks > 0) load_fc1(0);
+      if (n_chunks > 1) load_fc1(1);
+      for (int g = 0; g < n_chunks; ++g) {
+        load_w2(g);
+        if (g + 2 < n_chunks) load_fc1(g + 2);
       }
     }
   } else if (warp == 1) {
@@ -151,8 +151,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     int s = 0;
     uint32_t ph = 0;
     uint32_t n_a = 0, n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0;  // use counters -> mbarrier parities
-    auto fc1 = [&](int j) {  // acc1[j & 1] = A . W1[chunk j]^T
-      const int b = j & 1;
+    auto fc1 = [&](int g) {  // acc1[g & 1] = y . W1[chunk]^T
+      const int b = g & 1, j = g % G::NCH;
+      if (j == 0) {
+        mbar_wait(a_full, n_a & 1);
+        ++n_a;
+      }
       mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
       ++n_acc1[b];
       tcgen05_fence_after();
@@ -172,111 +176,50 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       }
       if (lane == 0) {
         umma_commit(&acc1_full[b]);
-        if (j == G::NCH - 1) umma_commit(a_empty);  // sA may be rewritten once every fc1 MMA has completed
+        if (j == G::NCH - 1) umma_commit(a_empty);  // sA may be refilled once every fc1 MMA of the tile completed
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(a_full, n_a & 1);
-      ++n_a;
+    if (n_chunks > 0) fc1(0);
+    if (n_chunks > 1) fc1(1);
+    for (int g = 0; g < n_chunks; ++g) {
+      const int j = g % G::NCH;
+      mbar_wait(h_full, n_h & 1);
+      ++n_h;
+      if (j == 0) {
+        mbar_wait(acc2_empty, (n_acc2 & 1) ^ 1);  // the previous tile's output phase has drained acc2
+        ++n_acc2;
+      }
       tcgen05_fence_after();
-      fc1(0);
-      fc1(1);
-      for (int j = 0; j < G::NCH; ++j) {
-        mbar_wait(h_full, n_h & 1);
-        ++n_h;
-        if (j == 0) {
-          mbar_wait(acc2_empty, (n_acc2 & 1) ^ 1);
-          ++n_acc2;
-        }
+      for (int kb = 0; kb < G::KB2; ++kb) {  // acc2 += H[chunk] . W2[:, chunk]^T
+        mbar_wait(&w_full[s], ph);
         tcgen05_fence_after();
-        for (int kb = 0; kb < G::KB2; ++kb) {  // acc2 += H[chunk j] . W2[:, chunk j]^T
-          mbar_wait(&w_full[s], ph);
-          tcgen05_fence_after();
-          if (lane == 0) {
-            const uint64_t da = umma_desc_sw128(smem_u32(sH + kb * 16384));
-            const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + G::ACC2_COL, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
-            umma_commit(&w_empty[s]);
-          }
-          __syncwarp();
-          if (++s == G::kStages) { s = 0; ph ^= 1; }
-        }
         if (lane == 0) {
-          umma_commit(h_empty);
-          if (j == G::NCH - 1) umma_commit(acc2_full);
+          const uint64_t da = umma_desc_sw128(smem_u32(sH + kb * 16384));
+          const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + G::ACC2_COL, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
+          umma_commit(&w_empty[s]);
         }
         __syncwarp();
-        if (j + 2 < G::NCH) fc1(j + 2);
+        if (++s == G::kStages) { s = 0; ph ^= 1; }
       }
+      if (lane == 0) {
+        umma_commit(h_empty);
+        if (j == G::NCH - 1) umma_commit(acc2_full);
+      }
+      __syncwarp();
+      if (g + 2 < n_chunks) fc1(g + 2);
     }
   } else {
-    // ------------------------------------------------------------------ workers: LayerNorm, GELU, output
+    // ------------------------------------------------------------------ workers: GELU chunks, tile output
     const int w = warp - 2;                 // 0..15
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const int cg = w >> 2;                  // column group 0..3
-    const int wt = w * 32 + lane;           // worker thread index 0..511
-    const int sub = wt % G::LPR;            // lane inside the LayerNorm row group
-    const int r_ln = wt / G::LPR;           // row inside a LayerNorm pass
-    const int r_t = q * 32 + lane;          // accumulator row owned in the GELU / output phases
+    const int r_t = q * 32 + lane;          // accumulator row owned by this thread
     // the four warps of a column group hold warp indices 2+4cg .. 5+4cg: elect the first as the TMA-store issuer
     const bool store_issuer = ((w & 3) == 0) && lane == 0;
-    uint32_t n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0, n_aempty = 0;
-
-    float4 xr[G::PASSES][3];  // prefetched rows of the next tile
-    auto prefetch = [&](int tile) {
-#pragma unroll
-      for (int ps = 0; ps < G::PASSES; ++ps) {
-        const long long row = static_cast<long long>(tile) * 128 + ps * G::ROWS_PER_PASS + r_ln;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          xr[ps][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < p.M) xr[ps][i] = *reinterpret_cast<const float4*>(p.x + row * C + (sub + G::LPR * i) * 4);
-        }
-      }
-    };
-    if (static_cast<int>(blockIdx.x) < num_tiles) prefetch(blockIdx.x);
-
-    // LayerNorm of the tile held in xr -> sA (bf16, swizzled K-major), then start fetching the tile after it
-    auto layer_norm_to_smem = [&](int next_tile) {
-      mbar_wait(a_empty, (n_aempty & 1) ^ 1);
-      ++n_aempty;
-#pragma unroll
-      for (int ps = 0; ps < G::PASSES; ++ps) {
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sum += (xr[ps][i].x + xr[ps][i].y) + (xr[ps][i].z + xr[ps][i].w);
-#pragma unroll
-        for (int o = G::LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum / C;
-        float var = 0.f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          xr[ps][i].x -= mean; xr[ps][i].y -= mean; xr[ps][i].z -= mean; xr[ps][i].w -= mean;
-          var += (xr[ps][i].x * xr[ps][i].x + xr[ps][i].y * xr[ps][i].y) + (xr[ps][i].z * xr[ps][i].z + xr[ps][i].w * xr[ps][i].w);
-        }
-#pragma unroll
-        for (int o = G::LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-        const float rstd = rsqrtf(var / C + 1e-5f);
-        const int r = ps * G::ROWS_PER_PASS + r_ln;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int e = (sub + G::LPR * i) * 4;
-          const float4 gm = *reinterpret_cast<const float4*>(&sGam[e]);
-          const float4 bt = *reinterpret_cast<const float4*>(&sBet[e]);
-          uint2 pk;
-          pk.x = pack_bf16x2(fmaf(xr[ps][i].x * rstd, gm.x, bt.x), fmaf(xr[ps][i].y * rstd, gm.y, bt.y));
-          pk.y = pack_bf16x2(fmaf(xr[ps][i].z * rstd, gm.z, bt.z), fmaf(xr[ps][i].w * rstd, gm.w, bt.w));
-          *reinterpret_cast<uint2*>(sA + sw128_offset(r, e) + (e & 7) * 2) = pk;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
-      if (next_tile < num_tiles) prefetch(next_tile);  // in flight during the GELU phases
-    };
-    if (static_cast<int>(blockIdx.x) < num_tiles) layer_norm_to_smem(blockIdx.x + gridDim.x);
+    uint32_t n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 -> sH
@@ -287,37 +230,34 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         ++n_acc1[b];
         tcgen05_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * G::HC + cg * G::CQ;
-        uint32_t hp[G::CQ / 2];  // packed bf16 pairs
 #pragma unroll
         for (int c0 = 0; c0 < G::CQ; c0 += 16) {
           uint32_t r[16];
           tmem_ld_32x16(t_addr + c0, r);
           tmem_ld_wait();
+          if (c0 + 16 >= G::CQ) {  // accumulator drained by this warp: fc1 of chunk g + 2 may overwrite it
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc1_empty[b]);
+          }
+          uint32_t hp[8];  // packed bf16 pairs
 #pragma unroll
           for (int k = 0; k < 16; k += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * G::CQ + c0 + k]);
-            hp[(c0 + k) >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
-            hp[((c0 + k) >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+            hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
+            hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
           }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[b]);  // accumulator drained: fc1 of chunk j + 2 may start
-        mbar_wait(h_empty, (n_h & 1) ^ 1);           // fc2 of the previous chunk has finished reading sH
-        ++n_h;
-#pragma unroll
-        for (int c8 = 0; c8 < G::CQ; c8 += 8) {
-          const uint4 v = make_uint4(hp[c8 / 2], hp[c8 / 2 + 1], hp[c8 / 2 + 2], hp[c8 / 2 + 3]);
-          *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c8)) = v;
+          if (c0 == 0) {
+            mbar_wait(h_empty, (n_h & 1) ^ 1);  // fc2 of the previous chunk has finished reading sH
+            ++n_h;
+          }
+          *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0 + 8)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(h_full);
       }
-
-      // ---- LayerNorm of the NEXT tile before this tile's output phase: the MMA warp can run fc2 of the last
-      //      chunk and fc1 of the next tile while the workers drain acc2
-      if (tile + static_cast<int>(gridDim.x) < num_tiles) layer_norm_to_smem(tile + 2 * gridDim.x);
 
       // ---- output: acc2 + b2 -> reduce-add into x (column groups 0 and 1, 32-column chunks)
       if (cg < 2) {
@@ -368,8 +308,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 }
 
 template <int C>
-int launch_c(const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX, const MlpParams& p,
-             cudaStream_t st) {
+int launch_c(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
+             const MlpParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(fused_mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -384,7 +324,7 @@ int launch_c(const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap
     if (sms <= 0) sms = 148;
   }
   const int tiles = (p.M + 127) / 128;
-  fused_mlp_kernel<C><<<tiles < sms ? tiles : sms, kMlpThreads, MlpCfg<C>::SMEM_BYTES, st>>>(*tmW1, *tmW2, *tmX, p);
+  fused_mlp_kernel<C><<<tiles < sms ? tiles : sms, kMlpThreads, MlpCfg<C>::SMEM_BYTES, st>>>(*tmY, *tmW1, *tmW2, *tmX, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -394,13 +334,12 @@ int launch_c(const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap
 bool fused_mlp_supported(int C) { return C == 96 || C == 192; }
 int fused_mlp_w1_box_rows(int C) { return C == 96 ? 192 : 128; }
 
-int launch_fused_mlp(const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX, float* x,
-                     const float* gamma, const float* beta, const float* b1, const float* b2, long long rows, int C,
-                     cudaStream_t st) {
+int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
+                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st) {
   DSG_REQUIRE(fused_mlp_supported(C) && rows > 0 && rows < 2147483647LL, "fused_mlp: C=%d rows=%lld", C, rows);
-  MlpParams p{x, gamma, beta, b1, b2, static_cast<int>(rows)};
-  if (C == 96) return launch_c<96>(tmW1, tmW2, tmX, p, st);
-  return launch_c<192>(tmW1, tmW2, tmX, p, st);
+  MlpParams p{b1, b2, static_cast<int>(rows)};
+  if (C == 96) return launch_c<96>(tmY, tmW1, tmW2, tmX, p, st);
+  return launch_c<192>(tmY, tmW1, tmW2, tmX, p, st);
 }
 
 }  // namespace dsg

@@ -431,21 +431,26 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   // x = x + proj(attn)                                                   (:137, :272)
   DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
   // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
+  DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
   if (m->use_fused_mlp && fused_mlp_supported(C)) {
-    auto okey = std::make_tuple(static_cast<const void*>(w.X), rows, -(C * 8 + EPI_RES_F32));
-    auto ot = m->a_maps.find(okey);
-    if (ot == m->a_maps.end()) {
-      CUtensorMap tm;
-      DSG_TRY(make_tmap_out(&tm, w.X, rows, C, EPI_RES_F32));
-      ot = m->a_maps.emplace(okey, tm).first;
-    }
-    DSG_TRY_P(PC_MLP, 16.0 * rc * C, rc * 12,
-              launch_fused_mlp(&b.mlp_w1, &b.mlp_w2, &ot->second, w.X, m->f32(p + ".norm2.weight"),
-                               m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"), m->f32(p + ".mlp.fc2.bias"),
-                               rows, C, st));
+    auto tmap = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
+      auto k = std::make_tuple(ptr, rows, key);
+      auto it = m->a_maps.find(k);
+      if (it == m->a_maps.end()) {
+        CUtensorMap tm;
+        if (make(&tm)) return nullptr;
+        it = m->a_maps.emplace(k, tm).first;
+      }
+      return &it->second;
+    };
+    const CUtensorMap* ty = tmap(w.Y, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.Y, rows, C, 128); });
+    const CUtensorMap* tx = tmap(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
+    if (ty == nullptr || tx == nullptr) return DSG_ERR_CUDA;
+    DSG_TRY_P(PC_MLP, 16.0 * rc * C, rc * 10,
+              launch_fused_mlp(ty, &b.mlp_w1, &b.mlp_w2, tx, m->f32(p + ".mlp.fc1.bias"), m->f32(p + ".mlp.fc2.bias"), rows,
+                               C, st));
     return DSG_OK;
   }
-  DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
   DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));
   DSG_TRY(gemm(m, w.H, rows, b.fc2, EPI_RES_F32, m->f32(p + ".mlp.fc2.bias"), w.X, w.X, st));
   return DSG_OK;
