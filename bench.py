@@ -188,6 +188,7 @@ def run_native(args, cfg, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DSG_NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout
         dist.init_process_group("nccl", device_id=device)
     native.lib()
     torch.manual_seed(1234 + rank)   # the reference offsets the seed by the rank (utils/arg_parser.py:293-294)

@@ -90,6 +90,44 @@ edm_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const flo
   }
 }
 
+// Decode of the final sample (runner/sampler/sampler_node_adj.py:199-285 of the reference, 'bits' encodings):
+//   class = clamp(bin2dec(x > 0, MSB first), 0, num_types - 1), masked; self-loops removed; box = x * 0.5 + 0.5, masked.
+// (clamp(x, -1, 1) > 0 == x > 0, so the reference's clamp -> sign -> gt(0) chain collapses to one comparison.)
+__global__ void __launch_bounds__(256)
+decode_kernel(const float* __restrict__ adj, const float* __restrict__ node, const uint8_t* __restrict__ flags,
+              int32_t* __restrict__ adj_cls, int32_t* __restrict__ node_cls, float* __restrict__ bbox, int num_adj_type,
+              int num_node_type, EdmShape sh) {
+  const int n = sh.n, nn = sh.n * sh.n;
+  const long long pixels = static_cast<long long>(sh.batch) * nn;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (long long px = tid; px < pixels; px += stride) {
+    const int b = static_cast<int>(px / nn);
+    const int ij = static_cast<int>(px - static_cast<long long>(b) * nn);
+    const int i = ij / n, j = ij - i * n;
+    int v = 0;
+    if (i != j && flags[b * n + i] != 0 && flags[b * n + j] != 0) {
+      for (int c = 0; c < sh.c_e; ++c) v = (v << 1) | (adj[(static_cast<size_t>(b) * sh.c_e + c) * nn + ij] > 0.0f ? 1 : 0);
+      v = v < 0 ? 0 : (v > num_adj_type - 1 ? num_adj_type - 1 : v);
+    }
+    adj_cls[px] = v;
+  }
+  const int nb = sh.c_n - 4;  // class bits; the last four node channels are the box
+  const long long nodes = static_cast<long long>(sh.batch) * n;
+  for (long long bi = tid; bi < nodes; bi += stride) {
+    const bool ok = flags[bi] != 0;
+    const float* x = node + bi * sh.c_n;
+    int v = 0;
+    if (ok) {
+      for (int c = 0; c < nb; ++c) v = (v << 1) | (x[c] > 0.0f ? 1 : 0);
+      v = v < 0 ? 0 : (v > num_node_type - 1 ? num_node_type - 1 : v);
+    }
+    node_cls[bi] = v;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bbox[bi * 4 + c] = ok ? __fadd_rn(__fmul_rn(x[nb + c], 0.5f), 0.5f) : 0.f;
+  }
+}
+
 template <int MODE>
 int launch_mode(const float* a0, const float* a1, const float* a2, float* a_out, const float* n0, const float* n1,
                 const float* n2, float* n_out, const uint8_t* flags, float s0, float s1, float s2, int batch, int c_e,
@@ -129,6 +167,20 @@ int launch_edm_post_step(const float* adj_hat, const float* node_hat, const floa
                           inv_t_prime, batch, c_e, n, c_n, st);
   return launch_mode<2>(adj_hat, d1_adj, nullptr, adj_next, node_hat, d1_node, nullptr, node_next, flags, inv_t_hat, h,
                         0.f, batch, c_e, n, c_n, st);
+}
+
+int launch_decode(const float* adj, const float* node, const uint8_t* flags, int32_t* adj_cls, int32_t* node_cls,
+                  float* bbox, int num_adj_type, int num_node_type, int batch, int c_e, int n, int c_n, cudaStream_t st) {
+  DSG_REQUIRE(batch > 0 && c_e > 0 && c_e <= 30 && n > 0 && c_n > 4 && c_n - 4 <= 30 && num_adj_type > 0 && num_node_type > 0,
+              "decode: bad shape B=%d C_e=%d N=%d C_n=%d", batch, c_e, n, c_n);
+  const long long pixels = static_cast<long long>(batch) * n * n;
+  long long blocks = (pixels + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  EdmShape sh{batch, c_e, n, c_n};
+  decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(adj, node, flags, adj_cls, node_cls, bbox, num_adj_type,
+                                                              num_node_type, sh);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
 }
 
 int launch_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,

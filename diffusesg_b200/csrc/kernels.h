@@ -66,7 +66,8 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
 bool fused_mlp_supported(int C);
 int fused_mlp_w1_box_rows(int C);
 int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
-                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st);
+                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st,
+                     long long* trace = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // shifted-window attention                                             (attention.cu)
@@ -131,6 +132,10 @@ int launch_edm_post_step(const float* adj_hat, const float* node_hat, const floa
                          int n, int c_n, cudaStream_t st);
 int launch_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
                       float* node_out, int batch, int c_e, int n, int c_n, cudaStream_t st);
+
+// bits -> class ids (+ boxes) of the final sample; adj_cls [B, n, n], node_cls [B, n] int32, bbox [B, n, 4]
+int launch_decode(const float* adj, const float* node, const uint8_t* flags, int32_t* adj_cls, int32_t* node_cls,
+                  float* bbox, int num_adj_type, int num_node_type, int batch, int c_e, int n, int c_n, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // weight packing helpers (run once per weight update)                  (pack.cu)

@@ -40,10 +40,17 @@ struct MlpCfg {
 };
 
 struct MlpParams {
-  const float* b1;  // [4C]
-  const float* b2;  // [C]
+  const float* b1;   // [4C]
+  const float* b2;   // [C]
   int M;
+  long long* trace;  // test hook: clock64 timeline of CTA 0 ([chunk < 64][warp < 18][event < 8]) or nullptr
 };
+
+#define DSG_MLP_TRACE(g, ev)                                                                         \
+  do {                                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (g) < 64)                              \
+      p.trace[(static_cast<size_t>(g) * 18 + warp) * 8 + (ev)] = clock64();                          \
+  } while (0)
 
 // byte offset of the 16-byte chunk holding elements [k, k + 8) of row r in a K-major 128-byte-swizzled operand
 // made of [128 rows x 64 bf16] k-blocks (what TMA SWIZZLE_128B writes and the UMMA descriptor reads)
@@ -160,9 +167,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
       ++n_acc1[b];
       tcgen05_fence_after();
+      DSG_MLP_TRACE(g, 0);  // fc1(g): accumulator and y tile available
       for (int kb = 0; kb < G::KB1; ++kb) {
         mbar_wait(&w_full[s], ph);
         tcgen05_fence_after();
+        if (kb == G::KB1 - 1) DSG_MLP_TRACE(g, 1);  // fc1(g): last W1 k-block landed
         if (lane == 0) {
           const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
@@ -191,9 +200,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ++n_acc2;
       }
       tcgen05_fence_after();
+      DSG_MLP_TRACE(g, 2);  // fc2(g): H chunk written (and acc2 free)
       for (int kb = 0; kb < G::KB2; ++kb) {  // acc2 += H[chunk] . W2[:, chunk]^T
         mbar_wait(&w_full[s], ph);
         tcgen05_fence_after();
+        if (kb == G::KB2 - 1) DSG_MLP_TRACE(g, 3);  // fc2(g): last W2 k-block landed
         if (lane == 0) {
           const uint64_t da = umma_desc_sw128(smem_u32(sH + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
@@ -221,14 +232,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const bool store_issuer = ((w & 3) == 0) && lane == 0;
     uint32_t n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0;
 
+    int g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 -> sH
 #pragma unroll 1
-      for (int j = 0; j < G::NCH; ++j) {
+      for (int j = 0; j < G::NCH; ++j, ++g) {
         const int b = j & 1;
+        DSG_MLP_TRACE(g, 0);  // worker: ready for chunk g
         mbar_wait(&acc1_full[b], n_acc1[b] & 1);
         ++n_acc1[b];
         tcgen05_fence_after();
+        DSG_MLP_TRACE(g, 1);  // worker: acc1 of chunk g available
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * G::HC + cg * G::CQ;
 #pragma unroll
         for (int c0 = 0; c0 < G::CQ; c0 += 16) {
@@ -248,8 +262,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
           }
           if (c0 == 0) {
+            DSG_MLP_TRACE(g, 2);
             mbar_wait(h_empty, (n_h & 1) ^ 1);  // fc2 of the previous chunk has finished reading sH
             ++n_h;
+            DSG_MLP_TRACE(g, 3);  // worker: sH free
           }
           *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0 + 8)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
@@ -257,13 +273,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(h_full);
+        DSG_MLP_TRACE(g, 4);  // worker: chunk g done
       }
 
       // ---- output: acc2 + b2 -> reduce-add into x (column groups 0 and 1, 32-column chunks)
       if (cg < 2) {
+        DSG_MLP_TRACE(g - 1, 5);
         mbar_wait(acc2_full, n_acc2 & 1);
         ++n_acc2;
         tcgen05_fence_after();
+        DSG_MLP_TRACE(g - 1, 6);  // worker: acc2 of the tile complete
         uint8_t* buf = sStg + cg * 16384;
         constexpr int kChunks = C / 32;
 #pragma unroll 1
@@ -296,6 +315,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
+        DSG_MLP_TRACE(g - 1, 7);  // worker: tile output issued
       }
     }
     if (store_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -335,9 +355,9 @@ bool fused_mlp_supported(int C) { return C == 96 || C == 192; }
 int fused_mlp_w1_box_rows(int C) { return C == 96 ? 192 : 128; }
 
 int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
-                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st) {
+                     const float* b1, const float* b2, long long rows, int C, cudaStream_t st, long long* trace) {
   DSG_REQUIRE(fused_mlp_supported(C) && rows > 0 && rows < 2147483647LL, "fused_mlp: C=%d rows=%lld", C, rows);
-  MlpParams p{b1, b2, static_cast<int>(rows)};
+  MlpParams p{b1, b2, static_cast<int>(rows), trace};
   if (C == 96) return launch_c<96>(tmY, tmW1, tmW2, tmX, p, st);
   return launch_c<192>(tmY, tmW1, tmW2, tmX, p, st);
 }

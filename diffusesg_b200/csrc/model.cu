@@ -23,6 +23,7 @@ namespace dsg {
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
 static unsigned long long g_launches = 0;
+static long long* g_mlp_trace = nullptr;  // test hook: device buffer for the fused-MLP timeline of its next launch
 static int g_stop_after = -1;  // test hook: leave the forward schedule after this many stages (-1: run all)
 
 void set_last_error(const char* fmt, ...) {
@@ -448,7 +449,8 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     if (ty == nullptr || tx == nullptr) return DSG_ERR_CUDA;
     DSG_TRY_P(PC_MLP, 16.0 * rc * C, rc * 10,
               launch_fused_mlp(ty, &b.mlp_w1, &b.mlp_w2, tx, m->f32(p + ".mlp.fc1.bias"), m->f32(p + ".mlp.fc2.bias"), rows,
-                               C, st));
+                               C, st, g_mlp_trace));
+    g_mlp_trace = nullptr;
     return DSG_OK;
   }
   DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));
@@ -701,6 +703,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
 }
 
 void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
+void dsg_debug_trace_next_mlp(long long* device_buffer) { g_mlp_trace = device_buffer; }
 
 int dsg_profile_begin(int pass_stride) {
   DSG_REQUIRE(pass_stride >= 1, "profile_begin: stride %d", pass_stride);
@@ -782,6 +785,14 @@ int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags
   DSG_REQUIRE(adj && node && flags && adj_out && node_out, "edm_mask_scale: null tensor");
   return launch_mask_scale(adj, node, flags, scale, adj_out, node_out, batch, c_e, n, c_n,
                            static_cast<cudaStream_t>(stream));
+}
+
+int dsg_decode_samples(const float* adj, const float* node, const uint8_t* flags, int32_t* adj_cls, int32_t* node_cls,
+                       float* bbox, int num_adj_type, int num_node_type, int batch, int c_e, int n, int c_n,
+                       dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && flags && adj_cls && node_cls && bbox, "decode_samples: null tensor");
+  return launch_decode(adj, node, flags, adj_cls, node_cls, bbox, num_adj_type, num_node_type, batch, c_e, n, c_n,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,

@@ -59,12 +59,14 @@ _SIGNATURES = {
     "dsg_edm_pre_step": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_post_step": (C.c_int, [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_decode_samples": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     "dsg_profile_begin": (C.c_int, [C.c_int]),
     "dsg_profile_read": (C.c_int, [C.POINTER(DsgProfileClass), C.c_int, C.POINTER(C.c_int)]),
     "dsg_profile_stop": (None, []),
     "dsg_debug_set_stop_after": (None, [C.c_int]),
+    "dsg_debug_trace_next_mlp": (None, [C.c_void_p]),
     "dsg_debug_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
 
@@ -188,3 +190,16 @@ def edm_mask_scale(adj, node, flags, scale: float):
     check(lib().dsg_edm_mask_scale(ptr(adj), ptr(node), ptr(flags), float(scale), ptr(adj_out), ptr(node_out), b, ce, n,
                                    cn, stream_ptr(adj.device)), "dsg_edm_mask_scale")
     return adj_out, node_out
+
+
+def decode_samples(adj, node, flags, num_adj_type: int, num_node_type: int):
+    """int32 edge classes [B,N,N], int32 node classes [B,N], fp32 boxes [B,N,4] of a final sample, on the device."""
+    b, ce, n, _ = adj.shape
+    cn = node.shape[-1]
+    adj_cls = torch.empty(b, n, n, dtype=torch.int32, device=adj.device)
+    node_cls = torch.empty(b, n, dtype=torch.int32, device=adj.device)
+    bbox = torch.empty(b, n, 4, dtype=torch.float32, device=adj.device)
+    check(lib().dsg_decode_samples(ptr(adj), ptr(node), ptr(flags), ptr(adj_cls), ptr(node_cls), ptr(bbox),
+                                   int(num_adj_type), int(num_node_type), b, ce, n, cn, stream_ptr(adj.device)),
+          "dsg_decode_samples")
+    return adj_cls, node_cls, bbox

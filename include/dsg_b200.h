@@ -134,6 +134,15 @@ DSG_API int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const
 DSG_API int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
                        float* node_out, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
 
+/* ---- decode of the final sample ("next" row f-1: runner/sampler/sampler_node_adj.py:199-285, 'bits' encodings) -- */
+/* adj_cls[b,i,j] = clamp(bin2dec(adj[b,:,i,j] > 0), 0, num_adj_type-1) for valid i != j else 0 (self-loops
+ * removed, :283); node_cls[b,i] = clamp(bin2dec(node[b,i,:c_n-4] > 0), 0, num_node_type-1) for valid i else 0;
+ * bbox[b,i,:] = node[b,i,c_n-4:] * 0.5 + 0.5 for valid i else 0 (:202-209).  Bits are MSB first
+ * (utils/attribute_code.py:319-328).  Only the int32 classes and 4 floats per node need to leave the GPU. */
+DSG_API int dsg_decode_samples(const float* adj, const float* node, const uint8_t* flags, int32_t* adj_cls,
+                               int32_t* node_cls, float* bbox, int num_adj_type, int num_node_type, int batch,
+                               int c_e, int n, int c_n, dsg_stream_t stream);
+
 /* ---- building blocks, exported for the kernel-level parity tests ------------------------------------------- */
 /* out[M, N] = epilogue(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major.  epi: 0 bf16, 1 gelu->bf16,
  * 2 fp32 + residual (res may alias out), 3 fp32.  tcgen05/TMEM/TMA kernel (nn.Linear of the reference). */
@@ -164,6 +173,9 @@ DSG_API void dsg_profile_stop(void);
 /* Leave dsg_denoiser_forward after n_stages schedule stages (0: patch embedding, then one per Swin block /
  * PatchMerging / PatchBreakup in execution order); -1 restores the full schedule.  Process-global. */
 DSG_API void dsg_debug_set_stop_after(int n_stages);
+/* The next fused-MLP launch records a clock64 timeline of its CTA 0 into device_buffer
+ * ([64 chunks][18 warps][8 events] int64, zero it first); used by tools/mlp_trace.py. */
+DSG_API void dsg_debug_trace_next_mlp(long long* device_buffer);
 /* Byte offset and size of a named activation buffer ("X", "Y", "QKV", "ATT", "H", "T", "REP", "skip0".."skip2",
  * "film", "rc", "emb", "coef") inside a workspace laid out for (batch, n_cond). */
 DSG_API int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name, size_t* offset, size_t* bytes);

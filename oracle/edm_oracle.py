@@ -135,3 +135,29 @@ def decode_bits(t: Tensor, num_classes: int) -> Tensor:
     nb = bits.shape[-1]
     weights = 2 ** torch.arange(nb - 1, -1, -1)
     return (bits * weights).sum(-1).clamp(0, num_classes - 1)
+
+
+def decode_samples(adjs: Tensor, nodes: Tensor, flags: Tensor, num_adj_type: int, num_node_type: int):
+    """The reference's post-sampling decode for the 'bits' encodings, op for op
+    (runner/sampler/sampler_node_adj.py:199-209 boxes, :222-237 _decode_node, :239-285 _decode_adj).
+    Returns float tensors like the reference: q_adj [B,N,N], q_node [B,N], bbox [B,N,4]."""
+    boxes = mask_rows(nodes[..., -4:] * 0.5 + 0.5, flags)
+    node_bits = nodes[..., :-4].clamp(-1.0, 1.0)
+    node_bits = torch.where(node_bits > 0.0, torch.ones_like(node_bits), -torch.ones_like(node_bits))
+    node_bits = mask_rows(node_bits, flags)
+    qb = mask_rows(node_bits.gt(0.0).float(), flags)
+    nb = qb.shape[-1]
+    weights = 2 ** torch.arange(nb - 1, -1, -1).to(qb.dtype)
+    q_node = (weights * qb).sum(-1)
+    q_node = q_node.masked_fill(~flags.bool(), 0.0).clamp(min=0, max=num_node_type - 1)
+    a = adjs.clamp(-1.0, 1.0)
+    a = torch.where(a > 0.0, torch.ones_like(a), -torch.ones_like(a))
+    a = mask_pairs(a, flags)
+    qa = mask_pairs(a.gt(0.0).float(), flags).permute(0, 2, 3, 1)
+    ne = qa.shape[-1]
+    q_adj = ((2 ** torch.arange(ne - 1, -1, -1).to(qa.dtype)) * qa).sum(-1)
+    pair = flags.bool()[:, :, None] & flags.bool()[:, None, :]
+    q_adj = q_adj.masked_fill(~pair, 0.0).clamp(min=0, max=num_adj_type - 1)
+    n = flags.shape[1]
+    q_adj[:, torch.eye(n).bool()] = 0.0
+    return q_adj.contiguous(), q_node, boxes

@@ -150,3 +150,22 @@ def test_edm_steps_bit_exact(b, ce, n, cn):
     sa, sn = native.edm_mask_scale(cu(torch.randn(b, ce, n, n, generator=g)), cu(node), cu(flags), 80.0)
     assert float(sa[~(flags[:, None, :, None] & flags[:, None, None, :]).expand_as(sa).to(DEV)].abs().sum()) == 0.0
     np.testing.assert_array_equal(sn.cpu().numpy(), (node * 80.0).numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# on-device decode of the final sample: integer outputs, bit-exact against the reference rule
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,ce,n,cn,n_adj,n_node", [(7, 6, 64, 12, 51, 150), (5, 3, 40, 12, 7, 171), (3, 3, 16, 5, 5, 2)])
+def test_decode_samples_bit_exact(b, ce, n, cn, n_adj, n_node):
+    g = torch.Generator().manual_seed(n + ce)
+    flags = torch.arange(n)[None, :] < torch.randint(1, n + 1, (b, 1), generator=g)
+    adj = torch.randn(b, ce, n, n, generator=g) * 1.5          # deliberately NOT masked: the decode masks itself
+    node = torch.randn(b, n, cn, generator=g) * 1.5
+    adj[0, :, 1, 2] = 0.0                                       # exactly on the threshold -> bit 0
+    qa, qn, box = E.decode_samples(adj, node, flags, n_adj, n_node)
+    ga, gn, gb = native.decode_samples(adj.to(DEV), node.to(DEV), flags.to(DEV), n_adj, n_node)
+    np.testing.assert_array_equal(ga.cpu().numpy(), qa.numpy().astype(np.int32))
+    np.testing.assert_array_equal(gn.cpu().numpy(), qn.numpy().astype(np.int32))
+    np.testing.assert_array_equal(gb.cpu().numpy(), box.numpy())
+    assert int(ga.max()) <= n_adj - 1 and int(gn.max()) <= n_node - 1
+    assert int(ga.diagonal(dim1=1, dim2=2).abs().sum()) == 0
