@@ -11,6 +11,8 @@
 //   MMA warp           acc1[g&1] = y . W1[chunk]^T  (TMEM, double buffered);  acc2 += H[chunk] . W2[:, chunk]^T
 //   worker warps (16)  tcgen05.ld acc1 -> + b1 -> exact-erf GELU -> bf16 -> 128-byte-swizzled K-major smem H chunk;
 //                      after the last chunk of a tile: tcgen05.ld acc2 -> + b2 -> fp32 staging -> TMA reduce-add into x
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,26 +25,35 @@ constexpr int kWorkers = 16 * 32;
 template <int C>
 struct MlpCfg {
   static constexpr int HID = 4 * C;
-  static constexpr int HC = (C == 96) ? 192 : 128;     // hidden columns per chunk
-  static constexpr int NCH = HID / HC;                  // 2 / 6 (even: acc1 buffers alternate cleanly)
+  static constexpr int HC = 128;                        // hidden columns per chunk
+  static constexpr int NCH = HID / HC;                  // 3 / 6 chunks per tile
   static constexpr int KB1 = (C + 63) / 64;             // k-blocks of fc1 (K = C)
   static constexpr int KB2 = HC / 64;                   // k-blocks of fc2 per chunk (K = HC)
-  static constexpr int A_BYTES = KB1 * 16384;           // LN output, [128 x 64] bf16 per k-block
+  static constexpr int A_BYTES = KB1 * 16384;           // y tile, [128 x 64] bf16 per k-block
   static constexpr int H_BYTES = KB2 * 16384;
   static constexpr int STAGE_BYTES = ((HC > C) ? HC : C) * 128;  // one weight k-block: [rows x 64] bf16
-  static constexpr int kStages = 4;
-  static constexpr int STG_BYTES = 2 * 16384;           // fp32 output staging, 2 x [128 x 32]
-  static constexpr int PAR_FLOATS = HID + C;            // b1, b2
-  static constexpr int SMEM_BYTES = 1024 + A_BYTES + H_BYTES + kStages * STAGE_BYTES + STG_BYTES + PAR_FLOATS * 4 + 256;
-  static constexpr int ACC2_COL = 2 * HC;               // TMEM: acc1[0] @0, acc1[1] @HC, acc2 @2HC
-  static constexpr int CQ = HC / 4;                     // GELU columns per warp: 48 / 32
-  static_assert(NCH % 2 == 0 && ACC2_COL + C <= 512 && SMEM_BYTES <= 227 * 1024, "fused MLP budget");
+  // C = 96: two y-tile buffers (the HBM latency of the next tile's y is off the critical path), 5 x 16 KB weight
+  // stages (a chunk is 2 W1 + 2 W2 k-blocks, all L2 hits), two acc2 buffers so that the output of tile t runs one
+  // chunk into tile t + 1, and three staging buffers: one TMA reduce per 32-column output chunk.  C = 192 does
+  // not have the TMEM / smem for that.
+  static constexpr bool kDefer = (C == 96);
+  static constexpr int kABufs = 1;                      // y tile buffers (2 = the next tile is fetched a whole tile ahead)
+  static constexpr int kStages = (C == 96) ? 5 : 3;     // weight ring: what is left of the 227 KB
+  static constexpr int kAcc2 = kDefer ? 2 : 1;
+  static constexpr int kOutGroups = (C == 96) ? 3 : 2;  // column groups that write the tile output
+  static constexpr int STG_BYTES = kOutGroups * 16384;  // fp32 output staging, [128 x 32] per group
+  static constexpr int PAR_FLOATS = HID;                // b1
+  static constexpr int SMEM_BYTES = 1024 + kABufs * A_BYTES + 2 * H_BYTES + kStages * STAGE_BYTES + STG_BYTES + PAR_FLOATS * 4 + 256;
+  static constexpr int ACC2_COL = 2 * HC;               // TMEM: acc1[0] @0, acc1[1] @HC, acc2[u] @2HC + u C
+  static constexpr int CQ = HC / 4;                     // GELU columns per warp: 32
+  static_assert(ACC2_COL + kAcc2 * C <= 512 && SMEM_BYTES <= 227 * 1024, "fused MLP budget");
 };
 
 struct MlpParams {
   const float* b1;   // [4C]
   const float* b2;   // [C]
   int M;
+  int skip_gelu;     // experiment hook: workers pack the raw accumulator (wrong results, light ALU load)
   long long* trace;  // test hook: clock64 timeline of CTA 0 ([chunk < 64][warp < 18][event < 8]) or nullptr
 };
 
@@ -69,44 +80,45 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   // keeps the shared address space and emits LDS / STS instead of generic loads and stores
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sH = sA + G::A_BYTES;
-  uint8_t* sW = sH + G::H_BYTES;
+  uint8_t* sH = sA + G::kABufs * G::A_BYTES;
+  uint8_t* sW = sH + 2 * G::H_BYTES;  // sH is double buffered: the workers never wait for fc2 of the previous chunk
   uint8_t* sStg = sW + G::kStages * G::STAGE_BYTES;
   float* sPar = reinterpret_cast<float*>(sStg + G::STG_BYTES);
   float* sB1 = sPar;
-  float* sB2 = sPar + G::HID;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + G::PAR_FLOATS);
   uint64_t* w_full = bars;                    // [kStages]
   uint64_t* w_empty = bars + G::kStages;      // [kStages]
-  uint64_t* a_full = bars + 2 * G::kStages;   // TMA -> MMA: y tile landed
-  uint64_t* a_empty = a_full + 1;             // MMA -> workers: every fc1 MMA of the tile has read sA
-  uint64_t* acc1_full = a_full + 2;           // [2]
-  uint64_t* acc1_empty = a_full + 4;          // [2]
-  uint64_t* h_full = a_full + 6;
-  uint64_t* h_empty = a_full + 7;
-  uint64_t* acc2_full = a_full + 8;
-  uint64_t* acc2_empty = a_full + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 10);
+  uint64_t* a_full = bars + 2 * G::kStages;   // [2] TMA -> MMA: y tile landed
+  uint64_t* a_empty = a_full + 2;             // [2] MMA -> TMA: every fc1 MMA of the tile has read its sA buffer
+  uint64_t* acc1_full = a_full + 4;           // [2]
+  uint64_t* acc1_empty = a_full + 6;          // [2]
+  uint64_t* h_full = a_full + 8;              // [2]
+  uint64_t* h_empty = a_full + 10;            // [2]
+  uint64_t* acc2_full = a_full + 12;          // [2]
+  uint64_t* acc2_empty = a_full + 14;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // the scheduler favours the highest warp id among ready warps: the control warps take the last two ids so that
+  // the 16 ALU-heavy workers (warps 0..15) cannot starve them
+  constexpr int kTmaWarp = 16, kMmaWarp = 17;
   const int num_tiles = (p.M + 127) / 128;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < G::kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int u = 0; u < 2; ++u) { mbar_init(&a_full[u], 1); mbar_init(&a_empty[u], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], 16); }
-    mbar_init(h_full, 16); mbar_init(h_empty, 1);
-    mbar_init(acc2_full, 1); mbar_init(acc2_empty, 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(&h_full[b], 16); mbar_init(&h_empty[b], 1); }
+    for (int u = 0; u < 2; ++u) { mbar_init(&acc2_full[u], 1); mbar_init(&acc2_empty[u], 4 * G::kOutGroups); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   for (int i = threadIdx.x; i < G::HID; i += kMlpThreads) sB1[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += kMlpThreads) sB2[i] = p.b2[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -114,19 +126,26 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x)) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int n_chunks = my_tiles * G::NCH;  // global chunk stream of this CTA
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0, n_tile = 0;
-      auto load_fc1 = [&](int g) {  // operands of fc1 of chunk g: (the y tile, once per tile,) W1[chunk]
+      uint32_t ph = 0, n_y[2] = {0, 0};
+      int y_loaded = 0;  // local tiles whose y load has been issued
+      auto load_y = [&](int tl) {  // y tile of local tile tl -> sA[tl % kABufs]
+        const int u = tl % G::kABufs;
+        const int tile = blockIdx.x + tl * gridDim.x;
+        mbar_wait(&a_empty[u], (n_y[u] & 1) ^ 1);  // every fc1 MMA of the tile that last used this buffer completed
+        ++n_y[u];
+        mbar_expect_tx(&a_full[u], G::A_BYTES);
+        for (int kb = 0; kb < G::KB1; ++kb)
+          tma_load_2d(sA + u * G::A_BYTES + kb * 16384, &tmY, &a_full[u], kb * 64, tile * 128);
+      };
+      auto load_fc1 = [&](int g) {  // operands of fc1 of chunk g: (y tiles, kept kABufs - 1 tiles ahead,) W1[chunk]
         const int j = g % G::NCH;
         if (j == 0) {
-          const int tile = blockIdx.x + (g / G::NCH) * gridDim.x;
-          mbar_wait(a_empty, (n_tile & 1) ^ 1);  // every fc1 MMA of the previous tile has read sA
-          ++n_tile;
-          mbar_expect_tx(a_full, G::A_BYTES);
-          for (int kb = 0; kb < G::KB1; ++kb) tma_load_2d(sA + kb * 16384, &tmY, a_full, kb * 64, tile * 128);
+          const int tl = g / G::NCH;
+          while (y_loaded < my_tiles && y_loaded < tl + G::kABufs) load_y(y_loaded++);
         }
         for (int kb = 0; kb < G::KB1; ++kb) {
           mbar_wait(&w_empty[s], ph ^ 1);
@@ -151,18 +170,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (g + 2 < n_chunks) load_fc1(g + 2);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc1 = umma_idesc_bf16(G::HC);
     constexpr uint32_t idesc2 = umma_idesc_bf16(C);
     int s = 0;
     uint32_t ph = 0;
-    uint32_t n_a = 0, n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0;  // use counters -> mbarrier parities
+    uint32_t n_a[2] = {0, 0}, n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};  // use counters -> parities
     auto fc1 = [&](int g) {  // acc1[g & 1] = y . W1[chunk]^T
       const int b = g & 1, j = g % G::NCH;
+      const int ua = (g / G::NCH) % G::kABufs;  // y buffer of this tile
       if (j == 0) {
-        mbar_wait(a_full, n_a & 1);
-        ++n_a;
+        mbar_wait(&a_full[ua], n_a[ua] & 1);
+        ++n_a[ua];
       }
       mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
       ++n_acc1[b];
@@ -173,7 +193,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         tcgen05_fence_after();
         if (kb == G::KB1 - 1) DSG_MLP_TRACE(g, 1);  // fc1(g): last W1 k-block landed
         if (lane == 0) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sA + kb * 16384));
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + ua * G::A_BYTES + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
           const int ksteps = ((C - kb * 64) < 64 ? (C - kb * 64) : 64) / 16;
           for (int k = 0; k < ksteps; ++k)
@@ -185,7 +205,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       if (lane == 0) {
         umma_commit(&acc1_full[b]);
-        if (j == G::NCH - 1) umma_commit(a_empty);  // sA may be refilled once every fc1 MMA of the tile completed
+        if (j == G::NCH - 1) umma_commit(&a_empty[ua]);  // the buffer may be refilled once every fc1 MMA of the tile completed
       }
       __syncwarp();
     };
@@ -193,11 +213,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     if (n_chunks > 1) fc1(1);
     for (int g = 0; g < n_chunks; ++g) {
       const int j = g % G::NCH;
-      mbar_wait(h_full, n_h & 1);
-      ++n_h;
+      const int u = G::kDefer ? ((g / G::NCH) & 1) : 0;  // acc2 buffer of this tile
+      const int hb = g & 1;                               // sH buffer of this chunk
+      mbar_wait(&h_full[hb], n_h[hb] & 1);
+      ++n_h[hb];
       if (j == 0) {
-        mbar_wait(acc2_empty, (n_acc2 & 1) ^ 1);  // the previous tile's output phase has drained acc2
-        ++n_acc2;
+        mbar_wait(&acc2_empty[u], (n_acc2[u] & 1) ^ 1);  // the output phase that last used this buffer has drained it
+        ++n_acc2[u];
       }
       tcgen05_fence_after();
       DSG_MLP_TRACE(g, 2);  // fc2(g): H chunk written (and acc2 free)
@@ -206,38 +228,83 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         tcgen05_fence_after();
         if (kb == G::KB2 - 1) DSG_MLP_TRACE(g, 3);  // fc2(g): last W2 k-block landed
         if (lane == 0) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sH + kb * 16384));
+          const uint64_t da = umma_desc_sw128(smem_u32(sH + hb * G::H_BYTES + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + G::ACC2_COL, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
+            umma_bf16_ss(tmem_base + G::ACC2_COL + u * C, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
           umma_commit(&w_empty[s]);
         }
         __syncwarp();
         if (++s == G::kStages) { s = 0; ph ^= 1; }
       }
       if (lane == 0) {
-        umma_commit(h_empty);
-        if (j == G::NCH - 1) umma_commit(acc2_full);
+        umma_commit(&h_empty[hb]);
+        if (j == G::NCH - 1) umma_commit(&acc2_full[u]);
       }
       __syncwarp();
       if (g + 2 < n_chunks) fc1(g + 2);
     }
   } else {
     // ------------------------------------------------------------------ workers: GELU chunks, tile output
-    const int w = warp - 2;                 // 0..15
+    const int w = warp;                     // 0..15
     const int q = warp & 3;                 // TMEM lane quarter of this warp
     const int cg = w >> 2;                  // column group 0..3
     const int r_t = q * 32 + lane;          // accumulator row owned by this thread
-    // the four warps of a column group hold warp indices 2+4cg .. 5+4cg: elect the first as the TMA-store issuer
+    // the four warps of a column group hold warp indices 4cg .. 4cg+3: elect the first as the TMA-store issuer
     const bool store_issuer = ((w & 3) == 0) && lane == 0;
-    uint32_t n_acc1[2] = {0, 0}, n_h = 0, n_acc2 = 0;
+    uint32_t n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
 
-    int g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // tile output: acc2[u] + b2 -> swizzled fp32 staging -> TMA reduce-add into x (column groups < kOutGroups)
+    auto tile_output = [&](int tile, int u, int g_trace) {
+      if (cg >= G::kOutGroups) return;
+      DSG_MLP_TRACE(g_trace, 5);
+      mbar_wait(&acc2_full[u], n_acc2[u] & 1);
+      ++n_acc2[u];
+      tcgen05_fence_after();
+      DSG_MLP_TRACE(g_trace, 6);  // worker: acc2 of the tile complete
+      uint8_t* buf = sStg + cg * 16384;
+      constexpr int kChunks = C / 32;
+#pragma unroll 1
+      for (int ci = cg; ci < kChunks; ci += G::kOutGroups) {
+        // the bulk reduce that last read this staging buffer must have drained it
+        if (store_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(cg + 1) : "memory");
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + G::ACC2_COL + u * C + ci * 32, r);
+        tmem_ld_wait();
+        if (ci + G::kOutGroups >= kChunks) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty[u]);
+        }
+        uint8_t* rowp = buf + r_t * 128;
+        const int sw = r_t & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + ci * 32 + 4 * c));
+          *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) =
+              make_float4(__uint_as_float(r[4 * c]) + bb.x, __uint_as_float(r[4 * c + 1]) + bb.y,
+                          __uint_as_float(r[4 * c + 2]) + bb.z, __uint_as_float(r[4 * c + 3]) + bb.w);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(cg + 1) : "memory");
+        if (store_issuer) {
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(buf)), "r"(ci * 32), "r"(tile * 128)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      DSG_MLP_TRACE(g_trace, 7);  // worker: tile output issued
+    };
+
+    int g = 0, tl = 0;  // global chunk index, local tile counter
+    int prev_tile = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 -> sH
 #pragma unroll 1
       for (int j = 0; j < G::NCH; ++j, ++g) {
-        const int b = j & 1;
+        const int b = g & 1;
         DSG_MLP_TRACE(g, 0);  // worker: ready for chunk g
         mbar_wait(&acc1_full[b], n_acc1[b] & 1);
         ++n_acc1[b];
@@ -256,75 +323,45 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
           uint32_t hp[8];  // packed bf16 pairs
 #pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * G::CQ + c0 + k]);
-            hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
-            hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+          if (p.skip_gelu) {
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) hp[k >> 1] = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * G::CQ + c0 + k]);
+              hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
+              hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+            }
           }
           if (c0 == 0) {
             DSG_MLP_TRACE(g, 2);
-            mbar_wait(h_empty, (n_h & 1) ^ 1);  // fc2 of the previous chunk has finished reading sH
-            ++n_h;
+            mbar_wait(&h_empty[b], (n_h[b] & 1) ^ 1);  // fc2 of chunk g - 2 has finished reading this sH buffer
+            ++n_h[b];
             DSG_MLP_TRACE(g, 3);  // worker: sH free
           }
-          *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(sH + sw128_offset(r_t, cg * G::CQ + c0 + 8)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          uint8_t* sHb = sH + b * G::H_BYTES;
+          *reinterpret_cast<uint4*>(sHb + sw128_offset(r_t, cg * G::CQ + c0)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(sHb + sw128_offset(r_t, cg * G::CQ + c0 + 8)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_full);
+        if (lane == 0) mbar_arrive(&h_full[b]);
         DSG_MLP_TRACE(g, 4);  // worker: chunk g done
+        // deferred output of the previous tile: its last fc2 has long completed, nobody waits
+        if (G::kDefer && j == 0 && prev_tile >= 0) tile_output(prev_tile, (tl - 1) & 1, g);
       }
-
-      // ---- output: acc2 + b2 -> reduce-add into x (column groups 0 and 1, 32-column chunks)
-      if (cg < 2) {
-        DSG_MLP_TRACE(g - 1, 5);
-        mbar_wait(acc2_full, n_acc2 & 1);
-        ++n_acc2;
-        tcgen05_fence_after();
-        DSG_MLP_TRACE(g - 1, 6);  // worker: acc2 of the tile complete
-        uint8_t* buf = sStg + cg * 16384;
-        constexpr int kChunks = C / 32;
-#pragma unroll 1
-        for (int ci = cg; ci < kChunks; ci += 2) {
-          if (store_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(cg + 1) : "memory");
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + G::ACC2_COL + ci * 32, r);
-          tmem_ld_wait();
-          if (ci + 2 >= kChunks) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc2_empty);
-          }
-          uint8_t* rowp = buf + r_t * 128;
-          const int sw = r_t & 7;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sB2[ci * 32 + 4 * c]);
-            *reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4)) =
-                make_float4(__uint_as_float(r[4 * c]) + bb.x, __uint_as_float(r[4 * c + 1]) + bb.y,
-                            __uint_as_float(r[4 * c + 2]) + bb.z, __uint_as_float(r[4 * c + 3]) + bb.w);
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(cg + 1) : "memory");
-          if (store_issuer) {
-            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(buf)), "r"(ci * 32), "r"(tile * 128)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
-        DSG_MLP_TRACE(g - 1, 7);  // worker: tile output issued
-      }
+      if (!G::kDefer) tile_output(tile, 0, g - 1);
+      prev_tile = tile;
     }
+    if (G::kDefer && prev_tile >= 0) tile_output(prev_tile, (tl - 1) & 1, g - 1);
     if (store_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
 template <int C>
@@ -352,12 +389,13 @@ int launch_c(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap*
 }  // namespace
 
 bool fused_mlp_supported(int C) { return C == 96 || C == 192; }
-int fused_mlp_w1_box_rows(int C) { return C == 96 ? 192 : 128; }
+int fused_mlp_w1_box_rows(int C) { (void)C; return 128; }
 
 int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
                      const float* b1, const float* b2, long long rows, int C, cudaStream_t st, long long* trace) {
   DSG_REQUIRE(fused_mlp_supported(C) && rows > 0 && rows < 2147483647LL, "fused_mlp: C=%d rows=%lld", C, rows);
-  MlpParams p{b1, b2, static_cast<int>(rows), trace};
+  static const int skip = (getenv("DSG_MLP_SKIP_GELU") != nullptr) ? 1 : 0;
+  MlpParams p{b1, b2, static_cast<int>(rows), skip, trace};
   if (C == 96) return launch_c<96>(tmY, tmW1, tmW2, tmX, p, st);
   return launch_c<192>(tmY, tmW1, tmW2, tmX, p, st);
 }

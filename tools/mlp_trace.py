@@ -25,11 +25,11 @@ torch.cuda.synchronize()
 t = buf.cpu().view(64, 18, 8)
 t0 = int(t[t > 0].min())
 rel = torch.where(t > 0, t - t0, torch.full_like(t, -1))
-print("MMA warp (1): ev0 fc1 ready, ev1 fc1 last W1 landed, ev2 fc2 H ready, ev3 fc2 last W2 landed")
-print("workers (2..17): ev0 ready, ev1 acc1 available, ev2 before h_empty, ev3 sH free, ev4 chunk done, ev5/6/7 output")
+print("MMA warp (17): ev0 fc1 ready, ev1 fc1 last W1 landed, ev2 fc2 H ready, ev3 fc2 last W2 landed")
+print("workers (0..15): ev0 ready, ev1 acc1 available, ev2 before h_empty, ev3 sH free, ev4 chunk done, ev5/6/7 output")
 for g in range(12):
-    mma = rel[g, 1, :4].tolist()
-    w = rel[g, 2:, :]
+    mma = rel[g, 17, :4].tolist()
+    w = rel[g, :16, :]
     def rng(e):
         v = w[:, e][w[:, e] >= 0]
         return f"{int(v.min())}-{int(v.max())}" if len(v) else "-"
