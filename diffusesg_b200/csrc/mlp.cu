@@ -224,15 +224,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       tcgen05_fence_after();
       DSG_MLP_TRACE(g, 2);  // fc2(g): H chunk written (and acc2 free)
       for (int kb = 0; kb < G::KB2; ++kb) {  // acc2 += H[chunk] . W2[:, chunk]^T
+        if (kb == 0) DSG_MLP_TRACE(g, 4);  // fine-grained: before the W2 k-block wait
         mbar_wait(&w_full[s], ph);
         tcgen05_fence_after();
+        if (kb == 0) DSG_MLP_TRACE(g, 5);  // after the wait
         if (kb == G::KB2 - 1) DSG_MLP_TRACE(g, 3);  // fc2(g): last W2 k-block landed
         if (lane == 0) {
           const uint64_t da = umma_desc_sw128(smem_u32(sH + hb * G::H_BYTES + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(tmem_base + G::ACC2_COL + u * C, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
+          if (kb == 0) DSG_MLP_TRACE(g, 6);  // 4 MMAs issued
           umma_commit(&w_empty[s]);
+          if (kb == 0) DSG_MLP_TRACE(g, 7);  // commit issued
         }
         __syncwarp();
         if (++s == G::kStages) { s = 0; ph ^= 1; }

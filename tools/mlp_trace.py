@@ -28,7 +28,7 @@ rel = torch.where(t > 0, t - t0, torch.full_like(t, -1))
 print("MMA warp (17): ev0 fc1 ready, ev1 fc1 last W1 landed, ev2 fc2 H ready, ev3 fc2 last W2 landed")
 print("workers (0..15): ev0 ready, ev1 acc1 available, ev2 before h_empty, ev3 sH free, ev4 chunk done, ev5/6/7 output")
 for g in range(12):
-    mma = rel[g, 17, :4].tolist()
+    mma = rel[g, 17, :8].tolist()
     w = rel[g, :16, :]
     def rng(e):
         v = w[:, e][w[:, e] >= 0]
