@@ -1,0 +1,591 @@
+// Fused tail of a Swin block for sm_100a (one kernel per block, C = 96):
+//
+//     x  = x + proj(att) + b_p                       (model/diffusesg/diffusesg.py:137, :272 of the reference)
+//     y  = LayerNorm2(x)                             (:275, norm2)
+//     x  = x + fc2(gelu(fc1(y) + b1)) + b2           (:275 with Mlp.forward :19-25)
+//
+// Unfused this is three launches (proj GEMM with a reduce-add epilogue, LayerNorm, fused MLP) that move the fp32
+// residual stream through HBM three times and the bf16 LayerNorm output twice; here a 128-token tile reads att
+// (bf16) and x (fp32) once and writes x once.  The residual never leaves the SM: the proj accumulator is turned
+// into x_new (+ b2) IN TENSOR MEMORY (tcgen05.ld -> add -> tcgen05.st) and fc2 accumulates on top of it, so the
+// final accumulator IS the block output.
+//
+//   warp 16  operand producer  att tile (TMA, 64-byte swizzle, 32-column k-blocks), W_proj / W1 / W2 rings
+//   warp 17  MMA issuer        proj -> acc2[u];  fc1 chunk -> acc1[b] (64 hidden columns);  fc2 chunk -> acc2[u] +=
+//   warp 18  residual mover    x tile in (TMA) / block output out (TMA store) through one fp32 staging tile
+//   warps 0..15 workers        P: acc2 + b_p + x -> LN -> y (bf16, swizzled A operand) and x_new + b2 -> acc2
+//                              G: acc1 + b1 -> exact GELU -> bf16 -> swizzled H chunk          (6 chunks / tile)
+//                              O: final acc2 -> staging tile (same thread-private slots the x tile was read from)
+//   worker order per tile t:   P(t), O(t - 1), G(t, 0..NCH-1)       MMA order: ..., fc2(t, NCH-2), proj(t + 1), ...
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+constexpr int kTailThreads = 19 * 32;
+constexpr float kTailLnEps = 1e-5f;
+
+template <int C>
+struct TailCfg {
+  static constexpr int HID = 4 * C;
+  static constexpr int HC = 64;                    // hidden columns per chunk
+  static constexpr int NCH = HID / HC;             // 6 chunks per tile
+  static constexpr int KBN = C / 32;               // 32-column k-blocks of a K = C operand (64-byte swizzle)
+  static constexpr int NPS = (KBN + 1) / 2;        // W2-ring slots holding W_proj (two k-blocks per slot)
+  static constexpr int A_KB = 128 * 64;            // one k-block of a 128-row A operand
+  static constexpr int A_BYTES = KBN * A_KB;       // att tile / y tile
+  static constexpr int H_BYTES = 128 * 128;        // one H chunk: [128 x 64] bf16, 128-byte swizzle
+  static constexpr int W1_KB = HC * 64;            // one k-block of a W1 chunk: [64 x 32] bf16
+  static constexpr int W1_SLOT = KBN * W1_KB;      // W1 rows [j HC, (j + 1) HC), all of K
+  static constexpr int WP_KB = C * 64;             // one k-block of W_proj: [C x 32] bf16
+  static constexpr int W2_SLOT = C * 128;          // W2[:, chunk]: [C x 64] bf16 (128-byte swizzle) == 2 W_proj k-blocks
+  static constexpr int S1 = 6, S2 = 5;             // ring depths
+  static constexpr int XB = C / 32;                // [128 x 32] fp32 boxes of the staging tile
+  static constexpr int X_BYTES = XB * 16384;
+  static constexpr int CW = C / 4;                 // columns per worker warp in the P / O phases
+  static constexpr int PAR_FLOATS = HID + 4 * C;   // b1, b_p, b2, gamma, beta
+  static constexpr int PART_BYTES = 4 * 128 * 8;   // LayerNorm partial sums: float2 [4 column groups][128 rows]
+  static constexpr int SMEM_BYTES = 1024 + A_BYTES + X_BYTES + S1 * W1_SLOT + S2 * W2_SLOT + PART_BYTES +
+                                    PAR_FLOATS * 4 + 512;
+  // TMEM columns: acc1[b] @ b HC | acc2[u] @ 2 HC + u C | y (bf16 pairs, the A operand of fc1) | H[b] (bf16 pairs,
+  // the A operand of fc2).  Both MLP GEMMs take A from tensor memory: an SS-mode MMA with N <= 96 is bound by the
+  // shared-memory read of its 128-row A operand (measured ~95 clk per K = 16 step instead of N / 2).
+  static constexpr int ACC2_COL = 2 * HC;
+  static constexpr int Y_COL = ACC2_COL + 2 * C;
+  static constexpr int H_COL = Y_COL + C / 2;
+  static_assert(C % 32 == 0 && CW % 8 == 0, "tail: C must be a multiple of 32");
+  static_assert(H_COL + HC <= 512 && SMEM_BYTES <= 227 * 1024, "tail budget");
+};
+
+struct TailParams {
+  const float* bp;     // [C]   proj bias
+  const float* gamma;  // [C]   norm2
+  const float* beta;   // [C]
+  const float* b1;     // [4C]
+  const float* b2;     // [C]
+  int M;
+  int skip_gelu;       // experiment hook (DSG_TAIL_SKIP_GELU): pack the raw accumulator (wrong results, light ALU load)
+  long long* trace;    // test hook: clock64 timeline of CTA 0 ([chunk < 64][warp < 19][event < 8]) or nullptr
+};
+
+#define DSG_TAIL_TRACE(g, ev)                                                                        \
+  do {                                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (g) < 64)                              \
+      p.trace[(static_cast<size_t>(g) * 19 + warp) * 8 + (ev)] = clock64();                          \
+  } while (0)
+
+// K-major operand, 64-byte swizzle, k-blocks of 32 bf16 columns: byte offset of the 16-byte chunk holding elements
+// [k, k + 8) of row r (what TMA SWIZZLE_64B writes and a SWIZZLE_64B UMMA descriptor reads); kb_bytes = rows * 64
+DSG_DEVICE uint32_t sw64_offset(int r, int k, int kb_bytes) {
+  return static_cast<uint32_t>((k >> 5) * kb_bytes + r * 64 + (((((k & 31) >> 3) ^ (r >> 1)) & 3) << 4));
+}
+DSG_DEVICE uint32_t sw128_offset_1kb(int r, int k) {  // one [rows x 64] k-block, 128-byte swizzle
+  return static_cast<uint32_t>(r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4));
+}
+
+// start address >> 4 | LBO = 1 (unused) | SBO = 512 B (8 rows of 64 bytes) | version 1 | SWIZZLE_64B
+DSG_DEVICE uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  const uint64_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16);
+  const uint64_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+  return lo | (hi << 32);
+}
+
+DSG_DEVICE void tmem_ld_32x8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+DSG_DEVICE void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+DSG_DEVICE void tmem_st_32x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+// D[tmem] (+)= A[tmem: lane = row, one 32-bit column per pair of K elements] . B[smem descriptor]^T
+DSG_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DSG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+DSG_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTailThreads, 1)
+block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant__ CUtensorMap tmWp,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmX, const TailParams p) {
+  using G = TailCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sAtt = smem;
+  uint8_t* sX = sAtt + G::A_BYTES;
+  uint8_t* sW1 = sX + G::X_BYTES;
+  uint8_t* sW2 = sW1 + G::S1 * G::W1_SLOT;
+  float2* sPart = reinterpret_cast<float2*>(sW2 + G::S2 * G::W2_SLOT);
+  float* sB1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sPart) + G::PART_BYTES);
+  float* sBp = sB1 + G::HID;
+  float* sB2 = sBp + C;
+  float* sGam = sB2 + C;
+  float* sBet = sGam + C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBet + C);
+  uint64_t* w1_full = bars;                 // [S1]
+  uint64_t* w1_empty = w1_full + G::S1;     // [S1]
+  uint64_t* w2_full = w1_empty + G::S1;     // [S2]
+  uint64_t* w2_empty = w2_full + G::S2;     // [S2]
+  uint64_t* att_full = w2_empty + G::S2;    // TMA -> MMA
+  uint64_t* att_empty = att_full + 1;       // MMA -> TMA: proj of the tile has read sAtt
+  uint64_t* xin_full = att_full + 2;        // TMA -> workers: x tile landed in sX
+  uint64_t* out_ready = att_full + 3;       // workers -> residual mover: sX consumed (and holds the previous output)
+  uint64_t* proj_full = att_full + 4;       // [2] MMA -> workers: proj accumulator of the tile complete in acc2[u]
+  uint64_t* y_ready = att_full + 6;         // workers -> MMA: y (bf16, tensor memory) and x_new + b2 (acc2[u]) stored
+  uint64_t* acc1_full = att_full + 7;       // [2]
+  uint64_t* acc1_empty = att_full + 9;      // [2]
+  uint64_t* h_full = att_full + 11;         // [2]
+  uint64_t* h_empty = att_full + 13;        // [2]
+  uint64_t* acc2_full = att_full + 15;      // [2] MMA -> workers: last fc2 of the tile complete
+  uint64_t* acc2_empty = att_full + 17;     // [2] workers -> MMA: output drained, proj of tile t + 2 may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_full + 19);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  constexpr int kTmaWarp = 16, kMmaWarp = 17, kXWarp = 18;
+  const int num_tiles = (p.M + 127) / 128;
+  const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x)) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmAtt);
+    tma_prefetch_desc(&tmWp);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < G::S1; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
+    for (int s = 0; s < G::S2; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
+    mbar_init(att_full, 1);
+    mbar_init(att_empty, 1);
+    mbar_init(xin_full, 1);
+    mbar_init(out_ready, 16);
+    mbar_init(y_ready, 16);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&proj_full[b], 1);
+      mbar_init(&acc1_full[b], 1);
+      mbar_init(&acc1_empty[b], 16);
+      mbar_init(&h_full[b], 16);
+      mbar_init(&h_empty[b], 1);
+      mbar_init(&acc2_full[b], 1);
+      mbar_init(&acc2_empty[b], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < G::HID; i += kTailThreads) sB1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += kTailThreads) {
+    sBp[i] = p.bp[i];
+    sB2[i] = p.b2[i];
+    sGam[i] = p.gamma[i];
+    sBet[i] = p.beta[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ operand producer (consumption order)
+    if (elect_one()) {
+      int s1 = 0, s2 = 0;
+      uint32_t ph1 = 0, ph2 = 0, n_att = 0;
+      auto load_att = [&](int tl) {
+        const int tile = blockIdx.x + tl * gridDim.x;
+        mbar_wait(att_empty, (n_att & 1) ^ 1);
+        ++n_att;
+        mbar_expect_tx(att_full, G::A_BYTES);
+        for (int kb = 0; kb < G::KBN; ++kb) tma_load_2d(sAtt + kb * G::A_KB, &tmAtt, att_full, kb * 32, tile * 128);
+      };
+      auto load_wp = [&]() {
+        for (int ps = 0; ps < G::NPS; ++ps) {
+          const int nkb = (2 * ps + 1 < G::KBN) ? 2 : 1;
+          mbar_wait(&w2_empty[s2], ph2 ^ 1);
+          mbar_expect_tx(&w2_full[s2], nkb * G::WP_KB);
+          for (int i = 0; i < nkb; ++i)
+            tma_load_2d(sW2 + s2 * G::W2_SLOT + i * G::WP_KB, &tmWp, &w2_full[s2], (2 * ps + i) * 32, 0);
+          if (++s2 == G::S2) { s2 = 0; ph2 ^= 1; }
+        }
+      };
+      auto load_w1 = [&](int j) {
+        mbar_wait(&w1_empty[s1], ph1 ^ 1);
+        mbar_expect_tx(&w1_full[s1], G::W1_SLOT);
+        for (int kb = 0; kb < G::KBN; ++kb)
+          tma_load_2d(sW1 + s1 * G::W1_SLOT + kb * G::W1_KB, &tmW1, &w1_full[s1], kb * 32, j * G::HC);
+        if (++s1 == G::S1) { s1 = 0; ph1 ^= 1; }
+      };
+      auto load_w2 = [&](int j) {
+        mbar_wait(&w2_empty[s2], ph2 ^ 1);
+        mbar_expect_tx(&w2_full[s2], G::W2_SLOT);
+        tma_load_2d(sW2 + s2 * G::W2_SLOT, &tmW2, &w2_full[s2], j * G::HC, 0);
+        if (++s2 == G::S2) { s2 = 0; ph2 ^= 1; }
+      };
+      if (my_tiles > 0) { load_att(0); load_wp(); }
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        load_w1(0);
+        DSG_TAIL_TRACE(tl * G::NCH, 0);
+        load_w1(1);
+        DSG_TAIL_TRACE(tl * G::NCH + 1, 0);
+        if (tl + 1 < my_tiles) load_att(tl + 1);  // proj(tl) completes long before its weights' successors are due
+        DSG_TAIL_TRACE(tl * G::NCH, 2);
+        for (int j = 0; j < G::NCH; ++j) {
+          load_w2(j);
+          DSG_TAIL_TRACE(tl * G::NCH + j, 1);
+          if (j + 2 < G::NCH) { load_w1(j + 2); DSG_TAIL_TRACE(tl * G::NCH + j + 2, 0); }
+          else if (j + 2 == G::NCH && tl + 1 < my_tiles) { load_wp(); DSG_TAIL_TRACE(tl * G::NCH + j, 3); }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_c = umma_idesc_bf16(C);       // proj, fc2: N = C
+    constexpr uint32_t idesc_h = umma_idesc_bf16(G::HC);   // fc1: N = HC
+    int s1 = 0, s2 = 0;
+    uint32_t ph1 = 0, ph2 = 0, n_att = 0, n_y = 0;
+    uint32_t n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
+    auto proj = [&](int tl) {  // acc2[u] = att . W_proj^T
+      const int u = tl & 1;
+      DSG_TAIL_TRACE(tl * G::NCH, 4);
+      mbar_wait(att_full, n_att & 1);
+      ++n_att;
+      mbar_wait(&acc2_empty[u], (n_acc2[u] & 1) ^ 1);
+      ++n_acc2[u];
+      tcgen05_fence_after();
+      DSG_TAIL_TRACE(tl * G::NCH, 5);
+      for (int ps = 0; ps < G::NPS; ++ps) {
+        const int nkb = (2 * ps + 1 < G::KBN) ? 2 : 1;
+        mbar_wait(&w2_full[s2], ph2);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          for (int i = 0; i < nkb; ++i) {
+            const int kb = 2 * ps + i;
+            const uint64_t da = umma_desc_sw64(smem_u32(sAtt + kb * G::A_KB));
+            const uint64_t db = umma_desc_sw64(smem_u32(sW2 + s2 * G::W2_SLOT + i * G::WP_KB));
+            for (int k = 0; k < 2; ++k)
+              umma_bf16_ss(tmem_base + G::ACC2_COL + u * C, da + 2 * k, db + 2 * k, idesc_c, (kb | k) != 0);
+          }
+          umma_commit(&w2_empty[s2]);
+        }
+        __syncwarp();
+        if (++s2 == G::S2) { s2 = 0; ph2 ^= 1; }
+      }
+      if (elect_one()) {
+        umma_commit(att_empty);
+        umma_commit(&proj_full[u]);
+      }
+      __syncwarp();
+      DSG_TAIL_TRACE(tl * G::NCH, 6);
+    };
+    auto fc1 = [&](int g) {  // acc1[g & 1] = y . W1[chunk]^T
+      const int b = g & 1;
+      mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
+      ++n_acc1[b];
+      mbar_wait(&w1_full[s1], ph1);
+      tcgen05_fence_after();
+      DSG_TAIL_TRACE(g, 0);
+      if (elect_one()) {
+        for (int kb = 0; kb < G::KBN; ++kb) {
+          const uint64_t db = umma_desc_sw64(smem_u32(sW1 + s1 * G::W1_SLOT + kb * G::W1_KB));
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_ts(tmem_base + b * G::HC, tmem_base + G::Y_COL + kb * 16 + k * 8, db + 2 * k, idesc_h, (kb | k) != 0);
+        }
+        umma_commit(&w1_empty[s1]);
+        umma_commit(&acc1_full[b]);
+      }
+      __syncwarp();
+      DSG_TAIL_TRACE(g, 1);
+      if (++s1 == G::S1) { s1 = 0; ph1 ^= 1; }
+    };
+    if (my_tiles > 0) proj(0);
+    int g = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int u = tl & 1;
+      mbar_wait(y_ready, n_y & 1);  // y in tensor memory, x_new + b2 in acc2[u]
+      ++n_y;
+      tcgen05_fence_after();
+      DSG_TAIL_TRACE(g, 7);
+      fc1(g);
+      fc1(g + 1);
+      for (int j = 0; j < G::NCH; ++j, ++g) {
+        const int hb = g & 1;
+        mbar_wait(&h_full[hb], n_h[hb] & 1);
+        ++n_h[hb];
+        DSG_TAIL_TRACE(g, 2);
+        mbar_wait(&w2_full[s2], ph2);
+        tcgen05_fence_after();
+        DSG_TAIL_TRACE(g, 3);
+        if (elect_one()) {  // acc2[u] += H[chunk] . W2[:, chunk]^T   (always accumulating: acc2 holds x_new + b2)
+          const uint64_t db = umma_desc_sw128(smem_u32(sW2 + s2 * G::W2_SLOT));
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem_base + G::ACC2_COL + u * C, tmem_base + G::H_COL + hb * (G::HC / 2) + k * 8, db + 2 * k,
+                         idesc_c, 1u);
+          umma_commit(&w2_empty[s2]);
+          umma_commit(&h_empty[hb]);
+          if (j == G::NCH - 1) umma_commit(&acc2_full[u]);
+        }
+        __syncwarp();
+        if (++s2 == G::S2) { s2 = 0; ph2 ^= 1; }
+        if (j + 2 < G::NCH) fc1(g + 2);
+        else if (j + 2 == G::NCH && tl + 1 < my_tiles) proj(tl + 1);
+      }
+    }
+  } else if (warp == kXWarp) {
+    // ------------------------------------------------------------------ residual mover
+    if (elect_one()) {
+      auto load_x = [&](int tl) {
+        const int tile = blockIdx.x + tl * gridDim.x;
+        mbar_expect_tx(xin_full, G::X_BYTES);
+        for (int xb = 0; xb < G::XB; ++xb) tma_load_2d(sX + xb * 16384, &tmX, xin_full, xb * 32, tile * 128);
+      };
+      auto store_x = [&](int tl) {
+        const int tile = blockIdx.x + tl * gridDim.x;
+        for (int xb = 0; xb < G::XB; ++xb) tma_store_2d(&tmX, sX + xb * 16384, xb * 32, tile * 128);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      };
+      if (my_tiles > 0) load_x(0);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        mbar_wait(out_ready, tl & 1);  // P(tl) consumed the x tile; O(tl - 1) left the previous output in sX
+        DSG_TAIL_TRACE(tl * G::NCH, 0);
+        if (tl > 0) {
+          store_x(tl - 1);
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        DSG_TAIL_TRACE(tl * G::NCH, 1);
+        if (tl + 1 < my_tiles) load_x(tl + 1);
+      }
+      if (my_tiles > 0) {
+        mbar_wait(out_ready, my_tiles & 1);
+        store_x(my_tiles - 1);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ------------------------------------------------------------------ workers
+    const int q = warp & 3;            // TMEM lane quarter of this warp
+    const int cg = warp >> 2;          // column group 0..3
+    const int r_t = q * 32 + lane;     // accumulator row owned by this thread
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int c0 = cg * G::CW;         // first column of this warp in the P / O phases
+    uint32_t n_x = 0, n_proj[2] = {0, 0}, n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
+
+    // address of the 16-byte chunk holding columns [c, c + 4) of this thread's row in the fp32 staging tile
+    auto sx_ptr = [&](int c) -> float4* {
+      return reinterpret_cast<float4*>(sX + (c >> 5) * 16384 + r_t * 128 + (((((c & 31) >> 2)) ^ (r_t & 7)) << 4));
+    };
+
+    int g = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int u = tl & 1;
+      // ---- P: x_new = acc2 + b_p + x;  y = LN(x_new) -> tensor memory;  acc2 = x_new + b2
+      {
+        DSG_TAIL_TRACE(g, 4);
+        mbar_wait(&proj_full[u], n_proj[u] & 1);
+        ++n_proj[u];
+        DSG_TAIL_TRACE(g, 5);
+        mbar_wait(xin_full, n_x & 1);
+        ++n_x;
+        tcgen05_fence_after();
+        DSG_TAIL_TRACE(g, 6);
+        uint32_t v[G::CW];
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 8) tmem_ld_32x8(t_lane + G::ACC2_COL + u * C + c0 + i, v + i);
+        tmem_ld_wait();
+        const float pivot = *reinterpret_cast<const float*>(sX + r_t * 128 + ((r_t & 7) << 4));  // x[r][0]
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 4) {
+          const float4 xi = *sx_ptr(c0 + i);
+          const float4 bb = *reinterpret_cast<const float4*>(&sBp[c0 + i]);
+          const float a0 = __uint_as_float(v[i]) + bb.x + xi.x, a1 = __uint_as_float(v[i + 1]) + bb.y + xi.y;
+          const float a2 = __uint_as_float(v[i + 2]) + bb.z + xi.z, a3 = __uint_as_float(v[i + 3]) + bb.w + xi.w;
+          v[i] = __float_as_uint(a0); v[i + 1] = __float_as_uint(a1);
+          v[i + 2] = __float_as_uint(a2); v[i + 3] = __float_as_uint(a3);
+          const float d0 = a0 - pivot, d1 = a1 - pivot, d2 = a2 - pivot, d3 = a3 - pivot;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+        }
+        sPart[cg * 128 + r_t] = make_float2(s1, s2);
+        // residual + fc2 bias back to tensor memory: fc2 accumulates on top of it
+        {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < G::CW; i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(__uint_as_float(v[i + k]) + sB2[c0 + i + k]);
+            tmem_st_32x8(t_lane + G::ACC2_COL + u * C + c0 + i, w);
+          }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 pp = sPart[k * 128 + r_t];
+          t1 += pp.x;
+          t2 += pp.y;
+        }
+        const float dm = t1 * (1.0f / C);                       // mean - pivot
+        const float var = fmaxf(t2 * (1.0f / C) - dm * dm, 0.f);
+        const float rstd = rsqrtf(var + kTailLnEps);
+        const float mean = pivot + dm;
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 8) {  // y as bf16 pairs: columns [c0 + i, + 8) -> 4 tensor-memory columns
+          uint32_t pk[4];
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const float y0 = fmaf((__uint_as_float(v[i + k]) - mean) * rstd, sGam[c0 + i + k], sBet[c0 + i + k]);
+            const float y1 = fmaf((__uint_as_float(v[i + k + 1]) - mean) * rstd, sGam[c0 + i + k + 1], sBet[c0 + i + k + 1]);
+            pk[k >> 1] = pack_bf16x2(y0, y1);
+          }
+          tmem_st_32x4(t_lane + G::Y_COL + ((c0 + i) >> 1), pk);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_ready);
+        DSG_TAIL_TRACE(g, 7);
+      }
+      // ---- O(t - 1): final accumulator of the previous tile -> staging tile (the slots this thread just read)
+      if (tl > 0) {
+        const int up = u ^ 1;
+        mbar_wait(&acc2_full[up], n_acc2[up] & 1);
+        ++n_acc2[up];
+        tcgen05_fence_after();
+        uint32_t v[G::CW];
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 8) tmem_ld_32x8(t_lane + G::ACC2_COL + up * C + c0 + i, v + i);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc2_empty[up]);
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 4)
+          *sx_ptr(c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                        __uint_as_float(v[i + 3]));
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_ready);
+      // ---- G: hidden chunks  acc1 -> + b1 -> GELU -> bf16 -> H[b] in tensor memory
+#pragma unroll 1
+      for (int j = 0; j < G::NCH; ++j, ++g) {
+        const int b = g & 1;
+        DSG_TAIL_TRACE(g, 0);
+        mbar_wait(&acc1_full[b], n_acc1[b] & 1);
+        ++n_acc1[b];
+        tcgen05_fence_after();
+        DSG_TAIL_TRACE(g, 1);
+        uint32_t r[16];
+        tmem_ld_32x16(t_lane + b * G::HC + cg * 16, r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_empty[b]);
+        uint32_t hp[8];
+        if (p.skip_gelu) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) hp[k >> 1] = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * 16 + k]);
+            hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
+            hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+          }
+        }
+        DSG_TAIL_TRACE(g, 2);
+        mbar_wait(&h_empty[b], (n_h[b] & 1) ^ 1);  // fc2 of chunk g - 2 has finished reading this H buffer
+        ++n_h[b];
+        tmem_st_32x8(t_lane + G::H_COL + b * (G::HC / 2) + cg * 8, hp);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_full[b]);
+        DSG_TAIL_TRACE(g, 3);
+      }
+    }
+    // ---- O(last)
+    if (my_tiles > 0) {
+      const int up = (my_tiles - 1) & 1;
+      mbar_wait(&acc2_full[up], n_acc2[up] & 1);
+      tcgen05_fence_after();
+      uint32_t v[G::CW];
+#pragma unroll
+      for (int i = 0; i < G::CW; i += 8) tmem_ld_32x8(t_lane + G::ACC2_COL + up * C + c0 + i, v + i);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < G::CW; i += 4)
+        *sx_ptr(c0 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                      __uint_as_float(v[i + 3]));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(out_ready);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+template <int C>
+int launch_c(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1, const CUtensorMap* tmW2,
+             const CUtensorMap* tmX, const TailParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TailCfg<C>::SMEM_BYTES));
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int tiles = (p.M + 127) / 128;
+  block_tail_kernel<C><<<tiles < sms ? tiles : sms, kTailThreads, TailCfg<C>::SMEM_BYTES, st>>>(*tmAtt, *tmWp, *tmW1,
+                                                                                               *tmW2, *tmX, p);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+}  // namespace
+
+bool block_tail_supported(int C) { return C == 96; }
+
+int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1,
+                      const CUtensorMap* tmW2, const CUtensorMap* tmX, const float* bp, const float* gamma,
+                      const float* beta, const float* b1, const float* b2, long long rows, int C, cudaStream_t st,
+                      long long* trace) {
+  DSG_REQUIRE(block_tail_supported(C) && rows > 0 && rows < 2147483647LL, "block_tail: C=%d rows=%lld", C, rows);
+  static const int skip = (getenv("DSG_TAIL_SKIP_GELU") != nullptr) ? 1 : 0;
+  TailParams p{bp, gamma, beta, b1, b2, static_cast<int>(rows), skip, trace};
+  return launch_c<96>(tmAtt, tmWp, tmW1, tmW2, tmX, p, st);
+}
+
+}  // namespace dsg

@@ -54,6 +54,23 @@ void count_launch(int n = 1);
 // ------------------------------------------------------------------------------------------------
 DSG_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// Warp-uniform values the compiler can PROVE uniform (a shuffle broadcast): branching on them keeps the MMA / TMA
+// issue code on the uniform datapath.  With `threadIdx.x >> 5` and `if (lane == 0)` ptxas wraps every tcgen05.mma
+// in an ELECT + 3x R2UR.BROADCAST + BRA.U.ANY loop (~95 clk per MMA, measured), which starves the tensor pipe.
+DSG_DEVICE int uniform_warp_id() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+DSG_DEVICE uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+DSG_DEVICE bool elect_one() {  // true in exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 DSG_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

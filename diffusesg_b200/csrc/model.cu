@@ -40,7 +40,7 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned 
 enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_MLP, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"gemm_tcgen05", "window_attention", "row_ln_film", "embed_heads_cond", "edm_step",
                                            "fused_mlp_tcgen05"};
-struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; char label[56]; long long rows; int c; };
 static bool g_prof_on = false;        // between dsg_profile_begin and dsg_profile_stop
 static bool g_prof_pass = false;      // the current denoiser pass is being bracketed
 static int g_prof_stride = 1, g_prof_counter = 0;
@@ -59,9 +59,13 @@ struct ProfScope {
   bool active = false;
   ProfRec rec;
   cudaStream_t st;
-  ProfScope(bool enabled, int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+  ProfScope(bool enabled, int cls, double flops, double bytes, cudaStream_t s, const char* label = "", long long rows = 0,
+            int c = 0) : st(s) {
     if (!enabled) return;
-    rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
+    rec.cls = cls; rec.flops = flops; rec.bytes = bytes; rec.rows = rows; rec.c = c;
+    size_t n = 0;  // label = the launcher's name: the text up to the first '(' of the bracketed expression
+    while (label[n] != 0 && label[n] != '(' && n + 1 < sizeof(rec.label)) { rec.label[n] = label[n]; ++n; }
+    rec.label[n] = 0;
     rec.e0 = prof_event(); rec.e1 = prof_event();
     if (rec.e0 == nullptr || rec.e1 == nullptr) return;
     active = cudaEventRecord(rec.e0, st) == cudaSuccess;
@@ -98,6 +102,7 @@ struct Block {
   int film_off;        // column of (scale, shift) in the film row
   Weight qkv, proj, fc1, fc2;
   CUtensorMap mlp_w1, mlp_w2;  // descriptors of fc1 / fc2 with the fused-MLP box shapes (C = 96, 192)
+  CUtensorMap tail_wp, tail_w1;  // proj / fc1 with the fused block-tail box shapes (32-column k-blocks)
   size_t qkv_bias_off;  // fp32 [3C], q part pre-scaled
   size_t attn_bias_off; // fp32 [heads, T, T]
 };
@@ -130,6 +135,7 @@ struct dsg_model {
   uint8_t* arena = nullptr;
   bool finalized = false;
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
+  bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -394,9 +400,11 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   const double mn = static_cast<double>(rows) * W.N;
   const double out_bytes = epi == EPI_ADJ_HEAD ? static_cast<double>(rows) * (extra ? extra->c_e : 0) * 4
                                                : mn * ((epi == EPI_BF16 || epi == EPI_GELU_BF16) ? 2 : 4);
+  char label[56];
+  snprintf(label, sizeof(label), "gemm_n%d_k%d_epi%d", W.N, W.K, epi);
   ProfScope ps(g_prof_pass, PC_GEMM, 2.0 * mn * W.K,
                static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
-                   (epi == EPI_RES_F32 ? mn * 4 : 0), st);
+                   (epi == EPI_RES_F32 ? mn * 4 : 0), st, label, rows, W.K);
   return launch_gemm(&it->second, &W.tmap, tmo, epi, p, st);
 }
 
@@ -409,7 +417,7 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
 // same, bracketed by a pair of CUDA events when this pass is being profiled (algorithmic flops / bytes attached)
 #define DSG_TRY_P(cls, flops, bytes, expr)                                    \
   do {                                                                        \
-    ProfScope _ps(g_prof_pass, cls, flops, bytes, st);                        \
+    ProfScope _ps(g_prof_pass, cls, flops, bytes, st, #expr);                 \
     int _rc = (expr);                                                         \
     if (_rc) return _rc;                                                      \
   } while (0)
@@ -429,21 +437,33 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
             launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
                                     b.heads, st));
+  auto tmap = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
+    auto k = std::make_tuple(ptr, rows, key);
+    auto it = m->a_maps.find(k);
+    if (it == m->a_maps.end()) {
+      CUtensorMap tm;
+      if (make(&tm)) return nullptr;
+      it = m->a_maps.emplace(k, tm).first;
+    }
+    return &it->second;
+  };
+  if (m->use_tail && block_tail_supported(C)) {
+    // x += proj(attn); x += fc2(gelu(fc1(LN2(x))))  in one launch        (:137, :272, :275)
+    const CUtensorMap* ta = tmap(w.ATT, 100000 + C, [&](CUtensorMap* t) { return make_tmap_2d(t, w.ATT, rows, C, 2, 32, 128); });
+    const CUtensorMap* tx = tmap(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
+    if (ta == nullptr || tx == nullptr) return DSG_ERR_CUDA;
+    DSG_TRY_P(PC_MLP, 18.0 * rc * C, rc * 10,
+              launch_block_tail(ta, &b.tail_wp, &b.tail_w1, &b.mlp_w2, tx, m->f32(p + ".attn.proj.bias"),
+                                m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"),
+                                m->f32(p + ".mlp.fc2.bias"), rows, C, st, g_mlp_trace));
+    g_mlp_trace = nullptr;
+    return DSG_OK;
+  }
   // x = x + proj(attn)                                                   (:137, :272)
   DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
   // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
   DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
   if (m->use_fused_mlp && fused_mlp_supported(C)) {
-    auto tmap = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
-      auto k = std::make_tuple(ptr, rows, key);
-      auto it = m->a_maps.find(k);
-      if (it == m->a_maps.end()) {
-        CUtensorMap tm;
-        if (make(&tm)) return nullptr;
-        it = m->a_maps.emplace(k, tm).first;
-      }
-      return &it->second;
-    };
     const CUtensorMap* ty = tmap(w.Y, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.Y, rows, C, 128); });
     const CUtensorMap* tx = tmap(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
     if (ty == nullptr || tx == nullptr) return DSG_ERR_CUDA;
@@ -475,6 +495,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   m->cfg = *cfg;
   const char* no_fuse = getenv("DSG_NO_FUSED_MLP");
   m->use_fused_mlp = !(no_fuse != nullptr && no_fuse[0] == '1');
+  const char* no_tail = getenv("DSG_NO_TAIL");
+  m->use_tail = !(no_tail != nullptr && no_tail[0] == '1');
   const int rc = build(m);
   if (rc) { delete m; return rc; }
   *out = m;
@@ -542,6 +564,10 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
     if (fused_mlp_supported(C)) {
       DSG_TRY(make_tmap_bf16(&b.mlp_w1, m->arena + b.fc1.offset, 4 * C, C, fused_mlp_w1_box_rows(C)));
       DSG_TRY(make_tmap_bf16(&b.mlp_w2, m->arena + b.fc2.offset, C, 4 * C, C));
+    }
+    if (block_tail_supported(C)) {
+      DSG_TRY(make_tmap_2d(&b.tail_wp, m->arena + b.proj.offset, C, C, 2, 32, C));
+      DSG_TRY(make_tmap_2d(&b.tail_w1, m->arena + b.fc1.offset, 4 * C, C, 2, 32, 64));
     }
     const TensorSpec& idx = m->tensors[m->index[p + ".attn.relative_position_index"]];
     DSG_TRY(launch_bias_expand(m->f32(p + ".attn.relative_position_bias_table"),
@@ -714,6 +740,21 @@ int dsg_profile_begin(int pass_stride) {
   g_prof_stride = pass_stride;
   g_prof_counter = 0;
   g_prof_on = true;
+  return DSG_OK;
+}
+
+int dsg_profile_dump(const char* path) {
+  DSG_REQUIRE(path != nullptr, "profile_dump: null path");
+  FILE* f = fopen(path, "w");
+  DSG_REQUIRE(f != nullptr, "profile_dump: cannot open %s", path);
+  fprintf(f, "index,class,label,rows,k,ms,flops,bytes\n");
+  int i = 0;
+  for (ProfRec& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1.f;
+    fprintf(f, "%d,%s,%s,%lld,%d,%.6f,%.0f,%.0f\n", i++, kProfNames[r.cls], r.label, r.rows, r.c, ms, r.flops, r.bytes);
+  }
+  fclose(f);
   return DSG_OK;
 }
 

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     "dsg_profile_begin": (C.c_int, [C.c_int]),
     "dsg_profile_read": (C.c_int, [C.POINTER(DsgProfileClass), C.c_int, C.POINTER(C.c_int)]),
+    "dsg_profile_dump": (C.c_int, [C.c_char_p]),
     "dsg_profile_stop": (None, []),
     "dsg_debug_set_stop_after": (None, [C.c_int]),
     "dsg_debug_trace_next_mlp": (None, [C.c_void_p]),
@@ -117,6 +118,11 @@ def profile_read() -> dict:
     check(lib().dsg_profile_read(arr, 8, C.byref(n)), "dsg_profile_read")
     return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=arr[i].ms, flops=arr[i].flops,
                                        bytes=arr[i].bytes) for i in range(n.value)}
+
+
+def profile_dump(path: str) -> None:
+    """Per-launch CSV (launch order) of the records gathered since the last profile_read."""
+    check(lib().dsg_profile_dump(path.encode()), "dsg_profile_dump")
 
 
 def profile_stop() -> None:

@@ -167,6 +167,9 @@ typedef struct dsg_profile_class {
 } dsg_profile_class;
 DSG_API int dsg_profile_begin(int pass_stride);
 DSG_API int dsg_profile_read(dsg_profile_class* out, int max_classes, int* n_classes);
+/* Write the records gathered since the last dsg_profile_read, one line per launch in launch order
+ * (index,class,label,rows,k,ms,flops,bytes), to a CSV file.  Call before dsg_profile_read (which consumes them). */
+DSG_API int dsg_profile_dump(const char* path);
 DSG_API void dsg_profile_stop(void);
 
 /* ---- test hooks (used by tests/ to localise a parity failure; not part of the product path) ------------------- */

@@ -134,6 +134,29 @@ def test_fused_mlp_matches_unfused_schedule(name, batch):
     assert rel(fa, ua) < 3e-3 and rel(fn, un) < 3e-3, (rel(fa, ua), rel(fn, un))
 
 
+@pytest.mark.parametrize("name,batch", [("vg", 3), ("vg", 40)])
+def test_block_tail_matches_unfused_schedule(name, batch):
+    """The fused proj + residual + LN2 + MLP kernel (C = 96 blocks) against the proj GEMM, LayerNorm and fused-MLP
+    launches it replaces: same bf16 roundings of the LN output and of the hidden activation; the fp32 accumulation
+    order and the (pivot-shifted one-pass) LayerNorm statistics differ, which flips bf16 roundings: measured 5.5e-3
+    on the stress weights, with both schedules at the same 0.97e-2 from the oracle (test_forward_stage_by_stage)."""
+    cfg = CONFIGS[name]
+    inputs = [t.to(DEV) for t in synthetic_inputs(cfg, batch, seed=13)]
+    adj, node, flags, sigmas, sc_adj, sc_node = inputs
+    outs = []
+    for no_tail in ("0", "1"):
+        os.environ["DSG_NO_TAIL"] = no_tail
+        try:
+            model, _ = build(cfg)
+            with torch.no_grad():
+                outs.append(model(adj, node, flags, sigmas.log() / 4, sc_adj, sc_node))
+        finally:
+            os.environ.pop("DSG_NO_TAIL", None)
+    (fa, fn), (ua, un) = outs
+    assert torch.isfinite(fa).all() and torch.isfinite(fn).all()
+    assert rel(fa, ua) < 8e-3 and rel(fn, un) < 8e-3, (rel(fa, ua), rel(fn, un))
+
+
 def test_forward_uniform_vs_per_sample_sigma():
     cfg = CONFIGS["tiny"]
     model, _ = build(cfg)
