@@ -50,14 +50,18 @@ struct TailCfg {
   static constexpr int PART_BYTES = 4 * 128 * 8;   // LayerNorm partial sums: float2 [4 column groups][128 rows]
   static constexpr int SMEM_BYTES = 1024 + A_BYTES + X_BYTES + S1 * W1_SLOT + S2 * W2_SLOT + PART_BYTES +
                                     PAR_FLOATS * 4 + 512;
-  // TMEM columns: acc1[b] @ b HC | acc2[u] @ 2 HC + u C | y (bf16 pairs, the A operand of fc1) | H[b] (bf16 pairs,
-  // the A operand of fc2).  Both MLP GEMMs take A from tensor memory: an SS-mode MMA with N <= 96 is bound by the
-  // shared-memory read of its 128-row A operand (measured ~95 clk per K = 16 step instead of N / 2).
-  static constexpr int ACC2_COL = 2 * HC;
+  // TMEM columns: acc1[b] @ b HC (NB chunk buffers) | acc2[u] @ NB HC + u C | y (bf16 pairs, the A operand of fc1).
+  // Both MLP GEMMs take A from tensor memory.  The GELU output of a chunk is written IN PLACE over its fc1
+  // accumulator: the 16 hidden columns of K step k (fp32 columns [16k, 16k + 16) of acc1[b]) become the 8 packed
+  // bf16 columns [16k, 16k + 8), read and written by the same warp.  fc1 of chunk g + NB reuses the buffer of chunk
+  // g; it is issued after fc2 of chunk g by the same thread, and the tensor pipe executes in issue order, so the
+  // chunk ring needs no "empty" barriers and keeps NB chunks in flight.
+  static constexpr int NB = 4;
+  static constexpr int kProjAt = 1;  // proj of tile t + 1 is issued after fc2 of this chunk of tile t (all fc1 issued)
+  static constexpr int ACC2_COL = NB * HC;
   static constexpr int Y_COL = ACC2_COL + 2 * C;
-  static constexpr int H_COL = Y_COL + C / 2;
   static_assert(C % 32 == 0 && CW % 8 == 0, "tail: C must be a multiple of 32");
-  static_assert(H_COL + HC <= 512 && SMEM_BYTES <= 227 * 1024, "tail budget");
+  static_assert(Y_COL + C / 2 <= 512 && NB <= NCH && SMEM_BYTES <= 227 * 1024, "tail budget");
 };
 
 struct TailParams {
@@ -157,13 +161,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
   uint64_t* out_ready = att_full + 3;       // workers -> residual mover: sX consumed (and holds the previous output)
   uint64_t* proj_full = att_full + 4;       // [2] MMA -> workers: proj accumulator of the tile complete in acc2[u]
   uint64_t* y_ready = att_full + 6;         // workers -> MMA: y (bf16, tensor memory) and x_new + b2 (acc2[u]) stored
-  uint64_t* acc1_full = att_full + 7;       // [2]
-  uint64_t* acc1_empty = att_full + 9;      // [2]
-  uint64_t* h_full = att_full + 11;         // [2]
-  uint64_t* h_empty = att_full + 13;        // [2]
+  uint64_t* acc1_full = att_full + 7;       // [NB] MMA -> workers: fc1 of the chunk complete
+  uint64_t* h_full = att_full + 11;         // [NB] workers -> MMA: GELU output of the chunk in place
   uint64_t* acc2_full = att_full + 15;      // [2] MMA -> workers: last fc2 of the tile complete
   uint64_t* acc2_empty = att_full + 17;     // [2] workers -> MMA: output drained, proj of tile t + 2 may overwrite
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(att_full + 19);
+  static_assert(G::NB == 4, "barrier layout above assumes four chunk buffers");
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -186,12 +189,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
     mbar_init(y_ready, 16);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&proj_full[b], 1);
-      mbar_init(&acc1_full[b], 1);
-      mbar_init(&acc1_empty[b], 16);
-      mbar_init(&h_full[b], 16);
-      mbar_init(&h_empty[b], 1);
       mbar_init(&acc2_full[b], 1);
       mbar_init(&acc2_empty[b], 16);
+    }
+    for (int b = 0; b < G::NB; ++b) {
+      mbar_init(&acc1_full[b], 1);
+      mbar_init(&h_full[b], 16);
     }
     fence_barrier_init();
   }
@@ -245,17 +248,17 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       };
       if (my_tiles > 0) { load_att(0); load_wp(); }
       for (int tl = 0; tl < my_tiles; ++tl) {
-        load_w1(0);
-        DSG_TAIL_TRACE(tl * G::NCH, 0);
-        load_w1(1);
-        DSG_TAIL_TRACE(tl * G::NCH + 1, 0);
+        for (int j = 0; j < G::NB; ++j) {
+          load_w1(j);
+          DSG_TAIL_TRACE(tl * G::NCH + j, 0);
+        }
         if (tl + 1 < my_tiles) load_att(tl + 1);  // proj(tl) completes long before its weights' successors are due
         DSG_TAIL_TRACE(tl * G::NCH, 2);
         for (int j = 0; j < G::NCH; ++j) {
           load_w2(j);
           DSG_TAIL_TRACE(tl * G::NCH + j, 1);
-          if (j + 2 < G::NCH) { load_w1(j + 2); DSG_TAIL_TRACE(tl * G::NCH + j + 2, 0); }
-          else if (j + 2 == G::NCH && tl + 1 < my_tiles) { load_wp(); DSG_TAIL_TRACE(tl * G::NCH + j, 3); }
+          if (j + G::NB < G::NCH) { load_w1(j + G::NB); DSG_TAIL_TRACE(tl * G::NCH + j + G::NB, 0); }
+          if (j == G::kProjAt && tl + 1 < my_tiles) { load_wp(); DSG_TAIL_TRACE(tl * G::NCH + j, 3); }
         }
       }
     }
@@ -265,7 +268,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
     constexpr uint32_t idesc_h = umma_idesc_bf16(G::HC);   // fc1: N = HC
     int s1 = 0, s2 = 0;
     uint32_t ph1 = 0, ph2 = 0, n_att = 0, n_y = 0;
-    uint32_t n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
+    uint32_t n_acc2[2] = {0, 0};
     auto proj = [&](int tl) {  // acc2[u] = att . W_proj^T
       const int u = tl & 1;
       DSG_TAIL_TRACE(tl * G::NCH, 4);
@@ -299,10 +302,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       __syncwarp();
       DSG_TAIL_TRACE(tl * G::NCH, 6);
     };
-    auto fc1 = [&](int g) {  // acc1[g & 1] = y . W1[chunk]^T
-      const int b = g & 1;
-      mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
-      ++n_acc1[b];
+    auto fc1 = [&](int g) {  // acc1[g % NB] = y . W1[chunk]^T   (the buffer's previous fc2 was issued earlier: in order)
+      const int b = g % G::NB;
       mbar_wait(&w1_full[s1], ph1);
       tcgen05_fence_after();
       DSG_TAIL_TRACE(g, 0);
@@ -327,12 +328,10 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       ++n_y;
       tcgen05_fence_after();
       DSG_TAIL_TRACE(g, 7);
-      fc1(g);
-      fc1(g + 1);
+      for (int j = 0; j < G::NB; ++j) fc1(g + j);
       for (int j = 0; j < G::NCH; ++j, ++g) {
-        const int hb = g & 1;
-        mbar_wait(&h_full[hb], n_h[hb] & 1);
-        ++n_h[hb];
+        const int hb = g % G::NB;
+        mbar_wait(&h_full[hb], (g / G::NB) & 1);
         DSG_TAIL_TRACE(g, 2);
         mbar_wait(&w2_full[s2], ph2);
         tcgen05_fence_after();
@@ -340,16 +339,14 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
         if (elect_one()) {  // acc2[u] += H[chunk] . W2[:, chunk]^T   (always accumulating: acc2 holds x_new + b2)
           const uint64_t db = umma_desc_sw128(smem_u32(sW2 + s2 * G::W2_SLOT));
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tmem_base + G::ACC2_COL + u * C, tmem_base + G::H_COL + hb * (G::HC / 2) + k * 8, db + 2 * k,
-                         idesc_c, 1u);
+            umma_bf16_ts(tmem_base + G::ACC2_COL + u * C, tmem_base + hb * G::HC + k * 16, db + 2 * k, idesc_c, 1u);
           umma_commit(&w2_empty[s2]);
-          umma_commit(&h_empty[hb]);
           if (j == G::NCH - 1) umma_commit(&acc2_full[u]);
         }
         __syncwarp();
         if (++s2 == G::S2) { s2 = 0; ph2 ^= 1; }
-        if (j + 2 < G::NCH) fc1(g + 2);
-        else if (j + 2 == G::NCH && tl + 1 < my_tiles) proj(tl + 1);
+        if (j + G::NB < G::NCH) fc1(g + G::NB);
+        if (j == G::kProjAt && tl + 1 < my_tiles) proj(tl + 1);
       }
     }
   } else if (warp == kXWarp) {
@@ -389,7 +386,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
     const int r_t = q * 32 + lane;     // accumulator row owned by this thread
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int c0 = cg * G::CW;         // first column of this warp in the P / O phases
-    uint32_t n_x = 0, n_proj[2] = {0, 0}, n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
+    uint32_t n_x = 0, n_proj[2] = {0, 0}, n_acc2[2] = {0, 0};
 
     // address of the 16-byte chunk holding columns [c, c + 4) of this thread's row in the fp32 staging tile
     auto sx_ptr = [&](int c) -> float4* {
@@ -413,30 +410,45 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
 #pragma unroll
         for (int i = 0; i < G::CW; i += 8) tmem_ld_32x8(t_lane + G::ACC2_COL + u * C + c0 + i, v + i);
         tmem_ld_wait();
+        // packed fp32 pairs throughout: the workers are issue-bound
         const float pivot = *reinterpret_cast<const float*>(sX + r_t * 128 + ((r_t & 7) << 4));  // x[r][0]
-        float s1 = 0.f, s2 = 0.f;
+        const f32x2 npiv = f2_splat(-pivot);
+        f32x2 a[G::CW / 2];
+        f32x2 s1 = f2_splat(0.f), s2 = f2_splat(0.f);
 #pragma unroll
         for (int i = 0; i < G::CW; i += 4) {
           const float4 xi = *sx_ptr(c0 + i);
           const float4 bb = *reinterpret_cast<const float4*>(&sBp[c0 + i]);
-          const float a0 = __uint_as_float(v[i]) + bb.x + xi.x, a1 = __uint_as_float(v[i + 1]) + bb.y + xi.y;
-          const float a2 = __uint_as_float(v[i + 2]) + bb.z + xi.z, a3 = __uint_as_float(v[i + 3]) + bb.w + xi.w;
-          v[i] = __float_as_uint(a0); v[i + 1] = __float_as_uint(a1);
-          v[i + 2] = __float_as_uint(a2); v[i + 3] = __float_as_uint(a3);
-          const float d0 = a0 - pivot, d1 = a1 - pivot, d2 = a2 - pivot, d3 = a3 - pivot;
-          s1 += (d0 + d1) + (d2 + d3);
-          s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+          const f32x2 a0 = f2_add(f2_add(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), f2_pack(bb.x, bb.y)),
+                                  f2_pack(xi.x, xi.y));
+          const f32x2 a1 = f2_add(f2_add(f2_pack(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), f2_pack(bb.z, bb.w)),
+                                  f2_pack(xi.z, xi.w));
+          a[i >> 1] = a0;
+          a[(i >> 1) + 1] = a1;
+          const f32x2 d0 = f2_add(a0, npiv), d1 = f2_add(a1, npiv);
+          s1 = f2_add(s1, f2_add(d0, d1));
+          s2 = f2_fma(d0, d0, f2_fma(d1, d1, s2));
         }
-        sPart[cg * 128 + r_t] = make_float2(s1, s2);
-        // residual + fc2 bias back to tensor memory: fc2 accumulates on top of it
         {
+          float s1a, s1b, s2a, s2b;
+          f2_unpack(s1, s1a, s1b);
+          f2_unpack(s2, s2a, s2b);
+          sPart[cg * 128 + r_t] = make_float2(s1a + s1b, s2a + s2b);
+        }
+        // residual + fc2 bias back to tensor memory: fc2 accumulates on top of it
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 8) {
           uint32_t w[8];
 #pragma unroll
-          for (int i = 0; i < G::CW; i += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(__uint_as_float(v[i + k]) + sB2[c0 + i + k]);
-            tmem_st_32x8(t_lane + G::ACC2_COL + u * C + c0 + i, w);
+          for (int k = 0; k < 8; k += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(&sB2[c0 + i + k]);
+            float w0, w1, w2, w3;
+            f2_unpack(f2_add(a[(i + k) >> 1], f2_pack(bb.x, bb.y)), w0, w1);
+            f2_unpack(f2_add(a[((i + k) >> 1) + 1], f2_pack(bb.z, bb.w)), w2, w3);
+            w[k] = __float_as_uint(w0); w[k + 1] = __float_as_uint(w1);
+            w[k + 2] = __float_as_uint(w2); w[k + 3] = __float_as_uint(w3);
           }
+          tmem_st_32x8(t_lane + G::ACC2_COL + u * C + c0 + i, w);
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         float t1 = 0.f, t2 = 0.f;
@@ -449,15 +461,18 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
         const float dm = t1 * (1.0f / C);                       // mean - pivot
         const float var = fmaxf(t2 * (1.0f / C) - dm * dm, 0.f);
         const float rstd = rsqrtf(var + kTailLnEps);
-        const float mean = pivot + dm;
+        const f32x2 rs2 = f2_splat(rstd);
+        const f32x2 nmr = f2_splat(-(pivot + dm) * rstd);       // y = (a rstd - mean rstd) gamma + beta
 #pragma unroll
         for (int i = 0; i < G::CW; i += 8) {  // y as bf16 pairs: columns [c0 + i, + 8) -> 4 tensor-memory columns
           uint32_t pk[4];
 #pragma unroll
-          for (int k = 0; k < 8; k += 2) {
-            const float y0 = fmaf((__uint_as_float(v[i + k]) - mean) * rstd, sGam[c0 + i + k], sBet[c0 + i + k]);
-            const float y1 = fmaf((__uint_as_float(v[i + k + 1]) - mean) * rstd, sGam[c0 + i + k + 1], sBet[c0 + i + k + 1]);
-            pk[k >> 1] = pack_bf16x2(y0, y1);
+          for (int k = 0; k < 8; k += 4) {
+            const float4 gg = *reinterpret_cast<const float4*>(&sGam[c0 + i + k]);
+            const float4 be = *reinterpret_cast<const float4*>(&sBet[c0 + i + k]);
+            pk[k >> 1] = pack_bf16x2(f2_fma(f2_fma(a[(i + k) >> 1], rs2, nmr), f2_pack(gg.x, gg.y), f2_pack(be.x, be.y)));
+            pk[(k >> 1) + 1] =
+                pack_bf16x2(f2_fma(f2_fma(a[((i + k) >> 1) + 1], rs2, nmr), f2_pack(gg.z, gg.w), f2_pack(be.z, be.w)));
           }
           tmem_st_32x4(t_lane + G::Y_COL + ((c0 + i) >> 1), pk);
         }
@@ -491,18 +506,14 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       // ---- G: hidden chunks  acc1 -> + b1 -> GELU -> bf16 -> H[b] in tensor memory
 #pragma unroll 1
       for (int j = 0; j < G::NCH; ++j, ++g) {
-        const int b = g & 1;
+        const int b = g % G::NB;
         DSG_TAIL_TRACE(g, 0);
-        mbar_wait(&acc1_full[b], n_acc1[b] & 1);
-        ++n_acc1[b];
+        mbar_wait(&acc1_full[b], (g / G::NB) & 1);
         tcgen05_fence_after();
         DSG_TAIL_TRACE(g, 1);
         uint32_t r[16];
         tmem_ld_32x16(t_lane + b * G::HC + cg * 16, r);
         tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[b]);
         uint32_t hp[8];
         if (p.skip_gelu) {
 #pragma unroll
@@ -511,14 +522,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 16; k += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * 16 + k]);
-            hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
-            hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+            hp[k >> 1] = gelu_bias_bf16x2(r[k], r[k + 1], bb.x, bb.y);
+            hp[(k >> 1) + 1] = gelu_bias_bf16x2(r[k + 2], r[k + 3], bb.z, bb.w);
           }
         }
         DSG_TAIL_TRACE(g, 2);
-        mbar_wait(&h_empty[b], (n_h[b] & 1) ^ 1);  // fc2 of chunk g - 2 has finished reading this H buffer
-        ++n_h[b];
-        tmem_st_32x8(t_lane + G::H_COL + b * (G::HC / 2) + cg * 8, hp);
+        tmem_st_32x8(t_lane + b * G::HC + cg * 16, hp);  // in place: first half of this warp's own 16 fp32 columns
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();

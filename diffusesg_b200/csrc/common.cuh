@@ -91,26 +91,74 @@ DSG_DEVICE float rcp_approx(float x) {
 
 DSG_DEVICE float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
-// exact (erf) GELU, the reference's nn.GELU() default (model/diffusesg/diffusesg.py:10,15):
-//   gelu(x) = x Phi(x) = max(x, 0) - |x| Phi(-|x|),   Phi(-a) = erfc(a / sqrt 2) / 2 = 2^P(a)
-// P = degree-7 Chebyshev fit of log2 of the Gaussian tail on [0, 8] (a is clamped there; 8 * Phi(-8) < 1e-14).
-// |gelu - gelu_erf| <= 4.2e-6 everywhere and the tail keeps 3.4e-5 RELATIVE accuracy (no 1 + erf cancellation),
-// both far below the bf16 rounding of the result.  11 FP32 ops + 1 MUFU per element; erff() costs ~40.
+// ------------------------------------------------------------------------------------------------
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot.  The epilogue warps of the
+// tcgen05 kernels are issue-bound, not latency-bound, so halving the instruction count is a direct speed-up.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+DSG_DEVICE f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+DSG_DEVICE f32x2 f2_splat(float v) { return f2_pack(v, v); }
+DSG_DEVICE void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DSG_DEVICE f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+DSG_DEVICE f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+DSG_DEVICE f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+DSG_DEVICE float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// erf GELU, the reference's nn.GELU() default (model/diffusesg/diffusesg.py:10,15), evaluated as
+//   gelu(x) = x/2 (1 + tanh(x (a + b x^2 + c x^4)))
+// with (a, b, c) a minimax fit to the ERF form (not the "tanh GELU" constants): |fit - gelu_erf| <= 2.6e-5
+// everywhere, 2.6e-5 relative rms under N(0,1) inputs.  MUFU.TANH adds <= 2^-11 relative error on tanh.  Both are far
+// below the bf16 rounding every call site applies to the result (1.7e-3 relative rms).  Two elements cost 6 packed
+// FP32 instructions + 2 MUFU; erff() costs ~40 per element.
+DSG_DEVICE f32x2 gelu_erf2(f32x2 x) {
+  const f32x2 x2 = f2_mul(x, x);
+  f32x2 q = f2_fma(x2, f2_splat(-3.51516789e-04f), f2_splat(3.70056460e-02f));
+  q = f2_fma(x2, q, f2_splat(7.97507884e-01f));
+  float u0, u1;
+  f2_unpack(f2_mul(x, q), u0, u1);
+  const f32x2 t = f2_pack(tanh_approx(u0), tanh_approx(u1));
+  const f32x2 h = f2_mul(x, f2_splat(0.5f));
+  return f2_fma(h, t, h);
+}
 DSG_DEVICE float gelu_erf(float x) {
-  const float a = fminf(fabsf(x), 8.0f);
-  float p = fmaf(-1.2696531257461174e-06f, a, 4.8437803343404084e-05f);
-  p = fmaf(p, a, -0.0008102938299998641f);
-  p = fmaf(p, a, 0.007964570075273514f);
-  p = fmaf(p, a, -0.0527045913040638f);
-  p = fmaf(p, a, -0.45983797311782837f);
-  p = fmaf(p, a, -1.150692105293274f);
-  p = fmaf(p, a, -1.0000319480895996f);
-  return fmaf(-a, ex2_approx(p), fmaxf(x, 0.0f));
+  const float x2 = x * x;
+  const float q = fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(x * q), h);
 }
 
 DSG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+DSG_DEVICE uint32_t pack_bf16x2(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+// bf16x2(gelu(acc + bias)) of two adjacent accumulator columns
+DSG_DEVICE uint32_t gelu_bias_bf16x2(uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  return pack_bf16x2(gelu_erf2(f2_add(f2_pack(__uint_as_float(acc_lo), __uint_as_float(acc_hi)), f2_pack(b_lo, b_hi))));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -274,7 +274,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (EPI == EPI_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; j += 2) f2_unpack(gelu_erf2(f2_pack(v[j], v[j + 1])), v[j], v[j + 1]);
           }
           if (kOutBf16) {
             // 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3

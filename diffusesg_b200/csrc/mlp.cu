@@ -334,8 +334,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(&sB1[j * G::HC + cg * G::CQ + c0 + k]);
-              hp[k >> 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k]) + bb.x), gelu_erf(__uint_as_float(r[k + 1]) + bb.y));
-              hp[(k >> 1) + 1] = pack_bf16x2(gelu_erf(__uint_as_float(r[k + 2]) + bb.z), gelu_erf(__uint_as_float(r[k + 3]) + bb.w));
+              hp[k >> 1] = gelu_bias_bf16x2(r[k], r[k + 1], bb.x, bb.y);
+              hp[(k >> 1) + 1] = gelu_bias_bf16x2(r[k + 2], r[k + 3], bb.z, bb.w);
             }
           }
           if (c0 == 0) {
