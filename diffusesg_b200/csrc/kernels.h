@@ -73,15 +73,15 @@ int launch_fused_mlp(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUte
 // fused block tail:  x += proj(att) + b_p;  x += fc2(gelu(fc1(LN2(x)) + b1)) + b2     (blocktail.cu)
 // ---------------------------------------------------------------------------------------------
 // Built for C = 96.  tmAtt: att [rows, C] bf16, box 32 x 128 (64-byte swizzle); tmWp: proj.weight [C, C] bf16, box
-// 32 x C; tmW1: fc1.weight [4C, C] bf16, box 32 x 64; tmW2: fc2.weight [C, 4C] bf16, box 64 x C (128-byte swizzle);
-// tmX: x [rows, C] fp32, box 32 x 128 (make_tmap_out, EPI_RES_F32) - read and written in place.
+// 32 x C; tmW1: fc1.weight [4C, C] bf16, box 32 x 128; tmW2: fc2.weight [C, 4C] bf16, box 64 x C (128-byte swizzle);
+// tmX: x [rows, C] fp32, box 32 x 128 (make_tmap_out, EPI_RES_F32); x: the same buffer, written in place.
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes, int box_cols,
                  int box_rows);
 bool block_tail_supported(int C);
 int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1,
                       const CUtensorMap* tmW2, const CUtensorMap* tmX, const float* bp, const float* gamma,
-                      const float* beta, const float* b1, const float* b2, long long rows, int C, cudaStream_t st,
-                      long long* trace = nullptr);
+                      const float* beta, const float* b1, const float* b2, float* x, long long rows, int C,
+                      cudaStream_t st, long long* trace = nullptr);
 
 // ---------------------------------------------------------------------------------------------
 // shifted-window attention                                             (attention.cu)

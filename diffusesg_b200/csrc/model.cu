@@ -455,7 +455,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     DSG_TRY_P(PC_MLP, 18.0 * rc * C, rc * 10,
               launch_block_tail(ta, &b.tail_wp, &b.tail_w1, &b.mlp_w2, tx, m->f32(p + ".attn.proj.bias"),
                                 m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"),
-                                m->f32(p + ".mlp.fc2.bias"), rows, C, st, g_mlp_trace));
+                                m->f32(p + ".mlp.fc2.bias"), w.X, rows, C, st, g_mlp_trace));
     g_mlp_trace = nullptr;
     return DSG_OK;
   }
@@ -567,7 +567,7 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
     }
     if (block_tail_supported(C)) {
       DSG_TRY(make_tmap_2d(&b.tail_wp, m->arena + b.proj.offset, C, C, 2, 32, C));
-      DSG_TRY(make_tmap_2d(&b.tail_w1, m->arena + b.fc1.offset, 4 * C, C, 2, 32, 64));
+      DSG_TRY(make_tmap_2d(&b.tail_w1, m->arena + b.fc1.offset, 4 * C, C, 2, 32, 128));
     }
     const TensorSpec& idx = m->tensors[m->index[p + ".attn.relative_position_index"]];
     DSG_TRY(launch_bias_expand(m->f32(p + ".attn.relative_position_bias_table"),
