@@ -231,6 +231,111 @@ breakup_ln_kernel(const float* __restrict__ t, bf16* __restrict__ y, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Quarter-warp versions of the two kernels above for the widths the shipped geometries use (C / Dq a multiple of
+// 32): lanes [8k, 8k + 8) own source pixel / chunk k, so the 2x2 gather (scatter) is plain address arithmetic per
+// lane group, the per-chunk LayerNorm is an 8-lane shuffle reduction, and no lane divides by a run-time width.  The
+// generic kernels above spend ~1.4 k instructions per row on that index arithmetic and are issue-bound at 2 TB/s.
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>  // NV = C / 32 float4 per lane
+__global__ void __launch_bounds__(kRowThreads)
+merge_ln_q_kernel(const float* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, long long rows_out, int res) {
+  constexpr int C = NV * 32, C4 = 4 * C;
+  const int lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows_out) return;
+  const int half = res >> 1;
+  const int ox = static_cast<int>(row % half);
+  const int oy = static_cast<int>((row / half) % half);
+  const long long b = row / (static_cast<long long>(half) * half);
+  // channel block q holds pixel (2y + q % 2, 2x + q / 2)                         (:325-329)
+  const float* src = x + ((b * res + (2 * oy + (q & 1))) * res + (2 * ox + (q >> 1))) * C;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (sub + 8 * i) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / C4);
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    qq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(qq) * (1.0f / C4) + kLnEps);
+  bf16* dst = y + row * C4 + q * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (sub + 8 * i) * 4;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma + q * C + e));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + q * C + e));
+    *reinterpret_cast<uint2*>(dst + e) = pack4_bf16(fmaf(v[i].x * rstd, gg.x, bb.x), fmaf(v[i].y * rstd, gg.y, bb.y),
+                                                    fmaf(v[i].z * rstd, gg.z, bb.z), fmaf(v[i].w * rstd, gg.w, bb.w));
+  }
+}
+
+template <int NV>  // NV = Dq / 32 float4 per lane, Dq = D / 4
+__global__ void __launch_bounds__(kRowThreads)
+breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const float* __restrict__ g1,
+                    const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
+                    long long rows_in, int res) {
+  constexpr int Dq = NV * 32, D = 4 * Dq;
+  const int lane = threadIdx.x & 31, k = lane >> 3, sub = lane & 7;
+  const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  if (row >= rows_in) return;
+  const int ix = static_cast<int>(row % res);
+  const int iy = static_cast<int>((row / res) % res);
+  const long long b = row / (static_cast<long long>(res) * res);
+  const float* src = t + row * D + k * Dq;  // lanes [8k, 8k + 8) own chunk k = elements [k Dq, (k + 1) Dq)
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (sub + 8 * i) * 4);
+  // LayerNorm(D) over the whole row                                              (:386)
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    qq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(qq) * (1.0f / D) + kLnEps);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = k * Dq + (sub + 8 * i) * 4;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g1 + e));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + e));
+    v[i].x = fmaf(v[i].x * rstd, gg.x, bb.x); v[i].y = fmaf(v[i].y * rstd, gg.y, bb.y);
+    v[i].z = fmaf(v[i].z * rstd, gg.z, bb.z); v[i].w = fmaf(v[i].w * rstd, gg.w, bb.w);
+    s2 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  // LayerNorm(D / 4) of this lane group's chunk                                   (:399)
+  const float mean2 = group_sum<8>(s2) * (1.0f / Dq);
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean2; v[i].y -= mean2; v[i].z -= mean2; v[i].w -= mean2;
+    q2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd2 = rsqrtf(group_sum<8>(q2) * (1.0f / Dq) + kLnEps);
+  // chunk k lands on pixel (2y + k % 2, 2x + k / 2) of the up-sampled grid        (:394-397)
+  const int res2 = 2 * res;
+  bf16* dst = y + ((b * res2 + (2 * iy + (k & 1))) * res2 + (2 * ix + (k >> 1))) * Dq;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (sub + 8 * i) * 4;
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g2 + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c));
+    *reinterpret_cast<uint2*>(dst + c) = pack4_bf16(fmaf(v[i].x * rstd2, gg.x, bb.x), fmaf(v[i].y * rstd2, gg.y, bb.y),
+                                                    fmaf(v[i].z * rstd2, gg.z, bb.z), fmaf(v[i].w * rstd2, gg.w, bb.w));
+  }
+}
+
 // y[m] = bf16([x[m], skip[m]])                                                    (:753 torch.cat)
 __global__ void __launch_bounds__(256)
 concat_bf16_kernel(const float* __restrict__ x, const float* __restrict__ skip, bf16* __restrict__ y, long long rows,
@@ -326,13 +431,15 @@ __global__ void node_proj_kernel(const float* __restrict__ node, const float* __
   rc[static_cast<size_t>(bi) * 2 * embed + e2] = acc;
 }
 
-// One thread per pixel (b, i, j), a warp covers 32 consecutive pixels: the c_e (x2) adjacency planes are read
-// coalesced, the 96 output channels of the pixel live in registers (1x1-conv weights broadcast from shared
-// memory), LayerNorm and FiLM are thread-local, and the [32 pixels x 96] tile leaves through a padded
-// shared-memory transpose so that every store instruction writes one full 128-byte line.
+// Eight lanes per pixel (b, i, j), a warp covers 4 consecutive pixels per step: lane `sub` of a group owns channels
+// [4 (sub + 8 i), + 4), i < 3, so the rc rows, the FiLM rows and the output row are read / written as whole
+// 128-byte lines and LayerNorm is an 8-lane shuffle reduction.  The c_e (x2) adjacency planes of the pixel are
+// loaded by the first lanes of the group and broadcast by shuffle; the 1x1-conv weights come from shared memory.
+// (A thread-per-pixel version with the 96 channels in registers ran at 1.3 TB/s: 128 registers, a shared-memory
+// transpose for the stores and 32 sectors per rc-row load instruction.)
 // x0 = silu(shift + LN(conv1x1(input)) * (1 + scale))
 constexpr int kPE = 96;
-__global__ void __launch_bounds__(kRowThreads, 2)
+__global__ void __launch_bounds__(kRowThreads, 4)
 patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_adj, const float* __restrict__ in_scale,
                    const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -340,93 +447,95 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
                    long long pixels, int n, int c_e, int self_cond) {
   constexpr int E = kPE;
   __shared__ __align__(16) float sW[16 * E];
-  __shared__ __align__(16) float sB[E], sG[E], sBe[E];
-  __shared__ float sT[kRowThreads / 32][32][33];
   const int planes = self_cond ? 2 * c_e : c_e;
-  for (int i = threadIdx.x; i < planes * E; i += kRowThreads) sW[i] = w_adj[i];
-  for (int i = threadIdx.x; i < E; i += kRowThreads) { sB[i] = bias[i]; sG[i] = gamma[i]; sBe[i] = beta[i]; }
+  for (int i = threadIdx.x; i < 16 * E; i += kRowThreads) sW[i] = (i < planes * E) ? w_adj[i] : 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp_base = lane & ~7;
   const int nn = n * n;
-  const long long groups = (pixels + 31) / 32;
-  for (long long grp = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + warp; grp < groups;
-       grp += static_cast<long long>(gridDim.x) * (kRowThreads / 32)) {
-    const long long pix0 = grp * 32;
-    const long long pix = pix0 + lane;
+  const long long quads = (pixels + 3) / 4;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (kRowThreads / 32);
+  // per-lane constants: bias, LayerNorm affine of this lane's 12 channels
+  float4 cb[3], cg[3], cbe[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int e = (sub + 8 * i) * 4;
+    cb[i] = __ldg(reinterpret_cast<const float4*>(bias + e));
+    cg[i] = __ldg(reinterpret_cast<const float4*>(gamma + e));
+    cbe[i] = __ldg(reinterpret_cast<const float4*>(beta + e));
+  }
+  for (long long quad = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5); quad < quads;
+       quad += warps_total) {
+    const long long pix = quad * 4 + (lane >> 3);
     const bool valid = pix < pixels;
     const long long pc = valid ? pix : pixels - 1;
     const int b = static_cast<int>(pc / nn);
     const int ij = static_cast<int>(pc - static_cast<long long>(b) * nn);
-    const int i = ij / n, j = ij - i * n;
-    const bool pair_ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+    const int i_ = ij / n, j_ = ij - i_ * n;
+    const bool pair_ok = flags[b * n + i_] != 0 && flags[b * n + j_] != 0;
     const float sc = in_scale ? in_scale[b] : 1.f;
-    float v[E];
+    // adjacency planes [self-cond adj (c_e), c_in * adj (c_e)]: lane `sub` fetches planes sub and sub + 8
+    float mine[2];
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = sB[e];
-    // adjacency planes: [self-cond adj (c_e), c_in * adj (c_e)]; all loads are issued before the first use
-    float a[16];
-#pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-      a[ch] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int ch = sub + 8 * h;
+      float a = 0.f;
       if (ch < planes) {
         if (self_cond && ch < c_e) {
-          if (sc_adj) a[ch] = sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij];
+          if (sc_adj) a = sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij];
         } else {
           const int c = self_cond ? ch - c_e : ch;
-          a[ch] = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+          a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
         }
       }
+      mine[h] = a;
     }
+    float4 v[3] = {cb[0], cb[1], cb[2]};
 #pragma unroll
     for (int ch = 0; ch < 16; ++ch) {
-      if (ch < planes) {
-        const float4* w4 = reinterpret_cast<const float4*>(&sW[ch * E]);
+      const float a = __shfl_sync(0xffffffffu, mine[ch >> 3], grp_base + (ch & 7));
+      if (ch < planes) {  // warp-uniform
 #pragma unroll
-        for (int e4 = 0; e4 < E / 4; ++e4) {
-          const float4 w = w4[e4];
-          v[4 * e4] = fmaf(w.x, a[ch], v[4 * e4]); v[4 * e4 + 1] = fmaf(w.y, a[ch], v[4 * e4 + 1]);
-          v[4 * e4 + 2] = fmaf(w.z, a[ch], v[4 * e4 + 2]); v[4 * e4 + 3] = fmaf(w.w, a[ch], v[4 * e4 + 3]);
+        for (int i = 0; i < 3; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(&sW[ch * E + (sub + 8 * i) * 4]);
+          v[i].x = fmaf(w.x, a, v[i].x); v[i].y = fmaf(w.y, a, v[i].y);
+          v[i].z = fmaf(w.z, a, v[i].z); v[i].w = fmaf(w.w, a, v[i].w);
         }
       }
     }
     if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)
-      const float4* rrow = reinterpret_cast<const float4*>(rc + (static_cast<size_t>(b) * n + i) * 2 * E);
-      const float4* rcol = reinterpret_cast<const float4*>(rc + (static_cast<size_t>(b) * n + j) * 2 * E + E);
+      const float* rrow = rc + (static_cast<size_t>(b) * n + i_) * 2 * E;
+      const float* rcol = rc + (static_cast<size_t>(b) * n + j_) * 2 * E + E;
 #pragma unroll
-      for (int e4 = 0; e4 < E / 4; ++e4) {
-        const float4 r1 = __ldg(rrow + e4), r2 = __ldg(rcol + e4);
-        v[4 * e4] += r1.x + r2.x; v[4 * e4 + 1] += r1.y + r2.y;
-        v[4 * e4 + 2] += r1.z + r2.z; v[4 * e4 + 3] += r1.w + r2.w;
+      for (int i = 0; i < 3; ++i) {
+        const int e = (sub + 8 * i) * 4;
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rrow + e));
+        const float4 r2 = __ldg(reinterpret_cast<const float4*>(rcol + e));
+        v[i].x += r1.x + r2.x; v[i].y += r1.y + r2.y; v[i].z += r1.z + r2.z; v[i].w += r1.w + r2.w;
       }
     }
-    float sum = 0.f;
+    float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) sum += v[e];
-    const float mean = sum / E;
+    for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = group_sum<8>(s) * (1.0f / E);
     float q = 0.f;
 #pragma unroll
-    for (int e = 0; e < E; ++e) { v[e] -= mean; q = fmaf(v[e], v[e], q); }
-    const float rstd = rsqrtf(q / E + kLnEps);
-    const float4* fs4 = reinterpret_cast<const float4*>(film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld);
-#pragma unroll
-    for (int e4 = 0; e4 < E / 4; ++e4) {
-      const float4 fsc = __ldg(fs4 + e4), fsh = __ldg(fs4 + E / 4 + e4);
-      const float s4[4] = {fsc.x, fsc.y, fsc.z, fsc.w}, t4[4] = {fsh.x, fsh.y, fsh.z, fsh.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int e = 4 * e4 + k;
-        const float y = fmaf(v[e] * rstd, sG[e], sBe[e]);
-        v[e] = silu_f(fmaf(y, s4[k] + 1.f, t4[k]));
-      }
+    for (int i = 0; i < 3; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
+    const float rstd = rsqrtf(group_sum<8>(q) * (1.0f / E) + kLnEps);
+    const float* fs = film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld;  // scale[E] then shift[E]
 #pragma unroll
-    for (int gq = 0; gq < E / 32; ++gq) {
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) sT[warp][lane][k] = v[32 * gq + k];
-      __syncwarp();
-      for (int p = 0; p < 32; ++p)
-        if (pix0 + p < pixels) x0[(pix0 + p) * E + 32 * gq + lane] = sT[warp][p][lane];
+    for (int i = 0; i < 3; ++i) {
+      const int e = (sub + 8 * i) * 4;
+      const float4 fsc = __ldg(reinterpret_cast<const float4*>(fs + e));
+      const float4 fsh = __ldg(reinterpret_cast<const float4*>(fs + E + e));
+      float4 o;
+      o.x = silu_f(fmaf(fmaf(v[i].x * rstd, cg[i].x, cbe[i].x), fsc.x + 1.f, fsh.x));
+      o.y = silu_f(fmaf(fmaf(v[i].y * rstd, cg[i].y, cbe[i].y), fsc.y + 1.f, fsh.y));
+      o.z = silu_f(fmaf(fmaf(v[i].z * rstd, cg[i].z, cbe[i].z), fsc.z + 1.f, fsh.z));
+      o.w = silu_f(fmaf(fmaf(v[i].w * rstd, cg[i].w, cbe[i].w), fsc.w + 1.f, fsh.w));
+      if (valid) *reinterpret_cast<float4*>(x0 + pix * E + e) = o;
     }
   }
 }
@@ -546,6 +655,14 @@ int launch_merge_ln(const float* x, bf16* y, const float* gamma, const float* be
                     cudaStream_t st) {
   DSG_REQUIRE(res % 2 == 0, "merge: odd resolution %d", res);
   const long long rows = static_cast<long long>(batch) * (res / 2) * (res / 2);
+  if (C == 96 || C == 192 || C == 384) {
+    const unsigned grid = row_grid(rows);
+    if (C == 96) merge_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
+    else if (C == 192) merge_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
+    else merge_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
+    DSG_LAUNCH_CHECK();
+    return DSG_OK;
+  }
   DSG_DISPATCH_NV(4 * C, (merge_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res, C)));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
@@ -564,6 +681,14 @@ int launch_breakup_ln(const float* t, bf16* y, const float* g1, const float* b1,
                       int batch, int res, int D, cudaStream_t st) {
   const long long rows = static_cast<long long>(batch) * res * res;
   DSG_REQUIRE(D % 16 == 0, "breakup: width %d", D);
+  if (D == 384 || D == 768 || D == 1536) {
+    const unsigned grid = row_grid(rows);
+    if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res);
+    else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res);
+    else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res);
+    DSG_LAUNCH_CHECK();
+    return DSG_OK;
+  }
   DSG_DISPATCH_NV(D, (breakup_ln_kernel<NV><<<row_grid(rows), kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, D)));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
@@ -609,8 +734,8 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
   DSG_REQUIRE(embed == 96, "patch_embed: embed_dim %d (only 96 is built)", embed);
   const long long pixels = static_cast<long long>(batch) * n * n;
   DSG_REQUIRE((self_cond ? 2 : 1) * c_e <= 16, "patch_embed: %d adjacency planes (max 16)", (self_cond ? 2 : 1) * c_e);
-  long long blocks = (pixels + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  long long blocks = (pixels / 4 + 7) / 8;  // one warp per 4 pixels per step
+  if (blocks > 148 * 64) blocks = 148 * 64;
   patch_embed_kernel<<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj,
                                                                            bias, gamma, beta, film + film_off, film_ld,
                                                                            cond_uniform, x0, pixels, n, c_e, self_cond);
