@@ -225,6 +225,11 @@ DSG_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "m
 template <int N>
 DSG_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+DSG_DEVICE void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
 DSG_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -261,17 +266,15 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
   const int g = lane >> 2, t4 = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
 
+  // two threads per token: thread `tid` fetches the 32-byte half `tid & 1` of the token's q, k and v head slices
   auto issue_loads = [&](int gw, int buf) {
     const WinOrigin org = window_origin(gw, res, shift, nW, nwx);
+    const int t = tid >> 1, half = (tid & 1) * 16;
+    const bf16* src = qkv + static_cast<size_t>(window_token_row(org, t, res)) * (3 * C) + h * HD + half;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int idx = tid + 128 * k;  // 64 tokens x 3 parts x 4 chunks of 16 bytes
-      const int t = idx / 12;
-      const int rem = idx - t * 12;
-      const int part = rem >> 2, chunk = rem & 3;
-      const int row = window_token_row(org, t, res);
-      cp_async16(&sbuf[buf][part][t * QK_PITCH + chunk * 8],
-                 qkv + static_cast<size_t>(row) * (3 * C) + part * C + h * HD + chunk * 8);
+    for (int part = 0; part < 3; ++part) {
+      cp_async16(&sbuf[buf][part][t * QK_PITCH + half], src + part * C);
+      cp_async16(&sbuf[buf][part][t * QK_PITCH + half + 8], src + part * C + 8);
     }
     cp_async_commit();
   };
@@ -303,26 +306,20 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
     const bf16* sK = sbuf[buf][1];
     const bf16* sV = sbuf[buf][2];
 
+    // A fragments of this warp's 16 query rows: matrices (rows 0-7 | 8-15) x (dims 0-7 | 8-15) of each K step
     uint32_t qa[2][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4]);
-      qa[ks][1] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4]);
-      qa[ks][2] = *reinterpret_cast<const uint32_t*>(&sQ[r0 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
-      qa[ks][3] = *reinterpret_cast<const uint32_t*>(&sQ[r1 * QK_PITCH + ks * 16 + 2 * t4 + 8]);
-    }
+    for (int ks = 0; ks < 2; ++ks)
+      ldmatrix_x4(qa[ks], &sQ[(warp * 16 + (lane & 15)) * QK_PITCH + ks * 16 + ((lane >> 4) << 3)]);
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = bia[nt][0]; s[nt][1] = bia[nt][1]; s[nt][2] = bia[nt][2]; s[nt][3] = bia[nt][3];
-      const int key = nt * 8 + g;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t kb[2];
-        kb[0] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4]);
-        kb[1] = *reinterpret_cast<const uint32_t*>(&sK[key * QK_PITCH + ks * 16 + 2 * t4 + 8]);
-        mma_m16n8k16_bf16(s[nt], qa[ks], kb);
-      }
+      // B fragments of keys nt*8 .. +7: matrices = dims [0,8) [8,16) [16,24) [24,32) -> (ks 0: b0 b1) (ks 1: b0 b1)
+      uint32_t kb[4];
+      ldmatrix_x4(kb, &sK[(nt * 8 + (lane & 7)) * QK_PITCH + ((lane >> 3) << 3)]);
+      mma_m16n8k16_bf16(s[nt], qa[0], reinterpret_cast<const uint32_t(&)[2]>(kb[0]));
+      mma_m16n8k16_bf16(s[nt], qa[1], reinterpret_cast<const uint32_t(&)[2]>(kb[2]));
     }
     if (mask != nullptr) {
       const float* mw = mask + static_cast<size_t>(gw % nW) * T * T;
