@@ -152,6 +152,19 @@ int launch_decode(const float* adj, const float* node, const uint8_t* flags, int
                   float* bbox, int num_adj_type, int num_node_type, int batch, int c_e, int n, int c_n, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
+// EDM training objective: noising and masked weighted squared-error sums            (train.cu)
+// ---------------------------------------------------------------------------------------------
+// x_adj = mask(y_adj + sigma_b e_adj), n_adj = mask(sigma_b e_adj); n_node = mask(sigma_b e_node), x_node = y_node + n_node
+int launch_train_noise(const float* y_adj, const float* y_node, const float* e_adj, const float* e_node,
+                       const float* sigmas, const uint8_t* flags, float* x_adj, float* n_adj, float* x_node,
+                       float* n_node, int batch, int c_e, int n, int c_n, cudaStream_t st);
+// s_adj[b] = sum mask w_b (d_adj - y_adj)^2, s_node[b] likewise; weights == nullptr means 1
+int launch_loss_sums(const float* d_adj, const float* y_adj, const float* d_node, const float* y_node,
+                     const float* weights, const uint8_t* flags, float* s_adj, float* s_node, int batch, int c_e, int n,
+                     int c_n, cudaStream_t st);
+
+
+// ---------------------------------------------------------------------------------------------
 // weight packing helpers (run once per weight update)                  (pack.cu)
 // ---------------------------------------------------------------------------------------------
 // dst bf16 = src * (i < n_scaled ? scale : 1)

@@ -836,6 +836,25 @@ int dsg_decode_samples(const float* adj, const float* node, const uint8_t* flags
                        static_cast<cudaStream_t>(stream));
 }
 
+int dsg_train_noise(const float* clean_adj, const float* clean_node, const float* eps_adj, const float* eps_node,
+                    const float* sigmas, const uint8_t* flags, float* noisy_adj, float* noise_adj, float* noisy_node,
+                    float* noise_node, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(clean_adj && clean_node && eps_adj && eps_node && sigmas && flags && noisy_adj && noise_adj && noisy_node &&
+                  noise_node,
+              "train_noise: null tensor");
+  return launch_train_noise(clean_adj, clean_node, eps_adj, eps_node, sigmas, flags, noisy_adj, noise_adj, noisy_node,
+                            noise_node, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, const float* pred_node, const float* target_node,
+                      const float* weights, const uint8_t* flags, float* sum_adj, float* sum_node, int batch, int c_e,
+                      int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(pred_adj && target_adj && pred_node && target_node && flags && sum_adj && sum_node,
+              "edm_loss_sums: null tensor");
+  return launch_loss_sums(pred_adj, target_adj, pred_node, target_node, weights, flags, sum_adj, sum_node, batch, c_e, n,
+                          c_n, static_cast<cudaStream_t>(stream));
+}
+
 int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
                   int epi, dsg_stream_t stream) {
   DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "dsg_edm_post_step": (C.c_int, [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_decode_samples": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p]),
+    "dsg_train_noise": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_loss_sums": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     "dsg_profile_begin": (C.c_int, [C.c_int]),
@@ -196,6 +198,42 @@ def edm_mask_scale(adj, node, flags, scale: float):
     check(lib().dsg_edm_mask_scale(ptr(adj), ptr(node), ptr(flags), float(scale), ptr(adj_out), ptr(node_out), b, ce, n,
                                    cn, stream_ptr(adj.device)), "dsg_edm_mask_scale")
     return adj_out, node_out
+
+
+def _flags_u8(flags: torch.Tensor) -> torch.Tensor:
+    return (flags if flags.dtype == torch.uint8 else flags.to(torch.uint8)).contiguous()
+
+
+def train_noise(clean_adj, clean_node, eps_adj, eps_node, sigmas, flags):
+    """(noisy_adj, noise_adj, noisy_node, noise_node) of the EDM training objective, one fused launch."""
+    clean_adj, clean_node = require_cuda(clean_adj, "clean_adj"), require_cuda(clean_node, "clean_node")
+    eps_adj, eps_node = require_cuda(eps_adj, "eps_adj"), require_cuda(eps_node, "eps_node")
+    sigmas = require_cuda(sigmas, "sigmas")
+    b, ce, n, _ = clean_adj.shape
+    cn = clean_node.shape[-1]
+    f = _flags_u8(flags)
+    outs = [torch.empty_like(clean_adj), torch.empty_like(clean_adj), torch.empty_like(clean_node),
+            torch.empty_like(clean_node)]
+    check(lib().dsg_train_noise(ptr(clean_adj), ptr(clean_node), ptr(eps_adj), ptr(eps_node), ptr(sigmas), ptr(f),
+                                ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), b, ce, n, cn,
+                                stream_ptr(clean_adj.device)), "dsg_train_noise")
+    return tuple(outs)
+
+
+def edm_loss_sums(pred_adj, target_adj, pred_node, target_node, weights, flags):
+    """([B] masked weighted squared-error sum over the adjacency tensor, [B] over the node tensor)."""
+    pred_adj, target_adj = require_cuda(pred_adj, "pred_adj"), require_cuda(target_adj, "target_adj")
+    pred_node, target_node = require_cuda(pred_node, "pred_node"), require_cuda(target_node, "target_node")
+    w = None if weights is None else require_cuda(weights.reshape(-1), "loss_weight")
+    b, ce, n, _ = pred_adj.shape
+    cn = pred_node.shape[-1]
+    f = _flags_u8(flags)
+    s_adj = torch.empty(b, device=pred_adj.device, dtype=torch.float32)
+    s_node = torch.empty_like(s_adj)
+    check(lib().dsg_edm_loss_sums(ptr(pred_adj), ptr(target_adj), ptr(pred_node), ptr(target_node), ptr(w), ptr(f),
+                                  ptr(s_adj), ptr(s_node), b, ce, n, cn, stream_ptr(pred_adj.device)),
+          "dsg_edm_loss_sums")
+    return s_adj, s_node
 
 
 def decode_samples(adj, node, flags, num_adj_type: int, num_node_type: int):

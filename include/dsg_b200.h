@@ -143,6 +143,22 @@ DSG_API int dsg_decode_samples(const float* adj, const float* node, const uint8_
                                int32_t* node_cls, float* bbox, int num_adj_type, int num_node_type, int batch,
                                int c_e, int n, int c_n, dsg_stream_t stream);
 
+/* ---- EDM training objective (BASELINE config 4; forward only) ---------------------------------------------------
+ * dsg_train_noise replaces NodeAdjEDMObjectiveGenerator.get_network_input (runner/objectives/edm.py:233-254) over
+ * add_sym_normal_noise(non_symmetric=True) (utils/graph_utils.py:122-152): eps_* are the caller's N(0,1) draws
+ * (torch.randn_like, in the reference's order: adjacency first, nodes second), sigmas is [batch]; the four outputs are
+ * bit-identical to the reference's fp32 expressions.
+ * dsg_edm_loss_sums replaces the elementwise part of NodeAdjRainbowLoss.get_regression_loss (loss/rainbow_loss.py:60-99):
+ * sum_adj[b] = sum mask w_b (pred - target)^2 over [C_e, N, N], sum_node[b] over [N, C_n]; weights may be NULL (= 1).
+ * The [batch]-sized normalisations (n_b^2 C_e, n_b C_n, loss weights, 'mean' / 'none') stay on the host. */
+DSG_API int dsg_train_noise(const float* clean_adj, const float* clean_node, const float* eps_adj, const float* eps_node,
+                            const float* sigmas, const uint8_t* flags, float* noisy_adj, float* noise_adj,
+                            float* noisy_node, float* noise_node, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
+DSG_API int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, const float* pred_node,
+                              const float* target_node, const float* weights, const uint8_t* flags, float* sum_adj,
+                              float* sum_node, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
+
+
 /* ---- building blocks, exported for the kernel-level parity tests ------------------------------------------- */
 /* out[M, N] = epilogue(A[M, K] . W[N, K]^T + bias); A, W bf16 row-major.  epi: 0 bf16, 1 gelu->bf16,
  * 2 fp32 + residual (res may alias out), 3 fp32.  tcgen05/TMEM/TMA kernel (nn.Linear of the reference). */

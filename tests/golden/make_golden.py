@@ -136,5 +136,51 @@ def main():
           float((ka - gt_a).abs().max()), float((kn - gt_n).abs().max()))
 
 
+def make_train_golden():
+    """(5) training objective + loss of the unmodified reference, tiny geometry, batch 4."""
+    torch.set_num_threads(8)
+    from diffusesg_b200.utils.synthetic import CONFIGS, synthetic_inputs
+    import_reference()
+    sys.path.insert(0, REF)
+    from runner.objectives.edm import NodeAdjEDMObjectiveGenerator
+    from loss.rainbow_loss import NodeAdjRainbowLoss
+    sys.path.remove(REF)
+    cfg = CONFIGS["tiny"]
+    adj, node, flags, _, _, _ = synthetic_inputs(cfg, 4, seed=7)
+    pair = flags[:, None, :, None] & flags[:, None, None, :]
+    clean_a = adj.sign() * pair                                   # +-1 bits, masked
+    clean_x = node.clamp(-1, 1) * flags[:, :, None]
+    gen = NodeAdjEDMObjectiveGenerator("edm", "edm", other_params=None, dev="cpu", symmetric_noise=False)
+    torch.manual_seed(31)
+    in_a, in_x, cond, tgt_a, tgt_x, (c_skip, c_out, c_in, c_noise, sigmas, weights) = gen.get_input_output(
+        clean_a, clean_x, flags)
+    # replay the draws the call above consumed: randn(B), randn_like(adj), randn_like(node)
+    torch.manual_seed(31)
+    rnd, eps_a, eps_x = torch.randn(4), torch.randn_like(clean_a), torch.randn_like(clean_x)
+    # a stand-in prediction: target + a smooth perturbation (no network involved)
+    torch.manual_seed(32)
+    pred_a = _maskf(tgt_a + 0.3 * torch.randn_like(tgt_a), pair)
+    pred_x = (tgt_x + 0.2 * torch.randn_like(tgt_x)) * flags[:, :, None]
+    loss = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=0.5, objective="edm")
+    out = dict(clean_a=clean_a.numpy(), clean_x=clean_x.numpy(), rnd=rnd.numpy(), eps_a=eps_a.numpy(),
+               eps_x=eps_x.numpy(), in_a=in_a.numpy(), in_x=in_x.numpy(), sigmas=sigmas.numpy(),
+               weights=weights.numpy(), c_skip=c_skip.numpy(), c_out=c_out.numpy(), c_in=c_in.numpy(),
+               c_noise=c_noise.numpy(), pred_a=pred_a.numpy(), pred_x=pred_x.numpy())
+    for red in ("none", "mean"):
+        la, ln = loss(pred_a, pred_x, tgt_a, tgt_x, cond, in_a, clean_a, in_x, clean_x, flags, loss_weight=weights,
+                      reduction=red)
+        out[f"loss_adj_{red}"], out[f"loss_node_{red}"] = la.numpy(), ln.numpy()
+    np.savez_compressed(os.path.join(HERE, "train_objective.npz"), **out)
+    print("train objective", {k: v.shape for k, v in out.items()})
+
+
+def _maskf(t, m):
+    return torch.where(m, t, torch.zeros_like(t))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-train" in sys.argv:
+        make_train_golden()
+    else:
+        main()
+        make_train_golden()

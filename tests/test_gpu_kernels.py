@@ -169,3 +169,62 @@ def test_decode_samples_bit_exact(b, ce, n, cn, n_adj, n_node):
     np.testing.assert_array_equal(gb.cpu().numpy(), box.numpy())
     assert int(ga.max()) <= n_adj - 1 and int(gn.max()) <= n_node - 1
     assert int(ga.diagonal(dim1=1, dim2=2).abs().sum()) == 0
+
+
+def test_training_objective_bit_exact_and_loss(golden_dir):
+    """Native noising (dsg_train_noise) and loss (dsg_edm_loss_sums) through the drop-in host classes against the
+    golden outputs of the unmodified reference: noising / coefficients bit-exact, loss within 1e-5 relative (fp64
+    accumulation here, fp32 pairwise sums there)."""
+    import os
+    from diffusesg_b200.loss.rainbow_loss import NodeAdjRainbowLoss
+    from diffusesg_b200.runner.objectives.edm import NodeAdjEDMObjectiveGenerator
+    from diffusesg_b200.utils.synthetic import CONFIGS, synthetic_inputs
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "train_objective.npz")).items()}
+    _, _, flags, _, _, _ = synthetic_inputs(CONFIGS["tiny"], 4, seed=7)
+    dev = torch.device("cuda:0")
+    # the fused launch on the reference's own draws
+    out = native.train_noise(g["clean_a"].to(dev), g["clean_x"].to(dev), g["eps_a"].to(dev), g["eps_x"].to(dev),
+                             g["sigmas"].to(dev), flags.to(dev))
+    assert torch.equal(out[0].cpu(), g["in_a"]) and torch.equal(out[2].cpu(), g["in_x"])
+    pair = flags[:, None, :, None] & flags[:, None, None, :]
+    assert torch.equal(out[1].cpu(), torch.where(pair, g["eps_a"] * g["sigmas"].view(-1, 1, 1, 1), torch.zeros(())))
+    assert float(out[3].cpu()[~flags].abs().sum()) == 0.0
+    # the generator end to end: same RNG consumption order as the reference (device generator here, so only the
+    # structure and the masking are checked, not the values)
+    gen = NodeAdjEDMObjectiveGenerator("edm", "edm", other_params=None, dev=dev, symmetric_noise=False)
+    torch.manual_seed(31)
+    in_a, in_x, cond, tgt_a, tgt_x, (c_skip, c_out, c_in, c_noise, sigmas, weights) = gen.get_input_output(
+        g["clean_a"].to(dev), g["clean_x"].to(dev), flags.to(dev))
+    assert in_a.shape == g["in_a"].shape and in_x.shape == g["in_x"].shape and cond is sigmas
+    assert float(in_a.cpu()[~pair.expand_as(in_a)].abs().sum()) == 0.0
+    torch.testing.assert_close(weights, (sigmas ** 2 + 0.25) / (sigmas * 0.5) ** 2)
+    # loss
+    loss = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=0.5, objective="edm")
+    for red in ("none", "mean"):
+        la, ln = loss(g["pred_a"].to(dev), g["pred_x"].to(dev), g["clean_a"].to(dev), g["clean_x"].to(dev),
+                      g["sigmas"].to(dev), None, None, None, None, flags.to(dev), loss_weight=g["weights"].to(dev),
+                      reduction=red)
+        torch.testing.assert_close(la.cpu(), g[f"loss_adj_{red}"], rtol=1e-5, atol=0)
+        torch.testing.assert_close(ln.cpu(), g[f"loss_node_{red}"], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("b,ce,n,cn", [(5, 6, 64, 12), (3, 3, 40, 12)])
+def test_training_objective_matches_oracle_full_size(b, ce, n, cn):
+    from oracle import train_oracle as T
+    g = torch.Generator().manual_seed(5)
+    flags = torch.zeros(b, n, dtype=torch.bool)
+    for i in range(b):
+        flags[i, : int(torch.randint(2, n - 1, (1,), generator=g))] = True
+    ca, cx = torch.randn(b, ce, n, n, generator=g).sign(), torch.rand(b, n, cn, generator=g) * 2 - 1
+    ea, ex = torch.randn(b, ce, n, n, generator=g), torch.randn(b, n, cn, generator=g)
+    sig, w = T.training_sigmas_weights(torch.randn(b, generator=g))
+    want = T.network_input(ca, cx, flags, sig, ea, ex)
+    dev = torch.device("cuda:0")
+    got = native.train_noise(ca.to(dev), cx.to(dev), ea.to(dev), ex.to(dev), sig.to(dev), flags.to(dev))
+    for a, bb in zip(got, want):
+        assert torch.equal(a.cpu(), bb)
+    sa, sn = native.edm_loss_sums(got[0], ca.to(dev), got[2], cx.to(dev), w.to(dev), flags.to(dev))
+    la, ln = T.regression_loss(want[0], want[2], ca, cx, flags, w, 1.0, 1.0, "none")
+    nn_ = flags.sum(-1)
+    torch.testing.assert_close(sa.cpu() / nn_ ** 2 / ce, la, rtol=1e-5, atol=0)
+    torch.testing.assert_close(sn.cpu() / nn_ / cn, ln, rtol=1e-5, atol=0)

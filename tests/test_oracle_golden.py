@@ -99,3 +99,19 @@ def test_sampler_known_answer(golden_dir):
     np.testing.assert_array_equal(a.numpy(), g["kat_adjs"])
     np.testing.assert_array_equal(n.numpy(), g["kat_nodes"])
     assert (a - gt[0]).abs().max() < 1e-6 and (n - gt[1]).abs().max() < 1e-6
+
+
+def test_training_objective_and_loss_match_reference(golden_dir):
+    """oracle/train_oracle.py against the unmodified reference's NodeAdjEDMObjectiveGenerator / NodeAdjRainbowLoss
+    (SURVEY 8a row a17): bit-exact noising and coefficients, loss within fp32 summation-order slack."""
+    from oracle import train_oracle as T
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "train_objective.npz")).items()}
+    _, _, flags, _, _, _ = synthetic_inputs(CONFIGS["tiny"], 4, seed=7)
+    sigmas, weights = T.training_sigmas_weights(g["rnd"])
+    assert torch.equal(sigmas, g["sigmas"]) and torch.equal(weights, g["weights"])
+    in_a, _, in_x, _ = T.network_input(g["clean_a"], g["clean_x"], flags, sigmas, g["eps_a"], g["eps_x"])
+    assert torch.equal(in_a, g["in_a"]) and torch.equal(in_x, g["in_x"])
+    for red in ("none", "mean"):
+        la, ln = T.regression_loss(g["pred_a"], g["pred_x"], g["clean_a"], g["clean_x"], flags, weights, 1.0, 0.5, red)
+        torch.testing.assert_close(la, g[f"loss_adj_{red}"], rtol=1e-6, atol=0)
+        torch.testing.assert_close(ln, g[f"loss_node_{red}"], rtol=1e-6, atol=0)
