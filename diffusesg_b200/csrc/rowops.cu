@@ -431,111 +431,184 @@ __global__ void node_proj_kernel(const float* __restrict__ node, const float* __
   rc[static_cast<size_t>(bi) * 2 * embed + e2] = acc;
 }
 
-// Eight lanes per pixel (b, i, j), a warp covers 4 consecutive pixels per step: lane `sub` of a group owns channels
-// [4 (sub + 8 i), + 4), i < 3, so the rc rows, the FiLM rows and the output row are read / written as whole
-// 128-byte lines and LayerNorm is an 8-lane shuffle reduction.  The c_e (x2) adjacency planes of the pixel are
-// loaded by the first lanes of the group and broadcast by shuffle; the 1x1-conv weights come from shared memory.
-// (A thread-per-pixel version with the 96 channels in registers ran at 1.3 TB/s: 128 registers, a shared-memory
-// transpose for the stores and 32 sectors per rc-row load instruction.)
+// Sixteen consecutive pixels (b, i, j) per warp step, on the legacy warp MMA (m16n8k16 bf16 -> fp32):
+//   conv1x1:  [16 pixels x 16 planes] . [16 planes x 96 channels], planes = c_e (x2 with self-conditioning), K padded
+//             with zeros.  Inputs and weights stay fp32-accurate: both are split into bf16 hi + lo parts and three
+//             products are accumulated (hi hi + hi lo + lo hi; the dropped lo lo term is 2^-16 relative).
+//   epilogue: on the accumulator fragments (thread (g, t) owns channel pairs 8 nt + 2t, +1 of pixels g and g + 8):
+//             + row / column node planes, LayerNorm over the 96 channels (quad shuffles), FiLM, SiLU, 8-byte stores
+//             (four lanes write one 32-byte sector).
+// The scalar versions of this kernel (one thread per pixel, then eight lanes per pixel) spent ~130 warp instructions
+// per pixel on the 1152 FMAs + weight loads of the conv and ran at 1.3 TB/s; this one needs ~35.
 // x0 = silu(shift + LN(conv1x1(input)) * (1 + scale))
 constexpr int kPE = 96;
-__global__ void __launch_bounds__(kRowThreads, 4)
+__global__ void __launch_bounds__(kRowThreads, 2)
 patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_adj, const float* __restrict__ in_scale,
                    const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ film, int film_ld, int cond_uniform, float* __restrict__ x0,
                    long long pixels, int n, int c_e, int self_cond) {
-  constexpr int E = kPE;
-  __shared__ __align__(16) float sW[16 * E];
+  constexpr int E = kPE, NT = E / 8;
+  __shared__ uint4 sBf[NT][32];                 // B fragments of n-tile nt for lane: {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
+  __shared__ __align__(16) float sBias[E], sGam[E], sBet[E];
   const int planes = self_cond ? 2 * c_e : c_e;
-  for (int i = threadIdx.x; i < 16 * E; i += kRowThreads) sW[i] = (i < planes * E) ? w_adj[i] : 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, sub = lane & 7, grp_base = lane & ~7;
-  const int nn = n * n;
-  const long long quads = (pixels + 3) / 4;
-  const long long warps_total = static_cast<long long>(gridDim.x) * (kRowThreads / 32);
-  // per-lane constants: bias, LayerNorm affine of this lane's 12 channels
-  float4 cb[3], cg[3], cbe[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int e = (sub + 8 * i) * 4;
-    cb[i] = __ldg(reinterpret_cast<const float4*>(bias + e));
-    cg[i] = __ldg(reinterpret_cast<const float4*>(gamma + e));
-    cbe[i] = __ldg(reinterpret_cast<const float4*>(beta + e));
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  auto split2 = [](float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    hi = pack_bf16x2(__bfloat162float(ah), __bfloat162float(bh));
+    lo = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+  };
+  for (int idx = threadIdx.x; idx < NT * 32; idx += kRowThreads) {
+    const int nt = idx >> 5, l = idx & 31, ch = nt * 8 + (l >> 2), k0 = 2 * (l & 3);
+    auto w = [&](int k) { return k < planes ? w_adj[k * E + ch] : 0.f; };  // B[k][n] = W[plane k][channel]
+    uint4 f;
+    split2(w(k0), w(k0 + 1), f.x, f.z);
+    split2(w(k0 + 8), w(k0 + 9), f.y, f.w);
+    sBf[nt][l] = f;
   }
-  for (long long quad = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5); quad < quads;
-       quad += warps_total) {
-    const long long pix = quad * 4 + (lane >> 3);
-    const bool valid = pix < pixels;
-    const long long pc = valid ? pix : pixels - 1;
-    const int b = static_cast<int>(pc / nn);
-    const int ij = static_cast<int>(pc - static_cast<long long>(b) * nn);
-    const int i_ = ij / n, j_ = ij - i_ * n;
-    const bool pair_ok = flags[b * n + i_] != 0 && flags[b * n + j_] != 0;
-    const float sc = in_scale ? in_scale[b] : 1.f;
-    // adjacency planes [self-cond adj (c_e), c_in * adj (c_e)]: lane `sub` fetches planes sub and sub + 8
-    float mine[2];
+  for (int i = threadIdx.x; i < E; i += kRowThreads) { sBias[i] = bias[i]; sGam[i] = gamma[i]; sBet[i] = beta[i]; }
+  __syncthreads();
+  const int nn = n * n;
+  const long long groups = (pixels + 15) / 16;
+  const long long warps_total = static_cast<long long>(gridDim.x) * (kRowThreads / 32);
+  // A-fragment inputs of a step: planes [self-cond adj (c_e), c_in * adj (c_e)] at k = 2t, 2t + 1, 2t + 8, 2t + 9 of
+  // fragment rows g and g + 8.  They are the only HBM reads of the kernel and are fetched ONE STEP AHEAD (the warp
+  // otherwise sits on this round trip with nothing else to do: 46 % long-scoreboard stalls in the ncu profile).
+  // (raw values only: the first USE of a loaded register stalls the in-order warp, so c_in is applied a step later)
+  auto load_planes = [&](long long grp, float (&pv)[8], float (&scl)[2]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int ch = sub + 8 * h;
-      float a = 0.f;
-      if (ch < planes) {
-        if (self_cond && ch < c_e) {
-          if (sc_adj) a = sc_adj[(static_cast<size_t>(b) * c_e + ch) * nn + ij];
-        } else {
-          const int c = self_cond ? ch - c_e : ch;
-          a = __fmul_rn(sc, adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+    for (int r = 0; r < 2; ++r) {
+      const long long px = grp * 16 + g + 8 * r;
+      const long long pc = px < pixels ? px : pixels - 1;
+      const int b_ = static_cast<int>(pc / nn);
+      const int ij_ = static_cast<int>(pc - static_cast<long long>(b_) * nn);
+      scl[r] = in_scale ? in_scale[b_] : 1.f;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int k = 2 * t + (h & 1) + 8 * (h >> 1);
+        float a = 0.f;
+        if (k < planes) {
+          if (self_cond && k < c_e) {
+            if (sc_adj) a = sc_adj[(static_cast<size_t>(b_) * c_e + k) * nn + ij_];
+          } else {
+            a = adj[(static_cast<size_t>(b_) * c_e + (self_cond ? k - c_e : k)) * nn + ij_];
+          }
+        }
+        pv[r * 4 + h] = a;
+      }
+    }
+  };
+  const long long grp0 = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
+  float pv_next[8], sc_next[2];
+  if (grp0 < groups) load_planes(grp0, pv_next, sc_next);
+  for (long long grp = grp0; grp < groups; grp += warps_total) {
+    float pv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // c_in * adj for the adjacency planes (self-conditioning planes are not scaled)
+      const int kk = 2 * t + (k & 1) + 8 * ((k >> 1) & 1);
+      pv[k] = (self_cond && kk < c_e) ? pv_next[k] : __fmul_rn(sc_next[k >> 2], pv_next[k]);
+    }
+    if (grp + warps_total < groups) load_planes(grp + warps_total, pv_next, sc_next);
+    // the two pixels (fragment rows g and g + 8) of this thread
+    long long pix[2];
+    int bb[2], ij[2];
+    bool valid[2], pair_ok[2];
+    const float *rrow[2], *rcol[2], *fs[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      pix[r] = grp * 16 + g + 8 * r;
+      valid[r] = pix[r] < pixels;
+      const long long pc = valid[r] ? pix[r] : pixels - 1;
+      bb[r] = static_cast<int>(pc / nn);
+      ij[r] = static_cast<int>(pc - static_cast<long long>(bb[r]) * nn);
+      const int i_ = ij[r] / n, j_ = ij[r] - i_ * n;
+      pair_ok[r] = flags[bb[r] * n + i_] != 0 && flags[bb[r] * n + j_] != 0;
+      rrow[r] = rc + (static_cast<size_t>(bb[r]) * n + i_) * 2 * E;
+      rcol[r] = rc + (static_cast<size_t>(bb[r]) * n + j_) * 2 * E + E;
+      fs[r] = film + static_cast<size_t>(cond_uniform ? 0 : bb[r]) * film_ld;  // scale[E] then shift[E]
+    }
+    uint32_t a_hi[4], a_lo[4];   // A fragment registers: (row g, k lo) (row g + 8, k lo) (row g, k hi) (row g + 8, k hi)
+    split2(pv[0], pv[1], a_hi[0], a_lo[0]);
+    split2(pv[4], pv[5], a_hi[1], a_lo[1]);
+    split2(pv[2], pv[3], a_hi[2], a_lo[2]);
+    split2(pv[6], pv[7], a_hi[3], a_lo[3]);
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float2 bv = *reinterpret_cast<const float2*>(&sBias[nt * 8 + 2 * t]);
+      acc[nt][0] = bv.x; acc[nt][1] = bv.y; acc[nt][2] = bv.x; acc[nt][3] = bv.y;
+      const uint4 f = sBf[nt][lane];
+      const uint32_t b_hi[2] = {f.x, f.y}, b_lo[2] = {f.z, f.w};
+      mma_m16n8k16_bf16(acc[nt], a_lo, b_hi);
+      mma_m16n8k16_bf16(acc[nt], a_hi, b_lo);
+      mma_m16n8k16_bf16(acc[nt], a_hi, b_hi);
+    }
+    // ---- epilogue on packed fp32 pairs: pr[nt][r] = channels (8 nt + 2t, + 1) of fragment row r
+    f32x2 pr[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      pr[nt][0] = f2_pack(acc[nt][0], acc[nt][1]);
+      pr[nt][1] = f2_pack(acc[nt][2], acc[nt][3]);
+    }
+    // node planes (zeroed on padded rows / columns, mask_adjs at :800) and the LayerNorm statistics
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (pair_ok[r]) {
+        const float2* p1 = reinterpret_cast<const float2*>(rrow[r] + 2 * t);
+        const float2* p2 = reinterpret_cast<const float2*>(rcol[r] + 2 * t);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const float2 r1 = __ldg(p1 + 4 * nt), r2 = __ldg(p2 + 4 * nt);
+          pr[nt][r] = f2_add(pr[nt][r], f2_add(f2_pack(r1.x, r1.y), f2_pack(r2.x, r2.y)));
         }
       }
-      mine[h] = a;
+      f32x2 s2 = pr[0][r];
+#pragma unroll
+      for (int nt = 1; nt < NT; ++nt) s2 = f2_add(s2, pr[nt][r]);
+      float sa, sb;
+      f2_unpack(s2, sa, sb);
+      float sm = sa + sb;
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      mean[r] = sm * (1.0f / E);
+      const f32x2 nm = f2_splat(-mean[r]);
+      f32x2 q2 = f2_splat(0.f);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        pr[nt][r] = f2_add(pr[nt][r], nm);
+        q2 = f2_fma(pr[nt][r], pr[nt][r], q2);
+      }
+      f2_unpack(q2, sa, sb);
+      float qq = sa + sb;
+      qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+      qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+      rstd[r] = rsqrtf(qq * (1.0f / E) + kLnEps);
     }
-    float4 v[3] = {cb[0], cb[1], cb[2]};
 #pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-      const float a = __shfl_sync(0xffffffffu, mine[ch >> 3], grp_base + (ch & 7));
-      if (ch < planes) {  // warp-uniform
+    for (int r = 0; r < 2; ++r) {
+      const f32x2 rs = f2_splat(rstd[r]);
+      const float2* psc = reinterpret_cast<const float2*>(fs[r] + 2 * t);
+      const float2* psh = reinterpret_cast<const float2*>(fs[r] + E + 2 * t);
+      float2* orow = reinterpret_cast<float2*>(x0 + pix[r] * E + 2 * t);
+      if (valid[r]) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(&sW[ch * E + (sub + 8 * i) * 4]);
-          v[i].x = fmaf(w.x, a, v[i].x); v[i].y = fmaf(w.y, a, v[i].y);
-          v[i].z = fmaf(w.z, a, v[i].z); v[i].w = fmaf(w.w, a, v[i].w);
+        for (int nt = 0; nt < NT; ++nt) {
+          const float2 gg = *reinterpret_cast<const float2*>(&sGam[nt * 8 + 2 * t]);
+          const float2 be = *reinterpret_cast<const float2*>(&sBet[nt * 8 + 2 * t]);
+          const float2 fsc = __ldg(psc + 4 * nt), fsh = __ldg(psh + 4 * nt);
+          // silu(LN(v) (1 + scale) + shift),  silu(x) = x / (1 + 2^(-x log2 e))
+          const f32x2 y = f2_fma(f2_mul(pr[nt][r], rs), f2_pack(gg.x, gg.y), f2_pack(be.x, be.y));
+          const f32x2 z = f2_fma(y, f2_add(f2_pack(fsc.x, fsc.y), f2_splat(1.f)), f2_pack(fsh.x, fsh.y));
+          float z0, z1, u0, u1;
+          f2_unpack(z, z0, z1);
+          f2_unpack(f2_mul(z, f2_splat(-1.4426950408889634f)), u0, u1);
+          const f32x2 den = f2_add(f2_pack(ex2_approx(u0), ex2_approx(u1)), f2_splat(1.f));
+          float d0, d1;
+          f2_unpack(den, d0, d1);
+          orow[4 * nt] = make_float2(z0 * rcp_approx(d0), z1 * rcp_approx(d1));
         }
       }
-    }
-    if (pair_ok) {  // node planes are zeroed on padded rows / columns (mask_adjs at :800)
-      const float* rrow = rc + (static_cast<size_t>(b) * n + i_) * 2 * E;
-      const float* rcol = rc + (static_cast<size_t>(b) * n + j_) * 2 * E + E;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int e = (sub + 8 * i) * 4;
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rrow + e));
-        const float4 r2 = __ldg(reinterpret_cast<const float4*>(rcol + e));
-        v[i].x += r1.x + r2.x; v[i].y += r1.y + r2.y; v[i].z += r1.z + r2.z; v[i].w += r1.w + r2.w;
-      }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = group_sum<8>(s) * (1.0f / E);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-    const float rstd = rsqrtf(group_sum<8>(q) * (1.0f / E) + kLnEps);
-    const float* fs = film + static_cast<size_t>(cond_uniform ? 0 : b) * film_ld;  // scale[E] then shift[E]
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int e = (sub + 8 * i) * 4;
-      const float4 fsc = __ldg(reinterpret_cast<const float4*>(fs + e));
-      const float4 fsh = __ldg(reinterpret_cast<const float4*>(fs + E + e));
-      float4 o;
-      o.x = silu_f(fmaf(fmaf(v[i].x * rstd, cg[i].x, cbe[i].x), fsc.x + 1.f, fsh.x));
-      o.y = silu_f(fmaf(fmaf(v[i].y * rstd, cg[i].y, cbe[i].y), fsc.y + 1.f, fsh.y));
-      o.z = silu_f(fmaf(fmaf(v[i].z * rstd, cg[i].z, cbe[i].z), fsc.z + 1.f, fsh.z));
-      o.w = silu_f(fmaf(fmaf(v[i].w * rstd, cg[i].w, cbe[i].w), fsc.w + 1.f, fsh.w));
-      if (valid) *reinterpret_cast<float4*>(x0 + pix * E + e) = o;
     }
   }
 }
@@ -734,8 +807,8 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
   DSG_REQUIRE(embed == 96, "patch_embed: embed_dim %d (only 96 is built)", embed);
   const long long pixels = static_cast<long long>(batch) * n * n;
   DSG_REQUIRE((self_cond ? 2 : 1) * c_e <= 16, "patch_embed: %d adjacency planes (max 16)", (self_cond ? 2 : 1) * c_e);
-  long long blocks = (pixels / 4 + 7) / 8;  // one warp per 4 pixels per step
-  if (blocks > 148 * 64) blocks = 148 * 64;
+  long long blocks = (pixels / 16 + 7) / 8;  // one warp per 16 pixels per step
+  if (blocks > 148 * 16) blocks = 148 * 16;
   patch_embed_kernel<<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj,
                                                                            bias, gamma, beta, film + film_off, film_ld,
                                                                            cond_uniform, x0, pixels, n, c_e, self_cond);
