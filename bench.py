@@ -41,6 +41,36 @@ EXPECTED_PASSES_256 = 766.5  # 511 precond calls + E[#coins < 0.5] (model/precon
 GFLOP_PER_PASS = {"vg": 13.30, "coco": 7.36, "n64w16": 14.66}  # GEMM + bmm + conv, per sample
 
 
+def ncu_traffic_per_launch(pattern: str):
+    """Average dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels matching `pattern`, over the
+    last denoiser pass of the committed ncu launch list (profiles/, same one-pass command), or None."""
+    import csv
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_launches_pass_ncu.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    try:
+        hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    except StopIteration:
+        return None
+    hdr = rows[hi]
+    col = {h: i for i, h in enumerate(hdr)}
+    per = {}
+    for r in rows[hi + 1:]:
+        if len(r) != len(hdr):
+            continue
+        e = per.setdefault(int(r[col["ID"]]), {"name": r[col["Kernel Name"]], "b": 0.0})
+        if r[col["Metric Name"]] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e["b"] += float(r[col["Metric Value"]].replace(",", ""))
+    ids = sorted(per)
+    starts = [i for i in ids if "sinusoid_kernel" in per[i]["name"]]  # first kernel of a denoiser pass
+    if not starts:
+        return None
+    sel = [per[i]["b"] for i in ids if i >= starts[-1] and re.search(pattern, per[i]["name"])]
+    return sum(sel) / len(sel) if sel else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -258,10 +288,13 @@ def run_native(args, cfg, rank, local_rank, world):
     g = {k: g0.get(k, 0) + g1.get(k, 0) for k in ("ms", "flops", "bytes", "launches")}  # every tcgen05 launch
     total_prof_ms = sum(c["ms"] for c in prof.values()) or 1.0
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> + fused_mlp_kernel<C> (tcgen05/TMEM/TMA: every nn.Linear of the denoiser)",
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI> + block_tail_kernel<96> + fused_mlp_kernel<192> (tcgen05/TMEM/TMA: every nn.Linear of the denoiser)",
                 "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": gemm_tflops / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "traffic": None, "launches_timed": g["launches"],
+                "traffic": ncu_traffic_per_launch(r"gemm_kernel|block_tail_kernel|fused_mlp_kernel"),
+                "traffic_note": "bytes per launch, mean over the tcgen05 launches of one denoiser pass (ncu dram__bytes_read + write, profiles/r1_launches_pass_ncu.csv)",
+                "algorithmic_bytes_per_launch": g["bytes"] / g["launches"] if g["launches"] else None,
+                "launches_timed": g["launches"],
                 "avg_launch_ms": g["ms"] / g["launches"] if g["launches"] else None,
                 "share_of_profiled_time": g["ms"] / total_prof_ms,
                 "how": f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region"}
@@ -276,7 +309,7 @@ def run_native(args, cfg, rank, local_rank, world):
     if edm and edm["ms"]:
         gbs = edm["bytes"] / (edm["ms"] * 1e-3) / 1e9
         edm_roof = {"bound": "hbm", "kernel": "edm_kernel<MODE> (fused pre / post step)", "achieved": gbs, "peak": pk["hbm"],
-                    "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None}
+                    "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": ncu_traffic_per_launch(r"edm_kernel")}
     flops_step = passes * GFLOP_PER_PASS.get(args.config, 0.0) * 1e9 * B
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -405,30 +405,44 @@ __global__ void precond_coef_kernel(const float* __restrict__ sigmas, int sigma_
 // rc[b, i, 0:E]  = sum_c W[:, row-plane c] * nodecat[b, i, c]      nodecat = [self-cond node, c_in * node]
 // rc[b, i, E:2E] = sum_c W[:, col-plane c] * nodecat[b, i, c]
 // w_rc is [2, 2 c_n(self_cond) or c_n, E] (input-channel major so that lanes read consecutive e).
+// One thread per output column e2 keeps its <= 32 weights in registers and walks kNodeRows rows (b, i); the rows' node
+// vectors are staged in shared memory.  (One CTA per row re-read the 18 KB weight table 32768 times: 87 us.)
+constexpr int kNodeRows = 16;
 __global__ void node_proj_kernel(const float* __restrict__ node, const float* __restrict__ sc_node,
                                  const float* __restrict__ in_scale, const float* __restrict__ w_rc,
                                  float* __restrict__ rc, int batch, int n, int c_n, int self_cond, int embed) {
-  const int bi = blockIdx.x;  // (b, i)
-  const int b = bi / n;
+  __shared__ float sv[kNodeRows][32];
+  const int cin = self_cond ? 2 * c_n : c_n;  // <= 32 (checked by the launcher)
+  const long long rows = static_cast<long long>(batch) * n;
+  const long long row0 = static_cast<long long>(blockIdx.x) * kNodeRows;
+  for (int idx = threadIdx.x; idx < kNodeRows * cin; idx += blockDim.x) {
+    const int r = idx / cin, ch = idx - r * cin;
+    const long long bi = row0 + r;
+    float v = 0.f;
+    if (bi < rows) {
+      if (self_cond && ch < c_n) {
+        v = sc_node ? sc_node[bi * c_n + ch] : 0.f;
+      } else {
+        const float sc = in_scale ? in_scale[bi / n] : 1.f;
+        v = __fmul_rn(sc, node[bi * c_n + (self_cond ? ch - c_n : ch)]);
+      }
+    }
+    sv[r][ch] = v;
+  }
+  __syncthreads();
   const int e2 = threadIdx.x;  // 0 .. 2E-1
   if (e2 >= 2 * embed) return;
   const int which = e2 / embed, e = e2 - which * embed;
-  const int cin = self_cond ? 2 * c_n : c_n;
-  const float sc = in_scale ? in_scale[b] : 1.f;
   const float* w = w_rc + static_cast<size_t>(which) * cin * embed + e;
-  float acc = 0.f;
-  int ch = 0;
-  if (self_cond) {
-    for (int c = 0; c < c_n; ++c, ++ch) {
-      const float v = sc_node ? sc_node[static_cast<size_t>(bi) * c_n + c] : 0.f;
-      acc = fmaf(w[ch * embed], v, acc);
-    }
+  float wr[32];
+#pragma unroll
+  for (int ch = 0; ch < 32; ++ch) wr[ch] = ch < cin ? w[ch * embed] : 0.f;
+  for (int r = 0; r < kNodeRows && row0 + r < rows; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 32; ++ch) acc = fmaf(wr[ch], sv[r][ch], acc);  // same order as the reference's channel cat
+    rc[(row0 + r) * 2 * embed + e2] = acc;
   }
-  for (int c = 0; c < c_n; ++c, ++ch) {
-    const float v = __fmul_rn(sc, node[static_cast<size_t>(bi) * c_n + c]);
-    acc = fmaf(w[ch * embed], v, acc);
-  }
-  rc[static_cast<size_t>(bi) * 2 * embed + e2] = acc;
 }
 
 // Sixteen consecutive pixels (b, i, j) per warp step, on the legacy warp MMA (m16n8k16 bf16 -> fp32):
@@ -794,8 +808,10 @@ int launch_precond_coef(const float* sigmas, int sigma_stride, float* coef, int 
 
 int launch_node_proj(const float* node, const float* sc_node, const float* in_scale, const float* w_rc, float* rc,
                      int batch, int n, int c_n, int self_cond, int embed, cudaStream_t st) {
-  DSG_REQUIRE(2 * embed <= 1024, "node_proj: embed %d", embed);
-  node_proj_kernel<<<batch * n, 2 * embed, 0, st>>>(node, sc_node, in_scale, w_rc, rc, batch, n, c_n, self_cond, embed);
+  DSG_REQUIRE(2 * embed <= 1024 && (self_cond ? 2 : 1) * c_n <= 32, "node_proj: embed %d, c_n %d", embed, c_n);
+  const long long rows = static_cast<long long>(batch) * n;
+  node_proj_kernel<<<static_cast<unsigned>((rows + kNodeRows - 1) / kNodeRows), 2 * embed, 0, st>>>(
+      node, sc_node, in_scale, w_rc, rc, batch, n, c_n, self_cond, embed);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
