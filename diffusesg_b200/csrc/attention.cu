@@ -238,11 +238,25 @@ DSG_DEVICE void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
 
 // Window gw = b * nW + wy * nwx + wx of the (rolled) grid: row of its token (0, 0) before wrapping, as (b, y0, x0).
 struct WinOrigin { int b_row0, y0, x0; };
-DSG_DEVICE WinOrigin window_origin(int gw, int res, int shift, int nW, int nwx) {
-  const int b = gw / nW, win = gw - b * nW;
-  const int wy = win / nwx, wx = win - wy * nwx;
-  return WinOrigin{b * res * res, wy * 8 + shift, wx * 8 + shift};
-}
+// (b, wy, wx) of a window, stepped to the next window without the run-time divisions of gw / nW, win / nwx, gw % nW
+// (two cursors x five divisions were ~200 of the ~640 instructions a warp spends per window)
+struct WinCursor {
+  int b, wy, wx, win;
+  DSG_DEVICE void init(int gw, int nW, int nwx) {
+    b = gw / nW;
+    win = gw - b * nW;
+    wy = win / nwx;
+    wx = win - wy * nwx;
+  }
+  DSG_DEVICE void next(int nW, int nwx) {
+    ++win;
+    if (++wx == nwx) {
+      wx = 0;
+      if (++wy == nwx) { wy = 0; win = 0; ++b; }
+    }
+  }
+  DSG_DEVICE WinOrigin origin(int res, int shift) const { return WinOrigin{b * res * res, wy * 8 + shift, wx * 8 + shift}; }
+};
 // token t = ty * 8 + tx of the window -> row of the un-rolled [B*res*res] token matrix (cyclic shift undone)
 DSG_DEVICE int window_token_row(const WinOrigin& o, int t, int res) {
   int oy = o.y0 + (t >> 3); if (oy >= res) oy -= res;
@@ -267,8 +281,12 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
   const int r0 = warp * 16 + g, r1 = r0 + 8;
 
   // two threads per token: thread `tid` fetches the 32-byte half `tid & 1` of the token's q, k and v head slices
-  auto issue_loads = [&](int gw, int buf) {
-    const WinOrigin org = window_origin(gw, res, shift, nW, nwx);
+  WinCursor cur_load, cur;
+  cur_load.init(w_begin, nW, nwx);
+  cur = cur_load;
+  auto issue_loads = [&](int buf) {  // window of the load cursor, which then advances
+    const WinOrigin org = cur_load.origin(res, shift);
+    cur_load.next(nW, nwx);
     const int t = tid >> 1, half = (tid & 1) * 16;
     const bf16* src = qkv + static_cast<size_t>(window_token_row(org, t, res)) * (3 * C) + h * HD + half;
 #pragma unroll
@@ -279,7 +297,7 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
     cp_async_commit();
   };
 
-  issue_loads(w_begin, 0);
+  issue_loads(0);
 
   // relative-position bias of this head, in score-fragment layout
   float bia[8][4];
@@ -296,7 +314,7 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
   for (int gw = w_begin; gw < w_end; ++gw) {
     const int buf = (gw - w_begin) & 1;
     if (gw + 1 < w_end) {
-      issue_loads(gw + 1, buf ^ 1);
+      issue_loads(buf ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -322,7 +340,7 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
       mma_m16n8k16_bf16(s[nt], qa[1], reinterpret_cast<const uint32_t(&)[2]>(kb[2]));
     }
     if (mask != nullptr) {
-      const float* mw = mask + static_cast<size_t>(gw % nW) * T * T;
+      const float* mw = mask + static_cast<size_t>(cur.win) * T * T;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const float2 a = __ldg(reinterpret_cast<const float2*>(mw + r0 * T + nt * 8 + 2 * t4));
@@ -376,7 +394,8 @@ window_attention64_kernel(const bf16* __restrict__ qkv, const float* __restrict_
       }
     }
     const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
-    const WinOrigin org_out = window_origin(gw, res, shift, nW, nwx);
+    const WinOrigin org_out = cur.origin(res, shift);
+    cur.next(nW, nwx);
     // stage the 16 x 32 output slab of this warp in its own (consumed) q rows, then one 64-byte store per token
     __syncwarp();
 #pragma unroll
