@@ -277,6 +277,68 @@ DSG_DEVICE void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a 2-cluster issue ONE M = 256 MMA; each holds its 128 rows of A, half of B
+// (N / 2 rows) and the accumulator rows of its own 128 rows.  Only the leader (cluster rank 0) issues; commits are
+// multicast to the barrier at the same shared-memory offset in both CTAs.  (tools/microbench/mma2_bench.cu)
+// ------------------------------------------------------------------------------------------------
+DSG_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DSG_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of this CTA) in the CTA of rank `rank`
+DSG_DEVICE uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+DSG_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <uint32_t kCols>
+DSG_DEVICE void tmem_alloc_pair(uint32_t* smem_result) {  // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+DSG_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_pair(int n) {  // M = 256 across the pair
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((256u >> 4) << 24);
+}
+DSG_DEVICE void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DSG_DEVICE void umma_commit_pair(uint64_t* bar) {  // arrives in BOTH CTAs once the issued MMAs have completed
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion is signalled on a barrier of the pair's leader
+DSG_DEVICE void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar_cluster_addr, int c_inner,
+                                 int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar_cluster_addr), "r"(c_inner),
+      "r"(c_outer)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
 DSG_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

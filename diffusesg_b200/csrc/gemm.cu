@@ -28,10 +28,12 @@ __host__ __device__ constexpr int epi_groups(int epi) { return (epi == EPI_RES_F
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * epi_groups(epi); }
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
-template <int BN>
+// PAIR: two CTAs of a 2-cluster share one 256 x BN tile (cta_group::2).  Each loads its 128 rows of A and HALF of the
+// B tile, so a stage is 28 KB instead of 40 KB (BN = 192): 30 % less L2 -> SM traffic per flop and a deeper ring.
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int kStages = (BN == 192) ? 4 : 5;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int kStages = PAIR ? ((BN == 192) ? 5 : 7) : ((BN == 192) ? 4 : 5);
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int ACC_STRIDE = (BN == 192) ? 256 : 128;  // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;       // 512 / 256
@@ -41,12 +43,14 @@ struct Cfg {
 };
 
 static_assert(Cfg<96>::SMEM_BYTES <= 227 * 1024 && Cfg<192>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(Cfg<96, true>::SMEM_BYTES <= 227 * 1024 && Cfg<192, true>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
+  static_assert(!(PAIR && EPI == EPI_ADJ_HEAD), "the adj-head epilogue is single-CTA");
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   // round up to 1024 bytes (128-byte swizzle atoms) without casting through an integer, so that the compiler
@@ -72,7 +76,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kEpiWarps = 4 * epi_groups(EPI);
   constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
-  const int num_m = (p.M + BM - 1) / BM;
+  // tile = (block of 128 rows, or of 256 rows shared by a CTA pair) x (BN columns)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int cta = PAIR ? (blockIdx.x >> 1) : blockIdx.x;  // tile-loop index of this CTA (pair)
+  const int ncta = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int num_m = (p.M + (PAIR ? 2 * BM : BM) - 1) / (PAIR ? 2 * BM : BM);
   const int num_n = p.N / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -87,17 +95,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 2 * epi_groups(EPI));  // one arrival per epilogue warp reading accumulator a
+      // one arrival per epilogue warp reading accumulator a (of both CTAs of a pair: the leader's MMA warp waits)
+      mbar_init(&tempty_bar[a], (PAIR ? 2 : 1) * 2 * epi_groups(EPI));
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   if (EPI == EPI_ADJ_HEAD) {
     for (int i = threadIdx.x; i < 96 * 8; i += gemm_threads(EPI)) s_w2t[i] = p.w2t[i];
     if (threadIdx.x < 8) s_b2[threadIdx.x] = p.b2[threadIdx.x];
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before any multicast commit / remote arrive reaches them
   tcgen05_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
@@ -106,25 +119,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < num_tiles; tile += ncta) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-          tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n_blk * BN);
+          if (PAIR) {
+            // this CTA's 128 rows of A and its half of the B tile; both CTAs' bytes complete on the LEADER's barrier
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(&full_bar[s], 0);
+            tma_load_2d_pair(sA + s * A_STAGE_BYTES, &tmA, lbar, kb * BK, (m_blk * 2 + static_cast<int>(rank)) * BM);
+            tma_load_2d_pair(sB + s * C::B_STAGE_BYTES, &tmW, lbar, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+            tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n_blk * BN);
+          }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+  } else if (warp == kMmaWarp && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the leader of a pair)
+    constexpr uint32_t idesc = PAIR ? umma_idesc_bf16_pair(BN) : umma_idesc_bf16(BN);
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < num_tiles; tile += ncta) {
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
@@ -137,10 +158,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int ksteps = min(BK, p.K - kb * BK) / 16;
           for (int k = 0; k < ksteps; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[s]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          if (PAIR) {
+            umma_commit_pair(&empty_bar[s]);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[s]);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1; }
@@ -148,6 +175,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
+  } else if (warp == kMmaWarp) {
+    // the peer's MMA warp only owns its half of the tensor-memory allocation
   } else {
     // ------------------------------------------------------------------ epilogue groups
     constexpr int kGroups = epi_groups(EPI);
@@ -166,8 +195,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float* sBiasA = sBias + acc * BN;
     uint32_t acc_ph = 0;
     int chunk_no = 0;  // running count of staged chunks -> staging buffer parity
-    for (int tile = blockIdx.x + acc * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    // accumulator hand-back: the leader's MMA warp counts the epilogue warps of both CTAs of a pair
+    const uint32_t tempty_addr = PAIR ? mapa_u32(&tempty_bar[acc], 0) : 0u;
+    auto release_acc = [&]() {
+      if (PAIR) mbar_arrive_cluster(tempty_addr);
+      else mbar_arrive(&tempty_bar[acc]);
+    };
+    for (int tile = cta + acc * ncta; tile < num_tiles; tile += 2 * ncta) {
+      const int m_blk = PAIR ? (tile / num_n) * 2 + static_cast<int>(rank) : tile / num_n;  // this CTA's 128-row block
+      const int n_blk = tile % num_n;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
       if (EPI == EPI_ADJ_HEAD) {
         // columns [48 half, 48 half + 48) of the hidden layer; partial sums of the 96 -> c_e linear are combined
@@ -201,7 +237,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) release_acc();
         if (half == 1) {
           *reinterpret_cast<float4*>(&sPart[r_in_tile * 8]) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(&sPart[r_in_tile * 8 + 4]) = make_float4(y[4], y[5], y[6], y[7]);
@@ -259,7 +295,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (ci + kHalves >= kChunks) {  // this group's last chunk: its warps are done with the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) release_acc();
           }
           const int col = n_blk * BN + c0;
           float v[32];
@@ -320,8 +356,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may retire while the other can still reach its shared / tensor memory
   tcgen05_fence_after();
-  if (warp == kMmaWarp) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -357,13 +397,43 @@ int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* 
              cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN, EPI><<<grid, gemm_threads(EPI), Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
+  gemm_kernel<BN, EPI, false><<<grid, gemm_threads(EPI), Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+// CTA-pair version: tmW must be the HALF-tile descriptor (box 64 x BN / 2)
+template <int BN, int EPI>
+int launch_pair(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, const GemmParams& p,
+                cudaStream_t st) {
+  using K = Cfg<BN, true>;
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        K::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(gemm_threads(EPI));
+  cfg.dynamicSmemBytes = K::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DSG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, true>, *tmA, *tmW, *tmO, p));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -412,7 +482,7 @@ int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
 int gemm_block_n(int N) { return (N % 192 == 0) ? 192 : 96; }
 
 int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,
-                cudaStream_t st) {
+                cudaStream_t st, bool pair) {
   DSG_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.N % 96 == 0 && p.K % 16 == 0,
               "gemm: unsupported shape M=%d N=%d K=%d (N %% 96 == 0 and K %% 16 == 0 required)", p.M, p.N, p.K);
   DSG_REQUIRE(p.out != nullptr, "gemm: null output");
@@ -426,6 +496,23 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
   DSG_REQUIRE(tmO != nullptr && p.ldo == p.N, "gemm: output tensor map missing or ldo != N");
   if (epi == EPI_RES_F32)
     DSG_REQUIRE(p.res == p.out, "gemm: the residual epilogue accumulates in place (res must alias out)");
+  if (pair) {  // CTA pairs: tmW is the half-tile descriptor
+    if (bn == 192) {
+      switch (epi) {
+        case EPI_BF16: return launch_pair<192, EPI_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_GELU_BF16: return launch_pair<192, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_RES_F32: return launch_pair<192, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+        case EPI_F32: return launch_pair<192, EPI_F32>(tmA, tmW, tmO, p, st);
+      }
+    } else {
+      switch (epi) {
+        case EPI_BF16: return launch_pair<96, EPI_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_GELU_BF16: return launch_pair<96, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_RES_F32: return launch_pair<96, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+        case EPI_F32: return launch_pair<96, EPI_F32>(tmA, tmW, tmO, p, st);
+      }
+    }
+  }
   if (bn == 192) {
     switch (epi) {
       case EPI_BF16: return launch_t<192, EPI_BF16>(tmA, tmW, tmO, p, st);

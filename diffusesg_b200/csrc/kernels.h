@@ -54,8 +54,9 @@ int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
 // box_rows of the W descriptor must equal gemm_block_n(N).
 int gemm_block_n(int N);
 // EPI_RES_F32 accumulates in place with a TMA reduce-add: p.res must alias p.out.
+// pair = true runs CTA pairs (cta_group::2, 256-row tiles): tmW must then have box_rows = gemm_block_n(N) / 2.
 int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,
-                cudaStream_t st);
+                cudaStream_t st, bool pair = false);
 
 // ---------------------------------------------------------------------------------------------
 // fused MLP:  x += fc2(gelu(fc1(y))), y = LN(x) in bf16                 (mlp.cu)

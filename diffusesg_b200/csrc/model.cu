@@ -93,7 +93,8 @@ struct TensorSpec {
 struct Weight {       // packed bf16 [N, K] + its TMA descriptor
   size_t offset = 0;  // into the arena
   int N = 0, K = 0;
-  CUtensorMap tmap;
+  CUtensorMap tmap;       // box 64 x gemm_block_n(N)
+  CUtensorMap tmap_half;  // box 64 x gemm_block_n(N) / 2: the B half each CTA of a pair loads
 };
 
 struct Block {
@@ -136,6 +137,7 @@ struct dsg_model {
   bool finalized = false;
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
+  bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -335,6 +337,7 @@ int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st
                 float scale = 1.f) {
   int rc = launch_pack_bf16(m->f32(key), m->at<bf16>(w.offset), static_cast<int64_t>(w.N) * w.K, n_scaled, scale, st);
   if (rc) return rc;
+  if (int rc2 = make_tmap_bf16(&w.tmap_half, m->arena + w.offset, w.N, w.K, gemm_block_n(w.N) / 2)) return rc2;
   return make_tmap_bf16(&w.tmap, m->arena + w.offset, w.N, w.K, gemm_block_n(w.N));
 }
 
@@ -405,7 +408,10 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   ProfScope ps(g_prof_pass, PC_GEMM, 2.0 * mn * W.K,
                static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
                    (epi == EPI_RES_F32 ? mn * 4 : 0), st, label, rows, W.K);
-  return launch_gemm(&it->second, &W.tmap, tmo, epi, p, st);
+  // CTA pairs pay off where the MMA stream is long (measured: +10..18 % for K >= 768, -5..-30 % for the HBM-bound
+  // K <= 384 shapes, whose tiles finish in a few hundred cycles and gain nothing from halved B traffic)
+  const bool pair = m->use_pair && epi != EPI_ADJ_HEAD && rows >= 256 && W.K >= 768;
+  return launch_gemm(&it->second, pair ? &W.tmap_half : &W.tmap, tmo, epi, p, st, pair);
 }
 
 #define DSG_TRY(expr)        \
@@ -497,6 +503,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   m->use_fused_mlp = !(no_fuse != nullptr && no_fuse[0] == '1');
   const char* no_tail = getenv("DSG_NO_TAIL");
   m->use_tail = !(no_tail != nullptr && no_tail[0] == '1');
+  const char* no_pair = getenv("DSG_NO_PAIR");
+  m->use_pair = !(no_pair != nullptr && no_pair[0] == '1');
   const int rc = build(m);
   if (rc) { delete m; return rc; }
   *out = m;
@@ -860,7 +868,9 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");
   CUtensorMap ta, tw, to;
   DSG_TRY(make_tmap_bf16(&ta, a, M, K, 128));
-  DSG_TRY(make_tmap_bf16(&tw, w, N, K, gemm_block_n(N)));
+  const char* no_pair = getenv("DSG_NO_PAIR");
+  const bool pair = M >= 256 && K >= 768 && !(no_pair != nullptr && no_pair[0] == '1');  // the denoiser schedule's rule
+  DSG_TRY(make_tmap_bf16(&tw, w, N, K, pair ? gemm_block_n(N) / 2 : gemm_block_n(N)));
   DSG_TRY(make_tmap_out(&to, out, M, N, epi));
   if (epi == EPI_RES_F32) {
     DSG_REQUIRE(res != nullptr, "gemm_bf16: residual epilogue without residual");
@@ -872,7 +882,7 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N;
-  return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream), pair);
 }
 
 int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,

@@ -23,6 +23,8 @@ GEMM_SHAPES = [
     # (M, N, K): tails in M (TMA zero fill + predicated stores), K = 96 (half-empty second k-block), both tile widths
     (128, 96, 64), (128, 192, 64), (256, 96, 96), (300, 288, 96), (1000, 384, 192), (4096, 1152, 384),
     (777, 768, 3072), (512, 1536, 1536), (48, 96, 384), (20000, 96, 96), (33000, 576, 192),
+    # CTA-pair path (cta_group::2, K >= 768, M >= 256): row tails inside the second CTA's half, both tile widths
+    (256, 96, 768), (300, 384, 768), (3000, 2304, 768), (1111, 96, 1536),
 ]
 
 
