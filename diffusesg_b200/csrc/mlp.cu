@@ -7,10 +7,16 @@
 // The hidden dimension is cut into chunks of HC columns that form ONE stream across the tiles of a persistent CTA
 // (global chunk index g): fc1 of chunk g + 2 is issued right after fc2 of chunk g, also across a tile boundary, so
 // the tensor pipe never waits for the workers and the workers never wait for the tensor pipe.
-//   TMA warp           y tile [128 x C] (once per tile) and the W1 / W2 k-blocks of every chunk (4-stage ring)
-//   MMA warp           acc1[g&1] = y . W1[chunk]^T  (TMEM, double buffered);  acc2 += H[chunk] . W2[:, chunk]^T
-//   worker warps (16)  tcgen05.ld acc1 -> + b1 -> exact-erf GELU -> bf16 -> 128-byte-swizzled K-major smem H chunk;
+//   TMA warp           y tile [128 x C] (once per tile) and the W1 / W2 k-blocks of every chunk (5-stage ring)
+//   MMA warp           acc1[g&1] = y . W1[chunk]^T  (SS mode, TMEM accumulators double buffered);
+//                      acc2 += H[chunk] . W2[:, chunk]^T  (TS mode: the A operand H is read from tensor memory)
+//   worker warps (16)  tcgen05.ld acc1 -> + b1 -> erf GELU -> bf16 pairs -> tcgen05.st IN PLACE over acc1 (the 16
+//                      hidden columns of K step k become the 8 packed columns [16k, 16k + 8), same warp);
 //                      after the last chunk of a tile: tcgen05.ld acc2 -> + b2 -> fp32 staging -> TMA reduce-add into x
+// fc1 of chunk g + 2 reuses the buffer of chunk g and is issued after fc2 of chunk g by the same thread; the tensor
+// pipe executes in issue order, so the chunk ring needs no "empty" barriers.  Keeping H out of shared memory frees
+// 64 KB for the weight ring: with 3 stages (0.6 chunk of look-ahead) every chunk waited ~2.5 k cycles for an L2 round
+// trip of its weights (430 us per launch at C = 192); 5 stages hold a whole chunk.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -38,12 +44,12 @@ struct MlpCfg {
   // not have the TMEM / smem for that.
   static constexpr bool kDefer = (C == 96);
   static constexpr int kABufs = 1;                      // y tile buffers (2 = the next tile is fetched a whole tile ahead)
-  static constexpr int kStages = (C == 96) ? 5 : 3;     // weight ring: what is left of the 227 KB
+  static constexpr int kStages = (C == 96) ? 6 : 5;     // weight ring: one chunk (4 / 5 k-blocks) of look-ahead
   static constexpr int kAcc2 = kDefer ? 2 : 1;
   static constexpr int kOutGroups = (C == 96) ? 3 : 2;  // column groups that write the tile output
   static constexpr int STG_BYTES = kOutGroups * 16384;  // fp32 output staging, [128 x 32] per group
   static constexpr int PAR_FLOATS = HID;                // b1
-  static constexpr int SMEM_BYTES = 1024 + kABufs * A_BYTES + 2 * H_BYTES + kStages * STAGE_BYTES + STG_BYTES + PAR_FLOATS * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 + kABufs * A_BYTES + kStages * STAGE_BYTES + STG_BYTES + PAR_FLOATS * 4 + 256;
   static constexpr int ACC2_COL = 2 * HC;               // TMEM: acc1[0] @0, acc1[1] @HC, acc2[u] @2HC + u C
   static constexpr int CQ = HC / 4;                     // GELU columns per warp: 32
   static_assert(ACC2_COL + kAcc2 * C <= 512 && SMEM_BYTES <= 227 * 1024, "fused MLP budget");
@@ -69,6 +75,24 @@ DSG_DEVICE uint32_t sw128_offset(int r, int k) {
   return static_cast<uint32_t>((k >> 6) * 16384 + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4));
 }
 
+// D[tmem] (+)= A[tmem: lane = row, one 32-bit column per pair of K elements] . B[smem descriptor]^T
+DSG_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DSG_DEVICE void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+DSG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int C>
 // 18 warps -> 5 on the fullest SM sub-partition (16K registers each): at most 96 registers per thread
 __global__ void __launch_bounds__(kMlpThreads, 1)
@@ -80,8 +104,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   // keeps the shared address space and emits LDS / STS instead of generic loads and stores
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sH = sA + G::kABufs * G::A_BYTES;
-  uint8_t* sW = sH + 2 * G::H_BYTES;  // sH is double buffered: the workers never wait for fc2 of the previous chunk
+  uint8_t* sW = sA + G::kABufs * G::A_BYTES;
   uint8_t* sStg = sW + G::kStages * G::STAGE_BYTES;
   float* sPar = reinterpret_cast<float*>(sStg + G::STG_BYTES);
   float* sB1 = sPar;
@@ -91,9 +114,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* a_full = bars + 2 * G::kStages;   // [2] TMA -> MMA: y tile landed
   uint64_t* a_empty = a_full + 2;             // [2] MMA -> TMA: every fc1 MMA of the tile has read its sA buffer
   uint64_t* acc1_full = a_full + 4;           // [2]
-  uint64_t* acc1_empty = a_full + 6;          // [2]
   uint64_t* h_full = a_full + 8;              // [2]
-  uint64_t* h_empty = a_full + 10;            // [2]
   uint64_t* acc2_full = a_full + 12;          // [2]
   uint64_t* acc2_empty = a_full + 14;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 16);
@@ -112,8 +133,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < G::kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int u = 0; u < 2; ++u) { mbar_init(&a_full[u], 1); mbar_init(&a_empty[u], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], 16); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&h_full[b], 16); mbar_init(&h_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc1_full[b], 1); mbar_init(&h_full[b], 16); }
     for (int u = 0; u < 2; ++u) { mbar_init(&acc2_full[u], 1); mbar_init(&acc2_empty[u], 4 * G::kOutGroups); }
     fence_barrier_init();
   }
@@ -176,7 +196,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     constexpr uint32_t idesc2 = umma_idesc_bf16(C);
     int s = 0;
     uint32_t ph = 0;
-    uint32_t n_a[2] = {0, 0}, n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};  // use counters -> parities
+    uint32_t n_a[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};  // use counters -> parities
     auto fc1 = [&](int g) {  // acc1[g & 1] = y . W1[chunk]^T
       const int b = g & 1, j = g % G::NCH;
       const int ua = (g / G::NCH) % G::kABufs;  // y buffer of this tile
@@ -184,10 +204,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         mbar_wait(&a_full[ua], n_a[ua] & 1);
         ++n_a[ua];
       }
-      mbar_wait(&acc1_empty[b], (n_acc1[b] & 1) ^ 1);
-      ++n_acc1[b];
+      // (acc1[b] last held chunk g - 2, whose fc2 was issued before this call: the tensor pipe runs in issue order)
       tcgen05_fence_after();
-      DSG_MLP_TRACE(g, 0);  // fc1(g): accumulator and y tile available
+      DSG_MLP_TRACE(g, 0);  // fc1(g): y tile available
       for (int kb = 0; kb < G::KB1; ++kb) {
         mbar_wait(&w_full[s], ph);
         tcgen05_fence_after();
@@ -214,7 +233,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     for (int g = 0; g < n_chunks; ++g) {
       const int j = g % G::NCH;
       const int u = G::kDefer ? ((g / G::NCH) & 1) : 0;  // acc2 buffer of this tile
-      const int hb = g & 1;                               // sH buffer of this chunk
+      const int hb = g & 1;                               // acc1 buffer holding the GELU output of this chunk
       mbar_wait(&h_full[hb], n_h[hb] & 1);
       ++n_h[hb];
       if (j == 0) {
@@ -230,10 +249,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (kb == 0) DSG_MLP_TRACE(g, 5);  // after the wait
         if (kb == G::KB2 - 1) DSG_MLP_TRACE(g, 3);  // fc2(g): last W2 k-block landed
         if (elect_one()) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sH + hb * G::H_BYTES + kb * 16384));
           const uint64_t db = umma_desc_sw128(smem_u32(sW + s * G::STAGE_BYTES));
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + G::ACC2_COL + u * C, da + 2 * k, db + 2 * k, idesc2, (j | kb | k) != 0);
+          for (int k = 0; k < 4; ++k)  // A = H from tensor memory: K step kb * 4 + k sits at columns [16 (..), + 8)
+            umma_bf16_ts(tmem_base + G::ACC2_COL + u * C, tmem_base + hb * G::HC + (kb * 4 + k) * 16, db + 2 * k, idesc2,
+                         (j | kb | k) != 0);
           if (kb == 0) DSG_MLP_TRACE(g, 6);  // 4 MMAs issued
           umma_commit(&w_empty[s]);
           if (kb == 0) DSG_MLP_TRACE(g, 7);  // commit issued
@@ -241,11 +260,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         __syncwarp();
         if (++s == G::kStages) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) {
-        umma_commit(&h_empty[hb]);
-        if (j == G::NCH - 1) umma_commit(&acc2_full[u]);
+      if (j == G::NCH - 1) {
+        if (elect_one()) umma_commit(&acc2_full[u]);
+        __syncwarp();
       }
-      __syncwarp();
       if (g + 2 < n_chunks) fc1(g + 2);
     }
   } else {
@@ -256,7 +274,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const int r_t = q * 32 + lane;          // accumulator row owned by this thread
     // the four warps of a column group hold warp indices 4cg .. 4cg+3: elect the first as the TMA-store issuer
     const bool store_issuer = ((w & 3) == 0) && lane == 0;
-    uint32_t n_acc1[2] = {0, 0}, n_h[2] = {0, 0}, n_acc2[2] = {0, 0};
+    uint32_t n_acc1[2] = {0, 0}, n_acc2[2] = {0, 0};
 
     // tile output: acc2[u] + b2 -> swizzled fp32 staging -> TMA reduce-add into x (column groups < kOutGroups)
     auto tile_output = [&](int tile, int u, int g_trace) {
@@ -305,7 +323,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     int g = 0, tl = 0;  // global chunk index, local tile counter
     int prev_tile = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 -> sH
+      // ---- hidden chunks: acc1 -> + b1 -> GELU -> bf16 pairs, in place in tensor memory
 #pragma unroll 1
       for (int j = 0; j < G::NCH; ++j, ++g) {
         const int b = g & 1;
@@ -316,17 +334,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         DSG_MLP_TRACE(g, 1);  // worker: acc1 of chunk g available
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * G::HC + cg * G::CQ;
 #pragma unroll
-        for (int c0 = 0; c0 < G::CQ; c0 += 16) {
+        for (int c0 = 0; c0 < G::CQ; c0 += 16) {  // 16 hidden columns = one K step of fc2
           uint32_t r[16];
           tmem_ld_32x16(t_addr + c0, r);
           tmem_ld_wait();
-          if (c0 + 16 >= G::CQ) {  // accumulator drained by this warp: fc1 of chunk g + 2 may overwrite it
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc1_empty[b]);
-          }
           uint32_t hp[8];  // packed bf16 pairs
-#pragma unroll
           if (p.skip_gelu) {
 #pragma unroll
             for (int k = 0; k < 16; k += 2) hp[k >> 1] = pack_bf16x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
@@ -338,17 +350,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               hp[(k >> 1) + 1] = gelu_bias_bf16x2(r[k + 2], r[k + 3], bb.z, bb.w);
             }
           }
-          if (c0 == 0) {
-            DSG_MLP_TRACE(g, 2);
-            mbar_wait(&h_empty[b], (n_h[b] & 1) ^ 1);  // fc2 of chunk g - 2 has finished reading this sH buffer
-            ++n_h[b];
-            DSG_MLP_TRACE(g, 3);  // worker: sH free
-          }
-          uint8_t* sHb = sH + b * G::H_BYTES;
-          *reinterpret_cast<uint4*>(sHb + sw128_offset(r_t, cg * G::CQ + c0)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(sHb + sw128_offset(r_t, cg * G::CQ + c0 + 8)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          tmem_st_32x8(t_addr + c0, hp);  // in place: the first 8 of the 16 fp32 columns just read
         }
-        fence_proxy_async_smem();
+        DSG_MLP_TRACE(g, 2);
+        tmem_st_wait();
+        tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&h_full[b]);
         DSG_MLP_TRACE(g, 4);  // worker: chunk g done

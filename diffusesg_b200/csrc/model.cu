@@ -24,6 +24,14 @@ namespace dsg {
 static thread_local char g_err[1024] = "";
 static unsigned long long g_launches = 0;
 static long long* g_mlp_trace = nullptr;  // test hook: device buffer for the fused-MLP timeline of its next launch
+// the launch that receives the trace buffer: the next fused block-tail / fused-MLP launch of width DSG_TRACE_C (any if unset)
+static long long* take_trace(int C) {
+  static const int want = getenv("DSG_TRACE_C") ? atoi(getenv("DSG_TRACE_C")) : 0;
+  if (g_mlp_trace == nullptr || (want != 0 && want != C)) return nullptr;
+  long long* t = g_mlp_trace;
+  g_mlp_trace = nullptr;
+  return t;
+}
 static int g_stop_after = -1;  // test hook: leave the forward schedule after this many stages (-1: run all)
 
 void set_last_error(const char* fmt, ...) {
@@ -461,8 +469,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     DSG_TRY_P(PC_MLP, 18.0 * rc * C, rc * 10,
               launch_block_tail(ta, &b.tail_wp, &b.tail_w1, &b.mlp_w2, tx, m->f32(p + ".attn.proj.bias"),
                                 m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"),
-                                m->f32(p + ".mlp.fc2.bias"), w.X, rows, C, st, g_mlp_trace));
-    g_mlp_trace = nullptr;
+                                m->f32(p + ".mlp.fc2.bias"), w.X, rows, C, st, take_trace(C)));
     return DSG_OK;
   }
   // x = x + proj(attn)                                                   (:137, :272)
@@ -475,8 +482,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     if (ty == nullptr || tx == nullptr) return DSG_ERR_CUDA;
     DSG_TRY_P(PC_MLP, 16.0 * rc * C, rc * 10,
               launch_fused_mlp(ty, &b.mlp_w1, &b.mlp_w2, tx, m->f32(p + ".mlp.fc1.bias"), m->f32(p + ".mlp.fc2.bias"), rows,
-                               C, st, g_mlp_trace));
-    g_mlp_trace = nullptr;
+                               C, st, take_trace(C)));
     return DSG_OK;
   }
   DSG_TRY(gemm(m, w.Y, rows, b.fc1, EPI_GELU_BF16, m->f32(p + ".mlp.fc1.bias"), nullptr, w.H, st));

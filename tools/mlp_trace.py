@@ -1,7 +1,8 @@
-"""Timeline of CTA 0 of the first fused-MLP launch of a denoiser pass (clock64 stamps), printed per chunk."""
+"""Timeline of CTA 0 of the first fused-MLP launch of width DSG_TRACE_C (default 192) of a denoiser pass."""
 import os
 import sys
 
+os.environ.setdefault("DSG_TRACE_C", "192")
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,6 +13,7 @@ from diffusesg_b200.utils.synthetic import CONFIGS, synthetic_inputs  # noqa: E4
 cfg = CONFIGS["vg"]
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+G0 = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 model = build_native_model(cfg, dev)
 adj, node, flags, sigmas, sc_adj, sc_node = [t.to(dev) for t in synthetic_inputs(cfg, B, seed=7)]
 sig = torch.tensor(1.5, device=dev).view(-1).expand(B)
@@ -25,12 +27,12 @@ torch.cuda.synchronize()
 t = buf.cpu().view(64, 18, 8)
 t0 = int(t[t > 0].min())
 rel = torch.where(t > 0, t - t0, torch.full_like(t, -1))
-print("MMA warp (17): ev0 fc1 ready, ev1 fc1 last W1 landed, ev2 fc2 H ready, ev3 fc2 last W2 landed")
-print("workers (0..15): ev0 ready, ev1 acc1 available, ev2 before h_empty, ev3 sH free, ev4 chunk done, ev5/6/7 output")
-for g in range(12):
-    mma = rel[g, 17, :8].tolist()
+print("MMA (17): fc1 ready / last W1 landed | fc2 H ready / last W2 landed")
+print("workers (0..15): ready, acc1 available, GELU stored, arrived | output: start / acc2 complete / issued")
+for g in range(G0, G0 + 14):
+    m = rel[g, 17, :].tolist()
     w = rel[g, :16, :]
     def rng(e):
         v = w[:, e][w[:, e] >= 0]
         return f"{int(v.min())}-{int(v.max())}" if len(v) else "-"
-    print(f"g={g:2d} MMA {mma}  W ready {rng(0)} acc1 {rng(1)} pre-h {rng(2)} hfree {rng(3)} done {rng(4)} out {rng(5)}/{rng(6)}/{rng(7)}")
+    print(f"g={g:2d} MMA fc1 {m[0]}/{m[1]} fc2 {m[2]}/{m[3]} | W {rng(0)} {rng(1)} {rng(2)} {rng(4)} | out {rng(5)} {rng(6)} {rng(7)}")
