@@ -195,7 +195,7 @@ def run_reference(args, cfg, rank, world):
             "config": workload_config(args, cfg, world),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, world):
@@ -327,12 +327,31 @@ def run_native(args, cfg, rank, local_rank, world):
                                 "sample": f"oracle port of the reference PyTorch CPU path, {args.config} geometry, batch "
                                           f"{args.cpu_batch}, {args.cpu_steps} Heun steps ({p:.0f} raw passes, {spp:.3f} "
                                           f"s/pass), extrapolated to {EXPECTED_PASSES_256} passes per 256-step batch"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Everything else that lands on fd 1 (NCCL's version banner is printed from C at every debug level but NONE,
+    # library chatter) goes to stderr, so that stdout carries exactly one line.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
