@@ -85,6 +85,16 @@ int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const C
                       cudaStream_t st, long long* trace = nullptr);
 
 // ---------------------------------------------------------------------------------------------
+// fused block head:  x = silu(FiLM(x));  qkv = LN1(x) W_qkv^T + b_qkv                     (blockhead.cu)
+// ---------------------------------------------------------------------------------------------
+// Built for C = 96.  tmXin / tmXout: x [rows, C] fp32 in / out (make_tmap_out, EPI_F32; may be the same buffer);
+// tmW: qkv.weight [3C, C] bf16, box 32 x C (64-byte swizzle); tmQ: qkv [rows, 3C] bf16 (make_tmap_out, EPI_BF16).
+bool block_head_supported(int C);
+int launch_block_head(const CUtensorMap* tmXin, const CUtensorMap* tmXout, const CUtensorMap* tmW, const CUtensorMap* tmQ,
+                      const float* film, int film_ld, int cond_uniform, int tokens_per_sample, const float* gamma,
+                      const float* beta, const float* bqkv, long long rows, int C, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
 // shifted-window attention                                             (attention.cu)
 // ---------------------------------------------------------------------------------------------
 // qkv [B*res*res, 3*C] bf16 (q pre-scaled through the packed weights), layout per token [3][heads][32];

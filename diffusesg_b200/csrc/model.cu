@@ -112,6 +112,7 @@ struct Block {
   Weight qkv, proj, fc1, fc2;
   CUtensorMap mlp_w1, mlp_w2;  // descriptors of fc1 / fc2 with the fused-MLP box shapes (C = 96, 192)
   CUtensorMap tail_wp, tail_w1;  // proj / fc1 with the fused block-tail box shapes (32-column k-blocks)
+  CUtensorMap head_w;            // qkv with the fused block-head box shape (32 x C)
   size_t qkv_bias_off;  // fp32 [3C], q part pre-scaled
   size_t attn_bias_off; // fp32 [heads, T, T]
 };
@@ -146,6 +147,7 @@ struct dsg_model {
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
+  bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -442,11 +444,33 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   const int L = b.res * b.res;
   const long long rows = static_cast<long long>(batch) * L;
   const std::string& p = b.prefix;
-  // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
   const double rc = static_cast<double>(rows) * C;
-  DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
-                                               m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"), batch, L, C, st));
-  DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
+  auto tmap0 = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
+    auto k = std::make_tuple(ptr, rows, key);
+    auto it = m->a_maps.find(k);
+    if (it == m->a_maps.end()) {
+      CUtensorMap tm;
+      if (make(&tm)) return nullptr;
+      it = m->a_maps.emplace(k, tm).first;
+    }
+    return &it->second;
+  };
+  if (m->use_head && block_head_supported(C)) {
+    // x = silu(FiLM(x)); qkv = LN1(x) W^T + b in one launch                (:238-243, :115)
+    const CUtensorMap* ti = tmap0(x_in, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, x_in, rows, C, EPI_RES_F32); });
+    const CUtensorMap* to = tmap0(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
+    const CUtensorMap* tq = tmap0(w.QKV, -(3 * C * 8 + EPI_BF16), [&](CUtensorMap* t) { return make_tmap_out(t, w.QKV, rows, 3 * C, EPI_BF16); });
+    if (ti == nullptr || to == nullptr || tq == nullptr) return DSG_ERR_CUDA;
+    DSG_TRY_P(PC_MLP, 6.0 * rc * C, rc * 14,
+              launch_block_head(ti, to, &b.head_w, tq, w.film + b.film_off, m->film_total, cond_uniform, L,
+                                m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"), m->at<float>(b.qkv_bias_off), rows,
+                                C, st));
+  } else {
+    // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
+    DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
+                                                 m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"), batch, L, C, st));
+    DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
+  }
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
   DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
             launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
@@ -511,6 +535,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   m->use_tail = !(no_tail != nullptr && no_tail[0] == '1');
   const char* no_pair = getenv("DSG_NO_PAIR");
   m->use_pair = !(no_pair != nullptr && no_pair[0] == '1');
+  const char* no_head = getenv("DSG_NO_HEAD");
+  m->use_head = !(no_head != nullptr && no_head[0] == '1');
   const int rc = build(m);
   if (rc) { delete m; return rc; }
   *out = m;
@@ -579,6 +605,7 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
       DSG_TRY(make_tmap_bf16(&b.mlp_w1, m->arena + b.fc1.offset, 4 * C, C, fused_mlp_w1_box_rows(C)));
       DSG_TRY(make_tmap_bf16(&b.mlp_w2, m->arena + b.fc2.offset, C, 4 * C, C));
     }
+    if (block_head_supported(C)) DSG_TRY(make_tmap_2d(&b.head_w, m->arena + b.qkv.offset, 3 * C, C, 2, 32, C));
     if (block_tail_supported(C)) {
       DSG_TRY(make_tmap_2d(&b.tail_wp, m->arena + b.proj.offset, C, C, 2, 32, C));
       DSG_TRY(make_tmap_2d(&b.tail_w1, m->arena + b.fc1.offset, 4 * C, C, 2, 32, 128));

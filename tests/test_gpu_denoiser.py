@@ -157,6 +157,30 @@ def test_block_tail_matches_unfused_schedule(name, batch):
     assert rel(fa, ua) < 8e-3 and rel(fn, un) < 8e-3, (rel(fa, ua), rel(fn, un))
 
 
+@pytest.mark.parametrize("name,batch", [("vg", 3), ("tiny", 5)])
+def test_block_head_matches_unfused_schedule(name, batch):
+    """The fused FiLM + LN1 + qkv kernel (C = 96 blocks) against the FiLM/LayerNorm row kernel + qkv GEMM it replaces:
+    same fp32 FiLM/SiLU/LayerNorm expressions and the same bf16 rounding of the LayerNorm output; only the fp32
+    accumulation order of the statistics and of the GEMM differs.  tiny has 256-token samples and per-sample sigmas,
+    i.e. per-row FiLM rows inside one 128-token tile sequence."""
+    cfg = CONFIGS[name]
+    inputs = [t.to(DEV) for t in synthetic_inputs(cfg, batch, seed=17)]
+    adj, node, flags, sigmas, sc_adj, sc_node = inputs
+    labels = (sigmas * torch.linspace(0.5, 2.0, batch, device=DEV)).log() / 4
+    outs = []
+    for no_head in ("0", "1"):
+        os.environ["DSG_NO_HEAD"] = no_head
+        try:
+            model, _ = build(cfg)
+            with torch.no_grad():
+                outs.append(model(adj, node, flags, labels, sc_adj, sc_node))
+        finally:
+            os.environ.pop("DSG_NO_HEAD", None)
+    (fa, fn), (ua, un) = outs
+    assert torch.isfinite(fa).all() and torch.isfinite(fn).all()
+    assert rel(fa, ua) < 8e-3 and rel(fn, un) < 8e-3, (rel(fa, ua), rel(fn, un))
+
+
 def test_forward_uniform_vs_per_sample_sigma():
     cfg = CONFIGS["tiny"]
     model, _ = build(cfg)
