@@ -209,32 +209,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // columns [48 half, 48 half + 48) of the hidden layer; partial sums of the 96 -> c_e linear are combined
         // through shared memory (reusing the staging area)
         float* sPart = reinterpret_cast<float*>(sOut) + acc * 128 * 8;
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // previous tile's bias reads are done
-        if (tig < 48) sBiasA[half * 48 + tig] = p.bias[half * 48 + tig];
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (tile == cta + acc * ncta) {  // first tile of this group: the bias slice never changes (N == BN == 96)
+          if (tig < 48) sBiasA[half * 48 + tig] = p.bias[half * 48 + tig];
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
+        const int row = m_blk * BM + r_in_tile;
+        // everything the output step needs from global memory is fetched BEFORE the accumulator wait: this group
+        // handles one tile at a time, so these dependent loads were ~1.5 k exposed cycles per tile
+        const int n_ = p.n_img, nn_ = n_ * n_;
+        const int rowc = row < p.M ? row : p.M - 1;
+        const int b_ = rowc / nn_, ij_ = rowc - b_ * nn_;
+        bool ok_ = false;
+        float cs_ = 0.f, co_ = 1.f, xa_[8];
+        if (half == 0) {
+          const int i_ = ij_ / n_, j_ = ij_ - i_ * n_;
+          ok_ = p.flags[b_ * n_ + i_] != 0 && p.flags[b_ * n_ + j_] != 0;
+          if (p.x_adj != nullptr) {
+            cs_ = p.c_skip[b_];
+            co_ = p.c_out[b_];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) xa_[c] = c < p.c_e ? p.x_adj[(static_cast<size_t>(b_) * p.c_e + c) * nn_ + ij_] : 0.f;
+          }
+        }
         mbar_wait(&tfull_bar[acc], acc_ph);
         tcgen05_fence_after();
-        const int row = m_blk * BM + r_in_tile;
-        float y[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = 0.f;
+        // packed fp32 pairs: the 8 outputs are four FFMA2 accumulators, GELU runs on column pairs
+        f32x2 y2[4] = {f2_splat(0.f), f2_splat(0.f), f2_splat(0.f), f2_splat(0.f)};
 #pragma unroll
         for (int c0 = 0; c0 < 48; c0 += 16) {
           uint32_t r[16];
           tmem_ld_32x16(t_row + half * 48 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 16; j += 2) {
             const int col = half * 48 + c0 + j;
-            const float v = gelu_erf(__uint_as_float(r[j]) + sBiasA[col]);
-            const float4 wa = *reinterpret_cast<const float4*>(&s_w2t[col * 8]);
-            const float4 wb = *reinterpret_cast<const float4*>(&s_w2t[col * 8 + 4]);
-            y[0] = fmaf(wa.x, v, y[0]); y[1] = fmaf(wa.y, v, y[1]);
-            y[2] = fmaf(wa.z, v, y[2]); y[3] = fmaf(wa.w, v, y[3]);
-            y[4] = fmaf(wb.x, v, y[4]); y[5] = fmaf(wb.y, v, y[5]);
-            y[6] = fmaf(wb.z, v, y[6]); y[7] = fmaf(wb.w, v, y[7]);
+            const float2 bb = *reinterpret_cast<const float2*>(&sBiasA[col]);
+            float v0, v1;
+            f2_unpack(gelu_erf2(f2_add(f2_pack(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), f2_pack(bb.x, bb.y))), v0, v1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const f32x2 vv = f2_splat(h == 0 ? v0 : v1);
+              const float4 wa = *reinterpret_cast<const float4*>(&s_w2t[(col + h) * 8]);
+              const float4 wb = *reinterpret_cast<const float4*>(&s_w2t[(col + h) * 8 + 4]);
+              y2[0] = f2_fma(f2_pack(wa.x, wa.y), vv, y2[0]);
+              y2[1] = f2_fma(f2_pack(wa.z, wa.w), vv, y2[1]);
+              y2[2] = f2_fma(f2_pack(wb.x, wb.y), vv, y2[2]);
+              y2[3] = f2_fma(f2_pack(wb.z, wb.w), vv, y2[3]);
+            }
           }
         }
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f2_unpack(y2[c], y[2 * c], y[2 * c + 1]);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) release_acc();
@@ -251,21 +277,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (row < p.M) {
             // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
             // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
-            const int n = p.n_img;
-            const int nn = n * n;
-            const int b = row / nn;
-            const int ij = row - b * nn;
-            const int i = ij / n, j = ij - i * n;
-            const bool ok = p.flags[b * n + i] != 0 && p.flags[b * n + j] != 0;
-            float cs = 0.f, co = 1.f;
-            if (p.x_adj != nullptr) { cs = p.c_skip[b]; co = p.c_out[b]; }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               if (c < p.c_e) {
-                const size_t o = (static_cast<size_t>(b) * p.c_e + c) * nn + ij;
+                const size_t o = (static_cast<size_t>(b_) * p.c_e + c) * nn_ + ij_;
                 float val = y[c];
-                if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs, p.x_adj[o]), __fmul_rn(co, val));
-                reinterpret_cast<float*>(p.out)[o] = ok ? val : 0.f;
+                if (p.x_adj != nullptr) val = __fadd_rn(__fmul_rn(cs_, xa_[c]), __fmul_rn(co_, val));
+                reinterpret_cast<float*>(p.out)[o] = ok_ ? val : 0.f;
               }
             }
           }

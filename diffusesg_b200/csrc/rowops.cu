@@ -630,52 +630,99 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
 // ---------------------------------------------------------------------------------------------------------
 // node read-out: masked row mean -> MLP -> mask (-> EDM output preconditioning)   (:812-822, precond.py:103-105)
 // ---------------------------------------------------------------------------------------------------------
-// One CTA (128 threads) per (b, i).  y is LN(x) of the last stage [B n n, E] (bf16); the folded read_out map
-// (fold_t [E][E] input-major, fold_b) is applied after pooling: mean_j m_ij (F y_ij + f) = F mean_j(m_ij y_ij) + f cnt/n.
-__global__ void __launch_bounds__(128)
+// One CTA (256 threads) per kHeadRows consecutive rows (b, i): the three weight matrices (77 KB from L2) are read
+// once per CTA instead of once per row, and the phases of the eight rows overlap each other's latencies.  y is LN(x)
+// of the last stage [B n n, E] (bf16); the folded read_out map (fold_t [E][E] input-major, fold_b) is applied after
+// pooling: mean_j m_ij (F y_ij + f) = F mean_j(m_ij y_ij) + f cnt/n.
+constexpr int kHeadRows = 8;
+__global__ void __launch_bounds__(256)
 node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags, const float* __restrict__ fold_t,
                  const float* __restrict__ fold_b, const float* __restrict__ w1t,
                  const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                  const float* __restrict__ x_node, const float* __restrict__ c_skip, const float* __restrict__ c_out,
-                 float* __restrict__ out_node, int n, int c_n, int embed) {
-  __shared__ float pooled[128];
-  __shared__ float hidden[128];
-  const int bi = blockIdx.x;
-  const int b = bi / n;
-  const int e = threadIdx.x;
-  const bool row_ok = flags[bi] != 0;
-  if (!row_ok) {  // masked node: output row is zero regardless of the features
-    if (e < c_n) out_node[static_cast<size_t>(bi) * c_n + e] = 0.f;
-    return;
-  }
-  if (e < embed) {
-    const bf16* p = rep + static_cast<size_t>(bi) * n * embed + e;
-    float s = 0.f;
+                 float* __restrict__ out_node, long long rows, int n, int c_n, int embed) {
+  __shared__ float va[kHeadRows][128];  // masked row means, then the hidden layer
+  __shared__ float vb[kHeadRows][128];  // pooled read-out
+  __shared__ float frac[kHeadRows];     // valid columns / n
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = static_cast<long long>(blockIdx.x) * kHeadRows;
+  // ---- masked mean over j of row (b, i) = row0 + warp: lanes 0 .. embed / 4 - 1 own four channels each
+  {
+    const long long bi = row0 + warp;
+    const bool live = bi < rows && flags[bi] != 0;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
-    for (int j = 0; j < n; ++j)
-      if (flags[b * n + j]) { s += __bfloat162float(p[static_cast<size_t>(j) * embed]); ++cnt; }
-    hidden[e] = s / n;  // mean over the full row length N, not over the valid count (:813)
-    pooled[e] = fold_b[e] * (static_cast<float>(cnt) / n);
+    if (live) {
+      const int b = static_cast<int>(bi / n);
+      const uint8_t* fj = flags + static_cast<size_t>(b) * n;
+      const bf16* p = rep + static_cast<size_t>(bi) * n * embed + 4 * lane;
+      const bool mine = 4 * lane < embed;
+      // unconditional, unrolled loads (masked columns are multiplied by zero): eight 8-byte loads in flight per lane
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) {
+        const float m = fj[j] != 0 ? 1.f : 0.f;
+        cnt += fj[j] != 0;
+        if (mine) {
+          const uint2 v = *reinterpret_cast<const uint2*>(p + static_cast<size_t>(j) * embed);
+          const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+          const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          s.x = fmaf(m, __low2float(lo), s.x); s.y = fmaf(m, __high2float(lo), s.y);
+          s.z = fmaf(m, __low2float(hi), s.z); s.w = fmaf(m, __high2float(hi), s.w);
+        }
+      }
+    }
+    if (4 * lane < embed) {  // mean over the full row length N, not over the valid count (:813)
+      va[warp][4 * lane] = s.x / n; va[warp][4 * lane + 1] = s.y / n;
+      va[warp][4 * lane + 2] = s.z / n; va[warp][4 * lane + 3] = s.w / n;
+    }
+    if (lane == 0) frac[warp] = static_cast<float>(cnt) / n;
+  }
+  __syncthreads();
+  // ---- three small matrix products, thread (e, rh): output column e of rows 4 rh .. 4 rh + 3
+  const int e = threadIdx.x % 128, rh = threadIdx.x / 128;
+  if (e < embed) {
+    float acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = fold_b[e] * frac[4 * rh + r];
+#pragma unroll 16
+    for (int k = 0; k < embed; ++k) {  // sixteen independent L2 loads in flight
+      const float w = fold_t[k * embed + e];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(w, va[4 * rh + r][k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vb[4 * rh + r][e] = acc[r];
   }
   __syncthreads();
   if (e < embed) {
-    float s = pooled[e];
-    for (int k = 0; k < embed; ++k) s = fmaf(fold_t[k * embed + e], hidden[k], s);
-    pooled[e] = s;
+    float acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = b1[e];
+#pragma unroll 16
+    for (int k = 0; k < embed; ++k) {
+      const float w = w1t[k * embed + e];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(w, vb[4 * rh + r][k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) va[4 * rh + r][e] = gelu_erf(acc[r]);
   }
   __syncthreads();
-  if (e < embed) {
-    float s = b1[e];
-    for (int k = 0; k < embed; ++k) s = fmaf(w1t[k * embed + e], pooled[k], s);
-    hidden[e] = gelu_erf(s);
-  }
-  __syncthreads();
-  if (e < c_n) {
-    float s = b2[e];
-    for (int k = 0; k < embed; ++k) s = fmaf(w2t[k * c_n + e], hidden[k], s);
-    const size_t o = static_cast<size_t>(bi) * c_n + e;
-    if (x_node != nullptr) s = __fadd_rn(__fmul_rn(c_skip[b], x_node[o]), __fmul_rn(c_out[b], s));
-    out_node[o] = s;
+  for (int idx = threadIdx.x; idx < kHeadRows * c_n; idx += blockDim.x) {
+    const int r = idx / c_n, c = idx - r * c_n;
+    const long long bi = row0 + r;
+    if (bi >= rows) continue;
+    const size_t o = static_cast<size_t>(bi) * c_n + c;
+    if (flags[bi] == 0) {  // masked node: output row is zero regardless of the features
+      out_node[o] = 0.f;
+      continue;
+    }
+    float sum = b2[c];
+#pragma unroll 16
+    for (int k = 0; k < embed; ++k) sum = fmaf(w2t[k * c_n + c], va[r][k], sum);
+    const int b = static_cast<int>(bi / n);
+    if (x_node != nullptr) sum = __fadd_rn(__fmul_rn(c_skip[b], x_node[o]), __fmul_rn(c_out[b], sum));
+    out_node[o] = sum;
   }
 }
 
@@ -835,9 +882,10 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
 int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip,
                      const float* c_out, float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st) {
-  DSG_REQUIRE(embed <= 128 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
-  node_head_kernel<<<batch * n, 128, 0, st>>>(rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out,
-                                              out_node, n, c_n, embed);
+  DSG_REQUIRE(embed <= 128 && embed % 4 == 0 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
+  const long long rows = static_cast<long long>(batch) * n;
+  node_head_kernel<<<static_cast<unsigned>((rows + kHeadRows - 1) / kHeadRows), 256, 0, st>>>(
+      rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, rows, n, c_n, embed);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
