@@ -7,6 +7,8 @@
 // packed qkv weights).  Scores, softmax statistics and the output accumulator are fp32; q/k/v/p are bf16
 // tensor-core operands (warp-level mma.sync m16n8k16: each warp owns a 16-query slab; the window tile is
 // far below the 128-row tcgen05 atom).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -443,6 +445,9 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
   DSG_REQUIRE((shift > 0) == (mask != nullptr), "attention: a shifted block needs its mask (and only it)");
   const int T = window * window;
   DSG_REQUIRE(T % 2 == 0, "attention: odd window token count %d", T);
+  static const bool no_tc = getenv("DSG_NO_ATTN_TC") != nullptr && getenv("DSG_NO_ATTN_TC")[0] == '1';
+  if (!no_tc && window_attention_tc_supported(batch, res, window, shift, heads))
+    return launch_window_attention_tc(qkv, bias, out, batch, res, heads, st);  // un-shifted 8 x 8 windows: tcgen05
   if (window == 8) {
     const long long total = static_cast<long long>(batch) * (res / 8) * (res / 8);
     const long long grid = ((total + kWPC - 1) / kWPC) * heads;

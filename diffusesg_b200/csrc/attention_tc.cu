@@ -1,0 +1,340 @@
+// Window attention on tcgen05 for un-shifted 8 x 8 windows (T = 64 tokens, head dim 32):
+//   WindowAttention.forward (model/diffusesg/diffusesg.py:108-139 of the reference) with window_partition /
+//   window_reverse (:28-57) folded into 8 x 8-token TMA boxes of the [B res, res, 3C] view of the qkv matrix.
+//
+// A 64 x 64 x 32 window-head is half a tcgen05 tile, so TWO windows share one M = 128 tile:
+//   S[128 x 128] = Q[128 x 32] K[128 x 32]^T      one SS-mode MMA pair; only the two diagonal 64 x 64 blocks are used
+//   P = softmax(S_diag + bias)                    by the row's own thread: 64 scores in registers, exp2, one pass;
+//                                                 written back IN PLACE over S as bf16 pairs, with the off-diagonal
+//                                                 half of the 128-key row zeroed (the S MMA dirtied it)
+//   O[128 x 32]  = P[128 x 128] V[128 x 32]       TS mode: A = P from tensor memory, B = V straight from its TMA box
+//                                                 ([keys x dims], i.e. an MN-major operand: no transpose anywhere)
+// The warp-MMA version spends ~640 instructions per warp per window-head (fragment shuffles, per-quad softmax
+// reductions, 32 mma.sync) and runs at half the HBM rate; here a thread owns a whole score row and the item costs
+// ~450 issue slots per row.
+//
+//   warp 12  loader   q, k, v boxes of the two windows of an item (6 x 4 KB per stage, 4-stage ring)
+//   warp 13  MMA      S(k + 2) is issued after PV(k): three items in flight, one tensor-memory slot per worker group
+//   warp 14  storer   output boxes (bf16, 2 x 4 KB per item) -> TMA store
+//   warps 0..11       three worker groups of four warps (one per tensor-memory lane quarter); group g takes items
+//                     g, g + 3, ...: softmax, then O / l -> bf16 -> swizzled staging
+// A CTA keeps one head (its relative-position bias sits in shared memory) and walks window pairs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+constexpr int kTcThreads = 15 * 32;
+constexpr int kTcStages = 4;
+constexpr int kTcStageBytes = 3 * 8192;      // q | k | v, each [128 tokens x 32] bf16 (two windows)
+constexpr int kTcBiasPitch = 68;             // floats per bias row: 16-byte aligned, conflict-free row-per-lane reads
+constexpr int kTcSlotCols = 160;             // tensor-memory columns per item: S 128 (P aliases the first 64) + O 32
+constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + 3 * 8192 + 64 * kTcBiasPitch * 4 + 256;
+
+struct TcParams {
+  const float* bias;  // [heads, 64, 64]
+  int heads, res, nwx, nW;
+  int pairs;          // window pairs = B * nW / 2
+};
+
+DSG_DEVICE uint64_t desc_sw64_kmajor(uint32_t smem_addr) {  // [rows x 32] bf16, 64-byte swizzle, 8-row groups 512 B apart
+  const uint64_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16);
+  const uint64_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+  return lo | (hi << 32);
+}
+// V as the B operand of P.V: shared memory holds [K = keys][N = 32 dims] (64-byte rows, 64-byte swizzle), which is
+// the canonical MN-major layout ((4, n), (8, k)) : ((1, LBO), (4, SBO)) in 16-byte units with n = 1: the N extent is
+// one swizzle atom (LBO unused), groups of 8 keys are SBO = 512 bytes apart.
+DSG_DEVICE uint64_t desc_sw64_mnmajor(uint32_t smem_addr) {
+  const uint64_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16);
+  const uint64_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+  return lo | (hi << 32);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_bmn(int n) {  // M = 128, B operand MN-major (bit 16)
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+DSG_DEVICE void umma_ts_tc(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DSG_DEVICE void tmem_st8_tc(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+DSG_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+DSG_DEVICE void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
+                           const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sStage = smem;
+  uint8_t* sOut = sStage + kTcStages * kTcStageBytes;                  // [3 groups][2 windows][64 x 64 B]
+  float* sBias = reinterpret_cast<float*>(sOut + 3 * 8192);            // [64][68]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64 * kTcBiasPitch);
+  uint64_t* stage_full = bars;                     // [4]
+  uint64_t* stage_empty = bars + kTcStages;        // [4]
+  uint64_t* s_full = bars + 2 * kTcStages;         // [3] MMA -> group: scores complete
+  uint64_t* p_ready = s_full + 3;                  // [3] group -> MMA: probabilities in place
+  uint64_t* o_full = s_full + 6;                   // [3] MMA -> group: P.V complete
+  uint64_t* slot_free = s_full + 9;                // [3] group -> MMA: O read, the slot may take the next item
+  uint64_t* out_ready = s_full + 12;               // [3] group -> storer
+  uint64_t* out_free = s_full + 15;                // [3] storer -> group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 18);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  constexpr int kLoadWarp = 12, kMmaWarp = 13, kStoreWarp = 14;
+  const int h = blockIdx.x % p.heads;
+  const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
+  const int n_items = (p.pairs > cta_in_head) ? (p.pairs - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
+  const int C = p.heads * 32;
+
+  if (warp == kLoadWarp && lane == 0) {
+    tma_prefetch_desc(&tmQkv);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
+    for (int g = 0; g < 3; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_ready[g], 4);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&slot_free[g], 4);
+      mbar_init(&out_ready[g], 4);
+      mbar_init(&out_free[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  {
+    const float* bh = p.bias + static_cast<size_t>(h) * 64 * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += kTcThreads) sBias[(i >> 6) * kTcBiasPitch + (i & 63)] = bh[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  // window gw -> TMA coordinates (token x, token row) of its top-left token in the [B res, res] grid
+  auto win_coords = [&](int gw, int& cx, int& cy) {
+    const int b = gw / p.nW, win = gw - b * p.nW;
+    const int wy = win / p.nwx, wx = win - wy * p.nwx;
+    cx = wx * 8;
+    cy = b * p.res + wy * 8;
+  };
+
+  if (warp == kLoadWarp) {
+    // ------------------------------------------------------------------ loader
+    if (elect_one()) {
+      for (int k = 0; k < n_items; ++k) {
+        const int st = k % kTcStages;
+        const int pair = cta_in_head + k * ctas_per_head;
+        mbar_wait(&stage_empty[st], ((k / kTcStages) & 1) ^ 1);
+        mbar_expect_tx(&stage_full[st], kTcStageBytes);
+        uint8_t* base = sStage + st * kTcStageBytes;
+        for (int w = 0; w < 2; ++w) {
+          int cx, cy;
+          win_coords(2 * pair + w, cx, cy);
+          for (int part = 0; part < 3; ++part)
+            tma_load_3d(base + part * 8192 + w * 4096, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128);   // S: N = 128 keys, both operands K-major
+    constexpr uint32_t idesc_o = idesc_bf16_bmn(32);     // O: N = 32 dims, V is MN-major
+    auto issue_s = [&](int k) {
+      const int st = k % kTcStages, g = k % 3;
+      mbar_wait(&stage_full[st], (k / kTcStages) & 1);
+      mbar_wait(&slot_free[g], ((k / 3) & 1) ^ 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t da = desc_sw64_kmajor(smem_u32(sStage + st * kTcStageBytes));
+        const uint64_t db = desc_sw64_kmajor(smem_u32(sStage + st * kTcStageBytes + 8192));
+        for (int ks = 0; ks < 2; ++ks) umma_bf16_ss(tmem_base + g * kTcSlotCols, da + 2 * ks, db + 2 * ks, idesc_s, ks != 0);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int k) {
+      const int st = k % kTcStages, g = k % 3;
+      mbar_wait(&p_ready[g], (k / 3) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc_sw64_mnmajor(smem_u32(sStage + st * kTcStageBytes + 16384));
+        for (int ks = 0; ks < 8; ++ks)  // 16 keys per step: 8 packed P columns, 16 V rows (1024 bytes)
+          umma_ts_tc(tmem_base + g * kTcSlotCols + 128, tmem_base + g * kTcSlotCols + ks * 8, dv + 64 * ks, idesc_o, ks != 0);
+        umma_commit(&o_full[g]);
+        umma_commit(&stage_empty[st]);
+      }
+      __syncwarp();
+    };
+    if (n_items > 0) issue_s(0);
+    if (n_items > 1) issue_s(1);
+    for (int k = 0; k < n_items; ++k) {
+      issue_pv(k);
+      if (k + 2 < n_items) issue_s(k + 2);
+    }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------------ storer
+    if (elect_one()) {
+      for (int k = 0; k < n_items; ++k) {
+        const int g = k % 3;
+        const int pair = cta_in_head + k * ctas_per_head;
+        mbar_wait(&out_ready[g], (k / 3) & 1);
+        for (int w = 0; w < 2; ++w) {
+          int cx, cy;
+          win_coords(2 * pair + w, cx, cy);
+          tma_store_3d(&tmOut, sOut + g * 8192 + w * 4096, h * 32, cx, cy);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&out_free[g]);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ------------------------------------------------------------------ worker groups
+    const int g = warp >> 2, q = warp & 3;
+    const int r = q * 32 + lane;          // query row of the 128-row tile
+    const int w = r >> 6, tq = r & 63;    // its window and token
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kTcSlotCols;
+    const float* brow = sBias + tq * kTcBiasPitch;
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int k = g, it = 0; k < n_items; k += 3, ++it) {
+      mbar_wait(&s_full[g], it & 1);
+      tcgen05_fence_after();
+      // the 64 scores of this row's own window: columns [64 w, 64 w + 64)
+      uint32_t sv[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 16) tmem_ld_32x16(t_s + 64 * w + c, reinterpret_cast<uint32_t(&)[16]>(sv[c]));
+      tmem_ld_wait();
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + c);
+        const float a0 = __uint_as_float(sv[c]) + bb.x, a1 = __uint_as_float(sv[c + 1]) + bb.y;
+        const float a2 = __uint_as_float(sv[c + 2]) + bb.z, a3 = __uint_as_float(sv[c + 3]) + bb.w;
+        sv[c] = __float_as_uint(a0); sv[c + 1] = __float_as_uint(a1);
+        sv[c + 2] = __float_as_uint(a2); sv[c + 3] = __float_as_uint(a3);
+        m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+      }
+      const float ms = m * kLog2e;
+      float l = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c]), kLog2e, -ms));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), kLog2e, -ms));
+        l += e0 + e1;
+        pk[c >> 1] = pack_bf16x2(e0, e1);
+      }
+      // P over the 128 keys of the tile: own window's 64 keys (32 packed columns at 32 w), zeros for the other window
+      uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        tmem_st8_tc(t_s + 32 * w + c, pk + c);
+        tmem_st8_tc(t_s + 32 * (1 - w) + c, zero);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      // ---- output: O / l -> bf16 -> swizzled staging (64-byte rows: chunk ^= (token >> 1) & 3)
+      const float inv = rcp_approx(l);
+      mbar_wait(&o_full[g], it & 1);
+      tcgen05_fence_after();
+      uint32_t ov[32];
+      tmem_ld_32x32(t_s + 128, ov);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      mbar_wait(&out_free[g], (it & 1) ^ 1);
+      uint8_t* orow = sOut + g * 8192 + w * 4096 + tq * 64;
+      const int sw = (tq >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o4;
+        o4.x = pack_bf16x2(__uint_as_float(ov[8 * c]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
+        o4.y = pack_bf16x2(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
+        o4.z = pack_bf16x2(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
+        o4.w = pack_bf16x2(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o4;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_ready[g]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads) {
+  if (window != 8 || shift != 0 || res % 8 != 0 || heads < 1 || heads > 74) return false;
+  const long long windows = static_cast<long long>(batch) * (res / 8) * (res / 8);
+  return windows % 2 == 0 && windows >= 2;
+}
+
+int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int heads,
+                               cudaStream_t st) {
+  DSG_REQUIRE(window_attention_tc_supported(batch, res, 8, 0, heads), "attention_tc: unsupported shape");
+  const int C = heads * 32;
+  CUtensorMap tq, to;
+  // [B res (token row), res (token column), channels]: a window is an 8 x 8 box of tokens, a head slice 32 channels
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, 8, 8))
+    return rc;
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, 8, 8))
+    return rc;
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  TcParams p;
+  p.bias = bias;
+  p.heads = heads;
+  p.res = res;
+  p.nwx = res / 8;
+  p.nW = p.nwx * p.nwx;
+  p.pairs = static_cast<int>(static_cast<long long>(batch) * p.nW / 2);
+  int per_head = sms / heads;
+  if (per_head > p.pairs) per_head = p.pairs;
+  if (per_head < 1) per_head = 1;
+  window_attention_tc_kernel<<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+}  // namespace dsg

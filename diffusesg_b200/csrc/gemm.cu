@@ -488,6 +488,32 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return DSG_OK;
 }
 
+// bf16 tensor [d2][d1][d0] (d0 contiguous, byte strides s1 / s2 of d1 / d2), box b0 x b1 x b2, 64-byte swizzle
+// (b0 must be 32 elements).  Used for the 8 x 8-token window boxes of the tcgen05 attention kernel.
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2, int b0,
+                      int b1, int b2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return DSG_ERR_CUDA;
+  }
+  DSG_REQUIRE(b0 == 32 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && s1 % 16 == 0 && s2 % 16 == 0 && b1 > 0 &&
+                  b1 <= 256 && b2 > 0 && b2 <= 256,
+              "make_tmap_3d_bf16: bad box / strides");
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(s1), static_cast<cuuint64_t>(s2)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1), static_cast<cuuint32_t>(b2)};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (3d) failed with CUresult %d", (int)r);
+    return DSG_ERR_CUDA;
+  }
+  return DSG_OK;
+}
+
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
   return make_tmap_2d(map, base, rows, cols, 2, BK, box_rows);
 }

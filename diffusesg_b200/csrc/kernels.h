@@ -100,6 +100,13 @@ int launch_block_head(const CUtensorMap* tmXin, const CUtensorMap* tmXout, const
 // qkv [B*res*res, 3*C] bf16 (q pre-scaled through the packed weights), layout per token [3][heads][32];
 // bias [heads, T, T] fp32 = gathered relative-position bias; mask [nW, T, T] fp32 (0 / -100) for shifted blocks,
 // nullptr otherwise; out [B*res*res, C] bf16 at the un-shifted token positions.
+int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2, int b0,
+                      int b1, int b2);
+// tcgen05 version for un-shifted 8 x 8 windows (attention_tc.cu): two windows per 128-row MMA tile, scores and
+// probabilities in tensor memory.  Returns DSG_ERR_INVALID for shapes it does not take.
+bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads);
+int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int heads,
+                               cudaStream_t st);
 int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
                             int window, int shift, int heads, cudaStream_t st);
 

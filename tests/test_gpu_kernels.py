@@ -93,7 +93,9 @@ def _attention_reference(qkv, bias, mask, batch, res, w, shift, heads):
 
 @pytest.mark.parametrize("batch,res,w,shift,heads", [
     (3, 16, 4, 0, 3), (3, 8, 4, 2, 6), (2, 64, 8, 0, 3), (5, 16, 8, 4, 12), (2, 8, 8, 0, 24),
-    (2, 20, 10, 5, 6), (3, 10, 10, 0, 12), (1, 32, 16, 8, 6), (2, 16, 16, 0, 12)])
+    (2, 20, 10, 5, 6), (3, 10, 10, 0, 12), (1, 32, 16, 8, 6), (2, 16, 16, 0, 12),
+    # un-shifted 8 x 8 windows with an even window count take the tcgen05 kernel (two windows per MMA tile)
+    (3, 16, 8, 0, 12), (4, 32, 8, 0, 6), (37, 16, 8, 0, 3), (1, 8, 8, 0, 3)])
 def test_window_attention_matches_torch(batch, res, w, shift, heads):
     g = torch.Generator(device=DEV).manual_seed(res * 100 + w + shift)
     c = heads * 32
