@@ -439,7 +439,7 @@ int launch_t(const bf16* qkv, const float* bias, const float* mask, bf16* out, i
 }  // namespace
 
 int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
-                            int window, int shift, int heads, cudaStream_t st) {
+                            int window, int shift, int heads, cudaStream_t st, int mask_canonical) {
   DSG_REQUIRE(res % window == 0 && shift >= 0 && shift < window, "attention: res %d window %d shift %d", res, window,
               shift);
   DSG_REQUIRE((shift > 0) == (mask != nullptr), "attention: a shifted block needs its mask (and only it)");
@@ -448,6 +448,11 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
   static const bool no_tc = getenv("DSG_NO_ATTN_TC") != nullptr && getenv("DSG_NO_ATTN_TC")[0] == '1';
   if (!no_tc && window_attention_tc_supported(batch, res, window, shift, heads))
     return launch_window_attention_tc(qkv, bias, out, batch, res, heads, st);  // un-shifted 8 x 8 windows: tcgen05
+  // one window per tile: pays off from 6 x 6 windows on (a shifted 8 x 8 window fills only half of its 128-row tile
+  // and the warp-MMA kernel below is faster: 190 vs 262 us on the VG shifted blocks)
+  if (!no_tc && window != 8 && (shift == 0 || mask_canonical == 1) &&
+      window_attention_quad_supported(batch, res, window, shift, heads))
+    return launch_window_attention_quad(qkv, bias, out, batch, res, window, shift, heads, st);
   if (window == 8) {
     const long long total = static_cast<long long>(batch) * (res / 8) * (res / 8);
     const long long grid = ((total + kWPC - 1) / kWPC) * heads;

@@ -292,6 +292,306 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
+
+// =================================================================================================
+// Quad-box version: ONE window per 128-row tile, for even windows up to 10 x 10 (COCO-Stuff: T = 100) with or
+// without the cyclic shift.  A w x w window is four (w/2) x (w/2) sub-boxes; sub-box (by, bx) is one TMA box and
+// lands in rows [32 (2 by + bx), +25) of the q / k / v tiles (rows beyond (w/2)^2 stay zero from the start-up fill).
+//   * a shifted window that wraps around the image edge splits exactly at its sub-box boundaries (shift = w/2), so
+//     torch.roll + window_partition / window_reverse + roll back (:248-250, :266-267) are TMA coordinates;
+//   * attention is invariant under a permutation of the window's tokens as long as the relative-position bias is
+//     permuted with it: the bias tile in shared memory is gathered in quad order (pad keys = -inf);
+//   * the SW-MSA mask (:207-222) is constant over a (query sub-box, key sub-box) pair: -100 where their region
+//     codes differ.  It enters as one scalar per 32-key chunk (the launcher only takes this kernel when the model's
+//     attn_mask buffer holds exactly those values).
+// Softmax runs in two passes over tensor memory (row max, then exp / sum / pack) in 32-key chunks; everything else
+// (roles, barriers, tensor-memory slots, P in place, MN-major V) is the un-shifted kernel above.
+// =================================================================================================
+constexpr int kQdBiasPitch = 132;  // floats per bias row: 16-byte aligned, conflict-free row-per-lane float4 reads
+constexpr int kQdGroups = 4;       // worker groups = items in flight = tensor-memory slots
+constexpr int kQdStages = 5;
+constexpr int kQdThreads = (4 * kQdGroups + 3) * 32;
+constexpr int kQdSlotCols = 128;   // S 128 columns; P aliases [0, 64), O aliases [64, 96) (dead once pass 2 has read them)
+constexpr int kQdSmemBytes = 1024 + kQdStages * kTcStageBytes + kQdGroups * 8192 + 128 * kQdBiasPitch * 4 + 512 /*barriers*/;
+static_assert(kQdSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct QdParams {
+  const float* bias;  // [heads, T, T], natural token order
+  int heads, res, w, hw, shift, nwx, nW, T;
+  int items;          // windows = B * nW
+};
+
+__global__ void __launch_bounds__(kQdThreads, 1)
+window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
+                             const QdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sStage = smem;
+  uint8_t* sOut = sStage + kQdStages * kTcStageBytes;                  // [groups][128 rows x 64 B]
+  float* sBias = reinterpret_cast<float*>(sOut + kQdGroups * 8192);    // [128][132], times log2(e)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128 * kQdBiasPitch);
+  uint64_t* stage_full = bars;
+  uint64_t* stage_empty = bars + kQdStages;
+  uint64_t* s_full = bars + 2 * kQdStages;
+  uint64_t* p_ready = s_full + kQdGroups;
+  uint64_t* o_full = s_full + 2 * kQdGroups;
+  uint64_t* slot_free = s_full + 3 * kQdGroups;
+  uint64_t* out_ready = s_full + 4 * kQdGroups;
+  uint64_t* out_free = s_full + 5 * kQdGroups;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6 * kQdGroups);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  constexpr int kLoadWarp = 4 * kQdGroups, kMmaWarp = kLoadWarp + 1, kStoreWarp = kLoadWarp + 2;
+  const int h = blockIdx.x % p.heads;
+  const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
+  const int n_items = (p.items > cta_in_head) ? (p.items - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
+  const int C = p.heads * 32;
+  const int hw = p.hw, sub = hw * hw;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  if (warp == kLoadWarp && lane == 0) {
+    tma_prefetch_desc(&tmQkv);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < kQdStages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
+    for (int g = 0; g < kQdGroups; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_ready[g], 4);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&slot_free[g], 4);
+      mbar_init(&out_ready[g], 4);
+      mbar_init(&out_free[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  // pad rows of every operand tile are zero for the whole kernel (the TMA boxes never touch them)
+  for (int i = threadIdx.x; i < kQdStages * kTcStageBytes / 16; i += kQdThreads)
+    reinterpret_cast<uint4*>(sStage)[i] = make_uint4(0u, 0u, 0u, 0u);
+  {
+    // bias tile in quad order; row / column r = 32 slot + (ry hw + rx)  <->  token (by hw + ry) w + (bx hw + rx)
+    const float* bh = p.bias + static_cast<size_t>(h) * p.T * p.T;
+    auto token = [&](int r) {
+      const int slot = r >> 5, i = r & 31;
+      if (i >= sub) return -1;
+      const int ry = i / hw, rx = i - ry * hw;
+      return ((slot >> 1) * hw + ry) * p.w + (slot & 1) * hw + rx;
+    };
+    for (int i = threadIdx.x; i < 128 * 128; i += kQdThreads) {
+      const int rq = i >> 7, rk = i & 127;
+      const int tq = token(rq), tk = token(rk);
+      float v = 0.f;
+      if (tk < 0) v = -INFINITY;
+      else if (tq >= 0) v = bh[static_cast<size_t>(tq) * p.T + tk] * kLog2e;
+      sBias[rq * kQdBiasPitch + rk] = v;
+    }
+  }
+  fence_proxy_async_smem();  // the zero fill (generic proxy) is ordered before the TMA writes into the same tiles
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  // sub-box (by, bx) of window gw -> TMA coordinates (token column, token row of the [B res, res] grid)
+  auto box_coords = [&](int gw, int slot, int& cx, int& cy) {
+    const int b = gw / p.nW, win = gw - b * p.nW;
+    const int wy = win / p.nwx, wx = win - wy * p.nwx;
+    int oy = wy * p.w + (slot >> 1) * hw + p.shift;
+    int ox = wx * p.w + (slot & 1) * hw + p.shift;
+    if (oy >= p.res) oy -= p.res;
+    if (ox >= p.res) ox -= p.res;
+    cx = ox;
+    cy = b * p.res + oy;
+  };
+
+  if (warp == kLoadWarp) {
+    // ------------------------------------------------------------------ loader (lanes 0..11: one box each)
+    const uint32_t box_bytes = static_cast<uint32_t>(sub) * 64u;
+    for (int k = 0; k < n_items; ++k) {
+      const int st = k % kQdStages;
+      const int gw = cta_in_head + k * ctas_per_head;
+      mbar_wait(&stage_empty[st], ((k / kQdStages) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&stage_full[st], 12u * box_bytes);
+      __syncwarp();
+      if (lane < 12) {
+        const int part = lane >> 2, slot = lane & 3;
+        int cx, cy;
+        box_coords(gw, slot, cx, cy);
+        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + slot * 2048, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128);
+    constexpr uint32_t idesc_o = idesc_bf16_bmn(32);
+    auto issue_s = [&](int k) {
+      const int st = k % kQdStages, g = k % kQdGroups;
+      mbar_wait(&stage_full[st], (k / kQdStages) & 1);
+      mbar_wait(&slot_free[g], ((k / kQdGroups) & 1) ^ 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t da = desc_sw64_kmajor(smem_u32(sStage + st * kTcStageBytes));
+        const uint64_t db = desc_sw64_kmajor(smem_u32(sStage + st * kTcStageBytes + 8192));
+        for (int ks = 0; ks < 2; ++ks) umma_bf16_ss(tmem_base + g * kQdSlotCols, da + 2 * ks, db + 2 * ks, idesc_s, ks != 0);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int k) {
+      const int st = k % kQdStages, g = k % kQdGroups;
+      mbar_wait(&p_ready[g], (k / kQdGroups) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc_sw64_mnmajor(smem_u32(sStage + st * kTcStageBytes + 16384));
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ts_tc(tmem_base + g * kQdSlotCols + 64, tmem_base + g * kQdSlotCols + ks * 8, dv + 64 * ks, idesc_o, ks != 0);
+        umma_commit(&o_full[g]);
+        umma_commit(&stage_empty[st]);
+      }
+      __syncwarp();
+    };
+    for (int k = 0; k < kQdGroups - 1; ++k)
+      if (k < n_items) issue_s(k);
+    for (int k = 0; k < n_items; ++k) {
+      issue_pv(k);
+      if (k + kQdGroups - 1 < n_items) issue_s(k + kQdGroups - 1);
+    }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------------ storer
+    if (elect_one()) {
+      for (int k = 0; k < n_items; ++k) {
+        const int g = k % kQdGroups;
+        const int gw = cta_in_head + k * ctas_per_head;
+        mbar_wait(&out_ready[g], (k / kQdGroups) & 1);
+        for (int slot = 0; slot < 4; ++slot) {
+          int cx, cy;
+          box_coords(gw, slot, cx, cy);
+          tma_store_3d(&tmOut, sOut + g * 8192 + slot * 2048, h * 32, cx, cy);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&out_free[g]);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ------------------------------------------------------------------ worker groups
+    const int g = warp >> 2, q = warp & 3;   // q = tensor-memory lane quarter = the query's sub-box
+    const int r = q * 32 + lane;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kQdSlotCols;
+    const float* brow = sBias + r * kQdBiasPitch;
+    for (int k = g, it = 0; k < n_items; k += kQdGroups, ++it) {
+      // SW-MSA mask of this window, per key sub-box j (times log2 e): -100 where the region codes differ
+      float mk[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.shift > 0) {
+        const int gw = cta_in_head + k * ctas_per_head;
+        const int win = gw % p.nW;
+        const int wy = win / p.nwx, wx = win - wy * p.nwx;
+        const int last_r = (wy == p.nwx - 1) ? 2 : 0, last_c = (wx == p.nwx - 1) ? 1 : 0;
+        const int code_q = (q & last_r) | (q & last_c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk[j] = (((j & last_r) | (j & last_c)) != code_q) ? -100.f * kLog2e : 0.f;
+      }
+      mbar_wait(&s_full[g], it & 1);
+      tcgen05_fence_after();
+      // ---- pass 1: row maximum of  s log2(e) + bias'  (+ mask per chunk)
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t sv[32];
+        tmem_ld_32x32(t_s + 32 * j, sv);
+        tmem_ld_wait();
+        float mj = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * j + c);
+          const float a0 = fmaf(__uint_as_float(sv[c]), kLog2e, bb.x), a1 = fmaf(__uint_as_float(sv[c + 1]), kLog2e, bb.y);
+          const float a2 = fmaf(__uint_as_float(sv[c + 2]), kLog2e, bb.z), a3 = fmaf(__uint_as_float(sv[c + 3]), kLog2e, bb.w);
+          mj = fmaxf(mj, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+        }
+        m = fmaxf(m, mj + mk[j]);
+      }
+      // ---- pass 2: p = exp2(. - m), row sum, bf16 pairs written in place over the scores already consumed
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t sv[32];
+        tmem_ld_32x32(t_s + 32 * j, sv);
+        tmem_ld_wait();
+        const float cj = mk[j] - m;
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * j + c);
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c]), kLog2e, bb.x) + cj);
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), kLog2e, bb.y) + cj);
+          const float e2 = ex2_approx(fmaf(__uint_as_float(sv[c + 2]), kLog2e, bb.z) + cj);
+          const float e3 = ex2_approx(fmaf(__uint_as_float(sv[c + 3]), kLog2e, bb.w) + cj);
+          l += (e0 + e1) + (e2 + e3);
+          pk[c >> 1] = pack_bf16x2(e0, e1);
+          pk[(c >> 1) + 1] = pack_bf16x2(e2, e3);
+        }
+        tmem_st8_tc(t_s + 16 * j, pk);
+        tmem_st8_tc(t_s + 16 * j + 8, pk + 8);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      // ---- output: O / l -> bf16 -> swizzled staging (64-byte rows: chunk ^= (row >> 1) & 3)
+      const float inv = rcp_approx(l);
+      mbar_wait(&o_full[g], it & 1);
+      tcgen05_fence_after();
+      uint32_t ov[32];
+      tmem_ld_32x32(t_s + 64, ov);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      mbar_wait(&out_free[g], (it & 1) ^ 1);
+      uint8_t* orow = sOut + g * 8192 + r * 64;
+      const int sw = (r >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 o4;
+        o4.x = pack_bf16x2(__uint_as_float(ov[8 * c]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
+        o4.y = pack_bf16x2(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
+        o4.z = pack_bf16x2(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
+        o4.w = pack_bf16x2(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o4;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_ready[g]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+// attn_mask buffer == the SW-MSA mask the reference constructs (model/diffusesg/diffusesg.py:207-222)?
+__global__ void mask_canonical_kernel(const float* __restrict__ mask, int nwx, int w, int shift, int* __restrict__ bad) {
+  const int T = w * w;
+  const long long total = static_cast<long long>(nwx) * nwx * T * T;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tk = static_cast<int>(i % T);
+    const int tq = static_cast<int>((i / T) % T);
+    const int win = static_cast<int>(i / (static_cast<long long>(T) * T));
+    const int wy = win / nwx, wx = win - wy * nwx;
+    auto code = [&](int t) {
+      const int ty = t / w, tx = t - ty * w;
+      return ((wy == nwx - 1 && ty >= w - shift) ? 2 : 0) | ((wx == nwx - 1 && tx >= w - shift) ? 1 : 0);
+    };
+    const float want = code(tq) != code(tk) ? -100.f : 0.f;
+    if (mask[i] != want) atomicOr(bad, 1);
+  }
+}
+
 }  // namespace
 
 bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads) {
@@ -333,6 +633,75 @@ int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, in
   if (per_head > p.pairs) per_head = p.pairs;
   if (per_head < 1) per_head = 1;
   window_attention_tc_kernel<<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+// ---- quad-box kernel (one window per tile): even windows up to 10 x 10, shift 0 or w / 2
+bool window_attention_quad_supported(int batch, int res, int window, int shift, int heads) {
+  if (window < 2 || window > 10 || (window & 1) || res % window != 0 || heads < 1 || heads > 74) return false;
+  if (shift != 0 && shift != window / 2) return false;
+  return batch >= 1;
+}
+
+// Synchronous (model finalisation / the building-block entry point, never inside a denoiser pass).
+int check_mask_canonical(const float* mask, int res, int window, int shift, cudaStream_t st, int* canonical) {
+  int* d_bad = nullptr;
+  DSG_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    mask_canonical_kernel<<<148, 256, 0, st>>>(mask, res / window, window, shift, d_bad);
+    e = cudaGetLastError();
+  }
+  int bad = 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_bad);
+  DSG_CUDA_CHECK(e);
+  count_launch();
+  *canonical = bad ? 0 : 1;
+  return DSG_OK;
+}
+
+int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
+                                 int heads, cudaStream_t st) {
+  DSG_REQUIRE(window_attention_quad_supported(batch, res, window, shift, heads), "attention_quad: unsupported shape");
+  const int C = heads * 32;
+  const int hw = window / 2;
+  CUtensorMap tq, to;
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, hw, hw))
+    return rc;
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, hw, hw))
+    return rc;
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  QdParams p;
+  p.bias = bias;
+  p.heads = heads;
+  p.res = res;
+  p.w = window;
+  p.hw = hw;
+  p.shift = shift;
+  p.nwx = res / window;
+  p.nW = p.nwx * p.nwx;
+  p.T = window * window;
+  const long long items = static_cast<long long>(batch) * p.nW;
+  DSG_REQUIRE(items < 2147483647LL, "attention_quad: too many windows");
+  p.items = static_cast<int>(items);
+  int per_head = sms / heads;
+  if (per_head > p.items) per_head = p.items;
+  if (per_head < 1) per_head = 1;
+  window_attention_quad_kernel<<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

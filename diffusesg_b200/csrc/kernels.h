@@ -107,8 +107,16 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t d0, int64_t d1
 bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads);
 int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int heads,
                                cudaStream_t st);
+// quad-box tcgen05 version (one window per tile): even windows up to 10 x 10, shift 0 or window / 2; the SW-MSA mask
+// is generated in the kernel, so a shifted block may only take it when check_mask_canonical() found the model's
+// attn_mask buffer equal to the reference's construction (synchronous; called at model finalisation).
+bool window_attention_quad_supported(int batch, int res, int window, int shift, int heads);
+int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
+                                 int heads, cudaStream_t st);
+int check_mask_canonical(const float* mask, int res, int window, int shift, cudaStream_t st, int* canonical);
+// mask_canonical: 1 if `mask` is known to hold the reference's SW-MSA values (ignored for un-shifted blocks)
 int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
-                            int window, int shift, int heads, cudaStream_t st);
+                            int window, int shift, int heads, cudaStream_t st, int mask_canonical = 0);
 
 // ---------------------------------------------------------------------------------------------
 // row kernels: LayerNorm / FiLM / merge / breakup / embed / heads       (rowops.cu)

@@ -95,7 +95,11 @@ def _attention_reference(qkv, bias, mask, batch, res, w, shift, heads):
     (3, 16, 4, 0, 3), (3, 8, 4, 2, 6), (2, 64, 8, 0, 3), (5, 16, 8, 4, 12), (2, 8, 8, 0, 24),
     (2, 20, 10, 5, 6), (3, 10, 10, 0, 12), (1, 32, 16, 8, 6), (2, 16, 16, 0, 12),
     # un-shifted 8 x 8 windows with an even window count take the tcgen05 kernel (two windows per MMA tile)
-    (3, 16, 8, 0, 12), (4, 32, 8, 0, 6), (37, 16, 8, 0, 3), (1, 8, 8, 0, 3)])
+    (3, 16, 8, 0, 12), (4, 32, 8, 0, 6), (37, 16, 8, 0, 3), (1, 8, 8, 0, 3),
+    # even windows up to 10 x 10, shifted or not, take the quad-box tcgen05 kernel (one window per tile; the COCO-Stuff
+    # geometry: 10 x 10 windows at res 40 / 20 / 10, shift 5 at res 20; the VG shifted blocks: 8 x 8, shift 4 at res 16)
+    (2, 40, 10, 0, 3), (3, 20, 10, 0, 6), (5, 20, 10, 5, 6), (1, 30, 10, 5, 3), (7, 16, 8, 4, 12), (3, 24, 8, 4, 3),
+    (2, 12, 6, 3, 3), (41, 10, 10, 0, 24)])
 def test_window_attention_matches_torch(batch, res, w, shift, heads):
     g = torch.Generator(device=DEV).manual_seed(res * 100 + w + shift)
     c = heads * 32
@@ -112,6 +116,22 @@ def test_window_attention_matches_torch(batch, res, w, shift, heads):
     assert torch.isfinite(got).all()
     assert _rel(got, want) < 1e-2, _rel(got, want)   # p is rounded to bf16 before p.v, output stored as bf16
     assert float((got - want).abs().max()) < 5e-2
+
+
+def test_window_attention_arbitrary_mask_takes_the_generic_kernel():
+    """The tcgen05 kernels generate the SW-MSA mask themselves; a mask buffer with other values must still be honoured
+    (the launcher checks the buffer and falls back to the kernel that reads it)."""
+    batch, res, w, shift, heads = 3, 20, 10, 5, 6
+    g = torch.Generator(device=DEV).manual_seed(5)
+    c, t = heads * 32, w * w
+    qkv = torch.randn(batch * res * res, 3 * c, device=DEV, generator=g)
+    qkv[:, :c] *= 32 ** -0.5
+    qkv = qkv.to(torch.bfloat16)
+    bias = torch.randn(heads, t, t, device=DEV, generator=g) * 0.3
+    mask = shifted_window_mask(res, w, shift).to(DEV) * 0.05 + torch.randn(4, t, t, device=DEV, generator=g) * 0.2
+    want = _attention_reference(qkv, bias, mask, batch, res, w, shift, heads)
+    got = native.window_attention(qkv, bias, mask.contiguous(), batch, res, w, shift, heads).float()
+    assert _rel(got, want) < 1e-2, _rel(got, want)
 
 
 # ---------------------------------------------------------------------------------------------------------
