@@ -321,6 +321,7 @@ struct QdParams {
   int items;          // windows = B * nW
 };
 
+template <int HW>  // sub-box edge = window / 2
 __global__ void __launch_bounds__(kQdThreads, 1)
 window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
                              const QdParams p) {
@@ -347,7 +348,9 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
   const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
   const int n_items = (p.items > cta_in_head) ? (p.items - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
   const int C = p.heads * 32;
-  const int hw = p.hw, sub = hw * hw;
+  constexpr int hw = HW, sub = HW * HW;
+  constexpr int SUB = HW * HW;               // valid rows / key columns per 32-row sub-box slot
+  constexpr int NVC = ((SUB + 3) / 4) * 4;   // key columns the softmax touches per slot (pads inside carry bias -inf)
   constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == kLoadWarp && lane == 0) {
@@ -481,66 +484,95 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
     const int r = q * 32 + lane;
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kQdSlotCols;
     const float* brow = sBias + r * kQdBiasPitch;
+    // largest bias of this row: with the largest raw score it bounds the row maximum from above, so the first pass
+    // needs neither the bias nor a multiply (the bound is at most range(bias) above the true maximum: no underflow)
+    float bmax = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int c = 0; c < SUB; ++c) bmax = fmaxf(bmax, brow[32 * jj + c]);
+    const f32x2 l2e2 = f2_splat(kLog2e);
     for (int k = g, it = 0; k < n_items; k += kQdGroups, ++it) {
       // SW-MSA mask of this window, per key sub-box j (times log2 e): -100 where the region codes differ
-      float mk[4] = {0.f, 0.f, 0.f, 0.f};
+      float mk0 = 0.f, mk1 = 0.f, mk2 = 0.f, mk3 = 0.f;
       if (p.shift > 0) {
         const int gw = cta_in_head + k * ctas_per_head;
         const int win = gw % p.nW;
         const int wy = win / p.nwx, wx = win - wy * p.nwx;
-        const int last_r = (wy == p.nwx - 1) ? 2 : 0, last_c = (wx == p.nwx - 1) ? 1 : 0;
-        const int code_q = (q & last_r) | (q & last_c);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mk[j] = (((j & last_r) | (j & last_c)) != code_q) ? -100.f * kLog2e : 0.f;
+        const int sel = ((wy == p.nwx - 1) ? 2 : 0) | ((wx == p.nwx - 1) ? 1 : 0);
+        const int code_q = q & sel;
+        constexpr float kMasked = -100.f * kLog2e;
+        mk0 = ((0 & sel) != code_q) ? kMasked : 0.f;
+        mk1 = ((1 & sel) != code_q) ? kMasked : 0.f;
+        mk2 = ((2 & sel) != code_q) ? kMasked : 0.f;
+        mk3 = ((3 & sel) != code_q) ? kMasked : 0.f;
       }
       mbar_wait(&s_full[g], it & 1);
       tcgen05_fence_after();
-      // ---- pass 1: row maximum of  s log2(e) + bias'  (+ mask per chunk)
-      float m = -INFINITY;
+      uint32_t bufA[32], bufB[32];
+      auto row_max = [&](const uint32_t (&sv)[32]) {
+        float m0 = __uint_as_float(sv[0]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t sv[32];
-        tmem_ld_32x32(t_s + 32 * j, sv);
-        tmem_ld_wait();
-        float mj = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * j + c);
-          const float a0 = fmaf(__uint_as_float(sv[c]), kLog2e, bb.x), a1 = fmaf(__uint_as_float(sv[c + 1]), kLog2e, bb.y);
-          const float a2 = fmaf(__uint_as_float(sv[c + 2]), kLog2e, bb.z), a3 = fmaf(__uint_as_float(sv[c + 3]), kLog2e, bb.w);
-          mj = fmaxf(mj, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
-        }
-        m = fmaxf(m, mj + mk[j]);
-      }
-      // ---- pass 2: p = exp2(. - m), row sum, bf16 pairs written in place over the scores already consumed
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t sv[32];
-        tmem_ld_32x32(t_s + 32 * j, sv);
-        tmem_ld_wait();
-        const float cj = mk[j] - m;
+        for (int c = 1; c < SUB; ++c) m0 = fmaxf(m0, __uint_as_float(sv[c]));
+        return m0;
+      };
+      // ---- pass 1: upper bound of the row maximum of  s log2(e) + bias' + mask
+      tmem_ld_32x32(t_s, bufA);
+      tmem_ld_32x32(t_s + 32, bufB);
+      tmem_ld_wait();
+      float m = fmaxf(fmaf(row_max(bufA), kLog2e, mk0), fmaf(row_max(bufB), kLog2e, mk1));
+      tmem_ld_32x32(t_s + 64, bufA);
+      tmem_ld_32x32(t_s + 96, bufB);
+      tmem_ld_wait();
+      m = fmaxf(m, fmaxf(fmaf(row_max(bufA), kLog2e, mk2), fmaf(row_max(bufB), kLog2e, mk3))) + bmax;
+      // ---- pass 2: p = exp2(. - m) on packed pairs, row sum, bf16 pairs written in place over consumed scores
+      f32x2 lsum = f2_splat(0.f);
+      auto chunk = [&](const uint32_t (&sv)[32], int jj, float mkj) {
+        const f32x2 cj = f2_splat(mkj - m);
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * j + c);
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c]), kLog2e, bb.x) + cj);
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), kLog2e, bb.y) + cj);
-          const float e2 = ex2_approx(fmaf(__uint_as_float(sv[c + 2]), kLog2e, bb.z) + cj);
-          const float e3 = ex2_approx(fmaf(__uint_as_float(sv[c + 3]), kLog2e, bb.w) + cj);
-          l += (e0 + e1) + (e2 + e3);
-          pk[c >> 1] = pack_bf16x2(e0, e1);
-          pk[(c >> 1) + 1] = pack_bf16x2(e2, e3);
+          if (c < NVC) {
+            const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * jj + c);
+            f32x2 t0 = f2_fma(f2_pack(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), l2e2, f2_pack(bb.x, bb.y));
+            f32x2 t1 = f2_fma(f2_pack(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), l2e2, f2_pack(bb.z, bb.w));
+            t0 = f2_add(t0, cj);
+            t1 = f2_add(t1, cj);
+            float a0, a1, a2, a3;
+            f2_unpack(t0, a0, a1);
+            f2_unpack(t1, a2, a3);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1), e2 = ex2_approx(a2), e3 = ex2_approx(a3);
+            lsum = f2_add(lsum, f2_add(f2_pack(e0, e1), f2_pack(e2, e3)));
+            pk[c >> 1] = pack_bf16x2(e0, e1);
+            pk[(c >> 1) + 1] = pack_bf16x2(e2, e3);
+          } else {
+            pk[c >> 1] = 0u;   // pad keys: P must be a clean zero (the columns still hold score bits)
+            pk[(c >> 1) + 1] = 0u;
+          }
         }
-        tmem_st8_tc(t_s + 16 * j, pk);
-        tmem_st8_tc(t_s + 16 * j + 8, pk + 8);
-      }
+        tmem_st8_tc(t_s + 16 * jj, pk);
+        tmem_st8_tc(t_s + 16 * jj + 8, pk + 8);
+      };
+      tmem_ld_32x32(t_s, bufA);
+      tmem_ld_wait();
+      tmem_ld_32x32(t_s + 32, bufB);
+      chunk(bufA, 0, mk0);
+      tmem_ld_wait();
+      tmem_ld_32x32(t_s + 64, bufA);
+      chunk(bufB, 1, mk1);
+      tmem_ld_wait();
+      tmem_ld_32x32(t_s + 96, bufB);
+      chunk(bufA, 2, mk2);
+      tmem_ld_wait();
+      chunk(bufB, 3, mk3);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
       // ---- output: O / l -> bf16 -> swizzled staging (64-byte rows: chunk ^= (row >> 1) & 3)
-      const float inv = rcp_approx(l);
+      float l0, l1;
+      f2_unpack(lsum, l0, l1);
+      const float inv = rcp_approx(l0 + l1);
       mbar_wait(&o_full[g], it & 1);
       tcgen05_fence_after();
       uint32_t ov[32];
@@ -552,13 +584,14 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
       mbar_wait(&out_free[g], (it & 1) ^ 1);
       uint8_t* orow = sOut + g * 8192 + r * 64;
       const int sw = (r >> 1) & 3;
+      const f32x2 inv2 = f2_splat(inv);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 o4;
-        o4.x = pack_bf16x2(__uint_as_float(ov[8 * c]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
-        o4.y = pack_bf16x2(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
-        o4.z = pack_bf16x2(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
-        o4.w = pack_bf16x2(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+        o4.x = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c]), __uint_as_float(ov[8 * c + 1])), inv2));
+        o4.y = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3])), inv2));
+        o4.z = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5])), inv2));
+        o4.w = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7])), inv2));
         *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o4;
       }
       fence_proxy_async_smem();
@@ -673,11 +706,6 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
     return rc;
   if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, hw, hw))
     return rc;
-  static bool configured = false;
-  if (!configured) {
-    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));
-    configured = true;
-  }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -701,7 +729,28 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
   int per_head = sms / heads;
   if (per_head > p.items) per_head = p.items;
   if (per_head < 1) per_head = 1;
-  window_attention_quad_kernel<<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);
+  switch (hw) {
+#define DSG_QUAD_CASE(H)                                                                                                  \
+  case H: {                                                                                                               \
+    static bool configured = false;                                                                                       \
+    if (!configured) {                                                                                                    \
+      DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                          kQdSmemBytes));                                                                 \
+      configured = true;                                                                                                  \
+    }                                                                                                                     \
+    window_attention_quad_kernel<H><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);                       \
+    break;                                                                                                                \
+  }
+    DSG_QUAD_CASE(1)
+    DSG_QUAD_CASE(2)
+    DSG_QUAD_CASE(3)
+    DSG_QUAD_CASE(4)
+    DSG_QUAD_CASE(5)
+#undef DSG_QUAD_CASE
+    default:
+      set_last_error("attention_quad: window %d", window);
+      return DSG_ERR_INVALID;
+  }
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
