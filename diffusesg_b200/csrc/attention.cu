@@ -450,9 +450,12 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
     return launch_window_attention_tc(qkv, bias, out, batch, res, heads, st);  // un-shifted 8 x 8 windows: tcgen05
   // one window per tile: pays off from 6 x 6 windows on (a shifted 8 x 8 window fills only half of its 128-row tile
   // and the warp-MMA kernel below is faster: 190 vs 262 us on the VG shifted blocks)
-  if (!no_tc && window != 8 && (shift == 0 || mask_canonical == 1) &&
-      window_attention_quad_supported(batch, res, window, shift, heads))
+  const bool mask_ok = shift == 0 || (mask_canonical & ATTN_MASK_CANONICAL) != 0;
+  if (!no_tc && window != 8 && mask_ok && window_attention_quad_supported(batch, res, window, shift, heads))
     return launch_window_attention_quad(qkv, bias, out, batch, res, window, shift, heads, st);
+  if (!no_tc && mask_ok && (mask_canonical & ATTN_BIAS_TOEPLITZ) != 0 &&
+      window_attention_w16_supported(batch, res, window, shift, heads))
+    return launch_window_attention_w16(qkv, bias, out, batch, res, shift, heads, st);  // 16 x 16 windows
   if (window == 8) {
     const long long total = static_cast<long long>(batch) * (res / 8) * (res / 8);
     const long long grid = ((total + kWPC - 1) / kWPC) * heads;

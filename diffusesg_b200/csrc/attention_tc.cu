@@ -606,6 +606,325 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
+// =================================================================================================
+// 16 x 16 windows (T = 256; BASELINE config 5): the quad-box scheme with 64-token sub-boxes.  An item is one HALF
+// of a window-head: 128 query rows (sub-boxes 2 half, 2 half + 1) against all 256 keys:
+//   S[128 x 256] = Q K^T   (N = 256, two K steps)       256 tensor-memory columns per slot, two slots in flight
+//   a group is 8 warps: two per tensor-memory lane quarter, each owning 128 of the 256 keys (row-max bound and row
+//   sum exchanged through shared memory); P of key half c in place over S columns [128 c, 128 c + 64) - each warp
+//   only overwrites scores it has consumed itself - and O[128 x 32] over S columns [192, 224); 16 TS-mode steps
+// The relative-position bias no longer fits in shared memory as a [T, T] tile (256 KB), so it is looked up from the
+// head's (2w - 1)^2 table: with the table stored x-reversed, the 8 keys of one token row of a sub-box are 8
+// CONSECUTIVE floats for any query, and a thread's alignment class (x_q + 1) mod 4 never changes, so it reads one of
+// four pre-shifted copies with float4 loads.  This needs bias[h][q][k] to depend on the offset only - which the
+// launcher takes from check_bias_toeplitz() (true for the reference's relative_position_index).
+// The exp2 count (32768 per item) makes this kernel MUFU-bound at ~2050 clk per item.
+// =================================================================================================
+constexpr int kW16Groups = 2;
+constexpr int kW16Stages = 3;
+constexpr int kW16StageBytes = 8192 + 16384 + 16384;  // q (128 rows) | k (256) | v (256)
+constexpr int kW16Threads = (8 * kW16Groups + 3) * 32;  // a group = 8 warps: two per lane quarter, 128 keys each
+constexpr int kW16SlotCols = 256;
+constexpr int kW16TabPitch = 36;                       // floats per table row (31 + up to 3 of shift, 16-byte multiple)
+constexpr int kW16TabCopy = 1120;                      // floats between the shifted copies (31 x 36 = 1116 -> multiple of 32)
+constexpr int kW16TabFloats = 4 * kW16TabCopy + 32;    // four shifted copies
+// bank offset of copy s: the 8 lanes of a quarter warp (one query token row) read the float4 at position 16, 12 or 8 of
+// copies (1, 2, 3, 0, 1, 2, 3, 0); with these offsets the eight reads fall into eight different 16-byte bank groups
+__device__ __forceinline__ int w16_copy_base(int s) { return s * kW16TabCopy + ((0x140C0400 >> (8 * s)) & 0xFF); }
+constexpr int kW16ExFloats = 2 * kW16Groups * 2 * 128;  // row-max bounds and row sums exchanged between the key halves
+constexpr int kW16SmemBytes = 1024 + kW16Stages * kW16StageBytes + kW16Groups * 8192 + (kW16TabFloats + kW16ExFloats) * 4 + 512;
+static_assert(kW16SmemBytes <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(kW16Threads, 1)
+window_attention_w16_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
+                            const QdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sStage = smem;
+  uint8_t* sOut = sStage + kW16Stages * kW16StageBytes;                // [groups][128 rows x 64 B]
+  float* sTab = reinterpret_cast<float*>(sOut + kW16Groups * 8192);    // [4 shifts][31 dy][36], times log2(e)
+  float* sExM = sTab + kW16TabFloats;                                  // [groups][2 key halves][128 rows]
+  float* sExL = sExM + kW16Groups * 2 * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sExL + kW16Groups * 2 * 128);
+  uint64_t* stage_full = bars;
+  uint64_t* stage_empty = bars + kW16Stages;
+  uint64_t* s_full = bars + 2 * kW16Stages;
+  uint64_t* p_ready = s_full + kW16Groups;
+  uint64_t* o_full = s_full + 2 * kW16Groups;
+  uint64_t* slot_free = s_full + 3 * kW16Groups;
+  uint64_t* out_ready = s_full + 4 * kW16Groups;
+  uint64_t* out_free = s_full + 5 * kW16Groups;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6 * kW16Groups);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  constexpr int kLoadWarp = 8 * kW16Groups, kMmaWarp = kLoadWarp + 1, kStoreWarp = kLoadWarp + 2;
+  const int h = blockIdx.x % p.heads;
+  const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
+  const int n_win = (p.items > cta_in_head) ? (p.items - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
+  const int n_items = 2 * n_win;  // item k = (window cta_in_head + (k / 2) ctas_per_head, query half k & 1)
+  const int C = p.heads * 32;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  if (warp == kLoadWarp && lane == 0) {
+    tma_prefetch_desc(&tmQkv);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < kW16Stages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
+    for (int g = 0; g < kW16Groups; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_ready[g], 8);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&slot_free[g], 8);
+      mbar_init(&out_ready[g], 8);
+      mbar_init(&out_free[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  {
+    // tab[s][dy + 15][(15 - dx) + s] = bias(dy, dx) log2(e)  with (dy, dx) = (y_q - y_k, x_q - x_k); pads = 0
+    const float* bh = p.bias + static_cast<size_t>(h) * 256 * 256;
+    for (int i = threadIdx.x; i < kW16TabFloats; i += kW16Threads) sTab[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 31 * 31; i += kW16Threads) {
+      const int sft = i / (31 * 31), rem = i - sft * 31 * 31;
+      const int dy = rem / 31 - 15, dx = rem % 31 - 15;
+      const int yq = dy > 0 ? dy : 0, yk = yq - dy, xq = dx > 0 ? dx : 0, xk = xq - dx;
+      sTab[w16_copy_base(sft) + (dy + 15) * kW16TabPitch + (15 - dx) + sft] = bh[static_cast<size_t>(yq * 16 + xq) * 256 + yk * 16 + xk] * kLog2e;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  // sub-box `slot` (by = slot >> 1, bx = slot & 1) of window gw -> TMA coordinates of its 8 x 8 token box
+  auto box_coords = [&](int gw, int slot, int& cx, int& cy) {
+    const int b = gw / p.nW, win = gw - b * p.nW;
+    const int wy = win / p.nwx, wx = win - wy * p.nwx;
+    int oy = wy * 16 + (slot >> 1) * 8 + p.shift;
+    int ox = wx * 16 + (slot & 1) * 8 + p.shift;
+    if (oy >= p.res) oy -= p.res;
+    if (ox >= p.res) ox -= p.res;
+    cx = ox;
+    cy = b * p.res + oy;
+  };
+
+  if (warp == kLoadWarp) {
+    // ------------------------------------------------------------------ loader (lanes 0..9: one 4 KB box each)
+    for (int k = 0; k < n_items; ++k) {
+      const int st = k % kW16Stages;
+      const int gw = cta_in_head + (k >> 1) * ctas_per_head, half = k & 1;
+      mbar_wait(&stage_empty[st], ((k / kW16Stages) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&stage_full[st], kW16StageBytes);
+      __syncwarp();
+      if (lane < 10) {
+        // lanes 0, 1: q sub-boxes 2 half, 2 half + 1; lanes 2..5: k; lanes 6..9: v
+        const int part = lane < 2 ? 0 : (lane < 6 ? 1 : 2);
+        const int slot = lane < 2 ? 2 * half + lane : (lane - 2) & 3;
+        const int dst = lane < 2 ? lane * 4096 : (part == 1 ? 8192 : 24576) + slot * 4096;
+        int cx, cy;
+        box_coords(gw, slot, cx, cy);
+        tma_load_3d(sStage + st * kW16StageBytes + dst, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(256);
+    constexpr uint32_t idesc_o = idesc_bf16_bmn(32);
+    auto issue_s = [&](int k) {
+      const int st = k % kW16Stages, g = k % kW16Groups;
+      mbar_wait(&stage_full[st], (k / kW16Stages) & 1);
+      mbar_wait(&slot_free[g], ((k / kW16Groups) & 1) ^ 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t da = desc_sw64_kmajor(smem_u32(sStage + st * kW16StageBytes));
+        const uint64_t db = desc_sw64_kmajor(smem_u32(sStage + st * kW16StageBytes + 8192));
+        for (int ks = 0; ks < 2; ++ks) umma_bf16_ss(tmem_base + g * kW16SlotCols, da + 2 * ks, db + 2 * ks, idesc_s, ks != 0);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int k) {
+      const int st = k % kW16Stages, g = k % kW16Groups;
+      mbar_wait(&p_ready[g], (k / kW16Groups) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t dv = desc_sw64_mnmajor(smem_u32(sStage + st * kW16StageBytes + 24576));
+        for (int ks = 0; ks < 16; ++ks)  // 16 keys per step: 8 packed P columns, 16 V rows (1024 bytes)
+          umma_ts_tc(tmem_base + g * kW16SlotCols + 192, tmem_base + g * kW16SlotCols + (ks >> 3) * 128 + (ks & 7) * 8,
+                     dv + 64 * ks, idesc_o, ks != 0);
+        umma_commit(&o_full[g]);
+        umma_commit(&stage_empty[st]);
+      }
+      __syncwarp();
+    };
+    if (n_items > 0) issue_s(0);
+    for (int k = 0; k < n_items; ++k) {
+      if (k + 1 < n_items) issue_s(k + 1);
+      issue_pv(k);
+    }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------------ storer
+    if (elect_one()) {
+      for (int k = 0; k < n_items; ++k) {
+        const int g = k % kW16Groups;
+        const int gw = cta_in_head + (k >> 1) * ctas_per_head, half = k & 1;
+        mbar_wait(&out_ready[g], (k / kW16Groups) & 1);
+        for (int bx = 0; bx < 2; ++bx) {
+          int cx, cy;
+          box_coords(gw, 2 * half + bx, cx, cy);
+          tma_store_3d(&tmOut, sOut + g * 8192 + bx * 4096, h * 32, cx, cy);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&out_free[g]);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ------------------------------------------------------------------ worker groups
+    // warp = 8 g + 4 ch + q: lane quarter q (query rows 32 q ..), key half ch (keys 128 ch .. = sub-boxes 2 ch, 2 ch + 1)
+    const int g = warp >> 3, q = warp & 3, ch = (warp >> 2) & 1;
+    const int r = q * 32 + lane;                  // query row of the 128-row tile
+    const int bxq = r >> 6, ryq = (r >> 3) & 7, rxq = r & 7;
+    const int xq = bxq * 8 + rxq;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kW16SlotCols;
+    const int sft = (xq + 1) & 3;
+    const float* tab = sTab + w16_copy_base(sft) + (15 - xq + sft);  // + dy row, + x_k: 16-byte aligned at x_k % 8 == 0
+    float bmax = -INFINITY;
+    for (int dy = 0; dy < 31; ++dy)
+      for (int dx = 0; dx < 31; ++dx) bmax = fmaxf(bmax, sTab[dy * kW16TabPitch + dx]);
+    float* exm = sExM + g * 256, *exl = sExL + g * 256;
+    const int bar_id = 1 + g;
+    const f32x2 l2e2 = f2_splat(kLog2e);
+    for (int k = g, it = 0; k < n_items; k += kW16Groups, ++it) {
+      const int half = k & 1;
+      const int yq = half * 8 + ryq;
+      // SW-MSA mask (times log2 e) of this thread's two key sub-boxes 2 ch, 2 ch + 1
+      float mkA = 0.f, mkB = 0.f;
+      if (p.shift > 0) {
+        const int gw = cta_in_head + (k >> 1) * ctas_per_head;
+        const int win = gw % p.nW;
+        const int wy = win / p.nwx, wx = win - wy * p.nwx;
+        const int sel = ((wy == p.nwx - 1) ? 2 : 0) | ((wx == p.nwx - 1) ? 1 : 0);
+        const int code_q = (2 * half + bxq) & sel;
+        constexpr float kMasked = -100.f * kLog2e;
+        mkA = (((2 * ch) & sel) != code_q) ? kMasked : 0.f;
+        mkB = (((2 * ch + 1) & sel) != code_q) ? kMasked : 0.f;
+      }
+      mbar_wait(&s_full[g], it & 1);
+      tcgen05_fence_after();
+      uint32_t sv[32];
+      auto row_max = [&]() {
+        float m0 = __uint_as_float(sv[0]);
+#pragma unroll
+        for (int c = 1; c < 32; ++c) m0 = fmaxf(m0, __uint_as_float(sv[c]));
+        return m0;
+      };
+      // ---- pass 1: upper bound of the row maximum over this warp's 128 keys, exchanged with the other key half
+      float m = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        tmem_ld_32x32(t_s + 128 * ch + 32 * jj, sv);
+        tmem_ld_wait();
+        m = fmaxf(m, fmaf(row_max(), kLog2e, jj < 2 ? mkA : mkB));
+      }
+      exm[ch * 128 + r] = m;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      m = fmaxf(m, exm[(ch ^ 1) * 128 + r]) + bmax;
+      // ---- pass 2: p = exp2(. - m) on packed pairs, written in place as bf16 pairs
+      f32x2 lsum = f2_splat(0.f);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        // chunk j = 4 ch + jj: key sub-box j >> 1, its token rows 4 (j & 1) .. + 3, eight keys per row
+        tmem_ld_32x32(t_s + 128 * ch + 32 * jj, sv);
+        tmem_ld_wait();
+        const f32x2 cj = f2_splat((jj < 2 ? mkA : mkB) - m);
+        const int yk0 = ch * 8 + 4 * (jj & 1);
+        const float* trow = tab + (yq - yk0 + 15) * kW16TabPitch + (jj >> 1) * 8;
+        uint32_t pk[16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c = 8 * a + 4 * hh;
+            const float4 bb = *reinterpret_cast<const float4*>(trow - a * kW16TabPitch + 4 * hh);
+            f32x2 t0 = f2_fma(f2_pack(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), l2e2, f2_pack(bb.x, bb.y));
+            f32x2 t1 = f2_fma(f2_pack(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), l2e2, f2_pack(bb.z, bb.w));
+            t0 = f2_add(t0, cj);
+            t1 = f2_add(t1, cj);
+            float a0, a1, a2, a3;
+            f2_unpack(t0, a0, a1);
+            f2_unpack(t1, a2, a3);
+            const float e0 = ex2_approx(a0), e1 = ex2_approx(a1), e2 = ex2_approx(a2), e3 = ex2_approx(a3);
+            lsum = f2_add(lsum, f2_add(f2_pack(e0, e1), f2_pack(e2, e3)));
+            pk[c >> 1] = pack_bf16x2(e0, e1);
+            pk[(c >> 1) + 1] = pack_bf16x2(e2, e3);
+          }
+        }
+        tmem_st8_tc(t_s + 128 * ch + 16 * jj, pk);
+        tmem_st8_tc(t_s + 128 * ch + 16 * jj + 8, pk + 8);
+      }
+      float l0, l1;
+      f2_unpack(lsum, l0, l1);
+      exl[ch * 128 + r] = l0 + l1;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      const float inv = rcp_approx((l0 + l1) + exl[(ch ^ 1) * 128 + r]);
+      // ---- output: this warp's 16 of the 32 head dims
+      mbar_wait(&o_full[g], it & 1);
+      tcgen05_fence_after();
+      uint32_t ov[16];
+      tmem_ld_32x16(t_s + 192 + 16 * ch, ov);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      mbar_wait(&out_free[g], (it & 1) ^ 1);
+      uint8_t* orow = sOut + g * 8192 + r * 64;
+      const int sw = (r >> 1) & 3;
+      const f32x2 inv2 = f2_splat(inv);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint4 o4;
+        o4.x = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c]), __uint_as_float(ov[8 * c + 1])), inv2));
+        o4.y = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3])), inv2));
+        o4.z = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5])), inv2));
+        o4.w = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7])), inv2));
+        *reinterpret_cast<uint4*>(orow + (((2 * ch + c) ^ sw) << 4)) = o4;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_ready[g]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+// bias[h][q][k] a function of (y_q - y_k, x_q - x_k) only (what relative_position_index produces, :88-98)?
+__global__ void bias_toeplitz_kernel(const float* __restrict__ bias, int heads, int w, int* __restrict__ bad) {
+  const int T = w * w;
+  const long long total = static_cast<long long>(heads) * T * T;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tk = static_cast<int>(i % T), tq = static_cast<int>((i / T) % T);
+    const int h = static_cast<int>(i / (static_cast<long long>(T) * T));
+    const int dy = tq / w - tk / w, dx = tq % w - tk % w;
+    const int yq = dy > 0 ? dy : 0, yk = yq - dy, xq = dx > 0 ? dx : 0, xk = xq - dx;
+    const float rep = bias[(static_cast<size_t>(h) * T + yq * w + xq) * T + yk * w + xk];
+    if (bias[i] != rep) atomicOr(bad, 1);
+  }
+}
+
 // attn_mask buffer == the SW-MSA mask the reference constructs (model/diffusesg/diffusesg.py:207-222)?
 __global__ void mask_canonical_kernel(const float* __restrict__ mask, int nwx, int w, int shift, int* __restrict__ bad) {
   const int T = w * w;
@@ -693,6 +1012,70 @@ int check_mask_canonical(const float* mask, int res, int window, int shift, cuda
   DSG_CUDA_CHECK(e);
   count_launch();
   *canonical = bad ? 0 : 1;
+  return DSG_OK;
+}
+
+int check_bias_toeplitz(const float* bias, int heads, int window, cudaStream_t st, int* toeplitz) {
+  int* d_bad = nullptr;
+  DSG_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    bias_toeplitz_kernel<<<148 * 4, 256, 0, st>>>(bias, heads, window, d_bad);
+    e = cudaGetLastError();
+  }
+  int bad = 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_bad);
+  DSG_CUDA_CHECK(e);
+  count_launch();
+  *toeplitz = bad ? 0 : 1;
+  return DSG_OK;
+}
+
+bool window_attention_w16_supported(int batch, int res, int window, int shift, int heads) {
+  return window == 16 && res % 16 == 0 && (shift == 0 || shift == 8) && heads >= 1 && heads <= 74 && batch >= 1;
+}
+
+int launch_window_attention_w16(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
+                                cudaStream_t st) {
+  DSG_REQUIRE(window_attention_w16_supported(batch, res, 16, shift, heads), "attention_w16: unsupported shape");
+  const int C = heads * 32;
+  CUtensorMap tq, to;
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, 8, 8))
+    return rc;
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, 8, 8))
+    return rc;
+  static bool configured = false;
+  if (!configured) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW16SmemBytes));
+    configured = true;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  QdParams p;
+  p.bias = bias;
+  p.heads = heads;
+  p.res = res;
+  p.w = 16;
+  p.hw = 8;
+  p.shift = shift;
+  p.nwx = res / 16;
+  p.nW = p.nwx * p.nwx;
+  p.T = 256;
+  const long long items = static_cast<long long>(batch) * p.nW;
+  DSG_REQUIRE(items < 1073741824LL, "attention_w16: too many windows");
+  p.items = static_cast<int>(items);
+  int per_head = sms / heads;
+  if (per_head > p.items) per_head = p.items;
+  if (per_head < 1) per_head = 1;
+  window_attention_w16_kernel<<<per_head * heads, kW16Threads, kW16SmemBytes, st>>>(tq, to, p);
+  DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
 

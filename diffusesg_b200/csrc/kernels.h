@@ -114,9 +114,17 @@ bool window_attention_quad_supported(int batch, int res, int window, int shift, 
 int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
                                  int heads, cudaStream_t st);
 int check_mask_canonical(const float* mask, int res, int window, int shift, cudaStream_t st, int* canonical);
-// mask_canonical: 1 if `mask` is known to hold the reference's SW-MSA values (ignored for un-shifted blocks)
+// 16 x 16 windows (T = 256): query halves of 128 rows against 256 keys, bias looked up from the head's offset table;
+// needs check_bias_toeplitz() (bias[h][q][k] depends on the token offset only; synchronous, at finalisation).
+bool window_attention_w16_supported(int batch, int res, int window, int shift, int heads);
+int launch_window_attention_w16(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
+                                cudaStream_t st);
+int check_bias_toeplitz(const float* bias, int heads, int window, cudaStream_t st, int* toeplitz);
+// canonical: bit 0 = `mask` is known to hold the reference's SW-MSA values (ignored for un-shifted blocks),
+//            bit 1 = `bias` is known to be a function of the token offset
+enum { ATTN_MASK_CANONICAL = 1, ATTN_BIAS_TOEPLITZ = 2 };
 int launch_window_attention(const bf16* qkv, const float* bias, const float* mask, bf16* out, int batch, int res,
-                            int window, int shift, int heads, cudaStream_t st, int mask_canonical = 0);
+                            int window, int shift, int heads, cudaStream_t st, int canonical = 0);
 
 // ---------------------------------------------------------------------------------------------
 // row kernels: LayerNorm / FiLM / merge / breakup / embed / heads       (rowops.cu)

@@ -115,7 +115,7 @@ struct Block {
   CUtensorMap head_w;            // qkv with the fused block-head box shape (32 x C)
   size_t qkv_bias_off;  // fp32 [3C], q part pre-scaled
   size_t attn_bias_off; // fp32 [heads, T, T]
-  int mask_canonical = 0;  // shifted blocks: attn_mask holds the reference's SW-MSA values (checked at finalisation)
+  int mask_canonical = 0;  // ATTN_MASK_CANONICAL / ATTN_BIAS_TOEPLITZ bits, checked at finalisation
 };
 
 struct Merge { std::string prefix; int C, res; Weight reduction; };
@@ -148,7 +148,7 @@ struct dsg_model {
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
-  int pair_min_k = 384;       // CTA pairs from this K upwards, residual epilogue from 768 (DSG_PAIR_MIN_K, tuning hook)
+  int pair_min_k = 384;       // CTA pairs from this K upwards for the bf16 epilogue, 768 for the others (DSG_PAIR_MIN_K)
   bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
@@ -421,11 +421,11 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
                static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
                    (epi == EPI_RES_F32 ? mn * 4 : 0), st, label, rows, W.K);
   // CTA pairs cut the L2 -> SM operand traffic per flop by 30 %, which is what bounds the single-CTA tiles (the L2
-  // delivers ~6300 B/clk chip-wide = 40 KB per 128 x 192 x 64 step -> ~920 TFLOP/s).  Measured: +10..18 % for
-  // K >= 768, +10 % for the K = 384 qkv / pre_linear shapes, nothing for the K = 384 fc1 (its GELU epilogue is the
-  // co-bound) and -2 % for the HBM-bound residual epilogue at K = 384; the K <= 192 shapes are HBM-bound.
+  // delivers ~6300 B/clk chip-wide = 40 KB per 128 x 192 x 64 step -> ~920 TFLOP/s).  Measured (same box, A/B):
+  // +10..18 % for K >= 768; at K = 384 +3..10 % for the plain bf16 epilogue (qkv), -8 % for fc1 (its GELU epilogue
+  // is the co-bound and loses its slack), -2 % for the HBM-bound residual epilogue; K <= 192 shapes are HBM-bound.
   const bool pair = m->use_pair && epi != EPI_ADJ_HEAD && rows >= 256 &&
-                    (W.K >= 768 || (W.K >= m->pair_min_k && epi != EPI_RES_F32));
+                    (W.K >= 768 || (W.K >= m->pair_min_k && epi == EPI_BF16));
   return launch_gemm(&it->second, pair ? &W.tmap_half : &W.tmap, tmo, epi, p, st, pair);
 }
 
@@ -622,8 +622,17 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
                                b.heads, (2 * b.window - 1) * (2 * b.window - 1), st));
     // the tcgen05 attention kernels generate the SW-MSA mask in registers: only for the reference's own values
     b.mask_canonical = 0;
-    if (b.shift > 0 && window_attention_quad_supported(1, b.res, b.window, b.shift, b.heads))
-      DSG_TRY(check_mask_canonical(m->f32(p + ".attn_mask"), b.res, b.window, b.shift, st, &b.mask_canonical));
+    const bool w16 = window_attention_w16_supported(1, b.res, b.window, b.shift, b.heads);
+    if (b.shift > 0 && (w16 || window_attention_quad_supported(1, b.res, b.window, b.shift, b.heads))) {
+      int ok = 0;
+      DSG_TRY(check_mask_canonical(m->f32(p + ".attn_mask"), b.res, b.window, b.shift, st, &ok));
+      if (ok) b.mask_canonical |= ATTN_MASK_CANONICAL;
+    }
+    if (w16) {  // the 16 x 16 kernel looks the bias up by token offset
+      int ok = 0;
+      DSG_TRY(check_bias_toeplitz(m->at<float>(b.attn_bias_off), b.heads, b.window, st, &ok));
+      if (ok) b.mask_canonical |= ATTN_BIAS_TOEPLITZ;
+    }
   }
   for (Merge& g : m->merges) DSG_TRY(pack_weight(m, g.reduction, g.prefix + ".reduction.weight", st));
   for (Breakup& u : m->breakups) {
@@ -912,7 +921,7 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   CUtensorMap ta, tw, to;
   DSG_TRY(make_tmap_bf16(&ta, a, M, K, 128));
   const char* no_pair = getenv("DSG_NO_PAIR");
-  const bool pair = M >= 256 && (K >= 768 || (K >= 384 && epi != EPI_RES_F32)) &&
+  const bool pair = M >= 256 && (K >= 768 || (K >= 384 && epi == EPI_BF16)) &&
                     !(no_pair != nullptr && no_pair[0] == '1');  // the denoiser schedule's rule
   DSG_TRY(make_tmap_bf16(&tw, w, N, K, pair ? gemm_block_n(N) / 2 : gemm_block_n(N)));
   DSG_TRY(make_tmap_out(&to, out, M, N, epi));
@@ -933,8 +942,17 @@ int dsg_window_attention(const void* qkv, const float* bias, const float* mask, 
                          int shift, int heads, dsg_stream_t stream) {
   DSG_REQUIRE(qkv && bias && out, "window_attention: null tensor");
   int canonical = 0;
-  if (mask != nullptr && shift > 0 && window_attention_quad_supported(batch, res, window, shift, heads))
-    DSG_TRY(check_mask_canonical(mask, res, window, shift, static_cast<cudaStream_t>(stream), &canonical));
+  const bool w16 = window_attention_w16_supported(batch, res, window, shift, heads);
+  if (mask != nullptr && shift > 0 && (w16 || window_attention_quad_supported(batch, res, window, shift, heads))) {
+    int ok = 0;
+    DSG_TRY(check_mask_canonical(mask, res, window, shift, static_cast<cudaStream_t>(stream), &ok));
+    if (ok) canonical |= ATTN_MASK_CANONICAL;
+  }
+  if (w16) {
+    int ok = 0;
+    DSG_TRY(check_bias_toeplitz(bias, heads, window, static_cast<cudaStream_t>(stream), &ok));
+    if (ok) canonical |= ATTN_BIAS_TOEPLITZ;
+  }
   return launch_window_attention(static_cast<const bf16*>(qkv), bias, mask, static_cast<bf16*>(out), batch, res, window,
                                  shift, heads, static_cast<cudaStream_t>(stream), canonical);
 }

@@ -99,7 +99,9 @@ def _attention_reference(qkv, bias, mask, batch, res, w, shift, heads):
     # even windows up to 10 x 10, shifted or not, take the quad-box tcgen05 kernel (one window per tile; the COCO-Stuff
     # geometry: 10 x 10 windows at res 40 / 20 / 10, shift 5 at res 20; the VG shifted blocks: 8 x 8, shift 4 at res 16)
     (2, 40, 10, 0, 3), (3, 20, 10, 0, 6), (5, 20, 10, 5, 6), (1, 30, 10, 5, 3), (7, 16, 8, 4, 12), (3, 24, 8, 4, 3),
-    (2, 12, 6, 3, 3), (41, 10, 10, 0, 24)])
+    (2, 12, 6, 3, 3), (41, 10, 10, 0, 24),
+    # 16 x 16 windows (BASELINE config 5): two 128-row query halves per window-head against 256 keys
+    (3, 64, 16, 0, 3), (2, 64, 16, 8, 3), (3, 32, 16, 8, 6), (5, 16, 16, 0, 12), (2, 48, 16, 8, 3)])
 def test_window_attention_matches_torch(batch, res, w, shift, heads):
     g = torch.Generator(device=DEV).manual_seed(res * 100 + w + shift)
     c = heads * 32
@@ -118,10 +120,11 @@ def test_window_attention_matches_torch(batch, res, w, shift, heads):
     assert float((got - want).abs().max()) < 5e-2
 
 
-def test_window_attention_arbitrary_mask_takes_the_generic_kernel():
-    """The tcgen05 kernels generate the SW-MSA mask themselves; a mask buffer with other values must still be honoured
-    (the launcher checks the buffer and falls back to the kernel that reads it)."""
-    batch, res, w, shift, heads = 3, 20, 10, 5, 6
+@pytest.mark.parametrize("batch,res,w,shift,heads", [(3, 20, 10, 5, 6), (2, 32, 16, 8, 3)])
+def test_window_attention_arbitrary_mask_takes_the_generic_kernel(batch, res, w, shift, heads):
+    """The tcgen05 kernels generate the SW-MSA mask themselves (and the 16 x 16 one looks the bias up by token
+    offset); a mask buffer with other values / a bias that is not a function of the offset must still be honoured
+    (the launcher checks the buffers and falls back to the kernel that reads them)."""
     g = torch.Generator(device=DEV).manual_seed(5)
     c, t = heads * 32, w * w
     qkv = torch.randn(batch * res * res, 3 * c, device=DEV, generator=g)
