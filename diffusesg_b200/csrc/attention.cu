@@ -446,10 +446,10 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
   const int T = window * window;
   DSG_REQUIRE(T % 2 == 0, "attention: odd window token count %d", T);
   static const bool no_tc = getenv("DSG_NO_ATTN_TC") != nullptr && getenv("DSG_NO_ATTN_TC")[0] == '1';
-  if (!no_tc && window_attention_tc_supported(batch, res, window, shift, heads))
-    return launch_window_attention_tc(qkv, bias, out, batch, res, heads, st);  // un-shifted 8 x 8 windows: tcgen05
-  // one window per tile: pays off from 6 x 6 windows on (a shifted 8 x 8 window fills only half of its 128-row tile
-  // and the warp-MMA kernel below is faster: 190 vs 262 us on the VG shifted blocks)
+  if (!no_tc && (shift == 0 || (mask_canonical & ATTN_MASK_CANONICAL) != 0) &&
+      window_attention_tc_supported(batch, res, window, shift, heads))
+    return launch_window_attention_tc(qkv, bias, out, batch, res, shift, heads, st);  // 8 x 8 windows, two per tile
+  // one window per tile for the other even windows up to 10 x 10 (an 8 x 8 window would fill only half of the tile)
   const bool mask_ok = shift == 0 || (mask_canonical & ATTN_MASK_CANONICAL) != 0;
   if (!no_tc && window != 8 && mask_ok && window_attention_quad_supported(batch, res, window, shift, heads))
     return launch_window_attention_quad(qkv, bias, out, batch, res, window, shift, heads, st);

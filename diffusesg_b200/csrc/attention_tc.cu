@@ -36,6 +36,7 @@ struct TcParams {
   const float* bias;  // [heads, 64, 64]
   int heads, res, nwx, nW;
   int pairs;          // window pairs = B * nW / 2
+  int shift;          // 0, or 4 (SHIFTED instantiation)
 };
 
 DSG_DEVICE uint64_t desc_sw64_kmajor(uint32_t smem_addr) {  // [rows x 32] bf16, 64-byte swizzle, 8-row groups 512 B apart
@@ -81,6 +82,11 @@ DSG_DEVICE void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c
                : "memory");
 }
 
+// SHIFTED (the SW-MSA blocks, shift 4): a window is gathered as four 4 x 4-token sub-boxes (a window that wraps around
+// the image edge splits exactly there), rows 16 (2 by + bx) + 4 ry + rx of its half tile; the bias tile is permuted
+// to that order and the mask is -100 between sub-boxes whose region codes differ (one scalar per 16-key chunk); the
+// launcher takes this instantiation only if the attn_mask buffer holds the reference's values.
+template <bool SHIFTED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
                            const TcParams p) {
@@ -125,7 +131,11 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   {
     const float* bh = p.bias + static_cast<size_t>(h) * 64 * 64;
-    for (int i = threadIdx.x; i < 64 * 64; i += kTcThreads) sBias[(i >> 6) * kTcBiasPitch + (i & 63)] = bh[i];
+    auto token = [](int r) {  // row of the sub-box order -> token of the window
+      return SHIFTED ? (((r >> 5) * 4 + ((r >> 2) & 3)) * 8 + ((r >> 4) & 1) * 4 + (r & 3)) : r;
+    };
+    for (int i = threadIdx.x; i < 64 * 64; i += kTcThreads)
+      sBias[(i >> 6) * kTcBiasPitch + (i & 63)] = bh[token(i >> 6) * 64 + token(i & 63)];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -140,7 +150,36 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     cy = b * p.res + wy * 8;
   };
 
-  if (warp == kLoadWarp) {
+  // SHIFTED: sub-box (by, bx) = slot of window gw -> TMA coordinates of its 4 x 4 token box
+  auto sub_coords = [&](int gw, int slot, int& cx, int& cy) {
+    const int b = gw / p.nW, win = gw - b * p.nW;
+    const int wy = win / p.nwx, wx = win - wy * p.nwx;
+    int oy = wy * 8 + (slot >> 1) * 4 + p.shift;
+    int ox = wx * 8 + (slot & 1) * 4 + p.shift;
+    if (oy >= p.res) oy -= p.res;
+    if (ox >= p.res) ox -= p.res;
+    cx = ox;
+    cy = b * p.res + oy;
+  };
+
+  if (warp == kLoadWarp && SHIFTED) {
+    // ------------------------------------------------------------------ loader (lanes 0..23: one 1 KB box each)
+    for (int k = 0; k < n_items; ++k) {
+      const int st = k % kTcStages;
+      const int pair = cta_in_head + k * ctas_per_head;
+      mbar_wait(&stage_empty[st], ((k / kTcStages) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&stage_full[st], kTcStageBytes);
+      __syncwarp();
+      if (lane < 24) {
+        const int part = lane >> 3, w = (lane >> 2) & 1, slot = lane & 3;
+        int cx, cy;
+        sub_coords(2 * pair + w, slot, cx, cy);
+        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096 + slot * 1024, &tmQkv, &stage_full[st],
+                    part * C + h * 32, cx, cy);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kLoadWarp) {
     // ------------------------------------------------------------------ loader
     if (elect_one()) {
       for (int k = 0; k < n_items; ++k) {
@@ -200,10 +239,18 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
         const int g = k % 3;
         const int pair = cta_in_head + k * ctas_per_head;
         mbar_wait(&out_ready[g], (k / 3) & 1);
-        for (int w = 0; w < 2; ++w) {
-          int cx, cy;
-          win_coords(2 * pair + w, cx, cy);
-          tma_store_3d(&tmOut, sOut + g * 8192 + w * 4096, h * 32, cx, cy);
+        if (SHIFTED) {
+          for (int ws = 0; ws < 8; ++ws) {
+            int cx, cy;
+            sub_coords(2 * pair + (ws >> 2), ws & 3, cx, cy);
+            tma_store_3d(&tmOut, sOut + g * 8192 + ws * 1024, h * 32, cx, cy);
+          }
+        } else {
+          for (int w = 0; w < 2; ++w) {
+            int cx, cy;
+            win_coords(2 * pair + w, cx, cy);
+            tma_store_3d(&tmOut, sOut + g * 8192 + w * 4096, h * 32, cx, cy);
+          }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -220,6 +267,16 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     const float* brow = sBias + tq * kTcBiasPitch;
     constexpr float kLog2e = 1.4426950408889634f;
     for (int k = g, it = 0; k < n_items; k += 3, ++it) {
+      float mk[4] = {0.f, 0.f, 0.f, 0.f};  // SW-MSA mask of this row's window, per key sub-box
+      if (SHIFTED) {
+        const int gw = 2 * (cta_in_head + k * ctas_per_head) + w;
+        const int win = gw % p.nW;
+        const int wy = win / p.nwx, wx = win - wy * p.nwx;
+        const int sel = ((wy == p.nwx - 1) ? 2 : 0) | ((wx == p.nwx - 1) ? 1 : 0);
+        const int code_q = (tq >> 4) & sel;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk[j] = ((j & sel) != code_q) ? -100.f : 0.f;
+      }
       mbar_wait(&s_full[g], it & 1);
       tcgen05_fence_after();
       // the 64 scores of this row's own window: columns [64 w, 64 w + 64)
@@ -230,7 +287,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
       float m = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 64; c += 4) {
-        const float4 bb = *reinterpret_cast<const float4*>(brow + c);
+        float4 bb = *reinterpret_cast<const float4*>(brow + c);
+        if (SHIFTED) { bb.x += mk[c >> 4]; bb.y += mk[c >> 4]; bb.z += mk[c >> 4]; bb.w += mk[c >> 4]; }
         const float a0 = __uint_as_float(sv[c]) + bb.x, a1 = __uint_as_float(sv[c + 1]) + bb.y;
         const float a2 = __uint_as_float(sv[c + 2]) + bb.z, a3 = __uint_as_float(sv[c + 3]) + bb.w;
         sv[c] = __float_as_uint(a0); sv[c + 1] = __float_as_uint(a1);
@@ -947,24 +1005,26 @@ __global__ void mask_canonical_kernel(const float* __restrict__ mask, int nwx, i
 }  // namespace
 
 bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads) {
-  if (window != 8 || shift != 0 || res % 8 != 0 || heads < 1 || heads > 74) return false;
+  if (window != 8 || (shift != 0 && shift != 4) || res % 8 != 0 || heads < 1 || heads > 74) return false;
   const long long windows = static_cast<long long>(batch) * (res / 8) * (res / 8);
   return windows % 2 == 0 && windows >= 2;
 }
 
-int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int heads,
+int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
                                cudaStream_t st) {
-  DSG_REQUIRE(window_attention_tc_supported(batch, res, 8, 0, heads), "attention_tc: unsupported shape");
+  DSG_REQUIRE(window_attention_tc_supported(batch, res, 8, shift, heads), "attention_tc: unsupported shape");
   const int C = heads * 32;
+  const int box = shift ? 4 : 8;  // shifted windows are gathered as four 4 x 4-token sub-boxes
   CUtensorMap tq, to;
   // [B res (token row), res (token column), channels]: a window is an 8 x 8 box of tokens, a head slice 32 channels
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, 8, 8))
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
     return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, 8, 8))
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
   static bool configured = false;
   if (!configured) {
-    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     configured = true;
   }
   static int sms = 0;
@@ -984,7 +1044,9 @@ int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, in
   int per_head = sms / heads;
   if (per_head > p.pairs) per_head = p.pairs;
   if (per_head < 1) per_head = 1;
-  window_attention_tc_kernel<<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
+  p.shift = shift;
+  if (shift) window_attention_tc_kernel<true><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
+  else window_attention_tc_kernel<false><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

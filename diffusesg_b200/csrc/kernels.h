@@ -105,7 +105,7 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t d0, int64_t d1
 // tcgen05 version for un-shifted 8 x 8 windows (attention_tc.cu): two windows per 128-row MMA tile, scores and
 // probabilities in tensor memory.  Returns DSG_ERR_INVALID for shapes it does not take.
 bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads);
-int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int heads,
+int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
                                cudaStream_t st);
 // quad-box tcgen05 version (one window per tile): even windows up to 10 x 10, shift 0 or window / 2; the SW-MSA mask
 // is generated in the kernel, so a shifted block may only take it when check_mask_canonical() found the model's

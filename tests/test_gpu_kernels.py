@@ -99,7 +99,7 @@ def _attention_reference(qkv, bias, mask, batch, res, w, shift, heads):
     # even windows up to 10 x 10, shifted or not, take the quad-box tcgen05 kernel (one window per tile; the COCO-Stuff
     # geometry: 10 x 10 windows at res 40 / 20 / 10, shift 5 at res 20; the VG shifted blocks: 8 x 8, shift 4 at res 16)
     (2, 40, 10, 0, 3), (3, 20, 10, 0, 6), (5, 20, 10, 5, 6), (1, 30, 10, 5, 3), (7, 16, 8, 4, 12), (3, 24, 8, 4, 3),
-    (2, 12, 6, 3, 3), (41, 10, 10, 0, 24),
+    (2, 12, 6, 3, 3), (41, 10, 10, 0, 24), (2, 32, 8, 4, 6), (512, 16, 8, 4, 12),
     # 16 x 16 windows (BASELINE config 5): two 128-row query halves per window-head against 256 keys
     (3, 64, 16, 0, 3), (2, 64, 16, 8, 3), (3, 32, 16, 8, 6), (5, 16, 16, 0, 12), (2, 48, 16, 8, 3)])
 def test_window_attention_matches_torch(batch, res, w, shift, heads):
