@@ -85,7 +85,11 @@ DSG_API int dsg_model_set_tensor(dsg_model* m, const char* key, const void* src,
                          dsg_stream_t stream);
 /* Build the packed forms (bf16 weights with the q scale folded in, gathered relative-position bias, folded
  * read_out chain, transposed head weights) and the weight TMA descriptors.  Call after all tensors are set and
- * again whenever any of them changed. */
+ * again whenever any of them changed.  For shifted blocks / 16 x 16 windows it also compares the attn_mask buffer
+ * with the reference's SW-MSA construction (diffusesg.py:207-222) and checks that the gathered bias depends on the
+ * token offset only; the tcgen05 attention kernels, which generate the mask and look the bias up themselves, are
+ * only selected when that holds.  These checks SYNCHRONISE the stream (one small readback per such block); the
+ * denoiser passes themselves never do. */
 DSG_API int dsg_model_finalize(dsg_model* m, dsg_stream_t stream);
 
 /* ---- denoiser forward --------------------------------------------------------------------------------------- */
@@ -165,7 +169,8 @@ DSG_API int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, co
 DSG_API int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
                   int epi, dsg_stream_t stream);
 /* qkv [B*res*res, 3*heads*32] bf16 -> out [B*res*res, heads*32] bf16 (WindowAttention.forward, :108-139, q
- * pre-scaled); bias [heads, T, T] fp32, mask [nW, T, T] fp32 or NULL (shift == 0). */
+ * pre-scaled); bias [heads, T, T] fp32, mask [nW, T, T] fp32 or NULL (shift == 0).  Runs the same mask / bias
+ * checks as dsg_model_finalize on every call (synchronous) and then the kernel the denoiser would pick. */
 DSG_API int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
                          int window, int shift, int heads, dsg_stream_t stream);
 

@@ -60,7 +60,7 @@ def stage_names(cfg):
     return names
 
 
-@pytest.mark.parametrize("name,batch", [("tiny", 3), ("vg", 2), ("coco", 2)])
+@pytest.mark.parametrize("name,batch", [("tiny", 3), ("vg", 2), ("coco", 2), ("n64w16", 2)])
 def test_forward_stage_by_stage(name, batch):
     """Localises a parity break: leave the native schedule after every stage and compare the residual stream
     with the oracle's capture of the same stage."""
