@@ -71,6 +71,8 @@ struct TailParams {
   const float* b1;     // [4C]
   const float* b2;     // [C]
   float* x;            // [M, C] fp32 residual stream (the same buffer tmX reads)
+  const float* gamma_f;  // FINAL: the network's last LayerNorm (model/diffusesg/diffusesg.py:758), fused into the O phase
+  const float* beta_f;
   int M;
   int skip_gelu;       // experiment hook (DSG_TAIL_SKIP_GELU): pack the raw accumulator (wrong results, light ALU load)
   long long* trace;    // test hook: clock64 timeline of CTA 0 ([chunk < 64][warp < 19][event < 8]) or nullptr
@@ -127,17 +129,24 @@ DSG_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, 
 }
 DSG_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int C>
+// FINAL (the last block of the network): the O phase applies the final LayerNorm to the block output and stores ONLY
+// its bf16 result (tmY) - the fp32 residual stream is dead after this block, so its 4 B/element write and the separate
+// LayerNorm launch (4 B read + 2 B write) disappear.  The row statistics use the LN2 mean of the same row as pivot.
+template <int C, bool FINAL>
 __global__ void __launch_bounds__(kTailThreads, 1)
 block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_constant__ CUtensorMap tmWp,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                  const __grid_constant__ CUtensorMap tmX, const TailParams p) {
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const TailParams p) {
   using G = TailCfg<C>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAtt = smem;
   uint8_t* sX = sAtt + G::A_BYTES;   // x tile in (TMA load -> P phase)
-  uint8_t* sXo = sX + G::X_BYTES;    // block output (O phase -> TMA store)
+  uint8_t* sXo = sX + G::X_BYTES;    // block output (O phase -> TMA store); FINAL: bf16 [C / 32][128 x 32] + extras
+  float2* sPartO = reinterpret_cast<float2*>(sXo + (C / 32) * 8192);               // FINAL: partial sums of the last LN
+  float* sGamF = reinterpret_cast<float*>(sXo + (C / 32) * 8192 + G::PART_BYTES);  // FINAL: its gamma | beta
+  float* sBetF = sGamF + C;
+  static_assert((C / 32) * 8192 + G::PART_BYTES + 2 * C * 4 <= G::X_BYTES, "FINAL extras must fit the output tile");
   uint8_t* sW1 = sXo + G::X_BYTES;
   uint8_t* sW2 = sW1 + G::S1 * G::W1_SLOT;
   float2* sPart = reinterpret_cast<float2*>(sW2 + G::S2 * G::W2_SLOT);
@@ -178,6 +187,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
+    if (FINAL) tma_prefetch_desc(&tmY);
     for (int s = 0; s < G::S1; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
     for (int s = 0; s < G::S2; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
     mbar_init(att_full, 1);
@@ -198,6 +208,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   for (int i = threadIdx.x; i < G::HID; i += kTailThreads) sB1[i] = p.b1[i];
+  if (FINAL) {
+    for (int i = threadIdx.x; i < C; i += kTailThreads) { sGamF[i] = p.gamma_f[i]; sBetF[i] = p.beta_f[i]; }
+  }
   for (int i = threadIdx.x; i < C; i += kTailThreads) {
     sBp[i] = p.bp[i];
     sB2[i] = p.b2[i];
@@ -354,10 +367,16 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       };
       auto store_x = [&](int tl) {
         const int tile = blockIdx.x + tl * gridDim.x;
-        for (int xb = 0; xb < G::XB; ++xb)
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(sXo + xb * 16384)), "r"(xb * 32), "r"(tile * 128)
-                       : "memory");
+        for (int xb = 0; xb < G::XB; ++xb) {
+          if (FINAL)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmY)), "r"(smem_u32(sXo + xb * 8192)), "r"(xb * 32), "r"(tile * 128)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmX)), "r"(smem_u32(sXo + xb * 16384)), "r"(xb * 32), "r"(tile * 128)
+                         : "memory");
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       };
       // worker events in time order: P(0), P(1), [O(k), P(k + 2)] for k = 0 ...
@@ -396,6 +415,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       return reinterpret_cast<float4*>(sX + (c >> 5) * 16384 + r_t * 128 + (((((c & 31) >> 2)) ^ (r_t & 7)) << 4));
     };
 
+    float mean_pre0 = 0.f, mean_pre1 = 0.f;  // FINAL: LN2 mean of this thread's row, tiles of parity 0 / 1 (pivot of O)
     // ---- P(tl): x_new = acc2 + b_p + x;  y = LN(x_new) -> tensor memory;  acc2 = x_new + b2
     auto phase_p = [&](int tl) {
       const int u = tl & 1;
@@ -463,6 +483,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       const float dm = t1 * (1.0f / C);                       // mean - pivot
       const float var = fmaxf(t2 * (1.0f / C) - dm * dm, 0.f);
       const float rstd = rsqrtf(var + kTailLnEps);
+      if (FINAL) { if (u) mean_pre1 = pivot + dm; else mean_pre0 = pivot + dm; }
       const f32x2 rs2 = f2_splat(rstd);
       const f32x2 nmr = f2_splat(-(pivot + dm) * rstd);       // y = (a rstd - mean rstd) gamma + beta
 #pragma unroll
@@ -498,6 +519,57 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc2_empty[u]);
+      if (FINAL) {
+        // last LayerNorm of the network on the block output: pivot-shifted one-pass statistics over the four column
+        // groups of the row, then bf16 into the [128 x 32]-column chunks the adj / node heads read (64-byte swizzle)
+        const float pivot = u ? mean_pre1 : mean_pre0;
+        const f32x2 npiv = f2_splat(-pivot);
+        f32x2 a[G::CW / 2];
+        f32x2 s1 = f2_splat(0.f), s2 = f2_splat(0.f);
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 2) {
+          a[i >> 1] = f2_add(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), npiv);
+          s1 = f2_add(s1, a[i >> 1]);
+          s2 = f2_fma(a[i >> 1], a[i >> 1], s2);
+        }
+        {
+          float s1a, s1b, s2a, s2b;
+          f2_unpack(s1, s1a, s1b);
+          f2_unpack(s2, s2a, s2b);
+          sPartO[cg * 128 + r_t] = make_float2(s1a + s1b, s2a + s2b);
+        }
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 pp = sPartO[k * 128 + r_t];
+          t1 += pp.x;
+          t2 += pp.y;
+        }
+        const float dm = t1 * (1.0f / C);
+        const float rstd = rsqrtf(fmaxf(t2 * (1.0f / C) - dm * dm, 0.f) + kTailLnEps);
+        const f32x2 rs2 = f2_splat(rstd), nmr = f2_splat(-dm * rstd);
+        if (tl > 0) mbar_wait(out_free, (tl - 1) & 1);  // the store of the previous output has read sXo
+#pragma unroll
+        for (int i = 0; i < G::CW; i += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int k = 0; k < 8; k += 4) {
+            const float4 gg = *reinterpret_cast<const float4*>(&sGamF[c0 + i + k]);
+            const float4 be = *reinterpret_cast<const float4*>(&sBetF[c0 + i + k]);
+            pk[k >> 1] = pack_bf16x2(f2_fma(f2_fma(a[(i + k) >> 1], rs2, nmr), f2_pack(gg.x, gg.y), f2_pack(be.x, be.y)));
+            pk[(k >> 1) + 1] =
+                pack_bf16x2(f2_fma(f2_fma(a[((i + k) >> 1) + 1], rs2, nmr), f2_pack(gg.z, gg.w), f2_pack(be.z, be.w)));
+          }
+          const int c = c0 + i;
+          *reinterpret_cast<uint4*>(sXo + (c >> 5) * 8192 + r_t * 64 + (((((c & 31) >> 3)) ^ ((r_t >> 1) & 3)) << 4)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_ready);
+        return;
+      }
       if (tl > 0) mbar_wait(out_free, (tl - 1) & 1);  // the store of the previous output has read sXo
 #pragma unroll
       for (int i = 0; i < G::CW; i += 4)
@@ -569,10 +641,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
 
 template <int C>
 int launch_c(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1, const CUtensorMap* tmW2,
-             const CUtensorMap* tmX, const TailParams& p, cudaStream_t st) {
+             const CUtensorMap* tmX, const CUtensorMap* tmY, const TailParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TailCfg<C>::SMEM_BYTES));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TailCfg<C>::SMEM_BYTES));
     configured = true;
   }
@@ -584,8 +658,12 @@ int launch_c(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMa
     if (sms <= 0) sms = 148;
   }
   const int tiles = (p.M + 127) / 128;
-  block_tail_kernel<C><<<tiles < sms ? tiles : sms, kTailThreads, TailCfg<C>::SMEM_BYTES, st>>>(*tmAtt, *tmWp, *tmW1,
-                                                                                               *tmW2, *tmX, p);
+  if (tmY != nullptr)
+    block_tail_kernel<C, true><<<tiles < sms ? tiles : sms, kTailThreads, TailCfg<C>::SMEM_BYTES, st>>>(
+        *tmAtt, *tmWp, *tmW1, *tmW2, *tmX, *tmY, p);
+  else
+    block_tail_kernel<C, false><<<tiles < sms ? tiles : sms, kTailThreads, TailCfg<C>::SMEM_BYTES, st>>>(
+        *tmAtt, *tmWp, *tmW1, *tmW2, *tmX, *tmX, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -597,11 +675,13 @@ bool block_tail_supported(int C) { return C == 96; }
 int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1,
                       const CUtensorMap* tmW2, const CUtensorMap* tmX, const float* bp, const float* gamma,
                       const float* beta, const float* b1, const float* b2, float* x, long long rows, int C,
-                      cudaStream_t st, long long* trace) {
+                      cudaStream_t st, long long* trace, const CUtensorMap* tmY, const float* gamma_f, const float* beta_f) {
   DSG_REQUIRE(block_tail_supported(C) && rows > 0 && rows < 2147483647LL, "block_tail: C=%d rows=%lld", C, rows);
+  DSG_REQUIRE((tmY == nullptr) == (gamma_f == nullptr) && (tmY == nullptr) == (beta_f == nullptr),
+              "block_tail: the fused final LayerNorm needs its output map, gamma and beta together");
   static const int skip = (getenv("DSG_TAIL_SKIP_GELU") != nullptr) ? 1 : 0;
-  TailParams p{bp, gamma, beta, b1, b2, x, static_cast<int>(rows), skip, trace};
-  return launch_c<96>(tmAtt, tmWp, tmW1, tmW2, tmX, p, st);
+  TailParams p{bp, gamma, beta, b1, b2, x, gamma_f, beta_f, static_cast<int>(rows), skip, trace};
+  return launch_c<96>(tmAtt, tmWp, tmW1, tmW2, tmX, tmY, p, st);
 }
 
 }  // namespace dsg

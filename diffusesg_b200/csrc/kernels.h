@@ -82,7 +82,11 @@ bool block_tail_supported(int C);
 int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1,
                       const CUtensorMap* tmW2, const CUtensorMap* tmX, const float* bp, const float* gamma,
                       const float* beta, const float* b1, const float* b2, float* x, long long rows, int C,
-                      cudaStream_t st, long long* trace = nullptr);
+                      cudaStream_t st, long long* trace = nullptr, const CUtensorMap* tmY = nullptr,
+                      const float* gamma_f = nullptr, const float* beta_f = nullptr);
+// tmY / gamma_f / beta_f (all or none): the LAST block of the network - the kernel applies the final LayerNorm
+// (:758) to the block output and stores only y = LN(x) as bf16 through tmY ([M, C] bf16, 32-column boxes); x is not
+// written back.
 
 // ---------------------------------------------------------------------------------------------
 // fused block head:  x = silu(FiLM(x));  qkv = LN1(x) W_qkv^T + b_qkv                     (blockhead.cu)

@@ -148,6 +148,7 @@ struct dsg_model {
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
+  bool use_final_ln = true;   // DSG_NO_FINAL_LN=1 keeps the network's last LayerNorm as its own launch
   int pair_min_k = 384;       // CTA pairs from this K upwards for the bf16 epilogue, 768 for the others (DSG_PAIR_MIN_K)
   bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
@@ -443,8 +444,10 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
     if (_rc) return _rc;                                                      \
   } while (0)
 
+// fuse_final_ln: this is the last block of the network; if it runs the fused tail, the tail also applies the final
+// LayerNorm and writes only Y (*fused_final_ln = true), and the caller skips the separate LayerNorm launch.
 int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
-              cudaStream_t st) {
+              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr) {
   const int C = b.dim;
   const int L = b.res * b.res;
   const long long rows = static_cast<long long>(batch) * L;
@@ -495,10 +498,18 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     const CUtensorMap* ta = tmap(w.ATT, 100000 + C, [&](CUtensorMap* t) { return make_tmap_2d(t, w.ATT, rows, C, 2, 32, 128); });
     const CUtensorMap* tx = tmap(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
     if (ta == nullptr || tx == nullptr) return DSG_ERR_CUDA;
-    DSG_TRY_P(PC_MLP, 18.0 * rc * C, rc * 10,
+    const CUtensorMap* ty = nullptr;
+    if (fuse_final_ln) {
+      ty = tmap(w.Y, -(C * 8 + EPI_BF16), [&](CUtensorMap* t) { return make_tmap_out(t, w.Y, rows, C, EPI_BF16); });
+      if (ty == nullptr) return DSG_ERR_CUDA;
+      if (fused_final_ln) *fused_final_ln = true;
+    }
+    DSG_TRY_P(PC_MLP, 18.0 * rc * C, rc * (fuse_final_ln ? 8 : 10),
               launch_block_tail(ta, &b.tail_wp, &b.tail_w1, &b.mlp_w2, tx, m->f32(p + ".attn.proj.bias"),
                                 m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), m->f32(p + ".mlp.fc1.bias"),
-                                m->f32(p + ".mlp.fc2.bias"), w.X, rows, C, st, take_trace(C)));
+                                m->f32(p + ".mlp.fc2.bias"), w.X, rows, C, st, take_trace(C), ty,
+                                fuse_final_ln ? m->f32("norm.weight") : nullptr,
+                                fuse_final_ln ? m->f32("norm.bias") : nullptr));
     return DSG_OK;
   }
   // x = x + proj(attn)                                                   (:137, :272)
@@ -541,6 +552,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   const char* no_pair = getenv("DSG_NO_PAIR");
   m->use_pair = !(no_pair != nullptr && no_pair[0] == '1');
   if (const char* mk = getenv("DSG_PAIR_MIN_K")) m->pair_min_k = atoi(mk) > 0 ? atoi(mk) : 384;
+  const char* no_fln = getenv("DSG_NO_FINAL_LN");
+  m->use_final_ln = !(no_fln != nullptr && no_fln[0] == '1');
   const char* no_head = getenv("DSG_NO_HEAD");
   m->use_head = !(no_head != nullptr && no_head[0] == '1');
   const int rc = build(m);
@@ -726,6 +739,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
                              m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
                              m->cfg.self_condition, E, st));
   int stage_no = 0;
+  bool final_ln_done = false;
 #define DSG_STAGE_DONE() do { if (g_stop_after >= 0 && stage_no++ == g_stop_after) return DSG_OK; } while (0)
   DSG_STAGE_DONE();
   // encoder                                                                  (:746-748)
@@ -763,13 +777,16 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
       DSG_STAGE_DONE();
     }
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
-      DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st));
+      // the last block: the final LayerNorm rides on its fused tail (not while a test walks the stages: those read X)
+      const bool last = u == m->nl - 1 && j == m->cfg.depths[s] - 1 && m->use_final_ln && g_stop_after < 0;
+      DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done));
       DSG_STAGE_DONE();
     }
   }
   // read-out                                                                 (:758-761, :806-825)
   const long long pixels = static_cast<long long>(B) * N * N;
-  DSG_TRY_P(PC_ROW, 0, px * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
+  if (!final_ln_done)
+    DSG_TRY_P(PC_ROW, 0, px * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
   GemmParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.w2t = m->at<float>(m->adj_w2t_off);
