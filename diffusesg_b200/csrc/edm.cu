@@ -12,6 +12,8 @@
 //          x'     = x_hat + h * k                                                                    (:389-390)
 //          x_next = mask(x_hat + h * (0.5 k + 0.5 (inv_tp * x' - inv_tp * D2)))     (Heun, :414-422)
 //          x_next = mask(x')                                                        (last step, :395-396)
+#include <curand_kernel.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -128,6 +130,46 @@ decode_kernel(const float* __restrict__ adj, const float* __restrict__ node, con
   }
 }
 
+// Pre-step with the noise drawn IN the kernel, bit-compatible with the two `torch.randn_like` calls of the reference
+// (runner/mcmc_sampler/edm.py:358-364): ATen's normal_ on CUDA is a grid-stride kernel over Philox4x32-10,
+//   curand_init(seed, thread, offset); per iteration  float4 r = curand_normal4()  ->  elements  li + k T, k < 4,
+//   T = 256 * grid threads, grid = min(SMs * (max threads per SM / 256), ceil(numel / 256))
+// (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, distribution_elementwise_grid_stride_kernel).
+// Launching the same virtual grid with the generator's (seed, offset) reproduces eps element for element; the caller
+// advances the generator by the same counter offset.  One launch per tensor (each has its own offset and grid).
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+edm_pre_philox_kernel(const float* __restrict__ x, float* __restrict__ out, const uint8_t* __restrict__ flags, float c,
+                      unsigned long long seed, unsigned long long offset, long long numel, EdmShape sh) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  curandStatePhilox4_32_10_t state;
+  curand_init(seed, idx, offset, &state);
+  const long long T = static_cast<long long>(blockDim.x) * gridDim.x;
+  const long long rounded = ((numel - 1) / (T * 4) + 1) * T * 4;
+  const int n = sh.n;
+  for (long long li = idx; li < rounded; li += T * 4) {
+    const float4 r = curand_normal4(&state);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const long long e = li + T * ii;
+      if (e < numel) {
+        const float eps = ii == 0 ? r.x : (ii == 1 ? r.y : (ii == 2 ? r.z : r.w));
+        bool ok;
+        if (ADJ) {
+          const int j = static_cast<int>(e % n);
+          const long long rr = e / n;
+          const int i = static_cast<int>(rr % n);
+          const long long b = rr / (static_cast<long long>(n) * sh.c_e);
+          ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+        } else {
+          ok = flags[e / sh.c_n] != 0;
+        }
+        out[e] = ok ? pre_one(x[e], eps, c) : 0.f;
+      }
+    }
+  }
+}
+
 template <int MODE>
 int launch_mode(const float* a0, const float* a1, const float* a2, float* a_out, const float* n0, const float* n1,
                 const float* n2, float* n_out, const uint8_t* flags, float s0, float s1, float s2, int batch, int c_e,
@@ -156,6 +198,24 @@ int launch_edm_pre_step(const float* adj, const float* node, const float* eps_ad
                         int n, int c_n, cudaStream_t st) {
   return launch_mode<0>(adj, eps_adj, nullptr, adj_hat, node, eps_node, nullptr, node_hat, flags, noise_coef, 0.f, 0.f,
                         batch, c_e, n, c_n, st);
+}
+
+int launch_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* flags, float noise_coef,
+                               unsigned long long seed, unsigned long long offset_adj, int grid_adj,
+                               unsigned long long offset_node, int grid_node, float* adj_hat, float* node_hat, int batch,
+                               int c_e, int n, int c_n, cudaStream_t st) {
+  DSG_REQUIRE(batch > 0 && c_e > 0 && n > 0 && c_n > 0 && grid_adj > 0 && grid_node > 0,
+              "edm philox pre-step: bad shape / grid B=%d C_e=%d N=%d C_n=%d grids %d %d", batch, c_e, n, c_n, grid_adj,
+              grid_node);
+  EdmShape sh{batch, c_e, n, c_n};
+  const long long na = static_cast<long long>(batch) * c_e * n * n, nn = static_cast<long long>(batch) * n * c_n;
+  edm_pre_philox_kernel<true><<<static_cast<unsigned>(grid_adj), 256, 0, st>>>(adj, adj_hat, flags, noise_coef, seed,
+                                                                               offset_adj, na, sh);
+  DSG_LAUNCH_CHECK();
+  edm_pre_philox_kernel<false><<<static_cast<unsigned>(grid_node), 256, 0, st>>>(node, node_hat, flags, noise_coef, seed,
+                                                                                 offset_node, nn, sh);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
 }
 
 int launch_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,

@@ -178,6 +178,12 @@ int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t,
 int launch_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
                         const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch,
                         int c_e, int n, int c_n, cudaStream_t st);
+// same, eps drawn in the kernel exactly as torch.randn_like would from generator state (seed, offset_*); grid_* =
+// ATen's launch grid for a tensor of that size (see edm.cu)
+int launch_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* flags, float noise_coef,
+                               unsigned long long seed, unsigned long long offset_adj, int grid_adj,
+                               unsigned long long offset_node, int grid_node, float* adj_hat, float* node_hat, int batch,
+                               int c_e, int n, int c_n, cudaStream_t st);
 int launch_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
                          const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat,
                          float h, float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e,

@@ -886,6 +886,16 @@ int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, 
                              static_cast<cudaStream_t>(stream));
 }
 
+int dsg_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* flags, float noise_coef, uint64_t seed,
+                            uint64_t offset_adj, int grid_adj, uint64_t offset_node, int grid_node, float* adj_hat,
+                            float* node_hat, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && flags && adj_hat && node_hat, "edm_pre_step_philox: null tensor");
+  const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
+  ProfScope ps(g_prof_on, PC_EDM, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));
+  return launch_edm_pre_step_philox(adj, node, flags, noise_coef, seed, offset_adj, grid_adj, offset_node, grid_node,
+                                    adj_hat, node_hat, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
 int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
                       const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat, float h,
                       float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e, int n, int c_n,

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "dsg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "dsg_denoiser_forward": (C.c_int, [C.c_void_p, C.POINTER(DsgForwardArgs), C.c_void_p]),
     "dsg_edm_pre_step": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_pre_step_philox": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
+                                           C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_post_step": (C.c_int, [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_decode_samples": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p]),
@@ -177,6 +179,34 @@ def edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef: float):
     adj_hat, node_hat = torch.empty_like(adj), torch.empty_like(node)
     check(lib().dsg_edm_pre_step(ptr(adj), ptr(node), ptr(eps_adj), ptr(eps_node), ptr(flags), float(noise_coef),
                                  ptr(adj_hat), ptr(node_hat), b, ce, n, cn, stream_ptr(adj.device)), "dsg_edm_pre_step")
+    return adj_hat, node_hat
+
+
+def _aten_normal_policy(numel: int, dev: torch.device):
+    """(grid, counter_offset) ATen uses for `normal_` on a float tensor of `numel` elements
+    (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, block 256, unroll 4)."""
+    props = torch.cuda.get_device_properties(dev)
+    blocks_per_sm = props.max_threads_per_multi_processor // 256
+    grid = min(props.multi_processor_count * blocks_per_sm, (numel + 255) // 256)
+    return grid, ((numel - 1) // (256 * grid * 4) + 1) * 4
+
+
+def edm_pre_step_fused_noise(adj, node, flags, noise_coef: float):
+    """edm_pre_step with eps_adj = randn_like(adj), eps_node = randn_like(node) drawn inside the kernel from the
+    current torch CUDA generator state, which is advanced exactly as the two randn_like calls would advance it
+    (bit-identical results, no eps tensors; tests/test_gpu_kernels.py::test_edm_pre_step_fused_noise_matches_torch)."""
+    b, ce, n, _ = adj.shape
+    cn = node.shape[-1]
+    dev = adj.device
+    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    grid_a, inc_a = _aten_normal_policy(adj.numel(), dev)
+    grid_n, inc_n = _aten_normal_policy(node.numel(), dev)
+    gen.set_offset(off + inc_a + inc_n)
+    adj_hat, node_hat = torch.empty_like(adj), torch.empty_like(node)
+    check(lib().dsg_edm_pre_step_philox(ptr(adj), ptr(node), ptr(flags), float(noise_coef), seed, off, grid_a, off + inc_a,
+                                        grid_n, ptr(adj_hat), ptr(node_hat), b, ce, n, cn, stream_ptr(dev)),
+          "dsg_edm_pre_step_philox")
     return adj_hat, node_hat
 
 

@@ -17,6 +17,7 @@ What changed underneath:
 from __future__ import annotations
 
 import logging
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -24,6 +25,8 @@ import torch
 import torch.nn as nn
 
 from ... import native
+
+_TORCH_RANDN_LIKE = torch.randn_like
 from ..objectives.edm import get_edm_params, get_edm_sigma_deriv_t, get_edm_sigma_from_t, get_edm_t_from_sigma
 
 
@@ -64,6 +67,9 @@ class NodeAdjEDMSampler:
         self.s = lambda t: 1
         self.s_deriv = lambda t: 0
         self.last_raw_passes = 0
+        # Draw the per-step noise inside the fused pre-step kernel (bit-identical to the reference's randn_like calls
+        # and generator advance).  DSG_NO_FUSED_NOISE=1 keeps the two torch.randn_like launches.
+        self.fused_noise = os.environ.get("DSG_NO_FUSED_NOISE", "0") != "1"
 
     # ------------------------------------------------------------------------------------------------------
     def step_scalars(self, t_cur: torch.Tensor, t_next: torch.Tensor) -> dict:
@@ -151,9 +157,13 @@ class NodeAdjEDMSampler:
         for i in range(self.num_steps):
             sc = scalars[i]
             # temporary noise increase; adjacency noise is drawn first        (edm.py:355-366)
-            eps_a = torch.randn_like(adjs)
-            eps_n = torch.randn_like(nodes)
-            adjs_hat, nodes_hat = native.edm_pre_step(adjs, nodes, eps_a, eps_n, flags, sc["noise_coef"])
+            if self.fused_noise and torch.randn_like is _TORCH_RANDN_LIKE:  # a patched randn_like (noise replay) wins
+                # the two randn_like draws happen inside the kernel, from (and advancing) the same generator state
+                adjs_hat, nodes_hat = native.edm_pre_step_fused_noise(adjs, nodes, flags, sc["noise_coef"])
+            else:
+                eps_a = torch.randn_like(adjs)
+                eps_n = torch.randn_like(nodes)
+                adjs_hat, nodes_hat = native.edm_pre_step(adjs, nodes, eps_a, eps_n, flags, sc["noise_coef"])
             sigma_tensors = t_hat_dev[i].view(-1).expand(flags.size(0))
             d1 = gt if gt is not None else model(adjs_hat, nodes_hat, flags, sigma_tensors, sc_a, sc_n)
             if i == self.num_steps - 1:

@@ -127,6 +127,15 @@ DSG_API int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* args, dsg
 DSG_API int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, const float* eps_node,
                      const uint8_t* flags, float noise_coef, float* adj_hat, float* node_hat, int batch, int c_e,
                      int n, int c_n, dsg_stream_t stream);
+/* The same step with eps drawn inside the kernel, bit-identical to `eps_adj = randn_like(adjs); eps_node =
+ * randn_like(nodes)` of the reference (:358-364) on this device: Philox4x32-10 keyed by the torch CUDA generator's
+ * seed, counter offsets offset_adj / offset_node, and ATen's launch grids for tensors of those sizes
+ * (grid = min(SMs * (max threads per SM / 256), ceil(numel / 256)); ATen/native/cuda/DistributionTemplates.h).
+ * The caller advances the generator by ((numel - 1) / (256 * grid * 4) + 1) * 4 per tensor.  No eps tensor is
+ * materialised. */
+DSG_API int dsg_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* flags, float noise_coef,
+                            uint64_t seed, uint64_t offset_adj, int grid_adj, uint64_t offset_node, int grid_node,
+                            float* adj_hat, float* node_hat, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
 /* Heun update from (x_hat, D1, D2); pass d2_* = NULL for the Euler update of the last step     (:384-422).
  * inv_t_hat = 1 / t_hat, h = t_next - t_hat, inv_t_prime = 1 / (t_hat + h), all evaluated in fp32 by the caller
  * exactly as the reference does. */

@@ -316,6 +316,28 @@ def test_sampler_known_answer(golden_dir):
     assert float((a - gt_a).abs().max()) < 1e-6 and float((n - gt_n).abs().max()) < 1e-6
 
 
+def test_sampler_fused_noise_is_bit_identical():
+    """The sampler with the per-step noise drawn inside the pre-step kernel == the sampler with the reference's two
+    torch.randn_like launches per step: same seeds, bit-identical samples, same generator state afterwards."""
+    cfg = CONFIGS["tiny"]
+    net, _ = build(cfg)
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, 6, seed=9)
+    outs = []
+    for fused in (True, False):
+        sampler = NodeAdjEDMSampler(num_steps=6, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                    clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                    symmetric_noise=False)
+        sampler.fused_noise = fused
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)
+        np.random.seed(5)
+        a, n = sampler.sample(model=model, node_flags=flags.to(DEV), num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"])
+        outs.append((a, n, torch.randn(100, device=DEV).cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2])
+
+
 def test_no_cpu_fallback():
     cfg = CONFIGS["tiny"]
     m = DiffuseSG(img_size=cfg["img"], in_chans=in_chans(cfg), patch_size=1, embed_dim=96, depths=cfg["depths"],

@@ -137,6 +137,33 @@ def test_window_attention_arbitrary_mask_takes_the_generic_kernel(batch, res, w,
     assert _rel(got, want) < 1e-2, _rel(got, want)
 
 
+@pytest.mark.parametrize("b,ce,n,cn", [(3, 3, 16, 5), (8, 6, 64, 12), (512, 6, 64, 12), (5, 3, 40, 12), (1, 1, 4, 1),
+                                       (700, 3, 40, 12)])
+def test_edm_pre_step_fused_noise_matches_torch(b, ce, n, cn):
+    """Noise drawn inside the pre-step kernel (Philox4x32-10 with ATen's launch geometry) == the reference's
+    `randn_like(adjs)` then `randn_like(nodes)` on this device, bit for bit, and the torch generator ends in the same
+    state (the next torch draw is identical too)."""
+    g = torch.Generator().manual_seed(b * 7 + n)
+    flags = (torch.arange(n)[None, :] < torch.randint(1, n + 1, (b, 1), generator=g)).to(DEV)
+    adj = (torch.randn(b, ce, n, n, generator=g) * 3).to(DEV)
+    node = (torch.randn(b, n, cn, generator=g) * 3).to(DEV)
+    for seed, burn in ((1234, 0), (99, 3)):
+        torch.cuda.manual_seed(seed)
+        for _ in range(burn):
+            torch.randn(1000, device=DEV)   # start from a non-zero generator offset
+        eps_a, eps_n = torch.randn_like(adj), torch.randn_like(node)
+        want_a, want_n = native.edm_pre_step(adj, node, eps_a, eps_n, flags, 0.37)
+        next_want = torch.randn(4097, device=DEV)
+        torch.cuda.manual_seed(seed)
+        for _ in range(burn):
+            torch.randn(1000, device=DEV)
+        got_a, got_n = native.edm_pre_step_fused_noise(adj, node, flags, 0.37)
+        next_got = torch.randn(4097, device=DEV)
+        torch.cuda.synchronize()
+        assert torch.equal(got_a, want_a) and torch.equal(got_n, want_n)
+        assert torch.equal(next_got, next_want)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fused EDM step kernels: bit-exact against the fp32 expressions of the reference sampler
 # ---------------------------------------------------------------------------------------------------------
