@@ -19,6 +19,8 @@
 //   warps 0..11       three worker groups of four warps (one per tensor-memory lane quarter); group g takes items
 //                     g, g + 3, ...: softmax, then O / l -> bf16 -> swizzled staging
 // A CTA keeps one head (its relative-position bias sits in shared memory) and walks window pairs.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -180,21 +182,22 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
       __syncwarp();
     }
   } else if (warp == kLoadWarp) {
-    // ------------------------------------------------------------------ loader
-    if (elect_one()) {
-      for (int k = 0; k < n_items; ++k) {
-        const int st = k % kTcStages;
-        const int pair = cta_in_head + k * ctas_per_head;
-        mbar_wait(&stage_empty[st], ((k / kTcStages) & 1) ^ 1);
-        mbar_expect_tx(&stage_full[st], kTcStageBytes);
-        uint8_t* base = sStage + st * kTcStageBytes;
-        for (int w = 0; w < 2; ++w) {
-          int cx, cy;
-          win_coords(2 * pair + w, cx, cy);
-          for (int part = 0; part < 3; ++part)
-            tma_load_3d(base + part * 8192 + w * 4096, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
-        }
+    // ------------------------------------------------------------------ loader (lanes 0..5: one 4 KB box each)
+    // One thread issuing the six boxes back to back is bound by the TMA issue latency (~330 clk per box: 3.6 TB/s of
+    // loads over the chip); six lanes issuing in parallel reach the HBM rate (tools/microbench/tma_rows_bench.cu).
+    for (int k = 0; k < n_items; ++k) {
+      const int st = k % kTcStages;
+      const int pair = cta_in_head + k * ctas_per_head;
+      mbar_wait(&stage_empty[st], ((k / kTcStages) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&stage_full[st], kTcStageBytes);
+      __syncwarp();
+      if (lane < 6) {
+        const int w = lane / 3, part = lane - 3 * w;
+        int cx, cy;
+        win_coords(2 * pair + w, cx, cy);
+        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
       }
+      __syncwarp();
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
@@ -234,30 +237,27 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     }
   } else if (warp == kStoreWarp) {
     // ------------------------------------------------------------------ storer
-    if (elect_one()) {
-      for (int k = 0; k < n_items; ++k) {
-        const int g = k % 3;
-        const int pair = cta_in_head + k * ctas_per_head;
-        mbar_wait(&out_ready[g], (k / 3) & 1);
+    // one box per lane (8 sub-boxes / 2 windows), each lane tracks its own bulk group
+    for (int k = 0; k < n_items; ++k) {
+      const int g = k % 3;
+      const int pair = cta_in_head + k * ctas_per_head;
+      mbar_wait(&out_ready[g], (k / 3) & 1);
+      if (lane < (SHIFTED ? 8 : 2)) {
+        int cx, cy;
         if (SHIFTED) {
-          for (int ws = 0; ws < 8; ++ws) {
-            int cx, cy;
-            sub_coords(2 * pair + (ws >> 2), ws & 3, cx, cy);
-            tma_store_3d(&tmOut, sOut + g * 8192 + ws * 1024, h * 32, cx, cy);
-          }
+          sub_coords(2 * pair + (lane >> 2), lane & 3, cx, cy);
+          tma_store_3d(&tmOut, sOut + g * 8192 + lane * 1024, h * 32, cx, cy);
         } else {
-          for (int w = 0; w < 2; ++w) {
-            int cx, cy;
-            win_coords(2 * pair + w, cx, cy);
-            tma_store_3d(&tmOut, sOut + g * 8192 + w * 4096, h * 32, cx, cy);
-          }
+          win_coords(2 * pair + lane, cx, cy);
+          tma_store_3d(&tmOut, sOut + g * 8192 + lane * 4096, h * 32, cx, cy);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(&out_free[g]);
       }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_free[g]);
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ------------------------------------------------------------------ worker groups
     const int g = warp >> 2, q = warp & 3;
@@ -368,7 +368,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
 constexpr int kQdBiasPitch = 132;  // floats per bias row: 16-byte aligned, conflict-free row-per-lane float4 reads
 constexpr int kQdGroups = 4;       // worker groups = items in flight = tensor-memory slots
 constexpr int kQdStages = 5;
-constexpr int kQdThreads = (4 * kQdGroups + 3) * 32;
+constexpr int kQdThreads = (4 * kQdGroups + 4) * 32;  // workers + loader, S issuer, storer, P.V issuer
 constexpr int kQdSlotCols = 128;   // S 128 columns; P aliases [0, 64), O aliases [64, 96) (dead once pass 2 has read them)
 constexpr int kQdSmemBytes = 1024 + kQdStages * kTcStageBytes + kQdGroups * 8192 + 128 * kQdBiasPitch * 4 + 512 /*barriers*/;
 static_assert(kQdSmemBytes <= 227 * 1024, "shared memory budget");
@@ -379,7 +379,10 @@ struct QdParams {
   int items;          // windows = B * nW
 };
 
-template <int HW>  // sub-box edge = window / 2
+// SHIFTED = false (15 of the 18 COCO launches): the window is ONE w x w TMA box per operand in natural token order
+// (rows >= w^2 are the zero pad) - a 5 x 5 sub-box costs the TMA unit ~5 clk per 64-byte token row, a 10 x 10 box ~2.6
+// (tools/microbench/tma_rows_bench.cu), and the four-sub-box gather was what bounded the kernel.
+template <int HW, bool SHIFTED>  // sub-box edge = window / 2
 __global__ void __launch_bounds__(kQdThreads, 1)
 window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
                              const QdParams p) {
@@ -401,14 +404,17 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
-  constexpr int kLoadWarp = 4 * kQdGroups, kMmaWarp = kLoadWarp + 1, kStoreWarp = kLoadWarp + 2;
+  constexpr int kLoadWarp = 4 * kQdGroups, kMmaWarp = kLoadWarp + 1, kStoreWarp = kLoadWarp + 2, kPvWarp = kLoadWarp + 3;
   const int h = blockIdx.x % p.heads;
   const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
   const int n_items = (p.items > cta_in_head) ? (p.items - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
   const int C = p.heads * 32;
   constexpr int hw = HW, sub = HW * HW;
-  constexpr int SUB = HW * HW;               // valid rows / key columns per 32-row sub-box slot
-  constexpr int NVC = ((SUB + 3) / 4) * 4;   // key columns the softmax touches per slot (pads inside carry bias -inf)
+  constexpr int SUB = HW * HW;               // SHIFTED: valid rows / key columns per 32-row sub-box slot
+  constexpr int T = 4 * SUB;                 // tokens of a window
+  // valid key columns of the 32-column chunk j (the softmax touches them rounded up to 4; pads inside carry bias -inf)
+  auto vc = [](int jc) constexpr { return SHIFTED ? SUB : (T - 32 * jc >= 32 ? 32 : (T - 32 * jc > 0 ? T - 32 * jc : 0)); };
+  constexpr int VC0 = vc(0), VC1 = vc(1), VC2 = vc(2), VC3 = vc(3);
   constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == kLoadWarp && lane == 0) {
@@ -433,6 +439,7 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
     // bias tile in quad order; row / column r = 32 slot + (ry hw + rx)  <->  token (by hw + ry) w + (bx hw + rx)
     const float* bh = p.bias + static_cast<size_t>(h) * p.T * p.T;
     auto token = [&](int r) {
+      if (!SHIFTED) return r < T ? r : -1;
       const int slot = r >> 5, i = r & 31;
       if (i >= sub) return -1;
       const int ry = i / hw, rx = i - ry * hw;
@@ -467,23 +474,23 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
 
   if (warp == kLoadWarp) {
     // ------------------------------------------------------------------ loader (lanes 0..11: one box each)
-    const uint32_t box_bytes = static_cast<uint32_t>(sub) * 64u;
+    const uint32_t box_bytes = static_cast<uint32_t>(SHIFTED ? sub : T) * 64u;
     for (int k = 0; k < n_items; ++k) {
       const int st = k % kQdStages;
       const int gw = cta_in_head + k * ctas_per_head;
       mbar_wait(&stage_empty[st], ((k / kQdStages) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&stage_full[st], 12u * box_bytes);
+      if (lane == 0) mbar_expect_tx(&stage_full[st], (SHIFTED ? 12u : 3u) * box_bytes);
       __syncwarp();
-      if (lane < 12) {
-        const int part = lane >> 2, slot = lane & 3;
+      if (lane < (SHIFTED ? 12 : 3)) {
+        const int part = SHIFTED ? lane >> 2 : lane, slot = SHIFTED ? lane & 3 : 0;
         int cx, cy;
-        box_coords(gw, slot, cx, cy);
+        box_coords(gw, slot, cx, cy);  // slot 0 of an un-shifted window = its top-left token
         tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + slot * 2048, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
       }
       __syncwarp();
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == kMmaWarp || warp == kPvWarp) {
+    // ------------------------------------------------------------------ MMA issuers
     constexpr uint32_t idesc_s = umma_idesc_bf16(128);
     constexpr uint32_t idesc_o = idesc_bf16_bmn(32);
     auto issue_s = [&](int k) {
@@ -512,30 +519,32 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
       }
       __syncwarp();
     };
-    for (int k = 0; k < kQdGroups - 1; ++k)
-      if (k < n_items) issue_s(k);
-    for (int k = 0; k < n_items; ++k) {
-      issue_pv(k);
-      if (k + kQdGroups - 1 < n_items) issue_s(k + kQdGroups - 1);
+    // Two issuing warps, so that neither waits behind the other's barrier: this one issues S(k) as soon as the
+    // operands have landed and the tensor-memory slot has been drained, the P.V warp issues P.V(k) as soon as the
+    // probabilities are in place.  (With one warp issuing  P.V(k), S(k + 3)  in order, a group waited for another
+    // group's softmax before it got its next scores: ncu showed the workers 46 % in barrier waits.)
+    if (warp == kMmaWarp) {
+      for (int k = 0; k < n_items; ++k) issue_s(k);
+    } else {
+      for (int k = 0; k < n_items; ++k) issue_pv(k);
     }
   } else if (warp == kStoreWarp) {
     // ------------------------------------------------------------------ storer
-    if (elect_one()) {
-      for (int k = 0; k < n_items; ++k) {
-        const int g = k % kQdGroups;
-        const int gw = cta_in_head + k * ctas_per_head;
-        mbar_wait(&out_ready[g], (k / kQdGroups) & 1);
-        for (int slot = 0; slot < 4; ++slot) {
-          int cx, cy;
-          box_coords(gw, slot, cx, cy);
-          tma_store_3d(&tmOut, sOut + g * 8192 + slot * 2048, h * 32, cx, cy);
-        }
+    for (int k = 0; k < n_items; ++k) {   // one box per lane, each lane tracks its own bulk group
+      const int g = k % kQdGroups;
+      const int gw = cta_in_head + k * ctas_per_head;
+      mbar_wait(&out_ready[g], (k / kQdGroups) & 1);
+      if (lane < (SHIFTED ? 4 : 1)) {
+        int cx, cy;
+        box_coords(gw, lane, cx, cy);
+        tma_store_3d(&tmOut, sOut + g * 8192 + lane * 2048, h * 32, cx, cy);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        mbar_arrive(&out_free[g]);
       }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_free[g]);
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ------------------------------------------------------------------ worker groups
     const int g = warp >> 2, q = warp & 3;   // q = tensor-memory lane quarter = the query's sub-box
@@ -548,12 +557,13 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-      for (int c = 0; c < SUB; ++c) bmax = fmaxf(bmax, brow[32 * jj + c]);
+      for (int c = 0; c < 32; ++c)
+        if (c < vc(jj)) bmax = fmaxf(bmax, brow[32 * jj + c]);
     const f32x2 l2e2 = f2_splat(kLog2e);
     for (int k = g, it = 0; k < n_items; k += kQdGroups, ++it) {
       // SW-MSA mask of this window, per key sub-box j (times log2 e): -100 where the region codes differ
       float mk0 = 0.f, mk1 = 0.f, mk2 = 0.f, mk3 = 0.f;
-      if (p.shift > 0) {
+      if (SHIFTED && p.shift > 0) {
         const int gw = cta_in_head + k * ctas_per_head;
         const int win = gw % p.nW;
         const int wy = win / p.nwx, wx = win - wy * p.nwx;
@@ -568,29 +578,36 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
       mbar_wait(&s_full[g], it & 1);
       tcgen05_fence_after();
       uint32_t bufA[32], bufB[32];
-      auto row_max = [&](const uint32_t (&sv)[32]) {
+      auto row_max = [&](const uint32_t (&sv)[32], auto nc) {  // over the valid columns of the chunk
+        constexpr int n = decltype(nc)::value;
         float m0 = __uint_as_float(sv[0]);
 #pragma unroll
-        for (int c = 1; c < SUB; ++c) m0 = fmaxf(m0, __uint_as_float(sv[c]));
+        for (int c = 1; c < n; ++c) m0 = fmaxf(m0, __uint_as_float(sv[c]));
         return m0;
       };
       // ---- pass 1: upper bound of the row maximum of  s log2(e) + bias' + mask
       tmem_ld_32x32(t_s, bufA);
-      tmem_ld_32x32(t_s + 32, bufB);
+      if (VC1 > 0) tmem_ld_32x32(t_s + 32, bufB);
       tmem_ld_wait();
-      float m = fmaxf(fmaf(row_max(bufA), kLog2e, mk0), fmaf(row_max(bufB), kLog2e, mk1));
-      tmem_ld_32x32(t_s + 64, bufA);
-      tmem_ld_32x32(t_s + 96, bufB);
-      tmem_ld_wait();
-      m = fmaxf(m, fmaxf(fmaf(row_max(bufA), kLog2e, mk2), fmaf(row_max(bufB), kLog2e, mk3))) + bmax;
+      float m = fmaf(row_max(bufA, std::integral_constant<int, VC0>{}), kLog2e, mk0);
+      if (VC1 > 0) m = fmaxf(m, fmaf(row_max(bufB, std::integral_constant<int, (VC1 > 0 ? VC1 : 1)>{}), kLog2e, mk1));
+      if (VC2 > 0) {
+        tmem_ld_32x32(t_s + 64, bufA);
+        if (VC3 > 0) tmem_ld_32x32(t_s + 96, bufB);
+        tmem_ld_wait();
+        m = fmaxf(m, fmaf(row_max(bufA, std::integral_constant<int, (VC2 > 0 ? VC2 : 1)>{}), kLog2e, mk2));
+        if (VC3 > 0) m = fmaxf(m, fmaf(row_max(bufB, std::integral_constant<int, (VC3 > 0 ? VC3 : 1)>{}), kLog2e, mk3));
+      }
+      m += bmax;
       // ---- pass 2: p = exp2(. - m) on packed pairs, row sum, bf16 pairs written in place over consumed scores
       f32x2 lsum = f2_splat(0.f);
-      auto chunk = [&](const uint32_t (&sv)[32], int jj, float mkj) {
+      auto chunk = [&](const uint32_t (&sv)[32], int jj, float mkj, auto nc) {
+        constexpr int nvc = (decltype(nc)::value + 3) / 4 * 4;
         const f32x2 cj = f2_splat(mkj - m);
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          if (c < NVC) {
+          if (c < nvc) {
             const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * jj + c);
             f32x2 t0 = f2_fma(f2_pack(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), l2e2, f2_pack(bb.x, bb.y));
             f32x2 t1 = f2_fma(f2_pack(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), l2e2, f2_pack(bb.z, bb.w));
@@ -611,18 +628,35 @@ window_attention_quad_kernel(const __grid_constant__ CUtensorMap tmQkv, const __
         tmem_st8_tc(t_s + 16 * jj, pk);
         tmem_st8_tc(t_s + 16 * jj + 8, pk + 8);
       };
+      auto zero_chunk = [&](int jj) {  // a chunk of pad keys only
+        const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8_tc(t_s + 16 * jj, z);
+        tmem_st8_tc(t_s + 16 * jj + 8, z);
+      };
       tmem_ld_32x32(t_s, bufA);
       tmem_ld_wait();
-      tmem_ld_32x32(t_s + 32, bufB);
-      chunk(bufA, 0, mk0);
-      tmem_ld_wait();
-      tmem_ld_32x32(t_s + 64, bufA);
-      chunk(bufB, 1, mk1);
-      tmem_ld_wait();
-      tmem_ld_32x32(t_s + 96, bufB);
-      chunk(bufA, 2, mk2);
-      tmem_ld_wait();
-      chunk(bufB, 3, mk3);
+      if (VC1 > 0) tmem_ld_32x32(t_s + 32, bufB);
+      chunk(bufA, 0, mk0, std::integral_constant<int, VC0>{});
+      if (VC1 > 0) {
+        tmem_ld_wait();
+        if (VC2 > 0) tmem_ld_32x32(t_s + 64, bufA);
+        chunk(bufB, 1, mk1, std::integral_constant<int, VC1>{});
+      } else {
+        zero_chunk(1);
+      }
+      if (VC2 > 0) {
+        tmem_ld_wait();
+        if (VC3 > 0) tmem_ld_32x32(t_s + 96, bufB);
+        chunk(bufA, 2, mk2, std::integral_constant<int, VC2>{});
+      } else {
+        zero_chunk(2);
+      }
+      if (VC3 > 0) {
+        tmem_ld_wait();
+        chunk(bufB, 3, mk3, std::integral_constant<int, VC3>{});
+      } else {
+        zero_chunk(3);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       __syncwarp();
@@ -1146,10 +1180,11 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
   DSG_REQUIRE(window_attention_quad_supported(batch, res, window, shift, heads), "attention_quad: unsupported shape");
   const int C = heads * 32;
   const int hw = window / 2;
+  const int box = shift ? hw : window;  // shifted: four sub-boxes per window; un-shifted: the whole window
   CUtensorMap tq, to;
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, hw, hw))
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
     return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, hw, hw))
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
   static int sms = 0;
   if (sms == 0) {
@@ -1179,11 +1214,14 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
   case H: {                                                                                                               \
     static bool configured = false;                                                                                       \
     if (!configured) {                                                                                                    \
-      DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                          kQdSmemBytes));                                                                 \
+      DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H, false>,                                         \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));                    \
+      DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H, true>,                                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));                    \
       configured = true;                                                                                                  \
     }                                                                                                                     \
-    window_attention_quad_kernel<H><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);                       \
+    if (shift) window_attention_quad_kernel<H, true><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);      \
+    else window_attention_quad_kernel<H, false><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);           \
     break;                                                                                                                \
   }
     DSG_QUAD_CASE(1)
