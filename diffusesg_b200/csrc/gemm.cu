@@ -116,26 +116,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = cta; tile < num_tiles; tile += ncta) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (PAIR) {
-            // this CTA's 128 rows of A and its half of the B tile; both CTAs' bytes complete on the LEADER's barrier
-            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-            const uint32_t lbar = mapa_u32(&full_bar[s], 0);
+    // The A box and the B box of a stage are issued by TWO lanes: one thread issuing boxes back to back is bound by
+    // the TMA issue latency (~400 clk per 16 KB box = 40 B/clk per SM), two lanes in parallel reach 60 B/clk per SM
+    // (tools/microbench/tma_rows_bench.cu).  Measured on the K = 384 shapes this changes nothing (still ~42 B/clk
+    // per SM = 920 TFLOP/s with 128 x 192 tiles): the cap is inside the SM - an SS-mode MMA reads 10 KB of operands
+    // per 96 clk from the same shared memory the TMA writes 40 KB per k-block into - not in the L2 or the issue path.
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = cta; tile < num_tiles; tile += ncta) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (PAIR) {
+          // this CTA's 128 rows of A and its half of the B tile; both CTAs' bytes complete on the LEADER's barrier
+          if (lane == 0 && rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          __syncwarp();
+          const uint32_t lbar = mapa_u32(&full_bar[s], 0);
+          if (lane == 0)
             tma_load_2d_pair(sA + s * A_STAGE_BYTES, &tmA, lbar, kb * BK, (m_blk * 2 + static_cast<int>(rank)) * BM);
+          else if (lane == 1)
             tma_load_2d_pair(sB + s * C::B_STAGE_BYTES, &tmW, lbar, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
-          } else {
-            mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-            tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-            tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n_blk * BN);
-          }
-          if (++s == kStages) { s = 0; ph ^= 1; }
+        } else {
+          if (lane == 0) mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          __syncwarp();
+          if (lane == 0) tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+          else if (lane == 1) tma_load_2d(sB + s * C::B_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n_blk * BN);
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == kMmaWarp && rank == 0) {

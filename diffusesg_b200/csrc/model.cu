@@ -421,8 +421,9 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   ProfScope ps(g_prof_pass, PC_GEMM, 2.0 * mn * W.K,
                static_cast<double>(rows) * W.K * 2 + static_cast<double>(W.N) * W.K * 2 + out_bytes +
                    (epi == EPI_RES_F32 ? mn * 4 : 0), st, label, rows, W.K);
-  // CTA pairs cut the L2 -> SM operand traffic per flop by 30 %, which is what bounds the single-CTA tiles (the L2
-  // delivers ~6300 B/clk chip-wide = 40 KB per 128 x 192 x 64 step -> ~920 TFLOP/s).  Measured (same box, A/B):
+  // CTA pairs cut the operand bytes a CTA's shared memory takes in (and serves to the tensor core) per flop by 30 %,
+  // which is what bounds the single-CTA tiles at ~42 B/clk per SM = 40 KB per 128 x 192 x 64 step -> ~920 TFLOP/s
+  // (not the L2: a TMA-only microbenchmark reaches 60 B/clk per SM from L2).  Measured (same box, A/B):
   // +10..18 % for K >= 768; at K = 384 +3..10 % for the plain bf16 epilogue (qkv), -8 % for fc1 (its GELU epilogue
   // is the co-bound and loses its slack), -2 % for the HBM-bound residual epilogue; K <= 192 shapes are HBM-bound.
   const bool pair = m->use_pair && epi != EPI_ADJ_HEAD && rows >= 256 &&
