@@ -314,8 +314,16 @@ def run_native(args, cfg, rank, local_rank, world):
     edm_roof = None
     if edm and edm["ms"]:
         gbs = edm["bytes"] / (edm["ms"] * 1e-3) / 1e9
-        edm_roof = {"bound": "hbm", "kernel": "edm_kernel<MODE> (fused pre / post step)", "achieved": gbs, "peak": pk["hbm"],
-                    "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": ncu_traffic_per_launch(r"edm_kernel")}
+        edm_roof = {"bound": "hbm", "kernel": "edm_kernel<MODE> (fused Heun / Euler post step, initial mask-scale)", "achieved": gbs,
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": ncu_traffic_per_launch(r"edm_kernel")}
+        nz = prof.get("edm_pre_step_philox")
+        if nz and nz["ms"]:
+            # the pre-step draws its noise in the kernel (same Philox4x32-10 / Box-Muller work as the two torch.randn_like
+            # launches it replaces): ALU-bound, reported as normals per second next to its HBM rate
+            edm_roof["pre_step_with_noise"] = {"kernel": "edm_pre_philox_kernel<ADJ> (x + c * eps with eps drawn in the kernel)",
+                                               "bound": "alu (Philox4x32-10 + Box-Muller, bit-compatible with torch.randn_like)",
+                                               "gnormals_per_s": nz["bytes"] / 8 / (nz["ms"] * 1e-3) / 1e9,
+                                               "gbs": nz["bytes"] / (nz["ms"] * 1e-3) / 1e9, "launches_timed": nz["launches"]}
     flops_step = passes * GFLOP_PER_PASS.get(args.config, 0.0) * 1e9 * B
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -45,9 +45,9 @@ void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned 
 // ------------------------------------------------------------------------------------------------
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
 // ------------------------------------------------------------------------------------------------
-enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_MLP, PC_COUNT };
+enum ProfClass { PC_GEMM = 0, PC_ATTN, PC_ROW, PC_EMBED_HEAD, PC_EDM, PC_MLP, PC_EDM_NOISE, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"gemm_tcgen05", "window_attention", "row_ln_film", "embed_heads_cond", "edm_step",
-                                           "fused_mlp_tcgen05"};
+                                           "fused_mlp_tcgen05", "edm_pre_step_philox"};
 struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; char label[56]; long long rows; int c; };
 static bool g_prof_on = false;        // between dsg_profile_begin and dsg_profile_stop
 static bool g_prof_pass = false;      // the current denoiser pass is being bracketed
@@ -892,7 +892,7 @@ int dsg_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* 
                             float* node_hat, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
   DSG_REQUIRE(adj && node && flags && adj_hat && node_hat, "edm_pre_step_philox: null tensor");
   const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
-  ProfScope ps(g_prof_on, PC_EDM, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));
+  ProfScope ps(g_prof_on, PC_EDM_NOISE, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));  // Philox / Box-Muller bound
   return launch_edm_pre_step_philox(adj, node, flags, noise_coef, seed, offset_adj, grid_adj, offset_node, grid_node,
                                     adj_hat, node_hat, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
 }
