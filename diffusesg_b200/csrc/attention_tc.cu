@@ -13,11 +13,12 @@
 // reductions, 32 mma.sync) and runs at half the HBM rate; here a thread owns a whole score row and the item costs
 // ~450 issue slots per row.
 //
-//   warp 12  loader   q, k, v boxes of the two windows of an item (6 x 4 KB per stage, 4-stage ring)
-//   warp 13  MMA      S(k + 2) is issued after PV(k): three items in flight, one tensor-memory slot per worker group
-//   warp 14  storer   output boxes (bf16, 2 x 4 KB per item) -> TMA store
-//   warps 0..11       three worker groups of four warps (one per tensor-memory lane quarter); group g takes items
-//                     g, g + 3, ...: softmax, then O / l -> bf16 -> swizzled staging
+//   warp 16  loader   q, k, v boxes of the two windows of an item (6 x 4 KB per stage, 5-stage ring), one box per lane
+//   warp 17  MMA      S(k + 3) is issued after PV(k): four items in flight, one tensor-memory slot per worker group
+//                     (S 128 columns; P aliases columns [0, 64), O aliases [64, 96): both regions are dead by then)
+//   warp 18  storer   output boxes (bf16, 2 x 4 KB per item) -> TMA store
+//   warps 0..15       four worker groups of four warps (one per tensor-memory lane quarter); group g takes items
+//                     g, g + 4, ...: row-max bound from the raw scores, exp2 on packed pairs, O / l -> bf16 -> staging
 // A CTA keeps one head (its relative-position bias sits in shared memory) and walks window pairs.
 #include <type_traits>
 
@@ -27,12 +28,13 @@
 namespace dsg {
 namespace {
 
-constexpr int kTcThreads = 15 * 32;
-constexpr int kTcStages = 4;
+constexpr int kTcGroups = 4;                 // worker groups = items in flight = tensor-memory slots
+constexpr int kTcThreads = (4 * kTcGroups + 3) * 32;
+constexpr int kTcStages = 5;
 constexpr int kTcStageBytes = 3 * 8192;      // q | k | v, each [128 tokens x 32] bf16 (two windows)
 constexpr int kTcBiasPitch = 68;             // floats per bias row: 16-byte aligned, conflict-free row-per-lane reads
-constexpr int kTcSlotCols = 160;             // tensor-memory columns per item: S 128 (P aliases the first 64) + O 32
-constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + 3 * 8192 + 64 * kTcBiasPitch * 4 + 256;
+constexpr int kTcSlotCols = 128;             // tensor-memory columns per item: S 128; P aliases [0, 64), O aliases [64, 96)
+constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + kTcGroups * 8192 + 64 * kTcBiasPitch * 4 + 512;
 
 struct TcParams {
   const float* bias;  // [heads, 64, 64]
@@ -95,22 +97,22 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem;
-  uint8_t* sOut = sStage + kTcStages * kTcStageBytes;                  // [3 groups][2 windows][64 x 64 B]
-  float* sBias = reinterpret_cast<float*>(sOut + 3 * 8192);            // [64][68]
+  uint8_t* sOut = sStage + kTcStages * kTcStageBytes;                  // [groups][2 windows][64 x 64 B]
+  float* sBias = reinterpret_cast<float*>(sOut + kTcGroups * 8192);    // [64][68], times log2(e)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64 * kTcBiasPitch);
   uint64_t* stage_full = bars;                     // [4]
   uint64_t* stage_empty = bars + kTcStages;        // [4]
-  uint64_t* s_full = bars + 2 * kTcStages;         // [3] MMA -> group: scores complete
-  uint64_t* p_ready = s_full + 3;                  // [3] group -> MMA: probabilities in place
-  uint64_t* o_full = s_full + 6;                   // [3] MMA -> group: P.V complete
-  uint64_t* slot_free = s_full + 9;                // [3] group -> MMA: O read, the slot may take the next item
-  uint64_t* out_ready = s_full + 12;               // [3] group -> storer
-  uint64_t* out_free = s_full + 15;                // [3] storer -> group
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 18);
+  uint64_t* s_full = bars + 2 * kTcStages;         // [groups] MMA -> group: scores complete
+  uint64_t* p_ready = s_full + kTcGroups;          // group -> MMA: probabilities in place
+  uint64_t* o_full = s_full + 2 * kTcGroups;       // MMA -> group: P.V complete
+  uint64_t* slot_free = s_full + 3 * kTcGroups;    // group -> MMA: O read, the slot may take the next item
+  uint64_t* out_ready = s_full + 4 * kTcGroups;    // group -> storer
+  uint64_t* out_free = s_full + 5 * kTcGroups;     // storer -> group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6 * kTcGroups);
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
-  constexpr int kLoadWarp = 12, kMmaWarp = 13, kStoreWarp = 14;
+  constexpr int kLoadWarp = 4 * kTcGroups, kMmaWarp = kLoadWarp + 1, kStoreWarp = kLoadWarp + 2;
   const int h = blockIdx.x % p.heads;
   const int cta_in_head = blockIdx.x / p.heads, ctas_per_head = gridDim.x / p.heads;
   const int n_items = (p.pairs > cta_in_head) ? (p.pairs - cta_in_head + ctas_per_head - 1) / ctas_per_head : 0;
@@ -120,7 +122,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     tma_prefetch_desc(&tmQkv);
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
-    for (int g = 0; g < 3; ++g) {
+    for (int g = 0; g < kTcGroups; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&p_ready[g], 4);
       mbar_init(&o_full[g], 1);
@@ -137,7 +139,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
       return SHIFTED ? (((r >> 5) * 4 + ((r >> 2) & 3)) * 8 + ((r >> 4) & 1) * 4 + (r & 3)) : r;
     };
     for (int i = threadIdx.x; i < 64 * 64; i += kTcThreads)
-      sBias[(i >> 6) * kTcBiasPitch + (i & 63)] = bh[token(i >> 6) * 64 + token(i & 63)];
+      sBias[(i >> 6) * kTcBiasPitch + (i & 63)] = bh[token(i >> 6) * 64 + token(i & 63)] * 1.4426950408889634f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -204,9 +206,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     constexpr uint32_t idesc_s = umma_idesc_bf16(128);   // S: N = 128 keys, both operands K-major
     constexpr uint32_t idesc_o = idesc_bf16_bmn(32);     // O: N = 32 dims, V is MN-major
     auto issue_s = [&](int k) {
-      const int st = k % kTcStages, g = k % 3;
+      const int st = k % kTcStages, g = k % kTcGroups;
       mbar_wait(&stage_full[st], (k / kTcStages) & 1);
-      mbar_wait(&slot_free[g], ((k / 3) & 1) ^ 1);
+      mbar_wait(&slot_free[g], ((k / kTcGroups) & 1) ^ 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint64_t da = desc_sw64_kmajor(smem_u32(sStage + st * kTcStageBytes));
@@ -217,31 +219,31 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
       __syncwarp();
     };
     auto issue_pv = [&](int k) {
-      const int st = k % kTcStages, g = k % 3;
-      mbar_wait(&p_ready[g], (k / 3) & 1);
+      const int st = k % kTcStages, g = k % kTcGroups;
+      mbar_wait(&p_ready[g], (k / kTcGroups) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint64_t dv = desc_sw64_mnmajor(smem_u32(sStage + st * kTcStageBytes + 16384));
         for (int ks = 0; ks < 8; ++ks)  // 16 keys per step: 8 packed P columns, 16 V rows (1024 bytes)
-          umma_ts_tc(tmem_base + g * kTcSlotCols + 128, tmem_base + g * kTcSlotCols + ks * 8, dv + 64 * ks, idesc_o, ks != 0);
+          umma_ts_tc(tmem_base + g * kTcSlotCols + 64, tmem_base + g * kTcSlotCols + ks * 8, dv + 64 * ks, idesc_o, ks != 0);
         umma_commit(&o_full[g]);
         umma_commit(&stage_empty[st]);
       }
       __syncwarp();
     };
-    if (n_items > 0) issue_s(0);
-    if (n_items > 1) issue_s(1);
+    for (int k = 0; k < kTcGroups - 1; ++k)
+      if (k < n_items) issue_s(k);
     for (int k = 0; k < n_items; ++k) {
       issue_pv(k);
-      if (k + 2 < n_items) issue_s(k + 2);
+      if (k + kTcGroups - 1 < n_items) issue_s(k + kTcGroups - 1);
     }
   } else if (warp == kStoreWarp) {
     // ------------------------------------------------------------------ storer
     // one box per lane (8 sub-boxes / 2 windows), each lane tracks its own bulk group
     for (int k = 0; k < n_items; ++k) {
-      const int g = k % 3;
+      const int g = k % kTcGroups;
       const int pair = cta_in_head + k * ctas_per_head;
-      mbar_wait(&out_ready[g], (k / 3) & 1);
+      mbar_wait(&out_ready[g], (k / kTcGroups) & 1);
       if (lane < (SHIFTED ? 8 : 2)) {
         int cx, cy;
         if (SHIFTED) {
@@ -266,8 +268,14 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kTcSlotCols;
     const float* brow = sBias + tq * kTcBiasPitch;
     constexpr float kLog2e = 1.4426950408889634f;
-    for (int k = g, it = 0; k < n_items; k += 3, ++it) {
-      float mk[4] = {0.f, 0.f, 0.f, 0.f};  // SW-MSA mask of this row's window, per key sub-box
+    // largest bias of the row: with the largest raw score it bounds the row maximum from above (at most range(bias)
+    // too high: no underflow), so no separate max pass over score + bias is needed
+    float bmax = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) bmax = fmaxf(bmax, brow[c]);
+    const f32x2 l2e2 = f2_splat(kLog2e);
+    for (int k = g, it = 0; k < n_items; k += kTcGroups, ++it) {
+      float mk[4] = {0.f, 0.f, 0.f, 0.f};  // SW-MSA mask of this row's window (times log2 e), per key sub-box
       if (SHIFTED) {
         const int gw = 2 * (cta_in_head + k * ctas_per_head) + w;
         const int win = gw % p.nW;
@@ -275,53 +283,70 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
         const int sel = ((wy == p.nwx - 1) ? 2 : 0) | ((wx == p.nwx - 1) ? 1 : 0);
         const int code_q = (tq >> 4) & sel;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mk[j] = ((j & sel) != code_q) ? -100.f : 0.f;
+        for (int j = 0; j < 4; ++j) mk[j] = ((j & sel) != code_q) ? -100.f * kLog2e : 0.f;
       }
       mbar_wait(&s_full[g], it & 1);
       tcgen05_fence_after();
-      // the 64 scores of this row's own window: columns [64 w, 64 w + 64)
-      uint32_t sv[64];
-#pragma unroll
-      for (int c = 0; c < 64; c += 16) tmem_ld_32x16(t_s + 64 * w + c, reinterpret_cast<uint32_t(&)[16]>(sv[c]));
+      // the 64 scores of this row's own window: columns [64 w, 64 w + 64), two chunks of 32
+      uint32_t bufA[32], bufB[32];
+      tmem_ld_32x32(t_s + 64 * w, bufA);
+      tmem_ld_32x32(t_s + 64 * w + 32, bufB);
       tmem_ld_wait();
-      float m = -INFINITY;
+      auto max16 = [&](const uint32_t (&sv)[32], int o) {
+        float m0 = __uint_as_float(sv[o]);
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        float4 bb = *reinterpret_cast<const float4*>(brow + c);
-        if (SHIFTED) { bb.x += mk[c >> 4]; bb.y += mk[c >> 4]; bb.z += mk[c >> 4]; bb.w += mk[c >> 4]; }
-        const float a0 = __uint_as_float(sv[c]) + bb.x, a1 = __uint_as_float(sv[c + 1]) + bb.y;
-        const float a2 = __uint_as_float(sv[c + 2]) + bb.z, a3 = __uint_as_float(sv[c + 3]) + bb.w;
-        sv[c] = __float_as_uint(a0); sv[c + 1] = __float_as_uint(a1);
-        sv[c + 2] = __float_as_uint(a2); sv[c + 3] = __float_as_uint(a3);
-        m = fmaxf(m, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+        for (int c = 1; c < 16; ++c) m0 = fmaxf(m0, __uint_as_float(sv[o + c]));
+        return m0;
+      };
+      float m;
+      if (SHIFTED) {
+        m = fmaxf(fmaxf(fmaf(max16(bufA, 0), kLog2e, mk[0]), fmaf(max16(bufA, 16), kLog2e, mk[1])),
+                  fmaxf(fmaf(max16(bufB, 0), kLog2e, mk[2]), fmaf(max16(bufB, 16), kLog2e, mk[3]))) + bmax;
+      } else {
+        m = fmaxf(fmaxf(max16(bufA, 0), max16(bufA, 16)), fmaxf(max16(bufB, 0), max16(bufB, 16))) * kLog2e + bmax;
       }
-      const float ms = m * kLog2e;
-      float l = 0.f;
-      uint32_t pk[32];
+      f32x2 lsum = f2_splat(0.f);
+      auto chunk = [&](const uint32_t (&sv)[32], int ch) {  // keys [32 ch, 32 ch + 32) of the own window
+        uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c]), kLog2e, -ms));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), kLog2e, -ms));
-        l += e0 + e1;
-        pk[c >> 1] = pack_bf16x2(e0, e1);
-      }
-      // P over the 128 keys of the tile: own window's 64 keys (32 packed columns at 32 w), zeros for the other window
-      uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        for (int c = 0; c < 32; c += 4) {
+          const f32x2 cj = f2_splat((SHIFTED ? mk[2 * ch + (c >> 4)] : 0.f) - m);
+          const float4 bb = *reinterpret_cast<const float4*>(brow + 32 * ch + c);
+          f32x2 t0 = f2_fma(f2_pack(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), l2e2, f2_pack(bb.x, bb.y));
+          f32x2 t1 = f2_fma(f2_pack(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), l2e2, f2_pack(bb.z, bb.w));
+          t0 = f2_add(t0, cj);
+          t1 = f2_add(t1, cj);
+          float a0, a1, a2, a3;
+          f2_unpack(t0, a0, a1);
+          f2_unpack(t1, a2, a3);
+          const float e0 = ex2_approx(a0), e1 = ex2_approx(a1), e2 = ex2_approx(a2), e3 = ex2_approx(a3);
+          lsum = f2_add(lsum, f2_add(f2_pack(e0, e1), f2_pack(e2, e3)));
+          pk[c >> 1] = pack_bf16x2(e0, e1);
+          pk[(c >> 1) + 1] = pack_bf16x2(e2, e3);
+        }
+        // P over the 128 keys of the tile: the own window's keys are packed columns [32 w, 32 w + 32)
+        tmem_st8_tc(t_s + 32 * w + 16 * ch, pk);
+        tmem_st8_tc(t_s + 32 * w + 16 * ch + 8, pk + 8);
+      };
+      chunk(bufA, 0);
+      chunk(bufB, 1);
+      {
+        const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // the other window's keys
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) {
-        tmem_st8_tc(t_s + 32 * w + c, pk + c);
-        tmem_st8_tc(t_s + 32 * (1 - w) + c, zero);
+        for (int c = 0; c < 32; c += 8) tmem_st8_tc(t_s + 32 * (1 - w) + c, zero);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
       // ---- output: O / l -> bf16 -> swizzled staging (64-byte rows: chunk ^= (token >> 1) & 3)
-      const float inv = rcp_approx(l);
+      float l0, l1;
+      f2_unpack(lsum, l0, l1);
+      const f32x2 inv2 = f2_splat(rcp_approx(l0 + l1));
       mbar_wait(&o_full[g], it & 1);
       tcgen05_fence_after();
       uint32_t ov[32];
-      tmem_ld_32x32(t_s + 128, ov);
+      tmem_ld_32x32(t_s + 64, ov);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
@@ -332,10 +357,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 o4;
-        o4.x = pack_bf16x2(__uint_as_float(ov[8 * c]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
-        o4.y = pack_bf16x2(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
-        o4.z = pack_bf16x2(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
-        o4.w = pack_bf16x2(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+        o4.x = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c]), __uint_as_float(ov[8 * c + 1])), inv2));
+        o4.y = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3])), inv2));
+        o4.z = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5])), inv2));
+        o4.w = pack_bf16x2(f2_mul(f2_pack(__uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7])), inv2));
         *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = o4;
       }
       fence_proxy_async_smem();
