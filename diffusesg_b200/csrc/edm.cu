@@ -155,14 +155,15 @@ edm_pre_philox_kernel(const float* __restrict__ x, float* __restrict__ out, cons
       if (e < numel) {
         const float eps = ii == 0 ? r.x : (ii == 1 ? r.y : (ii == 2 ? r.z : r.w));
         bool ok;
+        const unsigned eu = static_cast<unsigned>(e);  // numel < 2^31 (checked by the launcher): 32-bit divisions
         if (ADJ) {
-          const int j = static_cast<int>(e % n);
-          const long long rr = e / n;
-          const int i = static_cast<int>(rr % n);
-          const long long b = rr / (static_cast<long long>(n) * sh.c_e);
-          ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+          const unsigned un = static_cast<unsigned>(n);
+          const unsigned rr = eu / un, j = eu - rr * un;
+          const unsigned q2 = rr / un, i = rr - q2 * un;       // q2 = b * c_e + c
+          const unsigned b = q2 / static_cast<unsigned>(sh.c_e);
+          ok = flags[b * un + i] != 0 && flags[b * un + j] != 0;
         } else {
-          ok = flags[e / sh.c_n] != 0;
+          ok = flags[eu / static_cast<unsigned>(sh.c_n)] != 0;
         }
         out[e] = ok ? pre_one(x[e], eps, c) : 0.f;
       }
@@ -209,6 +210,7 @@ int launch_edm_pre_step_philox(const float* adj, const float* node, const uint8_
               grid_node);
   EdmShape sh{batch, c_e, n, c_n};
   const long long na = static_cast<long long>(batch) * c_e * n * n, nn = static_cast<long long>(batch) * n * c_n;
+  DSG_REQUIRE(na < 2147483647LL && nn < 2147483647LL, "edm philox pre-step: %lld / %lld elements (32-bit indexing)", na, nn);
   edm_pre_philox_kernel<true><<<static_cast<unsigned>(grid_adj), 256, 0, st>>>(adj, adj_hat, flags, noise_coef, seed,
                                                                                offset_adj, na, sh);
   DSG_LAUNCH_CHECK();
