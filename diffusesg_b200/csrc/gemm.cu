@@ -32,10 +32,10 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 // B tile, so a stage is 28 KB instead of 40 KB (BN = 192): 30 % less L2 -> SM traffic per flop and a deeper ring.
 template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int kStages = PAIR ? ((BN == 192) ? 5 : 7) : ((BN == 192) ? 4 : 5);
+  static constexpr int kStages = PAIR ? ((BN == 256) ? 4 : (BN == 192) ? 5 : 7) : ((BN == 256) ? 3 : (BN == 192) ? 4 : 5);
   static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int ACC_STRIDE = (BN == 192) ? 256 : 128;  // TMEM columns between the two accumulators
+  static constexpr int ACC_STRIDE = (BN >= 192) ? 256 : 128;  // TMEM columns between the two accumulators
   static constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;       // 512 / 256
   static constexpr int STAGING_BYTES = 64 * 1024;  // 2 groups x 2 x 16 KB (fp32 chunks) or 4 groups x 2 x 8 KB (bf16)
   static constexpr int BIAS_BYTES = 2 * BN * 4;     // bias slice of the current tile, per accumulator
@@ -44,6 +44,7 @@ struct Cfg {
 
 static_assert(Cfg<96>::SMEM_BYTES <= 227 * 1024 && Cfg<192>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(Cfg<96, true>::SMEM_BYTES <= 227 * 1024 && Cfg<192, true>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(Cfg<256>::SMEM_BYTES <= 227 * 1024 && Cfg<256, true>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
@@ -533,12 +534,26 @@ int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
 
 int gemm_block_n(int N) { return (N % 192 == 0) ? 192 : 96; }
 
+int gemm_choose_bn(long long rows, int N, int K, int epi, bool pair) {
+  const int bn0 = gemm_block_n(N);
+  static const bool no256 = getenv("DSG_NO_BN256") != nullptr && getenv("DSG_NO_BN256")[0] == '1';
+  if (no256 || N % 256 != 0 || K < 384 || epi == EPI_ADJ_HEAD) return bn0;
+  auto fill = [&](int bn) {  // how full the waves of a persistent launch are
+    const long long tiles = ((rows + (pair ? 255 : 127)) / (pair ? 256 : 128)) * (N / bn);
+    const long long slots = pair ? num_sms() / 2 : num_sms();
+    const long long waves = (tiles + slots - 1) / slots;
+    return static_cast<double>(tiles) / static_cast<double>(waves * slots);
+  };
+  return fill(256) * 1.08 > fill(bn0) ? 256 : bn0;
+}
+
 int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,
                 cudaStream_t st, bool pair) {
   DSG_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.N % 96 == 0 && p.K % 16 == 0,
               "gemm: unsupported shape M=%d N=%d K=%d (N %% 96 == 0 and K %% 16 == 0 required)", p.M, p.N, p.K);
   DSG_REQUIRE(p.out != nullptr, "gemm: null output");
-  const int bn = gemm_block_n(p.N);
+  const int bn = p.bn ? p.bn : gemm_block_n(p.N);
+  DSG_REQUIRE(p.N % bn == 0 && (bn == 96 || bn == 192 || bn == 256), "gemm: tile width %d for N = %d", bn, p.N);
   if (epi == EPI_ADJ_HEAD) {
     DSG_REQUIRE(p.N == 96 && p.c_e >= 1 && p.c_e <= 8 && p.w2t && p.b2 && p.flags && p.n_img > 0,
                 "gemm: adj-head epilogue needs N == 96, c_e <= 8 and the head tensors");
@@ -549,7 +564,14 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
   if (epi == EPI_RES_F32)
     DSG_REQUIRE(p.res == p.out, "gemm: the residual epilogue accumulates in place (res must alias out)");
   if (pair) {  // CTA pairs: tmW is the half-tile descriptor
-    if (bn == 192) {
+    if (bn == 256) {
+      switch (epi) {
+        case EPI_BF16: return launch_pair<256, EPI_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_GELU_BF16: return launch_pair<256, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+        case EPI_RES_F32: return launch_pair<256, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+        case EPI_F32: return launch_pair<256, EPI_F32>(tmA, tmW, tmO, p, st);
+      }
+    } else if (bn == 192) {
       switch (epi) {
         case EPI_BF16: return launch_pair<192, EPI_BF16>(tmA, tmW, tmO, p, st);
         case EPI_GELU_BF16: return launch_pair<192, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
@@ -565,7 +587,14 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
       }
     }
   }
-  if (bn == 192) {
+  if (bn == 256) {
+    switch (epi) {
+      case EPI_BF16: return launch_t<256, EPI_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_GELU_BF16: return launch_t<256, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);
+      case EPI_RES_F32: return launch_t<256, EPI_RES_F32>(tmA, tmW, tmO, p, st);
+      case EPI_F32: return launch_t<256, EPI_F32>(tmA, tmW, tmO, p, st);
+    }
+  } else if (bn == 192) {
     switch (epi) {
       case EPI_BF16: return launch_t<192, EPI_BF16>(tmA, tmW, tmO, p, st);
       case EPI_GELU_BF16: return launch_t<192, EPI_GELU_BF16>(tmA, tmW, tmO, p, st);

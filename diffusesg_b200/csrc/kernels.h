@@ -32,6 +32,7 @@ struct GemmParams {
   const float* res;    // [M, ldo] fp32 (EPI_RES_F32)
   void* out;           // [M, ldo] bf16 / fp32; EPI_ADJ_HEAD: float [B, c_e, n, n]
   int ldo;
+  int bn;              // tile width: 0 = gemm_block_n(N); 256 needs N % 256 == 0 and a W descriptor with that box
   // EPI_ADJ_HEAD only
   const float* w2t;    // [96][8]: second layer of the adj read-out MLP, transposed and zero padded
   const float* b2;     // [8]
@@ -53,6 +54,9 @@ int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
 // N must be a multiple of 96; K a multiple of 32; rows beyond M are neither read as valid nor written.
 // box_rows of the W descriptor must equal gemm_block_n(N).
 int gemm_block_n(int N);
+// Tile width the schedule uses for a [rows x N x K] GEMM: 256-wide tiles (16 % fewer operand bytes per flop through the
+// SM's shared memory than 192-wide ones) where N divides, the K loop is long enough and the waves stay full.
+int gemm_choose_bn(long long rows, int N, int K, int epi, bool pair);
 // EPI_RES_F32 accumulates in place with a TMA reduce-add: p.res must alias p.out.
 // pair = true runs CTA pairs (cta_group::2, 256-row tiles): tmW must then have box_rows = gemm_block_n(N) / 2.
 int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, int epi, const GemmParams& p,

@@ -103,6 +103,7 @@ struct Weight {       // packed bf16 [N, K] + its TMA descriptor
   int N = 0, K = 0;
   CUtensorMap tmap;       // box 64 x gemm_block_n(N)
   CUtensorMap tmap_half;  // box 64 x gemm_block_n(N) / 2: the B half each CTA of a pair loads
+  CUtensorMap tmap256, tmap256_half;  // N % 256 == 0: boxes of 256 / 128 rows for the 256-wide tiles
 };
 
 struct Block {
@@ -351,6 +352,10 @@ int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st
   int rc = launch_pack_bf16(m->f32(key), m->at<bf16>(w.offset), static_cast<int64_t>(w.N) * w.K, n_scaled, scale, st);
   if (rc) return rc;
   if (int rc2 = make_tmap_bf16(&w.tmap_half, m->arena + w.offset, w.N, w.K, gemm_block_n(w.N) / 2)) return rc2;
+  if (w.N % 256 == 0) {
+    if (int rc2 = make_tmap_bf16(&w.tmap256, m->arena + w.offset, w.N, w.K, 256)) return rc2;
+    if (int rc2 = make_tmap_bf16(&w.tmap256_half, m->arena + w.offset, w.N, w.K, 128)) return rc2;
+  }
   return make_tmap_bf16(&w.tmap, m->arena + w.offset, w.N, w.K, gemm_block_n(w.N));
 }
 
@@ -428,6 +433,8 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
   // is the co-bound and loses its slack), -2 % for the HBM-bound residual epilogue; K <= 192 shapes are HBM-bound.
   const bool pair = m->use_pair && epi != EPI_ADJ_HEAD && rows >= 256 &&
                     (W.K >= 768 || (W.K >= m->pair_min_k && epi == EPI_BF16));
+  p.bn = gemm_choose_bn(rows, W.N, W.K, epi, pair);
+  if (p.bn == 256) return launch_gemm(&it->second, pair ? &W.tmap256_half : &W.tmap256, tmo, epi, p, st, pair);
   return launch_gemm(&it->second, pair ? &W.tmap_half : &W.tmap, tmo, epi, p, st, pair);
 }
 
@@ -951,7 +958,8 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   const char* no_pair = getenv("DSG_NO_PAIR");
   const bool pair = M >= 256 && (K >= 768 || (K >= 384 && epi == EPI_BF16)) &&
                     !(no_pair != nullptr && no_pair[0] == '1');  // the denoiser schedule's rule
-  DSG_TRY(make_tmap_bf16(&tw, w, N, K, pair ? gemm_block_n(N) / 2 : gemm_block_n(N)));
+  const int bn = gemm_choose_bn(M, N, K, epi, pair);
+  DSG_TRY(make_tmap_bf16(&tw, w, N, K, pair ? bn / 2 : bn));
   DSG_TRY(make_tmap_out(&to, out, M, N, epi));
   if (epi == EPI_RES_F32) {
     DSG_REQUIRE(res != nullptr, "gemm_bf16: residual epilogue without residual");
@@ -962,7 +970,7 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N; p.bn = bn;
   return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream), pair);
 }
 

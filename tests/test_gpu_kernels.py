@@ -25,6 +25,8 @@ GEMM_SHAPES = [
     (777, 768, 3072), (512, 1536, 1536), (48, 96, 384), (20000, 96, 96), (33000, 576, 192),
     # CTA-pair path (cta_group::2, K >= 768, M >= 256): row tails inside the second CTA's half, both tile widths
     (256, 96, 768), (300, 384, 768), (3000, 2304, 768), (1111, 96, 1536),
+    # 256-wide tiles (N % 256 == 0, K >= 384, enough tiles to fill the waves): single CTA and CTA pairs, row tails
+    (20000, 1536, 384), (19999, 768, 384), (40000, 768, 768), (33333, 1536, 768),
 ]
 
 
