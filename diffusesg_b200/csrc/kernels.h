@@ -93,6 +93,15 @@ int launch_block_tail(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const C
 // written back.
 
 // ---------------------------------------------------------------------------------------------
+// fused attention projection + residual + LayerNorm2 for C = 192 / 384 (projln.cu):
+//   x += att W_proj^T + b_proj (in place, fp32);  y = LN(x) gamma + beta (bf16).  tmA: [rows, C] bf16, box 64 x 128;
+//   tmW: the proj weight [C, C] bf16, box 64 x 192 (= gemm_block_n(C)).
+// ---------------------------------------------------------------------------------------------
+bool proj_ln_supported(int C);
+int launch_proj_ln(const CUtensorMap* tmA, const CUtensorMap* tmW, const float* bias, const float* gamma, const float* beta,
+                   float* x, bf16* y, long long rows, int C, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
 // fused block head:  x = silu(FiLM(x));  qkv = LN1(x) W_qkv^T + b_qkv                     (blockhead.cu)
 // ---------------------------------------------------------------------------------------------
 // Built for C = 96.  tmXin / tmXout: x [rows, C] fp32 in / out (make_tmap_out, EPI_F32; may be the same buffer);

@@ -149,6 +149,7 @@ struct dsg_model {
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
+  bool use_proj_ln = false;   // DSG_PROJ_LN=1: fused proj + residual + LN2 kernel for C = 192 / 384 (break-even, see projln.cu)
   bool use_final_ln = true;   // DSG_NO_FINAL_LN=1 keeps the network's last LayerNorm as its own launch
   int pair_min_k = 384;       // CTA pairs from this K upwards for the bf16 epilogue, 768 for the others (DSG_PAIR_MIN_K)
   bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
@@ -520,10 +521,20 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
                                 fuse_final_ln ? m->f32("norm.bias") : nullptr));
     return DSG_OK;
   }
-  // x = x + proj(attn)                                                   (:137, :272)
-  DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
-  // x = x + fc2(gelu(fc1(LN2(x))))                                       (:275)
-  DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
+  if (m->use_proj_ln && proj_ln_supported(C)) {
+    // x = x + proj(attn);  y = LN2(x)  in one launch                     (:137, :272, :275)
+    const CUtensorMap* ta = tmap(w.ATT, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.ATT, rows, C, 128); });
+    if (ta == nullptr) return DSG_ERR_CUDA;
+    DSG_TRY_P(PC_GEMM, 2.0 * rc * C, rc * 12,
+              launch_proj_ln(ta, &b.proj.tmap, m->f32(p + ".attn.proj.bias"), m->f32(p + ".norm2.weight"),
+                             m->f32(p + ".norm2.bias"), w.X, w.Y, rows, C, st));
+  } else {
+    // x = x + proj(attn)                                                   (:137, :272)
+    DSG_TRY(gemm(m, w.ATT, rows, b.proj, EPI_RES_F32, m->f32(p + ".attn.proj.bias"), w.X, w.X, st));
+    // y = LN2(x)                                                           (:275)
+    DSG_TRY_P(PC_ROW, 0, rc * 6, launch_ln(w.X, w.Y, m->f32(p + ".norm2.weight"), m->f32(p + ".norm2.bias"), rows, C, st));
+  }
+  // x = x + fc2(gelu(fc1(y)))                                            (:275)
   if (m->use_fused_mlp && fused_mlp_supported(C)) {
     const CUtensorMap* ty = tmap(w.Y, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.Y, rows, C, 128); });
     const CUtensorMap* tx = tmap(w.X, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, w.X, rows, C, EPI_RES_F32); });
@@ -560,6 +571,8 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   const char* no_pair = getenv("DSG_NO_PAIR");
   m->use_pair = !(no_pair != nullptr && no_pair[0] == '1');
   if (const char* mk = getenv("DSG_PAIR_MIN_K")) m->pair_min_k = atoi(mk) > 0 ? atoi(mk) : 384;
+  const char* pln = getenv("DSG_PROJ_LN");
+  m->use_proj_ln = pln != nullptr && pln[0] == '1';
   const char* no_fln = getenv("DSG_NO_FINAL_LN");
   m->use_final_ln = !(no_fln != nullptr && no_fln[0] == '1');
   const char* no_head = getenv("DSG_NO_HEAD");
@@ -972,6 +985,16 @@ int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N; p.bn = bn;
   return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream), pair);
+}
+
+int dsg_proj_ln(const void* att, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* y,
+                int M, int C, dsg_stream_t stream) {
+  DSG_REQUIRE(att && w && bias && gamma && beta && x && y, "proj_ln: null tensor");
+  DSG_REQUIRE(proj_ln_supported(C), "proj_ln: C = %d (192 / 384)", C);
+  CUtensorMap ta, tw;
+  DSG_TRY(make_tmap_bf16(&ta, att, M, C, 128));
+  DSG_TRY(make_tmap_bf16(&tw, w, C, C, gemm_block_n(C)));
+  return launch_proj_ln(&ta, &tw, bias, gamma, beta, x, static_cast<bf16*>(y), M, C, static_cast<cudaStream_t>(stream));
 }
 
 int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,

@@ -177,6 +177,10 @@ DSG_API int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, co
  * 2 fp32 + residual (res may alias out), 3 fp32.  tcgen05/TMEM/TMA kernel (nn.Linear of the reference). */
 DSG_API int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
                   int epi, dsg_stream_t stream);
+/* x[M, C] += att[M, C] . w[C, C]^T + bias (fp32, in place);  y[M, C] = LayerNorm(x) * gamma + beta (bf16): the fused
+ * attention projection + residual + norm2 of the C = 192 / 384 Swin blocks (diffusesg.py:137, :272, :275). */
+DSG_API int dsg_proj_ln(const void* att, const void* w, const float* bias, const float* gamma, const float* beta, float* x,
+                void* y, int M, int C, dsg_stream_t stream);
 /* qkv [B*res*res, 3*heads*32] bf16 -> out [B*res*res, heads*32] bf16 (WindowAttention.forward, :108-139, q
  * pre-scaled); bias [heads, T, T] fp32, mask [nW, T, T] fp32 or NULL (shift == 0).  Runs the same mask / bias
  * checks as dsg_model_finalize on every call (synchronous) and then the kernel the denoiser would pick. */

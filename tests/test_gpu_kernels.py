@@ -64,6 +64,26 @@ def test_gemm_residual_in_place():
     assert _rel(x, want) < 1e-4
 
 
+@pytest.mark.parametrize("M,C", [(128, 192), (1000, 192), (4096, 384), (777, 384), (40000, 384), (33333, 192)])
+def test_proj_ln_matches_torch(M, C):
+    """Fused attention projection + residual + LayerNorm2 (C = 192 / 384) against fp32 torch on the same bf16 operands."""
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    att = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(C, C, device=DEV, generator=g) / C ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(C, device=DEV, generator=g) * 0.1
+    gamma = 1 + 0.2 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(C, device=DEV, generator=g)
+    x = torch.randn(M, C, device=DEV, generator=g) * 2 + 0.7   # a non-zero row mean exercises the pivot
+    want_x = x + (att.float() @ w.float().t() + bias)
+    want_y = torch.nn.functional.layer_norm(want_x, (C,), gamma, beta, 1e-5)
+    y = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    native.check(native.lib().dsg_proj_ln(att.data_ptr(), w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                          x.data_ptr(), y.data_ptr(), M, C, native.stream_ptr()), "proj_ln")
+    torch.cuda.synchronize()
+    assert _rel(x, want_x) < 1e-5, _rel(x, want_x)
+    assert float((y.float() - want_y).abs().max()) < 3e-2 and _rel(y.float(), want_y) < 4e-3   # bf16 output rounding
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
     w = torch.zeros(100, 64, device=DEV, dtype=torch.bfloat16)
