@@ -149,7 +149,8 @@ struct dsg_model {
   bool use_fused_mlp = true;  // DSG_NO_FUSED_MLP=1 keeps the LayerNorm + two-GEMM schedule (A/B measurements)
   bool use_tail = true;       // DSG_NO_TAIL=1 keeps proj GEMM + LayerNorm + fused MLP as separate launches
   bool use_pair = true;       // DSG_NO_PAIR=1 keeps single-CTA GEMM tiles (no cta_group::2)
-  bool use_proj_ln = false;   // DSG_PROJ_LN=1: fused proj + residual + LN2 kernel for C = 192 / 384 (break-even, see projln.cu)
+  int use_proj_ln = 1;        // fused proj + residual + LN2 kernel: 1 = for C = 384 (126 vs 146 us), 2 = also C = 192
+                              // (break-even: DSG_PROJ_LN=2), 0 = never (DSG_PROJ_LN=0)
   bool use_final_ln = true;   // DSG_NO_FINAL_LN=1 keeps the network's last LayerNorm as its own launch
   int pair_min_k = 384;       // CTA pairs from this K upwards for the bf16 epilogue, 768 for the others (DSG_PAIR_MIN_K)
   bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
@@ -521,7 +522,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
                                 fuse_final_ln ? m->f32("norm.bias") : nullptr));
     return DSG_OK;
   }
-  if (m->use_proj_ln && proj_ln_supported(C)) {
+  if (proj_ln_supported(C) && (m->use_proj_ln == 2 || (m->use_proj_ln == 1 && C == 384))) {
     // x = x + proj(attn);  y = LN2(x)  in one launch                     (:137, :272, :275)
     const CUtensorMap* ta = tmap(w.ATT, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.ATT, rows, C, 128); });
     if (ta == nullptr) return DSG_ERR_CUDA;
@@ -571,8 +572,7 @@ int dsg_model_create(const dsg_config* cfg, dsg_model** out) {
   const char* no_pair = getenv("DSG_NO_PAIR");
   m->use_pair = !(no_pair != nullptr && no_pair[0] == '1');
   if (const char* mk = getenv("DSG_PAIR_MIN_K")) m->pair_min_k = atoi(mk) > 0 ? atoi(mk) : 384;
-  const char* pln = getenv("DSG_PROJ_LN");
-  m->use_proj_ln = pln != nullptr && pln[0] == '1';
+  if (const char* pln = getenv("DSG_PROJ_LN")) m->use_proj_ln = (pln[0] >= '0' && pln[0] <= '2') ? pln[0] - '0' : 1;
   const char* no_fln = getenv("DSG_NO_FINAL_LN");
   m->use_final_ln = !(no_fln != nullptr && no_fln[0] == '1');
   const char* no_head = getenv("DSG_NO_HEAD");

@@ -3,20 +3,19 @@
 //     y  = LayerNorm(x) * gamma + beta       (:275, the input of the MLP), bf16
 // It replaces the proj GEMM (TMA reduce-add epilogue) followed by the LayerNorm row kernel, which read x a second time
 // (4 of the LayerNorm's 6 B / element) - both are HBM-bound, so the fused kernel's traffic is what it saves.
-// STATUS: correct (tests/test_gpu_kernels.py::test_proj_ln_matches_torch) but only break-even on the B200 - 140 us
-// against 87 + 60 us at C = 384, 275 against 178 + 105 us at C = 192 (4.3 TB/s: eight epilogue warps per SM do not
-// hide the latency of the chunk pipeline; releasing the accumulator after pass 1, so that the next tile's MMA phase
-// overlaps pass 2, changed nothing) - so the denoiser schedule takes it only with DSG_PROJ_LN=1.
+// Measured on the B200: 126 us against 87 + 60 us at C = 384 (4.8 TB/s), 281 against 178 + 105 us at C = 192 (the
+// epilogue warps do not hide the latency of the chunk pipeline there) - the denoiser schedule takes it for C = 384 and,
+// with DSG_PROJ_LN=2, for C = 192 as well (DSG_PROJ_LN=0: never).
 //
 // One persistent CTA per SM walks 128-row tiles and owns FULL rows (N = C columns of tensor memory, one accumulator:
 // the kernel is HBM-bound at ~1.5 KB of x traffic per row, so nothing is lost by not double buffering it):
-//   warps 0..7  epilogue, thread = row: group g = warp / 4 owns the column slice [g C / 2, (g + 1) C / 2) of the
+//   warps 0..11 epilogue, thread = row: group g = warp / 4 owns the column slice [g C / 3, (g + 1) C / 3) of the
 //               tile's 128 rows
 //   next warp   TMA producer: A box [128 x 64] + W boxes [192 x 64] per stage, one box per lane
 //   last warp   MMA issuer:   N = C as one (C = 192) or two (C = 384) tcgen05.mma of N = 192 per K step
 //       pass 1: x_new = acc + b + x, stored back to global memory, row sums in registers (pivot-shifted); the
 //               accumulator is released here, so the next tile's MMA phase runs under the rest of the epilogue;
-//               the two halves of a row exchange (sum, sum of squares, pivot)
+//               the column slices of a row exchange (sum, sum of squares, pivot)
 //       pass 2: every lane re-reads the x_new values it stored itself (L2 hits) -> normalise -> bf16 -> global memory
 //   Global memory is accessed COALESCED (a warp instruction covers 4 rows x 128 B of a 32 x 32 chunk; the next chunk
 //   of x is prefetched into registers) and transposed to / from the thread = row layout of tensor memory through a
@@ -37,9 +36,9 @@ struct PlCfg {
   static constexpr int STAGE = 16384 + B_STAGE;
   static constexpr int kStages = (C == 384) ? 2 : 4;
   static constexpr int TILE_BYTES = 32 * 36 * 4;          // per-warp transpose tile
-  // epilogue groups (4 warps each) = column slices of a row.  Four groups at C = 384 (3 chunks per thread instead of 6)
-  // measured slower: 172 vs 140 us (the 576-thread CTA is capped at 96 registers and spills)
-  static constexpr int NG = 2;
+  // epilogue groups (4 warps each) = column slices of a row.  Measured at C = 384: two groups 140 us, three 126 us,
+  // four 172 us (the 576-thread CTA is capped at 96 registers and spills)
+  static constexpr int NG = 3;
   static constexpr int THREADS = (4 * NG + 2) * 32;
   static constexpr int H = C / NG;                        // columns per epilogue group
   static constexpr int NCH = H / 32;                      // 32-column chunks per group
@@ -211,7 +210,7 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
-      // ---- row statistics over both column halves (each half has its own pivot)
+      // ---- row statistics over all column slices (each slice has its own pivot)
       {
         float a0, a1, b0, b1;
         f2_unpack(s1, a0, a1);
