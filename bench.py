@@ -288,28 +288,24 @@ def run_native(args, cfg, rank, local_rank, world):
     g = {k: g0.get(k, 0) + g1.get(k, 0) for k in ("ms", "flops", "bytes", "launches")}  # every tcgen05 launch
     total_prof_ms = sum(c["ms"] for c in prof.values()) or 1.0
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI,PAIR> + block_head_kernel<96> + block_tail_kernel<96> + fused_mlp_kernel<192> (tcgen05/TMEM/TMA: every nn.Linear of the denoiser, HBM-bound K <= 192 shapes included)",
-                "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "traffic": ncu_traffic_per_launch(r"gemm_kernel|block_head_kernel|block_tail_kernel|fused_mlp_kernel"),
-                "traffic_note": "bytes per launch, mean over the tcgen05 launches of one denoiser pass (ncu dram__bytes_read + write, profiles/r1_launches_pass_ncu.csv)",
-                "algorithmic_bytes_per_launch": g["bytes"] / g["launches"] if g["launches"] else None,
-                "launches_timed": g["launches"],
-                "avg_launch_ms": g["ms"] / g["launches"] if g["launches"] else None,
-                "share_of_profiled_time": g["ms"] / total_prof_ms,
-                "how": f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region"}
-    classes = {}
-    for name, c in prof.items():
-        sec = c["ms"] * 1e-3
-        classes[name] = {"launches": c["launches"], "ms": round(c["ms"], 3), "share": round(c["ms"] / total_prof_ms, 4),
-                         "tflops": round(c["flops"] / sec / 1e12, 2) if sec and c["flops"] else None,
-                         "gbs": round(c["bytes"] / sec / 1e9, 1) if sec and c["bytes"] else None}
-    # the single dominant kernel on its own (gemm_kernel: every nn.Linear that is not inside a fused block kernel)
+    # `roofline`: the single dominant kernel (gemm_kernel: every nn.Linear that is not inside a fused block kernel);
+    # `roofline_tcgen05_class`: all tcgen05 kernels together, i.e. including the HBM-bound fused block head / tail /
+    # proj + LN2 kernels whose LayerNorm / FiLM / GELU work carries no GEMM flops
+    how = f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region"
     g0_tflops = g0.get("flops", 0) / (g0["ms"] * 1e-3) / 1e12 if g0.get("ms") else 0.0
-    gemm_only = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI,PAIR>", "achieved": g0_tflops, "peak": pk["tensor_sustained"],
-                 "unit": "TFLOP/s", "frac": g0_tflops / pk["tensor_sustained"], "launches_timed": g0.get("launches"),
-                 "share_of_profiled_time": g0.get("ms", 0.0) / total_prof_ms,
-                 "traffic": ncu_traffic_per_launch(r"gemm_kernel")}
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI,PAIR> (tcgen05/TMEM/TMA; the dominant kernel of the pass)",
+                "achieved": g0_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": g0_tflops / pk["tensor_sustained"],
+                "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic": ncu_traffic_per_launch(r"gemm_kernel"),
+                "traffic_note": "bytes per launch, mean over the gemm_kernel launches of one denoiser pass (ncu dram__bytes_read + write, profiles/r1_launches_pass_ncu.csv)",
+                "algorithmic_bytes_per_launch": g0["bytes"] / g0["launches"] if g0.get("launches") else None,
+                "launches_timed": g0.get("launches"),
+                "avg_launch_ms": g0["ms"] / g0["launches"] if g0.get("launches") else None,
+                "share_of_profiled_time": g0.get("ms", 0.0) / total_prof_ms, "how": how}
+    class_roof = {"bound": "tensor", "kernel": "gemm_kernel + block_head_kernel<96> + block_tail_kernel<96> + fused_mlp_kernel<192> + proj_ln_kernel<384> (every nn.Linear of the denoiser, HBM-bound K <= 192 shapes and the fused LayerNorm / FiLM / GELU work included)",
+                  "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["tensor_sustained"],
+                  "traffic": ncu_traffic_per_launch(r"gemm_kernel|block_head_kernel|block_tail_kernel|fused_mlp_kernel|proj_ln_kernel"),
+                  "launches_timed": g["launches"], "share_of_profiled_time": g["ms"] / total_prof_ms, "how": how}
     edm = prof.get("edm_step")
     edm_roof = None
     if edm and edm["ms"]:
@@ -333,7 +329,7 @@ def run_native(args, cfg, rank, local_rank, world):
             "denoiser_frac_of_sustained_peak": (flops_step / (ms_step * 1e-3) / 1e12 / pk["tensor_sustained"]) if flops_step else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(flags_host.numel() + elems * 4), "d2h_bytes_per_step": int(elems * 4)},
-            "gpu_launches": int(launches), "roofline": roofline, "roofline_gemm_kernel": gemm_only,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_tcgen05_class": class_roof,
             "roofline_edm_step": edm_roof, "kernel_classes": classes,
             "clocks": clocks.summary()}
     if world == 1 and not args.no_cpu_baseline:

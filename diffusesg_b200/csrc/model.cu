@@ -526,7 +526,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     // x = x + proj(attn);  y = LN2(x)  in one launch                     (:137, :272, :275)
     const CUtensorMap* ta = tmap(w.ATT, C, [&](CUtensorMap* t) { return make_tmap_bf16(t, w.ATT, rows, C, 128); });
     if (ta == nullptr) return DSG_ERR_CUDA;
-    DSG_TRY_P(PC_GEMM, 2.0 * rc * C, rc * 12,
+    DSG_TRY_P(PC_MLP, 2.0 * rc * C, rc * 12,
               launch_proj_ln(ta, &b.proj.tmap, m->f32(p + ".attn.proj.bias"), m->f32(p + ".norm2.weight"),
                              m->f32(p + ".norm2.bias"), w.X, w.Y, rows, C, st));
   } else {
