@@ -306,6 +306,12 @@ def run_native(args, cfg, rank, local_rank, world):
                   "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["tensor_sustained"],
                   "traffic": ncu_traffic_per_launch(r"gemm_kernel|block_head_kernel|block_tail_kernel|fused_mlp_kernel|proj_ln_kernel"),
                   "launches_timed": g["launches"], "share_of_profiled_time": g["ms"] / total_prof_ms, "how": how}
+    classes = {}
+    for name, c in prof.items():
+        sec = c["ms"] * 1e-3
+        classes[name] = {"launches": c["launches"], "ms": round(c["ms"], 3), "share": round(c["ms"] / total_prof_ms, 4),
+                         "tflops": round(c["flops"] / sec / 1e12, 2) if sec and c["flops"] else None,
+                         "gbs": round(c["bytes"] / sec / 1e9, 1) if sec and c["bytes"] else None}
     edm = prof.get("edm_step")
     edm_roof = None
     if edm and edm["ms"]:
