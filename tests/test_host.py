@@ -259,3 +259,23 @@ def test_sharded_sampling_world_size_2_gloo(tmp_path):
     assert r0["n"][:, 0, 0].tolist() == [20, 30, 40, 50, 61, 71, 81]             # rows 0-3 from rank 0, 4-6 from rank 1
     assert r0["g"][:, 0].tolist() == [0, 0, 1, 1]
     assert not torch.equal(r0["draw"], r1["draw"])                               # seed + rank
+
+
+def test_aten_normal_policy_matches_calc_execution_policy(monkeypatch):
+    """Launch grid and Philox counter increment ATen uses for `normal_` on a float CUDA tensor
+    (ATen/native/cuda/DistributionTemplates.h::calc_execution_policy, block 256, unroll 4) - the fused-noise pre-step
+    advances the torch generator by exactly this much."""
+    import types
+
+    from diffusesg_b200 import native
+
+    props = types.SimpleNamespace(multi_processor_count=148, max_threads_per_multi_processor=2048)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev: props)
+    dev = torch.device("cuda", 0)
+    # VG adjacency state at batch 512: 512 * 6 * 64 * 64 elements -> the full grid of 148 * 8 blocks, 11 float4 per thread
+    assert native._aten_normal_policy(512 * 6 * 64 * 64, dev) == (1184, 44)
+    assert native._aten_normal_policy(512 * 64 * 12, dev) == (1184, 4)
+    assert native._aten_normal_policy(1000, dev) == (4, 4)
+    assert native._aten_normal_policy(1, dev) == (1, 4)
+    assert native._aten_normal_policy(1184 * 256 * 4 + 1, dev) == (1184, 8)
+
