@@ -14,8 +14,9 @@ Two numbers per step:
   e2e    the reference-facing call `sampler.sample(model, node_flags)` with HOST node flags: the initial noise
          is drawn on the CPU generator and uploaded (as the reference does), the samples come back as CPU tensors.
 
-`--impl reference` times the reference's CPU implementation of the same path (the oracle port of the unmodified
-PyTorch modules: same ATen CPU kernels, all host threads) on a bounded sample of the workload.
+`--impl reference` times the reference's CPU implementation of the same path - the UNMODIFIED reference modules staged
+under oracle/_ref by __graft_entry__.build() (oracle/stage_reference.py), all host threads - on a bounded sample of the
+workload (batch 8, a few Heun steps, extrapolated by counted denoiser passes; the line's config.measured_sample says so).
 """
 from __future__ import annotations
 
@@ -107,7 +108,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -117,13 +118,18 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for name, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         busy = sorted(sm)[len(sm) // 4:]  # drop idle samples at the edges
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(sorted(pw)[len(pw) // 4:])) if pw else None}
 
 
 def build_native_model(cfg, device):
@@ -146,24 +152,47 @@ def make_sampler(cfg, device, num_steps):
 
 
 # -----------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baseline: the staged unmodified reference on the host cores
 # -----------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(cfg, batch, num_steps, repeats, warmup):
-    """(graphs/s extrapolated to 256 steps, ms per repeat, raw passes per repeat, seconds per raw pass)."""
-    from oracle import denoiser_oracle as O
-    from oracle import edm_oracle as E
+    """Time the reference's CPU implementation of the path on all host cores.
+
+    Preferred: the UNMODIFIED reference staged under oracle/_ref (``NodeAdjEDMSampler.sample`` over
+    ``NodeAdjPrecond(DiffuseSG)``, dev='cpu'; kind = "reference").  Only if it is not staged (a box that never saw
+    /root/reference and no oracle/_ref travelled) the oracle port of the same modules runs (kind = "port").
+    Returns dict(rate = graphs/s extrapolated to 256 steps by counted raw denoiser passes, ms, passes, sec_per_pass,
+    kind, cores)."""
+    from oracle import stage_reference as R
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synthetic_state_dict(cfg, seed=1234, stress=False)
     flags = synthetic_node_flags(cfg, batch, seed=1234)
     passes = [0]
+    if R.root() is not None:
+        ref = R.load()
+        model = R.build_network(ref, cfg, sd)
+        model.model.register_forward_hook(lambda *_: passes.__setitem__(0, passes[0] + 1))
+        sampler = ref.NodeAdjEDMSampler(num_steps=num_steps, clip_samples=True, clip_samples_min=-1.0,
+                                        clip_samples_max=1.0, clip_samples_scope="x_0", dev="cpu", objective="edm",
+                                        self_condition=cfg["self_cond"], symmetric_noise=False)
+        kind = "reference"
 
-    def net(adj, node, f, labels, sa, sn):
-        passes[0] += 1
-        return O.denoiser_forward(sd, img=cfg["img"], embed=cfg["embed"], depths=cfg["depths"], heads=cfg["heads"],
-                                  window=cfg["window"], self_condition=cfg["self_cond"], adj=adj, node=node, flags=f,
-                                  noise_labels=labels, sc_adj=sa, sc_node=sn)
+        def run():
+            sampler.sample(model=model, node_flags=flags, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"])
+    else:
+        from oracle import denoiser_oracle as O
+        from oracle import edm_oracle as E
+        kind = "port"
 
-    model = lambda a, n, f, sig, sa, sn: O.precond_forward(net, a, n, f, sig, sa, sn, coin=np.random.rand)
+        def net(adj, node, f, labels, sa, sn):
+            passes[0] += 1
+            return O.denoiser_forward(sd, img=cfg["img"], embed=cfg["embed"], depths=cfg["depths"], heads=cfg["heads"],
+                                      window=cfg["window"], self_condition=cfg["self_cond"], adj=adj, node=node, flags=f,
+                                      noise_labels=labels, sc_adj=sa, sc_node=sn)
+
+        pmodel = lambda a, n, f, sig, sa, sn: O.precond_forward(net, a, n, f, sig, sa, sn, coin=np.random.rand)
+
+        def run():
+            E.sample(pmodel, flags, cfg["c_e"], cfg["c_n"], num_steps=num_steps)
     times, counts = [], []
     torch.manual_seed(1234)
     np.random.seed(1234)
@@ -171,30 +200,38 @@ def cpu_reference_rate(cfg, batch, num_steps, repeats, warmup):
         for it in range(warmup + repeats):
             passes[0] = 0
             t0 = time.perf_counter()
-            E.sample(model, flags, cfg["c_e"], cfg["c_n"], num_steps=num_steps)
+            run()
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
                 counts.append(passes[0])
     sec_per_pass = sum(times) / max(1, sum(counts))
-    rate = batch / (sec_per_pass * EXPECTED_PASSES_256)
-    return rate, 1e3 * sum(times) / len(times), sum(counts) / len(counts), sec_per_pass
+    return dict(rate=batch / (sec_per_pass * EXPECTED_PASSES_256), ms=1e3 * sum(times) / len(times),
+                passes=sum(counts) / len(counts), sec_per_pass=sec_per_pass, kind=kind, cores=torch.get_num_threads())
+
+
+def cpu_sample_text(args, r):
+    what = ("the UNMODIFIED reference (oracle/_ref: NodeAdjEDMSampler.sample over NodeAdjPrecond(DiffuseSG), fp32, dev=cpu)"
+            if r["kind"] == "reference" else "oracle port of the reference PyTorch CPU path (oracle/_ref not staged)")
+    return (f"{what}, {args.config} geometry, batch {args.cpu_batch}, {args.cpu_steps} Heun steps per timed step "
+            f"({r['passes']:.1f} raw denoiser passes, {r['sec_per_pass']:.3f} s/pass), extrapolated by counted passes to "
+            f"256 steps = {EXPECTED_PASSES_256} expected passes per graph batch")
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    b, ns = args.cpu_batch, args.cpu_steps
-    rate, ms, passes, spp = cpu_reference_rate(cfg, b, ns, args.steps, args.warmup)
-    cores = torch.get_num_threads()
-    sample = (f"{args.config} geometry, batch {b}, {ns} Heun steps per timed step ({passes:.1f} raw denoiser passes, "
-              f"{spp:.3f} s/pass), extrapolated to 256 steps = {EXPECTED_PASSES_256} expected passes per graph batch")
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, cfg, world),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    r = cpu_reference_rate(cfg, args.cpu_batch, args.cpu_steps, args.steps, args.warmup)
+    config = workload_config(args, cfg, world)
+    # what this arm actually executed per timed step (the metric is extrapolated to the workload above)
+    config["measured_sample"] = {"batch": args.cpu_batch, "heun_steps": args.cpu_steps, "raw_passes": r["passes"],
+                                 "extrapolated_to_passes": EXPECTED_PASSES_256, "device": "cpu", "world": 1}
+    line = {"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "sample": cpu_sample_text(args, r)},
+            "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
@@ -218,7 +255,8 @@ def run_native(args, cfg, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DSG_NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout
+        # NCCL_DEBUG is left as the caller set it (the driver reads NCCL's INFO lines); whatever NCCL prints on
+        # fd 1 lands on stderr through the fd swap in main(), so stdout still carries exactly one line
         dist.init_process_group("nccl", device_id=device)
     native.lib()
     torch.manual_seed(1234 + rank)   # the reference offsets the seed by the rank (utils/arg_parser.py:293-294)
@@ -258,18 +296,32 @@ def run_native(args, cfg, rank, local_rank, world):
         k[0] += 1
         sampler.sample_on_device(model, flags_dev, init_adjs=a, init_nodes=n, num_node_chan=cn, num_edge_chan=ce)
 
+    # e2e: the sharded entry point the reference's eval loop corresponds to (runner/sampler/sampler_node_adj.py:166-177
+    # + the final gather :331-345): every rank holds the host flags of ALL world * B graphs, samples its own slice and
+    # the slices are all-gathered, so at N > 1 the one collective of the path is inside the timed region
+    from diffusesg_b200.runner.sampler.sharded import sample_sharded
+    flags_all_host = torch.cat([synthetic_node_flags(cfg, B, seed=1234 + r) for r in range(world)])
+
     def step_e2e():
-        sampler.sample(model=model, node_flags=flags_host, num_node_chan=cn, num_edge_chan=ce)
+        a, n = sample_sharded(sampler, model, flags_all_host, world * B, cn, ce, gather_device=device)
+        assert a.shape[0] == world * B and not a.is_cuda
 
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     passes0, launches0 = model.raw_passes, native.launch_count()
-    native.profile_begin(args.profile_stride)
+    # per-kernel event brackets inside the timed region: with CUDA graphs (default) every `profile_stride`-th Heun STEP
+    # is issued through the eager launch sequence (same kernels, bit-identical results) with all of its launches
+    # bracketed; without graphs every `profile_stride`-th denoiser PASS is bracketed (and every EDM step launch)
+    graphs = sampler.use_graphs
+    if graphs:
+        sampler.eager_every = args.profile_stride
+    native.profile_begin(1 if graphs else args.profile_stride)
     with ClockSampler(local_rank) as clocks:
         ms_total = timed(step_device, args.steps)
     prof = native.profile_read()
     native.profile_stop()
+    sampler.eager_every = 0
     passes = (model.raw_passes - passes0) / args.steps
     launches = native.launch_count() - launches0
     ms_step = ms_total / args.steps
@@ -281,17 +333,38 @@ def run_native(args, cfg, rank, local_rank, world):
     ms_e2e = timed(step_e2e, e2e_steps) / e2e_steps
     e2e_value = world * B / (ms_e2e * 1e-3)
 
+    # strong scaling beside the weak-scaling headline: the same global batch of B graphs split over the ranks
+    strong = None
+    if world > 1 and B % world == 0 and not args.no_strong:
+        Bs = B // world
+        fl_s = flags_dev[:Bs].contiguous()
+        init_s = (init[0][0][:Bs].contiguous(), init[0][1][:Bs].contiguous())
+
+        def step_strong():
+            sampler.sample_on_device(model, fl_s, init_adjs=init_s[0], init_nodes=init_s[1], num_node_chan=cn,
+                                     num_edge_chan=ce)
+        step_strong()   # builds the plan / graphs for the smaller batch
+        ms_s = timed(step_strong, 1)
+        strong = {"scaling": "strong", "global_batch": B, "batch_per_gpu": Bs, "value": B / (ms_s * 1e-3), "unit": UNIT,
+                  "ms_per_step": ms_s, "steps": 1, "note": "device-resident, same definition as `value`"}
+
     if rank != 0:
         return
     pk = peaks()
     g0, g1 = prof.get("gemm_tcgen05", {}), prof.get("fused_mlp_tcgen05", {})
     g = {k: g0.get(k, 0) + g1.get(k, 0) for k in ("ms", "flops", "bytes", "launches")}  # every tcgen05 launch
-    total_prof_ms = sum(c["ms"] for c in prof.values()) or 1.0
+    # shares of the step: the denoiser classes are bracketed on every `profile_stride`-th pass only, the EDM step
+    # classes on every launch -> weight the former by the stride before forming shares
+    every_launch = ("edm_step", "edm_pre_step_philox")
+    eff_ms = {name: c["ms"] * (1 if (graphs or name in every_launch) else args.profile_stride) for name, c in prof.items()}
+    total_prof_ms = sum(eff_ms.values()) or 1.0
     gemm_tflops = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
     # `roofline`: the single dominant kernel (gemm_kernel: every nn.Linear that is not inside a fused block kernel);
     # `roofline_tcgen05_class`: all tcgen05 kernels together, i.e. including the HBM-bound fused block head / tail /
     # proj + LN2 kernels whose LayerNorm / FiLM / GELU work carries no GEMM flops
-    how = f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region"
+    how = (f"CUDA events around every launch of every {args.profile_stride}-th Heun step (issued eagerly; all other steps are "
+           "CUDA-graph replays of the same launches) inside the timed region" if graphs else
+           f"CUDA events around every launch of every {args.profile_stride}-th denoiser pass inside the timed region")
     g0_tflops = g0.get("flops", 0) / (g0["ms"] * 1e-3) / 1e12 if g0.get("ms") else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_kernel<BN,EPI,PAIR> (tcgen05/TMEM/TMA; the dominant kernel of the pass)",
                 "achieved": g0_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": g0_tflops / pk["tensor_sustained"],
@@ -301,15 +374,17 @@ def run_native(args, cfg, rank, local_rank, world):
                 "algorithmic_bytes_per_launch": g0["bytes"] / g0["launches"] if g0.get("launches") else None,
                 "launches_timed": g0.get("launches"),
                 "avg_launch_ms": g0["ms"] / g0["launches"] if g0.get("launches") else None,
-                "share_of_profiled_time": g0.get("ms", 0.0) / total_prof_ms, "how": how}
+                "share_of_profiled_time": eff_ms.get("gemm_tcgen05", 0.0) / total_prof_ms, "how": how}
     class_roof = {"bound": "tensor", "kernel": "gemm_kernel + block_head_kernel<96> + block_tail_kernel<96> + fused_mlp_kernel<192> + proj_ln_kernel<384> (every nn.Linear of the denoiser, HBM-bound K <= 192 shapes and the fused LayerNorm / FiLM / GELU work included)",
                   "achieved": gemm_tflops, "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["tensor_sustained"],
                   "traffic": ncu_traffic_per_launch(r"gemm_kernel|block_head_kernel|block_tail_kernel|fused_mlp_kernel|proj_ln_kernel"),
-                  "launches_timed": g["launches"], "share_of_profiled_time": g["ms"] / total_prof_ms, "how": how}
+                  "launches_timed": g["launches"],
+                  "share_of_profiled_time": (eff_ms.get("gemm_tcgen05", 0.0) + eff_ms.get("fused_mlp_tcgen05", 0.0)) / total_prof_ms,
+                  "how": how}
     classes = {}
     for name, c in prof.items():
         sec = c["ms"] * 1e-3
-        classes[name] = {"launches": c["launches"], "ms": round(c["ms"], 3), "share": round(c["ms"] / total_prof_ms, 4),
+        classes[name] = {"launches": c["launches"], "ms": round(c["ms"], 3), "share": round(eff_ms[name] / total_prof_ms, 4),
                          "tflops": round(c["flops"] / sec / 1e12, 2) if sec and c["flops"] else None,
                          "gbs": round(c["bytes"] / sec / 1e9, 1) if sec and c["bytes"] else None}
     edm = prof.get("edm_step")
@@ -334,16 +409,21 @@ def run_native(args, cfg, rank, local_rank, world):
             "denoiser_tflops_whole_step": flops_step / (ms_step * 1e-3) / 1e12 if flops_step else None,
             "denoiser_frac_of_sustained_peak": (flops_step / (ms_step * 1e-3) / 1e12 / pk["tensor_sustained"]) if flops_step else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "steps": e2e_steps,
-                    "h2d_bytes_per_step": int(flags_host.numel() + elems * 4), "d2h_bytes_per_step": int(elems * 4)},
+                    # per rank: flags of all graphs + the initial noise of its slice (+ at N > 1 the slice going back up
+                    # for the all-gather, as in the reference's gather_tensors); down: the slice (+ the gathered whole)
+                    "h2d_bytes_per_step": int(flags_all_host.numel() + elems * 4 + (elems * 4 if world > 1 else 0)),
+                    "d2h_bytes_per_step": int(elems * 4 + (world * elems * 4 if world > 1 else 0)),
+                    "api": "runner.sampler.sharded.sample_sharded -> NodeAdjEDMSampler.sample per rank"
+                           + (" + all_gather_into_tensor of the final samples (inside the timed region)" if world > 1 else "")},
             "gpu_launches": int(launches), "roofline": roofline, "roofline_tcgen05_class": class_roof,
             "roofline_edm_step": edm_roof, "kernel_classes": classes,
             "clocks": clocks.summary()}
+    if strong is not None:
+        line["strong_scaling"] = strong
     if world == 1 and not args.no_cpu_baseline:
-        rate, ms, p, spp = cpu_reference_rate(cfg, args.cpu_batch, args.cpu_steps, 1, 0)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"oracle port of the reference PyTorch CPU path, {args.config} geometry, batch "
-                                          f"{args.cpu_batch}, {args.cpu_steps} Heun steps ({p:.0f} raw passes, {spp:.3f} "
-                                          f"s/pass), extrapolated to {EXPECTED_PASSES_256} passes per 256-step batch"}
+        r = cpu_reference_rate(cfg, args.cpu_batch, args.cpu_steps, 1, 0)
+        line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": cpu_sample_text(args, r)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -382,6 +462,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra strong-scaling step at N > 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -195,12 +195,19 @@ int launch_edm_pre_step(const float* adj, const float* node, const float* eps_ad
 // ATen's launch grid for a tensor of that size (see edm.cu)
 int launch_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* flags, float noise_coef,
                                unsigned long long seed, unsigned long long offset_adj, int grid_adj,
-                               unsigned long long offset_node, int grid_node, float* adj_hat, float* node_hat, int batch,
-                               int c_e, int n, int c_n, cudaStream_t st);
+                               unsigned long long offset_node, int grid_node, const void* dev_params, float* adj_hat,
+                               float* node_hat, int batch, int c_e, int n, int c_n, cudaStream_t st);
+// dev_params: device dsg_edm_step_params the scalars are read from (CUDA-graph replay), or nullptr
 int launch_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
                          const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat,
-                         float h, float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e,
-                         int n, int c_n, cudaStream_t st);
+                         float h, float inv_t_prime, const void* dev_params, float* adj_next, float* node_next, int batch,
+                         int c_e, int n, int c_n, cudaStream_t st);
+int launch_edm_step_advance(const void* table, void* cur, int* counter, cudaStream_t st);
+// last (Euler) step + decode of the final sample in one pass; adj_next / node_next may be nullptr
+int launch_edm_final_decode(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                            const uint8_t* flags, float inv_t_hat, float h, const void* dev_params, float* adj_next,
+                            float* node_next, int32_t* adj_cls, int32_t* node_cls, float* bbox, int num_adj_type,
+                            int num_node_type, int batch, int c_e, int n, int c_n, cudaStream_t st);
 int launch_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
                       float* node_out, int batch, int c_e, int n, int c_n, cudaStream_t st);
 
@@ -227,6 +234,8 @@ int launch_loss_sums(const float* d_adj, const float* y_adj, const float* d_node
 // dst bf16 = src * (i < n_scaled ? scale : 1)
 int launch_pack_bf16(const float* src, bf16* dst, int64_t numel, int64_t n_scaled, float scale, cudaStream_t st);
 int launch_scale_copy(const float* src, float* dst, int64_t numel, int64_t n_scaled, float scale, cudaStream_t st);
+// *flag |= 1 when the two buffers differ in any 32-bit word (weight staleness probe)
+int launch_compare_words(const void* a, const void* b, int64_t words, int* flag, cudaStream_t st);
 // dst[c * dst_pitch + r] = src[r * ld + col0 + c], r < R, c < ncols   (dst is NOT cleared)
 int launch_transpose(const float* src, float* dst, int R, int ld, int col0, int ncols, int dst_pitch, cudaStream_t st);
 // out[h, p, q] = table[index[p, q], h]                              (diffusesg.py:121-124)

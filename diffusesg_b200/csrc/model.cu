@@ -63,6 +63,14 @@ static cudaEvent_t prof_event() {
   return e;
 }
 
+// event brackets are not recorded while the stream is being captured into a CUDA graph
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+static bool prof_every_launch(cudaStream_t st) { return g_prof_on && !stream_capturing(st); }
+
 struct ProfScope {
   bool active = false;
   ProfRec rec;
@@ -626,6 +634,19 @@ int dsg_model_set_tensor(dsg_model* m, const char* key, const void* src, int64_t
   return DSG_OK;
 }
 
+int dsg_model_tensor_differs(const dsg_model* m, const char* key, const void* src, int64_t bytes, int32_t* flag,
+                             dsg_stream_t stream) {
+  DSG_REQUIRE(m != nullptr && key != nullptr && src != nullptr && flag != nullptr, "tensor_differs: null argument");
+  if (m->arena == nullptr) { set_last_error("tensor_differs: no arena bound"); return DSG_ERR_STATE; }
+  auto it = m->index.find(key);
+  if (it == m->index.end()) { set_last_error("tensor_differs: unknown key '%s'", key); return DSG_ERR_UNKNOWN_KEY; }
+  const TensorSpec& t = m->tensors[it->second];
+  DSG_REQUIRE(static_cast<size_t>(bytes) == t.bytes() && (reinterpret_cast<uintptr_t>(src) & 3) == 0,
+              "tensor_differs: '%s' expects %zu bytes (4-byte aligned), got %lld", key, t.bytes(), static_cast<long long>(bytes));
+  return launch_compare_words(m->arena + t.offset, src, static_cast<int64_t>(t.bytes() / 4), flag,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
   DSG_REQUIRE(m != nullptr, "finalize: null model");
   if (m->arena == nullptr) { set_last_error("finalize: no arena bound"); return DSG_ERR_STATE; }
@@ -745,7 +766,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     labels = w.coef + 3 * B;
     label_stride = 1;
   }
-  g_prof_pass = g_prof_on && (g_prof_counter++ % g_prof_stride == 0);
+  g_prof_pass = g_prof_on && !stream_capturing(st) && (g_prof_counter++ % g_prof_stride == 0);
   struct ProfPassGuard { ~ProfPassGuard() { g_prof_pass = false; } } prof_pass_guard;
   const double px = static_cast<double>(B) * N * N;
   DSG_TRY_P(PC_EMBED_HEAD, 0, 0, launch_cond(labels, label_stride, a->n_cond, m->f32("map_layer0.weight"),
@@ -826,6 +847,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   return DSG_OK;
 }
 
+void dsg_launch_count_add(uint64_t n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
 void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
 void dsg_debug_trace_next_mlp(long long* device_buffer) { g_mlp_trace = device_buffer; }
 
@@ -902,7 +924,7 @@ int dsg_edm_pre_step(const float* adj, const float* node, const float* eps_adj, 
                      int c_n, dsg_stream_t stream) {
   DSG_REQUIRE(adj && node && eps_adj && eps_node && flags && adj_hat && node_hat, "edm_pre_step: null tensor");
   const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
-  ProfScope ps(g_prof_on, PC_EDM, 2 * el, 12 * el, static_cast<cudaStream_t>(stream));
+  ProfScope ps(prof_every_launch(static_cast<cudaStream_t>(stream)), PC_EDM, 2 * el, 12 * el, static_cast<cudaStream_t>(stream));
   return launch_edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef, adj_hat, node_hat, batch, c_e, n, c_n,
                              static_cast<cudaStream_t>(stream));
 }
@@ -912,9 +934,47 @@ int dsg_edm_pre_step_philox(const float* adj, const float* node, const uint8_t* 
                             float* node_hat, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
   DSG_REQUIRE(adj && node && flags && adj_hat && node_hat, "edm_pre_step_philox: null tensor");
   const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
-  ProfScope ps(g_prof_on, PC_EDM_NOISE, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));  // Philox / Box-Muller bound
+  ProfScope ps(prof_every_launch(static_cast<cudaStream_t>(stream)), PC_EDM_NOISE, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));  // Philox / Box-Muller bound
   return launch_edm_pre_step_philox(adj, node, flags, noise_coef, seed, offset_adj, grid_adj, offset_node, grid_node,
-                                    adj_hat, node_hat, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+                                    nullptr, adj_hat, node_hat, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_step_advance(const dsg_edm_step_params* table, dsg_edm_step_params* cur, int32_t* counter, dsg_stream_t stream) {
+  DSG_REQUIRE(table && cur && counter, "edm_step_advance: null pointer");
+  return launch_edm_step_advance(table, cur, counter, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_pre_step_philox_dev(const float* adj, const float* node, const uint8_t* flags, const dsg_edm_step_params* cur,
+                                int grid_adj, int grid_node, float* adj_hat, float* node_hat, int batch, int c_e, int n,
+                                int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && flags && cur && adj_hat && node_hat, "edm_pre_step_philox_dev: null tensor");
+  const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
+  ProfScope ps(prof_every_launch(static_cast<cudaStream_t>(stream)), PC_EDM_NOISE, 2 * el, 8 * el, static_cast<cudaStream_t>(stream));
+  return launch_edm_pre_step_philox(adj, node, flags, 0.f, 0, 0, grid_adj, 0, grid_node, cur, adj_hat, node_hat, batch,
+                                    c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_post_step_dev(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                          const float* d2_adj, const float* d2_node, const uint8_t* flags, const dsg_edm_step_params* cur,
+                          float* adj_next, float* node_next, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj_hat && node_hat && d1_adj && d1_node && flags && cur && adj_next && node_next, "edm_post_step_dev: null tensor");
+  DSG_REQUIRE((d2_adj == nullptr) == (d2_node == nullptr), "edm_post_step_dev: d2_adj / d2_node must both be given or both NULL");
+  const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
+  ProfScope ps(prof_every_launch(static_cast<cudaStream_t>(stream)), PC_EDM, (d2_adj ? 11 : 4) * el, (d2_adj ? 16 : 12) * el,
+               static_cast<cudaStream_t>(stream));
+  return launch_edm_post_step(adj_hat, node_hat, d1_adj, d1_node, d2_adj, d2_node, flags, 0.f, 0.f, 0.f, cur, adj_next,
+                              node_next, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
+int dsg_edm_final_step_decode(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                              const uint8_t* flags, float inv_t_hat, float h, const dsg_edm_step_params* cur, float* adj_next,
+                              float* node_next, int32_t* adj_cls, int32_t* node_cls, float* bbox, int num_adj_type,
+                              int num_node_type, int batch, int c_e, int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(adj_hat && node_hat && d1_adj && d1_node && flags && adj_cls && node_cls && bbox, "edm_final_step_decode: null tensor");
+  DSG_REQUIRE((adj_next == nullptr) == (node_next == nullptr), "edm_final_step_decode: adj_next / node_next both or neither");
+  return launch_edm_final_decode(adj_hat, node_hat, d1_adj, d1_node, flags, inv_t_hat, h, cur, adj_next, node_next, adj_cls,
+                                 node_cls, bbox, num_adj_type, num_node_type, batch, c_e, n, c_n,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
@@ -924,9 +984,9 @@ int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const float* 
   DSG_REQUIRE(adj_hat && node_hat && d1_adj && d1_node && flags && adj_next && node_next, "edm_post_step: null tensor");
   DSG_REQUIRE((d2_adj == nullptr) == (d2_node == nullptr), "edm_post_step: d2_adj / d2_node must both be given or both NULL");
   const double el = static_cast<double>(batch) * (static_cast<double>(c_e) * n * n + static_cast<double>(n) * c_n);
-  ProfScope ps(g_prof_on, PC_EDM, (d2_adj ? 11 : 4) * el, (d2_adj ? 16 : 12) * el, static_cast<cudaStream_t>(stream));
+  ProfScope ps(prof_every_launch(static_cast<cudaStream_t>(stream)), PC_EDM, (d2_adj ? 11 : 4) * el, (d2_adj ? 16 : 12) * el, static_cast<cudaStream_t>(stream));
   return launch_edm_post_step(adj_hat, node_hat, d1_adj, d1_node, d2_adj, d2_node, flags, inv_t_hat, h, inv_t_prime,
-                              adj_next, node_next, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+                              nullptr, adj_next, node_next, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
 }
 
 int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,

@@ -57,6 +57,16 @@ __global__ void small_mv_kernel(const float* __restrict__ A, const float* __rest
   y[o] = s + b[o];
 }
 
+// staleness probe: sets *flag when any 32-bit word of a differs from b (never clears it)
+__global__ void compare_words_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, long long words,
+                                     int* __restrict__ flag) {
+  bool diff = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < words;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    diff |= a[i] != b[i];
+  if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 unsigned blocks_for(long long n, int per = 256, long long cap = 148 * 8) {
   long long b = (n + per - 1) / per;
   if (b > cap) b = cap;
@@ -65,6 +75,14 @@ unsigned blocks_for(long long n, int per = 256, long long cap = 148 * 8) {
 }
 
 }  // namespace
+
+int launch_compare_words(const void* a, const void* b, int64_t words, int* flag, cudaStream_t st) {
+  if (words <= 0) return DSG_OK;
+  compare_words_kernel<<<blocks_for(words), 256, 0, st>>>(static_cast<const uint32_t*>(a), static_cast<const uint32_t*>(b),
+                                                          words, flag);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
 
 int launch_pack_bf16(const float* src, bf16* dst, int64_t numel, int64_t n_scaled, float scale, cudaStream_t st) {
   pack_bf16_kernel<<<blocks_for(numel), 256, 0, st>>>(src, dst, numel, n_scaled, scale);

@@ -9,7 +9,8 @@ Mirrors the reference interface (model/diffusesg/diffusesg.py:587-830 of ubc-vis
 * ``forward(adj, node, node_flags, noise_labels, self_cond_x=None, self_cond_feat=None) -> (adj_out, node_out)``.
 
 The module holds ordinary fp32 ``nn.Parameter`` masters.  The native side keeps its own arena with the packed
-bf16 / transposed / folded copies; it is refreshed lazily whenever a parameter's version counter moved.  There
+bf16 / transposed / folded copies; it is refreshed lazily whenever a parameter changed (version counters, plus a
+device-side comparison with the arena's master copies that also catches writes through ``.data``).  There
 is no PyTorch implementation of the forward in this file: without the shared library or a CUDA device the call
 raises.
 """
@@ -190,19 +191,46 @@ class DiffuseSG(nn.Module):
 
     def _versions(self):
         # (version counter, storage address) of every parameter / buffer: moves on optimizer steps,
-        # load_state_dict, .to(device) and EMA copies alike
+        # load_state_dict and .to(device).  NOT on writes through `.data` (ema_pytorch's `.data.lerp_()`,
+        # `p.data.copy_()`): those are caught by the deep probe below.
         return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
 
     def _native(self, device: torch.device) -> "_NativeModel":
+        """The native model for `device`, with its weight arena brought up to date.
+
+        Staleness is detected in two tiers: autograd version counters / storage addresses (free), and - because
+        writes through `.data` leave those untouched - a device-side comparison of every parameter with the fp32
+        master the arena holds (`dsg_model_tensor_differs`: one small launch per tensor and one 4-byte readback).
+        Inside `frozen_weights()` (the sampler wraps its loop in it) both tiers are skipped after the first call."""
         nat = self.__dict__.get("_nat")
         if nat is None or nat.device != device:
             nat = _NativeModel(self, device)
             self.__dict__["_nat"] = nat
-        ver = self._versions()
-        if nat.versions != ver:
-            nat.upload(self.state_dict(keep_vars=True))
+        if self.__dict__.get("_frozen", 0) > 0 and nat.versions is not None and self.__dict__.get("_frozen_checked"):
+            return nat
+        state = self.state_dict(keep_vars=True)
+        ver = tuple((t._version, t.data_ptr()) for t in state.values())
+        if nat.versions != ver or nat.differs(state):
+            nat.upload(state)
             nat.versions = ver
+        self.__dict__["_frozen_checked"] = True
         return nat
+
+    def invalidate_native(self) -> None:
+        """Force a re-upload of the weights on the next call."""
+        nat = self.__dict__.get("_nat")
+        if nat is not None:
+            nat.versions = None
+
+    def frozen_weights(self):
+        """Context manager: the caller promises not to modify the parameters inside (the EDM sampling loop); the
+        staleness checks then run once, on the first call inside the context."""
+        return _Frozen(self)
+
+    def train(self, mode: bool = True):
+        # train()/eval() transitions are where training loops hand the weights over for sampling
+        self.__dict__["_frozen_checked"] = False
+        return super().train(mode)
 
     def forward(self, adj, node, node_flags, noise_labels, self_cond_x=None, self_cond_feat=None):
         """Raw network F(adj, node | node_flags, c_noise)  (reference diffusesg.py:765-830).
@@ -217,6 +245,11 @@ class DiffuseSG(nn.Module):
         the body of NodeAdjPrecond.forward after the coin flip (model/precond/precond.py:100-105) in one
         native schedule (the scalings ride inside the patch-embedding and read-out kernels)."""
         return self._run(1, adjs, nodes, node_flags, sigmas, self_cond_adjs, self_cond_nodes)
+
+    def denoise_into(self, nat, adjs, nodes, flags, sigma_ptr_tensor, sc_adjs, sc_nodes, out_adjs, out_nodes):
+        """`denoise` on pre-validated contiguous fp32 CUDA tensors with one shared sigma read from device memory and
+        caller-provided outputs: no allocation, no checks - what the sampler captures into its CUDA graphs."""
+        nat.forward(1, adjs.shape[0], 1, adjs, nodes, flags, sigma_ptr_tensor, 0, sc_adjs, sc_nodes, out_adjs, out_nodes)
 
     def _run(self, mode, adj, node, flags, noise, sc_adj, sc_node):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
@@ -258,6 +291,22 @@ class DiffuseSG(nn.Module):
         return out_adj, out_node
 
 
+class _Frozen:
+    def __init__(self, module: "DiffuseSG"):
+        self.m = module
+
+    def __enter__(self):
+        d = self.m.__dict__
+        if d.get("_frozen", 0) == 0:
+            d["_frozen_checked"] = False
+        d["_frozen"] = d.get("_frozen", 0) + 1
+        return self.m
+
+    def __exit__(self, *exc):
+        self.m.__dict__["_frozen"] -= 1
+        return False
+
+
 class _NativeModel:
     """Owns the dsg_model handle, its weight arena and the activation workspace (torch tensors = device memory)."""
 
@@ -293,13 +342,37 @@ class _NativeModel:
             pass
 
     def keys(self):
+        if getattr(self, "_keys", None) is not None:
+            return self._keys
         out = []
         key, numel, dtype = C.c_char_p(), C.c_int64(), C.c_int32()
         for i in range(self.lib.dsg_model_num_tensors(self.handle)):
             native.check(self.lib.dsg_model_tensor_info(self.handle, i, C.byref(key), C.byref(numel), C.byref(dtype)),
                          "dsg_model_tensor_info")
             out.append((key.value.decode(), numel.value, dtype.value))
+        self._keys = out
         return out
+
+    def differs(self, state) -> bool:
+        """Deep staleness probe: does any tensor of `state` differ from the master copy in the arena?"""
+        if self.versions is None:
+            return True
+        st = native.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            keep = []
+            for key, numel, dtype in self.keys():
+                t = state[key].detach()
+                want = torch.int64 if dtype == 1 else torch.float32
+                if t.numel() != numel:
+                    return True
+                if t.device != self.device or t.dtype != want or not t.is_contiguous():
+                    t = t.to(device=self.device, dtype=want).contiguous()
+                    keep.append(t)
+                native.check(self.lib.dsg_model_tensor_differs(self.handle, key.encode(), t.data_ptr(),
+                                                               t.numel() * t.element_size(), flag.data_ptr(), st),
+                             "dsg_model_tensor_differs")
+            return bool(flag.item())
 
     def upload(self, state):
         st = native.stream_ptr(self.device)

@@ -13,7 +13,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdsg_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_F32 = 0, 1, 2, 3
 
@@ -36,6 +36,17 @@ class DsgForwardArgs(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class DsgEdmStepParams(C.Structure):
+    """include/dsg_b200.h: dsg_edm_step_params (48 bytes; one row per sampler step for CUDA-graph replays)."""
+    _fields_ = [("noise_coef", C.c_float), ("inv_t_hat", C.c_float), ("h", C.c_float), ("inv_t_prime", C.c_float),
+                ("t_hat", C.c_float), ("reserved", C.c_float), ("seed", C.c_uint64), ("offset_adj", C.c_uint64),
+                ("offset_node", C.c_uint64)]
+
+
+STEP_PARAMS_BYTES = 48
+STEP_PARAMS_T_HAT_OFFSET = 16
+
+
 class DsgProfileClass(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -45,6 +56,7 @@ _SIGNATURES = {
     "dsg_abi_version": (C.c_int, []),
     "dsg_last_error": (C.c_char_p, []),
     "dsg_launch_count": (C.c_uint64, []),
+    "dsg_launch_count_add": (None, [C.c_uint64]),
     "dsg_model_create": (C.c_int, [C.POINTER(DsgConfig), C.POINTER(C.c_void_p)]),
     "dsg_model_destroy": (None, [C.c_void_p]),
     "dsg_model_arena_bytes": (C.c_size_t, [C.c_void_p]),
@@ -54,12 +66,19 @@ _SIGNATURES = {
                                         C.POINTER(C.c_int32)]),
     "dsg_model_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "dsg_model_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dsg_model_tensor_differs": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dsg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "dsg_denoiser_forward": (C.c_int, [C.c_void_p, C.POINTER(DsgForwardArgs), C.c_void_p]),
     "dsg_edm_pre_step": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_pre_step_philox": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                            C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_post_step": (C.c_int, [C.c_void_p] * 7 + [C.c_float] * 3 + [C.c_void_p] * 2 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_step_advance": (C.c_int, [C.c_void_p] * 4),
+    "dsg_edm_pre_step_philox_dev": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4
+                                    + [C.c_void_p]),
+    "dsg_edm_post_step_dev": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_final_step_decode": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 6
+                                  + [C.c_void_p]),
     "dsg_edm_mask_scale": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_decode_samples": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p]),
     "dsg_train_noise": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
@@ -209,6 +228,29 @@ def edm_pre_step_fused_noise(adj, node, flags, noise_coef: float):
                                         grid_n, ptr(adj_hat), ptr(node_hat), b, ce, n, cn, stream_ptr(dev)),
           "dsg_edm_pre_step_philox")
     return adj_hat, node_hat
+
+
+def aten_normal_policy(numel: int, dev: torch.device):
+    return _aten_normal_policy(numel, dev)
+
+
+def edm_final_step_decode(adj_hat, node_hat, d1, flags, inv_t_hat: float, h: float, num_adj_type: int,
+                          num_node_type: int, want_state: bool = True, cur_params: Optional[int] = None):
+    """Last (Euler) sampler step fused with the decode of the final sample: returns
+    (adj_next | None, node_next | None, adj_cls int32 [B,N,N], node_cls int32 [B,N], bbox fp32 [B,N,4])."""
+    b, ce, n, _ = adj_hat.shape
+    cn = node_hat.shape[-1]
+    dev = adj_hat.device
+    adj_next = torch.empty_like(adj_hat) if want_state else None
+    node_next = torch.empty_like(node_hat) if want_state else None
+    adj_cls = torch.empty(b, n, n, dtype=torch.int32, device=dev)
+    node_cls = torch.empty(b, n, dtype=torch.int32, device=dev)
+    bbox = torch.empty(b, n, 4, dtype=torch.float32, device=dev)
+    check(lib().dsg_edm_final_step_decode(ptr(adj_hat), ptr(node_hat), ptr(d1[0]), ptr(d1[1]), ptr(flags), float(inv_t_hat),
+                                          float(h), cur_params, ptr(adj_next), ptr(node_next), ptr(adj_cls), ptr(node_cls),
+                                          ptr(bbox), int(num_adj_type), int(num_node_type), b, ce, n, cn, stream_ptr(dev)),
+          "dsg_edm_final_step_decode")
+    return adj_next, node_next, adj_cls, node_cls, bbox
 
 
 def edm_post_step(adj_hat, node_hat, d1, d2, flags, inv_t_hat: float, h: float, inv_t_prime: float):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSG_ABI_VERSION 1
+#define DSG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DSG_API __attribute__((visibility("default")))
@@ -63,6 +63,9 @@ DSG_API int dsg_abi_version(void);
 DSG_API const char* dsg_last_error(void);
 /* Number of CUDA kernels this library has launched in the calling process (all models). */
 DSG_API uint64_t dsg_launch_count(void);
+/* Kernels launched by replaying a CUDA graph captured from this library's launches are not seen by the counter
+ * above; the caller that replays the graph adds the number recorded at capture time. */
+DSG_API void dsg_launch_count_add(uint64_t n);
 
 /* ---- model life cycle -------------------------------------------------------------------------------------- */
 DSG_API int dsg_model_create(const dsg_config* cfg, dsg_model** out);
@@ -83,6 +86,12 @@ DSG_API int dsg_model_tensor_info(const dsg_model* m, int index, const char** ke
  * host pointer (src_is_host != 0). */
 DSG_API int dsg_model_set_tensor(dsg_model* m, const char* key, const void* src, int64_t bytes, int src_is_host,
                          dsg_stream_t stream);
+/* Staleness probe: *flag |= 1 (device int32, caller-zeroed) when `src` (device, same dtype / size as the tensor
+ * `key`) differs from the fp32 / int64 master the arena holds.  The Python module uses it to notice parameter
+ * updates that bypass autograd's version counters (`p.data.copy_()`, ema_pytorch's `.data.lerp_()`:
+ * utils/learning_utils.py:145-166 wraps the model in EMA and the reference samples from `ema_model`). */
+DSG_API int dsg_model_tensor_differs(const dsg_model* m, const char* key, const void* src, int64_t bytes, int32_t* flag,
+                                     dsg_stream_t stream);
 /* Build the packed forms (bf16 weights with the q scale folded in, gathered relative-position bias, folded
  * read_out chain, transposed head weights) and the weight TMA descriptors.  Call after all tensors are set and
  * again whenever any of them changed.  For shifted blocks / 16 x 16 windows it also compares the attn_mask buffer
@@ -143,6 +152,33 @@ DSG_API int dsg_edm_post_step(const float* adj_hat, const float* node_hat, const
                       const float* d2_adj, const float* d2_node, const uint8_t* flags, float inv_t_hat, float h,
                       float inv_t_prime, float* adj_next, float* node_next, int batch, int c_e, int n, int c_n,
                       dsg_stream_t stream);
+/* ---- the same steps for CUDA-graph replay: per-step scalars read from device memory -------------------------------
+ * A captured Heun step cannot carry per-step host scalars, so the sampler uploads ONE row per step (the values the
+ * reference derives at :355-356, :361, :369, :384-391, :414, evaluated on the host exactly as before, plus the Philox
+ * counter offsets of that step's two randn_like draws) and every captured launch reads the current row:
+ *   dsg_edm_step_advance: cur = table[*counter]; ++*counter   (first node of each captured step)
+ *   *_dev entry points:   as above with the scalars taken from `cur`; `cur->t_hat` is also what the captured
+ *                         dsg_denoiser_forward(mode 1, n_cond 1) is given as its sigma pointer. */
+typedef struct dsg_edm_step_params {
+  float noise_coef;    /* sqrt(t_hat^2 - t_cur^2) * S_noise                      (:361) */
+  float inv_t_hat;     /* sigma'(t_hat) / sigma(t_hat) = 1 / t_hat               (:384) */
+  float h;             /* t_next - t_hat                                         (:389) */
+  float inv_t_prime;   /* 1 / (t_hat + h); 0 on the last step                    (:414) */
+  float t_hat;         /* the noise level both denoiser calls of the step see    (:371) */
+  float reserved;
+  uint64_t seed;        /* torch CUDA generator seed */
+  uint64_t offset_adj;  /* Philox counter offset of randn_like(adjs) of this step */
+  uint64_t offset_node; /* ... of randn_like(nodes) */
+} dsg_edm_step_params;
+DSG_API int dsg_edm_step_advance(const dsg_edm_step_params* table, dsg_edm_step_params* cur, int32_t* counter,
+                                 dsg_stream_t stream);
+DSG_API int dsg_edm_pre_step_philox_dev(const float* adj, const float* node, const uint8_t* flags,
+                                        const dsg_edm_step_params* cur, int grid_adj, int grid_node, float* adj_hat,
+                                        float* node_hat, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
+DSG_API int dsg_edm_post_step_dev(const float* adj_hat, const float* node_hat, const float* d1_adj, const float* d1_node,
+                                  const float* d2_adj, const float* d2_node, const uint8_t* flags,
+                                  const dsg_edm_step_params* cur, float* adj_next, float* node_next, int batch, int c_e,
+                                  int n, int c_n, dsg_stream_t stream);
 /* x_out = mask(x * scale): masking of the initial noise and its scaling by sigma(t_0)         (:276-289, :346-347) */
 DSG_API int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_t* flags, float scale, float* adj_out,
                        float* node_out, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
@@ -155,6 +191,15 @@ DSG_API int dsg_edm_mask_scale(const float* adj, const float* node, const uint8_
 DSG_API int dsg_decode_samples(const float* adj, const float* node, const uint8_t* flags, int32_t* adj_cls,
                                int32_t* node_cls, float* bbox, int num_adj_type, int num_node_type, int batch,
                                int c_e, int n, int c_n, dsg_stream_t stream);
+
+/* The LAST sampler step (Euler, :389-396) fused with that decode: one pass over (x_hat, D1) writes the classes and
+ * boxes; the fp32 state is written only when adj_next / node_next are non-NULL.  Scalars from `cur` when it is
+ * non-NULL (graph replay), else from inv_t_hat / h. */
+DSG_API int dsg_edm_final_step_decode(const float* adj_hat, const float* node_hat, const float* d1_adj,
+                                      const float* d1_node, const uint8_t* flags, float inv_t_hat, float h,
+                                      const dsg_edm_step_params* cur, float* adj_next, float* node_next,
+                                      int32_t* adj_cls, int32_t* node_cls, float* bbox, int num_adj_type,
+                                      int num_node_type, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
 
 /* ---- EDM training objective (BASELINE config 4; forward only) ---------------------------------------------------
  * dsg_train_noise replaces NodeAdjEDMObjectiveGenerator.get_network_input (runner/objectives/edm.py:233-254) over

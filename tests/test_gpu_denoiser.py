@@ -348,3 +348,90 @@ def test_no_cpu_fallback():
     with pytest.raises(native.NativeError):
         with torch.no_grad():
             m(adj, node, flags, sigmas.log() / 4)
+
+
+def test_sampler_graphs_are_bit_identical():
+    """One CUDA-graph launch per step == the eager launch sequence: same samples, same interim snapshots, same
+    generator state afterwards, same pass count; also with every 3rd step taken eagerly (the bench's profiling mode)
+    and when the same sampler is called twice (buffers of the plan are reused)."""
+    cfg = CONFIGS["tiny"]
+    net, _ = build(cfg)
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, 6, seed=9)
+    outs = []
+    for graphs, eager_every in ((False, 0), (True, 0), (True, 3), (True, 0)):
+        sampler = NodeAdjEDMSampler(num_steps=10, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                    clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                    symmetric_noise=False)
+        sampler.use_graphs, sampler.eager_every = graphs, eager_every
+        for rep in range(2):
+            torch.manual_seed(5)
+            torch.cuda.manual_seed(5)
+            np.random.seed(5)
+            p0 = model.raw_passes
+            a, n, a_ls, n_ls = sampler.sample(model=model, node_flags=flags.to(DEV), flag_interim_adjs=True,
+                                              max_num_interim_adjs=4, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"])
+            outs.append((a, n, a_ls, n_ls, torch.randn(100, device=DEV).cpu(), torch.tensor(model.raw_passes - p0)))
+        assert (sampler._plan is not None) == graphs
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert torch.equal(x, y)
+
+
+def test_weights_written_through_data_are_noticed():
+    """ema_pytorch updates the EMA copy with `.data.lerp_()` / `.data.copy_()`, which moves no autograd version
+    counter: the native arena must still follow.  Forward after an in-place `.data` write == forward of
+    a freshly built model with the same weights; and the sampler (frozen inside its loop) re-probes on every call."""
+    cfg = CONFIGS["tiny"]
+    net, sd = build(cfg)
+    adj, node, flags, sigmas, sc_adj, sc_node = [t.to(DEV) for t in synthetic_inputs(cfg, 3, seed=7)]
+    labels = sigmas.log() / 4
+    with torch.no_grad():
+        a0, n0 = net(adj, node, flags, labels, sc_adj, sc_node)
+        versions = [p._version for p in net.parameters()]
+        for p in net.parameters():
+            p.data.mul_(1.25)
+        assert versions == [p._version for p in net.parameters()]     # the counters did not move
+        a1, n1 = net(adj, node, flags, labels, sc_adj, sc_node)
+    fresh = DiffuseSG(img_size=cfg["img"], in_chans=in_chans(cfg), patch_size=1, embed_dim=cfg["embed"],
+                      depths=cfg["depths"], num_heads=[3, 6, 12, 24], window_size=cfg["window"], mlp_ratio=4.,
+                      drop_rate=0., attn_drop_rate=0., drop_path_rate=0.0, self_condition=True, symmetric_noise=False,
+                      out_chans_adj=cfg["c_e"], out_chans_node=cfg["c_n"])
+    fresh.load_state_dict({k: (v * 1.25 if v.dtype == torch.float32 and "attn_mask" not in k else v) for k, v in sd.items()})
+    fresh = fresh.to(DEV).eval()
+    with torch.no_grad():
+        a2, n2 = fresh(adj, node, flags, labels, sc_adj, sc_node)
+    assert torch.equal(a1, a2) and torch.equal(n1, n2)
+    assert not torch.equal(a0, a1)
+    # sampler: weights changed between two sample() calls through .data only
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    sampler = NodeAdjEDMSampler(num_steps=3, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                symmetric_noise=False)
+    res = []
+    for scale in (1.0, 0.5, 2.0):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.data.mul_(scale)
+        torch.manual_seed(1); torch.cuda.manual_seed(1); np.random.seed(1)
+        res.append(sampler.sample(model=model, node_flags=flags, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"]))
+    assert not torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][0], res[2][0]) and torch.equal(res[0][1], res[2][1])   # x0.5 then x2: back to the start
+
+
+def test_sampler_accepts_any_flag_dtype():
+    """mask_adjs / mask_nodes of the reference take any flag dtype (logical_not); float and int64 flags must mask the
+    same rows as bool flags."""
+    cfg = CONFIGS["tiny"]
+    net, _ = build(cfg)
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, 4, seed=9)
+    sampler = NodeAdjEDMSampler(num_steps=2, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                symmetric_noise=False)
+    res = []
+    for f in (flags, flags.float(), flags.long()):
+        torch.manual_seed(2); torch.cuda.manual_seed(2); np.random.seed(2)
+        res.append(sampler.sample(model=model, node_flags=f.to(DEV), num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"]))
+    for r in res[1:]:
+        assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1])

@@ -247,6 +247,29 @@ def test_decode_samples_bit_exact(b, ce, n, cn, n_adj, n_node):
     assert int(ga.diagonal(dim1=1, dim2=2).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("b,ce,n,cn,n_adj,n_node", [(7, 6, 64, 12, 51, 150), (5, 3, 40, 12, 7, 171), (3, 3, 16, 5, 5, 2)])
+def test_final_step_decode_fused_bit_exact(b, ce, n, cn, n_adj, n_node):
+    """Last Euler step + decode in one kernel == dsg_edm_post_step followed by dsg_decode_samples (and the oracle)."""
+    g = torch.Generator().manual_seed(7 * n + ce)
+    flags = torch.arange(n)[None, :] < torch.randint(1, n + 1, (b, 1), generator=g)
+    xh_a, xh_n = torch.randn(b, ce, n, n, generator=g), torch.randn(b, n, cn, generator=g)
+    d_a, d_n = torch.randn(b, ce, n, n, generator=g), torch.randn(b, n, cn, generator=g)
+    cu = lambda t: t.to(DEV)
+    inv_t, h = 1.0 / 0.0021, -0.0021
+    sa, sn = native.edm_post_step(cu(xh_a), cu(xh_n), (cu(d_a), cu(d_n)), None, cu(flags), inv_t, h, 0.0)
+    ca, cn_, cb = native.decode_samples(sa, sn, cu(flags), n_adj, n_node)
+    fa, fn, qa, qn, qb = native.edm_final_step_decode(cu(xh_a), cu(xh_n), (cu(d_a), cu(d_n)), cu(flags), inv_t, h, n_adj, n_node)
+    assert torch.equal(fa, sa) and torch.equal(fn, sn)
+    assert torch.equal(qa, ca) and torch.equal(qn, cn_) and torch.equal(qb, cb)
+    oa, on, ob = E.decode_samples(sa.cpu(), sn.cpu(), flags, n_adj, n_node)
+    np.testing.assert_array_equal(qa.cpu().numpy(), oa.numpy().astype(np.int32))
+    np.testing.assert_array_equal(qn.cpu().numpy(), on.numpy().astype(np.int32))
+    np.testing.assert_array_equal(qb.cpu().numpy(), ob.numpy())
+    na, nn_, qa2, qn2, qb2 = native.edm_final_step_decode(cu(xh_a), cu(xh_n), (cu(d_a), cu(d_n)), cu(flags), inv_t, h, n_adj,
+                                                          n_node, want_state=False)
+    assert na is None and nn_ is None and torch.equal(qa2, qa) and torch.equal(qn2, qn) and torch.equal(qb2, qb)
+
+
 def test_training_objective_bit_exact_and_loss(golden_dir):
     """Native noising (dsg_train_noise) and loss (dsg_edm_loss_sums) through the drop-in host classes against the
     golden outputs of the unmodified reference: noising / coefficients bit-exact, loss within 1e-5 relative (fp64

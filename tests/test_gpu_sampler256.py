@@ -1,0 +1,139 @@
+"""Full-length sampler parity on the shipped geometries (run on the B200 with -m gpu).
+
+The golden files hold the OUTPUT of the unmodified reference sampler (NodeAdjEDMSampler.sample over
+NodeAdjPrecond(DiffuseSG), fp32, CPU; tests/golden/make_golden_full.py) for 256 stochastic-Heun steps, batch 8, on
+the Visual Genome and COCO-Stuff geometries.  That run drew its initial noise, its 2 x 256 per-step noise tensors
+and its self-conditioning coins from the global CPU / numpy generators; here the same streams are replayed
+(``torch.manual_seed`` / ``np.random.seed`` + a ``torch.randn_like`` that draws on the CPU generator), so the native
+sampler sees bit-identical noise and coins and every difference is arithmetic (bf16 tensor-core operands in the
+denoiser; the EDM step kernels themselves are bit-exact).
+
+Stated tolerances (BASELINE.json north_star: "decoded node, edge and box outputs agreeing at a stated rate"):
+  state after every 32 steps and at the end:   rel-L2 <= TOL_STATE
+  decoded edge / node classes (the reference's decode rule, golden from its own _decode_adj / _decode_node):
+       >= RATE over valid entries for reference-like init (`vg_refinit`: BASELINE's "random-init weights"),
+       and 100 % wherever every bit of the reference value is further than MARGIN from the sign threshold;
+  boxes: |delta| <= 1e-2 on the [0, 1] scale for >= 99 % of valid nodes.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffusesg_b200 import native
+from diffusesg_b200.model.diffusesg.diffusesg import DiffuseSG
+from diffusesg_b200.model.precond.precond import NodeAdjPrecond
+from diffusesg_b200.runner.mcmc_sampler.edm import NodeAdjEDMSampler
+from diffusesg_b200.utils.synthetic import CONFIGS, in_chans, synthetic_state_dict
+from oracle import edm_oracle as E
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+RAW_TYPES = {"vg": (150, 51), "coco": (171, 7)}   # raw_num_node_type, raw_num_adj_type (utils/sg_utils.py:355-394)
+CASES = {"vg": ("vg", True), "vg_refinit": ("vg", False), "coco": ("coco", True)}
+TOL_STATE = {"vg": 3e-2, "vg_refinit": 3e-3, "coco": 3e-2}
+RATE = {"vg": 0.97, "vg_refinit": 0.99, "coco": 0.97}
+MARGIN = 0.06
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _build(cfg, stress):
+    m = DiffuseSG(img_size=cfg["img"], in_chans=in_chans(cfg), patch_size=1, embed_dim=cfg["embed"],
+                  depths=cfg["depths"], num_heads=[3, 6, 12, 24], window_size=cfg["window"], mlp_ratio=4.,
+                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0.0, self_condition=True, symmetric_noise=False,
+                  out_chans_adj=cfg["c_e"], out_chans_node=cfg["c_n"])
+    m.load_state_dict(synthetic_state_dict(cfg, seed=1234, stress=stress), strict=True)
+    return NodeAdjPrecond(precond="edm", model=m.to(DEV).eval(), self_condition=True, symmetric_noise=False).eval()
+
+
+@pytest.mark.parametrize("case", ["vg", "vg_refinit", "coco"])
+def test_sampler256_matches_reference(case, golden_dir):
+    name, stress = CASES[case]
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"sampler256_{case}.npz"))
+    flags = torch.from_numpy(g["flags"])
+    model = _build(cfg, stress)
+    sampler = NodeAdjEDMSampler(num_steps=256, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                symmetric_noise=False)
+    real_like = torch.randn_like
+    torch.manual_seed(int(g["torch_seed"]))
+    np.random.seed(int(g["numpy_seed"]))
+    torch.randn_like = lambda x, **k: torch.randn(x.shape).to(x.device)   # the reference ran on the CPU generator
+    try:
+        a, n, a_ls, n_ls = sampler.sample(model=model, node_flags=flags.to(DEV), flag_interim_adjs=True,
+                                          max_num_interim_adjs=9, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"])
+    finally:
+        torch.randn_like = real_like
+    assert sampler.last_raw_passes == int(g["raw_passes"])          # same coin stream, same pass count
+    np.testing.assert_array_equal(n_ls[0, :2].numpy(), g["nodes_ls"][0])   # identical initial noise
+    traj = [(_rel(a_ls[k, :2], g["adjs_ls"][k]), _rel(n_ls[k, :2], g["nodes_ls"][k])) for k in range(1, 11)]
+    ga, gn = torch.from_numpy(g["adjs"]), torch.from_numpy(g["nodes"])
+    n_node, n_adj = RAW_TYPES[name]
+    d = np.load(os.path.join(golden_dir, f"decode_{name}.npz")) if case == name else None
+    qa, qn, box = E.decode_samples(a, n, flags, n_adj, n_node)           # reference rule (pinned by the CPU suite)
+    ra, rn, rbox = E.decode_samples(ga, gn, flags, n_adj, n_node)
+    if d is not None:   # ... and the reference's own closures on its own samples
+        np.testing.assert_array_equal(ra.numpy(), d["final_q_adj"])
+        np.testing.assert_array_equal(rn.numpy(), d["final_q_node"])
+    pair = flags[:, :, None] & flags[:, None, :] & ~torch.eye(flags.shape[1], dtype=torch.bool)
+    nb = cfg["c_n"] - 4
+    far_e = (ga.abs() > MARGIN).all(1) & pair
+    far_n = (gn[..., :nb].abs() > MARGIN).all(-1) & flags
+    stats = dict(case=case, rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
+                 edge_agree=float((qa == ra)[pair].float().mean()), node_agree=float((qn == rn)[flags].float().mean()),
+                 edge_agree_far=float((qa == ra)[far_e].float().mean()), node_agree_far=float((qn == rn)[far_n].float().mean()),
+                 far_frac=(float(far_e.sum() / pair.sum()), float(far_n.sum() / flags.sum())),
+                 box_within_1e2=float(((box - rbox).abs()[flags] <= 1e-2).float().mean()),
+                 passes=sampler.last_raw_passes, rms=float(ga.pow(2).mean().sqrt()))
+    print("SAMPLER256_PARITY", stats)
+    out = os.environ.get("DSG_PARITY_LOG")
+    if out:
+        with open(out, "a") as f:
+            f.write(repr(stats) + "\n")
+    assert stats["rel_adj"] <= TOL_STATE[case] and stats["rel_node"] <= TOL_STATE[case], stats
+    assert max(max(t) for t in traj) <= 2 * TOL_STATE[case], stats
+    assert stats["edge_agree"] >= RATE[case] and stats["node_agree"] >= RATE[case], stats
+    assert stats["edge_agree_far"] == 1.0 and stats["node_agree_far"] == 1.0, stats
+    assert stats["box_within_1e2"] >= 0.99, stats
+
+
+def test_sample_decoded_matches_decode_of_sample(golden_dir):
+    """sample_decoded (decode fused into the last Euler step) == the reference decode applied to sample()'s output,
+    same seeds; eager and CUDA-graph paths; raw state identical too."""
+    cfg = CONFIGS["coco"]
+    model = _build(cfg, True)
+    flags = torch.from_numpy(np.load(os.path.join(golden_dir, "sampler256_coco.npz"))["flags"])
+    n_node, n_adj = RAW_TYPES["coco"]
+    outs = []
+    for graphs in (True, False):
+        sampler = NodeAdjEDMSampler(num_steps=12, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                    clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                    symmetric_noise=False)
+        sampler.use_graphs = graphs
+        for decoded in (False, True):
+            torch.manual_seed(3)
+            torch.cuda.manual_seed(3)
+            np.random.seed(3)
+            if decoded:
+                outs.append(sampler.sample_decoded(model, flags.to(DEV), n_adj, n_node, num_node_chan=cfg["c_n"],
+                                                   num_edge_chan=cfg["c_e"], return_state=True))
+            else:
+                a, n = sampler.sample(model=model, node_flags=flags.to(DEV), num_node_chan=cfg["c_n"],
+                                      num_edge_chan=cfg["c_e"])
+                qa, qn, box = E.decode_samples(a, n, flags, n_adj, n_node)
+                outs.append((a, n, qa.to(torch.int32), qn.to(torch.int32), box))
+    ref = outs[0]
+    for o in outs[1:]:
+        for x, y in zip(ref, o):
+            assert torch.equal(x, y)
+    q_only = sampler.sample_decoded  # classes only: no fp32 state leaves the GPU
+    torch.manual_seed(3); torch.cuda.manual_seed(3); np.random.seed(3)
+    qa, qn, box = q_only(model, flags.to(DEV), n_adj, n_node, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"])
+    assert torch.equal(qa, ref[2]) and torch.equal(qn, ref[3]) and torch.equal(box, ref[4])
+    assert qa.dtype == torch.int32 and not qa.is_cuda

@@ -115,3 +115,82 @@ def test_training_objective_and_loss_match_reference(golden_dir):
         la, ln = T.regression_loss(g["pred_a"], g["pred_x"], g["clean_a"], g["clean_x"], flags, weights, 1.0, 0.5, red)
         torch.testing.assert_close(la, g[f"loss_adj_{red}"], rtol=1e-6, atol=0)
         torch.testing.assert_close(ln, g[f"loss_node_{red}"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["vg", "coco"])
+def test_precond_matches_reference_full_geometries(name, golden_dir):
+    """NodeAdjPrecond.forward of the unmodified reference on the shipped geometries (coin-flip stream included)."""
+    torch.set_num_threads(8)
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"precond_{name}.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    adj, node, flags, _, _, _ = synthetic_inputs(cfg, 2, seed=7)
+    coins = iter(g["coins"])
+    sa = sn = None
+    with torch.no_grad():
+        for k, s in enumerate((40.0, 3.0, 0.4, 0.01)):
+            sa, sn = O.precond_forward(_net(cfg, sd), adj * s, node * s, flags, torch.full((2,), s), sa, sn,
+                                       coin=lambda: next(coins))
+            for got, key in ((sa, f"adj_{k}"), (sn, f"node_{k}")):
+                want = torch.from_numpy(g[key])
+                assert (got - want).norm() / want.norm() < 2e-6, key
+
+
+RAW_TYPES = {"vg": (150, 51), "coco": (171, 7)}   # raw_num_node_type, raw_num_adj_type (utils/sg_utils.py:355-394)
+
+
+@pytest.mark.parametrize("name", ["vg", "coco"])
+def test_decode_matches_reference_closures(name, golden_dir):
+    """oracle.edm_oracle.decode_samples against the reference's own _decode_node / _decode_adj (the closures of
+    sg_go_sampling, runner/sampler/sampler_node_adj.py:222-285, executed from their source text by
+    tests/golden/make_golden_full.py) and its bbox rule (:202-209): bit-exact, on the 256-step samples of the
+    reference and on an edge-case tensor (exact zeros, values beyond the clamp, out-of-range bit patterns)."""
+    g = np.load(os.path.join(golden_dir, f"decode_{name}.npz"))
+    s = np.load(os.path.join(golden_dir, f"sampler256_{name}.npz"))
+    n_node, n_adj = RAW_TYPES[name]
+    cases = {"final": (s["adjs"], s["nodes"], s["flags"]), "edge": (g["edge_adj"], g["edge_node"], g["edge_flags"])}
+    for key, (a, n, f) in cases.items():
+        qa, qn, box = E.decode_samples(torch.from_numpy(a), torch.from_numpy(n), torch.from_numpy(f), n_adj, n_node)
+        np.testing.assert_array_equal(qa.numpy(), g[f"{key}_q_adj"])
+        np.testing.assert_array_equal(qn.numpy(), g[f"{key}_q_node"])
+        np.testing.assert_array_equal(box.numpy(), g[f"{key}_bbox"])
+    assert g["edge_q_adj"].max() == n_adj - 1 and g["edge_q_node"].max() == n_node - 1   # the clamp is exercised
+
+
+def _cpu_stream_normal(shape):
+    return torch.randn(shape)
+
+
+@pytest.mark.parametrize("case,name", [("coco", "coco"), ("vg", "vg")])
+def test_sampler256_first_snapshot_matches_reference(case, name, golden_dir):
+    """The oracle loop on the 256-step schedule against the reference's 256-step golden run, through the first
+    interim snapshot (after step 0; the full-length comparison is DSG_SLOW=1 / tools, it takes minutes on a CPU).
+    Noise and coins come from the global generators seeded like the golden run."""
+    torch.set_num_threads(8)
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"sampler256_{case}.npz"))
+    steps = 256 if os.environ.get("DSG_SLOW", "0") == "1" else 1
+    sd = synthetic_state_dict(cfg, seed=1234, stress=(case != "vg_refinit"))
+    flags = torch.from_numpy(g["flags"])
+
+    def model(a, n, f, sig, sa, sn):
+        return O.precond_forward(_net(cfg, sd), a, n, f, sig, sa, sn, coin=np.random.rand)
+
+    torch.manual_seed(int(g["torch_seed"]))
+    np.random.seed(int(g["numpy_seed"]))
+    ts = E.t_steps_fp32(256)
+    with torch.no_grad():
+        adjs, nodes = E.init_sample(flags, cfg["c_e"], cfg["c_n"], _cpu_stream_normal)
+        np.testing.assert_array_equal(nodes[:2].numpy(), g["nodes_ls"][0])          # the initial noise itself
+        adjs, nodes = adjs * ts[0], nodes * ts[0]
+        sc_a = sc_n = None
+        snap = {int(s): k + 1 for k, s in enumerate(g["snapshot_steps"])}
+        for i in range(steps):
+            adjs, nodes, sc_a, sc_n, _ = E.heun_step(model, adjs, nodes, flags, sc_a, sc_n, ts[i], ts[i + 1], i, 256,
+                                                     _cpu_stream_normal)
+            if i in snap:
+                for got, want in ((adjs[:2], g["adjs_ls"][snap[i]]), (nodes[:2], g["nodes_ls"][snap[i]])):
+                    want = torch.from_numpy(want)
+                    assert (got - want).norm() / want.norm() < 1e-5, (i, float((got - want).norm() / want.norm()))
+    if steps == 256:
+        assert (adjs - torch.from_numpy(g["adjs"])).norm() / torch.from_numpy(g["adjs"]).norm() < 1e-4
