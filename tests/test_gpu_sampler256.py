@@ -11,7 +11,8 @@ denoiser; the EDM step kernels themselves are bit-exact).
 Stated tolerances (BASELINE.json north_star: "decoded node, edge and box outputs agreeing at a stated rate"):
   state after every 32 steps and at the end:   rel-L2 <= TOL_STATE
   decoded edge / node classes (the reference's decode rule, golden from its own _decode_adj / _decode_node):
-       >= RATE over valid entries for reference-like init (`vg_refinit`: BASELINE's "random-init weights"),
+       >= RATE over valid entries (100 % for reference-like init, `vg_refinit`: BASELINE's "random-init weights";
+       >= 98 % / 99 % edges / nodes for the stress-initialised weights, whose outputs straddle the sign threshold),
        and 100 % wherever every bit of the reference value is further than MARGIN from the sign threshold;
   boxes: |delta| <= 1e-2 on the [0, 1] scale for >= 99 % of valid nodes.
 """
@@ -32,8 +33,14 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 RAW_TYPES = {"vg": (150, 51), "coco": (171, 7)}   # raw_num_node_type, raw_num_adj_type (utils/sg_utils.py:355-394)
 CASES = {"vg": ("vg", True), "vg_refinit": ("vg", False), "coco": ("coco", True)}
-TOL_STATE = {"vg": 3e-2, "vg_refinit": 3e-3, "coco": 3e-2}
-RATE = {"vg": 0.97, "vg_refinit": 0.99, "coco": 0.97}
+# measured on the B200 (r2): vg 6.3e-3 / 3.5e-3 (adj / node), coco 6.7e-3 / 3.4e-3, vg_refinit 1e-6 / 3e-7
+TOL_STATE = {"vg": 1.5e-2, "vg_refinit": 1e-4, "coco": 1.5e-2}
+# (edge classes, node classes, single bits); measured: vg 98.93 % / 99.41 % / 99.8 %, coco 99.35 % / 100 %, vg_refinit
+# 100 % / 100 %.  With the stress-initialised weights the final values are spread continuously through the sign
+# threshold (rms 0.6), so a 6-bit edge class flips whenever any of its bits lies within the ~4e-3 state error of 0;
+# with reference-like init (the weights the benchmark runs) and wherever the reference value is MARGIN away from the
+# threshold the agreement is exact.
+RATE = {"vg": (0.98, 0.99, 0.997), "vg_refinit": (0.9999, 0.9999, 0.9999), "coco": (0.99, 0.99, 0.997)}
 MARGIN = 0.06
 
 
@@ -72,7 +79,7 @@ def test_sampler256_matches_reference(case, golden_dir):
         torch.randn_like = real_like
     assert sampler.last_raw_passes == int(g["raw_passes"])          # same coin stream, same pass count
     np.testing.assert_array_equal(n_ls[0, :2].numpy(), g["nodes_ls"][0])   # identical initial noise
-    traj = [(_rel(a_ls[k, :2], g["adjs_ls"][k]), _rel(n_ls[k, :2], g["nodes_ls"][k])) for k in range(1, 11)]
+    traj = [(_rel(a_ls[k, :2], g["adjs_ls"][k]), _rel(n_ls[k, :2], g["nodes_ls"][k])) for k in range(1, 10)]
     ga, gn = torch.from_numpy(g["adjs"]), torch.from_numpy(g["nodes"])
     n_node, n_adj = RAW_TYPES[name]
     d = np.load(os.path.join(golden_dir, f"decode_{name}.npz")) if case == name else None
@@ -85,7 +92,9 @@ def test_sampler256_matches_reference(case, golden_dir):
     nb = cfg["c_n"] - 4
     far_e = (ga.abs() > MARGIN).all(1) & pair
     far_n = (gn[..., :nb].abs() > MARGIN).all(-1) & flags
-    stats = dict(case=case, rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
+    bits_g = torch.cat([(a > 0)[pair[:, None].expand_as(a)], (n[..., :nb] > 0)[flags]])
+    bits_r = torch.cat([(ga > 0)[pair[:, None].expand_as(ga)], (gn[..., :nb] > 0)[flags]])
+    stats = dict(case=case, bit_agree=float((bits_g == bits_r).float().mean()), rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
                  edge_agree=float((qa == ra)[pair].float().mean()), node_agree=float((qn == rn)[flags].float().mean()),
                  edge_agree_far=float((qa == ra)[far_e].float().mean()), node_agree_far=float((qn == rn)[far_n].float().mean()),
                  far_frac=(float(far_e.sum() / pair.sum()), float(far_n.sum() / flags.sum())),
@@ -98,7 +107,8 @@ def test_sampler256_matches_reference(case, golden_dir):
             f.write(repr(stats) + "\n")
     assert stats["rel_adj"] <= TOL_STATE[case] and stats["rel_node"] <= TOL_STATE[case], stats
     assert max(max(t) for t in traj) <= 2 * TOL_STATE[case], stats
-    assert stats["edge_agree"] >= RATE[case] and stats["node_agree"] >= RATE[case], stats
+    assert stats["edge_agree"] >= RATE[case][0] and stats["node_agree"] >= RATE[case][1], stats
+    assert stats["bit_agree"] >= RATE[case][2], stats
     assert stats["edge_agree_far"] == 1.0 and stats["node_agree_far"] == 1.0, stats
     assert stats["box_within_1e2"] >= 0.99, stats
 
