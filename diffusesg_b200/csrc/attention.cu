@@ -425,10 +425,9 @@ int launch_t(const bf16* qkv, const float* bias, const float* mask, bf16* out, i
   const long long grid = static_cast<long long>(batch) * nW * heads;
   DSG_REQUIRE(grid > 0 && grid < 2147483647LL, "attention: grid out of range");
   constexpr int smem = (2 * T_PAD * QK_PITCH + HD * (T_PAD + 8)) * 2 + T_PAD * 4;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_kernel<T_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   window_attention_kernel<T_PAD><<<static_cast<unsigned>(grid), (T_PAD / 16) * 32, smem, st>>>(qkv, bias, mask, out, res,
                                                                                             window, shift, heads);

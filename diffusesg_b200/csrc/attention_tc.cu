@@ -1080,19 +1080,12 @@ int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, in
     return rc;
   if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   TcParams p;
   p.bias = bias;
   p.heads = heads;
@@ -1167,18 +1160,11 @@ int launch_window_attention_w16(const bf16* qkv, const float* bias, bf16* out, i
     return rc;
   if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, 8, 8))
     return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_w16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW16SmemBytes));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   QdParams p;
   p.bias = bias;
   p.heads = heads;
@@ -1211,13 +1197,7 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
     return rc;
   if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   QdParams p;
   p.bias = bias;
   p.heads = heads;
@@ -1237,13 +1217,13 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
   switch (hw) {
 #define DSG_QUAD_CASE(H)                                                                                                  \
   case H: {                                                                                                               \
-    static bool configured = false;                                                                                       \
-    if (!configured) {                                                                                                    \
+    static PerDeviceOnce configured;                                                                                       \
+    if (configured.first()) {                                                                                                    \
       DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H, false>,                                         \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));                    \
       DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_quad_kernel<H, true>,                                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kQdSmemBytes));                    \
-      configured = true;                                                                                                  \
+                                                                                                                      \
     }                                                                                                                     \
     if (shift) window_attention_quad_kernel<H, true><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);      \
     else window_attention_quad_kernel<H, false><<<per_head * heads, kQdThreads, kQdSmemBytes, st>>>(tq, to, p);           \

@@ -368,18 +368,11 @@ int launch_block_head(const CUtensorMap* tmXin, const CUtensorMap* tmXout, const
                       const float* beta, const float* bqkv, long long rows, int C, cudaStream_t st) {
   DSG_REQUIRE(block_head_supported(C) && rows > 0 && rows < 2147483647LL, "block_head: C=%d rows=%lld", C, rows);
   using G = HeadCfg<96>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(block_head_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   HeadParams p{film, film_ld, cond_uniform, tokens_per_sample, gamma, beta, bqkv, static_cast<int>(rows)};
   const int tiles = (p.M + 127) / 128;
   block_head_kernel<96><<<tiles < sms ? tiles : sms, kHeadThreads, G::SMEM_BYTES, st>>>(*tmXin, *tmXout, *tmW, *tmQ, p);

@@ -642,21 +642,14 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmAtt, const __grid_consta
 template <int C>
 int launch_c(const CUtensorMap* tmAtt, const CUtensorMap* tmWp, const CUtensorMap* tmW1, const CUtensorMap* tmW2,
              const CUtensorMap* tmX, const CUtensorMap* tmY, const TailParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TailCfg<C>::SMEM_BYTES));
     DSG_CUDA_CHECK(cudaFuncSetAttribute(block_tail_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         TailCfg<C>::SMEM_BYTES));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   const int tiles = (p.M + 127) / 128;
   if (tmY != nullptr)
     block_tail_kernel<C, true><<<tiles < sms ? tiles : sms, kTailThreads, TailCfg<C>::SMEM_BYTES, st>>>(

@@ -377,4 +377,34 @@ DSG_DEVICE void mma_m16n8k16_bf16(float (&d)[4], const uint32_t (&a)[4], const u
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+
+// ---- per-device one-time setup -----------------------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a second
+// GPU driven from the same process (nn.DataParallel, a notebook) needs its own opt-in.  `once.first()` is true the
+// first time a call site runs with a given device current.
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev;
+}
+struct PerDeviceOnce {
+  unsigned long long seen[4] = {0, 0, 0, 0};  // 256 device ordinals
+  bool first() {
+    const int d = current_device() & 255;
+    const unsigned long long bit = 1ull << (d & 63);
+    const unsigned long long old = __atomic_fetch_or(&seen[d >> 6], bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0;
+  }
+};
+inline int device_sm_count() {
+  static int cache[256];
+  const int d = current_device() & 255;
+  int n = __atomic_load_n(&cache[d], __ATOMIC_RELAXED);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    __atomic_store_n(&cache[d], n, __ATOMIC_RELAXED);
+  }
+  return n;
+}
+
 }  // namespace dsg

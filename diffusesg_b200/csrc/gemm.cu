@@ -408,25 +408,15 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return device_sm_count(); }
 
 template <int BN, int EPI>
 int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, const GemmParams& p,
              cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg<BN>::SMEM_BYTES));
-    configured = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -440,11 +430,10 @@ template <int BN, int EPI>
 int launch_pair(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, const GemmParams& p,
                 cudaStream_t st) {
   using K = Cfg<BN, true>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         K::SMEM_BYTES));
-    configured = true;
   }
   const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * (p.N / BN);
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;

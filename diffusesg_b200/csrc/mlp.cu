@@ -377,19 +377,12 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 template <int C>
 int launch_c(const CUtensorMap* tmY, const CUtensorMap* tmW1, const CUtensorMap* tmW2, const CUtensorMap* tmX,
              const MlpParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(fused_mlp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         MlpCfg<C>::SMEM_BYTES));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   const int tiles = (p.M + 127) / 128;
   fused_mlp_kernel<C><<<tiles < sms ? tiles : sms, kMlpThreads, MlpCfg<C>::SMEM_BYTES, st>>>(*tmY, *tmW1, *tmW2, *tmX, p);
   DSG_LAUNCH_CHECK();

@@ -280,18 +280,11 @@ proj_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int C>
 int launch_c(const CUtensorMap* tmA, const CUtensorMap* tmW, const PlParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(proj_ln_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, PlCfg<C>::SMEM_BYTES));
-    configured = true;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   const int tiles = (p.M + 127) / 128;
   proj_ln_kernel<C><<<tiles < sms ? tiles : sms, PlCfg<C>::THREADS, PlCfg<C>::SMEM_BYTES, st>>>(*tmA, *tmW, p);
   DSG_LAUNCH_CHECK();

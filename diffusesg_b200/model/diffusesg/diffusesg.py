@@ -375,6 +375,10 @@ class _NativeModel:
             return bool(flag.item())
 
     def upload(self, state):
+        with native.device_guard(self.device):
+            self._upload(state)
+
+    def _upload(self, state):
         st = native.stream_ptr(self.device)
         keep = []
         for key, numel, dtype in self.keys():
@@ -407,8 +411,9 @@ class _NativeModel:
         a.out_adj, a.out_node = out_adj.data_ptr(), out_node.data_ptr()
         a.workspace = self.workspace.data_ptr() + off
         a.workspace_bytes = self.workspace.numel() - off
-        native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
-                     "dsg_denoiser_forward")
+        with native.device_guard(self.device):
+            native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
+                         "dsg_denoiser_forward")
 
     def debug_buffer(self, name: str, dtype: torch.dtype) -> torch.Tensor:
         """Test hook: flat view of a named activation buffer of the last forward's workspace."""

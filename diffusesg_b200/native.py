@@ -5,7 +5,9 @@ used only as the owner of device memory and streams; every pointer crossing the 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
 import os
 from typing import Optional
 
@@ -153,6 +155,26 @@ def profile_stop() -> None:
     lib().dsg_profile_stop()
 
 
+def device_guard(device):
+    """Make `device` current for the duration of a native call (the library's launches and one-time per-device
+    setup use the current device); free when it already is."""
+    idx = device.index if isinstance(device, torch.device) else device
+    if idx is None or torch.cuda.current_device() == idx:
+        return contextlib.nullcontext()
+    return torch.cuda.device(idx)
+
+
+def _on_device_of_first_tensor(fn):
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None:
+            return fn(*args, **kwargs)
+        with device_guard(t.device):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def stream_ptr(device=None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -172,6 +194,7 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tenso
 # ---------------------------------------------------------------------------------------------------------
 # thin functional wrappers (used by the kernel-level parity tests)
 # ---------------------------------------------------------------------------------------------------------
+@_on_device_of_first_tensor
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias=None, res=None, epi: int = EPI_F32) -> torch.Tensor:
     """epilogue(a [M,K] @ w [N,K]^T + bias) on the tcgen05 kernel.  a, w: bf16 CUDA."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -184,6 +207,7 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias=None, res=None, epi: int = 
     return out
 
 
+@_on_device_of_first_tensor
 def window_attention(qkv: torch.Tensor, bias: torch.Tensor, mask, batch: int, res: int, window: int, shift: int,
                      heads: int) -> torch.Tensor:
     assert qkv.is_cuda and qkv.dtype == torch.bfloat16
@@ -193,6 +217,7 @@ def window_attention(qkv: torch.Tensor, bias: torch.Tensor, mask, batch: int, re
     return out
 
 
+@_on_device_of_first_tensor
 def edm_pre_step(adj, node, eps_adj, eps_node, flags, noise_coef: float):
     b, ce, n, _ = adj.shape
     cn = node.shape[-1]
@@ -211,6 +236,7 @@ def _aten_normal_policy(numel: int, dev: torch.device):
     return grid, ((numel - 1) // (256 * grid * 4) + 1) * 4
 
 
+@_on_device_of_first_tensor
 def edm_pre_step_fused_noise(adj, node, flags, noise_coef: float):
     """edm_pre_step with eps_adj = randn_like(adj), eps_node = randn_like(node) drawn inside the kernel from the
     current torch CUDA generator state, which is advanced exactly as the two randn_like calls would advance it
@@ -234,6 +260,7 @@ def aten_normal_policy(numel: int, dev: torch.device):
     return _aten_normal_policy(numel, dev)
 
 
+@_on_device_of_first_tensor
 def edm_final_step_decode(adj_hat, node_hat, d1, flags, inv_t_hat: float, h: float, num_adj_type: int,
                           num_node_type: int, want_state: bool = True, cur_params: Optional[int] = None):
     """Last (Euler) sampler step fused with the decode of the final sample: returns
@@ -253,6 +280,7 @@ def edm_final_step_decode(adj_hat, node_hat, d1, flags, inv_t_hat: float, h: flo
     return adj_next, node_next, adj_cls, node_cls, bbox
 
 
+@_on_device_of_first_tensor
 def edm_post_step(adj_hat, node_hat, d1, d2, flags, inv_t_hat: float, h: float, inv_t_prime: float):
     b, ce, n, _ = adj_hat.shape
     cn = node_hat.shape[-1]
@@ -264,6 +292,7 @@ def edm_post_step(adj_hat, node_hat, d1, d2, flags, inv_t_hat: float, h: float, 
     return adj_next, node_next
 
 
+@_on_device_of_first_tensor
 def edm_mask_scale(adj, node, flags, scale: float):
     b, ce, n, _ = adj.shape
     cn = node.shape[-1]
@@ -277,6 +306,7 @@ def _flags_u8(flags: torch.Tensor) -> torch.Tensor:
     return (flags if flags.dtype == torch.uint8 else flags.to(torch.uint8)).contiguous()
 
 
+@_on_device_of_first_tensor
 def train_noise(clean_adj, clean_node, eps_adj, eps_node, sigmas, flags):
     """(noisy_adj, noise_adj, noisy_node, noise_node) of the EDM training objective, one fused launch."""
     clean_adj, clean_node = require_cuda(clean_adj, "clean_adj"), require_cuda(clean_node, "clean_node")
@@ -293,6 +323,7 @@ def train_noise(clean_adj, clean_node, eps_adj, eps_node, sigmas, flags):
     return tuple(outs)
 
 
+@_on_device_of_first_tensor
 def edm_loss_sums(pred_adj, target_adj, pred_node, target_node, weights, flags):
     """([B] masked weighted squared-error sum over the adjacency tensor, [B] over the node tensor)."""
     pred_adj, target_adj = require_cuda(pred_adj, "pred_adj"), require_cuda(target_adj, "target_adj")
@@ -309,6 +340,7 @@ def edm_loss_sums(pred_adj, target_adj, pred_node, target_node, weights, flags):
     return s_adj, s_node
 
 
+@_on_device_of_first_tensor
 def decode_samples(adj, node, flags, num_adj_type: int, num_node_type: int):
     """int32 edge classes [B,N,N], int32 node classes [B,N], fp32 boxes [B,N,4] of a final sample, on the device."""
     b, ce, n, _ = adj.shape
