@@ -35,6 +35,11 @@ class NodeAdjRainbowLoss(nn.Module):
             raise NotImplementedError
         if reweight_coef is not None or node_flags.dim() != 2 or pred_adj.dim() != 4 or pred_node.dim() != 3:
             raise NotImplementedError("only [B, C, N, N] / [B, N, F] tensors with [B, N] flags and no reweighting are built")
+        if torch.is_grad_enabled() and (pred_adj.requires_grad or pred_node.requires_grad):
+            raise NotImplementedError("NodeAdjRainbowLoss (B200) is forward-only: the fused reduction carries no autograd "
+                                      "graph, so loss.backward() would silently train nothing.  Evaluate it under "
+                                      "torch.no_grad() (validation loss), or keep the reference loss for training until "
+                                      "the native backward pass lands (SURVEY 8f-2)")
         s_adj, s_node = native.edm_loss_sums(pred_adj, target_adj, pred_node, target_node, loss_weight, node_flags)
         num_node_entries = node_flags.sum(dim=-1)      # [B]   (:80-82)
         num_adj_entries = num_node_entries ** 2

@@ -260,6 +260,42 @@ def aten_normal_policy(numel: int, dev: torch.device):
     return _aten_normal_policy(numel, dev)
 
 
+_FUSED_NOISE_OK = {}
+
+
+def fused_noise_ok(dev: torch.device) -> bool:
+    """One-time self-check per device: does the in-kernel Philox stream (which restates ATen's private launch policy
+    for ``normal_``: block 256, unroll 4, grid cap, counter increment) still reproduce ``torch.randn_like`` x 2 on the
+    installed torch, values AND generator advance?  If not (a torch upgrade changed the policy) the sampler keeps the
+    two ``randn_like`` launches instead of silently drawing a different stream.  The global generator is left
+    untouched."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key in _FUSED_NOISE_OK:
+        return _FUSED_NOISE_OK[key]
+    gen = torch.cuda.default_generators[key]
+    saved = gen.get_state()
+    try:
+        with device_guard(dev):
+            adj = torch.zeros(2, 3, 16, 16, device=dev)
+            node = torch.zeros(2, 16, 5, device=dev)
+            flags = torch.ones(2, 16, dtype=torch.bool, device=dev)
+            gen.manual_seed(0x5EED)
+            a, n = edm_pre_step_fused_noise(adj, node, flags, 1.0)      # 0 + 1 * eps == eps
+            probe = torch.rand(4, device=dev)
+            gen.manual_seed(0x5EED)
+            ra, rn = torch.randn_like(adj), torch.randn_like(node)
+            rprobe = torch.rand(4, device=dev)
+            ok = bool(torch.equal(a, ra) and torch.equal(n, rn) and torch.equal(probe, rprobe))
+    finally:
+        gen.set_state(saved)
+    if not ok:
+        import warnings
+        warnings.warn("diffusesg_b200: the fused Philox noise no longer matches torch.randn_like on this torch build "
+                      f"({torch.__version__}); falling back to torch.randn_like launches (and eager steps)")
+    _FUSED_NOISE_OK[key] = ok
+    return ok
+
+
 @_on_device_of_first_tensor
 def edm_final_step_decode(adj_hat, node_hat, d1, flags, inv_t_hat: float, h: float, num_adj_type: int,
                           num_node_type: int, want_state: bool = True, cur_params: Optional[int] = None):

@@ -204,7 +204,8 @@ class NodeAdjEDMSampler:
         adjs, nodes = native.edm_mask_scale(adjs, nodes, flags, float(self.sigma(t_steps[0]) * self.s(t_steps[0])))
         # all per-step scalars up front (host), the noise levels uploaded once: no per-step H2D copy or sync
         scalars = [self.step_scalars(t_steps[i], t_steps[i + 1]) for i in range(self.num_steps)]
-        fused = self.fused_noise and torch.randn_like is _TORCH_RANDN_LIKE   # a patched randn_like (noise replay) wins
+        # a patched randn_like (noise replay) wins; so does a torch whose normal_ launch policy moved (self-check)
+        fused = self.fused_noise and torch.randn_like is _TORCH_RANDN_LIKE and native.fused_noise_ok(dev)
         net = getattr(self._unwrap(model), "model", None)
         frozen = net.frozen_weights() if hasattr(net, "frozen_weights") else contextlib.nullcontext()
         with frozen:   # the weights cannot change inside the loop: staleness is probed once, on the first call
