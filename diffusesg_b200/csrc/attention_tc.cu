@@ -1069,16 +1069,27 @@ bool window_attention_tc_supported(int batch, int res, int window, int shift, in
   return windows % 2 == 0 && windows >= 2;
 }
 
+static int launch_tc_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int shift, int heads,
+                          cudaStream_t st);
+
 int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
                                cudaStream_t st) {
   DSG_REQUIRE(window_attention_tc_supported(batch, res, 8, shift, heads), "attention_tc: unsupported shape");
+  return launch_tc_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, shift, heads, st);
+}
+
+// img_rows token rows of `res` tokens: B stacked res x res grids, or (un-shifted windows only: a window's TMA
+// coordinates are 8 * (window / nwx), 8 * (window % nwx), no sample index involved) any stack of whole window rows
+static int launch_tc_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int shift, int heads,
+                          cudaStream_t st) {
+  const long long batch = img_rows;  // only ever used as batch * res below
   const int C = heads * 32;
   const int box = shift ? 4 : 8;  // shifted windows are gathered as four 4 x 4-token sub-boxes
   CUtensorMap tq, to;
   // [B res (token row), res (token column), channels]: a window is an 8 x 8 box of tokens, a head slice 32 channels
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch), 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
     return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch), 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
   static PerDeviceOnce configured;
   if (configured.first()) {
@@ -1092,7 +1103,7 @@ int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, in
   p.res = res;
   p.nwx = res / 8;
   p.nW = p.nwx * p.nwx;
-  p.pairs = static_cast<int>(static_cast<long long>(batch) * p.nW / 2);
+  p.pairs = static_cast<int>((img_rows / 8) * p.nwx / 2);
   int per_head = sms / heads;
   if (per_head > p.pairs) per_head = p.pairs;
   if (per_head < 1) per_head = 1;
@@ -1186,16 +1197,38 @@ int launch_window_attention_w16(const bf16* qkv, const float* bias, bf16* out, i
   return DSG_OK;
 }
 
+static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window, int shift,
+                            int heads, cudaStream_t st);
+
 int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
                                  int heads, cudaStream_t st) {
   DSG_REQUIRE(window_attention_quad_supported(batch, res, window, shift, heads), "attention_quad: unsupported shape");
+  return launch_quad_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, window, shift, heads, st);
+}
+
+bool window_attention_rows_supported(int res, int window, int heads) {
+  if (window == 8) return res % 8 == 0 && ((res / 8) % 2 == 0) && heads >= 1 && heads <= 74;
+  return window_attention_quad_supported(1, res, window, 0, heads);
+}
+
+int launch_window_attention_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window,
+                                 int heads, cudaStream_t st) {
+  DSG_REQUIRE(window_attention_rows_supported(res, window, heads) && img_rows > 0 && img_rows % window == 0,
+              "attention (rows): res %d window %d heads %d rows %lld", res, window, heads, img_rows);
+  if (window == 8) return launch_tc_rows(qkv, bias, out, img_rows, res, 0, heads, st);
+  return launch_quad_rows(qkv, bias, out, img_rows, res, window, 0, heads, st);
+}
+
+static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window, int shift,
+                            int heads, cudaStream_t st) {
+  const long long batch = img_rows;  // only ever used as batch * res below
   const int C = heads * 32;
   const int hw = window / 2;
   const int box = shift ? hw : window;  // shifted: four sub-boxes per window; un-shifted: the whole window
   CUtensorMap tq, to;
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch), 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
     return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch), 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
   const int sms = device_sm_count();
   QdParams p;
@@ -1208,7 +1241,7 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
   p.nwx = res / window;
   p.nW = p.nwx * p.nwx;
   p.T = window * window;
-  const long long items = static_cast<long long>(batch) * p.nW;
+  const long long items = (img_rows / window) * p.nwx;
   DSG_REQUIRE(items < 2147483647LL, "attention_quad: too many windows");
   p.items = static_cast<int>(items);
   int per_head = sms / heads;

@@ -227,7 +227,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // handles one tile at a time, so these dependent loads were ~1.5 k exposed cycles per tile
         const int n_ = p.n_img, nn_ = n_ * n_;
         const int rowc = row < p.M ? row : p.M - 1;
-        const int b_ = rowc / nn_, ij_ = rowc - b_ * nn_;
+        int b_ = rowc / nn_, ij_ = rowc - b_ * nn_;
+        if (p.row_b != nullptr) {
+          const int gr = rowc / n_;
+          b_ = p.row_b[gr];
+          ij_ = p.row_i[gr] * n_ + (rowc - gr * n_);
+        }
+        const bool real_ = b_ >= 0;   // phantom rows of the compact layout produce no output
+        if (!real_) b_ = 0;
         bool ok_ = false;
         float cs_ = 0.f, co_ = 1.f, xa_[8];
         if (half == 0) {
@@ -283,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const float4 pb = *reinterpret_cast<const float4*>(&sPart[r_in_tile * 8 + 4]);
           y[0] += pa.x + s_b2[0]; y[1] += pa.y + s_b2[1]; y[2] += pa.z + s_b2[2]; y[3] += pa.w + s_b2[3];
           y[4] += pb.x + s_b2[4]; y[5] += pb.y + s_b2[5]; y[6] += pb.z + s_b2[6]; y[7] += pb.w + s_b2[7];
-          if (row < p.M) {
+          if (row < p.M && real_) {
             // row = pixel (b, i, j); zero rows/cols of padded nodes (utils/graph_utils.py:5-38), optional EDM
             // output preconditioning D = c_skip x + c_out F (model/precond/precond.py:102-104)
 #pragma unroll

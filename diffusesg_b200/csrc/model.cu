@@ -162,6 +162,10 @@ struct dsg_model {
   bool use_final_ln = true;   // DSG_NO_FINAL_LN=1 keeps the network's last LayerNorm as its own launch
   int pair_min_k = 384;       // CTA pairs from this K upwards for the bf16 epilogue, 768 for the others (DSG_PAIR_MIN_K)
   bool use_head = true;       // DSG_NO_HEAD=1 keeps the FiLM + LayerNorm row kernel and the qkv GEMM as two launches
+  // Padded-row skipping (dsg_forward_args.skip_*): the leading `skip_stages` resolution stages are
+  // computed on a compact layout holding, per sample, only the first R_b image rows (R_b = n_b rounded up to
+  // `skip_granule` pixels).  0 = the geometry does not allow it (see skip_geometry below).
+  int skip_stages = 0, skip_granule = 0;
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -171,6 +175,8 @@ struct dsg_model {
 };
 
 namespace {
+
+void skip_geometry(dsg_model* m);
 
 void add_tensor(dsg_model* m, const std::string& key, int64_t numel, int dtype = 0) {
   TensorSpec t;
@@ -284,6 +290,7 @@ int build(dsg_model* m) {
       add_block(m, buf, dim, res, c.num_heads[s], j, s);
     }
   }
+  skip_geometry(m);
   for (int k = 0; k < 3; ++k) {
     snprintf(buf, sizeof(buf), "read_out.%d", k);
     add_linear(m, buf, m->E, m->E);
@@ -357,6 +364,38 @@ int build(dsg_model* m) {
   return DSG_OK;
 }
 
+// Leading stages whose blocks are all un-shifted window attention on the tcgen05 kernels and whose merge / breakup
+// widths have the sample-independent quarter-warp kernels.  Why un-shifted only: inside such a stage information
+// moves only within aligned windows, so (a) in the encoder a window that lies entirely in the padding of its sample
+// (rows >= n_b: every input of mask_adjs'ed pixels is zero, diffusesg.py:796-802) holds ONE token value, the same for
+// every such window of every sample at a given sigma - it is computed once, on an all-padding "phantom" sample;
+// (b) in the decoder nothing computed in such a window can reach a valid output pixel (the heads mask padded pixels,
+// diffusesg.py:812-825).  The first shifted block / merged-down dense stage mixes everything, so from there on the
+// grid is dense (the skipped rows are filled with the phantom's token first).
+void skip_geometry(dsg_model* m) {
+  m->skip_stages = 0;
+  m->skip_granule = 0;
+  const char* off = getenv("DSG_NO_SKIP");
+  if (off != nullptr && off[0] == '1') return;
+  int S = 0;
+  for (int s = 0; s + 1 < m->nl; ++s) {
+    bool ok = true;
+    for (int j = 0; j < m->cfg.depths[s]; ++j) {
+      const Block& b = m->blocks[m->down_first[s] + j];
+      const Block& u = m->blocks[m->up_first[m->nl - 1 - s] + j];
+      ok = ok && b.shift == 0 && u.shift == 0 && window_attention_rows_supported(b.res, b.window, b.heads);
+    }
+    ok = ok && row_compaction_supported(m->E << s, 4 * (m->E << s));
+    if (!ok) break;
+    S = s + 1;
+  }
+  while (S > 0) {
+    const int g = m->blocks[m->down_first[S - 1]].window << (S - 1);  // window of the coarsest compact stage, in pixels
+    if (g < m->N && m->N % g == 0) { m->skip_stages = S; m->skip_granule = g; return; }
+    --S;  // a single window spans the whole grid there: nothing to skip at that stage
+  }
+}
+
 int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st, int64_t n_scaled = 0,
                 float scale = 1.f) {
   int rc = launch_pack_bf16(m->f32(key), m->at<bf16>(w.offset), static_cast<int64_t>(w.N) * w.K, n_scaled, scale, st);
@@ -380,7 +419,8 @@ Workspace carve(const dsg_model* m, int batch, int n_cond, void* base) {
   Workspace w;
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t cur = 0;
-  const size_t tok0 = static_cast<size_t>(batch) * m->N * m->N;
+  // one extra sample of capacity: the compact layout of the padded-row skipping appends the phantom's rows
+  const size_t tok0 = static_cast<size_t>(batch + (m->skip_stages > 0 ? 1 : 0)) * m->N * m->N;
   const size_t full = tok0 * m->E;  // elements of a stage-0 activation; later stages hold full / 2^s
   auto take = [&](size_t bytes) { void* r = p ? p + cur : nullptr; cur = align_up(cur + bytes); return r; };
   w.X = static_cast<float*>(take(full * 4));
@@ -465,10 +505,11 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
 // fuse_final_ln: this is the last block of the network; if it runs the fused tail, the tail also applies the final
 // LayerNorm and writes only Y (*fused_final_ln = true), and the caller skips the separate LayerNorm launch.
 int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
-              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr) {
+              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr, long long img_rows = 0) {
+  // img_rows > 0: compact layout - the activation is a stack of img_rows token rows (not whole res x res grids)
   const int C = b.dim;
   const int L = b.res * b.res;
-  const long long rows = static_cast<long long>(batch) * L;
+  const long long rows = img_rows > 0 ? img_rows * b.res : static_cast<long long>(batch) * L;
   const std::string& p = b.prefix;
   const double rc = static_cast<double>(rows) * C;
   auto tmap0 = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
@@ -494,13 +535,19 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
   } else {
     // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
     DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
-                                                 m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"), batch, L, C, st));
+                                                 m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"),
+                                                 img_rows > 0 ? 1 : batch, img_rows > 0 ? static_cast<int>(rows) : L, C, st));
     DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
   }
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
-  DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
-            launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
-                                    b.heads, st, b.mask_canonical));
+  if (img_rows > 0) {
+    DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
+              launch_window_attention_rows(w.QKV, m->at<float>(b.attn_bias_off), w.ATT, img_rows, b.res, b.window, b.heads, st));
+  } else {
+    DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
+              launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
+                                      b.heads, st, b.mask_canonical));
+  }
   auto tmap = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
     auto k = std::make_tuple(ptr, rows, key);
     auto it = m->a_maps.find(k);
@@ -731,6 +778,13 @@ int dsg_model_finalize(dsg_model* m, dsg_stream_t stream) {
   return DSG_OK;
 }
 
+int dsg_model_skip_info(const dsg_model* m, int32_t* stages, int32_t* granule) {
+  DSG_REQUIRE(m != nullptr && stages != nullptr && granule != nullptr, "skip_info: null argument");
+  *stages = m->skip_stages;
+  *granule = m->skip_granule;
+  return DSG_OK;
+}
+
 size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond) {
   if (m == nullptr || batch <= 0 || n_cond <= 0) return 0;
   return carve(m, batch, n_cond, nullptr).bytes;
@@ -766,6 +820,25 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     labels = w.coef + 3 * B;
     label_stride = 1;
   }
+  // ---- padded-row skipping: compact layout of the leading un-shifted stages (see skip_geometry) ----------------
+  const int S = (a->skip_tables != nullptr && a->skip_img_rows > 0) ? m->skip_stages : 0;
+  const int G = m->skip_granule;
+  const int *row_b = nullptr, *row_i = nullptr, *sk_off = nullptr, *sk_rb = nullptr;
+  long long R0 = 0, R0_live = 0;  // image rows of the compact stage-0 grid with / without the phantom's G rows
+  if (a->skip_tables != nullptr && a->skip_img_rows > 0) {
+    DSG_REQUIRE(m->skip_stages > 0, "forward: this geometry has no compactable stage (skip_tables given)");
+    DSG_REQUIRE(uniform, "forward: padded-row skipping needs one shared noise level (n_cond == 1)");
+    DSG_REQUIRE(g_stop_after < 0, "forward: the stage-walk test hook runs on the dense schedule");
+    DSG_REQUIRE(a->skip_img_rows % G == 0 && a->skip_img_rows >= 2 * G && a->skip_cap_rows >= a->skip_img_rows &&
+                    a->skip_img_rows <= static_cast<long long>(B + 1) * N,
+                "forward: skip_img_rows %d (granule %d, capacity %d)", a->skip_img_rows, G, a->skip_cap_rows);
+    row_b = a->skip_tables;
+    row_i = row_b + a->skip_cap_rows;
+    sk_off = row_i + a->skip_cap_rows;   // [B + 2]: first image row of each sample, of the phantom, and the end
+    sk_rb = sk_off + (B + 2);            // [B + 1]: kept rows per sample (phantom: G)
+    R0 = a->skip_img_rows;
+    R0_live = R0 - G;
+  }
   g_prof_pass = g_prof_on && !stream_capturing(st) && (g_prof_counter++ % g_prof_stride == 0);
   struct ProfPassGuard { ~ProfPassGuard() { g_prof_pass = false; } } prof_pass_guard;
   const double px = static_cast<double>(B) * N * N;
@@ -776,10 +849,11 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   // patch embedding straight from (adj, node): the [B, cin, N, N] grid of :784-802 is never built
   DSG_TRY_P(PC_EMBED_HEAD, 0, 0, launch_node_proj(a->node, a->sc_node, c_in, m->at<float>(m->w_rc_off), w.rc, B, N, m->cfg.c_n,
                            m->cfg.self_condition, E, st));
-  DSG_TRY_P(PC_EMBED_HEAD, 0, px * (m->planes_adj * 4 + E * 4), launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
+  const double px0 = S > 0 ? static_cast<double>(R0) * N : px;   // pixels actually embedded
+  DSG_TRY_P(PC_EMBED_HEAD, 0, px0 * (m->planes_adj * 4 + E * 4), launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
                              m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
                              m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
-                             m->cfg.self_condition, E, st));
+                             m->cfg.self_condition, E, st, row_b, row_i, R0));
   int stage_no = 0;
   bool final_ln_done = false;
 #define DSG_STAGE_DONE() do { if (g_stop_after >= 0 && stage_no++ == g_stop_after) return DSG_OK; } while (0)
@@ -788,16 +862,32 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   for (int s = 0; s < m->nl; ++s) {
     const float* x_in = s == 0 ? w.X : w.skip[s - 1];
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
-      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st));
+      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr, s < S ? (R0 >> s) : 0));
       x_in = w.X;
       DSG_STAGE_DONE();
     }
     if (s < m->nl - 1) {
       const Merge& g = m->merges[s];
-      const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
-      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows) * 4 * g.C * 6,
-                launch_merge_ln(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), B, g.res, g.C, st));
-      DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
+      if (s < S) {
+        // compact stage: merge the stacked rows; the last compact stage expands into the dense grid of stage s + 1,
+        // filling every skipped row with the phantom's token
+        const long long rows = ((R0 >> s) / 2) * (g.res / 2);
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows) * 4 * g.C * 6,
+                  launch_merge_ln_rows(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), R0 >> s,
+                                       g.res, g.C, st));
+        if (s + 1 < S) {
+          DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
+        } else {
+          DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.T, st));
+          const double dense_el = static_cast<double>(B) * (g.res / 2) * (g.res / 2) * 2 * g.C;
+          DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_expand_fill(w.T, w.skip[s], sk_off, sk_rb, s + 1, B, g.res / 2, 2 * g.C, st));
+        }
+      } else {
+        const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows) * 4 * g.C * 6,
+                  launch_merge_ln(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), B, g.res, g.C, st));
+        DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
+      }
       DSG_STAGE_DONE();
     }
   }
@@ -808,25 +898,52 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     const float* x_in = w.X;
     if (u > 0) {
       const Breakup& bu = m->breakups[u - 1];
-      const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
       // the low-resolution stream lives in X unless no block ran since the last merge (cannot happen: depth >= 1)
-      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
-      DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
-      DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_breakup_ln(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
-                                m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"), B, bu.res,
-                                bu.D, st));
-      DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
+      if (s + 1 < S) {
+        // compact -> compact (the phantom's rows are dead in the decoder: R0_live)
+        const long long img_low = R0_live >> (s + 1);
+        const long long rows_low = img_low * bu.res;
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+        DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6,
+                  launch_breakup_ln_rows(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                         m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
+                                         img_low, bu.res, bu.D, nullptr, nullptr, 0, st));
+        DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
+      } else if (s < S) {
+        // dense -> compact: only the children inside each sample's kept rows are produced
+        const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
+        const long long rows_hi = (R0_live >> s) * (2 * bu.res);
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+        DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 4 + static_cast<double>(rows_hi) * bu.D / 2,
+                  launch_breakup_ln_rows(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                         m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
+                                         static_cast<long long>(B) * bu.res, bu.res, bu.D, sk_off, sk_rb, s, st));
+        DSG_TRY(gemm(m, w.Y, rows_hi, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
+      } else {
+        const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+        DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_breakup_ln(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                  m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"), B, bu.res,
+                                  bu.D, st));
+        DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
+      }
       DSG_STAGE_DONE();
     }
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
       // the last block: the final LayerNorm rides on its fused tail (not while a test walks the stages: those read X)
       const bool last = u == m->nl - 1 && j == m->cfg.depths[s] - 1 && m->use_final_ln && g_stop_after < 0;
-      DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done));
+      DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done,
+                        s < S ? (R0_live >> s) : 0));
       DSG_STAGE_DONE();
     }
   }
   // read-out                                                                 (:758-761, :806-825)
-  const long long pixels = static_cast<long long>(B) * N * N;
+  const long long pixels = S > 0 ? R0_live * N : static_cast<long long>(B) * N * N;
+  if (S > 0)  // rows that are not computed are padding: their outputs are the masked zeros
+    DSG_CUDA_CHECK(cudaMemsetAsync(a->out_adj, 0, static_cast<size_t>(B) * m->cfg.c_e * N * N * 4, st));
   if (!final_ln_done)
     DSG_TRY_P(PC_ROW, 0, px * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
   GemmParams hp;
@@ -839,11 +956,13 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   hp.x_adj = a->mode == 1 ? a->adj : nullptr;
   hp.c_skip = c_skip;
   hp.c_out = c_out;
+  hp.row_b = row_b;
+  hp.row_i = row_i;
   DSG_TRY(gemm(m, w.Y, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->at<float>(m->adj_b1_off), nullptr, a->out_adj, st, &hp));
   DSG_TRY_P(PC_EMBED_HEAD, 0, px * E * 2, launch_node_head(w.Y, a->flags, m->at<float>(m->fold_ft_off), m->at<float>(m->fold_b_off),
                            m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
                            m->at<float>(m->node_w2t_off), m->f32("readout_node_mlp.fc2.bias"),
-                           a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st));
+                           a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st, sk_off));
   return DSG_OK;
 }
 

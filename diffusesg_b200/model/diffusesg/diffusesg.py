@@ -246,10 +246,22 @@ class DiffuseSG(nn.Module):
         native schedule (the scalings ride inside the patch-embedding and read-out kernels)."""
         return self._run(1, adjs, nodes, node_flags, sigmas, self_cond_adjs, self_cond_nodes)
 
-    def denoise_into(self, nat, adjs, nodes, flags, sigma_ptr_tensor, sc_adjs, sc_nodes, out_adjs, out_nodes):
+    def denoise_into(self, nat, adjs, nodes, flags, sigma_ptr_tensor, sc_adjs, sc_nodes, out_adjs, out_nodes, skip=None):
         """`denoise` on pre-validated contiguous fp32 CUDA tensors with one shared sigma read from device memory and
         caller-provided outputs: no allocation, no checks - what the sampler captures into its CUDA graphs."""
-        nat.forward(1, adjs.shape[0], 1, adjs, nodes, flags, sigma_ptr_tensor, 0, sc_adjs, sc_nodes, out_adjs, out_nodes)
+        nat.forward(1, adjs.shape[0], 1, adjs, nodes, flags, sigma_ptr_tensor, 0, sc_adjs, sc_nodes, out_adjs, out_nodes,
+                    skip)
+
+    def make_skip_plan(self, node_flags, device=None):
+        """Padded-row skipping plan for a batch with these node flags (include/dsg_b200.h: dsg_model_skip_info), or
+        None when the geometry has no compactable stage or the batch has (almost) no padding to skip.  Reads the
+        flags on the host (one small D2H copy): build it once per batch, not per call."""
+        device = torch.device(device) if device is not None else node_flags.device
+        return SkipPlan.build(self._native(device), node_flags, self.img_size)
+
+    def skipping(self, plan):
+        """Context manager: calls with one shared noise level and the plan's batch size inside use `plan`."""
+        return _Skipping(self, plan)
 
     def _run(self, mode, adj, node, flags, noise, sc_adj, sc_node):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
@@ -287,8 +299,73 @@ class DiffuseSG(nn.Module):
         nat = self._native(dev)
         out_adj = torch.empty_like(adj)
         out_node = torch.empty_like(node)
-        nat.forward(mode, b, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node)
+        skip = self.__dict__.get("_active_skip")
+        if skip is not None and (n_cond != 1 or skip.batch != b or skip.nat is not nat):
+            skip = None
+        nat.forward(mode, b, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node, skip)
         return out_adj, out_node
+
+
+class SkipPlan:
+    """Device tables of the compact row layout (row_b | row_i | off | rb, int32) for one batch of node flags."""
+
+    def __init__(self, nat, batch, tables, img_rows, cap, kept_fraction):
+        self.nat, self.batch, self.tables, self.img_rows, self.cap = nat, batch, tables, img_rows, cap
+        self.kept_fraction = kept_fraction
+
+    @staticmethod
+    def host_tables(flags_host: torch.Tensor, n: int, granule: int, cap: int):
+        """(int32 numpy table of length 2 * cap + 2 * B + 3, image rows incl. the phantom's)."""
+        import numpy as np
+        f = flags_host.to(torch.bool).cpu().numpy()
+        b = f.shape[0]
+        last = np.where(f.any(1), n - np.argmax(f[:, ::-1], axis=1), 0)          # index of the last valid node + 1
+        rb = np.minimum(n, np.maximum(granule, -(-last // granule) * granule)).astype(np.int64)
+        off = np.zeros(b + 2, dtype=np.int64)
+        off[1:b + 1] = np.cumsum(rb)
+        off[b + 1] = off[b] + granule
+        total = int(off[b + 1])
+        table = np.zeros(2 * cap + 2 * b + 3, dtype=np.int32)
+        row_b = np.repeat(np.arange(b + 1), np.append(rb, granule))
+        row_b[row_b == b] = -1
+        row_i = np.arange(total) - np.repeat(off[:b + 1], np.append(rb, granule))
+        table[:total] = row_b
+        table[cap:cap + total] = row_i
+        table[2 * cap:2 * cap + b + 2] = off
+        table[2 * cap + b + 2:2 * cap + 2 * b + 2] = rb
+        table[2 * cap + 2 * b + 2] = granule
+        return table, total
+
+    @staticmethod
+    def build(nat, node_flags, n, out=None, min_saving=0.03):
+        stages, granule = nat.skip_info()
+        if stages == 0 or node_flags.dim() != 2 or node_flags.shape[1] != n:
+            return None
+        b = node_flags.shape[0]
+        cap = (b + 1) * n
+        table, total = SkipPlan.host_tables(node_flags, n, granule, cap)
+        if total > (1.0 - min_saving) * b * n:
+            return None      # (almost) nothing to skip: the dense schedule is as fast and has no phantom
+        t = torch.from_numpy(table)
+        if out is None:
+            out = t.to(nat.device)
+        else:
+            out.copy_(t)
+        return SkipPlan(nat, b, out, total, cap, total / float(b * n))
+
+
+class _Skipping:
+    def __init__(self, module, plan):
+        self.m, self.plan = module, plan
+
+    def __enter__(self):
+        self.prev = self.m.__dict__.get("_active_skip")
+        self.m.__dict__["_active_skip"] = self.plan
+        return self.plan
+
+    def __exit__(self, *exc):
+        self.m.__dict__["_active_skip"] = self.prev
+        return False
 
 
 class _Frozen:
@@ -393,7 +470,13 @@ class _NativeModel:
         native.check(self.lib.dsg_model_finalize(self.handle, st), "dsg_model_finalize")
         del keep  # stream-ordered: the caching allocator keeps the blocks alive until the copies ran
 
-    def forward(self, mode, batch, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node):
+    def skip_info(self):
+        stages, granule = C.c_int32(), C.c_int32()
+        native.check(self.lib.dsg_model_skip_info(self.handle, C.byref(stages), C.byref(granule)), "dsg_model_skip_info")
+        return stages.value, granule.value
+
+    def forward(self, mode, batch, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node,
+                skip=None):
         key = (batch, n_cond)
         if self.ws_key != key:
             need = self.lib.dsg_workspace_bytes(self.handle, batch, n_cond)
@@ -411,6 +494,8 @@ class _NativeModel:
         a.out_adj, a.out_node = out_adj.data_ptr(), out_node.data_ptr()
         a.workspace = self.workspace.data_ptr() + off
         a.workspace_bytes = self.workspace.numel() - off
+        if skip is not None:
+            a.skip_tables, a.skip_img_rows, a.skip_cap_rows = skip.tables.data_ptr(), skip.img_rows, skip.cap
         with native.device_guard(self.device):
             native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
                          "dsg_denoiser_forward")

@@ -82,6 +82,9 @@ class NodeAdjEDMSampler:
         self.use_graphs = os.environ.get("DSG_NO_GRAPH", "0") != "1"
         self.eager_every = 0
         self._plan = None
+        # Padded-row skipping (include/dsg_b200.h: dsg_model_skip_info): the un-shifted leading stages of
+        # the denoiser run only on the image rows that can hold valid nodes.  DSG_NO_SKIP=1 keeps the dense schedule.
+        self.skip_padding = os.environ.get("DSG_NO_SKIP", "0") != "1"
 
     # ------------------------------------------------------------------------------------------------------
     def step_scalars(self, t_cur: torch.Tensor, t_next: torch.Tensor) -> dict:
@@ -213,11 +216,16 @@ class NodeAdjEDMSampler:
             if self.use_graphs and fused and gt is None:
                 plan, pre = self._graph_plan(model, adjs.shape[0], adjs.shape[2], adjs.shape[1], nodes.shape[2])
             if plan is not None:
+                plan.set_flags(flags, self.skip_padding)
                 out = self._loop_graphs(plan, pre, adjs, nodes, flags, scalars, flag_interim_adjs,
                                         flag_adj_multi_channel, timesteps_snapshot, snaps_a, snaps_n, decode)
             else:
-                out = self._loop_eager(model, adjs, nodes, flags, scalars, gt, fused, flag_interim_adjs,
-                                       flag_adj_multi_channel, timesteps_snapshot, snaps_a, snaps_n, decode)
+                skip = None
+                if self.skip_padding and gt is None and hasattr(net, "make_skip_plan"):
+                    skip = net.make_skip_plan(flags, dev)
+                with (net.skipping(skip) if skip is not None else contextlib.nullcontext()):
+                    out = self._loop_eager(model, adjs, nodes, flags, scalars, gt, fused, flag_interim_adjs,
+                                           flag_adj_multi_channel, timesteps_snapshot, snaps_a, snaps_n, decode)
         self.last_raw_passes = getattr(self._unwrap(model), "raw_passes", 0) - passes0
         logging.info("Done with EDM-NodeAdj MCMC.")
         return out
@@ -275,7 +283,6 @@ class NodeAdjEDMSampler:
         dev = self.dev
         gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
         seed, off0 = gen.initial_seed(), gen.get_offset()
-        plan.flags.copy_(flags)
         plan.X[0].copy_(adjs)
         plan.X[1].copy_(nodes)
         if plan.self_condition:
@@ -314,7 +321,8 @@ class NodeAdjEDMSampler:
         scp = plan.SC if plan.self_condition else (None, None)
 
         def D(scin, out):
-            net.denoise_into(nat, plan.XH[0], plan.XH[1], plan.flags, plan.sigma, scin[0], scin[1], out[0], out[1])
+            net.denoise_into(nat, plan.XH[0], plan.XH[1], plan.flags, plan.sigma, scin[0], scin[1], out[0], out[1],
+                             plan.skip)
 
         if c1:
             D(scp, plan.T)

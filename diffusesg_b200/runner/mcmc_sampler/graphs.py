@@ -58,6 +58,10 @@ class HeunGraphPlan:
         self.bbox = torch.zeros(batch, n, 4, **f32)
         self.grid_a, self.inc_a = native.aten_normal_policy(self.X[0].numel(), device)
         self.grid_n, self.inc_n = native.aten_normal_policy(self.X[1].numel(), device)
+        # padded-row skipping: the table is a fixed buffer (its address is part of the captured launches), refilled
+        # per sampling run; the compact row count is baked into launch grids and TMA descriptors, so it keys the graphs
+        self.skip_tables = torch.zeros(2 * (batch + 1) * n + 2 * batch + 3, dtype=torch.int32, device=device)
+        self.skip = None
         self.graphs: Dict[Tuple, torch.cuda.CUDAGraph] = {}
         self.pool = None
         self.host_table = np.zeros(num_steps, dtype=np.dtype([
@@ -68,6 +72,13 @@ class HeunGraphPlan:
         self.net.denoise_into(nat, self.XH[0], self.XH[1], self.flags, self.sigma, None, None, self.T[0], self.T[1])
 
     # --------------------------------------------------------------------------------------------------
+    def set_flags(self, flags, skip_padding: bool):
+        from ...model.diffusesg.diffusesg import SkipPlan
+        self.flags.copy_(flags)
+        self.skip = SkipPlan.build(self.nat, flags, self.N, out=self.skip_tables) if skip_padding else None
+        if len(self.graphs) > 24:   # many distinct compact sizes seen: drop the captured graphs, keep the buffers
+            self.graphs.clear()
+
     def begin(self, scalars, seed: int, offset0: int) -> int:
         """Upload the per-step table for one sampling run; returns the generator offset after the run."""
         t = self.host_table
@@ -101,7 +112,7 @@ class HeunGraphPlan:
 
         def D(sc_pair, out):
             self.net.denoise_into(self.nat, self.XH[0], self.XH[1], self.flags, self.sigma, sc_pair[0], sc_pair[1],
-                                  out[0], out[1])
+                                  out[0], out[1], self.skip)
 
         if c1:
             D(sc, self.T)
@@ -131,7 +142,7 @@ class HeunGraphPlan:
                                                cn, st), "dsg_edm_post_step_dev")
 
     def replay(self, c1: bool, c2: bool, last: bool, decode=None):
-        key = (bool(c1), bool(c2) and not last, bool(last), decode)
+        key = (bool(c1), bool(c2) and not last, bool(last), decode, self.skip.img_rows if self.skip is not None else 0)
         g = self.graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

@@ -435,3 +435,72 @@ def test_sampler_accepts_any_flag_dtype():
         res.append(sampler.sample(model=model, node_flags=f.to(DEV), num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"]))
     for r in res[1:]:
         assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1])
+
+
+def _flags_with_counts(cfg, counts):
+    return torch.arange(cfg["img"])[None, :] < torch.tensor(counts)[:, None]
+
+
+@pytest.mark.parametrize("name,counts", [("vg", [2, 9, 16, 17, 33, 48, 62, 5]), ("tiny", [1, 4, 5, 8, 14, 3]),
+                                         ("coco", [2, 10, 11, 33, 21, 30])])
+def test_padded_row_skipping_matches_dense(name, counts):
+    """the compact-row schedule (leading un-shifted stages computed only on the image rows that can hold
+    valid nodes, the all-padding region represented by one phantom token) against the dense schedule on the same
+    inputs.  Equal in exact arithmetic; here both sides are bf16 tensor-core runs whose only difference is WHERE the
+    padding tokens were computed, so the gap must stay far below the parity tolerance (2e-2) - and masked outputs
+    must be exactly zero in both."""
+    cfg = CONFIGS[name]
+    net, sd = build(cfg)
+    b = len(counts)
+    adj, node, _, _, sc_adj, sc_node = synthetic_inputs(cfg, b, seed=11)
+    flags = _flags_with_counts(cfg, counts)
+    pair = (flags[:, None, :, None] & flags[:, None, None, :]).float()
+    adj, sc_adj = adj.abs().clamp_min(0.1) * adj.sign() * pair, sc_adj * pair   # re-mask for these flags
+    node, sc_node = node * flags[:, :, None], sc_node * flags[:, :, None]
+    stages, granule = net._native(DEV).skip_info()
+    assert stages >= 1, (name, stages, granule)
+    plan = net.make_skip_plan(flags.to(DEV))
+    assert plan is not None and plan.img_rows < (b + 1) * cfg["img"]
+    sig = torch.full((1,), 1.5, device=DEV).expand(b)       # one shared noise level, as in sampling
+    args = [t.to(DEV) for t in (adj, node, flags)]
+    with torch.no_grad():
+        da, dn = net.denoise(args[0], args[1], args[2], sig, sc_adj.to(DEV), sc_node.to(DEV))
+        with net.skipping(plan):
+            sa, sn = net.denoise(args[0], args[1], args[2], sig, sc_adj.to(DEV), sc_node.to(DEV))
+            sa2, sn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
+        da2, dn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
+        # reference: oracle D on the CPU
+        oa, on = O.precond_forward(oracle_net(cfg, sd), adj, node, flags, torch.full((b,), 1.5), sc_adj, sc_node, coin=lambda: 1.0)
+    stats = dict(name=name, kept=plan.kept_fraction, skip_vs_dense=(rel(sa, da), rel(sn, dn)), nosc=(rel(sa2, da2), rel(sn2, dn2)),
+                 skip_vs_oracle=(rel(sa, oa), rel(sn, on)), dense_vs_oracle=(rel(da, oa), rel(dn, on)))
+    print("SKIP_PARITY", stats)
+    assert max(stats["skip_vs_dense"] + stats["nosc"]) < 3e-3, stats
+    assert max(stats["skip_vs_oracle"]) < max(1.5 * max(stats["dense_vs_oracle"]), 1e-3), stats
+    invalid = ~(flags[:, None, :, None] & flags[:, None, None, :]).expand_as(adj)
+    assert float(sa.cpu()[invalid].abs().sum()) == 0.0 and float(sn.cpu()[~flags].abs().sum()) == 0.0
+    # a batch without padding keeps the dense schedule
+    full = _flags_with_counts(cfg, [cfg["img"]] * 3)
+    assert net.make_skip_plan(full.to(DEV)) is None
+
+
+@pytest.mark.parametrize("name", ["vg", "coco"])
+def test_precond_matches_golden_with_skipping(name, golden_dir):
+    """NodeAdjPrecond.forward of the unmodified reference (golden) against the native call with padded-row skipping
+    active: same tolerance as the dense path (test_precond_matches_golden)."""
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"precond_{name}.npz"))
+    net, _ = build(cfg)
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    adj, node, flags, _, _, _ = [t.to(DEV) for t in synthetic_inputs(cfg, 2, seed=7)]
+    plan = net.make_skip_plan(flags)
+    assert plan is not None
+    np.random.seed(5)
+    sa = sn = None
+    with torch.no_grad(), net.skipping(plan):
+        for k, s in enumerate((40.0, 3.0, 0.4, 0.01)):
+            sa, sn = model(adj * s, node * s, flags, torch.full((1,), s, device=DEV).expand(2), sa, sn)
+            c_out = s * 0.5 / (s * s + 0.25) ** 0.5
+            for got, key in ((sa, f"adj_{k}"), (sn, f"node_{k}")):
+                want = torch.from_numpy(g[key])
+                err = float((got.cpu() - want).abs().max())
+                assert err < F_TOL * c_out * 4 + 1e-5, (key, err)

@@ -58,8 +58,9 @@ def _build(cfg, stress):
     return NodeAdjPrecond(precond="edm", model=m.to(DEV).eval(), self_condition=True, symmetric_noise=False).eval()
 
 
-@pytest.mark.parametrize("case", ["vg", "vg_refinit", "coco"])
-def test_sampler256_matches_reference(case, golden_dir):
+@pytest.mark.parametrize("case,skip", [("vg", True), ("vg", False), ("vg_refinit", True), ("coco", True)])
+def test_sampler256_matches_reference(case, skip, golden_dir):
+    """skip: padded-row skipping (the sampler's default) on / off."""
     name, stress = CASES[case]
     cfg = CONFIGS[name]
     g = np.load(os.path.join(golden_dir, f"sampler256_{case}.npz"))
@@ -68,6 +69,7 @@ def test_sampler256_matches_reference(case, golden_dir):
     sampler = NodeAdjEDMSampler(num_steps=256, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
                                 clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
                                 symmetric_noise=False)
+    sampler.skip_padding = skip
     real_like = torch.randn_like
     torch.manual_seed(int(g["torch_seed"]))
     np.random.seed(int(g["numpy_seed"]))
@@ -94,7 +96,7 @@ def test_sampler256_matches_reference(case, golden_dir):
     far_n = (gn[..., :nb].abs() > MARGIN).all(-1) & flags
     bits_g = torch.cat([(a > 0)[pair[:, None].expand_as(a)], (n[..., :nb] > 0)[flags]])
     bits_r = torch.cat([(ga > 0)[pair[:, None].expand_as(ga)], (gn[..., :nb] > 0)[flags]])
-    stats = dict(case=case, bit_agree=float((bits_g == bits_r).float().mean()), rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
+    stats = dict(case=case, skip=skip, bit_agree=float((bits_g == bits_r).float().mean()), rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
                  edge_agree=float((qa == ra)[pair].float().mean()), node_agree=float((qn == rn)[flags].float().mean()),
                  edge_agree_far=float((qa == ra)[far_e].float().mean()), node_agree_far=float((qn == rn)[far_n].float().mean()),
                  far_frac=(float(far_e.sum() / pair.sum()), float(far_n.sum() / flags.sum())),
