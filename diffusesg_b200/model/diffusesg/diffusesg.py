@@ -252,12 +252,12 @@ class DiffuseSG(nn.Module):
         nat.forward(1, adjs.shape[0], 1, adjs, nodes, flags, sigma_ptr_tensor, 0, sc_adjs, sc_nodes, out_adjs, out_nodes,
                     skip)
 
-    def make_skip_plan(self, node_flags, device=None):
+    def make_skip_plan(self, node_flags, device=None, force=False):
         """Padded-row skipping plan for a batch with these node flags (include/dsg_b200.h: dsg_model_skip_info), or
         None when the geometry has no compactable stage or the batch has (almost) no padding to skip.  Reads the
         flags on the host (one small D2H copy): build it once per batch, not per call."""
         device = torch.device(device) if device is not None else node_flags.device
-        return SkipPlan.build(self._native(device), node_flags, self.img_size)
+        return SkipPlan.build(self._native(device), node_flags, self.img_size, min_saving=-1e9 if force else 0.03)
 
     def skipping(self, plan):
         """Context manager: calls with one shared noise level and the plan's batch size inside use `plan`."""

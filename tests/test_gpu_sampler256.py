@@ -94,8 +94,8 @@ def test_sampler256_matches_reference(case, skip, golden_dir):
     nb = cfg["c_n"] - 4
     far_e = (ga.abs() > MARGIN).all(1) & pair
     far_n = (gn[..., :nb].abs() > MARGIN).all(-1) & flags
-    bits_g = torch.cat([(a > 0)[pair[:, None].expand_as(a)], (n[..., :nb] > 0)[flags]])
-    bits_r = torch.cat([(ga > 0)[pair[:, None].expand_as(ga)], (gn[..., :nb] > 0)[flags]])
+    bits_g = torch.cat([(a > 0)[pair[:, None].expand_as(a)], (n[..., :nb] > 0)[flags].reshape(-1)])
+    bits_r = torch.cat([(ga > 0)[pair[:, None].expand_as(ga)], (gn[..., :nb] > 0)[flags].reshape(-1)])
     stats = dict(case=case, skip=skip, bit_agree=float((bits_g == bits_r).float().mean()), rel_adj=_rel(a, ga), rel_node=_rel(n, gn), traj=[(round(x, 5), round(y, 5)) for x, y in traj],
                  edge_agree=float((qa == ra)[pair].float().mean()), node_agree=float((qn == rn)[flags].float().mean()),
                  edge_agree_far=float((qa == ra)[far_e].float().mean()), node_agree_far=float((qn == rn)[far_n].float().mean()),
