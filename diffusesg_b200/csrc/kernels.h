@@ -249,6 +249,10 @@ int launch_train_noise(const float* y_adj, const float* y_node, const float* e_a
 int launch_loss_sums(const float* d_adj, const float* y_adj, const float* d_node, const float* y_node,
                      const float* weights, const uint8_t* flags, float* s_adj, float* s_node, int batch, int c_e, int n,
                      int c_n, cudaStream_t st);
+// gradient of the two sums w.r.t. the predictions, scaled by the upstream gradients g_adj / g_node [B]
+int launch_loss_sums_backward(const float* d_adj, const float* y_adj, const float* d_node, const float* y_node,
+                              const float* weights, const uint8_t* flags, const float* g_adj, const float* g_node,
+                              float* gd_adj, float* gd_node, int batch, int c_e, int n, int c_n, cudaStream_t st);
 
 
 // ---------------------------------------------------------------------------------------------

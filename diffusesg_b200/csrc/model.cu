@@ -1142,6 +1142,16 @@ int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, const floa
                           c_n, static_cast<cudaStream_t>(stream));
 }
 
+int dsg_edm_loss_sums_backward(const float* pred_adj, const float* target_adj, const float* pred_node,
+                               const float* target_node, const float* weights, const uint8_t* flags, const float* grad_sum_adj,
+                               const float* grad_sum_node, float* grad_pred_adj, float* grad_pred_node, int batch, int c_e,
+                               int n, int c_n, dsg_stream_t stream) {
+  DSG_REQUIRE(pred_adj && target_adj && pred_node && target_node && flags && grad_sum_adj && grad_sum_node && grad_pred_adj &&
+                  grad_pred_node, "edm_loss_sums_backward: null tensor");
+  return launch_loss_sums_backward(pred_adj, target_adj, pred_node, target_node, weights, flags, grad_sum_adj, grad_sum_node,
+                                   grad_pred_adj, grad_pred_node, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
+}
+
 int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
                   int epi, dsg_stream_t stream) {
   DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");

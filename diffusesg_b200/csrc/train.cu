@@ -108,6 +108,35 @@ loss_sums_kernel(const float* __restrict__ d_adj, const float* __restrict__ y_ad
   }
 }
 
+// Backward of loss_sums_kernel: d s_adj[b] / d D = 2 w_b (D - y) on valid pairs, 0 elsewhere (the mask and the target
+// carry no gradient), scaled by the upstream gradient of the per-sample sums.
+__global__ void __launch_bounds__(256)
+loss_sums_bwd_kernel(const float* __restrict__ d_adj, const float* __restrict__ y_adj, const float* __restrict__ d_node,
+                     const float* __restrict__ y_node, const float* __restrict__ weights, const uint8_t* __restrict__ flags,
+                     const float* __restrict__ g_adj, const float* __restrict__ g_node, float* __restrict__ gd_adj,
+                     float* __restrict__ gd_node, int batch, int c_e, int n, int c_n) {
+  const unsigned n4 = n >> 2, per_sample = c_e * n * n4;
+  const unsigned total = static_cast<unsigned>(batch) * per_sample;
+  const unsigned stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned v = tid; v < total; v += stride) {
+    const unsigned b = v / per_sample, r = v - b * per_sample;
+    const unsigned j4 = r % n4, i = (r / n4) % n;
+    const uint8_t* f = flags + static_cast<size_t>(b) * n;
+    const float k = 2.f * (weights ? weights[b] : 1.f) * g_adj[b];
+    const bool fi = f[i] != 0;
+    const uchar4 fj = *reinterpret_cast<const uchar4*>(f + 4 * j4);
+    const float4 d = reinterpret_cast<const float4*>(d_adj)[v], y = reinterpret_cast<const float4*>(y_adj)[v];
+    reinterpret_cast<float4*>(gd_adj)[v] = make_float4((fi && fj.x) ? k * (d.x - y.x) : 0.f, (fi && fj.y) ? k * (d.y - y.y) : 0.f,
+                                                       (fi && fj.z) ? k * (d.z - y.z) : 0.f, (fi && fj.w) ? k * (d.w - y.w) : 0.f);
+  }
+  const unsigned node_el = static_cast<unsigned>(batch) * n * c_n;
+  for (unsigned v = tid; v < node_el; v += stride) {
+    const unsigned bi = v / c_n, b = bi / n;
+    const float k = 2.f * (weights ? weights[b] : 1.f) * g_node[b];
+    gd_node[v] = flags[bi] != 0 ? k * (d_node[v] - y_node[v]) : 0.f;
+  }
+}
+
 int check_shape(const char* what, int batch, int c_e, int n, int c_n) {
   DSG_REQUIRE(batch > 0 && c_e > 0 && n > 0 && c_n > 0 && n % 4 == 0, "%s: bad shape B=%d C_e=%d N=%d C_n=%d", what,
               batch, c_e, n, c_n);
@@ -141,6 +170,23 @@ int launch_loss_sums(const float* d_adj, const float* y_adj, const float* d_node
                   (reinterpret_cast<uintptr_t>(flags) & 3) == 0,
               "loss_sums: adjacency tensors must be 16-byte aligned (flags 4-byte)");
   loss_sums_kernel<<<batch, 256, 0, st>>>(d_adj, y_adj, d_node, y_node, weights, flags, s_adj, s_node, c_e, n, c_n);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int launch_loss_sums_backward(const float* d_adj, const float* y_adj, const float* d_node, const float* y_node,
+                              const float* weights, const uint8_t* flags, const float* g_adj, const float* g_node,
+                              float* gd_adj, float* gd_node, int batch, int c_e, int n, int c_n, cudaStream_t st) {
+  if (int rc = check_shape("loss_sums_backward", batch, c_e, n, c_n)) return rc;
+  DSG_REQUIRE(((reinterpret_cast<uintptr_t>(d_adj) | reinterpret_cast<uintptr_t>(y_adj) | reinterpret_cast<uintptr_t>(gd_adj)) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(flags) & 3) == 0,
+              "loss_sums_backward: adjacency tensors must be 16-byte aligned (flags 4-byte)");
+  const long long vec = static_cast<long long>(batch) * c_e * n * (n / 4);
+  DSG_REQUIRE(vec < 2147483647LL, "loss_sums_backward: %lld vectors", vec);
+  long long blocks = (vec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  loss_sums_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(d_adj, y_adj, d_node, y_node, weights, flags, g_adj,
+                                                                     g_node, gd_adj, gd_node, batch, c_e, n, c_n);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

@@ -1,9 +1,11 @@
 """EDM regression loss for node + adjacency attributes (loss/rainbow_loss.py:5-99 of the reference).
 
-Forward only: the masked, weighted squared-error reduction over the [B, C_e, N, N] / [B, N, C_n] tensors is one
-native launch (dsg_edm_loss_sums); the [B]-sized normalisation keeps the reference's expressions, including its use
-of ``edge_loss_weight`` for the node term under reduction='mean' (:84-85).  The training step (backward through the
-native denoiser) is not built, so the result carries no autograd graph.
+The masked, weighted squared-error reduction over the [B, C_e, N, N] / [B, N, C_n] tensors is one native launch
+(dsg_edm_loss_sums) and, when the predictions require grad, an autograd node whose backward is one more
+(dsg_edm_loss_sums_backward): ``loss.backward()`` works against any model that produced the predictions with an
+autograd graph (the reference's PyTorch denoiser; the native denoiser has no backward pass yet).  The
+[B]-sized normalisation keeps the reference's expressions, including its use of ``edge_loss_weight`` for the node term
+under reduction='mean' (:84-85).
 """
 from __future__ import annotations
 
@@ -36,11 +38,11 @@ class NodeAdjRainbowLoss(nn.Module):
         if reweight_coef is not None or node_flags.dim() != 2 or pred_adj.dim() != 4 or pred_node.dim() != 3:
             raise NotImplementedError("only [B, C, N, N] / [B, N, F] tensors with [B, N] flags and no reweighting are built")
         if torch.is_grad_enabled() and (pred_adj.requires_grad or pred_node.requires_grad):
-            raise NotImplementedError("NodeAdjRainbowLoss (B200) is forward-only: the fused reduction carries no autograd "
-                                      "graph, so loss.backward() would silently train nothing.  Evaluate it under "
-                                      "torch.no_grad() (validation loss), or keep the reference loss for training until "
-                                      "the native backward pass lands (SURVEY 8f-2)")
-        s_adj, s_node = native.edm_loss_sums(pred_adj, target_adj, pred_node, target_node, loss_weight, node_flags)
+            # trainer path (runner/trainer/trainer_node_adj.py:112-173): loss.backward() reaches the predictions through
+            # the fused backward kernel; the [B]-sized normalisation below is ordinary torch arithmetic
+            s_adj, s_node = native.edm_loss_sums_autograd(pred_adj, target_adj, pred_node, target_node, loss_weight, node_flags)
+        else:
+            s_adj, s_node = native.edm_loss_sums(pred_adj, target_adj, pred_node, target_node, loss_weight, node_flags)
         num_node_entries = node_flags.sum(dim=-1)      # [B]   (:80-82)
         num_adj_entries = num_node_entries ** 2
         if reduction == "mean":

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "dsg_decode_samples": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_void_p]),
     "dsg_train_noise": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_loss_sums": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_edm_loss_sums_backward": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     "dsg_profile_begin": (C.c_int, [C.c_int]),
@@ -376,6 +377,40 @@ def edm_loss_sums(pred_adj, target_adj, pred_node, target_node, weights, flags):
                                   ptr(s_adj), ptr(s_node), b, ce, n, cn, stream_ptr(pred_adj.device)),
           "dsg_edm_loss_sums")
     return s_adj, s_node
+
+
+class _EdmLossSums(torch.autograd.Function):
+    """Autograd node around the fused loss reduction: forward dsg_edm_loss_sums, backward dsg_edm_loss_sums_backward."""
+
+    @staticmethod
+    def forward(ctx, pred_adj, target_adj, pred_node, target_node, weights, flags):
+        s_adj, s_node = edm_loss_sums(pred_adj.detach(), target_adj, pred_node.detach(), target_node, weights, flags)
+        ctx.save_for_backward(pred_adj.detach(), target_adj, pred_node.detach(), target_node,
+                              weights if weights is not None else torch.empty(0, device=pred_adj.device), flags)
+        ctx.has_w = weights is not None
+        return s_adj, s_node
+
+    @staticmethod
+    def backward(ctx, g_adj, g_node):
+        pred_adj, target_adj, pred_node, target_node, w, flags = ctx.saved_tensors
+        pa, ta = require_cuda(pred_adj, "pred_adj"), require_cuda(target_adj, "target_adj")
+        pn, tn = require_cuda(pred_node, "pred_node"), require_cuda(target_node, "target_node")
+        wv = require_cuda(w.reshape(-1), "loss_weight") if ctx.has_w else None
+        b, ce, n, _ = pa.shape
+        cn = pn.shape[-1]
+        f = _flags_u8(flags)
+        ga, gn = require_cuda(g_adj.contiguous(), "grad"), require_cuda(g_node.contiguous(), "grad")
+        gd_a, gd_n = torch.empty_like(pa), torch.empty_like(pn)
+        with device_guard(pa.device):
+            check(lib().dsg_edm_loss_sums_backward(ptr(pa), ptr(ta), ptr(pn), ptr(tn), ptr(wv), ptr(f), ptr(ga), ptr(gn),
+                                                   ptr(gd_a), ptr(gd_n), b, ce, n, cn, stream_ptr(pa.device)),
+                  "dsg_edm_loss_sums_backward")
+        return gd_a, None, gd_n, None, None, None
+
+
+def edm_loss_sums_autograd(pred_adj, target_adj, pred_node, target_node, weights, flags):
+    """edm_loss_sums with an autograd graph to the predictions (targets / weights / flags are constants)."""
+    return _EdmLossSums.apply(pred_adj, target_adj, pred_node, target_node, weights, flags)
 
 
 @_on_device_of_first_tensor

@@ -104,10 +104,36 @@ class NodeAdjEDMSampler:
                         flag_adj_multi_channel=False, num_node_chan=150, num_edge_chan=51):
         """Unit-variance start drawn on the CPU generator, adjacency first (edm.py:257-289), masked on device."""
         batch_size, max_node_num = node_flags.shape[:2]
-        init_adjs = torch.randn((batch_size, num_edge_chan, max_node_num, max_node_num)).to(self.dev, non_blocking=True)
-        init_nodes = torch.randn((batch_size, max_node_num, num_node_chan)).to(self.dev, non_blocking=True)
+        # torch.randn(size) IS torch.empty(size).normal_() on the default CPU generator (same stream, same values); the
+        # draws go straight into pinned staging buffers that are reused from call to call (no page faults, async H2D)
+        host_a = self._staging("init_a", (batch_size, num_edge_chan, max_node_num, max_node_num))
+        host_n = self._staging("init_n", (batch_size, max_node_num, num_node_chan))
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream(self.dev).synchronize()   # the previous call's upload has left the buffers
+        init_adjs = host_a.normal_().to(self.dev, non_blocking=True)
+        init_nodes = host_n.normal_().to(self.dev, non_blocking=True)
         flags = node_flags.to(self.dev).to(torch.bool).contiguous()   # any flag dtype, like mask_adjs' logical_not
         return native.edm_mask_scale(init_adjs, init_nodes, flags, 1.0)
+
+    def _staging(self, name, shape):
+        cache = self.__dict__.setdefault("_staging_bufs", {})
+        buf = cache.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, dtype=torch.float32, pin_memory=self.dev.type == "cuda")
+            cache[name] = buf
+        return buf
+
+    @staticmethod
+    def _to_host(*tensors):
+        """Device -> freshly allocated pinned host tensors (torch's caching host allocator recycles the blocks), one
+        synchronisation for all of them."""
+        outs = []
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            outs.append(h)
+        torch.cuda.current_stream(tensors[0].device).synchronize()
+        return outs
 
     @torch.no_grad()
     def sample(self, model, node_flags, init_adjs=None, init_nodes=None, sanity_check_gt_adjs=None,
@@ -118,7 +144,7 @@ class NodeAdjEDMSampler:
                                     sanity_check_gt_nodes, flag_interim_adjs, max_num_interim_adjs, flag_use_double,
                                     flag_adj_multi_channel, num_node_chan, num_edge_chan)
         adjs, nodes, snaps_a, snaps_n = out
-        adjs_cpu, nodes_cpu = adjs.cpu(), nodes.cpu()  # synchronises the stream: the pinned snapshots are complete too
+        adjs_cpu, nodes_cpu = self._to_host(adjs, nodes)  # synchronises the stream: the pinned snapshots are complete too
         if flag_interim_adjs:
             if flag_adj_multi_channel:
                 return adjs_cpu, nodes_cpu, [None], torch.stack(snaps_n)
@@ -140,10 +166,9 @@ class NodeAdjEDMSampler:
                                     num_edge_chan=num_edge_chan,
                                     decode=(int(num_adj_type), int(num_node_type), bool(return_state)))
         adjs, nodes, _, _, (q_adj, q_node, bbox) = out
-        res = (q_adj.cpu(), q_node.cpu(), bbox.cpu())
         if return_state:
-            return (adjs.cpu(), nodes.cpu()) + res
-        return res
+            return tuple(self._to_host(adjs, nodes, q_adj, q_node, bbox))
+        return tuple(self._to_host(q_adj, q_node, bbox))
 
     @staticmethod
     def _unwrap(model):

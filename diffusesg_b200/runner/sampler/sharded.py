@@ -61,8 +61,8 @@ def sample_sharded(sampler, model, node_flags_all: torch.Tensor, batch_size: int
         adjs.append(a)
         nodes.append(n)
     n_img = node_flags_all.shape[1]
-    adjs = torch.cat(adjs) if adjs else torch.zeros(0, num_edge_chan, n_img, n_img)
-    nodes = torch.cat(nodes) if nodes else torch.zeros(0, n_img, num_node_chan)
+    adjs = (adjs[0] if len(adjs) == 1 else torch.cat(adjs)) if adjs else torch.zeros(0, num_edge_chan, n_img, n_img)
+    nodes = (nodes[0] if len(nodes) == 1 else torch.cat(nodes)) if nodes else torch.zeros(0, n_img, num_node_chan)
     if not ddp:
         return adjs, nodes
     longest = -(-total // world)

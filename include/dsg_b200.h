@@ -236,6 +236,12 @@ DSG_API int dsg_train_noise(const float* clean_adj, const float* clean_node, con
 DSG_API int dsg_edm_loss_sums(const float* pred_adj, const float* target_adj, const float* pred_node,
                               const float* target_node, const float* weights, const uint8_t* flags, float* sum_adj,
                               float* sum_node, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
+/* Backward of dsg_edm_loss_sums for loss.backward() (runner/trainer/trainer_node_adj.py:173): grad_pred = grad_sum[b] *
+ * 2 w_b (pred - target) on valid entries, 0 on masked ones; the targets, weights and flags carry no gradient. */
+DSG_API int dsg_edm_loss_sums_backward(const float* pred_adj, const float* target_adj, const float* pred_node,
+                                       const float* target_node, const float* weights, const uint8_t* flags,
+                                       const float* grad_sum_adj, const float* grad_sum_node, float* grad_pred_adj,
+                                       float* grad_pred_node, int batch, int c_e, int n, int c_n, dsg_stream_t stream);
 
 
 /* ---- building blocks, exported for the kernel-level parity tests ------------------------------------------- */

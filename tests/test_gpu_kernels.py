@@ -327,3 +327,28 @@ def test_training_objective_matches_oracle_full_size(b, ce, n, cn):
     nn_ = flags.sum(-1)
     torch.testing.assert_close(sa.cpu() / nn_ ** 2 / ce, la, rtol=1e-5, atol=0)
     torch.testing.assert_close(sn.cpu() / nn_ / cn, ln, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("b,ce,n,cn,red", [(4, 6, 64, 12, "mean"), (3, 3, 40, 12, "none"), (5, 3, 16, 5, "mean")])
+def test_loss_backward_matches_torch_autograd(b, ce, n, cn, red):
+    """NodeAdjRainbowLoss with predictions that require grad: loss.backward() through the fused backward kernel
+    (dsg_edm_loss_sums_backward) against torch autograd of the oracle's restatement of loss/rainbow_loss.py:60-99."""
+    from diffusesg_b200.loss.rainbow_loss import NodeAdjRainbowLoss
+    from oracle import train_oracle as T
+    g = torch.Generator().manual_seed(b * n)
+    flags = torch.arange(n)[None, :] < torch.randint(2, n + 1, (b, 1), generator=g)
+    pa, ta = torch.randn(b, ce, n, n, generator=g), torch.randn(b, ce, n, n, generator=g)
+    pn, tn = torch.randn(b, n, cn, generator=g), torch.randn(b, n, cn, generator=g)
+    w = torch.rand(b, generator=g) + 0.5
+    loss = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=0.5, objective="edm")
+    ga = pa.clone().to(DEV).requires_grad_(True)
+    gn = pn.clone().to(DEV).requires_grad_(True)
+    la, ln = loss(ga, gn, ta.to(DEV), tn.to(DEV), None, None, None, None, None, flags.to(DEV), loss_weight=w.to(DEV), reduction=red)
+    (la.sum() + 2.0 * ln.sum()).backward()
+    ra, rn = pa.clone().requires_grad_(True), pn.clone().requires_grad_(True)
+    oa, on = T.regression_loss(ra, rn, ta, tn, flags, w, 1.0, 0.5, red)
+    (oa.sum() + 2.0 * on.sum()).backward()
+    torch.testing.assert_close(la.detach().cpu(), oa.detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(ga.grad.cpu(), ra.grad, rtol=2e-5, atol=1e-9)
+    torch.testing.assert_close(gn.grad.cpu(), rn.grad, rtol=2e-5, atol=1e-9)
+    assert float(ga.grad.cpu()[~(flags[:, None, :, None] & flags[:, None, None, :]).expand_as(pa)].abs().sum()) == 0.0
