@@ -32,6 +32,7 @@ import torch.nn as nn
 from ... import native
 
 _TORCH_RANDN_LIKE = torch.randn_like
+_TORCH_RANDN = torch.randn
 from .graphs import HeunGraphPlan
 from ..objectives.edm import get_edm_params, get_edm_sigma_deriv_t, get_edm_sigma_from_t, get_edm_t_from_sigma
 
@@ -106,6 +107,11 @@ class NodeAdjEDMSampler:
         batch_size, max_node_num = node_flags.shape[:2]
         # torch.randn(size) IS torch.empty(size).normal_() on the default CPU generator (same stream, same values); the
         # draws go straight into pinned staging buffers that are reused from call to call (no page faults, async H2D)
+        if torch.randn is not _TORCH_RANDN:   # a patched torch.randn (noise recording / replay hooks) is honoured
+            init_adjs = torch.randn((batch_size, num_edge_chan, max_node_num, max_node_num)).to(self.dev, non_blocking=True)
+            init_nodes = torch.randn((batch_size, max_node_num, num_node_chan)).to(self.dev, non_blocking=True)
+            flags = node_flags.to(self.dev).to(torch.bool).contiguous()
+            return native.edm_mask_scale(init_adjs, init_nodes, flags, 1.0)
         host_a = self._staging("init_a", (batch_size, num_edge_chan, max_node_num, max_node_num))
         host_n = self._staging("init_n", (batch_size, max_node_num, num_node_chan))
         if self.dev.type == "cuda":
