@@ -228,10 +228,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n_ = p.n_img, nn_ = n_ * n_;
         const int rowc = row < p.M ? row : p.M - 1;
         int b_ = rowc / nn_, ij_ = rowc - b_ * nn_;
-        if (p.row_b != nullptr) {
-          const int gr = rowc / n_;
-          b_ = p.row_b[gr];
-          ij_ = p.row_i[gr] * n_ + (rowc - gr * n_);
+        if (p.perm != nullptr) {
+          const int ss = p.side * p.side;
+          const int img = rowc / ss, rem = rowc - img * ss;
+          const int ii = rem / p.side;
+          b_ = p.perm[img];
+          ij_ = ii * n_ + (rem - ii * p.side);
         }
         const bool real_ = b_ >= 0;   // phantom rows of the compact layout produce no output
         if (!real_) b_ = 0;

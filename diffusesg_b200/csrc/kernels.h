@@ -42,8 +42,8 @@ struct GemmParams {
   const float* x_adj;    // preconditioning: D = c_skip * x + c_out * F; nullptr -> raw F
   const float* c_skip;   // [B]
   const float* c_out;    // [B]
-  const int* row_b;      // compact layout (padded-row skipping): GEMM row m is pixel (row_b[m / N], row_i[m / N], m % N);
-  const int* row_i;      //   row_b < 0 = phantom row, nothing is stored.  nullptr: dense rows
+  const int* perm;       // compact layout (padding skipping): the rows are a stack of side x side corners, image k =
+  int side;              //   sample perm[k] (< 0: phantom, nothing is stored).  nullptr: dense rows
 };
 
 // Encode a TMA descriptor for a row-major bf16 matrix [rows, cols] (cols contiguous), box = 64 cols x
@@ -187,26 +187,24 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
                        const float* rc, const float* w_adj, const float* bias, const float* gamma,
                        const float* beta, const float* film, int film_ld, int film_off, int cond_uniform,
                        float* x0, int batch, int n, int c_e, int self_cond, int embed, cudaStream_t st,
-                       const int* row_b = nullptr, const int* row_i = nullptr, long long img_rows = 0);
-// row_b / row_i / img_rows: compact layout of the padded-row skipping (model.cu): x0 has img_rows image rows; image row
-// r belongs to sample row_b[r] (-1 = the all-padding phantom) and is its row row_i[r]
+                       const int* perm = nullptr, int side = 0);
+// perm / side: compact layout of the padding skipping (model.cu): x0 is a stack of `batch` corners of side x side
+// pixels, image k showing the top-left corner of sample perm[k] (-1 = the all-padding phantom)
 // node head: masked row mean of y = LN(x) [B*n*n, E] bf16 -> folded read_out -> MLP -> (precond) -> out_node [B, n, c_n]
 // fold_t [E][E], w1t [E][E] and w2t [E][c_n] are transposed (input-channel major)
 int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip, const float* c_out,
-                     float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st, const int* off = nullptr);
-// off: compact layout - sample b's image rows of `rep` start at off[b]
+                     float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st, const int* tok0 = nullptr,
+                     const int* width = nullptr);
+// tok0 / width: compact layout - `rep` holds sample b as a width[b]^2 corner starting at token tok0[b]
 
-// padded-row skipping helpers: the merge / breakup kernels on an image of img_rows x res tokens (any number of
-// samples stacked; only widths with quarter-warp kernels), the breakup optionally writing the compact layout from a
-// dense input, and the compact -> dense expansion with the phantom's token as fill
+// padding-skipping helpers: the breakup writing the compact layout from a dense input, and the compact -> dense
+// expansion with the phantom's token as fill (quarter-warp widths only)
 bool row_compaction_supported(int C_merge, int D_breakup);
-int launch_merge_ln_rows(const float* x, bf16* y, const float* gamma, const float* beta, long long img_rows, int res, int C,
-                         cudaStream_t st);
-int launch_breakup_ln_rows(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
-                           long long img_rows_in, int res, int D, const int* off, const int* rb, int sh, cudaStream_t st);
-int launch_expand_fill(const float* compact, float* dense, const int* off, const int* rb, int sh, int batch, int res, int C,
-                       cudaStream_t st);
+int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
+                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st);
+int launch_expand_fill(const float* compact, float* dense, const int* tok0, const int* width, int sh, long long phantom_tok,
+                       int batch, int res, int C, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // fused EDM step kernels                                               (edm.cu)

@@ -383,7 +383,9 @@ void skip_geometry(dsg_model* m) {
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
       const Block& b = m->blocks[m->down_first[s] + j];
       const Block& u = m->blocks[m->up_first[m->nl - 1 - s] + j];
-      ok = ok && b.shift == 0 && u.shift == 0 && window_attention_rows_supported(b.res, b.window, b.heads);
+      // 8 x 8 windows: two windows per tile (the plan keeps every bucket's image count even); others: quad kernel
+      ok = ok && b.shift == 0 && u.shift == 0 && b.window < b.res &&
+           (b.window == 8 || window_attention_quad_supported(1, b.res, b.window, 0, b.heads));
     }
     ok = ok && row_compaction_supported(m->E << s, 4 * (m->E << s));
     if (!ok) break;
@@ -415,11 +417,26 @@ struct Workspace {
   size_t bytes;
 };
 
+// Compact layout of the padding skipping (see skip_geometry): the samples are grouped into K buckets by the side of
+// their kept corner; bucket k is a stack of count[k] images of side[k] x side[k] pixels (>> s tokens at stage s), the
+// buckets follow each other in memory.  Every geometry-aware kernel runs once per bucket on an ordinary
+// (batch, res) = (count[k], side[k] >> s) tensor; every row-wise kernel runs once over all tokens.
+struct Compact {
+  int K = 0;
+  int count[8], side[8], img0[8];   // images, corner side in pixels, index of the first image in `perm`
+  long long tok[9];                 // stage-0 token offset of each bucket; tok[K] = all tokens
+  const int *perm = nullptr, *tok0 = nullptr, *width = nullptr;   // device tables (include/dsg_b200.h)
+  long long phantom_tok0 = 0;       // stage-0 token offset of the all-padding phantom image
+  long long tokens(int s) const { return tok[K] >> (2 * s); }
+  long long at(int k, int s) const { return tok[k] >> (2 * s); }
+};
+
 Workspace carve(const dsg_model* m, int batch, int n_cond, void* base) {
   Workspace w;
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t cur = 0;
-  // one extra sample of capacity: the compact layout of the padded-row skipping appends the phantom's rows
+  // one extra sample of capacity: the compact layout of the padding skipping adds the phantom and up to one dummy
+  // image per bucket (a plan that would not fit is refused by the caller and the dense schedule runs)
   const size_t tok0 = static_cast<size_t>(batch + (m->skip_stages > 0 ? 1 : 0)) * m->N * m->N;
   const size_t full = tok0 * m->E;  // elements of a stage-0 activation; later stages hold full / 2^s
   auto take = [&](size_t bytes) { void* r = p ? p + cur : nullptr; cur = align_up(cur + bytes); return r; };
@@ -505,11 +522,11 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
 // fuse_final_ln: this is the last block of the network; if it runs the fused tail, the tail also applies the final
 // LayerNorm and writes only Y (*fused_final_ln = true), and the caller skips the separate LayerNorm launch.
 int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
-              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr, long long img_rows = 0) {
-  // img_rows > 0: compact layout - the activation is a stack of img_rows token rows (not whole res x res grids)
+              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr, const Compact* cp = nullptr) {
+  // cp: compact layout - the activation holds cp->tokens(stage) tokens, bucket by bucket (see Compact)
   const int C = b.dim;
   const int L = b.res * b.res;
-  const long long rows = img_rows > 0 ? img_rows * b.res : static_cast<long long>(batch) * L;
+  const long long rows = cp != nullptr ? cp->tokens(b.stage) : static_cast<long long>(batch) * L;
   const std::string& p = b.prefix;
   const double rc = static_cast<double>(rows) * C;
   auto tmap0 = [&](const void* ptr, int key, auto make) -> const CUtensorMap* {
@@ -536,13 +553,17 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
     DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
                                                  m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"),
-                                                 img_rows > 0 ? 1 : batch, img_rows > 0 ? static_cast<int>(rows) : L, C, st));
+                                                 cp != nullptr ? 1 : batch, cp != nullptr ? static_cast<int>(rows) : L, C, st));
     DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
   }
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
-  if (img_rows > 0) {
-    DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
-              launch_window_attention_rows(w.QKV, m->at<float>(b.attn_bias_off), w.ATT, img_rows, b.res, b.window, b.heads, st));
+  if (cp != nullptr) {
+    for (int k = 0; k < cp->K; ++k) {   // one (count, side) tensor per bucket
+      const long long t0 = cp->at(k, b.stage), tk = cp->at(k + 1, b.stage) - t0;
+      DSG_TRY_P(PC_ATTN, 4.0 * tk * C * b.window * b.window, static_cast<double>(tk) * C * 8,
+                launch_window_attention(w.QKV + t0 * 3 * C, m->at<float>(b.attn_bias_off), nullptr, w.ATT + t0 * C, cp->count[k],
+                                        cp->side[k] >> b.stage, b.window, 0, b.heads, st, b.mask_canonical));
+    }
   } else {
     DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
               launch_window_attention(w.QKV, m->at<float>(b.attn_bias_off), mask, w.ATT, batch, b.res, b.window, b.shift,
@@ -820,24 +841,40 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     labels = w.coef + 3 * B;
     label_stride = 1;
   }
-  // ---- padded-row skipping: compact layout of the leading un-shifted stages (see skip_geometry) ----------------
-  const int S = (a->skip_tables != nullptr && a->skip_img_rows > 0) ? m->skip_stages : 0;
-  const int G = m->skip_granule;
-  const int *row_b = nullptr, *row_i = nullptr, *sk_off = nullptr, *sk_rb = nullptr;
-  long long R0 = 0, R0_live = 0;  // image rows of the compact stage-0 grid with / without the phantom's G rows
-  if (a->skip_tables != nullptr && a->skip_img_rows > 0) {
+  // ---- padding skipping: compact layout of the leading un-shifted stages (see skip_geometry, Compact) ------------
+  Compact cpl;
+  const Compact* cp = nullptr;
+  int S = 0;
+  if (a->skip_tables != nullptr && a->skip_buckets > 0) {
+    const int G = m->skip_granule;
     DSG_REQUIRE(m->skip_stages > 0, "forward: this geometry has no compactable stage (skip_tables given)");
-    DSG_REQUIRE(uniform, "forward: padded-row skipping needs one shared noise level (n_cond == 1)");
+    DSG_REQUIRE(uniform, "forward: padding skipping needs one shared noise level (n_cond == 1)");
     DSG_REQUIRE(g_stop_after < 0, "forward: the stage-walk test hook runs on the dense schedule");
-    DSG_REQUIRE(a->skip_img_rows % G == 0 && a->skip_img_rows >= 2 * G && a->skip_cap_rows >= a->skip_img_rows &&
-                    a->skip_img_rows <= static_cast<long long>(B + 1) * N,
-                "forward: skip_img_rows %d (granule %d, capacity %d)", a->skip_img_rows, G, a->skip_cap_rows);
-    row_b = a->skip_tables;
-    row_i = row_b + a->skip_cap_rows;
-    sk_off = row_i + a->skip_cap_rows;   // [B + 2]: first image row of each sample, of the phantom, and the end
-    sk_rb = sk_off + (B + 2);            // [B + 1]: kept rows per sample (phantom: G)
-    R0 = a->skip_img_rows;
-    R0_live = R0 - G;
+    DSG_REQUIRE(a->skip_buckets <= 8 && a->skip_table_images > 0, "forward: %d buckets", a->skip_buckets);
+    cpl.K = a->skip_buckets;
+    long long tok = 0;
+    int img = 0;
+    for (int k = 0; k < cpl.K; ++k) {
+      cpl.count[k] = a->skip_count[k];
+      cpl.side[k] = a->skip_side[k];
+      DSG_REQUIRE(cpl.count[k] > 0 && cpl.count[k] % 2 == 0 && cpl.side[k] >= G && cpl.side[k] <= N && cpl.side[k] % G == 0,
+                  "forward: bucket %d holds %d images of side %d (granule %d)", k, cpl.count[k], cpl.side[k], G);
+      cpl.img0[k] = img;
+      cpl.tok[k] = tok;
+      img += cpl.count[k];
+      tok += static_cast<long long>(cpl.count[k]) * cpl.side[k] * cpl.side[k];
+    }
+    cpl.tok[cpl.K] = tok;
+    DSG_REQUIRE(img <= a->skip_table_images && tok <= static_cast<long long>(B + 1) * N * N,
+                "forward: the compact plan holds %d images / %lld pixels (table %d, capacity %lld)", img, tok,
+                a->skip_table_images, static_cast<long long>(B + 1) * N * N);
+    DSG_REQUIRE(a->skip_phantom_tok0 >= 0 && a->skip_phantom_tok0 + static_cast<long long>(G) * G <= tok, "forward: phantom offset");
+    cpl.perm = a->skip_tables;
+    cpl.tok0 = cpl.perm + a->skip_table_images;
+    cpl.width = cpl.tok0 + B;
+    cpl.phantom_tok0 = a->skip_phantom_tok0;
+    cp = &cpl;
+    S = m->skip_stages;
   }
   g_prof_pass = g_prof_on && !stream_capturing(st) && (g_prof_counter++ % g_prof_stride == 0);
   struct ProfPassGuard { ~ProfPassGuard() { g_prof_pass = false; } } prof_pass_guard;
@@ -849,11 +886,21 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   // patch embedding straight from (adj, node): the [B, cin, N, N] grid of :784-802 is never built
   DSG_TRY_P(PC_EMBED_HEAD, 0, 0, launch_node_proj(a->node, a->sc_node, c_in, m->at<float>(m->w_rc_off), w.rc, B, N, m->cfg.c_n,
                            m->cfg.self_condition, E, st));
-  const double px0 = S > 0 ? static_cast<double>(R0) * N : px;   // pixels actually embedded
-  DSG_TRY_P(PC_EMBED_HEAD, 0, px0 * (m->planes_adj * 4 + E * 4), launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
-                             m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
-                             m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
-                             m->cfg.self_condition, E, st, row_b, row_i, R0));
+  if (cp != nullptr) {
+    for (int k = 0; k < cp->K; ++k) {
+      const double pxk = static_cast<double>(cp->count[k]) * cp->side[k] * cp->side[k];
+      DSG_TRY_P(PC_EMBED_HEAD, 0, pxk * (m->planes_adj * 4 + E * 4),
+                launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
+                                   m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
+                                   m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X + cp->tok[k] * E,
+                                   cp->count[k], N, m->cfg.c_e, m->cfg.self_condition, E, st, cp->perm + cp->img0[k], cp->side[k]));
+    }
+  } else {
+    DSG_TRY_P(PC_EMBED_HEAD, 0, px * (m->planes_adj * 4 + E * 4), launch_patch_embed(a->adj, a->sc_adj, c_in, a->flags, w.rc, m->at<float>(m->w_adj_off),
+                               m->f32("patch_embed.proj.bias"), m->f32("patch_embed.norm.weight"),
+                               m->f32("patch_embed.norm.bias"), w.film, m->film_total, 0, uniform, w.X, B, N, m->cfg.c_e,
+                               m->cfg.self_condition, E, st));
+  }
   int stage_no = 0;
   bool final_ln_done = false;
 #define DSG_STAGE_DONE() do { if (g_stop_after >= 0 && stage_no++ == g_stop_after) return DSG_OK; } while (0)
@@ -862,25 +909,29 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   for (int s = 0; s < m->nl; ++s) {
     const float* x_in = s == 0 ? w.X : w.skip[s - 1];
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
-      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr, s < S ? (R0 >> s) : 0));
+      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr, s < S ? cp : nullptr));
       x_in = w.X;
       DSG_STAGE_DONE();
     }
     if (s < m->nl - 1) {
       const Merge& g = m->merges[s];
       if (s < S) {
-        // compact stage: merge the stacked rows; the last compact stage expands into the dense grid of stage s + 1,
-        // filling every skipped row with the phantom's token
-        const long long rows = ((R0 >> s) / 2) * (g.res / 2);
-        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows) * 4 * g.C * 6,
-                  launch_merge_ln_rows(w.X, w.Y, m->f32(g.prefix + ".norm.weight"), m->f32(g.prefix + ".norm.bias"), R0 >> s,
-                                       g.res, g.C, st));
+        // compact stage: merge bucket by bucket; the last compact stage expands into the dense grid of stage s + 1,
+        // filling everything outside the kept corners with the phantom's token
+        const long long rows = cp->tokens(s + 1);
+        for (int k = 0; k < cp->K; ++k) {
+          const double rk = static_cast<double>(cp->at(k + 1, s + 1) - cp->at(k, s + 1));
+          DSG_TRY_P(PC_ROW, 0, rk * 4 * g.C * 6,
+                    launch_merge_ln(w.X + cp->at(k, s) * g.C, w.Y + cp->at(k, s + 1) * 4 * g.C, m->f32(g.prefix + ".norm.weight"),
+                                    m->f32(g.prefix + ".norm.bias"), cp->count[k], cp->side[k] >> s, g.C, st));
+        }
         if (s + 1 < S) {
           DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
         } else {
           DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.T, st));
           const double dense_el = static_cast<double>(B) * (g.res / 2) * (g.res / 2) * 2 * g.C;
-          DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_expand_fill(w.T, w.skip[s], sk_off, sk_rb, s + 1, B, g.res / 2, 2 * g.C, st));
+          DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_expand_fill(w.T, w.skip[s], cp->tok0, cp->width, s + 1,
+                                                                cp->phantom_tok0 >> (2 * (s + 1)), B, g.res / 2, 2 * g.C, st));
         }
       } else {
         const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
@@ -900,26 +951,28 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
       const Breakup& bu = m->breakups[u - 1];
       // the low-resolution stream lives in X unless no block ran since the last merge (cannot happen: depth >= 1)
       if (s + 1 < S) {
-        // compact -> compact (the phantom's rows are dead in the decoder: R0_live)
-        const long long img_low = R0_live >> (s + 1);
-        const long long rows_low = img_low * bu.res;
+        // compact -> compact, bucket by bucket
+        const long long rows_low = cp->tokens(s + 1);
         DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
         DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
-        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6,
-                  launch_breakup_ln_rows(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
-                                         m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
-                                         img_low, bu.res, bu.D, nullptr, nullptr, 0, st));
+        for (int k = 0; k < cp->K; ++k) {
+          const double rk = static_cast<double>(cp->at(k + 1, s + 1) - cp->at(k, s + 1));
+          DSG_TRY_P(PC_ROW, 0, rk * bu.D * 6,
+                    launch_breakup_ln(w.T + cp->at(k, s + 1) * bu.D, w.Y + cp->at(k, s) * (bu.D / 4), m->f32(bu.prefix + ".norm.weight"),
+                                      m->f32(bu.prefix + ".norm.bias"), m->f32(bu.prefix + ".post_norm.weight"),
+                                      m->f32(bu.prefix + ".post_norm.bias"), cp->count[k], cp->side[k] >> (s + 1), bu.D, st));
+        }
         DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
       } else if (s < S) {
-        // dense -> compact: only the children inside each sample's kept rows are produced
+        // dense -> compact: only the children inside each sample's kept corner are produced
         const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
-        const long long rows_hi = (R0_live >> s) * (2 * bu.res);
+        const long long rows_hi = cp->tokens(s);
         DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
         DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
         DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 4 + static_cast<double>(rows_hi) * bu.D / 2,
-                  launch_breakup_ln_rows(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
-                                         m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
-                                         static_cast<long long>(B) * bu.res, bu.res, bu.D, sk_off, sk_rb, s, st));
+                  launch_breakup_ln_compact(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                            m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
+                                            B, bu.res, bu.D, cp->tok0, cp->width, s, st));
         DSG_TRY(gemm(m, w.Y, rows_hi, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
       } else {
         const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
@@ -936,16 +989,16 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
       // the last block: the final LayerNorm rides on its fused tail (not while a test walks the stages: those read X)
       const bool last = u == m->nl - 1 && j == m->cfg.depths[s] - 1 && m->use_final_ln && g_stop_after < 0;
       DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done,
-                        s < S ? (R0_live >> s) : 0));
+                        s < S ? cp : nullptr));
       DSG_STAGE_DONE();
     }
   }
   // read-out                                                                 (:758-761, :806-825)
-  const long long pixels = S > 0 ? R0_live * N : static_cast<long long>(B) * N * N;
-  if (S > 0)  // rows that are not computed are padding: their outputs are the masked zeros
+  const long long pixels = S > 0 ? cp->tokens(0) : static_cast<long long>(B) * N * N;
+  if (S > 0)  // pixels that are not computed are padding: their outputs are the masked zeros
     DSG_CUDA_CHECK(cudaMemsetAsync(a->out_adj, 0, static_cast<size_t>(B) * m->cfg.c_e * N * N * 4, st));
   if (!final_ln_done)
-    DSG_TRY_P(PC_ROW, 0, px * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
+    DSG_TRY_P(PC_ROW, 0, static_cast<double>(pixels) * E * 6, launch_ln(w.X, w.Y, m->f32("norm.weight"), m->f32("norm.bias"), pixels, E, st));
   GemmParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.w2t = m->at<float>(m->adj_w2t_off);
@@ -956,17 +1009,24 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   hp.x_adj = a->mode == 1 ? a->adj : nullptr;
   hp.c_skip = c_skip;
   hp.c_out = c_out;
-  hp.row_b = row_b;
-  hp.row_i = row_i;
-  DSG_TRY(gemm(m, w.Y, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->at<float>(m->adj_b1_off), nullptr, a->out_adj, st, &hp));
-  DSG_TRY_P(PC_EMBED_HEAD, 0, px * E * 2, launch_node_head(w.Y, a->flags, m->at<float>(m->fold_ft_off), m->at<float>(m->fold_b_off),
+  if (S > 0) {
+    for (int k = 0; k < cp->K; ++k) {   // the epilogue maps a GEMM row to its pixel through the bucket's geometry
+      hp.perm = cp->perm + cp->img0[k];
+      hp.side = cp->side[k];
+      DSG_TRY(gemm(m, w.Y + cp->tok[k] * E, cp->tok[k + 1] - cp->tok[k], m->adj_fc1, EPI_ADJ_HEAD, m->at<float>(m->adj_b1_off),
+                   nullptr, a->out_adj, st, &hp));
+    }
+  } else {
+    DSG_TRY(gemm(m, w.Y, pixels, m->adj_fc1, EPI_ADJ_HEAD, m->at<float>(m->adj_b1_off), nullptr, a->out_adj, st, &hp));
+  }
+  DSG_TRY_P(PC_EMBED_HEAD, 0, static_cast<double>(pixels) * E * 2, launch_node_head(w.Y, a->flags, m->at<float>(m->fold_ft_off), m->at<float>(m->fold_b_off),
                            m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
                            m->at<float>(m->node_w2t_off), m->f32("readout_node_mlp.fc2.bias"),
-                           a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st, sk_off));
+                           a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st,
+                           S > 0 ? cp->tok0 : nullptr, S > 0 ? cp->width : nullptr));
   return DSG_OK;
 }
 
-void dsg_launch_count_add(uint64_t n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
 void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
 void dsg_debug_trace_next_mlp(long long* device_buffer) { g_mlp_trace = device_buffer; }
 

@@ -280,7 +280,7 @@ template <int NV>  // NV = Dq / 32 float4 per lane, Dq = D / 4
 __global__ void __launch_bounds__(kRowThreads)
 breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const float* __restrict__ g1,
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
-                    long long rows_in, int res, const int* __restrict__ off, const int* __restrict__ rb, int sh) {
+                    long long rows_in, int res, const int* __restrict__ tok0, const int* __restrict__ width, int sh) {
   constexpr int Dq = NV * 32, D = 4 * Dq;
   const int lane = threadIdx.x & 31, k = lane >> 3, sub = lane & 7;
   const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
@@ -288,12 +288,16 @@ breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const flo
   const int ix = static_cast<int>(row % res);
   const int iy = static_cast<int>((row / res) % res);
   const long long b = row / (static_cast<long long>(res) * res);
-  // compacting variant (padded-row skipping, model.cu): the input is the dense [B, res, res] grid, the output the
-  // compact image whose sample b starts at image row off[b] >> sh and keeps rb[b] >> sh rows
-  long long out_row0 = (b * res + iy) * 2;   // image row of the (dy = 0) children: sample-independent when dense
-  if (off != nullptr) {
-    if (2 * iy >= (rb[b] >> sh)) return;     // children beyond the kept prefix: dead, never read
-    out_row0 = (off[b] >> sh) + 2 * iy;
+  // compacting variant (padding skipping, model.cu): the input is the dense [B, res, res] grid, the output the compact
+  // layout in which sample b is a (width[b] >> sh)^2 image starting at token tok0[b] >> 2 sh
+  const int res2 = 2 * res;
+  long long out_tok0 = ((b * res2 + 2 * iy) * res2) + 2 * ix;   // token of the (dy, dx) = (0, 0) child, dense
+  int out_pitch = res2;
+  if (tok0 != nullptr) {
+    const int wc = width[b] >> sh;
+    if (2 * iy >= wc || 2 * ix >= wc) return;   // children outside the kept corner: dead, never read
+    out_pitch = wc;
+    out_tok0 = (static_cast<long long>(tok0[b]) >> (2 * sh)) + static_cast<long long>(2 * iy) * wc + 2 * ix;
   }
   const float* src = t + row * D + k * Dq;  // lanes [8k, 8k + 8) own chunk k = elements [k Dq, (k + 1) Dq)
   float4 v[NV];
@@ -331,8 +335,7 @@ breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const flo
   }
   const float rstd2 = rsqrtf(group_sum<8>(q2) * (1.0f / Dq) + kLnEps);
   // chunk k lands on pixel (2y + k % 2, 2x + k / 2) of the up-sampled grid        (:394-397)
-  const int res2 = 2 * res;
-  bf16* dst = y + ((out_row0 + (k & 1)) * res2 + (2 * ix + (k >> 1))) * Dq;
+  bf16* dst = y + (out_tok0 + static_cast<long long>(k & 1) * out_pitch + (k >> 1)) * Dq;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (sub + 8 * i) * 4;
@@ -468,8 +471,7 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
                    const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ film, int film_ld, int cond_uniform, float* __restrict__ x0,
-                   long long pixels, int n, int c_e, int self_cond, const int* __restrict__ row_b,
-                   const int* __restrict__ row_i) {
+                   long long pixels, int n, int c_e, int self_cond, const int* __restrict__ perm, int side) {
   constexpr int E = kPE, NT = E / 8;
   __shared__ uint4 sBf[NT][32];                 // B fragments of n-tile nt for lane: {hi k0-7, hi k8-15, lo k0-7, lo k8-15}
   __shared__ __align__(16) float sBias[E], sGam[E], sBet[E];
@@ -504,10 +506,12 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
       const long long pc = px < pixels ? px : pixels - 1;
       int b_ = static_cast<int>(pc / nn);
       int ij_ = static_cast<int>(pc - static_cast<long long>(b_) * nn);
-      if (row_b != nullptr) {  // compact layout: image row pc / n belongs to sample row_b (-1: the all-padding phantom)
-        const int gr = static_cast<int>(pc / n);
-        b_ = row_b[gr];
-        ij_ = row_i[gr] * n + static_cast<int>(pc - static_cast<long long>(gr) * n);
+      if (perm != nullptr) {  // compact layout: a stack of side x side corners; image k is sample perm[k] (-1: all padding)
+        const int img = static_cast<int>(pc / (side * side));
+        const int rem = static_cast<int>(pc - static_cast<long long>(img) * side * side);
+        const int i_ = rem / side;
+        b_ = perm[img];
+        ij_ = i_ * n + (rem - i_ * side);
       }
       scl[r] = (in_scale && b_ >= 0) ? in_scale[b_] : 1.f;
       if (b_ < 0) {
@@ -553,10 +557,12 @@ patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_a
       const long long pc = valid[r] ? pix[r] : pixels - 1;
       bb[r] = static_cast<int>(pc / nn);
       ij[r] = static_cast<int>(pc - static_cast<long long>(bb[r]) * nn);
-      if (row_b != nullptr) {
-        const int gr = static_cast<int>(pc / n);
-        bb[r] = row_b[gr];
-        ij[r] = row_i[gr] * n + static_cast<int>(pc - static_cast<long long>(gr) * n);
+      if (perm != nullptr) {
+        const int img = static_cast<int>(pc / (side * side));
+        const int rem = static_cast<int>(pc - static_cast<long long>(img) * side * side);
+        const int ii = rem / side;
+        bb[r] = perm[img];
+        ij[r] = ii * n + (rem - ii * side);
       }
       const int i_ = ij[r] / n, j_ = ij[r] - i_ * n;
       const int bs = bb[r] < 0 ? 0 : bb[r];
@@ -664,7 +670,8 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
                  const float* __restrict__ fold_b, const float* __restrict__ w1t,
                  const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                  const float* __restrict__ x_node, const float* __restrict__ c_skip, const float* __restrict__ c_out,
-                 float* __restrict__ out_node, long long rows, int n, int c_n, int embed, const int* __restrict__ off) {
+                 float* __restrict__ out_node, long long rows, int n, int c_n, int embed, const int* __restrict__ tok0,
+                 const int* __restrict__ width) {
   __shared__ float va[kHeadRows][128];  // masked row means, then the hidden layer
   __shared__ float vb[kHeadRows][128];  // pooled read-out
   __shared__ float frac[kHeadRows];     // valid columns / n
@@ -679,14 +686,15 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
     if (live) {
       const int b = static_cast<int>(bi / n);
       const uint8_t* fj = flags + static_cast<size_t>(b) * n;
-      // compact layout: sample b's image rows start at off[b] (a valid node's row always lies in the kept prefix)
-      const size_t img_row = off != nullptr ? static_cast<size_t>(off[b]) + static_cast<size_t>(bi - static_cast<long long>(b) * n)
-                                            : static_cast<size_t>(bi);
-      const bf16* p = rep + img_row * n * embed + 4 * lane;
+      // compact layout: sample b is a width[b]^2 corner starting at token tok0[b]; valid nodes always lie inside it
+      const int nj = tok0 != nullptr ? width[b] : n;
+      const size_t row_tok = tok0 != nullptr ? static_cast<size_t>(tok0[b]) + static_cast<size_t>(bi - static_cast<long long>(b) * n) * nj
+                                             : static_cast<size_t>(bi) * n;
+      const bf16* p = rep + row_tok * embed + 4 * lane;
       const bool mine = 4 * lane < embed;
       // unconditional, unrolled loads (masked columns are multiplied by zero): eight 8-byte loads in flight per lane
 #pragma unroll 8
-      for (int j = 0; j < n; ++j) {
+      for (int j = 0; j < nj; ++j) {
         const float m = fj[j] != 0 ? 1.f : 0.f;
         cnt += fj[j] != 0;
         if (mine) {
@@ -753,24 +761,26 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
   }
 }
 
-// compact -> dense at the first stage that is computed densely (padded-row skipping, model.cu): sample b's kept rows
-// are copied, the rows below them are filled with the phantom sample's token - the value every token of an
-// all-padding region takes at this stage.
+// compact -> dense at the first stage that is computed densely (padding skipping, model.cu): sample b's kept corner
+// ((width[b] >> sh)^2 tokens starting at tok0[b] >> 2 sh) is copied, every other token of its grid is filled with the
+// phantom's token - the value every token of an all-padding region takes at this stage.
 __global__ void __launch_bounds__(256)
-expand_fill_kernel(const float* __restrict__ compact, float* __restrict__ dense, const int* __restrict__ off,
-                   const int* __restrict__ rb, int sh, int batch, int res, int C4) {
-  const long long row_vecs = static_cast<long long>(res) * C4;             // float4 per image row
-  const long long total = static_cast<long long>(batch) * res * row_vecs;
+expand_fill_kernel(const float* __restrict__ compact, float* __restrict__ dense, const int* __restrict__ tok0,
+                   const int* __restrict__ width, int sh, long long phantom_tok, int batch, int res, int C4) {
+  const long long total = static_cast<long long>(batch) * res * res * C4;
   const float4* src = reinterpret_cast<const float4*>(compact);
   float4* dst = reinterpret_cast<float4*>(dense);
-  const long long phantom = static_cast<long long>(off[batch] >> sh) * row_vecs;   // first token of the phantom
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long gr = v / row_vecs;
-    const long long within = v - gr * row_vecs;
-    const int b = static_cast<int>(gr / res), r = static_cast<int>(gr - static_cast<long long>(b) * res);
-    const bool kept = r < (rb[b] >> sh);
-    dst[v] = kept ? src[(static_cast<long long>(off[b] >> sh) + r) * row_vecs + within] : src[phantom + within % C4];
+    const long long tok = v / C4;
+    const int c4 = static_cast<int>(v - tok * C4);
+    const int b = static_cast<int>(tok / (res * res));
+    const int rem = static_cast<int>(tok - static_cast<long long>(b) * res * res);
+    const int r = rem / res, x = rem - r * res;
+    const int wc = width[b] >> sh;
+    const long long st = (r < wc && x < wc) ? (static_cast<long long>(tok0[b]) >> (2 * sh)) + static_cast<long long>(r) * wc + x
+                                            : phantom_tok;
+    dst[v] = src[st * C4 + c4];
   }
 }
 
@@ -850,42 +860,31 @@ int launch_merge_ln(const float* x, bf16* y, const float* gamma, const float* be
   return DSG_OK;
 }
 
-int launch_merge_ln_rows(const float* x, bf16* y, const float* gamma, const float* beta, long long img_rows, int res, int C,
-                         cudaStream_t st) {
-  DSG_REQUIRE(res % 2 == 0 && img_rows % 2 == 0 && (C == 96 || C == 192 || C == 384), "merge (rows): res %d, %lld rows, C %d",
-              res, img_rows, C);
-  const long long rows = (img_rows / 2) * (res / 2);
-  const unsigned grid = row_grid(rows);
-  if (C == 96) merge_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
-  else if (C == 192) merge_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
-  else merge_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(x, y, gamma, beta, rows, res);
-  DSG_LAUNCH_CHECK();
-  return DSG_OK;
-}
-
 bool row_compaction_supported(int C_merge, int D_breakup) {
   return (C_merge == 96 || C_merge == 192 || C_merge == 384) && (D_breakup == 384 || D_breakup == 768 || D_breakup == 1536);
 }
 
-int launch_breakup_ln_rows(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
-                           long long img_rows_in, int res, int D, const int* off, const int* rb, int sh, cudaStream_t st) {
-  DSG_REQUIRE(D == 384 || D == 768 || D == 1536, "breakup (rows): width %d", D);
-  const long long rows = img_rows_in * res;
+// dense [B, res, res, D] -> compact children (see breakup_ln_q_kernel); quarter-warp widths only
+int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
+                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st) {
+  DSG_REQUIRE((D == 384 || D == 768 || D == 1536) && tok0 && width, "breakup (compact): width %d", D);
+  const long long rows = static_cast<long long>(batch) * res * res;
   const unsigned grid = row_grid(rows);
-  if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, off, rb, sh);
-  else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, off, rb, sh);
-  else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, off, rb, sh);
+  if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
+  else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
+  else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
 
-int launch_expand_fill(const float* compact, float* dense, const int* off, const int* rb, int sh, int batch, int res, int C,
-                       cudaStream_t st) {
-  DSG_REQUIRE(C % 4 == 0 && off && rb, "expand_fill: width %d", C);
+int launch_expand_fill(const float* compact, float* dense, const int* tok0, const int* width, int sh, long long phantom_tok,
+                       int batch, int res, int C, cudaStream_t st) {
+  DSG_REQUIRE(C % 4 == 0 && tok0 && width, "expand_fill: width %d", C);
   const long long total = static_cast<long long>(batch) * res * res * (C / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  expand_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(compact, dense, off, rb, sh, batch, res, C / 4);
+  expand_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(compact, dense, tok0, width, sh, phantom_tok, batch, res,
+                                                                    C / 4);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -954,17 +953,17 @@ int launch_node_proj(const float* node, const float* sc_node, const float* in_sc
 int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_scale, const uint8_t* flags,
                        const float* rc, const float* w_adj, const float* bias, const float* gamma, const float* beta,
                        const float* film, int film_ld, int film_off, int cond_uniform, float* x0, int batch, int n,
-                       int c_e, int self_cond, int embed, cudaStream_t st, const int* row_b, const int* row_i,
-                       long long img_rows) {
+                       int c_e, int self_cond, int embed, cudaStream_t st, const int* perm, int side) {
   DSG_REQUIRE(embed == 96, "patch_embed: embed_dim %d (only 96 is built)", embed);
-  const long long pixels = row_b != nullptr ? img_rows * n : static_cast<long long>(batch) * n * n;
+  // perm: `batch` counts the images of a compact stack of side x side corners (see patch_embed_kernel)
+  const long long pixels = perm != nullptr ? static_cast<long long>(batch) * side * side : static_cast<long long>(batch) * n * n;
   DSG_REQUIRE((self_cond ? 2 : 1) * c_e <= 16, "patch_embed: %d adjacency planes (max 16)", (self_cond ? 2 : 1) * c_e);
   long long blocks = (pixels / 16 + 7) / 8;  // one warp per 16 pixels per step
   if (blocks > 148 * 16) blocks = 148 * 16;
   patch_embed_kernel<<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj,
                                                                            bias, gamma, beta, film + film_off, film_ld,
                                                                            cond_uniform, x0, pixels, n, c_e, self_cond,
-                                                                           row_b, row_i);
+                                                                           perm, side);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -972,11 +971,11 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
 int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip,
                      const float* c_out, float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st,
-                     const int* off) {
+                     const int* tok0, const int* width) {
   DSG_REQUIRE(embed <= 128 && embed % 4 == 0 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
   const long long rows = static_cast<long long>(batch) * n;
   node_head_kernel<<<static_cast<unsigned>((rows + kHeadRows - 1) / kHeadRows), 256, 0, st>>>(
-      rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, rows, n, c_n, embed, off);
+      rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, rows, n, c_n, embed, tok0, width);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

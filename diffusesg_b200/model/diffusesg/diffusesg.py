@@ -307,34 +307,51 @@ class DiffuseSG(nn.Module):
 
 
 class SkipPlan:
-    """Device tables of the compact row layout (row_b | row_i | off | rb, int32) for one batch of node flags."""
+    """Compact layout of the padding skipping for one batch of node flags (include/dsg_b200.h: dsg_model_skip_info):
+    device table ``perm | tok0 | width`` (int32) plus the bucket geometry that goes into ``dsg_forward_args``."""
 
-    def __init__(self, nat, batch, tables, img_rows, cap, kept_fraction):
-        self.nat, self.batch, self.tables, self.img_rows, self.cap = nat, batch, tables, img_rows, cap
-        self.kept_fraction = kept_fraction
+    TABLE_EXTRA = 17   # phantom + one dummy image per bucket (<= 8 buckets)
+
+    def __init__(self, nat, batch, tables, n_images_cap, counts, sides, phantom_tok0, kept_fraction):
+        self.nat, self.batch, self.tables, self.n_images_cap = nat, batch, tables, n_images_cap
+        self.counts, self.sides, self.phantom_tok0, self.kept_fraction = counts, sides, phantom_tok0, kept_fraction
+        self.key = (tuple(counts), tuple(sides), phantom_tok0)   # what the launch sequence of a pass depends on
 
     @staticmethod
-    def host_tables(flags_host: torch.Tensor, n: int, granule: int, cap: int):
-        """(int32 numpy table of length 2 * cap + 2 * B + 3, image rows incl. the phantom's)."""
+    def table_len(batch: int) -> int:
+        return (batch + SkipPlan.TABLE_EXTRA) + 2 * batch
+
+    @staticmethod
+    def host_tables(flags_host: torch.Tensor, n: int, granule: int):
+        """-> (int32 table, counts, sides, phantom_tok0, compact pixels) or None when more than 8 buckets would be needed."""
         import numpy as np
         f = flags_host.to(torch.bool).cpu().numpy()
         b = f.shape[0]
         last = np.where(f.any(1), n - np.argmax(f[:, ::-1], axis=1), 0)          # index of the last valid node + 1
         rb = np.minimum(n, np.maximum(granule, -(-last // granule) * granule)).astype(np.int64)
-        off = np.zeros(b + 2, dtype=np.int64)
-        off[1:b + 1] = np.cumsum(rb)
-        off[b + 1] = off[b] + granule
-        total = int(off[b + 1])
-        table = np.zeros(2 * cap + 2 * b + 3, dtype=np.int32)
-        row_b = np.repeat(np.arange(b + 1), np.append(rb, granule))
-        row_b[row_b == b] = -1
-        row_i = np.arange(total) - np.repeat(off[:b + 1], np.append(rb, granule))
-        table[:total] = row_b
-        table[cap:cap + total] = row_i
-        table[2 * cap:2 * cap + b + 2] = off
-        table[2 * cap + b + 2:2 * cap + 2 * b + 2] = rb
-        table[2 * cap + 2 * b + 2] = granule
-        return table, total
+        sides = sorted(set(rb.tolist()) | {granule})      # the phantom lives in the bucket of side `granule`
+        if len(sides) > 8:
+            return None
+        cap = b + SkipPlan.TABLE_EXTRA
+        table = np.zeros(SkipPlan.table_len(b), dtype=np.int32)
+        perm, counts, tok, phantom_tok0 = [], [], 0, 0
+        tok0 = np.zeros(b, dtype=np.int64)
+        for side in sides:
+            members = np.nonzero(rb == side)[0]
+            tok0[members] = tok + np.arange(len(members)) * side * side
+            images = members.tolist()
+            if side == granule:
+                phantom_tok0 = tok + len(images) * side * side
+                images.append(-1)
+            if len(images) % 2:
+                images.append(-1)                          # all-padding dummy: the 8 x 8 kernel pairs windows
+            perm += images
+            counts.append(len(images))
+            tok += len(images) * side * side
+        table[:len(perm)] = perm
+        table[cap:cap + b] = tok0
+        table[cap + b:cap + 2 * b] = rb
+        return table, counts, sides, int(phantom_tok0), int(tok)
 
     @staticmethod
     def build(nat, node_flags, n, out=None, min_saving=0.03):
@@ -342,16 +359,20 @@ class SkipPlan:
         if stages == 0 or node_flags.dim() != 2 or node_flags.shape[1] != n:
             return None
         b = node_flags.shape[0]
-        cap = (b + 1) * n
-        table, total = SkipPlan.host_tables(node_flags, n, granule, cap)
-        if total > (1.0 - min_saving) * b * n:
+        res = SkipPlan.host_tables(node_flags, n, granule)
+        if res is None:
+            return None
+        table, counts, sides, phantom_tok0, pixels = res
+        if pixels > (1.0 - min_saving) * b * n * n and min_saving > -1e8:
             return None      # (almost) nothing to skip: the dense schedule is as fast and has no phantom
+        if pixels > (b + 1) * n * n:
+            return None      # would not fit the workspace (only possible when forced on a batch without padding)
         t = torch.from_numpy(table)
         if out is None:
             out = t.to(nat.device)
         else:
             out.copy_(t)
-        return SkipPlan(nat, b, out, total, cap, total / float(b * n))
+        return SkipPlan(nat, b, out, b + SkipPlan.TABLE_EXTRA, counts, sides, phantom_tok0, pixels / float(b * n * n))
 
 
 class _Skipping:
@@ -495,7 +516,10 @@ class _NativeModel:
         a.workspace = self.workspace.data_ptr() + off
         a.workspace_bytes = self.workspace.numel() - off
         if skip is not None:
-            a.skip_tables, a.skip_img_rows, a.skip_cap_rows = skip.tables.data_ptr(), skip.img_rows, skip.cap
+            a.skip_tables, a.skip_table_images, a.skip_buckets = skip.tables.data_ptr(), skip.n_images_cap, len(skip.counts)
+            for k, (cnt, side) in enumerate(zip(skip.counts, skip.sides)):
+                a.skip_count[k], a.skip_side[k] = cnt, side
+            a.skip_phantom_tok0 = skip.phantom_tok0
         with native.device_guard(self.device):
             native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
                          "dsg_denoiser_forward")

@@ -35,8 +35,9 @@ class DsgForwardArgs(C.Structure):
                 ("adj", C.c_void_p), ("node", C.c_void_p), ("flags", C.c_void_p), ("noise", C.c_void_p),
                 ("noise_stride", C.c_int64), ("sc_adj", C.c_void_p), ("sc_node", C.c_void_p),
                 ("out_adj", C.c_void_p), ("out_node", C.c_void_p), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t), ("skip_tables", C.c_void_p), ("skip_img_rows", C.c_int32),
-                ("skip_cap_rows", C.c_int32)]
+                ("workspace_bytes", C.c_size_t), ("skip_tables", C.c_void_p), ("skip_table_images", C.c_int32),
+                ("skip_buckets", C.c_int32), ("skip_count", C.c_int32 * 8), ("skip_side", C.c_int32 * 8),
+                ("skip_phantom_tok0", C.c_int64)]
 
 
 class DsgEdmStepParams(C.Structure):

@@ -58,9 +58,10 @@ class HeunGraphPlan:
         self.bbox = torch.zeros(batch, n, 4, **f32)
         self.grid_a, self.inc_a = native.aten_normal_policy(self.X[0].numel(), device)
         self.grid_n, self.inc_n = native.aten_normal_policy(self.X[1].numel(), device)
-        # padded-row skipping: the table is a fixed buffer (its address is part of the captured launches), refilled
-        # per sampling run; the compact row count is baked into launch grids and TMA descriptors, so it keys the graphs
-        self.skip_tables = torch.zeros(2 * (batch + 1) * n + 2 * batch + 3, dtype=torch.int32, device=device)
+        # padding skipping: the table is a fixed buffer (its address is part of the captured launches), refilled per
+        # sampling run; the bucket geometry is baked into launch grids and TMA descriptors, so it keys the graphs
+        from ...model.diffusesg.diffusesg import SkipPlan
+        self.skip_tables = torch.zeros(SkipPlan.table_len(batch), dtype=torch.int32, device=device)
         self.skip = None
         self.graphs: Dict[Tuple, torch.cuda.CUDAGraph] = {}
         self.pool = None
@@ -142,7 +143,7 @@ class HeunGraphPlan:
                                                cn, st), "dsg_edm_post_step_dev")
 
     def replay(self, c1: bool, c2: bool, last: bool, decode=None):
-        key = (bool(c1), bool(c2) and not last, bool(last), decode, self.skip.img_rows if self.skip is not None else 0)
+        key = (bool(c1), bool(c2) and not last, bool(last), decode, self.skip.key if self.skip is not None else None)
         g = self.graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()

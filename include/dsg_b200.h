@@ -106,22 +106,24 @@ DSG_API int dsg_model_finalize(dsg_model* m, dsg_stream_t stream);
  * scalar), = batch otherwise (training). */
 DSG_API size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond);
 
-/* ---- padded-row skipping (model/diffusesg/diffusesg.py:796-802, :812-825) ---------------------------
+/* ---- padding skipping (model/diffusesg/diffusesg.py:796-802, :812-825) ------------------------------
  * A graph with n_b < N nodes occupies the top-left n_b x n_b corner of the N x N pair grid; every other pixel is
  * padding: its inputs are zeroed by mask_adjs (:800) and its outputs are masked (:822-825).  The reference still
  * computes on it.  For the leading resolution stages whose blocks are all UN-shifted window attention, nothing moves
- * between aligned windows, so image rows >= R_b = ceil(n_b / granule) * granule (i) hold, in the encoder, one and the
- * same token value for every sample - computed once on an all-padding "phantom" sample and filled in where the first
- * dense stage needs it - and (ii) cannot influence any unmasked output in the decoder.  Those stages run on a compact
- * layout that stacks only the first R_b image rows of each sample (then the phantom's `granule` rows).  In exact
- * arithmetic the result equals the dense computation; tests/test_gpu_denoiser.py::test_padded_row_skipping_*
- * hold it to the dense path and to the reference's golden outputs at the tolerances of DESIGN.md section 1.
+ * between aligned windows, so every window outside the corner of side R_b = ceil(n_b / granule) * granule (i) holds,
+ * in the encoder, one and the same token value for every sample - computed once on an all-padding "phantom" image
+ * and filled in where the first dense stage needs it - and (ii) cannot influence any unmasked output in the decoder.
+ * Those stages run on a compact layout: the samples are grouped into buckets by R_b, bucket k is a stack of count[k]
+ * images of side[k] x side[k] pixels, the buckets follow each other in memory.  In exact arithmetic the result equals
+ * the dense computation; tests/test_gpu_denoiser.py::test_padding_skipping_* hold it to the dense path (bit-identical
+ * on every tested input) and to the reference's golden outputs at the tolerances of DESIGN.md section 1.
  * dsg_model_skip_info: stages = number of compactable leading stages (0: none for this geometry), granule in pixels.
  * The caller builds, from the node counts, one int32 table on the device (dsg_forward_args.skip_tables):
- *     row_b[cap] | row_i[cap] | off[B + 2] | rb[B + 1]
- * row_b[r] / row_i[r]: sample and image row of compact stage-0 image row r (row_b = -1 for the phantom's rows);
- * off[b]: first compact row of sample b (off[B]: of the phantom, off[B + 1]: total = skip_img_rows); rb[b] = R_b
- * (rb[B] = granule).  Needs n_cond == 1 (one shared noise level, as in sampling). */
+ *     perm[skip_table_images] | tok0[B] | width[B]
+ * perm[k]: the sample shown by compact image k, bucket by bucket (-1: an all-padding image - the phantom, or the
+ * dummy that keeps a bucket's image count even); tok0[b]: stage-0 token offset of sample b's image in the compact
+ * layout; width[b] = R_b.  skip_phantom_tok0: token offset of the phantom image (it lives in the bucket of side
+ * `granule`).  Needs n_cond == 1 (one shared noise level, as in sampling). */
 DSG_API int dsg_model_skip_info(const dsg_model* m, int32_t* stages, int32_t* granule);
 
 typedef struct dsg_forward_args {
@@ -146,8 +148,11 @@ typedef struct dsg_forward_args {
   void* workspace;
   size_t workspace_bytes;
   const int32_t* skip_tables; /* NULL: dense.  Device table described at dsg_model_skip_info */
-  int32_t skip_img_rows;    /* compact stage-0 image rows including the phantom's; multiple of the granule */
-  int32_t skip_cap_rows;    /* capacity `cap` of the row_b / row_i sections (>= skip_img_rows) */
+  int32_t skip_table_images;  /* length of the perm section (>= sum of skip_count) */
+  int32_t skip_buckets;       /* K <= 8 (0: dense) */
+  int32_t skip_count[8];      /* images per bucket, even */
+  int32_t skip_side[8];       /* corner side of the bucket's images in pixels: a multiple of the granule */
+  int64_t skip_phantom_tok0;  /* stage-0 token offset of the phantom image */
 } dsg_forward_args;
 
 DSG_API int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* args, dsg_stream_t stream);

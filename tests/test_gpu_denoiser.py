@@ -443,8 +443,8 @@ def _flags_with_counts(cfg, counts):
 
 @pytest.mark.parametrize("name,counts", [("vg", [2, 9, 16, 17, 33, 48, 62, 5]), ("tiny", [1, 4, 5, 8, 14, 3]),
                                          ("coco", [2, 10, 11, 33, 21, 30])])
-def test_padded_row_skipping_matches_dense(name, counts):
-    """the compact-row schedule (leading un-shifted stages computed only on the image rows that can hold
+def test_padding_skipping_matches_dense(name, counts):
+    """the compact schedule (leading un-shifted stages computed only on each sample's corner that can hold
     valid nodes, the all-padding region represented by one phantom token) against the dense schedule on the same
     inputs.  Equal in exact arithmetic; here both sides are bf16 tensor-core runs whose only difference is WHERE the
     padding tokens were computed, so the gap must stay far below the parity tolerance (2e-2) - and masked outputs
@@ -460,7 +460,7 @@ def test_padded_row_skipping_matches_dense(name, counts):
     stages, granule = net._native(DEV).skip_info()
     assert stages >= 1, (name, stages, granule)
     plan = net.make_skip_plan(flags.to(DEV))
-    assert plan is not None and plan.img_rows < (b + 1) * cfg["img"]
+    assert plan is not None and plan.kept_fraction < 1.0
     sig = torch.full((1,), 1.5, device=DEV).expand(b)       # one shared noise level, as in sampling
     args = [t.to(DEV) for t in (adj, node, flags)]
     with torch.no_grad():
@@ -469,7 +469,7 @@ def test_padded_row_skipping_matches_dense(name, counts):
         n1 = native.launch_count()
         with net.skipping(plan):
             sa, sn = net.denoise(args[0], args[1], args[2], sig, sc_adj.to(DEV), sc_node.to(DEV))
-            assert native.launch_count() - n1 == n1 - n0 + 1      # the compact schedule ran: + the expand / fill launch
+            assert native.launch_count() - n1 > n1 - n0            # the compact schedule ran (per-bucket launches + expand)
             sa2, sn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
         da2, dn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
         # reference: oracle D on the CPU
@@ -487,7 +487,7 @@ def test_padded_row_skipping_matches_dense(name, counts):
 
 
 @pytest.mark.parametrize("name", ["vg", "coco"])
-def test_precond_matches_golden_with_skipping(name, golden_dir):
+def test_padding_skipping_precond_matches_golden(name, golden_dir):
     """NodeAdjPrecond.forward of the unmodified reference (golden) against the native call with padded-row skipping
     active: same tolerance as the dense path (test_precond_matches_golden)."""
     cfg = CONFIGS[name]

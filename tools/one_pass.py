@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--config", default="vg")
-ap.add_argument("--dense", action="store_true", help="no padded-row skipping (the sampler's default is to skip)")
+ap.add_argument("--dense", action="store_true", help="no padding skipping (the sampler's default is to skip)")
 args = ap.parse_args()
 cfg = CONFIGS[args.config]
 dev = torch.device("cuda:0")
@@ -27,7 +27,7 @@ import contextlib  # noqa: E402
 plan = None if args.dense else model.model.make_skip_plan(flags)
 skipping = model.model.skipping(plan) if plan is not None else contextlib.nullcontext()
 skipping.__enter__()
-print("padded-row skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 rows")
+print("padding skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 pixels, buckets {plan.counts} x {plan.sides}")
 with torch.no_grad():
     for _ in range(args.passes):
         a, n = model.model.denoise(adj, node, flags, sig, sc_adj, sc_node)

@@ -20,7 +20,7 @@ from diffusesg_b200.utils.synthetic import CONFIGS, synthetic_inputs  # noqa: E4
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--config", default="vg")
-ap.add_argument("--dense", action="store_true", help="no padded-row skipping (the sampler's default is to skip)")
+ap.add_argument("--dense", action="store_true", help="no padding skipping (the sampler's default is to skip)")
 ap.add_argument("--csv", default="gpurun_out/timeline.csv")
 ap.add_argument("--quiet", action="store_true")
 args = ap.parse_args()
@@ -33,7 +33,7 @@ import contextlib  # noqa: E402
 plan = None if args.dense else model.model.make_skip_plan(flags)
 skipping = model.model.skipping(plan) if plan is not None else contextlib.nullcontext()
 skipping.__enter__()
-print("padded-row skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 rows")
+print("padding skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 pixels, buckets {plan.counts} x {plan.sides}")
 with torch.no_grad():
     for _ in range(3):
         model.model.denoise(adj, node, flags, sig, sc_adj, sc_node)
