@@ -1027,6 +1027,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   return DSG_OK;
 }
 
+void dsg_launch_count_add(uint64_t n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
 void dsg_debug_set_stop_after(int n_stages) { g_stop_after = n_stages; }
 void dsg_debug_trace_next_mlp(long long* device_buffer) { g_mlp_trace = device_buffer; }
 
