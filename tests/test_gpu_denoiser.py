@@ -454,6 +454,9 @@ def test_padding_skipping_matches_dense(name, counts):
     b = len(counts)
     adj, node, _, _, sc_adj, sc_node = synthetic_inputs(cfg, b, seed=11)
     flags = _flags_with_counts(cfg, counts)
+    flags[0, 0] = False                      # node flags need not be a prefix: holes, and ...
+    if counts[1] + 2 < cfg["img"]:
+        flags[1, counts[1] + 1] = True       # ... a valid node beyond a gap (the kept corner follows the LAST valid node)
     pair = (flags[:, None, :, None] & flags[:, None, None, :]).float()
     adj, sc_adj = adj.abs().clamp_min(0.1) * adj.sign() * pair, sc_adj * pair   # re-mask for these flags
     node, sc_node = node * flags[:, :, None], sc_node * flags[:, :, None]

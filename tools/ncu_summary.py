@@ -32,10 +32,17 @@ def raw(path):
         for k in KEEP:
             if k in idx:
                 print(f"    {k} = {r[idx[k]]} {units[idx[k]]}")
-        stalls = [(h, r[idx[h]]) for h in hdr if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")]
-        stalls = sorted(((h, float(v)) for h, v in stalls if v not in ("", "n/a")), key=lambda t: -t[1])[:6]
-        for h, v in stalls:
-            print(f"    stall {h.split('warp_issue_stalled_')[1].split('_per_warp')[0]} = {v:.1f} %")
+        # warp-state sampling (pc sampling counters of --set full): share of all samples per stall reason
+        samp = []
+        for h in hdr:
+            if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+                try:
+                    samp.append((float(r[idx[h]].replace(",", "")), h[len("smsp__pcsamp_warps_issue_stalled_"):]))
+                except ValueError:
+                    pass
+        tot = sum(v for v, _ in samp) or 1.0
+        for v, name in sorted(samp, reverse=True)[:8]:
+            print(f"    warp samples {name} = {100 * v / tot:.1f} %")
         print()
 
 
