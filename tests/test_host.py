@@ -279,3 +279,55 @@ def test_aten_normal_policy_matches_calc_execution_policy(monkeypatch):
     assert native._aten_normal_policy(1, dev) == (1, 4)
     assert native._aten_normal_policy(1184 * 256 * 4 + 1, dev) == (1184, 8)
 
+
+
+@pytest.mark.parametrize("n,granule,counts", [(64, 16, [2, 9, 16, 17, 33, 48, 62, 5, 64, 1]), (40, 10, [33, 2, 10, 11, 21, 30, 40]),
+                                              (16, 4, [1, 4, 5, 8, 14, 3, 16])])
+def test_skip_plan_host_tables(n, granule, counts):
+    """Host side of the padding skipping (include/dsg_b200.h: dsg_model_skip_info): the compact layout must show every
+    sample exactly once, inside a corner that covers its last valid node, bucket by bucket, with even image counts
+    (the 8 x 8 attention kernel pairs windows) and one all-padding phantom image in the bucket of side `granule`."""
+    import numpy as np
+    from diffusesg_b200.model.diffusesg.diffusesg import SkipPlan
+    b = len(counts)
+    flags = torch.arange(n)[None, :] < torch.tensor(counts)[:, None]
+    flags[0, 0] = False                       # holes are allowed: only the LAST valid node matters
+    table, cnt, sides, phantom_tok0, pixels = SkipPlan.host_tables(flags, n, granule)
+    cap = b + SkipPlan.TABLE_EXTRA
+    assert len(table) == SkipPlan.table_len(b)
+    perm, tok0, width = table[:sum(cnt)], table[cap:cap + b], table[cap + b:cap + 2 * b]
+    assert sorted(p for p in perm if p >= 0) == list(range(b))
+    assert sides == sorted(sides) and sides[0] == granule and all(s % granule == 0 and s <= n for s in sides)
+    assert all(c % 2 == 0 and c > 0 for c in cnt)
+    assert pixels == sum(c * s * s for c, s in zip(cnt, sides))
+    img, tok = 0, 0
+    phantom_seen = False
+    for c, s in zip(cnt, sides):
+        for k in range(c):
+            p = perm[img + k]
+            if p >= 0:
+                assert width[p] == s and tok0[p] == tok + k * s * s
+                assert s >= counts[p] and (s - granule < counts[p] or s == granule)     # smallest corner that covers it
+            elif s == granule and tok + k * s * s == phantom_tok0:
+                phantom_seen = True
+        img += c
+        tok += c * s * s
+    assert phantom_seen
+    # more than 8 distinct corner sizes cannot be expressed: the caller then keeps the dense schedule
+    many = torch.arange(64)[None, :] < torch.arange(1, 65, 7)[:, None]
+    assert SkipPlan.host_tables(many, 64, 4) is None
+
+
+def test_step_params_row_layout():
+    """The per-step table the captured graphs read (dsg_edm_step_params, 48 bytes): the numpy packing of graphs.py and
+    the ctypes mirror of native.py must agree field by field."""
+    import ctypes as C
+    import numpy as np
+    from diffusesg_b200 import native
+    assert C.sizeof(native.DsgEdmStepParams) == native.STEP_PARAMS_BYTES == 48
+    assert native.DsgEdmStepParams.t_hat.offset == native.STEP_PARAMS_T_HAT_OFFSET
+    dt = np.dtype([("noise_coef", "<f4"), ("inv_t_hat", "<f4"), ("h", "<f4"), ("inv_t_prime", "<f4"), ("t_hat", "<f4"),
+                   ("reserved", "<f4"), ("seed", "<u8"), ("offset_adj", "<u8"), ("offset_node", "<u8")])
+    assert dt.itemsize == 48
+    for name, _ in native.DsgEdmStepParams._fields_:
+        assert dt.fields[name][1] == getattr(native.DsgEdmStepParams, name).offset, name
