@@ -202,9 +202,11 @@ int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t,
 // expansion with the phantom's token as fill (quarter-warp widths only)
 bool row_compaction_supported(int C_merge, int D_breakup);
 int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
-                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st);
-int launch_expand_fill(const float* compact, float* dense, const int* tok0, const int* width, int sh, long long phantom_tok,
-                       int batch, int res, int C, cudaStream_t st);
+                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st,
+                              const int* src_perm = nullptr);
+// re-layout between the dense grid and the compact layouts (see relayout_kernel in rowops.cu)
+int launch_relayout(const float* src, float* dst, const int* dst_perm, int n_images, int dst_side, const int* src_tok0,
+                    const int* src_width, int src_side, int sh, long long phantom_tok, int C, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // fused EDM step kernels                                               (edm.cu)

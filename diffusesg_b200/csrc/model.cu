@@ -166,6 +166,10 @@ struct dsg_model {
   // computed on a compact layout holding, per sample, only the first R_b image rows (R_b = n_b rounded up to
   // `skip_granule` pixels).  0 = the geometry does not allow it (see skip_geometry below).
   int skip_stages = 0, skip_granule = 0;
+  // Second level: the first block of the first DENSE stage (encoder) and that stage's last block (decoder) are
+  // un-shifted too; they run on a second, coarser compact layout (corner side rounded up to skip2_granule pixels =
+  // that stage's window).  0 = not available.
+  int skip2_granule = 0;
   std::map<std::tuple<const void*, long long, int>, CUtensorMap> a_maps;
 
   const float* f32(const std::string& key) const {
@@ -393,9 +397,22 @@ void skip_geometry(dsg_model* m) {
   }
   while (S > 0) {
     const int g = m->blocks[m->down_first[S - 1]].window << (S - 1);  // window of the coarsest compact stage, in pixels
-    if (g < m->N && m->N % g == 0) { m->skip_stages = S; m->skip_granule = g; return; }
+    if (g < m->N && m->N % g == 0) { m->skip_stages = S; m->skip_granule = g; break; }
     --S;  // a single window spans the whole grid there: nothing to skip at that stage
   }
+  m->skip2_granule = 0;
+  const char* off2 = getenv("DSG_NO_SKIP2");
+  if (S == 0 || S > m->nl - 1 || (off2 != nullptr && off2[0] == '1')) return;
+  // level 2 at stage S: its first encoder block and its last decoder block must be un-shifted window attention over more
+  // than one window, with at least one (shifted) block between them and the rest of the network
+  const int d = m->cfg.depths[S];
+  if (d < 2) return;
+  const Block& e0 = m->blocks[m->down_first[S]];
+  const Block& dl = m->blocks[m->up_first[m->nl - 1 - S] + d - 1];
+  const bool ok = e0.shift == 0 && dl.shift == 0 && e0.window < e0.res && dl.window == e0.window &&
+                  (e0.window == 8 || window_attention_quad_supported(1, e0.res, e0.window, 0, e0.heads));
+  const int g2 = e0.window << S;
+  if (ok && g2 < m->N && m->N % g2 == 0 && g2 % m->skip_granule == 0) m->skip2_granule = g2;
 }
 
 int pack_weight(dsg_model* m, Weight& w, const std::string& key, cudaStream_t st, int64_t n_scaled = 0,
@@ -806,6 +823,12 @@ int dsg_model_skip_info(const dsg_model* m, int32_t* stages, int32_t* granule) {
   return DSG_OK;
 }
 
+int dsg_model_skip_info2(const dsg_model* m, int32_t* granule2) {
+  DSG_REQUIRE(m != nullptr && granule2 != nullptr, "skip_info2: null argument");
+  *granule2 = m->skip2_granule;
+  return DSG_OK;
+}
+
 size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond) {
   if (m == nullptr || batch <= 0 || n_cond <= 0) return 0;
   return carve(m, batch, n_cond, nullptr).bytes;
@@ -842,39 +865,50 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     label_stride = 1;
   }
   // ---- padding skipping: compact layout of the leading un-shifted stages (see skip_geometry, Compact) ------------
-  Compact cpl;
-  const Compact* cp = nullptr;
+  Compact cpl, cpl2;
+  const Compact *cp = nullptr, *cp2 = nullptr;
   int S = 0;
+  auto parse_plan = [&](Compact& c, const int32_t* tables, int table_images, int buckets, const int32_t* counts,
+                        const int32_t* sides, long long phantom_tok0, int G) -> int {
+    DSG_REQUIRE(buckets > 0 && buckets <= 8 && table_images > 0, "forward: %d buckets", buckets);
+    c.K = buckets;
+    long long tok = 0;
+    int img = 0;
+    for (int k = 0; k < c.K; ++k) {
+      c.count[k] = counts[k];
+      c.side[k] = sides[k];
+      DSG_REQUIRE(c.count[k] > 0 && c.count[k] % 2 == 0 && c.side[k] >= G && c.side[k] <= N && c.side[k] % G == 0,
+                  "forward: bucket %d holds %d images of side %d (granule %d)", k, c.count[k], c.side[k], G);
+      c.img0[k] = img;
+      c.tok[k] = tok;
+      img += c.count[k];
+      tok += static_cast<long long>(c.count[k]) * c.side[k] * c.side[k];
+    }
+    c.tok[c.K] = tok;
+    DSG_REQUIRE(img <= table_images && tok <= static_cast<long long>(B + 1) * N * N,
+                "forward: the compact plan holds %d images / %lld pixels (table %d, capacity %lld)", img, tok, table_images,
+                static_cast<long long>(B + 1) * N * N);
+    DSG_REQUIRE(phantom_tok0 >= 0 && phantom_tok0 + static_cast<long long>(G) * G <= tok, "forward: phantom offset");
+    c.perm = tables;
+    c.tok0 = c.perm + table_images;
+    c.width = c.tok0 + B;
+    c.phantom_tok0 = phantom_tok0;
+    return DSG_OK;
+  };
   if (a->skip_tables != nullptr && a->skip_buckets > 0) {
-    const int G = m->skip_granule;
     DSG_REQUIRE(m->skip_stages > 0, "forward: this geometry has no compactable stage (skip_tables given)");
     DSG_REQUIRE(uniform, "forward: padding skipping needs one shared noise level (n_cond == 1)");
     DSG_REQUIRE(g_stop_after < 0, "forward: the stage-walk test hook runs on the dense schedule");
-    DSG_REQUIRE(a->skip_buckets <= 8 && a->skip_table_images > 0, "forward: %d buckets", a->skip_buckets);
-    cpl.K = a->skip_buckets;
-    long long tok = 0;
-    int img = 0;
-    for (int k = 0; k < cpl.K; ++k) {
-      cpl.count[k] = a->skip_count[k];
-      cpl.side[k] = a->skip_side[k];
-      DSG_REQUIRE(cpl.count[k] > 0 && cpl.count[k] % 2 == 0 && cpl.side[k] >= G && cpl.side[k] <= N && cpl.side[k] % G == 0,
-                  "forward: bucket %d holds %d images of side %d (granule %d)", k, cpl.count[k], cpl.side[k], G);
-      cpl.img0[k] = img;
-      cpl.tok[k] = tok;
-      img += cpl.count[k];
-      tok += static_cast<long long>(cpl.count[k]) * cpl.side[k] * cpl.side[k];
-    }
-    cpl.tok[cpl.K] = tok;
-    DSG_REQUIRE(img <= a->skip_table_images && tok <= static_cast<long long>(B + 1) * N * N,
-                "forward: the compact plan holds %d images / %lld pixels (table %d, capacity %lld)", img, tok,
-                a->skip_table_images, static_cast<long long>(B + 1) * N * N);
-    DSG_REQUIRE(a->skip_phantom_tok0 >= 0 && a->skip_phantom_tok0 + static_cast<long long>(G) * G <= tok, "forward: phantom offset");
-    cpl.perm = a->skip_tables;
-    cpl.tok0 = cpl.perm + a->skip_table_images;
-    cpl.width = cpl.tok0 + B;
-    cpl.phantom_tok0 = a->skip_phantom_tok0;
+    DSG_TRY(parse_plan(cpl, a->skip_tables, a->skip_table_images, a->skip_buckets, a->skip_count, a->skip_side,
+                       a->skip_phantom_tok0, m->skip_granule));
     cp = &cpl;
     S = m->skip_stages;
+    if (a->skip2_tables != nullptr && a->skip2_buckets > 0) {
+      DSG_REQUIRE(m->skip2_granule > 0, "forward: this geometry has no second compaction level (skip2_tables given)");
+      DSG_TRY(parse_plan(cpl2, a->skip2_tables, a->skip2_table_images, a->skip2_buckets, a->skip2_count, a->skip2_side,
+                         a->skip2_phantom_tok0, m->skip2_granule));
+      cp2 = &cpl2;
+    }
   }
   g_prof_pass = g_prof_on && !stream_capturing(st) && (g_prof_counter++ % g_prof_stride == 0);
   struct ProfPassGuard { ~ProfPassGuard() { g_prof_pass = false; } } prof_pass_guard;
@@ -909,8 +943,17 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   for (int s = 0; s < m->nl; ++s) {
     const float* x_in = s == 0 ? w.X : w.skip[s - 1];
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
-      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr, s < S ? cp : nullptr));
+      const bool level2 = cp2 != nullptr && s == S && j == 0;   // first block of the first dense stage, on the second layout
+      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr,
+                        s < S ? cp : (level2 ? cp2 : nullptr)));
       x_in = w.X;
+      if (level2) {
+        // compact (level 2) -> dense for the shifted blocks that follow; outside the kept corners: the phantom's token
+        const int res_s = N >> s, C_s = E << s;
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(B) * res_s * res_s * C_s * 8,
+                  launch_relayout(w.X, w.T, nullptr, B, res_s, cp2->tok0, cp2->width, 0, s, cp2->phantom_tok0 >> (2 * s), C_s, st));
+        x_in = w.T;
+      }
       DSG_STAGE_DONE();
     }
     if (s < m->nl - 1) {
@@ -929,9 +972,20 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
           DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
         } else {
           DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.T, st));
-          const double dense_el = static_cast<double>(B) * (g.res / 2) * (g.res / 2) * 2 * g.C;
-          DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_expand_fill(w.T, w.skip[s], cp->tok0, cp->width, s + 1,
-                                                                cp->phantom_tok0 >> (2 * (s + 1)), B, g.res / 2, 2 * g.C, st));
+          const long long ph = cp->phantom_tok0 >> (2 * (s + 1));
+          if (cp2 != nullptr) {
+            // ... into the second compact layout (the stage's first block and the decoder's skip read it there)
+            for (int k = 0; k < cp2->K; ++k) {
+              const int side_t = cp2->side[k] >> (s + 1);
+              DSG_TRY_P(PC_ROW, 0, static_cast<double>(cp2->count[k]) * side_t * side_t * 2 * g.C * 8,
+                        launch_relayout(w.T, w.skip[s] + cp2->at(k, s + 1) * 2 * g.C, cp2->perm + cp2->img0[k], cp2->count[k], side_t,
+                                        cp->tok0, cp->width, 0, s + 1, ph, 2 * g.C, st));
+            }
+          } else {
+            const double dense_el = static_cast<double>(B) * (g.res / 2) * (g.res / 2) * 2 * g.C;
+            DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_relayout(w.T, w.skip[s], nullptr, B, g.res / 2, cp->tok0, cp->width, 0, s + 1,
+                                                               ph, 2 * g.C, st));
+          }
         }
       } else {
         const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
@@ -964,15 +1018,26 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
         }
         DSG_TRY(gemm(m, w.Y, rows_low * 4, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
       } else if (s < S) {
-        // dense -> compact: only the children inside each sample's kept corner are produced
-        const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
+        // dense (or level-2 compact) -> compact: only the children inside each sample's kept corner are produced
+        const long long rows_low = cp2 != nullptr ? cp2->tokens(s + 1) : static_cast<long long>(B) * bu.res * bu.res;
         const long long rows_hi = cp->tokens(s);
         DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
         DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
-        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 4 + static_cast<double>(rows_hi) * bu.D / 2,
-                  launch_breakup_ln_compact(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
-                                            m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
-                                            B, bu.res, bu.D, cp->tok0, cp->width, s, st));
+        if (cp2 != nullptr) {
+          for (int k = 0; k < cp2->K; ++k) {
+            const double rk = static_cast<double>(cp2->at(k + 1, s + 1) - cp2->at(k, s + 1));
+            DSG_TRY_P(PC_ROW, 0, rk * bu.D * 6,
+                      launch_breakup_ln_compact(w.T + cp2->at(k, s + 1) * bu.D, w.Y, m->f32(bu.prefix + ".norm.weight"),
+                                                m->f32(bu.prefix + ".norm.bias"), m->f32(bu.prefix + ".post_norm.weight"),
+                                                m->f32(bu.prefix + ".post_norm.bias"), cp2->count[k], cp2->side[k] >> (s + 1), bu.D,
+                                                cp->tok0, cp->width, s, st, cp2->perm + cp2->img0[k]));
+          }
+        } else {
+          DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 4 + static_cast<double>(rows_hi) * bu.D / 2,
+                    launch_breakup_ln_compact(w.T, w.Y, m->f32(bu.prefix + ".norm.weight"), m->f32(bu.prefix + ".norm.bias"),
+                                              m->f32(bu.prefix + ".post_norm.weight"), m->f32(bu.prefix + ".post_norm.bias"),
+                                              B, bu.res, bu.D, cp->tok0, cp->width, s, st));
+        }
         DSG_TRY(gemm(m, w.Y, rows_hi, bu.post, EPI_F32, nullptr, nullptr, w.X, st));
       } else {
         const long long rows_low = static_cast<long long>(B) * bu.res * bu.res;
@@ -988,8 +1053,20 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
       // the last block: the final LayerNorm rides on its fused tail (not while a test walks the stages: those read X)
       const bool last = u == m->nl - 1 && j == m->cfg.depths[s] - 1 && m->use_final_ln && g_stop_after < 0;
+      const bool level2 = cp2 != nullptr && s == S && j == m->cfg.depths[s] - 1;   // last block of the first dense stage
+      if (level2) {
+        // dense -> compact (level 2): only the kept corners feed this window-local block and the breakup after it
+        const int res_s = N >> s, C_s = E << s;
+        for (int k = 0; k < cp2->K; ++k) {
+          const int side_t = cp2->side[k] >> s;
+          DSG_TRY_P(PC_ROW, 0, static_cast<double>(cp2->count[k]) * side_t * side_t * C_s * 8,
+                    launch_relayout(w.X, w.T + cp2->at(k, s) * C_s, cp2->perm + cp2->img0[k], cp2->count[k], side_t, nullptr, nullptr,
+                                    res_s, 0, -1, C_s, st));
+        }
+        x_in = w.T;
+      }
       DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done,
-                        s < S ? cp : nullptr));
+                        s < S ? cp : (level2 ? cp2 : nullptr)));
       DSG_STAGE_DONE();
     }
   }

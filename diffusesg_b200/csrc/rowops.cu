@@ -280,7 +280,8 @@ template <int NV>  // NV = Dq / 32 float4 per lane, Dq = D / 4
 __global__ void __launch_bounds__(kRowThreads)
 breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const float* __restrict__ g1,
                     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
-                    long long rows_in, int res, const int* __restrict__ tok0, const int* __restrict__ width, int sh) {
+                    long long rows_in, int res, const int* __restrict__ tok0, const int* __restrict__ width, int sh,
+                    const int* __restrict__ src_perm) {
   constexpr int Dq = NV * 32, D = 4 * Dq;
   const int lane = threadIdx.x & 31, k = lane >> 3, sub = lane & 7;
   const long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / 32) + (threadIdx.x >> 5);
@@ -294,10 +295,13 @@ breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const flo
   long long out_tok0 = ((b * res2 + 2 * iy) * res2) + 2 * ix;   // token of the (dy, dx) = (0, 0) child, dense
   int out_pitch = res2;
   if (tok0 != nullptr) {
-    const int wc = width[b] >> sh;
+    // the input image shows sample src_perm[b] when the input itself is a compact stack (nullptr: dense, sample b)
+    const long long sb = src_perm != nullptr ? src_perm[b] : b;
+    if (sb < 0) return;                          // an all-padding image has no children anyone reads
+    const int wc = width[sb] >> sh;
     if (2 * iy >= wc || 2 * ix >= wc) return;   // children outside the kept corner: dead, never read
     out_pitch = wc;
-    out_tok0 = (static_cast<long long>(tok0[b]) >> (2 * sh)) + static_cast<long long>(2 * iy) * wc + 2 * ix;
+    out_tok0 = (static_cast<long long>(tok0[sb]) >> (2 * sh)) + static_cast<long long>(2 * iy) * wc + 2 * ix;
   }
   const float* src = t + row * D + k * Dq;  // lanes [8k, 8k + 8) own chunk k = elements [k Dq, (k + 1) Dq)
   float4 v[NV];
@@ -761,26 +765,35 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
   }
 }
 
-// compact -> dense at the first stage that is computed densely (padding skipping, model.cu): sample b's kept corner
-// ((width[b] >> sh)^2 tokens starting at tok0[b] >> 2 sh) is copied, every other token of its grid is filled with the
-// phantom's token - the value every token of an all-padding region takes at this stage.
+// Re-layout between the dense grid and the compact layouts of the padding skipping (model.cu), fp32 rows of 4 C4 floats.
+// Destination: n_images square images of dst_side tokens; image k shows sample dst_perm[k] (nullptr: sample k, i.e. the
+// dense grid; < 0: an all-padding image).  Source: sample b's kept corner of (src_width[b] >> sh) tokens starting at
+// token src_tok0[b] >> 2 sh (src_tok0 == nullptr: the dense grid of src_side tokens).  Destination tokens outside the
+// source corner take the phantom's token (phantom_tok < 0: zeros) - the value every token of an all-padding region
+// holds at this point of the network.
 __global__ void __launch_bounds__(256)
-expand_fill_kernel(const float* __restrict__ compact, float* __restrict__ dense, const int* __restrict__ tok0,
-                   const int* __restrict__ width, int sh, long long phantom_tok, int batch, int res, int C4) {
-  const long long total = static_cast<long long>(batch) * res * res * C4;
-  const float4* src = reinterpret_cast<const float4*>(compact);
-  float4* dst = reinterpret_cast<float4*>(dense);
+relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ dst_perm, int n_images,
+                int dst_side, const int* __restrict__ src_tok0, const int* __restrict__ src_width, int src_side, int sh,
+                long long phantom_tok, int C4) {
+  const long long total = static_cast<long long>(n_images) * dst_side * dst_side * C4;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long tok = v / C4;
     const int c4 = static_cast<int>(v - tok * C4);
-    const int b = static_cast<int>(tok / (res * res));
-    const int rem = static_cast<int>(tok - static_cast<long long>(b) * res * res);
-    const int r = rem / res, x = rem - r * res;
-    const int wc = width[b] >> sh;
-    const long long st = (r < wc && x < wc) ? (static_cast<long long>(tok0[b]) >> (2 * sh)) + static_cast<long long>(r) * wc + x
-                                            : phantom_tok;
-    dst[v] = src[st * C4 + c4];
+    const int img = static_cast<int>(tok / (dst_side * dst_side));
+    const int rem = static_cast<int>(tok - static_cast<long long>(img) * dst_side * dst_side);
+    const int r = rem / dst_side, x = rem - r * dst_side;
+    const int b = dst_perm != nullptr ? dst_perm[img] : img;
+    long long st = phantom_tok;
+    if (b >= 0) {
+      const int wc = src_tok0 != nullptr ? (src_width[b] >> sh) : src_side;
+      if (r < wc && x < wc)
+        st = (src_tok0 != nullptr ? (static_cast<long long>(src_tok0[b]) >> (2 * sh)) : static_cast<long long>(b) * src_side * src_side) +
+             static_cast<long long>(r) * wc + x;
+    }
+    d4[v] = st >= 0 ? s4[st * C4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -866,25 +879,27 @@ bool row_compaction_supported(int C_merge, int D_breakup) {
 
 // dense [B, res, res, D] -> compact children (see breakup_ln_q_kernel); quarter-warp widths only
 int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
-                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st) {
+                              int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st,
+                              const int* src_perm) {
   DSG_REQUIRE((D == 384 || D == 768 || D == 1536) && tok0 && width, "breakup (compact): width %d", D);
   const long long rows = static_cast<long long>(batch) * res * res;
   const unsigned grid = row_grid(rows);
-  if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
-  else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
-  else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh);
+  if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh, src_perm);
+  else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh, src_perm);
+  else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, tok0, width, sh, src_perm);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
 
-int launch_expand_fill(const float* compact, float* dense, const int* tok0, const int* width, int sh, long long phantom_tok,
-                       int batch, int res, int C, cudaStream_t st) {
-  DSG_REQUIRE(C % 4 == 0 && tok0 && width, "expand_fill: width %d", C);
-  const long long total = static_cast<long long>(batch) * res * res * (C / 4);
+int launch_relayout(const float* src, float* dst, const int* dst_perm, int n_images, int dst_side, const int* src_tok0,
+                    const int* src_width, int src_side, int sh, long long phantom_tok, int C, cudaStream_t st) {
+  DSG_REQUIRE(C % 4 == 0 && n_images > 0 && dst_side > 0 && (src_tok0 == nullptr) == (src_width == nullptr),
+              "relayout: width %d, %d images of side %d", C, n_images, dst_side);
+  const long long total = static_cast<long long>(n_images) * dst_side * dst_side * (C / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  expand_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(compact, dense, tok0, width, sh, phantom_tok, batch, res,
-                                                                    C / 4);
+  relayout_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, dst, dst_perm, n_images, dst_side, src_tok0, src_width,
+                                                                 src_side, sh, phantom_tok, C / 4);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -904,9 +919,9 @@ int launch_breakup_ln(const float* t, bf16* y, const float* g1, const float* b1,
   DSG_REQUIRE(D % 16 == 0, "breakup: width %d", D);
   if (D == 384 || D == 768 || D == 1536) {
     const unsigned grid = row_grid(rows);
-    if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0);
-    else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0);
-    else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0);
+    if (D == 384) breakup_ln_q_kernel<3><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0, nullptr);
+    else if (D == 768) breakup_ln_q_kernel<6><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0, nullptr);
+    else breakup_ln_q_kernel<12><<<grid, kRowThreads, 0, st>>>(t, y, g1, b1, g2, b2, rows, res, nullptr, nullptr, 0, nullptr);
     DSG_LAUNCH_CHECK();
     return DSG_OK;
   }

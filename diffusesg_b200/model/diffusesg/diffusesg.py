@@ -312,13 +312,17 @@ class SkipPlan:
 
     TABLE_EXTRA = 17   # phantom + one dummy image per bucket (<= 8 buckets)
 
-    def __init__(self, nat, batch, tables, n_images_cap, counts, sides, phantom_tok0, kept_fraction):
+    def __init__(self, nat, batch, tables, n_images_cap, counts, sides, phantom_tok0, kept_fraction, level2=None):
         self.nat, self.batch, self.tables, self.n_images_cap = nat, batch, tables, n_images_cap
         self.counts, self.sides, self.phantom_tok0, self.kept_fraction = counts, sides, phantom_tok0, kept_fraction
-        self.key = (tuple(counts), tuple(sides), phantom_tok0)   # what the launch sequence of a pass depends on
+        # level2: (table offset in `tables`, counts, sides, phantom_tok0, kept fraction) of the second, coarser layout
+        self.level2 = level2
+        # what the launch sequence of a pass depends on
+        self.key = (tuple(counts), tuple(sides), phantom_tok0) + ((tuple(level2[1]), tuple(level2[2]), level2[3]) if level2 else ())
 
     @staticmethod
     def table_len(batch: int) -> int:
+        """int32 entries of one level's table; the device buffer holds two levels back to back."""
         return (batch + SkipPlan.TABLE_EXTRA) + 2 * batch
 
     @staticmethod
@@ -355,11 +359,13 @@ class SkipPlan:
 
     @staticmethod
     def build(nat, node_flags, n, out=None, min_saving=0.03):
+        import numpy as np
         stages, granule = nat.skip_info()
         if stages == 0 or node_flags.dim() != 2 or node_flags.shape[1] != n:
             return None
         b = node_flags.shape[0]
-        res = SkipPlan.host_tables(node_flags, n, granule)
+        flags_host = node_flags.to(torch.bool).cpu()
+        res = SkipPlan.host_tables(flags_host, n, granule)
         if res is None:
             return None
         table, counts, sides, phantom_tok0, pixels = res
@@ -367,12 +373,20 @@ class SkipPlan:
             return None      # (almost) nothing to skip: the dense schedule is as fast and has no phantom
         if pixels > (b + 1) * n * n:
             return None      # would not fit the workspace (only possible when forced on a batch without padding)
-        t = torch.from_numpy(table)
+        level2 = None
+        table2 = np.zeros(SkipPlan.table_len(b), dtype=np.int32)
+        granule2 = nat.skip_info2()
+        if granule2 > 0:
+            res2 = SkipPlan.host_tables(flags_host, n, granule2)
+            if res2 is not None and res2[4] <= min((b + 1) * n * n, (1.0 - min_saving) * b * n * n if min_saving > -1e8 else 1e30):
+                table2, counts2, sides2, phantom2, pixels2 = res2
+                level2 = (SkipPlan.table_len(b), counts2, sides2, phantom2, pixels2 / float(b * n * n))
+        t = torch.from_numpy(np.concatenate([table, table2]))
         if out is None:
             out = t.to(nat.device)
         else:
             out.copy_(t)
-        return SkipPlan(nat, b, out, b + SkipPlan.TABLE_EXTRA, counts, sides, phantom_tok0, pixels / float(b * n * n))
+        return SkipPlan(nat, b, out, b + SkipPlan.TABLE_EXTRA, counts, sides, phantom_tok0, pixels / float(b * n * n), level2)
 
 
 class _Skipping:
@@ -496,6 +510,11 @@ class _NativeModel:
         native.check(self.lib.dsg_model_skip_info(self.handle, C.byref(stages), C.byref(granule)), "dsg_model_skip_info")
         return stages.value, granule.value
 
+    def skip_info2(self):
+        granule2 = C.c_int32()
+        native.check(self.lib.dsg_model_skip_info2(self.handle, C.byref(granule2)), "dsg_model_skip_info2")
+        return granule2.value
+
     def forward(self, mode, batch, n_cond, adj, node, flags, noise, stride, sc_adj, sc_node, out_adj, out_node,
                 skip=None):
         key = (batch, n_cond)
@@ -520,6 +539,13 @@ class _NativeModel:
             for k, (cnt, side) in enumerate(zip(skip.counts, skip.sides)):
                 a.skip_count[k], a.skip_side[k] = cnt, side
             a.skip_phantom_tok0 = skip.phantom_tok0
+            if skip.level2 is not None:
+                off2, counts2, sides2, phantom2, _ = skip.level2
+                a.skip2_tables = skip.tables.data_ptr() + 4 * off2
+                a.skip2_table_images, a.skip2_buckets = skip.n_images_cap, len(counts2)
+                for k, (cnt, side) in enumerate(zip(counts2, sides2)):
+                    a.skip2_count[k], a.skip2_side[k] = cnt, side
+                a.skip2_phantom_tok0 = phantom2
         with native.device_guard(self.device):
             native.check(self.lib.dsg_denoiser_forward(self.handle, C.byref(a), native.stream_ptr(self.device)),
                          "dsg_denoiser_forward")

@@ -37,7 +37,9 @@ class DsgForwardArgs(C.Structure):
                 ("out_adj", C.c_void_p), ("out_node", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("skip_tables", C.c_void_p), ("skip_table_images", C.c_int32),
                 ("skip_buckets", C.c_int32), ("skip_count", C.c_int32 * 8), ("skip_side", C.c_int32 * 8),
-                ("skip_phantom_tok0", C.c_int64)]
+                ("skip_phantom_tok0", C.c_int64), ("skip2_tables", C.c_void_p), ("skip2_table_images", C.c_int32),
+                ("skip2_buckets", C.c_int32), ("skip2_count", C.c_int32 * 8), ("skip2_side", C.c_int32 * 8),
+                ("skip2_phantom_tok0", C.c_int64)]
 
 
 class DsgEdmStepParams(C.Structure):
@@ -73,6 +75,7 @@ _SIGNATURES = {
     "dsg_model_tensor_differs": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dsg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "dsg_model_skip_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "dsg_model_skip_info2": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "dsg_denoiser_forward": (C.c_int, [C.c_void_p, C.POINTER(DsgForwardArgs), C.c_void_p]),
     "dsg_edm_pre_step": (C.c_int, [C.c_void_p] * 5 + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_edm_pre_step_philox": (C.c_int, [C.c_void_p] * 3 + [C.c_float, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_int,

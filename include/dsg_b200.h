@@ -125,6 +125,12 @@ DSG_API size_t dsg_workspace_bytes(const dsg_model* m, int batch, int n_cond);
  * layout; width[b] = R_b.  skip_phantom_tok0: token offset of the phantom image (it lives in the bucket of side
  * `granule`).  Needs n_cond == 1 (one shared noise level, as in sampling). */
 DSG_API int dsg_model_skip_info(const dsg_model* m, int32_t* stages, int32_t* granule);
+/* Second level (0: not available): when the first block of the first DENSE stage and that stage's last block on the way
+ * up are un-shifted as well (Visual Genome: the C = 384 stage, blocks [un-shifted, shifted, un-shifted]), those two
+ * blocks, the encoder skip of that stage and the PatchBreakup input run on a second compact layout with the coarser
+ * granule2 (that stage's window in pixels), described by dsg_forward_args.skip2_* exactly like the first
+ * (perm2 | tok2 | width2 with its own phantom image); the shifted blocks in between stay dense. */
+DSG_API int dsg_model_skip_info2(const dsg_model* m, int32_t* granule2);
 
 typedef struct dsg_forward_args {
   uint32_t struct_size;     /* sizeof(dsg_forward_args) */
@@ -153,6 +159,12 @@ typedef struct dsg_forward_args {
   int32_t skip_count[8];      /* images per bucket, even */
   int32_t skip_side[8];       /* corner side of the bucket's images in pixels: a multiple of the granule */
   int64_t skip_phantom_tok0;  /* stage-0 token offset of the phantom image */
+  const int32_t* skip2_tables; /* second level (dsg_model_skip_info2), same layout; NULL: none */
+  int32_t skip2_table_images;
+  int32_t skip2_buckets;
+  int32_t skip2_count[8];
+  int32_t skip2_side[8];
+  int64_t skip2_phantom_tok0;
 } dsg_forward_args;
 
 DSG_API int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* args, dsg_stream_t stream);

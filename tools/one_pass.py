@@ -27,7 +27,7 @@ import contextlib  # noqa: E402
 plan = None if args.dense else model.model.make_skip_plan(flags)
 skipping = model.model.skipping(plan) if plan is not None else contextlib.nullcontext()
 skipping.__enter__()
-print("padding skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 pixels, buckets {plan.counts} x {plan.sides}")
+print("padding skipping:", "off" if plan is None else f"kept {plan.kept_fraction:.3f} of the stage-0 pixels, buckets {plan.counts} x {plan.sides}, level 2: {plan.level2[1:] if plan.level2 else None}")
 with torch.no_grad():
     for _ in range(args.passes):
         a, n = model.model.denoise(adj, node, flags, sig, sc_adj, sc_node)
