@@ -1078,8 +1078,7 @@ int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, in
   return launch_tc_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, shift, heads, st);
 }
 
-// img_rows token rows of `res` tokens: B stacked res x res grids, or (un-shifted windows only: a window's TMA
-// coordinates are 8 * (window / nwx), 8 * (window % nwx), no sample index involved) any stack of whole window rows
+// img_rows = B res token rows of `res` tokens (B stacked res x res grids)
 static int launch_tc_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int shift, int heads,
                           cudaStream_t st) {
   const long long batch = img_rows;  // only ever used as batch * res below
@@ -1204,19 +1203,6 @@ int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, 
                                  int heads, cudaStream_t st) {
   DSG_REQUIRE(window_attention_quad_supported(batch, res, window, shift, heads), "attention_quad: unsupported shape");
   return launch_quad_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, window, shift, heads, st);
-}
-
-bool window_attention_rows_supported(int res, int window, int heads) {
-  if (window == 8) return res % 8 == 0 && ((res / 8) % 2 == 0) && heads >= 1 && heads <= 74;
-  return window_attention_quad_supported(1, res, window, 0, heads);
-}
-
-int launch_window_attention_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window,
-                                 int heads, cudaStream_t st) {
-  DSG_REQUIRE(window_attention_rows_supported(res, window, heads) && img_rows > 0 && img_rows % window == 0,
-              "attention (rows): res %d window %d heads %d rows %lld", res, window, heads, img_rows);
-  if (window == 8) return launch_tc_rows(qkv, bias, out, img_rows, res, 0, heads, st);
-  return launch_quad_rows(qkv, bias, out, img_rows, res, window, 0, heads, st);
 }
 
 static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window, int shift,

@@ -133,12 +133,6 @@ bool window_attention_quad_supported(int batch, int res, int window, int shift, 
 int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
                                  int heads, cudaStream_t st);
 int check_mask_canonical(const float* mask, int res, int window, int shift, cudaStream_t st, int* canonical);
-// un-shifted windows over a stack of img_rows token rows (img_rows % window == 0) that need not be whole res x res
-// grids: the compact layout of the padded-row skipping.  tcgen05 kernels only (8 x 8: two windows per tile; other
-// even windows up to 10 x 10: quad kernel).
-bool window_attention_rows_supported(int res, int window, int heads);
-int launch_window_attention_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window,
-                                 int heads, cudaStream_t st);
 // 16 x 16 windows (T = 256): query halves of 128 rows against 256 keys, bias looked up from the head's offset table;
 // needs check_bias_toeplitz() (bias[h][q][k] depends on the token offset only; synchronous, at finalisation).
 bool window_attention_w16_supported(int batch, int res, int window, int shift, int heads);
