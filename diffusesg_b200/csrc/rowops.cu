@@ -470,7 +470,7 @@ __global__ void node_proj_kernel(const float* __restrict__ node, const float* __
 // per pixel on the 1152 FMAs + weight loads of the conv and ran at 1.3 TB/s; this one needs ~35.
 // x0 = silu(shift + LN(conv1x1(input)) * (1 + scale))
 constexpr int kPE = 96;
-__global__ void __launch_bounds__(kRowThreads, 2)
+__global__ void __launch_bounds__(kRowThreads, 3)
 patch_embed_kernel(const float* __restrict__ adj, const float* __restrict__ sc_adj, const float* __restrict__ in_scale,
                    const uint8_t* __restrict__ flags, const float* __restrict__ rc, const float* __restrict__ w_adj,
                    const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -974,7 +974,7 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
   const long long pixels = perm != nullptr ? static_cast<long long>(batch) * side * side : static_cast<long long>(batch) * n * n;
   DSG_REQUIRE((self_cond ? 2 : 1) * c_e <= 16, "patch_embed: %d adjacency planes (max 16)", (self_cond ? 2 : 1) * c_e);
   long long blocks = (pixels / 16 + 7) / 8;  // one warp per 16 pixels per step
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 3) blocks = 148 * 3;  // persistent: three resident CTAs per SM, the weight-fragment prologue is paid once each
   patch_embed_kernel<<<static_cast<unsigned>(blocks), kRowThreads, 0, st>>>(adj, sc_adj, in_scale, flags, rc, w_adj,
                                                                            bias, gamma, beta, film + film_off, film_ld,
                                                                            cond_uniform, x0, pixels, n, c_e, self_cond,
