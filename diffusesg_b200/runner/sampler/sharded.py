@@ -73,8 +73,17 @@ def sample_sharded(sampler, model, node_flags_all: torch.Tensor, batch_size: int
             return t
         return torch.cat([t, t.new_zeros((longest - t.shape[0],) + tuple(t.shape[1:]))])
 
-    ga = gather_tensors(pad(adjs), 0, dev).cpu()
-    gn = gather_tensors(pad(nodes), 0, dev).cpu()
+    def to_host(t):
+        if not t.is_cuda:
+            return t
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)   # pinned: the gathered set is world x the local one
+        h.copy_(t, non_blocking=True)
+        return h
+
+    ga = to_host(gather_tensors(pad(adjs), 0, dev))
+    gn = to_host(gather_tensors(pad(nodes), 0, dev))
+    if ga.is_pinned() and torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
     keep = torch.cat([torch.arange(r * longest, r * longest + (shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0]))
                       for r in range(world)])
     return ga[keep], gn[keep]
