@@ -84,6 +84,8 @@ def sample_sharded(sampler, model, node_flags_all: torch.Tensor, batch_size: int
     gn = to_host(gather_tensors(pad(nodes), 0, dev))
     if ga.is_pinned() and torch.cuda.is_available():
         torch.cuda.current_stream().synchronize()
+    if total % world == 0:
+        return ga, gn            # equal shards: nothing was padded
     keep = torch.cat([torch.arange(r * longest, r * longest + (shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0]))
                       for r in range(world)])
     return ga[keep], gn[keep]
