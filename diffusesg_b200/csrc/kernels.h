@@ -152,13 +152,15 @@ int launch_window_attention(const bf16* qkv, const float* bias, const float* mas
 // holds (scale[C], shift[C]) at column film_off; sample s uses row (cond_uniform ? 0 : s).
 int launch_film_ln(const float* x_in, float* x_out, bf16* y, const float* film, int film_ld, int film_off,
                    int cond_uniform, const float* gamma, const float* beta, int batch, int tokens_per_sample,
-                   int C, cudaStream_t st);
+                   int C, cudaStream_t st, const int* src_rows = nullptr);
+// src_rows [rows]: output row r reads input row src_rows[r] (layout changes of the padding skipping; not in place)
 int launch_ln(const float* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, cudaStream_t st);
 // PatchMerging front half: gather the 2x2 neighbourhood (order (0,0),(1,0),(0,1),(1,1)), LN(4C) -> bf16
 int launch_merge_ln(const float* x, bf16* y, const float* gamma, const float* beta, int batch, int res, int C,
                     cudaStream_t st);
 // PatchBreakup input: y[m, 0:C] = bf16(x[m]), y[m, C:2C] = bf16(skip[m])
-int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st);
+int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st,
+                       const int* skip_rows = nullptr);   // skip_rows: row r reads skip row skip_rows[r]
 // PatchBreakup middle: LN(D) over each row of t [B*res*res, D], split into 4 chunks of D/4, chunk k goes to
 // pixel (2y + k%2, 2x + k/2) of the 2res x 2res grid, LN(D/4) -> bf16 [B*4*res*res, D/4]
 int launch_breakup_ln(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
@@ -198,9 +200,7 @@ bool row_compaction_supported(int C_merge, int D_breakup);
 int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const float* b1, const float* g2, const float* b2,
                               int batch, int res, int D, const int* tok0, const int* width, int sh, cudaStream_t st,
                               const int* src_perm = nullptr);
-// re-layout between the dense grid and the compact layouts (see relayout_kernel in rowops.cu)
-int launch_relayout(const float* src, float* dst, const int* dst_perm, int n_images, int dst_side, const int* src_tok0,
-                    const int* src_width, int src_side, int sh, long long phantom_tok, int C, cudaStream_t st);
+
 
 // ---------------------------------------------------------------------------------------------
 // fused EDM step kernels                                               (edm.cu)

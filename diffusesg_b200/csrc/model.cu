@@ -539,8 +539,10 @@ int gemm(dsg_model* m, const bf16* A, long long rows, const Weight& W, int epi, 
 // fuse_final_ln: this is the last block of the network; if it runs the fused tail, the tail also applies the final
 // LayerNorm and writes only Y (*fused_final_ln = true), and the caller skips the separate LayerNorm launch.
 int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_in, int batch, int cond_uniform,
-              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr, const Compact* cp = nullptr) {
+              cudaStream_t st, bool fuse_final_ln = false, bool* fused_final_ln = nullptr, const Compact* cp = nullptr,
+              const int* x_in_rows = nullptr) {
   // cp: compact layout - the activation holds cp->tokens(stage) tokens, bucket by bucket (see Compact)
+  // x_in_rows: x_in is in another layout; row r of this block reads x_in row x_in_rows[r] (x_in must not be w.X)
   const int C = b.dim;
   const int L = b.res * b.res;
   const long long rows = cp != nullptr ? cp->tokens(b.stage) : static_cast<long long>(batch) * L;
@@ -556,6 +558,7 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     }
     return &it->second;
   };
+  DSG_REQUIRE(x_in_rows == nullptr || (x_in != w.X && !block_head_supported(C)), "run_block: layout-changing input at C = %d", C);
   if (m->use_head && block_head_supported(C)) {
     // x = silu(FiLM(x)); qkv = LN1(x) W^T + b in one launch                (:238-243, :115)
     const CUtensorMap* ti = tmap0(x_in, -(C * 8 + EPI_RES_F32), [&](CUtensorMap* t) { return make_tmap_out(t, x_in, rows, C, EPI_RES_F32); });
@@ -570,7 +573,8 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     // x = silu(FiLM(x)); y = LN1(x)                                        (:238-243)
     DSG_TRY_P(PC_ROW, 0, rc * 10, launch_film_ln(x_in, w.X, w.Y, w.film, m->film_total, b.film_off, cond_uniform,
                                                  m->f32(p + ".norm1.weight"), m->f32(p + ".norm1.bias"),
-                                                 cp != nullptr ? 1 : batch, cp != nullptr ? static_cast<int>(rows) : L, C, st));
+                                                 cp != nullptr ? 1 : batch, cp != nullptr ? static_cast<int>(rows) : L, C, st,
+                                                 x_in_rows));
     DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
   }
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
@@ -845,7 +849,7 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   DSG_REQUIRE((reinterpret_cast<uintptr_t>(a->flags) & 3) == 0, "forward: node_flags must be 4-byte aligned");
   DSG_REQUIRE(static_cast<long long>(a->batch) * m->N * m->N < 2147483647LL, "forward: batch %d too large", a->batch);
   const int B = a->batch, N = m->N, E = m->E;
-  Workspace w = carve(m, B, a->n_cond, a->workspace);
+  Workspace w = carve(m, B, a->n_cond, a->workspace);   // X and T trade places at the layout changes of the padding skipping
   if (a->workspace == nullptr || a->workspace_bytes < w.bytes ||
       (reinterpret_cast<uintptr_t>(a->workspace) & (kAlign - 1)) != 0) {
     set_last_error("forward: workspace needs %zu bytes aligned to %zu (got %zu at %p)", w.bytes, kAlign,
@@ -903,7 +907,11 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
                        a->skip_phantom_tok0, m->skip_granule));
     cp = &cpl;
     S = m->skip_stages;
+    DSG_REQUIRE((a->skip2_tables != nullptr && a->skip2_buckets > 0) || a->skip_map_dense_from_c1 != nullptr,
+                "forward: the row map dense <- compact is missing");
     if (a->skip2_tables != nullptr && a->skip2_buckets > 0) {
+      DSG_REQUIRE(a->skip2_map_c2_from_c1 && a->skip2_map_dense_from_c2 && a->skip2_map_c2_from_dense,
+                  "forward: the level-2 row maps are missing");
       DSG_REQUIRE(m->skip2_granule > 0, "forward: this geometry has no second compaction level (skip2_tables given)");
       DSG_TRY(parse_plan(cpl2, a->skip2_tables, a->skip2_table_images, a->skip2_buckets, a->skip2_count, a->skip2_side,
                          a->skip2_phantom_tok0, m->skip2_granule));
@@ -943,17 +951,21 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
   for (int s = 0; s < m->nl; ++s) {
     const float* x_in = s == 0 ? w.X : w.skip[s - 1];
     for (int j = 0; j < m->cfg.depths[s]; ++j) {
-      const bool level2 = cp2 != nullptr && s == S && j == 0;   // first block of the first dense stage, on the second layout
-      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr,
-                        s < S ? cp : (level2 ? cp2 : nullptr)));
-      x_in = w.X;
-      if (level2) {
-        // compact (level 2) -> dense for the shifted blocks that follow; outside the kept corners: the phantom's token
-        const int res_s = N >> s, C_s = E << s;
-        DSG_TRY_P(PC_ROW, 0, static_cast<double>(B) * res_s * res_s * C_s * 8,
-                  launch_relayout(w.X, w.T, nullptr, B, res_s, cp2->tok0, cp2->width, 0, s, cp2->phantom_tok0 >> (2 * s), C_s, st));
-        x_in = w.T;
+      // The first block of the first dense stage reads the last compact stage's merge output (skip[S - 1], first compact
+      // layout) through a row map: into the second compact layout when there is one (level 2), else into the dense grid;
+      // after a level-2 block the next one reads ITS output through the map back to the dense grid.  A mapped read
+      // cannot be in place, so X and T trade places there.
+      const bool level2 = cp2 != nullptr && s == S && j == 0;
+      const int* rows_map = nullptr;
+      if (cp != nullptr && s == S && j == 0) rows_map = cp2 != nullptr ? a->skip2_map_c2_from_c1 : a->skip_map_dense_from_c1;
+      if (cp2 != nullptr && s == S && j == 1) {
+        rows_map = a->skip2_map_dense_from_c2;
+        x_in = w.X;
+        std::swap(w.X, w.T);
       }
+      DSG_TRY(run_block(m, m->blocks[m->down_first[s] + j], w, x_in, B, uniform, st, false, nullptr,
+                        s < S ? cp : (level2 ? cp2 : nullptr), rows_map));
+      x_in = w.X;
       DSG_STAGE_DONE();
     }
     if (s < m->nl - 1) {
@@ -971,21 +983,9 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
         if (s + 1 < S) {
           DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
         } else {
-          DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.T, st));
-          const long long ph = cp->phantom_tok0 >> (2 * (s + 1));
-          if (cp2 != nullptr) {
-            // ... into the second compact layout (the stage's first block and the decoder's skip read it there)
-            for (int k = 0; k < cp2->K; ++k) {
-              const int side_t = cp2->side[k] >> (s + 1);
-              DSG_TRY_P(PC_ROW, 0, static_cast<double>(cp2->count[k]) * side_t * side_t * 2 * g.C * 8,
-                        launch_relayout(w.T, w.skip[s] + cp2->at(k, s + 1) * 2 * g.C, cp2->perm + cp2->img0[k], cp2->count[k], side_t,
-                                        cp->tok0, cp->width, 0, s + 1, ph, 2 * g.C, st));
-            }
-          } else {
-            const double dense_el = static_cast<double>(B) * (g.res / 2) * (g.res / 2) * 2 * g.C;
-            DSG_TRY_P(PC_ROW, 0, dense_el * 8, launch_relayout(w.T, w.skip[s], nullptr, B, g.res / 2, cp->tok0, cp->width, 0, s + 1,
-                                                               ph, 2 * g.C, st));
-          }
+          // the merge output stays in the first compact layout; its readers (the next stage's first block, the decoder's
+          // skip concat) go through row maps, so no expansion pass is needed
+          DSG_TRY(gemm(m, w.Y, rows, g.reduction, EPI_F32, nullptr, nullptr, w.skip[s], st));
         }
       } else {
         const long long rows = static_cast<long long>(B) * (g.res / 2) * (g.res / 2);
@@ -1021,7 +1021,10 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
         // dense (or level-2 compact) -> compact: only the children inside each sample's kept corner are produced
         const long long rows_low = cp2 != nullptr ? cp2->tokens(s + 1) : static_cast<long long>(B) * bu.res * bu.res;
         const long long rows_hi = cp->tokens(s);
-        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6, launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st));
+        // the skip (the merge output of the way down) is still in the first compact layout: read it through the row map
+        DSG_TRY_P(PC_ROW, 0, static_cast<double>(rows_low) * bu.D * 6,
+                  launch_concat_bf16(w.X, w.skip[s], w.Y, rows_low, bu.D / 2, st,
+                                     cp2 != nullptr ? a->skip2_map_c2_from_c1 : a->skip_map_dense_from_c1));
         DSG_TRY(gemm(m, w.Y, rows_low, bu.pre, EPI_F32, nullptr, nullptr, w.T, st));
         if (cp2 != nullptr) {
           for (int k = 0; k < cp2->K; ++k) {
@@ -1054,19 +1057,18 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
       // the last block: the final LayerNorm rides on its fused tail (not while a test walks the stages: those read X)
       const bool last = u == m->nl - 1 && j == m->cfg.depths[s] - 1 && m->use_final_ln && g_stop_after < 0;
       const bool level2 = cp2 != nullptr && s == S && j == m->cfg.depths[s] - 1;   // last block of the first dense stage
+      const int* rows_map = nullptr;
       if (level2) {
-        // dense -> compact (level 2): only the kept corners feed this window-local block and the breakup after it
-        const int res_s = N >> s, C_s = E << s;
-        for (int k = 0; k < cp2->K; ++k) {
-          const int side_t = cp2->side[k] >> s;
-          DSG_TRY_P(PC_ROW, 0, static_cast<double>(cp2->count[k]) * side_t * side_t * C_s * 8,
-                    launch_relayout(w.X, w.T + cp2->at(k, s) * C_s, cp2->perm + cp2->img0[k], cp2->count[k], side_t, nullptr, nullptr,
-                                    res_s, 0, -1, C_s, st));
-        }
-        x_in = w.T;
+        // dense -> compact (level 2): only the kept corners feed this window-local block and the breakup after it; the
+        // block reads the dense X through the row map into the other buffer
+        rows_map = a->skip2_map_c2_from_dense;
+        x_in = w.X;
+        std::swap(w.X, w.T);
+      } else {
+        x_in = w.X;
       }
       DSG_TRY(run_block(m, m->blocks[m->up_first[u] + j], w, x_in, B, uniform, st, last, &final_ln_done,
-                        s < S ? cp : (level2 ? cp2 : nullptr)));
+                        s < S ? cp : (level2 ? cp2 : nullptr), rows_map));
       DSG_STAGE_DONE();
     }
   }

@@ -90,7 +90,8 @@ template <int NV, int LPR>
 __global__ void __launch_bounds__(kRowThreads)
 film_ln_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, bf16* __restrict__ y,
                const float* __restrict__ film, int film_ld, int cond_uniform, const float* __restrict__ gamma,
-               const float* __restrict__ beta, long long rows, int tokens_per_sample, int C) {
+               const float* __restrict__ beta, long long rows, int tokens_per_sample, int C,
+               const int* __restrict__ src_rows) {
   const int lane = threadIdx.x % LPR;
   long long row = static_cast<long long>(blockIdx.x) * (kRowThreads / LPR) + threadIdx.x / LPR;
   const bool valid = row < rows;  // surplus lane groups stay for the shuffles but never store
@@ -98,7 +99,9 @@ film_ln_kernel(const float* __restrict__ x_in, float* __restrict__ x_out, bf16* 
   const int b = cond_uniform ? 0 : static_cast<int>(row / tokens_per_sample);
   const float* sc = film + static_cast<size_t>(b) * film_ld;  // scale[C] then shift[C]
   Row<NV, LPR> r;
-  r.load(x_in + row * C, C, lane);
+  // src_rows: the input lives in another layout of the padding skipping (model.cu); output row `row` reads input row
+  // src_rows[row] - the layout change costs nothing beyond the 4-byte index (x_in must not alias x_out then)
+  r.load(x_in + (src_rows != nullptr ? static_cast<long long>(src_rows[row]) : row) * C, C, lane);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int e = (lane + LPR * i) * 4;
@@ -353,14 +356,16 @@ breakup_ln_q_kernel(const float* __restrict__ t, bf16* __restrict__ y, const flo
 // y[m] = bf16([x[m], skip[m]])                                                    (:753 torch.cat)
 __global__ void __launch_bounds__(256)
 concat_bf16_kernel(const float* __restrict__ x, const float* __restrict__ skip, bf16* __restrict__ y, long long rows,
-                   int C) {
+                   int C, const int* __restrict__ skip_rows) {
   const int c4 = C >> 2;
   const long long total = rows * 2 * c4;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = idx / (2 * c4);
     const int e = static_cast<int>(idx - row * (2 * c4));
-    const float* src = (e < c4) ? x + row * C + e * 4 : skip + row * C + (e - c4) * 4;
+    // skip_rows: the skip tensor lives in another layout of the padding skipping (see film_ln_kernel)
+    const long long srow = skip_rows != nullptr ? static_cast<long long>(skip_rows[row]) : row;
+    const float* src = (e < c4) ? x + row * C + e * 4 : skip + srow * C + (e - c4) * 4;
     const float4 v = *reinterpret_cast<const float4*>(src);
     *reinterpret_cast<uint2*>(y + row * (2 * C) + e * 4) = pack4_bf16(v.x, v.y, v.z, v.w);
   }
@@ -765,38 +770,6 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
   }
 }
 
-// Re-layout between the dense grid and the compact layouts of the padding skipping (model.cu), fp32 rows of 4 C4 floats.
-// Destination: n_images square images of dst_side tokens; image k shows sample dst_perm[k] (nullptr: sample k, i.e. the
-// dense grid; < 0: an all-padding image).  Source: sample b's kept corner of (src_width[b] >> sh) tokens starting at
-// token src_tok0[b] >> 2 sh (src_tok0 == nullptr: the dense grid of src_side tokens).  Destination tokens outside the
-// source corner take the phantom's token (phantom_tok < 0: zeros) - the value every token of an all-padding region
-// holds at this point of the network.
-__global__ void __launch_bounds__(256)
-relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ dst_perm, int n_images,
-                int dst_side, const int* __restrict__ src_tok0, const int* __restrict__ src_width, int src_side, int sh,
-                long long phantom_tok, int C4) {
-  const long long total = static_cast<long long>(n_images) * dst_side * dst_side * C4;
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  float4* d4 = reinterpret_cast<float4*>(dst);
-  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long tok = v / C4;
-    const int c4 = static_cast<int>(v - tok * C4);
-    const int img = static_cast<int>(tok / (dst_side * dst_side));
-    const int rem = static_cast<int>(tok - static_cast<long long>(img) * dst_side * dst_side);
-    const int r = rem / dst_side, x = rem - r * dst_side;
-    const int b = dst_perm != nullptr ? dst_perm[img] : img;
-    long long st = phantom_tok;
-    if (b >= 0) {
-      const int wc = src_tok0 != nullptr ? (src_width[b] >> sh) : src_side;
-      if (r < wc && x < wc)
-        st = (src_tok0 != nullptr ? (static_cast<long long>(src_tok0[b]) >> (2 * sh)) : static_cast<long long>(b) * src_side * src_side) +
-             static_cast<long long>(r) * wc + x;
-    }
-    d4[v] = st >= 0 ? s4[st * C4 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
 int nv_of(int C) {
   switch (C) {
     case 96: return 1;
@@ -842,10 +815,12 @@ inline unsigned row_grid(long long rows, int lpr = 32) {
 
 int launch_film_ln(const float* x_in, float* x_out, bf16* y, const float* film, int film_ld, int film_off,
                    int cond_uniform, const float* gamma, const float* beta, int batch, int tokens_per_sample, int C,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* src_rows) {
   const long long rows = static_cast<long long>(batch) * tokens_per_sample;
+  DSG_REQUIRE(src_rows == nullptr || x_in != x_out, "film_ln: a gathering launch cannot run in place");
   DSG_DISPATCH_ROW(C, (film_ln_kernel<NV, LPR><<<row_grid(rows, LPR), kRowThreads, 0, st>>>(
-                          x_in, x_out, y, film + film_off, film_ld, cond_uniform, gamma, beta, rows, tokens_per_sample, C)));
+                          x_in, x_out, y, film + film_off, film_ld, cond_uniform, gamma, beta, rows, tokens_per_sample, C,
+                          src_rows)));
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -891,24 +866,11 @@ int launch_breakup_ln_compact(const float* t, bf16* y, const float* g1, const fl
   return DSG_OK;
 }
 
-int launch_relayout(const float* src, float* dst, const int* dst_perm, int n_images, int dst_side, const int* src_tok0,
-                    const int* src_width, int src_side, int sh, long long phantom_tok, int C, cudaStream_t st) {
-  DSG_REQUIRE(C % 4 == 0 && n_images > 0 && dst_side > 0 && (src_tok0 == nullptr) == (src_width == nullptr),
-              "relayout: width %d, %d images of side %d", C, n_images, dst_side);
-  const long long total = static_cast<long long>(n_images) * dst_side * dst_side * (C / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  relayout_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, dst, dst_perm, n_images, dst_side, src_tok0, src_width,
-                                                                 src_side, sh, phantom_tok, C / 4);
-  DSG_LAUNCH_CHECK();
-  return DSG_OK;
-}
-
-int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st) {
+int launch_concat_bf16(const float* x, const float* skip, bf16* y, int64_t rows, int C, cudaStream_t st, const int* skip_rows) {
   DSG_REQUIRE(C % 4 == 0, "concat: width %d", C);
   const long long total = rows * 2 * (C / 4);
   const unsigned grid = static_cast<unsigned>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
-  concat_bf16_kernel<<<grid, 256, 0, st>>>(x, skip, y, rows, C);
+  concat_bf16_kernel<<<grid, 256, 0, st>>>(x, skip, y, rows, C, skip_rows);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

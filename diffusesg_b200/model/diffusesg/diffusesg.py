@@ -322,8 +322,60 @@ class SkipPlan:
 
     @staticmethod
     def table_len(batch: int) -> int:
-        """int32 entries of one level's table; the device buffer holds two levels back to back."""
+        """int32 entries of one level's table; the device buffer holds two levels back to back, then the row maps."""
         return (batch + SkipPlan.TABLE_EXTRA) + 2 * batch
+
+    @staticmethod
+    def buffer_len(batch: int, n: int, stages: int) -> int:
+        """int32 entries of the whole device buffer: two level tables + up to three row maps at the first dense stage
+        (dense grid: B res^2 tokens; a compact layout never holds more than (B + 1) res^2)."""
+        res = n >> stages
+        return 2 * SkipPlan.table_len(batch) + (3 * batch + 2) * res * res
+
+    @staticmethod
+    def corner_index(tok0, width, sh, b, res):
+        """[res, res] int64: index of token (r, x) of sample b in a compact layout at stage `sh`, -1 outside its corner."""
+        import numpy as np
+        wc = int(width[b]) >> sh
+        idx = np.full((res, res), -1, dtype=np.int64)
+        rr, xx = np.meshgrid(np.arange(wc), np.arange(wc), indexing="ij")
+        idx[:wc, :wc] = (int(tok0[b]) >> (2 * sh)) + rr * wc + xx
+        return idx
+
+    @staticmethod
+    def row_maps(table, counts, sides, phantom_tok0, batch, n, stages, level2=None):
+        """Row maps of include/dsg_b200.h (dsg_forward_args.skip_map_* / skip2_map_*), as int32 numpy arrays."""
+        import numpy as np
+        cap = batch + SkipPlan.TABLE_EXTRA
+        res = n >> stages
+        tok0, width = table[cap:cap + batch], table[cap + batch:cap + 2 * batch]
+        ph1 = phantom_tok0 >> (2 * stages)
+        c1 = np.stack([SkipPlan.corner_index(tok0, width, stages, b, res) for b in range(batch)])     # [B, res, res]
+        if level2 is None:
+            return dict(dense_from_c1=np.where(c1 >= 0, c1, ph1).astype(np.int32).reshape(-1))
+        table2, counts2, sides2, phantom2_tok0 = level2
+        tok2, width2 = table2[cap:cap + batch], table2[cap + batch:cap + 2 * batch]
+        perm2 = table2[:sum(counts2)]
+        ph2 = phantom2_tok0 >> (2 * stages)
+        c2 = np.stack([SkipPlan.corner_index(tok2, width2, stages, b, res) for b in range(batch)])    # [B, res, res]
+        dense_from_c2 = np.where(c2 >= 0, c2, ph2).astype(np.int32).reshape(-1)
+        c2_from_c1, c2_from_dense = [], []
+        img = 0
+        for cnt, side in zip(counts2, sides2):
+            st = side >> stages
+            for k in range(cnt):
+                b = int(perm2[img + k])
+                if b < 0:
+                    c2_from_c1.append(np.full(st * st, ph1, dtype=np.int64))
+                    c2_from_dense.append(np.zeros(st * st, dtype=np.int64))
+                else:
+                    sub = c1[b, :st, :st]
+                    c2_from_c1.append(np.where(sub >= 0, sub, ph1).reshape(-1))
+                    rr, xx = np.meshgrid(np.arange(st), np.arange(st), indexing="ij")
+                    c2_from_dense.append((b * res * res + rr * res + xx).reshape(-1))
+            img += cnt
+        return dict(c2_from_c1=np.concatenate(c2_from_c1).astype(np.int32), dense_from_c2=dense_from_c2,
+                    c2_from_dense=np.concatenate(c2_from_dense).astype(np.int32))
 
     @staticmethod
     def host_tables(flags_host: torch.Tensor, n: int, granule: int):
@@ -381,12 +433,21 @@ class SkipPlan:
             if res2 is not None and res2[4] <= min((b + 1) * n * n, (1.0 - min_saving) * b * n * n if min_saving > -1e8 else 1e30):
                 table2, counts2, sides2, phantom2, pixels2 = res2
                 level2 = (SkipPlan.table_len(b), counts2, sides2, phantom2, pixels2 / float(b * n * n))
-        t = torch.from_numpy(np.concatenate([table, table2]))
+        maps = SkipPlan.row_maps(table, counts, sides, phantom_tok0, b, n, stages,
+                                 (table2, level2[1], level2[2], level2[3]) if level2 else None)
+        parts, map_offsets, off = [table, table2], {}, 2 * SkipPlan.table_len(b)
+        for name, arr in maps.items():
+            map_offsets[name] = off
+            parts.append(arr)
+            off += len(arr)
+        t = torch.from_numpy(np.concatenate(parts))
         if out is None:
             out = t.to(nat.device)
         else:
-            out.copy_(t)
-        return SkipPlan(nat, b, out, b + SkipPlan.TABLE_EXTRA, counts, sides, phantom_tok0, pixels / float(b * n * n), level2)
+            out[:t.numel()].copy_(t)
+        plan = SkipPlan(nat, b, out, b + SkipPlan.TABLE_EXTRA, counts, sides, phantom_tok0, pixels / float(b * n * n), level2)
+        plan.map_offsets = map_offsets
+        return plan
 
 
 class _Skipping:
@@ -539,6 +600,14 @@ class _NativeModel:
             for k, (cnt, side) in enumerate(zip(skip.counts, skip.sides)):
                 a.skip_count[k], a.skip_side[k] = cnt, side
             a.skip_phantom_tok0 = skip.phantom_tok0
+            base = skip.tables.data_ptr()
+            mo = skip.map_offsets
+            if "dense_from_c1" in mo:
+                a.skip_map_dense_from_c1 = base + 4 * mo["dense_from_c1"]
+            else:
+                a.skip2_map_c2_from_c1 = base + 4 * mo["c2_from_c1"]
+                a.skip2_map_dense_from_c2 = base + 4 * mo["dense_from_c2"]
+                a.skip2_map_c2_from_dense = base + 4 * mo["c2_from_dense"]
             if skip.level2 is not None:
                 off2, counts2, sides2, phantom2, _ = skip.level2
                 a.skip2_tables = skip.tables.data_ptr() + 4 * off2

@@ -37,7 +37,9 @@ class DsgForwardArgs(C.Structure):
                 ("out_adj", C.c_void_p), ("out_node", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("skip_tables", C.c_void_p), ("skip_table_images", C.c_int32),
                 ("skip_buckets", C.c_int32), ("skip_count", C.c_int32 * 8), ("skip_side", C.c_int32 * 8),
-                ("skip_phantom_tok0", C.c_int64), ("skip2_tables", C.c_void_p), ("skip2_table_images", C.c_int32),
+                ("skip_phantom_tok0", C.c_int64), ("skip_map_dense_from_c1", C.c_void_p),
+                ("skip2_map_c2_from_c1", C.c_void_p), ("skip2_map_dense_from_c2", C.c_void_p),
+                ("skip2_map_c2_from_dense", C.c_void_p), ("skip2_tables", C.c_void_p), ("skip2_table_images", C.c_int32),
                 ("skip2_buckets", C.c_int32), ("skip2_count", C.c_int32 * 8), ("skip2_side", C.c_int32 * 8),
                 ("skip2_phantom_tok0", C.c_int64)]
 

@@ -61,7 +61,8 @@ class HeunGraphPlan:
         # padding skipping: the table is a fixed buffer (its address is part of the captured launches), refilled per
         # sampling run; the bucket geometry is baked into launch grids and TMA descriptors, so it keys the graphs
         from ...model.diffusesg.diffusesg import SkipPlan
-        self.skip_tables = torch.zeros(2 * SkipPlan.table_len(batch), dtype=torch.int32, device=device)   # two levels
+        self.skip_tables = torch.zeros(SkipPlan.buffer_len(batch, n, max(1, nat.skip_info()[0])), dtype=torch.int32,
+                                       device=device)   # two level tables + the row maps
         self.skip = None
         self.graphs: Dict[Tuple, torch.cuda.CUDAGraph] = {}
         self.pool = None

@@ -159,6 +159,17 @@ typedef struct dsg_forward_args {
   int32_t skip_count[8];      /* images per bucket, even */
   int32_t skip_side[8];       /* corner side of the bucket's images in pixels: a multiple of the granule */
   int64_t skip_phantom_tok0;  /* stage-0 token offset of the phantom image */
+  /* Row maps of the layout changes (int32 token indices at the first dense stage; a reader in layout Y of a tensor stored
+   * in layout X reads row map[r] - tokens outside X's kept corner point at X's phantom token):
+   *   skip_map_dense_from_c1 [B res^2]   without a second level: the dense grid reads the merge output of the last compact
+   *                                      stage (first dense block on the way down, skip concat on the way up)
+   *   skip2_map_c2_from_c1   [tokens of the second layout]   the same readers when there is a second level
+   *   skip2_map_dense_from_c2 [B res^2]  the shifted block after the level-2 block reads its output
+   *   skip2_map_c2_from_dense [tokens of the second layout]   the level-2 block on the way up reads the dense grid */
+  const int32_t* skip_map_dense_from_c1;
+  const int32_t* skip2_map_c2_from_c1;
+  const int32_t* skip2_map_dense_from_c2;
+  const int32_t* skip2_map_c2_from_dense;
   const int32_t* skip2_tables; /* second level (dsg_model_skip_info2), same layout; NULL: none */
   int32_t skip2_table_images;
   int32_t skip2_buckets;

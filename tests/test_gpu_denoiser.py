@@ -442,7 +442,8 @@ def _flags_with_counts(cfg, counts):
 
 
 @pytest.mark.parametrize("name,counts", [("vg", [2, 9, 16, 17, 33, 48, 62, 5]), ("tiny", [1, 4, 5, 8, 14, 3]),
-                                         ("coco", [2, 10, 11, 33, 21, 30])])
+                                         ("coco", [2, 10, 11, 33, 21, 30]), ("vg", [20]), ("vg", [40, 0]),
+                                         ("vg", [30] * 5), ("coco", [7])])
 def test_padding_skipping_matches_dense(name, counts):
     """the compact schedule (leading un-shifted stages computed only on each sample's corner that can hold
     valid nodes, the all-padding region represented by one phantom token) against the dense schedule on the same
@@ -454,16 +455,17 @@ def test_padding_skipping_matches_dense(name, counts):
     b = len(counts)
     adj, node, _, _, sc_adj, sc_node = synthetic_inputs(cfg, b, seed=11)
     flags = _flags_with_counts(cfg, counts)
-    flags[0, 0] = False                      # node flags need not be a prefix: holes, and ...
-    if counts[1] + 2 < cfg["img"]:
-        flags[1, counts[1] + 1] = True       # ... a valid node beyond a gap (the kept corner follows the LAST valid node)
+    if b > 2:
+        flags[0, 0] = False                      # node flags need not be a prefix: holes, and ...
+        if counts[1] + 2 < cfg["img"]:
+            flags[1, counts[1] + 1] = True       # ... a valid node beyond a gap (the kept corner follows the LAST valid node)
     pair = (flags[:, None, :, None] & flags[:, None, None, :]).float()
     adj, sc_adj = adj.abs().clamp_min(0.1) * adj.sign() * pair, sc_adj * pair   # re-mask for these flags
     node, sc_node = node * flags[:, :, None], sc_node * flags[:, :, None]
     stages, granule = net._native(DEV).skip_info()
     assert stages >= 1, (name, stages, granule)
-    plan = net.make_skip_plan(flags.to(DEV))
-    assert plan is not None and plan.kept_fraction < 1.0
+    plan = net.make_skip_plan(flags.to(DEV), force=b <= 2)   # tiny batches: the phantom may outweigh what is skipped
+    assert plan is not None and (plan.kept_fraction < 1.0 or b <= 2)
     sig = torch.full((1,), 1.5, device=DEV).expand(b)       # one shared noise level, as in sampling
     args = [t.to(DEV) for t in (adj, node, flags)]
     with torch.no_grad():

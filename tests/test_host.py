@@ -331,3 +331,46 @@ def test_step_params_row_layout():
     assert dt.itemsize == 48
     for name, _ in native.DsgEdmStepParams._fields_:
         assert dt.fields[name][1] == getattr(native.DsgEdmStepParams, name).offset, name
+
+
+def test_skip_plan_row_maps_compose():
+    """The row maps between the dense grid and the two compact layouts (dsg_forward_args.skip_map_* / skip2_map_*): reading
+    a tensor through the maps must reproduce it inside every kept corner and deliver the phantom's token outside."""
+    import numpy as np
+    from diffusesg_b200.model.diffusesg.diffusesg import SkipPlan
+    n, g1, g2, stages = 64, 16, 32, 2
+    counts = [2, 9, 16, 17, 33, 48, 62, 5, 64, 31]
+    b, res = len(counts), n >> stages
+    flags = torch.arange(n)[None, :] < torch.tensor(counts)[:, None]
+    t1, c1, s1, ph1, _ = SkipPlan.host_tables(flags, n, g1)
+    t2, c2, s2, ph2, px2 = SkipPlan.host_tables(flags, n, g2)
+    cap = b + SkipPlan.TABLE_EXTRA
+    maps = SkipPlan.row_maps(t1, c1, s1, ph1, b, n, stages, (t2, c2, s2, ph2))
+    only1 = SkipPlan.row_maps(t1, c1, s1, ph1, b, n, stages)["dense_from_c1"]
+    w1, w2 = t1[cap + b:cap + 2 * b] >> stages, t2[cap + b:cap + 2 * b] >> stages
+    n1 = sum(c * (s >> stages) ** 2 for c, s in zip(c1, s1))
+    n2 = px2 >> (2 * stages)
+    assert len(maps["c2_from_c1"]) == len(maps["c2_from_dense"]) == n2 and len(maps["dense_from_c2"]) == b * res * res
+    assert maps["c2_from_c1"].max() < n1 and maps["dense_from_c2"].max() < n2 and maps["c2_from_dense"].max() < b * res * res
+    # a tensor in the first compact layout: value = 1000 b + 16 r + x inside the corners, -7 at the phantom, -1 elsewhere
+    x1 = np.full(n1, -1.0)
+    dense_ref = np.full((b, res, res), -7.0)
+    for k in range(b):
+        idx = SkipPlan.corner_index(t1[cap:cap + b], t1[cap + b:cap + 2 * b], stages, k, res)
+        rr, xx = np.nonzero(idx >= 0)
+        x1[idx[rr, xx]] = 1000 * k + 16 * rr + xx
+        dense_ref[k, rr, xx] = 1000 * k + 16 * rr + xx
+    phantom1 = ph1 >> (2 * stages)
+    x1[phantom1:phantom1 + (g1 >> stages) ** 2] = -7.0
+    assert np.array_equal(x1[only1].reshape(b, res, res), dense_ref)                      # level 1 only: dense <- c1
+    x2 = x1[maps["c2_from_c1"]]                                                            # c2 <- c1
+    dense = x2[maps["dense_from_c2"]].reshape(b, res, res)                                  # dense <- c2
+    for k in range(b):                                                                      # the level-2 corner survives, -7 outside
+        assert np.array_equal(dense[k, :w2[k], :w2[k]], dense_ref[k, :w2[k], :w2[k]])
+        outside = np.ones((res, res), bool)
+        outside[:w2[k], :w2[k]] = False
+        assert (dense[k][outside] == -7.0).all()
+        assert w1[k] <= w2[k]
+    back = dense_ref.reshape(-1)[maps["c2_from_dense"]]                                     # c2 <- dense
+    keep = x2 != -7.0
+    assert np.array_equal(back[keep], x2[keep])
