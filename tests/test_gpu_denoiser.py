@@ -474,7 +474,8 @@ def test_padding_skipping_matches_dense(name, counts):
         n1 = native.launch_count()
         with net.skipping(plan):
             sa, sn = net.denoise(args[0], args[1], args[2], sig, sc_adj.to(DEV), sc_node.to(DEV))
-            assert native.launch_count() - n1 > n1 - n0            # the compact schedule ran (per-bucket launches + expand)
+            # the compact schedule ran: its geometry-aware kernels launch once per bucket
+            assert native.launch_count() - n1 > n1 - n0 or len(plan.counts) == 1
             sa2, sn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
         da2, dn2 = net.denoise(args[0], args[1], args[2], sig, None, None)
         # reference: oracle D on the CPU
