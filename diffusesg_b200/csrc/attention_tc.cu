@@ -36,11 +36,20 @@ constexpr int kTcBiasPitch = 68;             // floats per bias row: 16-byte ali
 constexpr int kTcSlotCols = 128;             // tensor-memory columns per item: S 128; P aliases [0, 64), O aliases [64, 96)
 constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + kTcGroups * 8192 + 64 * kTcBiasPitch * 4 + 512;
 
+constexpr int kTcMaxGroups = 4;
+// Up to four stacks of square grids in one launch (the buckets of the padding skipping, model.cu: each has its own
+// resolution and therefore its own pair of tensor maps); an ordinary call is one group.
+struct TcMaps {
+  CUtensorMap q[kTcMaxGroups], o[kTcMaxGroups];
+};
 struct TcParams {
   const float* bias;  // [heads, 64, 64]
-  int heads, res, nwx, nW;
-  int pairs;          // window pairs = B * nW / 2
+  int heads, res, nwx, nW;   // geometry of group 0 (the only one of an ordinary call; SHIFTED runs one group)
+  int pairs;          // window pairs over all groups
   int shift;          // 0, or 4 (SHIFTED instantiation)
+  int n_groups;
+  int win_prefix[kTcMaxGroups + 1];   // group g holds windows [win_prefix[g], win_prefix[g + 1]) (even counts)
+  int g_res[kTcMaxGroups], g_nwx[kTcMaxGroups];
 };
 
 DSG_DEVICE uint64_t desc_sw64_kmajor(uint32_t smem_addr) {  // [rows x 32] bf16, 64-byte swizzle, 8-row groups 512 B apart
@@ -92,8 +101,7 @@ DSG_DEVICE void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c
 // launcher takes this instantiation only if the attn_mask buffer holds the reference's values.
 template <bool SHIFTED>
 __global__ void __launch_bounds__(kTcThreads, 1)
-window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __grid_constant__ CUtensorMap tmOut,
-                           const TcParams p) {
+window_attention_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem;
@@ -119,8 +127,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
   const int C = p.heads * 32;
 
   if (warp == kLoadWarp && lane == 0) {
-    tma_prefetch_desc(&tmQkv);
-    tma_prefetch_desc(&tmOut);
+    for (int gi = 0; gi < p.n_groups; ++gi) {
+      tma_prefetch_desc(&maps.q[gi]);
+      tma_prefetch_desc(&maps.o[gi]);
+    }
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
     for (int g = 0; g < kTcGroups; ++g) {
       mbar_init(&s_full[g], 1);
@@ -147,11 +157,17 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // window gw -> TMA coordinates (token x, token row) of its top-left token in the [B res, res] grid
-  auto win_coords = [&](int gw, int& cx, int& cy) {
-    const int b = gw / p.nW, win = gw - b * p.nW;
-    const int wy = win / p.nwx, wx = win - wy * p.nwx;
-    cx = wx * 8;
-    cy = b * p.res + wy * 8;
+  // (returns the window's group: which pair of tensor maps it is addressed through)
+  auto win_coords = [&](int gw, int& cx, int& cy) -> int {
+    int gi = 0;
+#pragma unroll
+    for (int t = 1; t < kTcMaxGroups; ++t) gi += (t < p.n_groups && gw >= p.win_prefix[t]) ? 1 : 0;
+    const int local = gw - p.win_prefix[gi];
+    const int nwx = p.g_nwx[gi];
+    const int row = local / nwx;          // window row over the whole stack: 8 * row = b * res + wy * 8
+    cx = (local - row * nwx) * 8;
+    cy = row * 8;
+    return gi;
   };
 
   // SHIFTED: sub-box (by, bx) = slot of window gw -> TMA coordinates of its 4 x 4 token box
@@ -178,7 +194,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
         const int part = lane >> 3, w = (lane >> 2) & 1, slot = lane & 3;
         int cx, cy;
         sub_coords(2 * pair + w, slot, cx, cy);
-        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096 + slot * 1024, &tmQkv, &stage_full[st],
+        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096 + slot * 1024, &maps.q[0], &stage_full[st],
                     part * C + h * 32, cx, cy);
       }
       __syncwarp();
@@ -196,8 +212,8 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
       if (lane < 6) {
         const int w = lane / 3, part = lane - 3 * w;
         int cx, cy;
-        win_coords(2 * pair + w, cx, cy);
-        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096, &tmQkv, &stage_full[st], part * C + h * 32, cx, cy);
+        const int gi = win_coords(2 * pair + w, cx, cy);
+        tma_load_3d(sStage + st * kTcStageBytes + part * 8192 + w * 4096, &maps.q[gi], &stage_full[st], part * C + h * 32, cx, cy);
       }
       __syncwarp();
     }
@@ -248,10 +264,10 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const __gr
         int cx, cy;
         if (SHIFTED) {
           sub_coords(2 * pair + (lane >> 2), lane & 3, cx, cy);
-          tma_store_3d(&tmOut, sOut + g * 8192 + lane * 1024, h * 32, cx, cy);
+          tma_store_3d(&maps.o[0], sOut + g * 8192 + lane * 1024, h * 32, cx, cy);
         } else {
-          win_coords(2 * pair + lane, cx, cy);
-          tma_store_3d(&tmOut, sOut + g * 8192 + lane * 4096, h * 32, cx, cy);
+          const int gi = win_coords(2 * pair + lane, cx, cy);
+          tma_store_3d(&maps.o[gi], sOut + g * 8192 + lane * 4096, h * 32, cx, cy);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1069,46 +1085,69 @@ bool window_attention_tc_supported(int batch, int res, int window, int shift, in
   return windows % 2 == 0 && windows >= 2;
 }
 
-static int launch_tc_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int shift, int heads,
-                          cudaStream_t st);
+static int launch_tc_groups(const bf16* qkv, const float* bias, bf16* out, int n_groups, const int* counts, const int* res,
+                            const long long* tok_off, int shift, int heads, cudaStream_t st);
 
 int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
                                cudaStream_t st) {
   DSG_REQUIRE(window_attention_tc_supported(batch, res, 8, shift, heads), "attention_tc: unsupported shape");
-  return launch_tc_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, shift, heads, st);
+  const long long zero = 0;
+  return launch_tc_groups(qkv, bias, out, 1, &batch, &res, &zero, shift, heads, st);
 }
 
-// img_rows = B res token rows of `res` tokens (B stacked res x res grids)
-static int launch_tc_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int shift, int heads,
-                          cudaStream_t st) {
-  const long long batch = img_rows;  // only ever used as batch * res below
+// Several stacks of square grids in one launch: group g = counts[g] grids of res[g] x res[g] tokens starting at token
+// tok_off[g] of qkv / out (un-shifted 8 x 8 windows; every group holds an even number of windows)
+int launch_window_attention_tc_groups(const bf16* qkv, const float* bias, bf16* out, int n_groups, const int* counts,
+                                      const int* res, const long long* tok_off, int heads, cudaStream_t st) {
+  DSG_REQUIRE(n_groups >= 1 && n_groups <= kTcMaxGroups && heads >= 1 && heads <= 74, "attention_tc (groups): %d groups", n_groups);
+  for (int g = 0; g < n_groups; ++g)
+    DSG_REQUIRE(counts[g] > 0 && res[g] % 8 == 0 && (static_cast<long long>(counts[g]) * (res[g] / 8) * (res[g] / 8)) % 2 == 0,
+                "attention_tc (groups): group %d holds %d grids of %d tokens", g, counts[g], res[g]);
+  return launch_tc_groups(qkv, bias, out, n_groups, counts, res, tok_off, 0, heads, st);
+}
+
+static int launch_tc_groups(const bf16* qkv, const float* bias, bf16* out, int n_groups, const int* counts, const int* res,
+                            const long long* tok_off, int shift, int heads, cudaStream_t st) {
   const int C = heads * 32;
   const int box = shift ? 4 : 8;  // shifted windows are gathered as four 4 x 4-token sub-boxes
-  CUtensorMap tq, to;
-  // [B res (token row), res (token column), channels]: a window is an 8 x 8 box of tokens, a head slice 32 channels
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch), 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
-    return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch), 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
-    return rc;
+  TcMaps maps;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  long long windows = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    // [count res (token row), res (token column), channels]: a window is an 8 x 8 box of tokens, a head slice 32 channels
+    const long long rows = static_cast<long long>(counts[g]) * res[g];
+    if (int rc = make_tmap_3d_bf16(&maps.q[g], qkv + tok_off[g] * 3 * C, 3 * C, res[g], rows, 3LL * C * 2, 3LL * C * 2 * res[g], 32, box, box))
+      return rc;
+    if (int rc = make_tmap_3d_bf16(&maps.o[g], out + tok_off[g] * C, C, res[g], rows, 1LL * C * 2, 1LL * C * 2 * res[g], 32, box, box))
+      return rc;
+    p.win_prefix[g] = static_cast<int>(windows);
+    p.g_res[g] = res[g];
+    p.g_nwx[g] = res[g] / 8;
+    windows += static_cast<long long>(counts[g]) * (res[g] / 8) * (res[g] / 8);
+  }
+  DSG_REQUIRE(windows < 2147483647LL, "attention_tc: too many windows");
+  for (int g = n_groups; g <= kTcMaxGroups; ++g) p.win_prefix[g] = static_cast<int>(windows);
+  for (int g = n_groups; g < kTcMaxGroups; ++g) { maps.q[g] = maps.q[0]; maps.o[g] = maps.o[0]; p.g_res[g] = res[0]; p.g_nwx[g] = res[0] / 8; }
   static PerDeviceOnce configured;
   if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   }
   const int sms = device_sm_count();
-  TcParams p;
   p.bias = bias;
   p.heads = heads;
-  p.res = res;
-  p.nwx = res / 8;
+  p.res = res[0];
+  p.nwx = res[0] / 8;
   p.nW = p.nwx * p.nwx;
-  p.pairs = static_cast<int>((img_rows / 8) * p.nwx / 2);
+  p.n_groups = n_groups;
+  p.pairs = static_cast<int>(windows / 2);
   int per_head = sms / heads;
   if (per_head > p.pairs) per_head = p.pairs;
   if (per_head < 1) per_head = 1;
   p.shift = shift;
-  if (shift) window_attention_tc_kernel<true><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
-  else window_attention_tc_kernel<false><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(tq, to, p);
+  if (shift) window_attention_tc_kernel<true><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(maps, p);
+  else window_attention_tc_kernel<false><<<per_head * heads, kTcThreads, kTcSmemBytes, st>>>(maps, p);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

@@ -126,6 +126,10 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, int64_t d0, int64_t d1
 bool window_attention_tc_supported(int batch, int res, int window, int shift, int heads);
 int launch_window_attention_tc(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int shift, int heads,
                                cudaStream_t st);
+// several stacks of square grids in one launch (the buckets of the padding skipping): group g = counts[g] grids of
+// res[g] x res[g] tokens starting at token tok_off[g]; un-shifted windows, an even number of windows per group, <= 4 groups
+int launch_window_attention_tc_groups(const bf16* qkv, const float* bias, bf16* out, int n_groups, const int* counts,
+                                      const int* res, const long long* tok_off, int heads, cudaStream_t st);
 // quad-box tcgen05 version (one window per tile): even windows up to 10 x 10, shift 0 or window / 2; the SW-MSA mask
 // is generated in the kernel, so a shifted block may only take it when check_mask_canonical() found the model's
 // attn_mask buffer equal to the reference's construction (synchronous; called at model finalisation).

@@ -578,7 +578,15 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
     DSG_TRY(gemm(m, w.Y, rows, b.qkv, EPI_BF16, m->at<float>(b.qkv_bias_off), nullptr, w.QKV, st));
   }
   const float* mask = b.shift > 0 ? m->f32(p + ".attn_mask") : nullptr;
-  if (cp != nullptr) {
+  if (cp != nullptr && b.window == 8 && cp->K <= 4) {
+    // 8 x 8 windows: all buckets in ONE launch (a tensor-map pair per bucket); per-bucket launches of the persistent
+    // kernel each paid its prologue and pipeline ramp for a handful of windows per CTA
+    int res_k[4];
+    long long tok_k[4];
+    for (int k = 0; k < cp->K; ++k) { res_k[k] = cp->side[k] >> b.stage; tok_k[k] = cp->at(k, b.stage); }
+    DSG_TRY_P(PC_ATTN, 4.0 * rc * b.window * b.window, rc * 8,
+              launch_window_attention_tc_groups(w.QKV, m->at<float>(b.attn_bias_off), w.ATT, cp->K, cp->count, res_k, tok_k, b.heads, st));
+  } else if (cp != nullptr) {
     for (int k = 0; k < cp->K; ++k) {   // one (count, side) tensor per bucket
       const long long t0 = cp->at(k, b.stage), tk = cp->at(k + 1, b.stage) - t0;
       DSG_TRY_P(PC_ATTN, 4.0 * tk * C * b.window * b.window, static_cast<double>(tk) * C * 8,
