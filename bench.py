@@ -442,6 +442,17 @@ def run_native(args, cfg, rank, local_rank, world):
             "clocks": clocks.summary()}
     if strong is not None:
         line["strong_scaling"] = strong
+    # how the launch sequence is organised (all three are on by default; each is bit-identical to its plain counterpart:
+    # tests/test_gpu_denoiser.py::test_sampler_graphs_are_bit_identical, ::test_padding_skipping_matches_dense)
+    plan = getattr(getattr(sampler, "_plan", None), "skip", None)
+    line["schedule"] = {
+        "cuda_graphs": bool(sampler.use_graphs), "fused_philox_noise": bool(sampler.fused_noise),
+        "padding_skipping": None if plan is None else {
+            "kept_fraction_of_compact_stage_pixels": round(plan.kept_fraction, 4),
+            "level2_kept_fraction": round(plan.level2[4], 4) if plan.level2 else None,
+            "note": "un-shifted stages run only on each sample's corner that can hold valid nodes (DESIGN.md 3.3); outputs "
+                    "identical to the dense schedule; `roofline` counts the flops actually executed, "
+                    "`denoiser_tflops_whole_step` the reference's dense flops (an effective rate)"}}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_rate(cfg, args.cpu_batch, args.cpu_steps, 1, 0)
         line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
