@@ -1235,25 +1235,16 @@ int launch_window_attention_w16(const bf16* qkv, const float* bias, bf16* out, i
   return DSG_OK;
 }
 
-static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window, int shift,
-                            int heads, cudaStream_t st);
-
 int launch_window_attention_quad(const bf16* qkv, const float* bias, bf16* out, int batch, int res, int window, int shift,
                                  int heads, cudaStream_t st) {
   DSG_REQUIRE(window_attention_quad_supported(batch, res, window, shift, heads), "attention_quad: unsupported shape");
-  return launch_quad_rows(qkv, bias, out, static_cast<long long>(batch) * res, res, window, shift, heads, st);
-}
-
-static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long long img_rows, int res, int window, int shift,
-                            int heads, cudaStream_t st) {
-  const long long batch = img_rows;  // only ever used as batch * res below
   const int C = heads * 32;
   const int hw = window / 2;
   const int box = shift ? hw : window;  // shifted: four sub-boxes per window; un-shifted: the whole window
   CUtensorMap tq, to;
-  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch), 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&tq, qkv, 3 * C, res, static_cast<int64_t>(batch) * res, 3LL * C * 2, 3LL * C * 2 * res, 32, box, box))
     return rc;
-  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch), 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
+  if (int rc = make_tmap_3d_bf16(&to, out, C, res, static_cast<int64_t>(batch) * res, 1LL * C * 2, 1LL * C * 2 * res, 32, box, box))
     return rc;
   const int sms = device_sm_count();
   QdParams p;
@@ -1266,7 +1257,7 @@ static int launch_quad_rows(const bf16* qkv, const float* bias, bf16* out, long 
   p.nwx = res / window;
   p.nW = p.nwx * p.nwx;
   p.T = window * window;
-  const long long items = (img_rows / window) * p.nwx;
+  const long long items = static_cast<long long>(batch) * p.nW;
   DSG_REQUIRE(items < 2147483647LL, "attention_quad: too many windows");
   p.items = static_cast<int>(items);
   int per_head = sms / heads;

@@ -494,7 +494,7 @@ def test_padding_skipping_matches_dense(name, counts):
 
 @pytest.mark.parametrize("name", ["vg", "coco"])
 def test_padding_skipping_precond_matches_golden(name, golden_dir):
-    """NodeAdjPrecond.forward of the unmodified reference (golden) against the native call with padded-row skipping
+    """NodeAdjPrecond.forward of the unmodified reference (golden) against the native call with padding skipping
     active: same tolerance as the dense path (test_precond_matches_golden)."""
     cfg = CONFIGS[name]
     g = np.load(os.path.join(golden_dir, f"precond_{name}.npz"))
