@@ -195,7 +195,9 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
 int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip, const float* c_out,
                      float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st, const int* tok0 = nullptr,
-                     const int* width = nullptr);
+                     const int* width = nullptr, float* scratch = nullptr);
+// scratch [B n, 128] fp32: with it (embed 96, c_n <= 32) the head runs as two kernels - masked row sums, then the MLP
+// for 32 rows per CTA with the weights in shared memory; without it, the single-kernel version
 // tok0 / width: compact layout - `rep` holds sample b as a width[b]^2 corner starting at token tok0[b]
 
 // padding-skipping helpers: the breakup writing the compact layout from a dense input, and the compact -> dense

@@ -1110,7 +1110,8 @@ int dsg_denoiser_forward(dsg_model* m, const dsg_forward_args* a, dsg_stream_t s
                            m->at<float>(m->node_w1t_off), m->f32("readout_node_mlp.fc1.bias"),
                            m->at<float>(m->node_w2t_off), m->f32("readout_node_mlp.fc2.bias"),
                            a->mode == 1 ? a->node : nullptr, c_skip, c_out, a->out_node, B, N, m->cfg.c_n, E, st,
-                           S > 0 ? cp->tok0 : nullptr, S > 0 ? cp->width : nullptr));
+                           S > 0 ? cp->tok0 : nullptr, S > 0 ? cp->width : nullptr,
+                           2 * E >= 128 ? w.rc : nullptr));   // rc (row / column planes of the embedding) is dead by now
   return DSG_OK;
 }
 

@@ -770,6 +770,154 @@ node_head_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// node read-out in two kernels (embed = 96): (1) masked row sums, one warp per row (b, i), 16-byte loads, masked
+// columns never loaded; (2) the three small matrix products for 32 rows per CTA with the weights staged in shared
+// memory once per CTA (the single-kernel version above read 77 KB of weights from L2 per 8 rows and ran at 1.1 TB/s).
+// pooled [B n, 128]: columns 0..95 = mean over j of the masked features (divided by n, :813), column 96 = valid / n.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPoolPitch = 128;
+__global__ void __launch_bounds__(256)
+node_pool_kernel(const bf16* __restrict__ rep, const uint8_t* __restrict__ flags, float* __restrict__ pooled, long long rows,
+                 int n, const int* __restrict__ tok0, const int* __restrict__ width) {
+  constexpr int E = 96;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bi = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (bi >= rows) return;
+  float* out = pooled + bi * kPoolPitch;
+  if (flags[bi] == 0) {   // masked node: its output row is zero whatever the features are
+    for (int c = lane; c <= E; c += 32) out[c] = 0.f;
+    return;
+  }
+  const int b = static_cast<int>(bi / n);
+  const uint8_t* fj = flags + static_cast<size_t>(b) * n;
+  const int nj = tok0 != nullptr ? width[b] : n;
+  const size_t row_tok = tok0 != nullptr ? static_cast<size_t>(tok0[b]) + static_cast<size_t>(bi - static_cast<long long>(b) * n) * nj
+                                         : static_cast<size_t>(bi) * n;
+  const int tsub = lane / 12, c8 = lane - 12 * tsub;   // lanes 0..23: token parity, 8-channel chunk
+  // the row's column mask as two 32-bit words (n <= 64): the data loads below depend on registers only, not on a flag
+  // load per token, so the compiler keeps eight of them in flight
+  const unsigned m_lo = __ballot_sync(0xffffffffu, lane < nj && fj[lane] != 0);
+  const unsigned m_hi = __ballot_sync(0xffffffffu, lane + 32 < nj && fj[lane + 32] != 0);
+  const unsigned long long mask = (static_cast<unsigned long long>(m_hi) << 32) | m_lo;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (lane < 24) {
+    const bf16* p = rep + row_tok * E + 8 * c8;
+#pragma unroll 8
+    for (int j = tsub; j < nj; j += 2) {
+      if (((mask >> j) & 1ull) == 0) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(p + static_cast<size_t>(j) * E);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[2 * k] += __low2float(h[k]); acc[2 * k + 1] += __high2float(h[k]); }
+    }
+  }
+  const int cnt = __popcll(mask);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], 12);
+  if (lane < 12) {
+    const float inv = 1.0f / n;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[8 * c8 + k] = acc[k] * inv;
+  }
+  if (lane == 0) out[E] = static_cast<float>(cnt) / n;
+}
+
+constexpr int kMlpRows = 32;
+// activations are kept k-major in shared memory (vT[k][row]): for one k the 16 rows of a thread are four broadcast
+// 16-byte loads, so a k step costs 5 shared-memory loads per 16 FMAs (row-major: 17)
+__global__ void __launch_bounds__(192)
+node_mlp_kernel(const float* __restrict__ pooled, const uint8_t* __restrict__ flags, const float* __restrict__ fold_t,
+                const float* __restrict__ fold_b, const float* __restrict__ w1t, const float* __restrict__ b1,
+                const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ x_node,
+                const float* __restrict__ c_skip, const float* __restrict__ c_out, float* __restrict__ out_node, long long rows,
+                int n, int c_n) {
+  constexpr int E = 96, R = kMlpRows, RH = R / 2;
+  extern __shared__ __align__(16) float sm[];
+  float* sW2 = sm;                    // [E][c_n]; the two E x E matrices are read through L1 (one coalesced load per 16 FMAs)
+  float* vaT = sW2 + E * 32;          // [E + 1][R]: pooled features (row E: valid fraction), later the hidden layer
+  float* vbT = vaT + (E + 1) * R;     // [E][R]
+  __shared__ int any_live;
+  const long long row0 = static_cast<long long>(blockIdx.x) * R;
+  if (threadIdx.x == 0) any_live = 0;
+  __syncthreads();
+  if (threadIdx.x < R && row0 + threadIdx.x < rows && flags[row0 + threadIdx.x] != 0) any_live = 1;
+  __syncthreads();
+  if (!any_live) {   // a block of masked nodes: zeros, no weights needed
+    for (int idx = threadIdx.x; idx < R * c_n; idx += blockDim.x) {
+      const long long bi = row0 + idx / c_n;
+      if (bi < rows) out_node[bi * c_n + idx % c_n] = 0.f;
+    }
+    return;
+  }
+  {
+    // pooled features: thread = (row, 16-float segment), six segments per row + the valid fraction
+    const int pr = threadIdx.x / 6, ps = threadIdx.x - 6 * pr;
+    float4 pv[4];
+    const bool prow = row0 + pr < rows;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      pv[q] = prow ? *reinterpret_cast<const float4*>(pooled + (row0 + pr) * kPoolPitch + 16 * ps + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      vaT[(16 * ps + 4 * q) * R + pr] = pv[q].x; vaT[(16 * ps + 4 * q + 1) * R + pr] = pv[q].y;
+      vaT[(16 * ps + 4 * q + 2) * R + pr] = pv[q].z; vaT[(16 * ps + 4 * q + 3) * R + pr] = pv[q].w;
+    }
+    if (threadIdx.x < R) vaT[E * R + threadIdx.x] = row0 + threadIdx.x < rows ? pooled[(row0 + threadIdx.x) * kPoolPitch + E] : 0.f;
+  }
+  for (int i = threadIdx.x; i < E * c_n; i += blockDim.x) sW2[i] = w2t[i];
+  __syncthreads();
+  const int e = threadIdx.x % E, rg = threadIdx.x / E;   // output column, half of the rows
+  auto matvec = [&](const float* W, const float* vT, float (&acc)[RH]) {
+#pragma unroll 8
+    for (int k = 0; k < E; ++k) {
+      const float w = __ldg(W + k * E + e);
+      const float4* v4 = reinterpret_cast<const float4*>(vT + k * R + rg * RH);
+#pragma unroll
+      for (int q = 0; q < RH / 4; ++q) {
+        const float4 v = v4[q];
+        acc[4 * q] = fmaf(w, v.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
+      }
+    }
+  };
+  {
+    float acc[RH];
+    const float fb = fold_b[e];
+#pragma unroll
+    for (int r = 0; r < RH; ++r) acc[r] = fb * vaT[E * R + rg * RH + r];
+    matvec(fold_t, vaT, acc);
+#pragma unroll
+    for (int r = 0; r < RH; ++r) vbT[e * R + rg * RH + r] = acc[r];
+  }
+  __syncthreads();
+  {
+    float acc[RH];
+    const float bb = b1[e];
+#pragma unroll
+    for (int r = 0; r < RH; ++r) acc[r] = bb;
+    matvec(w1t, vbT, acc);
+#pragma unroll
+    for (int r = 0; r < RH; ++r) vaT[e * R + rg * RH + r] = gelu_erf(acc[r]);   // vaT's features were consumed before the barrier above
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < R * c_n; idx += blockDim.x) {
+    const int r = idx / c_n, c = idx - r * c_n;
+    const long long bi = row0 + r;
+    if (bi >= rows) continue;
+    const size_t o = static_cast<size_t>(bi) * c_n + c;
+    if (flags[bi] == 0) { out_node[o] = 0.f; continue; }
+    float sum = b2[c];
+#pragma unroll 16
+    for (int k = 0; k < E; ++k) sum = fmaf(sW2[k * c_n + c], vaT[k * R + r], sum);
+    const int b = static_cast<int>(bi / n);
+    if (x_node != nullptr) sum = __fadd_rn(__fmul_rn(c_skip[b], x_node[o]), __fmul_rn(c_out[b], sum));
+    out_node[o] = sum;
+  }
+}
+
 int nv_of(int C) {
   switch (C) {
     case 96: return 1;
@@ -948,9 +1096,22 @@ int launch_patch_embed(const float* adj, const float* sc_adj, const float* in_sc
 int launch_node_head(const bf16* rep, const uint8_t* flags, const float* fold_t, const float* fold_b, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, const float* x_node, const float* c_skip,
                      const float* c_out, float* out_node, int batch, int n, int c_n, int embed, cudaStream_t st,
-                     const int* tok0, const int* width) {
+                     const int* tok0, const int* width, float* scratch) {
   DSG_REQUIRE(embed <= 128 && embed % 4 == 0 && c_n <= 128, "node_head: embed %d c_n %d", embed, c_n);
   const long long rows = static_cast<long long>(batch) * n;
+  if (embed == 96 && c_n <= 32 && n <= 64 && scratch != nullptr) {
+    // two kernels: masked row sums, then the MLP for 32 rows per CTA with the weights in shared memory
+    node_pool_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(rep, flags, scratch, rows, n, tok0, width);
+    DSG_LAUNCH_CHECK();
+    constexpr int smem = (96 * 32 + (2 * 96 + 1) * kMlpRows) * 4;
+    static PerDeviceOnce configured;
+    if (configured.first())
+      DSG_CUDA_CHECK(cudaFuncSetAttribute(node_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    node_mlp_kernel<<<static_cast<unsigned>((rows + kMlpRows - 1) / kMlpRows), 192, smem, st>>>(
+        scratch, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, rows, n, c_n);
+    DSG_LAUNCH_CHECK();
+    return DSG_OK;
+  }
   node_head_kernel<<<static_cast<unsigned>((rows + kHeadRows - 1) / kHeadRows), 256, 0, st>>>(
       rep, flags, fold_t, fold_b, w1t, b1, w2t, b2, x_node, c_skip, c_out, out_node, rows, n, c_n, embed, tok0, width);
   DSG_LAUNCH_CHECK();
