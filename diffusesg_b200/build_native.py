@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdsg_b200.so")
-SOURCES = ["gemm.cu", "mlp.cu", "blocktail.cu", "blockhead.cu", "projln.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "edm.cu", "train.cu", "pack.cu", "model.cu"]
+SOURCES = ["gemm.cu", "mlp.cu", "blocktail.cu", "blockhead.cu", "projln.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "edm.cu", "train.cu", "backward.cu", "pack.cu", "model.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "dsg_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

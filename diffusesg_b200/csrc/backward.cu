@@ -1,0 +1,1035 @@
+// Training step of the denoiser: the row-wise forward kernels that keep what the backward pass needs,
+// and every backward kernel that is not a GEMM.  The GEMMs of the backward pass (dgrad: dX = dY . W, wgrad:
+// dW = dY^T . X contracted over the tokens with split-K) run on gemm_kernel (gemm.cu) - the wgrad operands are the
+// token-major transposes written by transpose_colsum_kernel below.
+//
+// Reference: loss.backward() of runner/trainer/trainer_node_adj.py:171-178 through model/diffusesg/diffusesg.py
+// (LayerNorm :243/:275, FiLM + SiLU :238-240/:574-576, nn.GELU :15, PatchMerging :314-335, PatchBreakup :374-403,
+// WindowAttention :108-139, the read-out heads :806-825) and model/precond/precond.py:100-105.
+//
+// All kernels are HBM-bound row kernels (one warp per token row, 16-byte accesses) except window_attention_bwd_kernel,
+// which is a CUDA-core fp32 kernel (five T x T x 32 products per window-head from shared memory).
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dsg {
+namespace {
+
+typedef __nv_bfloat16 bf16_t;
+
+DSG_DEVICE float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+DSG_DEVICE void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+DSG_DEVICE void st4_bf16(bf16_t* p, float4 v) {
+  uint2 w;
+  w.x = pack_bf16x2(v.x, v.y);
+  w.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = w;
+}
+DSG_DEVICE float4 ld4_bf16(const bf16_t* p) {
+  const uint2 w = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+DSG_DEVICE float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm forward (training form): y = (x - mean) * rstd * gamma + beta, one warp per row, two exact passes for
+// the statistics (the row stays in L1).  Writes bf16 (GEMM operand) and / or fp32.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              bf16_t* __restrict__ y16, float* __restrict__ y32, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * 8;
+  const int nv = C >> 2;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < M; row += warps) {
+    const float* xr = x + row * C;
+    float s = 0.f;
+    for (int v = lane; v < nv; v += 32) { const float4 a = ld4(xr + 4 * v); s += (a.x + a.y) + (a.z + a.w); }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld4(xr + 4 * v);
+      const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld4(xr + 4 * v), g = ld4(gamma + 4 * v), b = ld4(beta + 4 * v);
+      const float4 o = make_float4((a.x - mean) * rstd * g.x + b.x, (a.y - mean) * rstd * g.y + b.y,
+                                   (a.z - mean) * rstd * g.z + b.z, (a.w - mean) * rstd * g.w + b.w);
+      if (y16 != nullptr) st4_bf16(y16 + row * C + 4 * v, o);
+      if (y32 != nullptr) st4(y32 + row * C + 4 * v, o);
+    }
+  }
+}
+
+// LayerNorm backward: dx = rstd (g - mean(g) - xhat mean(g xhat)) with g = dy gamma, statistics recomputed from x;
+// dx (+= dx_add when given: the gradient arriving over the residual connection).  dgamma / dbeta: per-CTA
+// shared-memory accumulators, flushed with one atomicAdd per channel per CTA.
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+              const float* dx_add, float* dx, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, long long M, int C) {
+  extern __shared__ float sacc[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = static_cast<long long>(gridDim.x) * 8;
+  const int nv = C >> 2;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < M; row += warps) {
+    const float* xr = x + row * C;
+    const float* dr = dy + row * C;
+    float s = 0.f;
+    for (int v = lane; v < nv; v += 32) { const float4 a = ld4(xr + 4 * v); s += (a.x + a.y) + (a.z + a.w); }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld4(xr + 4 * v);
+      const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
+    float m1 = 0.f, m2 = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld4(xr + 4 * v), d = ld4(dr + 4 * v), g = ld4(gamma + 4 * v);
+      const float h0 = (a.x - mean) * rstd, h1 = (a.y - mean) * rstd, h2 = (a.z - mean) * rstd, h3 = (a.w - mean) * rstd;
+      const float g0 = d.x * g.x, g1 = d.y * g.y, g2 = d.z * g.z, g3 = d.w * g.w;
+      m1 += (g0 + g1) + (g2 + g3);
+      m2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+      atomicAdd(&sacc[4 * v], d.x * h0); atomicAdd(&sacc[4 * v + 1], d.y * h1);
+      atomicAdd(&sacc[4 * v + 2], d.z * h2); atomicAdd(&sacc[4 * v + 3], d.w * h3);
+      atomicAdd(&sacc[C + 4 * v], d.x); atomicAdd(&sacc[C + 4 * v + 1], d.y);
+      atomicAdd(&sacc[C + 4 * v + 2], d.z); atomicAdd(&sacc[C + 4 * v + 3], d.w);
+    }
+    m1 = warp_sum(m1) / C;
+    m2 = warp_sum(m2) / C;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld4(xr + 4 * v), d = ld4(dr + 4 * v), g = ld4(gamma + 4 * v);
+      float4 o = make_float4(rstd * (d.x * g.x - m1 - (a.x - mean) * rstd * m2), rstd * (d.y * g.y - m1 - (a.y - mean) * rstd * m2),
+                             rstd * (d.z * g.z - m1 - (a.z - mean) * rstd * m2), rstd * (d.w * g.w - m1 - (a.w - mean) * rstd * m2));
+      if (dx_add != nullptr) {
+        const float4 e = ld4(dx_add + row * C + 4 * v);
+        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      }
+      st4(dx + row * C + 4 * v, o);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(&dgamma[i], sacc[i]);
+    atomicAdd(&dbeta[i], sacc[C + i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FiLM + SiLU: out = silu(shift_b + v (1 + scale_b)), (scale, shift) = film[b, off : off + C], [off + C : off + 2C]
+// (diffusesg.py:238-240, :574-576).  One CTA per (sample, chunk of 32 tokens).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFilmTokens = 32;
+__global__ void __launch_bounds__(256)
+film_silu_fwd_kernel(const float* __restrict__ v, const float* __restrict__ film, int ldf, int off,
+                     float* __restrict__ out, int L, int C) {
+  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
+  const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kFilmTokens;
+  const int nt = min(kFilmTokens, L - t0);
+  const float* fs = film + static_cast<size_t>(b) * ldf + off;
+  const size_t base = (static_cast<size_t>(b) * L + t0) * C;
+  const int nv = C >> 2;
+  for (int i = threadIdx.x; i < nt * nv; i += 256) {
+    const int c = (i % nv) * 4;
+    const size_t o = base + static_cast<size_t>(i / nv) * C + c;
+    const float4 a = ld4(v + o), sc = ld4(fs + c), sh = ld4(fs + C + c);
+    const float u0 = fmaf(a.x, sc.x + 1.f, sh.x), u1 = fmaf(a.y, sc.y + 1.f, sh.y), u2 = fmaf(a.z, sc.z + 1.f, sh.z),
+                u3 = fmaf(a.w, sc.w + 1.f, sh.w);
+    st4(out + o, make_float4(u0 * sigmoid_f(u0), u1 * sigmoid_f(u1), u2 * sigmoid_f(u2), u3 * sigmoid_f(u3)));
+  }
+}
+
+// du = dout silu'(u); dv = du (1 + scale); dscale[b, c] += sum_tokens du v; dshift[b, c] += sum_tokens du
+__global__ void __launch_bounds__(256)
+film_silu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ v, const float* __restrict__ film, int ldf,
+                     int off, float* __restrict__ dv, float* __restrict__ dfilm, int L, int C) {
+  extern __shared__ float sacc[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
+  const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kFilmTokens;
+  const int nt = min(kFilmTokens, L - t0);
+  const float* fs = film + static_cast<size_t>(b) * ldf + off;
+  const size_t base = (static_cast<size_t>(b) * L + t0) * C;
+  const int nv = C >> 2;
+  for (int i = threadIdx.x; i < nt * nv; i += 256) {
+    const int c = (i % nv) * 4;
+    const size_t o = base + static_cast<size_t>(i / nv) * C + c;
+    const float4 a = ld4(v + o), sc = ld4(fs + c), sh = ld4(fs + C + c), g = ld4(dout + o);
+    const float av[4] = {a.x, a.y, a.z, a.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w},
+                gv[4] = {g.x, g.y, g.z, g.w};
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float u = fmaf(av[k], scv[k] + 1.f, shv[k]);
+      const float sg = sigmoid_f(u);
+      const float du = gv[k] * sg * (1.f + u * (1.f - sg));
+      r[k] = du * (scv[k] + 1.f);
+      atomicAdd(&sacc[c + k], du * av[k]);
+      atomicAdd(&sacc[C + c + k], du);
+    }
+    st4(dv + o, make_float4(r[0], r[1], r[2], r[3]));
+  }
+  __syncthreads();
+  float* df = dfilm + static_cast<size_t>(b) * ldf + off;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&df[i], sacc[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// erf GELU (nn.GELU default), exact form for the training path: forward on the pre-activation kept for backward
+// ---------------------------------------------------------------------------------------------------------
+DSG_DEVICE float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+DSG_DEVICE float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const bf16_t* __restrict__ pre, bf16_t* __restrict__ out, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 a = ld4_bf16(pre + 4 * i);
+    st4_bf16(out + 4 * i, make_float4(gelu_exact(a.x), gelu_exact(a.y), gelu_exact(a.z), gelu_exact(a.w)));
+  }
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const bf16_t* __restrict__ dh, const bf16_t* __restrict__ pre, bf16_t* __restrict__ dpre, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 a = ld4_bf16(pre + 4 * i), g = ld4_bf16(dh + 4 * i);
+    st4_bf16(dpre + 4 * i, make_float4(g.x * gelu_grad(a.x), g.y * gelu_grad(a.y), g.z * gelu_grad(a.z), g.w * gelu_grad(a.w)));
+  }
+}
+__global__ void __launch_bounds__(256)
+gelu_f32_kernel(const float* __restrict__ pre, const float* __restrict__ dout, float* __restrict__ out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256)
+    out[i] = dout == nullptr ? gelu_exact(pre[i]) : dout[i] * gelu_grad(pre[i]);
+}
+// out[c] += sum over rows of src[r, c] (bias gradients of the small fp32 layers)
+__global__ void __launch_bounds__(256)
+colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ out, long long M, int C, int rows_per_cta) {
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += src[r * C + c];
+    atomicAdd(&out[c], s);
+  }
+}
+// EDM preconditioning coefficients (runner/objectives/edm.py:122-126), sigma_data = 0.5: out = [c_skip | c_out | c_in | c_noise]
+__global__ void precond_coef_kernel(const float* __restrict__ sigmas, float* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float s = sigmas[b], sd = 0.5f;
+  const float q = s * s + sd * sd;
+  out[b] = sd * sd / q;
+  out[B + b] = s * sd / sqrtf(q);
+  out[2 * B + b] = 1.0f / sqrtf(q);
+  out[3 * B + b] = logf(s) / 4.0f;
+}
+__global__ void __launch_bounds__(256)
+silu_fwd_kernel(const float* __restrict__ pre, float* __restrict__ out, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float u = pre[i];
+    out[i] = u * sigmoid_f(u);
+  }
+}
+__global__ void __launch_bounds__(256)
+silu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre, float* __restrict__ dpre, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const float u = pre[i], sg = sigmoid_f(u);
+    dpre[i] = dout[i] * sg * (1.f + u * (1.f - sg));
+  }
+}
+// y += x (gradient accumulation where a tensor has two consumers)
+__global__ void __launch_bounds__(256)
+add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 a = ld4(y + 4 * i), b = ld4(x + 4 * i);
+    st4(y + 4 * i, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Token-major transpose for the weight-gradient GEMMs: src [M, C] (fp32 or bf16) -> dst [C, M] bf16, optionally the
+// straight bf16 cast [M, C] (the dgrad operand), the column sums (bias gradient, atomicAdd) and a scale on the first
+// `scale_cols` columns of dst / colsum (the q rows of qkv run pre-scaled by head_dim^-1/2).
+// A CTA owns 32 columns x kTrRows rows: one atomicAdd per column per CTA.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTrRows = 1024;
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_colsum_kernel(const T* __restrict__ src, bf16_t* __restrict__ dst, bf16_t* __restrict__ cast,
+                        float* __restrict__ colsum, long long M, long long Mp, int C, int scale_cols, float scale) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int c0 = blockIdx.x * 32;
+  const long long r_begin = static_cast<long long>(blockIdx.y) * kTrRows;
+  const long long r_end = min(Mp, r_begin + kTrRows);   // rows [M, Mp) are the zero padding of the destination pitch
+  const float fac = (c0 + tx < scale_cols) ? scale : 1.f;
+  float csum = 0.f;  // column c0 + tx, rows ty + 8 k
+  for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long r = r0 + ty + 8 * k;
+      float val = 0.f;
+      if (r < M && c0 + tx < C) {
+        val = static_cast<float>(src[r * C + c0 + tx]);
+        if (cast != nullptr) cast[r * C + c0 + tx] = __float2bfloat16_rn(val);
+        val *= fac;
+      }
+      csum += val;
+      tile[ty + 8 * k][tx] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = ty + 8 * k;   // column inside the tile
+      const long long r = r0 + tx;
+      if (r < r_end && c0 + c < C) dst[static_cast<long long>(c0 + c) * Mp + r] = __float2bfloat16_rn(tile[tx][c]);
+    }
+    __syncthreads();
+  }
+  if (colsum != nullptr) {
+    tile[ty][tx] = csum;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += tile[k][tx];
+      atomicAdd(&colsum[c0 + tx], s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2 x 2 space <-> depth: fine [B, 2H, 2W, C] <-> coarse [B, H, W, 4, C], chunk k = dy + 2 dx (PatchMerging's
+// x0..x3 order, diffusesg.py:325-329, and PatchBreakup's scatter, :394-397: the same map).  fp32, pure permutation.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shuffle2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int H, int W, int C, int to_coarse) {
+  const int nv = C >> 2;
+  const long long total = static_cast<long long>(B) * H * W * 4 * nv;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int v = static_cast<int>(i % nv);
+    long long t = i / nv;
+    const int k = static_cast<int>(t & 3);
+    t >>= 2;
+    const int xw = static_cast<int>(t % W);
+    t /= W;
+    const int yh = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    const long long coarse = i * 4;  // ((((b H + y) W + x) 4 + k) C + 4 v
+    const long long fine = ((static_cast<long long>(b) * 2 * H + 2 * yh + (k & 1)) * 2 * W + 2 * xw + (k >> 1)) * C + 4 * v;
+    if (to_coarse) st4(dst + coarse, ld4(src + fine));
+    else st4(dst + fine, ld4(src + coarse));
+  }
+}
+
+// dst[:, dcol : dcol + n] (=, +=) src[:, scol : scol + n]; src fp32, dst fp32 or bf16 (skip concat and its split)
+__global__ void __launch_bounds__(256)
+copy_cols_kernel(const float* __restrict__ src, int lds, int scol, void* __restrict__ dst, int ldd, int dcol, int ncols,
+                 long long M, int dst_bf16, int accumulate) {
+  const int nv = ncols >> 2;
+  const long long total = M * nv;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long r = i / nv;
+    const int c = static_cast<int>(i - r * nv) * 4;
+    float4 a = ld4(src + r * lds + scol + c);
+    if (dst_bf16) {
+      st4_bf16(static_cast<bf16_t*>(dst) + r * ldd + dcol + c, a);
+    } else {
+      float* d = static_cast<float*>(dst) + r * ldd + dcol + c;
+      if (accumulate) { const float4 e = ld4(d); a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w; }
+      st4(d, a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Input grid of the patch embedding as a GEMM operand: row (b, i, j) = [sc_adj(Ce) | c_in adj(Ce) | node planes of i:
+// sc_node, c_in node (2 Cn) | node planes of j (2 Cn) | zero pad to `ld`], node planes masked by flag_i & flag_j
+// (diffusesg.py:791-802; c_in of model/precond/precond.py:100).  Without self-conditioning the sc blocks are absent.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_input_kernel(const float* __restrict__ adj, const float* __restrict__ node, const float* __restrict__ sc_adj,
+                   const float* __restrict__ sc_node, const uint8_t* __restrict__ flags, const float* __restrict__ c_in,
+                   bf16_t* __restrict__ out, int B, int n, int c_e, int c_n, int self_cond, int ld) {
+  const long long total = static_cast<long long>(B) * n * n;
+  const int nn = n * n;
+  for (long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; pix < total; pix += static_cast<long long>(gridDim.x) * 256) {
+    const int b = static_cast<int>(pix / nn), ij = static_cast<int>(pix - static_cast<long long>(b) * nn);
+    const int i = ij / n, j = ij - i * n;
+    const float ci = c_in != nullptr ? c_in[b] : 1.f;
+    const bool ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+    bf16_t* o = out + pix * ld;
+    int k = 0;
+    if (self_cond) {
+      for (int c = 0; c < c_e; ++c) o[k++] = __float2bfloat16_rn(sc_adj != nullptr ? sc_adj[(static_cast<size_t>(b) * c_e + c) * nn + ij] : 0.f);
+    }
+    for (int c = 0; c < c_e; ++c) o[k++] = __float2bfloat16_rn(ci * adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
+    for (int side = 0; side < 2; ++side) {
+      const size_t nrow = (static_cast<size_t>(b) * n + (side == 0 ? i : j)) * c_n;
+      if (self_cond)
+        for (int c = 0; c < c_n; ++c) o[k++] = __float2bfloat16_rn(ok && sc_node != nullptr ? sc_node[nrow + c] : 0.f);
+      for (int c = 0; c < c_n; ++c) o[k++] = __float2bfloat16_rn(ok ? ci * node[nrow + c] : 0.f);
+    }
+    for (; k < ld; ++k) o[k] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Read-out heads: token-major head outputs -> the reference's output tensors (mask, optional EDM output
+// preconditioning D = c_skip x + c_out F), and back.
+//   adj: tok [B n n, ce] -> out [B, ce, n, n] masked by flag_i & flag_j       (diffusesg.py:809, :825; precond.py:102-105)
+//   node: tok [B n, cn]  -> out [B, n, cn]   masked by flag_i                 (:818-822)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adj_out_kernel(const float* __restrict__ tok, const uint8_t* __restrict__ flags, const float* __restrict__ x_adj,
+               const float* __restrict__ c_skip, const float* __restrict__ c_out, float* __restrict__ out, int B, int n,
+               int c_e, int backward) {
+  // forward: out = mask (c_skip x + c_out tok); backward: tok_grad (written to `out` [B n n, ce]) = mask c_out * grad (`tok` [B, ce, n, n])
+  const int nn = n * n;
+  const long long total = static_cast<long long>(B) * nn;
+  for (long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; pix < total; pix += static_cast<long long>(gridDim.x) * 256) {
+    const int b = static_cast<int>(pix / nn), ij = static_cast<int>(pix - static_cast<long long>(b) * nn);
+    const int i = ij / n, j = ij - i * n;
+    const bool ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
+    const float co = c_out != nullptr ? c_out[b] : 1.f;
+    for (int c = 0; c < c_e; ++c) {
+      const size_t plane = (static_cast<size_t>(b) * c_e + c) * nn + ij;
+      if (!backward) {
+        float val = co * tok[pix * c_e + c];
+        if (x_adj != nullptr) val += c_skip[b] * x_adj[plane];
+        out[plane] = ok ? val : 0.f;
+      } else {
+        out[pix * c_e + c] = ok ? co * tok[plane] : 0.f;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+node_out_kernel(const float* __restrict__ tok, const uint8_t* __restrict__ flags, const float* __restrict__ x_node,
+                const float* __restrict__ c_skip, const float* __restrict__ c_out, float* __restrict__ out, int B, int n,
+                int c_n, int backward) {
+  const long long total = static_cast<long long>(B) * n * c_n;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long bi = i / c_n;
+    const int b = static_cast<int>(bi / n);
+    const bool ok = flags[bi] != 0;
+    const float co = c_out != nullptr ? c_out[b] : 1.f;
+    if (!backward) {
+      float val = co * tok[i];
+      if (x_node != nullptr) val += c_skip[b] * x_node[i];
+      out[i] = ok ? val : 0.f;
+    } else {
+      out[i] = ok ? co * tok[i] : 0.f;
+    }
+  }
+}
+// masked mean over the last pair axis: pooled[b, i, :] = flag_i / n * sum_j flag_j rep[b, i, j, :]  (:812-813);
+// backward: drep[b, i, j, :] += flag_i flag_j / n * dpooled[b, i, :]
+__global__ void __launch_bounds__(256)
+node_pool_train_kernel(const float* __restrict__ rep, const uint8_t* __restrict__ flags, float* __restrict__ pooled, int B,
+                       int n, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(B) * n;
+  const long long bi = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (bi >= rows) return;
+  const int b = static_cast<int>(bi / n);
+  const bool live = flags[bi] != 0;
+  for (int c = lane; c < C; c += 32) {
+    float s = 0.f;
+    if (live)
+      for (int j = 0; j < n; ++j)
+        if (flags[b * n + j] != 0) s += rep[(bi * n + j) * C + c];
+    pooled[bi * C + c] = s / n;
+  }
+}
+__global__ void __launch_bounds__(256)
+node_pool_bwd_kernel(const float* __restrict__ dpooled, const uint8_t* __restrict__ flags, float* __restrict__ drep, int B,
+                     int n, int C) {
+  const int nv = C >> 2;
+  const long long total = static_cast<long long>(B) * n * n * nv;
+  const float inv = 1.0f / n;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int v = static_cast<int>(i % nv);
+    const long long pix = i / nv;
+    const long long bi = pix / n;
+    const int j = static_cast<int>(pix - bi * n);
+    const int b = static_cast<int>(bi / n);
+    if (flags[bi] == 0 || flags[b * n + j] == 0) continue;
+    const float4 g = ld4(dpooled + bi * C + 4 * v);
+    float* d = drep + pix * C + 4 * v;
+    const float4 e = ld4(d);
+    st4(d, make_float4(e.x + inv * g.x, e.y + inv * g.y, e.z + inv * g.z, e.w + inv * g.w));
+  }
+}
+
+// sinusoidal noise embedding (PositionalEmbedding, diffusesg.py:507-513): [cos(x f_k) | sin(x f_k)], f_k = 10000^(-k / half)
+__global__ void posemb_kernel(const float* __restrict__ labels, float* __restrict__ out, int B, int embed) {
+  const int half = embed / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i - b * half;
+    const float f = powf(1.0f / 10000.0f, static_cast<float>(k) / static_cast<float>(half));
+    const float a = labels[b] * f;
+    out[b * embed + k] = cosf(a);
+    out[b * embed + half + k] = sinf(a);
+  }
+}
+
+// relative-position bias: bias[h, t, u] = table[index[t, u], h] (:121-124) and its transpose-scatter
+__global__ void bias_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ index, float* __restrict__ bias,
+                                   int heads, int TT, int backward, float* __restrict__ dtable) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < heads * TT; i += gridDim.x * blockDim.x) {
+    const int h = i / TT, tu = i - h * TT;
+    const long long idx = index[tu];
+    if (!backward) bias[i] = table[idx * heads + h];
+    else atomicAdd(&dtable[idx * heads + h], bias[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Small fp32 GEMM with arbitrary strides and an accumulate / split-K mode, for the matrices far too small or too
+// oddly shaped for the tcgen05 kernel: the noise-embedding MLP and the FiLM generators (batch rows), the node
+// read-out MLP ([B n] rows), the c_e / c_n wide output layers and all their gradients.
+//   C[m, n] (+)= sum_k A(m, k) B(k, n) (+ bias[n]),  A(m, k) = A[m sam + k sak] (fp32 or bf16), B(k, n) = B[k sbk + n sbn]
+// 64 x 64 tile, 16-deep k steps, 256 threads x (4 x 4); gridDim.z = K slices combined with atomicAdd.
+// ---------------------------------------------------------------------------------------------------------
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const TA* __restrict__ A, long long sam, long long sak, const TB* __restrict__ Bm, long long sbk, long long sbn,
+             const float* __restrict__ bias, float* __restrict__ Cm, long long ldc, int M, int N, int K, int k_per,
+             int accumulate) {
+  __shared__ float sA[16][65], sB[16][65];
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int k_begin = blockIdx.z * k_per, k_end = min(K, k_begin + k_per);
+  const int tn = threadIdx.x & 15, tm = threadIdx.x >> 4;   // thread tile: rows tm + 16 r, cols tn + 16 c
+  float acc[4][4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      // A tile: choose the faster-running index to follow the smaller stride
+      int kk, mm;
+      if (sak <= sam) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+      const int m = m0 + mm, k = k0 + kk;
+      sA[kk][mm] = (m < M && k < k_end) ? static_cast<float>(A[m * sam + k * sak]) : 0.f;
+      int kb, nb;
+      if (sbk <= sbn) { kb = i & 15; nb = i >> 4; } else { nb = i & 63; kb = i >> 6; }
+      const int n = n0 + nb, k2 = k0 + kb;
+      sB[kb][nb] = (n < N && k2 < k_end) ? static_cast<float>(Bm[k2 * sbk + n * sbn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = sA[kk][tm + 16 * r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = sB[kk][tn + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = m0 + tm + 16 * r;
+    if (m >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + tn + 16 * c;
+      if (n >= N) continue;
+      float val = acc[r][c];
+      if (bias != nullptr && blockIdx.z == 0) val += bias[n];
+      float* o = Cm + static_cast<long long>(m) * ldc + n;
+      if (gridDim.z > 1 || accumulate) atomicAdd(o, val);
+      else *o = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Window attention backward (WindowAttention.forward, diffusesg.py:108-139, with roll / window_partition /
+// window_reverse :28-57, :248-267 as index arithmetic).  One CTA = one head and a contiguous chunk of (sample, window)
+// pairs; per window-head, all in fp32 from shared memory:
+//   S = Q K^T + bias (+ mask);  P = softmax(S);  dV = P^T dO;  dP = dO V^T;  dS = P o (dP - rowsum(dP o P));
+//   dQ = dS K;  dK = dS^T Q;  dbias += dS   (accumulated per CTA in shared memory, one atomicAdd per entry per CTA)
+// q arrives pre-scaled (the qkv weight's q rows carry head_dim^-1/2), so dQ is the gradient w.r.t. the scaled q.
+// Matrices live in shared memory with odd pitches; a thread owns a strided 4 x 4 micro-tile, so both the straight and
+// the transposed operand reads are bank-conflict free.
+// ---------------------------------------------------------------------------------------------------------
+template <int NC, typename F>
+DSG_DEVICE void smem_mm(const float* __restrict__ A, int ai, int ak, const float* __restrict__ Bm, int bk, int bj, int I,
+                        int J, int Kd, F&& store) {
+  // thread tile: rows it + r TI (r < 4), columns jt + c TJ (c < NC)
+  const int TI = (I + 3) >> 2, TJ = (J + NC - 1) / NC;
+  for (int t = threadIdx.x; t < TI * TJ; t += blockDim.x) {
+    const int it = t / TJ, jt = t - it * TJ;
+    int ia[4], ja[NC];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ia[r] = min(it + r * TI, I - 1) * ai;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) ja[c] = min(jt + c * TJ, J - 1) * bj;
+    float acc[4][NC] = {};
+    for (int k = 0; k < Kd; ++k) {
+      float a[4], b[NC];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = A[ia[r] + k * ak];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) b[c] = Bm[ja[c] + k * bk];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int i = it + r * TI, j = jt + c * TJ;
+        if (i < I && j < J) store(i, j, acc[r][c]);
+      }
+  }
+}
+
+constexpr int kHd = 32, kHdP = 33;
+__global__ void __launch_bounds__(256)
+window_attention_bwd_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ datt, const float* __restrict__ bias,
+                            const float* __restrict__ mask, bf16_t* __restrict__ dqkv, float* __restrict__ dbias, int batch,
+                            int res, int w, int shift, int heads, int items_per_cta) {
+  extern __shared__ float sm[];
+  const int T = w * w, TP = T + 1, C = heads * kHd;
+  float* sQ = sm;
+  float* sK = sQ + T * kHdP;
+  float* sV = sK + T * kHdP;
+  float* sDO = sV + T * kHdP;
+  float* sP = sDO + T * kHdP;     // S, then P
+  float* sD = sP + T * TP;        // dP, then dS
+  float* sAcc = sD + T * TP;      // dbias accumulator [T][T] (pitch T)
+  int* sTok = reinterpret_cast<int*>(sAcc + T * T);  // global token row of window token t
+  const int h = blockIdx.y;
+  const int nw = res / w, nW = nw * nw;
+  const int total = batch * nW;
+  const int item0 = blockIdx.x * items_per_cta, item1 = min(total, item0 + items_per_cta);
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) sAcc[i] = 0.f;
+  const float* bh = bias + static_cast<size_t>(h) * T * T;
+  for (int item = item0; item < item1; ++item) {
+    const int b = item / nW, win = item - b * nW;
+    const int wy = win / nw, wx = win - wy * nw;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const int r = t / w, c = t - r * w;
+      const int y = (wy * w + r + shift) % res, x = (wx * w + c + shift) % res;  // shifted frame -> image (roll by -shift)
+      sTok[t] = (b * res + y) * res + x;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * kHd; i += blockDim.x) {
+      const int t = i >> 5, d = i & 31;
+      const size_t row = static_cast<size_t>(sTok[t]);
+      const bf16_t* p = qkv + row * 3 * C + h * kHd + d;
+      sQ[t * kHdP + d] = __bfloat162float(p[0]);
+      sK[t * kHdP + d] = __bfloat162float(p[C]);
+      sV[t * kHdP + d] = __bfloat162float(p[2 * C]);
+      sDO[t * kHdP + d] = __bfloat162float(datt[row * C + h * kHd + d]);
+    }
+    __syncthreads();
+    const float* mk = (mask != nullptr && shift > 0) ? mask + static_cast<size_t>(win) * T * T : nullptr;
+    smem_mm<4>(sQ, kHdP, 1, sK, 1, kHdP, T, T, kHd, [&](int i, int j, float v) {
+      sP[i * TP + j] = v + bh[i * T + j] + (mk != nullptr ? mk[i * T + j] : 0.f);
+    });
+    // dP = dO V^T (independent of the softmax: same barrier interval)
+    smem_mm<4>(sDO, kHdP, 1, sV, 1, kHdP, T, T, kHd, [&](int i, int j, float v) { sD[i * TP + j] = v; });
+    __syncthreads();
+    // softmax rows and dS, one warp per row
+    for (int i = threadIdx.x >> 5; i < T; i += blockDim.x >> 5) {
+      const int lane = threadIdx.x & 31;
+      float mx = -INFINITY;
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sP[i * TP + j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) { const float e = __expf(sP[i * TP + j] - mx); sP[i * TP + j] = e; sum += e; }
+      const float inv = 1.0f / warp_sum(sum);
+      float dot = 0.f;
+      for (int j = lane; j < T; j += 32) { const float p = sP[i * TP + j] * inv; sP[i * TP + j] = p; dot += p * sD[i * TP + j]; }
+      dot = warp_sum(dot);
+      for (int j = lane; j < T; j += 32) {
+        const float ds = sP[i * TP + j] * (sD[i * TP + j] - dot);
+        sD[i * TP + j] = ds;
+        sAcc[i * T + j] += ds;   // row i belongs to this warp for every item: no race
+      }
+    }
+    __syncthreads();
+    // dV[j, d] = sum_i P[i, j] dO[i, d]
+    smem_mm<2>(sP, 1, TP, sDO, kHdP, 1, T, kHd, T, [&](int j, int d, float v) {
+      dqkv[static_cast<size_t>(sTok[j]) * 3 * C + 2 * C + h * kHd + d] = __float2bfloat16_rn(v);
+    });
+    // dQ[i, d] = sum_j dS[i, j] K[j, d]
+    smem_mm<2>(sD, TP, 1, sK, kHdP, 1, T, kHd, T, [&](int i, int d, float v) {
+      dqkv[static_cast<size_t>(sTok[i]) * 3 * C + h * kHd + d] = __float2bfloat16_rn(v);
+    });
+    // dK[j, d] = sum_i dS[i, j] Q[i, d]
+    smem_mm<2>(sD, 1, TP, sQ, kHdP, 1, T, kHd, T, [&](int j, int d, float v) {
+      dqkv[static_cast<size_t>(sTok[j]) * 3 * C + C + h * kHd + d] = __float2bfloat16_rn(v);
+    });
+  }
+  __syncthreads();
+  float* dbh = dbias + static_cast<size_t>(h) * T * T;
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) atomicAdd(&dbh[i], sAcc[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Optimiser: global gradient norm (nn.utils.clip_grad_norm_, trainer_node_adj.py:174), Adam (torch.optim.Adam
+// semantics incl. L2 weight decay, utils/learning_utils.py:126-145) and up to 8 exponential moving averages
+// (ema_pytorch.EMA.update with update_every 1, :148-166) over ONE flat fp32 parameter buffer in one launch.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) s += g[i] * g[i];
+  __shared__ float part[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    atomicAdd(out, t);
+  }
+}
+struct AdamArgs {
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm;
+  int n_ema;
+  float ema_decay[8];
+  float* ema[8];
+};
+__global__ void __launch_bounds__(256)
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                const float* __restrict__ gsumsq, AdamArgs a) {
+  float clip = 1.f;
+  if (gsumsq != nullptr && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / (sqrtf(*gsumsq) + 1e-6f));
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    float w = p[i];
+    if (m != nullptr) {   // m == NULL: moving averages only
+      float gi = g[i] * clip + a.weight_decay * w;
+      const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
+      const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      w -= (a.lr / a.bc1) * mi / (sqrtf(vi) / a.bc2_sqrt + a.eps);
+      p[i] = w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < a.n_ema) {   // lerp(ema, w, 1 - decay); decay 0 is ema_pytorch's plain copy
+        float* e = a.ema[k];
+        e[i] = a.ema_decay[k] == 0.f ? w : e[i] + (1.f - a.ema_decay[k]) * (w - e[i]);
+      }
+  }
+}
+
+// weight preparation: bf16 shadows of the fp32 masters for the tcgen05 GEMMs, one launch for all matrices.
+// job: src [rows, cols] fp32 -> dst [rows, ldd] bf16 (zero padded to ldd), dst_t [cols_t_rows = ldt_rows, rows]: the
+// transpose with `ldt` = rows pitch (dgrad operand W^T), first `scale_elems` source elements scaled (q rows of qkv);
+// dtype_f32: dst is an fp32 vector copy (the scaled qkv bias).
+struct PrepJob {
+  const float* src;
+  void* dst;
+  bf16_t* dst_t;
+  int rows, cols, ldd, rows_t;   // rows_t: row count of dst_t (>= cols, zero padded)
+  long long scale_elems;
+  float scale;
+  int dst_f32;
+};
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const PrepJob* __restrict__ jobs) {
+  const PrepJob j = jobs[blockIdx.y];
+  const long long n = static_cast<long long>(j.rows) * j.ldd;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+    const int r = static_cast<int>(i / j.ldd), c = static_cast<int>(i - static_cast<long long>(r) * j.ldd);
+    float val = 0.f;
+    if (c < j.cols) {
+      const long long s = static_cast<long long>(r) * j.cols + c;
+      val = j.src[s];
+      if (s < j.scale_elems) val *= j.scale;
+    }
+    if (j.dst_f32) static_cast<float*>(j.dst)[i] = val;
+    else static_cast<bf16_t*>(j.dst)[i] = __float2bfloat16_rn(val);
+    if (j.dst_t != nullptr) j.dst_t[static_cast<long long>(c) * j.rows + r] = __float2bfloat16_rn(val);
+  }
+  if (j.dst_t != nullptr) {  // zero rows [ldd, rows_t) of the transpose
+    const long long extra = static_cast<long long>(j.rows_t - j.ldd) * j.rows;
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < extra; i += static_cast<long long>(gridDim.x) * 256)
+      j.dst_t[static_cast<long long>(j.ldd) * j.rows + i] = __float2bfloat16_rn(0.f);
+  }
+}
+
+inline unsigned grid_for(long long work, int per_block = 256, int cap_mult = 16) {
+  long long g = (work + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(device_sm_count()) * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" {
+
+int dsg_tr_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, long long M, int C,
+                  dsg_stream_t stream) {
+  DSG_REQUIRE(x && gamma && beta && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0, "tr_ln_fwd: bad argument");
+  ln_fwd_kernel<<<grid_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, static_cast<bf16_t*>(y_bf16), y_f32, M, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_ln_bwd(const float* dy, const float* x, const float* gamma, const float* dx_add, float* dx, float* dgamma,
+                  float* dbeta, long long M, int C, dsg_stream_t stream) {
+  DSG_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && M > 0 && C > 0 && C % 4 == 0 && C <= 4096, "tr_ln_bwd: bad argument");
+  ln_bwd_kernel<<<grid_for(M, 8 * 16, 4), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_film_silu_fwd(const float* v, const float* film, int ldf, int off, float* out, int B, int L, int C,
+                         dsg_stream_t stream) {
+  DSG_REQUIRE(v && film && out && B > 0 && L > 0 && C % 4 == 0 && off % 4 == 0 && ldf % 4 == 0, "tr_film_silu_fwd: bad argument");
+  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
+  film_silu_fwd_kernel<<<B * chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, film, ldf, off, out, L, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_film_silu_bwd(const float* dout, const float* v, const float* film, int ldf, int off, float* dv, float* dfilm,
+                         int B, int L, int C, dsg_stream_t stream) {
+  DSG_REQUIRE(dout && v && film && dv && dfilm && B > 0 && L > 0 && C % 4 == 0 && off % 4 == 0 && ldf % 4 == 0 && C <= 4096,
+              "tr_film_silu_bwd: bad argument");
+  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
+  film_silu_bwd_kernel<<<B * chunks, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(dout, v, film, ldf, off, dv, dfilm, L, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_gelu(const void* pre, const void* dh, void* out, long long n, dsg_stream_t stream) {
+  DSG_REQUIRE(pre && out && n > 0 && n % 4 == 0, "tr_gelu: bad argument");
+  if (dh == nullptr)
+    gelu_fwd_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 4);
+  else
+    gelu_bwd_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(dh), static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 4);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_gelu_f32(const float* pre, const float* dout, float* out, long long n, dsg_stream_t stream) {
+  DSG_REQUIRE(pre && out && n > 0, "tr_gelu_f32: bad argument");
+  gelu_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(pre, dout, out, n);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_colsum(const float* src, float* out, long long M, int C, dsg_stream_t stream) {
+  DSG_REQUIRE(src && out && M > 0 && C > 0, "tr_colsum: bad argument");
+  const int rows = 256;
+  colsum_f32_kernel<<<static_cast<unsigned>((M + rows - 1) / rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, out, M, C, rows);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_precond_coef(const float* sigmas, float* out, int B, dsg_stream_t stream) {
+  DSG_REQUIRE(sigmas && out && B > 0, "tr_precond_coef: bad argument");
+  precond_coef_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sigmas, out, B);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_silu(const float* pre, const float* dout, float* out, long long n, dsg_stream_t stream) {
+  DSG_REQUIRE(pre && out && n > 0, "tr_silu: bad argument");
+  if (dout == nullptr) silu_fwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(pre, out, n);
+  else silu_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, pre, out, n);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_add_inplace(float* y, const float* x, long long n, dsg_stream_t stream) {
+  DSG_REQUIRE(y && x && n > 0 && n % 4 == 0, "tr_add_inplace: bad argument");
+  add_inplace_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, x, n / 4);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_transpose(const void* src, int src_is_bf16, void* dst_t, void* cast, float* colsum, long long M, long long Mp,
+                     int C, int scale_cols, float scale, dsg_stream_t stream) {
+  DSG_REQUIRE(src && dst_t && M > 0 && C > 0 && Mp >= M && Mp % 16 == 0,
+              "tr_transpose: bad argument (destination pitch Mp %% 16 == 0: TMA pitch and the GEMM's K step)");
+  const dim3 grid((C + 31) / 32, static_cast<unsigned>((Mp + kTrRows - 1) / kTrRows));
+  if (src_is_bf16)
+    transpose_colsum_kernel<bf16_t><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(src), static_cast<bf16_t*>(dst_t), static_cast<bf16_t*>(cast), colsum, M, Mp, C, scale_cols, scale);
+  else
+    transpose_colsum_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(src), static_cast<bf16_t*>(dst_t), static_cast<bf16_t*>(cast), colsum, M, Mp, C, scale_cols, scale);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_shuffle2x2(const float* src, float* dst, int B, int H, int W, int C, int to_coarse, dsg_stream_t stream) {
+  DSG_REQUIRE(src && dst && B > 0 && H > 0 && W > 0 && C % 4 == 0, "tr_shuffle2x2: bad argument");
+  shuffle2x2_kernel<<<grid_for(static_cast<long long>(B) * H * W * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, B, H, W, C, to_coarse);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_copy_cols(const float* src, int lds, int scol, void* dst, int ldd, int dcol, int ncols, long long M, int dst_bf16,
+                     int accumulate, dsg_stream_t stream) {
+  DSG_REQUIRE(src && dst && M > 0 && ncols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && scol % 4 == 0 && dcol % 4 == 0,
+              "tr_copy_cols: bad argument");
+  copy_cols_kernel<<<grid_for(M * ncols / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, scol, dst, ldd, dcol, ncols, M, dst_bf16, accumulate);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_embed_input(const float* adj, const float* node, const float* sc_adj, const float* sc_node, const uint8_t* flags,
+                       const float* c_in, void* out, int B, int n, int c_e, int c_n, int self_cond, int ld,
+                       dsg_stream_t stream) {
+  DSG_REQUIRE(adj && node && flags && out && (self_cond ? 2 : 1) * (c_e + 2 * c_n) <= ld, "tr_embed_input: bad argument");
+  embed_input_kernel<<<grid_for(static_cast<long long>(B) * n * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      adj, node, sc_adj, sc_node, flags, c_in, static_cast<bf16_t*>(out), B, n, c_e, c_n, self_cond, ld);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_adj_out(const float* in, const uint8_t* flags, const float* x_adj, const float* c_skip, const float* c_out,
+                   float* out, int B, int n, int c_e, int backward, dsg_stream_t stream) {
+  DSG_REQUIRE(in && flags && out, "tr_adj_out: bad argument");
+  adj_out_kernel<<<grid_for(static_cast<long long>(B) * n * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, flags, x_adj, c_skip, c_out, out, B, n, c_e, backward);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_node_out(const float* in, const uint8_t* flags, const float* x_node, const float* c_skip, const float* c_out,
+                    float* out, int B, int n, int c_n, int backward, dsg_stream_t stream) {
+  DSG_REQUIRE(in && flags && out, "tr_node_out: bad argument");
+  node_out_kernel<<<grid_for(static_cast<long long>(B) * n * c_n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, flags, x_node, c_skip, c_out, out, B, n, c_n, backward);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_node_pool(const float* rep, const uint8_t* flags, float* pooled, const float* dpooled, float* drep, int B, int n,
+                     int C, dsg_stream_t stream) {
+  DSG_REQUIRE(flags && C % 4 == 0 && ((rep && pooled) || (dpooled && drep)), "tr_node_pool: bad argument");
+  if (dpooled == nullptr)
+    node_pool_train_kernel<<<static_cast<unsigned>((static_cast<long long>(B) * n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(rep, flags, pooled, B, n, C);
+  else
+    node_pool_bwd_kernel<<<grid_for(static_cast<long long>(B) * n * n * C / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(dpooled, flags, drep, B, n, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_posemb(const float* labels, float* out, int B, int embed, dsg_stream_t stream) {
+  DSG_REQUIRE(labels && out && embed % 2 == 0, "tr_posemb: bad argument");
+  posemb_kernel<<<(B * embed / 2 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(labels, out, B, embed);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_bias_gather(const float* table, const int64_t* index, float* bias, int heads, int T, int backward, float* dtable,
+                       dsg_stream_t stream) {
+  DSG_REQUIRE(index && bias && (backward ? dtable != nullptr : table != nullptr), "tr_bias_gather: bad argument");
+  bias_gather_kernel<<<(heads * T * T + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, index, bias, heads, T * T, backward, dtable);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_sgemm(const void* A, int a_is_bf16, long long sam, long long sak, const void* B, int b_is_bf16, long long sbk,
+                 long long sbn, const float* bias, float* C, long long ldc, int M, int N, int K, int ksplit, int accumulate,
+                 dsg_stream_t stream) {
+  DSG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ksplit >= 1, "tr_sgemm: bad argument");
+  int k_per = (K + ksplit - 1) / ksplit;
+  k_per = (k_per + 15) / 16 * 16;
+  const int slices = (K + k_per - 1) / k_per;
+  DSG_REQUIRE(slices == 1 || accumulate, "tr_sgemm: split-K accumulates (zero C first and pass accumulate = 1)");
+  const dim3 grid((M + 63) / 64, (N + 63) / 64, slices);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a_is_bf16 && b_is_bf16)
+    sgemm_kernel<bf16_t, bf16_t><<<grid, 256, 0, st>>>(static_cast<const bf16_t*>(A), sam, sak, static_cast<const bf16_t*>(B), sbk, sbn, bias, C, ldc, M, N, K, k_per, accumulate);
+  else if (a_is_bf16)
+    sgemm_kernel<bf16_t, float><<<grid, 256, 0, st>>>(static_cast<const bf16_t*>(A), sam, sak, static_cast<const float*>(B), sbk, sbn, bias, C, ldc, M, N, K, k_per, accumulate);
+  else if (b_is_bf16)
+    sgemm_kernel<float, bf16_t><<<grid, 256, 0, st>>>(static_cast<const float*>(A), sam, sak, static_cast<const bf16_t*>(B), sbk, sbn, bias, C, ldc, M, N, K, k_per, accumulate);
+  else
+    sgemm_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(A), sam, sak, static_cast<const float*>(B), sbk, sbn, bias, C, ldc, M, N, K, k_per, accumulate);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* bias, const float* mask, void* dqkv,
+                                float* dbias, int batch, int res, int window, int shift, int heads, dsg_stream_t stream) {
+  DSG_REQUIRE(qkv && datt && bias && dqkv && dbias && res % window == 0 && shift >= 0 && shift < window,
+              "tr_window_attention_bwd: bad argument");
+  DSG_REQUIRE(shift == 0 || mask != nullptr, "tr_window_attention_bwd: shifted windows need the attention mask");
+  const int T = window * window;
+  const size_t smem = (static_cast<size_t>(4) * T * kHdP + 2 * static_cast<size_t>(T) * (T + 1) + static_cast<size_t>(T) * T) * 4 + static_cast<size_t>(T) * 4;
+  DSG_REQUIRE(smem <= 227 * 1024, "tr_window_attention_bwd: %d-token windows do not fit shared memory (T <= 121)", T);
+  static PerDeviceOnce configured;
+  if (configured.first())
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int total = batch * (res / window) * (res / window);
+  // one atomicAdd pass over dbias per CTA: keep the CTA count near two waves
+  const int resident = static_cast<int>((227 * 1024) / smem) > 0 ? static_cast<int>((227 * 1024) / smem) : 1;
+  int ctas_x = (device_sm_count() * (resident > 4 ? 4 : resident) * 2 + heads - 1) / heads;
+  if (ctas_x > total) ctas_x = total;
+  const int per = (total + ctas_x - 1) / ctas_x;
+  ctas_x = (total + per - 1) / per;
+  window_attention_bwd_kernel<<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
+      res, window, shift, heads, per);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_sumsq(const float* g, long long n, float* out, dsg_stream_t stream) {
+  DSG_REQUIRE(g && out && n > 0, "tr_sumsq: bad argument");
+  DSG_CUDA_CHECK(cudaMemsetAsync(out, 0, 4, static_cast<cudaStream_t>(stream)));
+  sumsq_kernel<<<grid_for(n, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_adam_ema(float* p, const float* g, float* m, float* v, long long n, const float* gsumsq, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float max_norm, int n_ema, float* const* ema,
+                    const float* ema_decay, dsg_stream_t stream) {
+  DSG_REQUIRE(p && n > 0 && step >= 1 && n_ema >= 0 && n_ema <= 8 && ((g && m && v) || (!m && !v && n_ema > 0)),
+              "tr_adam_ema: bad argument");
+  AdamArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
+  a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  a.n_ema = n_ema;
+  for (int k = 0; k < n_ema; ++k) { a.ema[k] = ema[k]; a.ema_decay[k] = ema_decay[k]; }
+  adam_ema_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, gsumsq, a);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_prep_weights(const void* jobs_device, int n_jobs, dsg_stream_t stream) {
+  DSG_REQUIRE(jobs_device && n_jobs > 0, "tr_prep_weights: bad argument");
+  prep_weights_kernel<<<dim3(64, n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PrepJob*>(jobs_device));
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_prep_job_bytes(void) { return static_cast<int>(sizeof(PrepJob)); }
+
+}  // extern "C"

@@ -83,8 +83,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int ncta = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int num_m = (p.M + (PAIR ? 2 * BM : BM) - 1) / (PAIR ? 2 * BM : BM);
   const int num_n = p.N / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  // split-K (weight gradients: few output tiles, a contraction over every token): a work item is (output tile,
+  // K slice), the slices of a tile are combined by the reduce-add epilogue.  ksplit = 1 everywhere else.
+  const int ksplit = (!PAIR && p.ksplit > 1) ? p.ksplit : 1;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
+  const int num_tiles = num_m * num_n * ksplit;
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -125,8 +129,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int s = 0;
     uint32_t ph = 0;
     for (int tile = cta; tile < num_tiles; tile += ncta) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int mn = tile / ksplit, kb0 = (tile - mn * ksplit) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      const int m_blk = mn / num_n, n_blk = mn % num_n;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (PAIR) {
           // this CTA's 128 rows of A and its half of the B tile; both CTAs' bytes complete on the LEADER's barrier
@@ -158,7 +163,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = (tile % ksplit) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -167,15 +173,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int ksteps = min(BK, p.K - kb * BK) / 16;
           for (int k = 0; k < ksteps; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           if (PAIR) {
             umma_commit_pair(&empty_bar[s]);
-            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);
           } else {
             umma_commit(&empty_bar[s]);
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
           }
         }
         __syncwarp();
@@ -211,8 +217,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       else mbar_arrive(&tempty_bar[acc]);
     };
     for (int tile = cta + acc * ncta; tile < num_tiles; tile += 2 * ncta) {
-      const int m_blk = PAIR ? (tile / num_n) * 2 + static_cast<int>(rank) : tile / num_n;  // this CTA's 128-row block
-      const int n_blk = tile % num_n;
+      const int mn = tile / ksplit;
+      const int m_blk = PAIR ? (mn / num_n) * 2 + static_cast<int>(rank) : mn / num_n;  // this CTA's 128-row block
+      const int n_blk = mn % num_n;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
       if (EPI == EPI_ADJ_HEAD) {
         // columns [48 half, 48 half + 48) of the hidden layer; partial sums of the 96 -> c_e linear are combined
@@ -427,7 +434,7 @@ int launch_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* 
     DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg<BN>::SMEM_BYTES));
   }
-  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, EPI, false><<<grid, gemm_threads(EPI), Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
   DSG_LAUNCH_CHECK();
@@ -561,6 +568,11 @@ int launch_gemm(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
   DSG_REQUIRE(tmO != nullptr && p.ldo == p.N, "gemm: output tensor map missing or ldo != N");
   if (epi == EPI_RES_F32)
     DSG_REQUIRE(p.res == p.out, "gemm: the residual epilogue accumulates in place (res must alias out)");
+  if (p.ksplit > 1) {
+    const int num_kb = (p.K + BK - 1) / BK, per = (num_kb + p.ksplit - 1) / p.ksplit;
+    DSG_REQUIRE(epi == EPI_RES_F32 && p.bias == nullptr && !pair && (p.ksplit - 1) * per < num_kb,
+                "gemm: split-K needs the reduce-add epilogue, no bias, single CTAs and non-empty slices (ksplit %d)", p.ksplit);
+  }
   if (pair) {  // CTA pairs: tmW is the half-tile descriptor
     if (bn == 256) {
       switch (epi) {

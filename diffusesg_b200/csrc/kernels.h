@@ -33,6 +33,7 @@ struct GemmParams {
   void* out;           // [M, ldo] bf16 / fp32; EPI_ADJ_HEAD: float [B, c_e, n, n]
   int ldo;
   int bn;              // tile width: 0 = gemm_block_n(N); 256 needs N % 256 == 0 and a W descriptor with that box
+  int ksplit;          // > 1: split the contraction into that many slices per output tile (EPI_RES_F32, no bias)
   // EPI_ADJ_HEAD only
   const float* w2t;    // [96][8]: second layer of the adj read-out MLP, transposed and zero padded
   const float* b2;     // [8]

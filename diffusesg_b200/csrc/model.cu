@@ -1301,28 +1301,38 @@ int dsg_edm_loss_sums_backward(const float* pred_adj, const float* target_adj, c
                                    grad_pred_adj, grad_pred_node, batch, c_e, n, c_n, static_cast<cudaStream_t>(stream));
 }
 
-int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
-                  int epi, dsg_stream_t stream) {
+int dsg_gemm_bf16_ex(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
+                     int epi, int ksplit, int out_cols, dsg_stream_t stream) {
   DSG_REQUIRE(a && w && out && epi >= 0 && epi <= 3, "gemm_bf16: bad argument");
+  DSG_REQUIRE(out_cols > 0 && out_cols <= N, "gemm_bf16: out_cols %d for N = %d", out_cols, N);
   CUtensorMap ta, tw, to;
   DSG_TRY(make_tmap_bf16(&ta, a, M, K, 128));
   const char* no_pair = getenv("DSG_NO_PAIR");
-  const bool pair = M >= 256 && (K >= 768 || (K >= 384 && epi == EPI_BF16)) &&
+  const bool pair = ksplit <= 1 && M >= 256 && (K >= 768 || (K >= 384 && epi == EPI_BF16)) &&
                     !(no_pair != nullptr && no_pair[0] == '1');  // the denoiser schedule's rule
   const int bn = gemm_choose_bn(M, N, K, epi, pair);
   DSG_TRY(make_tmap_bf16(&tw, w, N, K, pair ? bn / 2 : bn));
-  DSG_TRY(make_tmap_out(&to, out, M, N, epi));
+  DSG_TRY(make_tmap_out(&to, out, M, out_cols, epi));
   if (epi == EPI_RES_F32) {
     DSG_REQUIRE(res != nullptr, "gemm_bf16: residual epilogue without residual");
     if (res != out)  // the kernel accumulates in place: seed the output with the residual
-      DSG_CUDA_CHECK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToDevice,
+      DSG_CUDA_CHECK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * out_cols * 4, cudaMemcpyDeviceToDevice,
                                      static_cast<cudaStream_t>(stream)));
     res = static_cast<const float*>(out);
   }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.out = out; p.ldo = N; p.bn = bn;
+  if (ksplit > 1) {  // no empty slice: round the slice count to what the per-slice block count gives
+    const int num_kb = (K + 63) / 64, per = (num_kb + ksplit - 1) / ksplit;
+    p.ksplit = (num_kb + per - 1) / per;
+  }
   return launch_gemm(&ta, &tw, &to, epi, p, static_cast<cudaStream_t>(stream), pair);
+}
+
+int dsg_gemm_bf16(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
+                  int epi, dsg_stream_t stream) {
+  return dsg_gemm_bf16_ex(a, w, bias, res, out, M, N, K, epi, 1, N, stream);
 }
 
 int dsg_proj_ln(const void* att, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* y,

@@ -181,12 +181,17 @@ class DiffuseSG(nn.Module):
         memo[id(self)] = new
         import copy
         for k, v in self.__dict__.items():
-            new.__dict__[k] = None if k == "_nat" else copy.deepcopy(v, memo)
+            if k in ("_nat", "_train_state", "_active_skip"):   # device-side state is rebuilt lazily by the copy
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_nat"] = None
+        d.pop("_train_state", None)
+        d.pop("_active_skip", None)
         return d
 
     def _versions(self):
@@ -264,10 +269,10 @@ class DiffuseSG(nn.Module):
         return _Skipping(self, plan)
 
     def _run(self, mode, adj, node, flags, noise, sc_adj, sc_node):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and \
-                (adj.requires_grad or self.training):
-            raise NotImplementedError("DiffuseSG (B200): backward through the native kernels is not built yet; "
-                                      "call under torch.no_grad() / model.eval() (training step = SURVEY 8f-2)")
+        train = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if torch.is_grad_enabled() and (adj.requires_grad or node.requires_grad):
+            raise NotImplementedError("DiffuseSG (B200): gradients w.r.t. the input graphs are not built (the reference's "
+                                      "training step differentiates the parameters only, trainer_node_adj.py:96-173)")
         if adj.dim() != 4 or node.dim() != 3 or flags.dim() != 2:
             raise NotImplementedError("DiffuseSG (B200): expects adj [B,C,N,N], node [B,N,C], node_flags [B,N] "
                                       "(the scene-graph path of the reference)")
@@ -296,6 +301,11 @@ class DiffuseSG(nn.Module):
             sc_node = None if sc_node is None else native.require_cuda(sc_node, "self_cond_feat")
         else:
             sc_adj = sc_node = None
+        if train:
+            # training step: forward with saved activations as one autograd node, model/diffusesg/train_graph.py
+            from .train_graph import run_training_forward
+            noise_b = (noise.reshape(1).expand(b) if n_cond == 1 else noise).contiguous()
+            return run_training_forward(self, mode, adj, node, flags, noise_b, sc_adj, sc_node)
         nat = self._native(dev)
         out_adj = torch.empty_like(adj)
         out_node = torch.empty_like(node)

@@ -96,6 +96,38 @@ _SIGNATURES = {
     "dsg_edm_loss_sums_backward": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_gemm_bf16_ex": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p]),
+    # training step
+    "dsg_tr_ln_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "dsg_tr_ln_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "dsg_tr_film_silu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 3 + [C.c_void_p]),
+    "dsg_tr_film_silu_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 3
+                             + [C.c_void_p]),
+    "dsg_tr_gelu": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_void_p]),
+    "dsg_tr_silu": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_void_p]),
+    "dsg_tr_add_inplace": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p]),
+    "dsg_tr_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,
+                                   C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "dsg_tr_shuffle2x2": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_tr_copy_cols": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                   C.c_int, C.c_int, C.c_void_p]),
+    "dsg_tr_embed_input": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_void_p]),
+    "dsg_tr_adj_out": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_tr_node_out": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]),
+    "dsg_tr_node_pool": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p]),
+    "dsg_tr_posemb": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p]),
+    "dsg_tr_bias_gather": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p]),
+    "dsg_tr_sgemm": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
+                               C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_tr_gelu_f32": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_void_p]),
+    "dsg_tr_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "dsg_tr_precond_coef": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "dsg_tr_window_attention_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_tr_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dsg_tr_adam_ema": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 5 + [C.c_int, C.c_float,
+                                  C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_float), C.c_void_p]),
+    "dsg_tr_prep_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dsg_tr_prep_job_bytes": (C.c_int, []),
     "dsg_profile_begin": (C.c_int, [C.c_int]),
     "dsg_profile_read": (C.c_int, [C.POINTER(DsgProfileClass), C.c_int, C.POINTER(C.c_int)]),
     "dsg_profile_dump": (C.c_int, [C.c_char_p]),

@@ -41,3 +41,32 @@ def get_network(config, dist_helper=None):
     if dist_helper is not None:
         denoising_model = dist_helper.dist_adapt_model(denoising_model)
     return denoising_model
+
+
+def get_optimizer(model, config, dist_helper=None):
+    """utils/learning_utils.py:126-145: Adam(lr_init, betas (0.9, 0.999), eps 1e-8, weight_decay) + ExponentialLR.  The
+    reference shards the optimiser state with ZeroRedundancyOptimizer under DDP; here the 36 M-parameter state is one
+    flat buffer per GPU and the step is one fused launch (utils/train_utils.py)."""
+    from .train_utils import FusedAdam
+    optimizer = FusedAdam(model, lr=config.train.lr_init, betas=(0.9, 0.999), eps=1e-8,
+                          weight_decay=config.train.weight_decay, max_grad_norm=10.0)
+    scheduler = torch.optim.lr_scheduler.ExponentialLR(optimizer, gamma=config.train.lr_dacey)
+    return optimizer, scheduler
+
+
+def get_ema_helper(config, model, optimizer=None):
+    """utils/learning_utils.py:148-166: one moving average per coefficient (sorted), or None.  Pass the FusedAdam to have
+    every average updated inside the optimiser launch."""
+    from .train_utils import FusedAdam, NativeEMA
+    ema_coef = config.train.ema_coef
+    flag_ema = isinstance(ema_coef, list) or (isinstance(ema_coef, float) and ema_coef < 1)
+    if not flag_ema:
+        logging.info("Exponential moving average is OFF.")
+        return None
+    coefs = [ema_coef] if isinstance(ema_coef, float) else list(ema_coef)
+    inner = model.module if hasattr(model, "module") else model
+    helpers = [NativeEMA(inner, beta=c) for c in sorted(coefs)]
+    if isinstance(optimizer, FusedAdam):
+        optimizer.attach_emas(helpers)
+    logging.info("Exponential moving average is ON. Coefficient: {}".format(coefs))
+    return helpers

@@ -1,0 +1,163 @@
+"""Optimiser, moving averages and data-parallel wrapper of the training step, over the flat parameter
+buffer of model/diffusesg/train_graph.py.
+
+Drop-ins for utils/learning_utils.py:126-166 (``get_optimizer``: Adam(lr_init, betas (0.9, 0.999), eps 1e-8,
+weight_decay) + ExponentialLR; ``get_ema_helper``: one ``ema_pytorch.EMA(beta=coef, update_every=1,
+update_after_step=0, inv_gamma=1, power=1)`` per coefficient) and utils/dist_training.py:62-69 (DDP wrap).  One fused
+launch (dsg_tr_adam_ema) applies gradient clipping (trainer_node_adj.py:174), Adam and every moving average; the
+gradient all-reduce is NCCL over NVLink on two contiguous ranges of the flat gradient buffer, overlapped with backward.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import native
+from ..model.diffusesg.diffusesg import DiffuseSG
+from ..model.diffusesg.train_graph import train_state
+
+
+def find_denoiser(model: nn.Module) -> DiffuseSG:
+    for m in model.modules():
+        if isinstance(m, DiffuseSG):
+            return m
+    raise ValueError("no DiffuseSG module inside the model")
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments) on the flat parameter
+    buffer, optional clip_grad_norm_ (`max_grad_norm`) and the attached moving averages, in one kernel launch."""
+
+    def __init__(self, model: nn.Module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None):
+        self.denoiser = find_denoiser(model)
+        dev = next(self.denoiser.parameters()).device
+        self.ts = train_state(self.denoiser, dev)
+        params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        n_flat = sum(1 for _ in self.denoiser.parameters())
+        if len(params) != n_flat:
+            raise NotImplementedError("FusedAdam: the model has trainable parameters outside the DiffuseSG denoiser")
+        self.max_grad_norm = max_grad_norm
+        with torch.cuda.device(dev):
+            self.m = torch.zeros_like(self.ts.flat)
+            self.v = torch.zeros_like(self.ts.flat)
+            self.gsumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.steps = 0
+        self.emas: List["NativeEMA"] = []
+
+    def attach_emas(self, emas):
+        self.emas = list(emas or [])
+        for e in self.emas:
+            e.fused_into = self
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        ts = self.ts
+        if not ts.attached():
+            raise native.NativeError("FusedAdam: the model's parameters were moved off the flat buffer (.to() after "
+                                     "construction?); rebuild the optimiser")
+        if ts.attach_grads():
+            return None   # no backward ran since zero_grad(set_to_none=True): nothing to apply
+        g = self.param_groups[0]
+        self.steps += 1
+        st = native.stream_ptr(ts.dev)
+        lib = native.lib()
+        with native.device_guard(ts.dev):
+            gs = None
+            if self.max_grad_norm is not None:
+                native.check(lib.dsg_tr_sumsq(ts.grad.data_ptr(), ts.numel, self.gsumsq.data_ptr(), st), "dsg_tr_sumsq")
+                gs = self.gsumsq.data_ptr()
+            n = len(self.emas)
+            ptrs = (C.c_void_p * 8)(*[e.flat.data_ptr() for e in self.emas])
+            decays = (C.c_float * 8)(*[e.next_decay() for e in self.emas])
+            native.check(lib.dsg_tr_adam_ema(ts.flat.data_ptr(), ts.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                             ts.numel, gs, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                             float(g["eps"]), float(g["weight_decay"]), self.steps,
+                                             float(self.max_grad_norm or 0.0), n, ptrs, decays, st), "dsg_tr_adam_ema")
+        for e in self.emas:
+            e.fused_done()
+        self.denoiser.invalidate_native()
+        return None
+
+    def grad_norm(self) -> torch.Tensor:
+        """sqrt of the sum of squares the last step clipped with (device scalar)."""
+        return self.gsumsq.sqrt()
+
+
+class NativeEMA:
+    """ema_pytorch.EMA(model, beta, update_every=1, update_after_step=0, inv_gamma=1, power=1) on a flat buffer:
+    ``.ema_model`` is a deep copy of the online model whose denoiser parameters are views of ``.flat``; ``update()``
+    follows ema_pytorch's schedule (copy on the first two calls, then decay = min(beta, 1 - 1 / (1 + epoch)))."""
+
+    def __init__(self, model: nn.Module, beta: float):
+        self.online = model
+        self.beta = float(beta)
+        self.online_ts = train_state(find_denoiser(model), next(model.parameters()).device)
+        self.ema_model = copy.deepcopy(model)
+        self.ema_model.requires_grad_(False)
+        den = find_denoiser(self.ema_model)
+        self.ts = train_state(den, self.online_ts.dev)
+        self.flat = self.ts.flat
+        self.denoiser = den
+        self.step = 0
+        self.initted = False
+        self.fused_into: Optional[FusedAdam] = None
+        self._pending = 0
+
+    def next_decay(self) -> float:
+        """Decay ema_pytorch would use for the update that follows the current optimiser step."""
+        step = self.step
+        if step <= 0 or not self.initted:
+            return 0.0                      # copy_params_from_model_to_ema
+        epoch = max(step + 1 - 0 - 1, 0)    # get_current_decay reads self.step AFTER the increment
+        if epoch <= 0:
+            return 0.0
+        return min(max(1.0 - 1.0 / (1.0 + epoch), 0.0), self.beta)
+
+    def _advance(self):
+        if self.step > 0:
+            self.initted = True
+        self.step += 1
+        self.denoiser.invalidate_native()
+
+    def fused_done(self):
+        self._advance()
+        self._pending += 1
+
+    def update(self):
+        """trainer_node_adj.py:178.  A no-op when the optimiser's fused launch already moved this average."""
+        if self._pending > 0:
+            self._pending -= 1
+            return
+        d = self.next_decay()
+        lib = native.lib()
+        ptrs = (C.c_void_p * 8)(self.flat.data_ptr())
+        decays = (C.c_float * 8)(d)
+        with native.device_guard(self.ts.dev):
+            native.check(lib.dsg_tr_adam_ema(self.online_ts.flat.data_ptr(), None, None, None, self.online_ts.numel, None,
+                                             0.0, 0.9, 0.999, 1e-8, 0.0, 1, 0.0, 1, ptrs, decays,
+                                             native.stream_ptr(self.ts.dev)), "dsg_tr_adam_ema")
+        self._advance()
+
+
+class NativeDDP(nn.Module):
+    """Data-parallel wrapper of the training step (utils/dist_training.py:62-69 wraps with torch DDP): parameters are
+    broadcast from rank 0 at construction; the tape's backward averages the flat gradient buffer over the group with
+    NCCL all-reduces (the read-out range while the U-Net backward still runs, the rest at the end)."""
+
+    def __init__(self, module: nn.Module, process_group=None):
+        super().__init__()
+        import torch.distributed as dist
+        self.module = module
+        den = find_denoiser(module)
+        ts = train_state(den, next(den.parameters()).device)
+        dist.broadcast(ts.flat, src=0, group=process_group)
+        ts.ddp_group = process_group if process_group is not None else dist.group.WORLD
+        den.invalidate_native()
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

@@ -287,6 +287,100 @@ DSG_API int dsg_proj_ln(const void* att, const void* w, const float* bias, const
 DSG_API int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
                          int window, int shift, int heads, dsg_stream_t stream);
 
+/* out = epilogue(A . W^T) like dsg_gemm_bf16, with (a) split-K: the contraction is cut into `ksplit` slices per output
+ * tile, combined by the reduce-add epilogue (epi 2, no bias; out must hold the value to accumulate onto) - the weight
+ * gradients dW[N_out, K_in] += dY^T[N_out, tokens] . X^T[K_in, tokens]^T of loss.backward() contract over every token
+ * and have only a handful of output tiles; (b) out_cols <= N: the output matrix is [M, out_cols] (columns beyond it are
+ * computed and dropped: the 60-input-channel patch-embedding weight).  ksplit <= 1 and out_cols == N: dsg_gemm_bf16. */
+DSG_API int dsg_gemm_bf16_ex(const void* a, const void* w, const float* bias, const float* res, void* out, int M, int N, int K,
+                             int epi, int ksplit, int out_cols, dsg_stream_t stream);
+
+/* ---- training step: loss.backward() and optimizer.step() of runner/trainer/trainer_node_adj.py:171-178 ---
+ * Row-wise forward kernels in the form the backward pass needs (out of place, pre-activations kept) and every backward
+ * kernel that is not a GEMM.  fp32 unless a pointer is `void*` (bf16).  The host-side tape that strings them together is
+ * diffusesg_b200/model/diffusesg/train_graph.py. */
+/* nn.LayerNorm (diffusesg.py:243, :275, :333, :386, :400, :571, :758), eps 1e-5: y as bf16 and / or fp32 (either may be
+ * NULL).  Backward: dx = LN'(dy) (+ dx_add, may alias dx), dgamma / dbeta ACCUMULATED (atomicAdd). */
+DSG_API int dsg_tr_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, long long M, int C,
+                          dsg_stream_t stream);
+DSG_API int dsg_tr_ln_bwd(const float* dy, const float* x, const float* gamma, const float* dx_add, float* dx, float* dgamma,
+                          float* dbeta, long long M, int C, dsg_stream_t stream);
+/* Noise conditioning out = silu(shift_b + v (1 + scale_b)) (diffusesg.py:238-240, :574-576); (scale, shift) of sample b =
+ * film[b * ldf + off + (0..C)], [.. + C + (0..C)].  Backward: dv written, dfilm[b, off .. off + 2C) ACCUMULATED. */
+DSG_API int dsg_tr_film_silu_fwd(const float* v, const float* film, int ldf, int off, float* out, int B, int L, int C,
+                                 dsg_stream_t stream);
+DSG_API int dsg_tr_film_silu_bwd(const float* dout, const float* v, const float* film, int ldf, int off, float* dv, float* dfilm,
+                                 int B, int L, int C, dsg_stream_t stream);
+/* nn.GELU (erf form, diffusesg.py:15) on bf16: dh == NULL: out = gelu(pre); else out = dh * gelu'(pre).  n % 4 == 0. */
+DSG_API int dsg_tr_gelu(const void* pre, const void* dh, void* out, long long n, dsg_stream_t stream);
+/* the same on fp32 (the node read-out MLP, :818): dout == NULL: forward */
+DSG_API int dsg_tr_gelu_f32(const float* pre, const float* dout, float* out, long long n, dsg_stream_t stream);
+/* out[c] += sum_r src[r, c] (bias gradients of the small fp32 layers) */
+DSG_API int dsg_tr_colsum(const float* src, float* out, long long M, int C, dsg_stream_t stream);
+/* out [4, B] = c_skip | c_out | c_in | c_noise of runner/objectives/edm.py:122-126 ('edm', sigma_data 0.5) */
+DSG_API int dsg_tr_precond_coef(const float* sigmas, float* out, int B, dsg_stream_t stream);
+/* silu on fp32 (:769-771): dout == NULL: out = silu(pre); else out = dout * silu'(pre). */
+DSG_API int dsg_tr_silu(const float* pre, const float* dout, float* out, long long n, dsg_stream_t stream);
+DSG_API int dsg_tr_add_inplace(float* y, const float* x, long long n, dsg_stream_t stream);
+/* src [M, C] (fp32, or bf16 when src_is_bf16) -> dst_t [C, Mp] bf16 (the token-major operand of a weight-gradient GEMM;
+ * Mp >= M, Mp % 16 == 0, columns [M, Mp) are written as zeros);
+ * optional: cast [M, C] bf16 (straight copy), colsum [C] += column sums (the bias gradient); columns < scale_cols are
+ * multiplied by `scale` in dst_t and colsum (the q third of qkv runs pre-scaled by head_dim^-1/2, :118). */
+DSG_API int dsg_tr_transpose(const void* src, int src_is_bf16, void* dst_t, void* cast, float* colsum, long long M,
+                             long long Mp, int C, int scale_cols, float scale, dsg_stream_t stream);
+/* fine [B, 2H, 2W, C] <-> coarse [B, H, W, 4, C], chunk k = dy + 2 dx: the gather of PatchMerging (:325-329) and the
+ * scatter of PatchBreakup (:394-397); to_coarse selects the direction (each is the other's backward). */
+DSG_API int dsg_tr_shuffle2x2(const float* src, float* dst, int B, int H, int W, int C, int to_coarse, dsg_stream_t stream);
+/* dst[:, dcol : dcol + ncols] (=, +=) src[:, scol : scol + ncols], dst fp32 or bf16: torch.cat of :753 and its split */
+DSG_API int dsg_tr_copy_cols(const float* src, int lds, int scol, void* dst, int ldd, int dcol, int ncols, long long M,
+                             int dst_bf16, int accumulate, dsg_stream_t stream);
+/* the input grid of :791-802 (self-conditioning first, node planes masked) as a bf16 GEMM operand [B N N, ld], inputs
+ * scaled by c_in[b] when given (model/precond/precond.py:100) */
+DSG_API int dsg_tr_embed_input(const float* adj, const float* node, const float* sc_adj, const float* sc_node,
+                               const uint8_t* flags, const float* c_in, void* out, int B, int n, int c_e, int c_n,
+                               int self_cond, int ld, dsg_stream_t stream);
+/* head outputs, token-major -> the reference's tensors with masks (:822-825) and D = c_skip x + c_out F
+ * (precond.py:102-105; x == NULL: raw F); backward != 0: `in` is the output gradient, `out` the token-major gradient */
+DSG_API int dsg_tr_adj_out(const float* in, const uint8_t* flags, const float* x_adj, const float* c_skip, const float* c_out,
+                           float* out, int B, int n, int c_e, int backward, dsg_stream_t stream);
+DSG_API int dsg_tr_node_out(const float* in, const uint8_t* flags, const float* x_node, const float* c_skip, const float* c_out,
+                            float* out, int B, int n, int c_n, int backward, dsg_stream_t stream);
+/* masked mean of :812-813: dpooled == NULL: pooled [B n, C] from rep [B n n, C]; else drep += its backward */
+DSG_API int dsg_tr_node_pool(const float* rep, const uint8_t* flags, float* pooled, const float* dpooled, float* drep, int B,
+                             int n, int C, dsg_stream_t stream);
+/* PositionalEmbedding (:507-513) */
+DSG_API int dsg_tr_posemb(const float* labels, float* out, int B, int embed, dsg_stream_t stream);
+/* bias[h, t, u] = table[index[t, u], h] (:121-124); backward != 0: dtable[index[t, u], h] += bias[h, t, u] */
+DSG_API int dsg_tr_bias_gather(const float* table, const int64_t* index, float* bias, int heads, int T, int backward,
+                               float* dtable, dsg_stream_t stream);
+/* C[m, n] (=, +=) sum_k A[m sam + k sak] B[k sbk + n sbn] (+ bias[n]); fp32 CUDA-core GEMM for the small matrices (noise
+ * embedding MLP, FiLM generators, node read-out, c_e / c_n wide output layers) and their gradients; ksplit > 1 or
+ * accumulate: atomicAdd onto C. */
+DSG_API int dsg_tr_sgemm(const void* A, int a_is_bf16, long long sam, long long sak, const void* B, int b_is_bf16,
+                         long long sbk, long long sbn, const float* bias, float* C, long long ldc, int M, int N, int K,
+                         int ksplit, int accumulate, dsg_stream_t stream);
+/* backward of dsg_window_attention (:108-139 with the roll / partition index arithmetic of :28-57, :248-267): qkv
+ * [B res res, 3 heads 32] bf16 (q pre-scaled), datt [B res res, heads 32] bf16 -> dqkv (same layout as qkv; dq w.r.t. the
+ * scaled q), dbias [heads, T, T] ACCUMULATED.  mask [nW, T, T] is required when shift > 0.  T = window^2 <= 121. */
+DSG_API int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* bias, const float* mask, void* dqkv,
+                                        float* dbias, int batch, int res, int window, int shift, int heads,
+                                        dsg_stream_t stream);
+/* optimizer.step(): out[0] = sum g^2 (for clip_grad_norm_, trainer_node_adj.py:174); then Adam with torch.optim.Adam
+ * semantics (utils/learning_utils.py:126-145) and n_ema <= 8 exponential moving averages (ema_pytorch.EMA.update, :148-166:
+ * ema += (1 - decay) (p - ema)) over one flat parameter buffer in one launch; gsumsq (device) and max_norm > 0 apply the
+ * gradient clipping coefficient min(1, max_norm / (sqrt(gsumsq) + 1e-6)).  m == v == NULL: only the moving averages move
+ * (ema.update() without a fused optimiser); decay 0 copies the parameters (ema_pytorch's first updates). */
+DSG_API int dsg_tr_sumsq(const float* g, long long n, float* out, dsg_stream_t stream);
+DSG_API int dsg_tr_adam_ema(float* p, const float* g, float* m, float* v, long long n, const float* gsumsq, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, int step, float max_norm, int n_ema,
+                            float* const* ema, const float* ema_decay, dsg_stream_t stream);
+/* bf16 shadows of the fp32 master weights for the tcgen05 GEMMs of a training step, one launch: jobs_device is an array
+ * of { const float* src; void* dst; void* dst_t; int32 rows, cols, ldd, rows_t; int64 scale_elems; float scale; int32
+ * dst_f32 } (dsg_tr_prep_job_bytes() each): dst [rows, ldd] = src [rows, cols] zero padded (bf16, or fp32 when dst_f32),
+ * dst_t [rows_t, rows] its transpose (the dgrad operand) or NULL, the first scale_elems source elements scaled. */
+DSG_API int dsg_tr_prep_weights(const void* jobs_device, int n_jobs, dsg_stream_t stream);
+DSG_API int dsg_tr_prep_job_bytes(void);
+
 /* ---- per-kernel-class timing (bench.py roofline numbers) ------------------------------------------------------- */
 /* While enabled, every pass_stride-th dsg_denoiser_forward and every dsg_edm_* call brackets each of its kernel
  * launches with a pair of CUDA events on the launching stream.  dsg_profile_read waits for the recorded events
