@@ -333,22 +333,35 @@ shuffle2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
   }
 }
 
-// dst[:, dcol : dcol + n] (=, +=) src[:, scol : scol + n]; src fp32, dst fp32 or bf16 (skip concat and its split)
+// dst[:, dcol : dcol + n] (=, +=) src[:, scol : scol + n]; src fp32, dst fp32 or bf16 (skip concat and its split).
+// VEC: 16-byte accesses (every column count / pitch / offset a multiple of 4); otherwise element-wise.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 copy_cols_kernel(const float* __restrict__ src, int lds, int scol, void* __restrict__ dst, int ldd, int dcol, int ncols,
                  long long M, int dst_bf16, int accumulate) {
-  const int nv = ncols >> 2;
+  constexpr int W = VEC ? 4 : 1;
+  const int nv = ncols / W;
   const long long total = M * nv;
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
     const long long r = i / nv;
-    const int c = static_cast<int>(i - r * nv) * 4;
-    float4 a = ld4(src + r * lds + scol + c);
-    if (dst_bf16) {
-      st4_bf16(static_cast<bf16_t*>(dst) + r * ldd + dcol + c, a);
+    const int c = static_cast<int>(i - r * nv) * W;
+    if (VEC) {
+      float4 a = ld4(src + r * lds + scol + c);
+      if (dst_bf16) {
+        st4_bf16(static_cast<bf16_t*>(dst) + r * ldd + dcol + c, a);
+      } else {
+        float* d = static_cast<float*>(dst) + r * ldd + dcol + c;
+        if (accumulate) { const float4 e = ld4(d); a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w; }
+        st4(d, a);
+      }
     } else {
-      float* d = static_cast<float*>(dst) + r * ldd + dcol + c;
-      if (accumulate) { const float4 e = ld4(d); a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w; }
-      st4(d, a);
+      const float a = src[r * lds + scol + c];
+      if (dst_bf16) {
+        static_cast<bf16_t*>(dst)[r * ldd + dcol + c] = __float2bfloat16_rn(a);
+      } else {
+        float* d = static_cast<float*>(dst) + r * ldd + dcol + c;
+        *d = accumulate ? *d + a : a;
+      }
     }
   }
 }
@@ -892,9 +905,13 @@ int dsg_tr_shuffle2x2(const float* src, float* dst, int B, int H, int W, int C, 
 
 int dsg_tr_copy_cols(const float* src, int lds, int scol, void* dst, int ldd, int dcol, int ncols, long long M, int dst_bf16,
                      int accumulate, dsg_stream_t stream) {
-  DSG_REQUIRE(src && dst && M > 0 && ncols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && scol % 4 == 0 && dcol % 4 == 0,
-              "tr_copy_cols: bad argument");
-  copy_cols_kernel<<<grid_for(M * ncols / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, scol, dst, ldd, dcol, ncols, M, dst_bf16, accumulate);
+  DSG_REQUIRE(src && dst && M > 0 && ncols > 0, "tr_copy_cols: bad argument");
+  const bool vec = ((ncols | lds | ldd | scol | dcol) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  if (vec)
+    copy_cols_kernel<true><<<grid_for(M * ncols / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, scol, dst, ldd, dcol, ncols, M, dst_bf16, accumulate);
+  else
+    copy_cols_kernel<false><<<grid_for(M * ncols), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, lds, scol, dst, ldd, dcol, ncols, M, dst_bf16, accumulate);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

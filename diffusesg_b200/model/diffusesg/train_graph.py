@@ -319,6 +319,12 @@ class TrainPass:
         dw2 = dw.view(dw.shape[0], -1)
         if transposed_weight:   # ConvTranspose2d weight [in, out]: y = x W
             o.wgrad(x_t, dy_t, dw2)
+        elif (dw2.shape[1] * 4) % 16 != 0:
+            # a weight row that is no multiple of 16 bytes (the 26 / 54-channel embeddings) cannot be a TMA destination:
+            # accumulate a zero-padded copy and add its leading columns
+            pad = o.zeros((dw2.shape[0], x_t.shape[0]))
+            o.wgrad(dy_t, x_t, pad)
+            o.copy_cols(pad, 0, dw2, 0, dw2.shape[1], accumulate=True)
         else:
             o.wgrad(dy_t, x_t, dw2, k_in=dw2.shape[1])
         if not need_dx:
