@@ -10,6 +10,7 @@
 // All kernels are HBM-bound row kernels (one warp per token row, 16-byte accesses) except window_attention_bwd_kernel,
 // which is a CUDA-core fp32 kernel (five T x T x 32 products per window-head from shared memory).
 #include <math.h>
+#include <mma.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -70,54 +71,87 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // LayerNorm backward: dx = rstd (g - mean(g) - xhat mean(g xhat)) with g = dy gamma, statistics recomputed from x;
-// dx (+= dx_add when given: the gradient arriving over the residual connection).  dgamma / dbeta: per-CTA
-// shared-memory accumulators, flushed with one atomicAdd per channel per CTA.
+// dx (+= dx_add when given: the gradient arriving over the residual connection).  dgamma / dbeta: a lane owns the same
+// NV float4 column groups in every row, so the parameter gradients accumulate in registers over the rows of the warp and
+// are combined once per CTA (shared memory, then one atomicAdd per channel per CTA).  The row is held in registers.
+template <int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-              const float* dx_add, float* dx, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, long long M, int C) {
+              const float* dx_add, float* dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
   extern __shared__ float sacc[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += 256) sacc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warps = static_cast<long long>(gridDim.x) * 8;
   const int nv = C >> 2;
+  constexpr bool kGammaInRegs = NV <= 3;   // wide rows re-read gamma (L1) instead of holding it: register budget
+  float4 gm[kGammaInRegs ? NV : 1], ag[NV], ab[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    if (kGammaInRegs) gm[k] = v < nv ? ld4(gamma + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.0f / C;
   for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < M; row += warps) {
     const float* xr = x + row * C;
     const float* dr = dy + row * C;
+    float4 a[NV], d[NV];
     float s = 0.f;
-    for (int v = lane; v < nv; v += 32) { const float4 a = ld4(xr + 4 * v); s += (a.x + a.y) + (a.z + a.w); }
-    const float mean = warp_sum(s) / C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      a[k] = v < nv ? ld4(xr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[k] = v < nv ? ld4(dr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (a[k].x + a[k].y) + (a[k].z + a[k].w);
+    }
+    const float mean = warp_sum(s) * invC;
     float q = 0.f;
-    for (int v = lane; v < nv; v += 32) {
-      const float4 a = ld4(xr + 4 * v);
-      const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    }
-    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
-    float m1 = 0.f, m2 = 0.f;
-    for (int v = lane; v < nv; v += 32) {
-      const float4 a = ld4(xr + 4 * v), d = ld4(dr + 4 * v), g = ld4(gamma + 4 * v);
-      const float h0 = (a.x - mean) * rstd, h1 = (a.y - mean) * rstd, h2 = (a.z - mean) * rstd, h3 = (a.w - mean) * rstd;
-      const float g0 = d.x * g.x, g1 = d.y * g.y, g2 = d.z * g.z, g3 = d.w * g.w;
-      m1 += (g0 + g1) + (g2 + g3);
-      m2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
-      atomicAdd(&sacc[4 * v], d.x * h0); atomicAdd(&sacc[4 * v + 1], d.y * h1);
-      atomicAdd(&sacc[4 * v + 2], d.z * h2); atomicAdd(&sacc[4 * v + 3], d.w * h3);
-      atomicAdd(&sacc[C + 4 * v], d.x); atomicAdd(&sacc[C + 4 * v + 1], d.y);
-      atomicAdd(&sacc[C + 4 * v + 2], d.z); atomicAdd(&sacc[C + 4 * v + 3], d.w);
-    }
-    m1 = warp_sum(m1) / C;
-    m2 = warp_sum(m2) / C;
-    for (int v = lane; v < nv; v += 32) {
-      const float4 a = ld4(xr + 4 * v), d = ld4(dr + 4 * v), g = ld4(gamma + 4 * v);
-      float4 o = make_float4(rstd * (d.x * g.x - m1 - (a.x - mean) * rstd * m2), rstd * (d.y * g.y - m1 - (a.y - mean) * rstd * m2),
-                             rstd * (d.z * g.z - m1 - (a.z - mean) * rstd * m2), rstd * (d.w * g.w - m1 - (a.w - mean) * rstd * m2));
-      if (dx_add != nullptr) {
-        const float4 e = ld4(dx_add + row * C + 4 * v);
-        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (lane + 32 * k < nv) {
+        a[k].x -= mean; a[k].y -= mean; a[k].z -= mean; a[k].w -= mean;
+        q += (a[k].x * a[k].x + a[k].y * a[k].y) + (a[k].z * a[k].z + a[k].w * a[k].w);
       }
-      st4(dx + row * C + 4 * v, o);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + kLnEps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      a[k].x *= rstd; a[k].y *= rstd; a[k].z *= rstd; a[k].w *= rstd;      // xhat (zero in the unused groups)
+      ag[k].x += d[k].x * a[k].x; ag[k].y += d[k].y * a[k].y; ag[k].z += d[k].z * a[k].z; ag[k].w += d[k].w * a[k].w;
+      ab[k].x += d[k].x; ab[k].y += d[k].y; ab[k].z += d[k].z; ab[k].w += d[k].w;
+      const float4 gk = kGammaInRegs ? gm[kGammaInRegs ? k : 0]
+                                     : (lane + 32 * k < nv ? ld4(gamma + 4 * (lane + 32 * k)) : make_float4(0.f, 0.f, 0.f, 0.f));
+      d[k].x *= gk.x; d[k].y *= gk.y; d[k].z *= gk.z; d[k].w *= gk.w;   // g = dy gamma
+      m1 += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+      m2 += (d[k].x * a[k].x + d[k].y * a[k].y) + (d[k].z * a[k].z + d[k].w * a[k].w);
+    }
+    m1 = warp_sum(m1) * invC;
+    m2 = warp_sum(m2) * invC;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv) {
+        float4 o = make_float4(rstd * (d[k].x - m1 - a[k].x * m2), rstd * (d[k].y - m1 - a[k].y * m2),
+                               rstd * (d[k].z - m1 - a[k].z * m2), rstd * (d[k].w - m1 - a[k].w * m2));
+        if (dx_add != nullptr) {
+          const float4 e = ld4(dx_add + row * C + 4 * v);
+          o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+        }
+        st4(dx + row * C + 4 * v, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      atomicAdd(&sacc[4 * v], ag[k].x); atomicAdd(&sacc[4 * v + 1], ag[k].y);
+      atomicAdd(&sacc[4 * v + 2], ag[k].z); atomicAdd(&sacc[4 * v + 3], ag[k].w);
+      atomicAdd(&sacc[C + 4 * v], ab[k].x); atomicAdd(&sacc[C + 4 * v + 1], ab[k].y);
+      atomicAdd(&sacc[C + 4 * v + 2], ab[k].z); atomicAdd(&sacc[C + 4 * v + 3], ab[k].w);
     }
   }
   __syncthreads();
@@ -194,18 +228,58 @@ DSG_DEVICE float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710
 DSG_DEVICE float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
+DSG_DEVICE void unpack8(const uint4& w, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = __low2float(h[j]); f[2 * j + 1] = __high2float(h[j]); }
+}
+DSG_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+  return w;
+}
+// n8 = element count / 8; pointers 16-byte aligned
 __global__ void __launch_bounds__(256)
-gelu_fwd_kernel(const bf16_t* __restrict__ pre, bf16_t* __restrict__ out, long long n4) {
-  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
-    const float4 a = ld4_bf16(pre + 4 * i);
-    st4_bf16(out + 4 * i, make_float4(gelu_exact(a.x), gelu_exact(a.y), gelu_exact(a.z), gelu_exact(a.w)));
+gelu_fwd_kernel(const bf16_t* __restrict__ pre, bf16_t* __restrict__ out, long long n8) {
+  const uint4* in = reinterpret_cast<const uint4*>(pre);
+  uint4* o = reinterpret_cast<uint4*>(out);
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += 2 * stride) {
+    const bool two = i + stride < n8;
+    const uint4 w0 = in[i], w1 = two ? in[i + stride] : w0;
+    float f[8];
+    unpack8(w0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
+    o[i] = pack8(f);
+    if (two) {
+      unpack8(w1, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = gelu_exact(f[j]);
+      o[i + stride] = pack8(f);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
-gelu_bwd_kernel(const bf16_t* __restrict__ dh, const bf16_t* __restrict__ pre, bf16_t* __restrict__ dpre, long long n4) {
-  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
-    const float4 a = ld4_bf16(pre + 4 * i), g = ld4_bf16(dh + 4 * i);
-    st4_bf16(dpre + 4 * i, make_float4(g.x * gelu_grad(a.x), g.y * gelu_grad(a.y), g.z * gelu_grad(a.z), g.w * gelu_grad(a.w)));
+gelu_bwd_kernel(const bf16_t* __restrict__ dh, const bf16_t* __restrict__ pre, bf16_t* __restrict__ dpre, long long n8) {
+  const uint4* in = reinterpret_cast<const uint4*>(pre);
+  const uint4* gin = reinterpret_cast<const uint4*>(dh);
+  uint4* o = reinterpret_cast<uint4*>(dpre);
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n8; i += 2 * stride) {
+    const bool two = i + stride < n8;
+    const uint4 a0 = in[i], g0 = gin[i], a1 = two ? in[i + stride] : a0, g1 = two ? gin[i + stride] : g0;
+    float f[8], g[8];
+    unpack8(a0, f); unpack8(g0, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = g[j] * gelu_grad(f[j]);
+    o[i] = pack8(f);
+    if (two) {
+      unpack8(a1, f); unpack8(g1, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = g[j] * gelu_grad(f[j]);
+      o[i + stride] = pack8(f);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
@@ -264,47 +338,166 @@ add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long
 // A CTA owns 32 columns x kTrRows rows: one atomicAdd per column per CTA.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTrRows = 1024;
+// 64 x 64 tiles: a warp reads 64 consecutive columns of a row (two per lane: 128 B of bf16, 256 B of fp32) and writes 64
+// consecutive tokens of a column (a bf16 pair per lane: 128 B), so both directions move full 128-byte lines.
 template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_colsum_kernel(const T* __restrict__ src, bf16_t* __restrict__ dst, bf16_t* __restrict__ cast,
+transpose_colsum_generic_kernel(const T* __restrict__ src, bf16_t* __restrict__ dst, bf16_t* __restrict__ cast,
                         float* __restrict__ colsum, long long M, long long Mp, int C, int scale_cols, float scale) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int c0 = blockIdx.x * 32;
+  __shared__ float tile[64][65];
+  __shared__ float part[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64;
   const long long r_begin = static_cast<long long>(blockIdx.y) * kTrRows;
   const long long r_end = min(Mp, r_begin + kTrRows);   // rows [M, Mp) are the zero padding of the destination pitch
-  const float fac = (c0 + tx < scale_cols) ? scale : 1.f;
-  float csum = 0.f;  // column c0 + tx, rows ty + 8 k
-  for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
+  const int ca = c0 + 2 * lane;                          // this lane's column pair when reading
+  const bool pair_ok = (C & 1) == 0;                     // even C: the pair is aligned and inside the row together
+  const float fa = ca < scale_cols ? scale : 1.f, fb = ca + 1 < scale_cols ? scale : 1.f;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long r0 = r_begin; r0 < r_end; r0 += 64) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long r = r0 + ty + 8 * k;
-      float val = 0.f;
-      if (r < M && c0 + tx < C) {
-        val = static_cast<float>(src[r * C + c0 + tx]);
-        if (cast != nullptr) cast[r * C + c0 + tx] = __float2bfloat16_rn(val);
-        val *= fac;
+    for (int k = 0; k < 8; ++k) {
+      const int rr = warp + 8 * k;
+      const long long r = r0 + rr;
+      float v0 = 0.f, v1 = 0.f;
+      if (r < M) {
+        const T* p = src + r * C + ca;
+        if (pair_ok && ca + 1 < C) {
+          if (sizeof(T) == 2) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(p);
+            v0 = __low2float(h); v1 = __high2float(h);
+          } else {
+            const float2 f = *reinterpret_cast<const float2*>(p);
+            v0 = f.x; v1 = f.y;
+          }
+          if (cast != nullptr) *reinterpret_cast<__nv_bfloat162*>(cast + r * C + ca) = __floats2bfloat162_rn(v0, v1);
+        } else {
+          if (ca < C) { v0 = static_cast<float>(p[0]); if (cast != nullptr) cast[r * C + ca] = __float2bfloat16_rn(v0); }
+          if (ca + 1 < C) { v1 = static_cast<float>(p[1]); if (cast != nullptr) cast[r * C + ca + 1] = __float2bfloat16_rn(v1); }
+        }
+        v0 *= fa; v1 *= fb;
       }
-      csum += val;
-      tile[ty + 8 * k][tx] = val;
+      s0 += v0; s1 += v1;
+      tile[rr][2 * lane] = v0;
+      tile[rr][2 * lane + 1] = v1;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = ty + 8 * k;   // column inside the tile
-      const long long r = r0 + tx;
-      if (r < r_end && c0 + c < C) dst[static_cast<long long>(c0 + c) * Mp + r] = __float2bfloat16_rn(tile[tx][c]);
+    for (int k = 0; k < 8; ++k) {
+      const int c = warp + 8 * k;                 // column inside the tile
+      const long long r = r0 + 2 * lane;          // token pair (Mp is even: the pair is inside the row together)
+      if (c0 + c < C && r < r_end)
+        *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<long long>(c0 + c) * Mp + r) =
+            __floats2bfloat162_rn(tile[2 * lane][c], tile[2 * lane + 1][c]);
     }
     __syncthreads();
   }
   if (colsum != nullptr) {
-    tile[ty][tx] = csum;
+    part[warp][2 * lane] = s0;
+    part[warp][2 * lane + 1] = s1;
     __syncthreads();
-    if (ty == 0 && c0 + tx < C) {
+    if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+      atomicAdd(&colsum[c0 + threadIdx.x], t);
+    }
+  }
+}
+
+// The fast path (C % 8 == 0): every global access is 16 bytes and a thread issues all loads of a tile before it uses any
+// (the first versions had one 2- or 4-byte load in flight per thread: ~1 TB/s).  Tile = 64 tokens x 64 columns, held in
+// shared memory as bf16 [64][72].  Load: thread = (row, 8-column group), 2 groups per thread; store: thread = (column,
+// 8-token group): eight 2-byte shared-memory reads down a column (a warp covers 32 consecutive columns: conflict free)
+// packed into one 16-byte store.  Column sums: a thread keeps the same 8 columns for all its rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_colsum_kernel(const T* __restrict__ src, bf16_t* __restrict__ dst, bf16_t* __restrict__ cast,
+                        float* __restrict__ colsum, long long M, long long Mp, int C, int scale_cols, float scale) {
+  constexpr int P = 72;
+  __shared__ __align__(16) bf16_t tile[64 * P];
+  __shared__ float part[32][64];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * 64;
+  const long long r_begin = static_cast<long long>(blockIdx.y) * kTrRows;
+  const long long r_end = min(Mp, r_begin + kTrRows);
+  const int q = t & 7, lr = t >> 3;            // load role: column group, row (and row + 32)
+  const int cq = c0 + 8 * q;
+  const bool col_ok = cq < C;                  // C % 8 == 0: a group is inside the row or outside as a whole
+  float fac[8], csum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fac[j] = (cq + j < scale_cols) ? scale : 1.f; csum[j] = 0.f; }
+  const int sc = t & 63, sg = t >> 6;          // store role: column, token group (and group + 4)
+  // raw 16-byte words of the tile being loaded: the loads of tile k + 1 are issued before the store phase of tile k
+  constexpr int kWords = sizeof(T) == 2 ? 1 : 2;
+  uint4 raw[2][kWords];
+  auto issue_loads = [&](long long r0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r = r0 + lr + 32 * u;
+      const bool ok = col_ok && r < M;
+      const uint4* p = reinterpret_cast<const uint4*>(src + (ok ? r * C + cq : 0));
+#pragma unroll
+      for (int k = 0; k < kWords; ++k) raw[u][k] = ok ? p[k] : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  issue_loads(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += 64) {
+    float v[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (sizeof(T) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[u][2 * j] = __low2float(h[j]); v[u][2 * j + 1] = __high2float(h[j]); }
+      } else {
+        const float* f = reinterpret_cast<const float*>(&raw[u][0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = f[j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r = r0 + lr + 32 * u;
+      if (cast != nullptr && col_ok && r < M) {
+        uint4 w;
+        w.x = pack_bf16x2(v[u][0], v[u][1]); w.y = pack_bf16x2(v[u][2], v[u][3]);
+        w.z = pack_bf16x2(v[u][4], v[u][5]); w.w = pack_bf16x2(v[u][6], v[u][7]);
+        *reinterpret_cast<uint4*>(cast + r * C + cq) = w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[u][j] *= fac[j]; csum[j] += v[u][j]; }
+      uint4 w;
+      w.x = pack_bf16x2(v[u][0], v[u][1]); w.y = pack_bf16x2(v[u][2], v[u][3]);
+      w.z = pack_bf16x2(v[u][4], v[u][5]); w.w = pack_bf16x2(v[u][6], v[u][7]);
+      *reinterpret_cast<uint4*>(&tile[(lr + 32 * u) * P + 8 * q]) = w;
+    }
+    __syncthreads();
+    if (r0 + 64 < r_end) issue_loads(r0 + 64);
+    if (c0 + sc < C) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = sg + 4 * u;
+        const unsigned short* col = reinterpret_cast<const unsigned short*>(tile) + (8 * g) * P + sc;
+        uint4 w;
+        w.x = col[0] | (static_cast<unsigned>(col[P]) << 16);
+        w.y = col[2 * P] | (static_cast<unsigned>(col[3 * P]) << 16);
+        w.z = col[4 * P] | (static_cast<unsigned>(col[5 * P]) << 16);
+        w.w = col[6 * P] | (static_cast<unsigned>(col[7 * P]) << 16);
+        *reinterpret_cast<uint4*>(dst + static_cast<long long>(c0 + sc) * Mp + r0 + 8 * g) = w;
+      }
+    }
+    __syncthreads();
+  }
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[lr][8 * q + j] = csum[j];
+    __syncthreads();
+    if (t < 64 && c0 + t < C) {
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += tile[k][tx];
-      atomicAdd(&colsum[c0 + tx], s);
+      for (int k = 0; k < 32; ++k) s += part[k][t];
+      atomicAdd(&colsum[c0 + t], s);
     }
   }
 }
@@ -701,6 +894,175 @@ window_attention_bwd_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The same backward on the warp-level tensor cores (wmma m16n16k16, bf16 operands, fp32 accumulation): the five products
+// of a window-head are 4 x 4 (x 2) tiles; the softmax / dS pass stays fp32, dbias accumulates the fp32 dS.  P and dS are
+// rounded to bf16 for the second set of products (as the forward kernel rounds P).  Token counts that are no multiple of
+// 16 (10 x 10 windows) are zero padded to TP.  Shared-memory plan per CTA (PF = fp32 pitch of S / dP, >= TP + 16):
+//   sQ sK sV sDO  bf16 [TP][40]
+//   sS, sD        fp32 [TP][PF]: S -> exp -> (in place, row start) P as bf16; the upper half of each row then stages
+//                 the fp32 outputs dV (sS) / dQ (sD), the lower half of sS stages dK once P is dead
+//   sAcc          fp32 [T][T] dbias accumulator, sTok int [TP]
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kQP = 40;
+__global__ void __launch_bounds__(256)
+window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ datt, const float* __restrict__ bias,
+                               const float* __restrict__ mask, bf16_t* __restrict__ dqkv, float* __restrict__ dbias,
+                               int batch, int res, int w, int shift, int heads, int items_per_cta) {
+  using namespace nvcuda;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int T = w * w, TP = (T + 15) & ~15, NT = TP >> 4, C = heads * kHd;
+  const int PF = (TP + 16 > 80) ? TP + 16 : 80;
+  bf16_t* sQ = reinterpret_cast<bf16_t*>(smraw);
+  bf16_t* sK = sQ + TP * kQP;
+  bf16_t* sV = sK + TP * kQP;
+  bf16_t* sDO = sV + TP * kQP;
+  float* sS = reinterpret_cast<float*>(sDO + TP * kQP);
+  float* sD = sS + TP * PF;
+  float* sAcc = sD + TP * PF;
+  int* sTok = reinterpret_cast<int*>(sAcc + T * T);
+  bf16_t* sPb = reinterpret_cast<bf16_t*>(sS);    // P, bf16, row pitch 2 PF
+  bf16_t* sDb = reinterpret_cast<bf16_t*>(sD);    // dS
+  const int LDB = 2 * PF;
+  float* stV = sS + PF / 2;                       // fp32 staging [TP][32], row pitch PF
+  float* stQ = sD + PF / 2;
+  float* stK = sS;
+  const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = res / w, nW = nw * nw;
+  const int total = batch * nW;
+  const int item0 = blockIdx.x * items_per_cta, item1 = min(total, item0 + items_per_cta);
+  for (int i = threadIdx.x; i < T * T; i += 256) sAcc[i] = 0.f;
+  const float* bh = bias + static_cast<size_t>(h) * T * T;
+  for (int item = item0; item < item1; ++item) {
+    const int b = item / nW, win = item - b * nW;
+    const int wy = win / nw, wx = win - wy * nw;
+    __syncthreads();
+    for (int t = threadIdx.x; t < TP; t += 256) {
+      const int r = t / w, c = t - r * w;
+      sTok[t] = t < T ? (b * res + (wy * w + r + shift) % res) * res + (wx * w + c + shift) % res : -1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TP * 16; i += 256) {   // 4 matrices x 4 16-byte chunks per token
+      const int t = i >> 4, m = (i >> 2) & 3, ch = i & 3;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      const int tok = sTok[t];
+      if (tok >= 0) {
+        const bf16_t* p = m < 3 ? qkv + static_cast<size_t>(tok) * 3 * C + m * C + h * kHd : datt + static_cast<size_t>(tok) * C + h * kHd;
+        val = *reinterpret_cast<const uint4*>(p + 8 * ch);
+      }
+      bf16_t* d = (m == 0 ? sQ : m == 1 ? sK : m == 2 ? sV : sDO) + t * kQP + 8 * ch;
+      *reinterpret_cast<uint4*>(d) = val;
+    }
+    __syncthreads();
+    // S = Q K^T and dP = dO V^T
+    for (int job = warp; job < 2 * NT * NT; job += 8) {
+      const int which = job / (NT * NT), tile = job - which * NT * NT;
+      const int ti = tile / NT, tj = tile - ti * NT;
+      const bf16_t* A = which == 0 ? sQ : sDO;
+      const bf16_t* Bt = which == 0 ? sK : sV;
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> fc;
+      wmma::fill_fragment(fc, 0.f);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa;
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb;
+        wmma::load_matrix_sync(fa, A + ti * 16 * kQP + kk * 16, kQP);
+        wmma::load_matrix_sync(fb, Bt + tj * 16 * kQP + kk * 16, kQP);
+        wmma::mma_sync(fc, fa, fb, fc);
+      }
+      wmma::store_matrix_sync((which == 0 ? sS : sD) + ti * 16 * PF + tj * 16, fc, PF, wmma::mem_row_major);
+    }
+    __syncthreads();
+    const float* mk = (mask != nullptr && shift > 0) ? mask + static_cast<size_t>(win) * T * T : nullptr;
+    for (int i = warp; i < TP; i += 8) {
+      float* srow = sS + i * PF;
+      float* drow = sD + i * PF;
+      bf16_t* prow = sPb + i * LDB;
+      bf16_t* dsrow = sDb + i * LDB;
+      if (i >= T) {   // padding rows: zero operands
+        for (int j = lane; j < TP; j += 32) { prow[j] = __float2bfloat16_rn(0.f); dsrow[j] = __float2bfloat16_rn(0.f); }
+        continue;
+      }
+      float mx = -INFINITY;
+      for (int j = lane; j < T; j += 32) {
+        const float v = srow[j] + bh[i * T + j] + (mk != nullptr ? mk[i * T + j] : 0.f);
+        srow[j] = v;
+        mx = fmaxf(mx, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      for (int j = lane; j < T; j += 32) { const float e = __expf(srow[j] - mx); srow[j] = e; sum += e; }
+      const float inv = 1.0f / warp_sum(sum);
+      float dot = 0.f;
+      for (int j = lane; j < T; j += 32) dot += srow[j] * inv * drow[j];
+      dot = warp_sum(dot);
+      // last pass: P and dS as bf16 at the start of their own rows.  The bf16 element j lies inside the fp32 element j / 2,
+      // which an EARLIER trip of this loop consumed - except in the first trip, where the reads finish before the writes.
+      for (int j0 = 0; j0 < TP; j0 += 32) {
+        const int j = j0 + lane;
+        float pv = 0.f, ds = 0.f;
+        if (j < T) {
+          pv = srow[j] * inv;
+          ds = pv * (drow[j] - dot);
+          sAcc[i * T + j] += ds;
+        }
+        __syncwarp();
+        if (j < TP) { prow[j] = __float2bfloat16_rn(pv); dsrow[j] = __float2bfloat16_rn(ds); }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // dV = P^T dO -> stV, dQ = dS K -> stQ
+    for (int job = warp; job < 2 * NT * 2; job += 8) {
+      const int which = job / (NT * 2), tile = job - which * NT * 2;
+      const int tr = tile >> 1, td = tile & 1;
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> fc;
+      wmma::fill_fragment(fc, 0.f);
+      for (int kt = 0; kt < NT; ++kt) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+        if (which == 0) {
+          wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;   // A(j, i) = P[i][j]
+          wmma::load_matrix_sync(fa, sPb + kt * 16 * LDB + tr * 16, LDB);
+          wmma::load_matrix_sync(fb, sDO + kt * 16 * kQP + td * 16, kQP);
+          wmma::mma_sync(fc, fa, fb, fc);
+        } else {
+          wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa;   // A(i, j) = dS[i][j]
+          wmma::load_matrix_sync(fa, sDb + tr * 16 * LDB + kt * 16, LDB);
+          wmma::load_matrix_sync(fb, sK + kt * 16 * kQP + td * 16, kQP);
+          wmma::mma_sync(fc, fa, fb, fc);
+        }
+      }
+      wmma::store_matrix_sync((which == 0 ? stV : stQ) + tr * 16 * PF + td * 16, fc, PF, wmma::mem_row_major);
+    }
+    __syncthreads();
+    // dK = dS^T Q -> stK (the bf16 P it overwrites is dead)
+    for (int job = warp; job < NT * 2; job += 8) {
+      const int tr = job >> 1, td = job & 1;
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> fc;
+      wmma::fill_fragment(fc, 0.f);
+      for (int kt = 0; kt < NT; ++kt) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;     // A(j, i) = dS[i][j]
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb;
+        wmma::load_matrix_sync(fa, sDb + kt * 16 * LDB + tr * 16, LDB);
+        wmma::load_matrix_sync(fb, sQ + kt * 16 * kQP + td * 16, kQP);
+        wmma::mma_sync(fc, fa, fb, fc);
+      }
+      wmma::store_matrix_sync(stK + tr * 16 * PF + td * 16, fc, PF, wmma::mem_row_major);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * 48; i += 256) {   // (token, matrix, channel pair)
+      const int t = i / 48, rem = i - t * 48, m = rem >> 4, d = (rem & 15) * 2;
+      const float* st = (m == 0 ? stQ : m == 1 ? stK : stV) + t * PF + d;
+      *reinterpret_cast<__nv_bfloat162*>(dqkv + static_cast<size_t>(sTok[t]) * 3 * C + m * C + h * kHd + d) =
+          __floats2bfloat162_rn(st[0], st[1]);
+    }
+  }
+  __syncthreads();
+  float* dbh = dbias + static_cast<size_t>(h) * T * T;
+  for (int i = threadIdx.x; i < T * T; i += 256) atomicAdd(&dbh[i], sAcc[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Optimiser: global gradient norm (nn.utils.clip_grad_norm_, trainer_node_adj.py:174), Adam (torch.optim.Adam
 // semantics incl. L2 weight decay, utils/learning_utils.py:126-145) and up to 8 exponential moving averages
 // (ema_pytorch.EMA.update with update_every 1, :148-166) over ONE flat fp32 parameter buffer in one launch.
@@ -811,8 +1173,17 @@ int dsg_tr_ln_fwd(const float* x, const float* gamma, const float* beta, void* y
 
 int dsg_tr_ln_bwd(const float* dy, const float* x, const float* gamma, const float* dx_add, float* dx, float* dgamma,
                   float* dbeta, long long M, int C, dsg_stream_t stream) {
-  DSG_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && M > 0 && C > 0 && C % 4 == 0 && C <= 4096, "tr_ln_bwd: bad argument");
-  ln_bwd_kernel<<<grid_for(M, 8 * 16, 4), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  DSG_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "tr_ln_bwd: bad argument (C <= 2048)");
+  const unsigned grid = grid_for(M, 8 * 16, 4);
+  const size_t smem = 2 * C * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nvw = (C / 4 + 31) / 32;   // float4 groups per lane
+  if (nvw <= 1) ln_bwd_kernel<1><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  else if (nvw <= 2) ln_bwd_kernel<2><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  else if (nvw <= 3) ln_bwd_kernel<3><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  else if (nvw <= 6) ln_bwd_kernel<6><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  else if (nvw <= 12) ln_bwd_kernel<12><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
+  else ln_bwd_kernel<16><<<grid, 256, smem, st>>>(dy, x, gamma, dx_add, dx, dgamma, dbeta, M, C);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -837,11 +1208,13 @@ int dsg_tr_film_silu_bwd(const float* dout, const float* v, const float* film, i
 }
 
 int dsg_tr_gelu(const void* pre, const void* dh, void* out, long long n, dsg_stream_t stream) {
-  DSG_REQUIRE(pre && out && n > 0 && n % 4 == 0, "tr_gelu: bad argument");
+  DSG_REQUIRE(pre && out && n > 0 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out) |
+                                                      reinterpret_cast<uintptr_t>(dh)) & 15) == 0,
+              "tr_gelu: bad argument (n %% 8 == 0, 16-byte aligned tensors)");
   if (dh == nullptr)
-    gelu_fwd_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 4);
+    gelu_fwd_kernel<<<grid_for(n / 8, 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 8);
   else
-    gelu_bwd_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(dh), static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 4);
+    gelu_bwd_kernel<<<grid_for(n / 8, 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(dh), static_cast<const bf16_t*>(pre), static_cast<bf16_t*>(out), n / 8);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -887,11 +1260,21 @@ int dsg_tr_transpose(const void* src, int src_is_bf16, void* dst_t, void* cast, 
                      int C, int scale_cols, float scale, dsg_stream_t stream) {
   DSG_REQUIRE(src && dst_t && M > 0 && C > 0 && Mp >= M && Mp % 16 == 0,
               "tr_transpose: bad argument (destination pitch Mp %% 16 == 0: TMA pitch and the GEMM's K step)");
-  const dim3 grid((C + 31) / 32, static_cast<unsigned>((Mp + kTrRows - 1) / kTrRows));
-  if (src_is_bf16)
-    transpose_colsum_kernel<bf16_t><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(src), static_cast<bf16_t*>(dst_t), static_cast<bf16_t*>(cast), colsum, M, Mp, C, scale_cols, scale);
-  else
-    transpose_colsum_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(src), static_cast<bf16_t*>(dst_t), static_cast<bf16_t*>(cast), colsum, M, Mp, C, scale_cols, scale);
+  const dim3 grid((C + 63) / 64, static_cast<unsigned>((Mp + kTrRows - 1) / kTrRows));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fast = C % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_t) & 15) == 0 &&
+                    (cast == nullptr || (reinterpret_cast<uintptr_t>(cast) & 15) == 0);
+  bf16_t* d = static_cast<bf16_t*>(dst_t);
+  bf16_t* cs = static_cast<bf16_t*>(cast);
+  if (src_is_bf16) {
+    const bf16_t* sp = static_cast<const bf16_t*>(src);
+    if (fast) transpose_colsum_kernel<bf16_t><<<grid, 256, 0, st>>>(sp, d, cs, colsum, M, Mp, C, scale_cols, scale);
+    else transpose_colsum_generic_kernel<bf16_t><<<grid, 256, 0, st>>>(sp, d, cs, colsum, M, Mp, C, scale_cols, scale);
+  } else {
+    const float* sp = static_cast<const float*>(src);
+    if (fast) transpose_colsum_kernel<float><<<grid, 256, 0, st>>>(sp, d, cs, colsum, M, Mp, C, scale_cols, scale);
+    else transpose_colsum_generic_kernel<float><<<grid, 256, 0, st>>>(sp, d, cs, colsum, M, Mp, C, scale_cols, scale);
+  }
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -996,11 +1379,18 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
               "tr_window_attention_bwd: bad argument");
   DSG_REQUIRE(shift == 0 || mask != nullptr, "tr_window_attention_bwd: shifted windows need the attention mask");
   const int T = window * window;
-  const size_t smem = (static_cast<size_t>(4) * T * kHdP + 2 * static_cast<size_t>(T) * (T + 1) + static_cast<size_t>(T) * T) * 4 + static_cast<size_t>(T) * 4;
-  DSG_REQUIRE(smem <= 227 * 1024, "tr_window_attention_bwd: %d-token windows do not fit shared memory (T <= 121)", T);
+  static const bool fp32_only = getenv("DSG_ATTN_BWD_FP32") != nullptr && getenv("DSG_ATTN_BWD_FP32")[0] == '1';
+  const int TP = (T + 15) & ~15, PF = (TP + 16 > 80) ? TP + 16 : 80;
+  const size_t smem_tc = static_cast<size_t>(4) * TP * kQP * 2 + static_cast<size_t>(2) * TP * PF * 4 + static_cast<size_t>(T) * T * 4 + static_cast<size_t>(TP) * 4;
+  const size_t smem_f32 = (static_cast<size_t>(4) * T * kHdP + 2 * static_cast<size_t>(T) * (T + 1) + static_cast<size_t>(T) * T) * 4 + static_cast<size_t>(T) * 4;
+  const bool tc = !fp32_only && smem_tc <= 227 * 1024;
+  const size_t smem = tc ? smem_tc : smem_f32;
+  DSG_REQUIRE(smem <= 227 * 1024, "tr_window_attention_bwd: %d-token windows do not fit shared memory (T <= 100)", T);
   static PerDeviceOnce configured;
-  if (configured.first())
+  if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
   const int total = batch * (res / window) * (res / window);
   // one atomicAdd pass over dbias per CTA: keep the CTA count near two waves
   const int resident = static_cast<int>((227 * 1024) / smem) > 0 ? static_cast<int>((227 * 1024) / smem) : 1;
@@ -1008,9 +1398,14 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   if (ctas_x > total) ctas_x = total;
   const int per = (total + ctas_x - 1) / ctas_x;
   ctas_x = (total + per - 1) / per;
-  window_attention_bwd_kernel<<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
-      res, window, shift, heads, per);
+  if (tc)
+    window_attention_bwd_tc_kernel<<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
+        res, window, shift, heads, per);
+  else
+    window_attention_bwd_kernel<<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
+        res, window, shift, heads, per);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

@@ -67,7 +67,7 @@ class TrainState:
             pos += _up(named[k].numel(), 4)
         self.numel = pos
         self.order = order
-        with torch.cuda.device(device):
+        with native.device_guard(device):
             self.flat = torch.zeros(pos, dtype=F32, device=device)
             self.grad = torch.zeros(pos, dtype=F32, device=device)
         self.shapes = {k: tuple(named[k].shape) for k in order}
@@ -126,7 +126,7 @@ class TrainState:
             total += _up(rows * ldd, 64)
             if want_t:
                 total_t += _up(rows * ldd, 64)
-        with torch.cuda.device(self.dev):
+        with native.device_guard(self.dev):
             self._wb_flat = torch.zeros(total, dtype=BF16, device=self.dev)
             self._wbt_flat = torch.zeros(max(total_t, 64), dtype=BF16, device=self.dev)
         scale = HEAD_DIM ** -0.5
@@ -142,7 +142,7 @@ class TrainState:
             if name.endswith(".attn.qkv"):
                 dim = cols
                 j.scale, j.scale_elems = scale, dim * dim   # the q rows carry head_dim^-1/2 (diffusesg.py:118)
-                with torch.cuda.device(self.dev):
+                with native.device_guard(self.dev):
                     self.qkv_bias[name] = torch.zeros(3 * dim, dtype=F32, device=self.dev)
                 jb = _PrepJob()
                 jb.src, jb.dst = self.w(name + ".bias").data_ptr(), self.qkv_bias[name].data_ptr()
@@ -585,11 +585,12 @@ class TrainPass:
             return
         import torch.distributed as dist
         lo = s.offs["read_out.0.weight"]   # flat order: FiLM + noise MLP, embedding, encoder, decoder, then the heads
-        if what == "heads":
-            rng = s.grad[lo:]
-        else:
-            rng = s.grad[:lo]
-        s.ddp_work.append(dist.all_reduce(rng, op=dist.ReduceOp.AVG, group=s.ddp_group, async_op=True))
+        rng = s.grad[lo:] if what == "heads" else s.grad[:lo]
+        if dist.get_backend(s.ddp_group) == "nccl":
+            s.ddp_work.append(dist.all_reduce(rng, op=dist.ReduceOp.AVG, group=s.ddp_group, async_op=True))
+        else:   # gloo (the CPU tests of the host logic) has no AVG
+            dist.all_reduce(rng, op=dist.ReduceOp.SUM, group=s.ddp_group)
+            rng.div_(dist.get_world_size(s.ddp_group))
         if what == "rest":
             for wk in s.ddp_work:
                 wk.wait()

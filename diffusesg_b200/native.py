@@ -199,6 +199,8 @@ def profile_stop() -> None:
 def device_guard(device):
     """Make `device` current for the duration of a native call (the library's launches and one-time per-device
     setup use the current device); free when it already is."""
+    if isinstance(device, torch.device) and device.type != "cuda":
+        return contextlib.nullcontext()
     idx = device.index if isinstance(device, torch.device) else device
     if idx is None or torch.cuda.current_device() == idx:
         return contextlib.nullcontext()

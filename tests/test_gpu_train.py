@@ -226,8 +226,9 @@ def test_window_attention_backward(batch, res, w, shift, heads):
     native.check(native.lib().dsg_tr_bias_gather(None, index.data_ptr(), dbias.data_ptr(), heads, t, 1, dtable.data_ptr(), o.st),
                  "bias_scatter")
     torch.cuda.synchronize()
-    assert _rel(dqkv.float(), q32.grad) < 5e-3, _rel(dqkv.float(), q32.grad)     # bf16 rounding of the stored gradient
-    assert _rel(dtable, tab.grad) < 1e-4, _rel(dtable, tab.grad)
+    # bf16 operands of the tensor-core products (P and dS are rounded like the forward's P) and of the stored gradient
+    assert _rel(dqkv.float(), q32.grad) < 1e-2, _rel(dqkv.float(), q32.grad)
+    assert _rel(dtable, tab.grad) < 2e-3, _rel(dtable, tab.grad)     # fp32 dS from bf16-operand S / dP tiles
 
 
 # ---------------------------------------------------------------------------------------------------------

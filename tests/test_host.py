@@ -374,3 +374,87 @@ def test_skip_plan_row_maps_compose():
     back = dense_ref.reshape(-1)[maps["c2_from_dense"]]                                     # c2 <- dense
     keep = x2 != -7.0
     assert np.array_equal(back[keep], x2[keep])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training step, host logic: flat parameter layout, ema_pytorch's decay schedule, data-parallel ranges
+# ---------------------------------------------------------------------------------------------------------
+def test_train_state_flat_layout():
+    from diffusesg_b200.model.diffusesg.train_graph import TrainState
+    m = _module(CONFIGS["tiny"])
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    ts = TrainState(m, torch.device("cpu"))
+    assert ts.attached() and ts.numel % 4 == 0
+    for k, p in m.named_parameters():
+        assert torch.equal(p.data, before[k]) and ts.offs[k] % 4 == 0, k               # values kept, 16-byte aligned
+        assert p.data.data_ptr() == ts.flat.data_ptr() + 4 * ts.offs[k], k               # views into the flat buffer
+    spans = sorted((ts.offs[k], ts.offs[k] + before[k].numel()) for k in before)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))                           # no overlap
+    # the FiLM generators of all blocks form ONE [film_total, 512] matrix at the start, their biases follow
+    ft = ts.film_total
+    assert ft == sum(v.shape[0] for k, v in before.items() if k.endswith("affine.weight"))
+    w = ts.flat[: ft * 512].view(ft, 512)
+    off = ts.film_off["down_layers.1.blocks.1.affine"]
+    assert torch.equal(w[off: off + 384], before["down_layers.1.blocks.1.affine.weight"])
+    assert torch.equal(ts.flat[ft * 512 + off: ft * 512 + off + 384], before["down_layers.1.blocks.1.affine.bias"])
+    # the read-out range (reduced first under DDP) is the tail of the buffer and holds nothing else
+    lo = ts.offs["read_out.0.weight"]
+    tail = {k for k in before if ts.offs[k] >= lo}
+    assert tail == {k for k in before if k.startswith(("read_out.", "norm.", "readout_"))}
+    assert ts.attach_grads() and not ts.attach_grads()
+    assert all(p.grad.data_ptr() == ts.grad.data_ptr() + 4 * ts.offs[k] for k, p in m.named_parameters())
+    m2 = copy.deepcopy(m)                                    # the EMA copy gets its own storage, not the flat views
+    assert m2.__dict__.get("_train_state") is None
+    assert next(m2.parameters()).data_ptr() != next(m.parameters()).data_ptr()
+
+
+def test_native_ema_follows_the_ema_pytorch_schedule():
+    """ema_pytorch.EMA(beta, update_every=1, update_after_step=0, inv_gamma=1, power=1): copy, copy, then
+    decay = min(beta, 1 - 1 / (1 + epoch)), epoch = number of updates so far (utils/learning_utils.py:148-166)."""
+    from diffusesg_b200.utils.train_utils import NativeEMA
+    e = NativeEMA.__new__(NativeEMA)
+    e.beta, e.step, e.initted = 0.9, 0, False
+    e.denoiser = types.SimpleNamespace(invalidate_native=lambda: None)
+    got = []
+    for _ in range(12):
+        got.append(e.next_decay())
+        e._advance()
+    want = [0.0, 0.0] + [min(0.9, 1 - 1 / (1 + k)) for k in range(2, 12)]
+    assert got == pytest.approx(want)
+
+
+def _ddp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from diffusesg_b200.model.diffusesg.train_graph import TrainPass
+    from diffusesg_b200.utils.train_utils import NativeDDP, find_denoiser
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                       # different initial weights per rank
+        net = _module(CONFIGS["tiny"])
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(torch.randn_like(p) * 0.01)
+        model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False)
+        ddp = NativeDDP(model)
+        ts = find_denoiser(ddp).__dict__["_train_state"]
+        ts.attach_grads()
+        ts.grad.fill_(float(rank + 1))                      # what a backward on this rank would have left
+        tp = TrainPass(ts)
+        tp._reduce_range("heads")
+        lo = ts.offs["read_out.0.weight"]
+        mid = (float(ts.grad[:lo].mean()), float(ts.grad[lo:].mean()))
+        tp._reduce_range("rest")
+        torch.save(dict(flat=ts.flat.clone(), grad=ts.grad.clone(), mid=mid), os.path.join(out_dir, f"d{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_native_ddp_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    d0, d1 = torch.load(tmp_path / "d0.pt"), torch.load(tmp_path / "d1.pt")
+    assert torch.equal(d0["flat"], d1["flat"])                                   # parameters broadcast from rank 0
+    assert d0["mid"] == (1.0, 1.5) and d1["mid"] == (2.0, 1.5)                   # read-out range reduced first
+    assert float(d0["grad"].min()) == 1.5 == float(d0["grad"].max()) and torch.equal(d0["grad"], d1["grad"])
