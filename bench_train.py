@@ -134,7 +134,7 @@ def run_native(args, cfg, rank, local_rank, world):
     wrapped = NativeDDP(model) if world > 1 else model
     gen = NodeAdjEDMObjectiveGenerator("edm", "edm", dev=device, symmetric_noise=False)
     loss_fn = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=1.0, objective="edm")
-    adj_h, node_h, flags_h = [t.pin_memory() for t in clean_batch(cfg, args.batch, 1234 + rank)]
+    adj_h, node_h, flags_h = [t.pin_memory() for t in clean_batch(cfg, args.batch, args.data_seed + rank)]
     adj_d, node_d, flags_d = adj_h.to(device), node_h.to(device), flags_h.to(device)
     last = {}
 
@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--config", default="vg", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--data-seed", type=int, default=1234, help="seed of the synthetic clean batch (+ rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

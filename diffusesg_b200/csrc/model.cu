@@ -40,7 +40,26 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED); }
+// test hook (dsg_debug_set_smem_poison): after every counted launch, a kernel on the legacy default stream overwrites the
+// shared memory of every SM with a bit pattern - a kernel that reads shared memory it never wrote then shows it
+static unsigned g_smem_poison = 0;
+static bool g_smem_poison_on = false;
+__global__ void poison_smem_kernel(unsigned pattern, int words) {
+  extern __shared__ unsigned psm[];
+  for (int i = threadIdx.x; i < words; i += blockDim.x) psm[i] = pattern;
+  __syncthreads();
+  if (psm[(threadIdx.x * 7) % words] != pattern) __trap();   // keeps the stores alive
+}
+static void poison_smem_now() {
+  constexpr int bytes = 200 * 1024;
+  static PerDeviceOnce configured;
+  if (configured.first()) cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  poison_smem_kernel<<<device_sm_count() * 2, 256, bytes, 0>>>(g_smem_poison, bytes / 4);
+}
+void count_launch(int n) {
+  __atomic_fetch_add(&g_launches, static_cast<unsigned long long>(n), __ATOMIC_RELAXED);
+  if (g_smem_poison_on) poison_smem_now();
+}
 
 // ------------------------------------------------------------------------------------------------
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers)
@@ -663,6 +682,10 @@ int run_block(dsg_model* m, const Block& b, const Workspace& w, const float* x_i
 extern "C" {
 
 int dsg_abi_version(void) { return DSG_ABI_VERSION; }
+void dsg_debug_set_smem_poison(unsigned pattern, int enable) {
+  g_smem_poison = pattern;
+  g_smem_poison_on = enable != 0;
+}
 const char* dsg_last_error(void) { return g_err; }
 uint64_t dsg_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 

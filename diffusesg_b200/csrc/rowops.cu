@@ -434,11 +434,13 @@ __global__ void node_proj_kernel(const float* __restrict__ node, const float* __
   const int cin = self_cond ? 2 * c_n : c_n;  // <= 32 (checked by the launcher)
   const long long rows = static_cast<long long>(batch) * n;
   const long long row0 = static_cast<long long>(blockIdx.x) * kNodeRows;
-  for (int idx = threadIdx.x; idx < kNodeRows * cin; idx += blockDim.x) {
-    const int r = idx / cin, ch = idx - r * cin;
+  // all 32 channel slots are written: the product loop below runs over 32 channels with zero weights beyond cin, and
+  // 0 x (whatever an earlier kernel left in this SM's shared memory) is NaN whenever the leftover is a NaN / Inf pattern
+  for (int idx = threadIdx.x; idx < kNodeRows * 32; idx += blockDim.x) {
+    const int r = idx >> 5, ch = idx & 31;
     const long long bi = row0 + r;
     float v = 0.f;
-    if (bi < rows) {
+    if (bi < rows && ch < cin) {
       if (self_cond && ch < c_n) {
         v = sc_node ? sc_node[bi * c_n + ch] : 0.f;
       } else {

@@ -134,6 +134,7 @@ _SIGNATURES = {
     "dsg_profile_stop": (None, []),
     "dsg_proj_ln": (C.c_int, [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]),
     "dsg_debug_set_stop_after": (None, [C.c_int]),
+    "dsg_debug_set_smem_poison": (None, [C.c_uint, C.c_int]),
     "dsg_debug_trace_next_mlp": (None, [C.c_void_p]),
     "dsg_debug_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }

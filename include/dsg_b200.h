@@ -407,6 +407,12 @@ DSG_API void dsg_debug_set_stop_after(int n_stages);
 /* The next fused-MLP launch records a clock64 timeline of its CTA 0 into device_buffer
  * ([64 chunks][18 warps][8 events] int64, zero it first); used by tools/mlp_trace.py. */
 DSG_API void dsg_debug_trace_next_mlp(long long* device_buffer);
+/* While enabled, every kernel launch of the library is followed by a kernel (legacy default stream: use it with torch's
+ * default stream only) that fills the shared memory of every SM with `pattern` (e.g. 0x7fc00000, a NaN): what a foreign
+ * kernel - NCCL, another library - may leave behind.  A kernel that reads shared memory it never wrote, e.g. a
+ * zero-weighted padding slot, then produces NaN (tests/test_gpu_denoiser.py::test_kernels_ignore_shared_memory_leftovers).
+ * Process-global. */
+DSG_API void dsg_debug_set_smem_poison(unsigned pattern, int enable);
 /* Byte offset and size of a named activation buffer ("X", "Y", "QKV", "ATT", "H", "T", "REP", "skip0".."skip2",
  * "film", "rc", "emb", "coef") inside a workspace laid out for (batch, n_cond). */
 DSG_API int dsg_debug_buffer(const dsg_model* m, int batch, int n_cond, const char* name, size_t* offset, size_t* bytes);

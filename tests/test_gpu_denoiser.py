@@ -537,3 +537,29 @@ def test_sampler_graphs_follow_changing_flags():
         outs[mode] = res
     for (a0, n0), (a1, n1) in zip(outs["graphs+skip"], outs["eager-dense"]):
         assert torch.equal(a0, a1) and torch.equal(n0, n1)
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 3), ("vg", 2), ("coco", 2)])
+def test_kernels_ignore_shared_memory_leftovers(name, batch):
+    """Every launch followed by a kernel that fills all shared memory with NaN / Inf patterns (what NCCL or any foreign
+    kernel may leave behind on an SM): the forward (shared and per-sample noise levels, with and without
+    self-conditioning) must not change by a bit.  Regression test for node_proj_kernel, which multiplied its zero padding
+    weights with shared-memory slots it never wrote (0 x NaN): NaN samples on the first pass of a 2-process run."""
+    cfg = CONFIGS[name]
+    model, _ = build(cfg)
+    adj, node, flags, sigmas, sc_adj, sc_node = [t.to(DEV) for t in synthetic_inputs(cfg, batch, seed=7)]
+    per_sample = (sigmas * torch.linspace(0.1, 3.0, batch, device=DEV)).log() / 4
+    cases = [(sigmas.log() / 4, sc_adj, sc_node), (per_sample, None, None), ((sigmas[:1].log() / 4).expand(batch), None, None)]
+    lib = native.lib()
+    with torch.no_grad():
+        want = [model(adj, node, flags, lab, sa, sn) for lab, sa, sn in cases]
+        for pattern in (0x7fc00000, 0xff800000, 0x7f7fffff):
+            lib.dsg_debug_set_smem_poison(pattern, 1)
+            try:
+                got = [model(adj, node, flags, lab, sa, sn) for lab, sa, sn in cases]
+                torch.cuda.synchronize()
+            finally:
+                lib.dsg_debug_set_smem_poison(0, 0)
+            for (wa, wn), (ga, gn) in zip(want, got):
+                assert torch.isfinite(ga).all() and torch.isfinite(gn).all(), hex(pattern)
+                assert torch.equal(wa, ga) and torch.equal(wn, gn), hex(pattern)

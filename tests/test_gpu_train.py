@@ -393,3 +393,27 @@ def test_fused_adam_step_matches_torch_adam_on_the_model():
     opt.step()
     for r, (k, v) in zip(ref, net.named_parameters()):
         assert _rel(v.detach(), r.detach()) < 1e-6, k
+
+
+def test_training_kernels_ignore_shared_memory_leftovers():
+    """Forward + backward of the training step with all shared memory overwritten by NaN patterns after every launch: the
+    outputs are unchanged and the gradients stay within the run-to-run spread of their atomic accumulation order."""
+    cfg = CONFIGS["tiny"]
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    adj, node, flags, sigmas, sc_adj, sc_node = [t.to(DEV) for t in synthetic_inputs(cfg, 4, seed=11)]
+    sigmas = torch.tensor([0.2, 1.5, 4.0, 0.7], device=DEV)
+    res = []
+    for poison in (0, 1):
+        net = _net(cfg, sd).train()
+        model = NodeAdjPrecond(precond="edm", model=net, self_condition=False, symmetric_noise=False).train()
+        native.lib().dsg_debug_set_smem_poison(0x7fc00000, poison)
+        try:
+            da, dn = model(adj, node, flags, sigmas, sc_adj, sc_node)
+            (da.square().mean() + dn.square().mean()).backward()
+            torch.cuda.synchronize()
+        finally:
+            native.lib().dsg_debug_set_smem_poison(0, 0)
+        res.append((da.detach().clone(), dn.detach().clone(), train_state(net, DEV).grad.clone()))
+    (a0, n0, g0), (a1, n1, g1) = res
+    assert torch.equal(a0, a1) and torch.equal(n0, n1)
+    assert torch.isfinite(g1).all() and _rel(g1, g0) < 1e-5, _rel(g1, g0)
