@@ -270,6 +270,8 @@ class DiffuseSG(nn.Module):
 
     def _run(self, mode, adj, node, flags, noise, sc_adj, sc_node):
         train = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if not train and self.training and not torch.is_grad_enabled() and self.__dict__.get("_train_state") is not None:
+            train = True    # no-grad pass inside a training loop (self-conditioning refresh): the training kernels, no tape
         if torch.is_grad_enabled() and (adj.requires_grad or node.requires_grad):
             raise NotImplementedError("DiffuseSG (B200): gradients w.r.t. the input graphs are not built (the reference's "
                                       "training step differentiates the parameters only, trainer_node_adj.py:96-173)")

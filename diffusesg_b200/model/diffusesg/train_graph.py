@@ -34,8 +34,16 @@ class _PrepJob(C.Structure):
                 ("dst_f32", C.c_int32)]
 
 
+_FN: Dict[str, object] = {}
+
+
 def _nc(name: str, *args) -> None:
-    native.check(getattr(native.lib(), name)(*args), name)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(native.lib(), name)
+    rc = fn(*args)
+    if rc != 0:
+        native.check(rc, name)
 
 
 def _up(n: int, m: int) -> int:
@@ -71,6 +79,7 @@ class TrainState:
             self.flat = torch.zeros(pos, dtype=F32, device=device)
             self.grad = torch.zeros(pos, dtype=F32, device=device)
         self.shapes = {k: tuple(named[k].shape) for k in order}
+        self._wviews: Dict[str, torch.Tensor] = {}
         for k in order:
             p = named[k]
             view = self.flat[self.offs[k]: self.offs[k] + p.numel()].view(p.shape)
@@ -85,7 +94,10 @@ class TrainState:
 
     # ---- views ---------------------------------------------------------------------------------------------------
     def w(self, key: str) -> torch.Tensor:
-        return self.flat[self.offs[key]: self.offs[key] + math.prod(self.shapes[key])].view(self.shapes[key])
+        v = self._wviews.get(key)
+        if v is None:
+            v = self._wviews[key] = self.flat[self.offs[key]: self.offs[key] + math.prod(self.shapes[key])].view(self.shapes[key])
+        return v
 
     def g(self, key: str) -> torch.Tensor:
         return self.gviews[key]
@@ -167,10 +179,9 @@ class TrainState:
 class _Ops:
     def __init__(self, dev):
         self.dev = dev
-
-    @property
-    def st(self):
-        return native.stream_ptr(self.dev)
+        # the stream current when the pass was created (one lookup, not one per launch); None on a CPU device, where only
+        # the host-side logic (flat layout, gradient ranges) can run
+        self.st = native.stream_ptr(dev) if dev.type == "cuda" else None
 
     def empty(self, shape, dtype=F32):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -634,4 +645,11 @@ def run_training_forward(module, mode, adj, node, flags, noise, sc_adj, sc_node)
     dev = adj.device
     st = train_state(module, dev)
     with native.device_guard(dev):
+        if not torch.is_grad_enabled():
+            # the self-conditioning refresh of a training step (model/precond/precond.py:90-98): same kernels, no tape kept -
+            # the fused inference schedule would need its packed weight arena rebuilt after every optimiser step
+            tp = TrainPass(st)
+            out = tp.forward(mode, adj, node, flags, noise, sc_adj, sc_node)
+            del tp
+            return out
         return DenoiserTrainFn.apply(st.anchor, TrainPass(st), mode, adj, node, flags, noise, sc_adj, sc_node)
