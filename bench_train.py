@@ -117,7 +117,7 @@ def run_native(args, cfg, rank, local_rank, world):
     from diffusesg_b200.loss.rainbow_loss import NodeAdjRainbowLoss
     from diffusesg_b200.runner.objectives.edm import NodeAdjEDMObjectiveGenerator
     from diffusesg_b200.runner.trainer.trainer_node_adj import train_one_step
-    from diffusesg_b200.utils.train_utils import FusedAdam, NativeDDP, NativeEMA
+    from diffusesg_b200.utils.train_utils import FusedAdam, GraphedTrainStep, NativeDDP, NativeEMA
     if not torch.cuda.is_available():
         raise SystemExit("bench_train.py: no CUDA device - the native path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
@@ -156,12 +156,20 @@ def run_native(args, cfg, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    graphed = None if args.no_graph else GraphedTrainStep(wrapped, opt, emas, gen, loss_fn, MAX_NORM)
+
     def step_device():
-        last["loss"] = train_one_step(wrapped, opt, emas, gen, loss_fn, adj_d, node_d, flags_d, MAX_NORM)
+        if graphed is not None:
+            last["loss"] = graphed(adj_d, node_d, flags_d)
+        else:
+            last["loss"] = train_one_step(wrapped, opt, emas, gen, loss_fn, adj_d, node_d, flags_d, MAX_NORM)
 
     def step_e2e():
-        a, x, f = adj_h.to(device, non_blocking=True), node_h.to(device, non_blocking=True), flags_h.to(device, non_blocking=True)
-        la, ln = train_one_step(wrapped, opt, emas, gen, loss_fn, a, x, f, MAX_NORM)
+        if graphed is not None:
+            la, ln = graphed(adj_h, node_h, flags_h)      # pinned host batch -> static device buffers inside the call
+        else:
+            a, x, f = adj_h.to(device, non_blocking=True), node_h.to(device, non_blocking=True), flags_h.to(device, non_blocking=True)
+            la, ln = train_one_step(wrapped, opt, emas, gen, loss_fn, a, x, f, MAX_NORM)
         last["host_loss"] = float((la.mean() + ln.mean()).item())
 
     for _ in range(max(3, args.warmup)):
@@ -185,6 +193,9 @@ def run_native(args, cfg, rank, local_rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload(args, cfg, world), "gpu_launches": int(launches),
+            "schedule": {"cuda_graph_per_iteration": graphed is not None,
+                         "note": "gpu_launches counts the library's launch calls; with graphs the ~600 launches of objective + "
+                                 "forward + loss + backward replay from one captured graph and only the eager ones are counted"},
             "raw_forward_passes_per_step": passes / args.steps,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e.summary()},
@@ -209,6 +220,7 @@ def main():
     ap.add_argument("--config", default="vg", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per iteration")
     ap.add_argument("--data-seed", type=int, default=1234, help="seed of the synthetic clean batch (+ rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -1368,9 +1368,9 @@ int dsg_proj_ln(const void* att, const void* w, const float* bias, const float* 
   return launch_proj_ln(&ta, &tw, bias, gamma, beta, x, static_cast<bf16*>(y), M, C, static_cast<cudaStream_t>(stream));
 }
 
-int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,
-                         int shift, int heads, dsg_stream_t stream) {
-  DSG_REQUIRE(qkv && bias && out, "window_attention: null tensor");
+int dsg_window_attention_check(const float* bias, const float* mask, int batch, int res, int window, int shift, int heads,
+                               dsg_stream_t stream, int* flags_out) {
+  DSG_REQUIRE(bias && flags_out, "window_attention_check: null argument");
   int canonical = 0;
   const bool w16 = window_attention_w16_supported(batch, res, window, shift, heads);
   if (mask != nullptr && shift > 0 && (w16 || window_attention_quad_supported(batch, res, window, shift, heads))) {
@@ -1383,8 +1383,22 @@ int dsg_window_attention(const void* qkv, const float* bias, const float* mask, 
     DSG_TRY(check_bias_toeplitz(bias, heads, window, static_cast<cudaStream_t>(stream), &ok));
     if (ok) canonical |= ATTN_BIAS_TOEPLITZ;
   }
+  *flags_out = canonical;
+  return DSG_OK;
+}
+
+int dsg_window_attention_flags(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,
+                               int shift, int heads, int flags, dsg_stream_t stream) {
+  DSG_REQUIRE(qkv && bias && out, "window_attention: null tensor");
   return launch_window_attention(static_cast<const bf16*>(qkv), bias, mask, static_cast<bf16*>(out), batch, res, window,
-                                 shift, heads, static_cast<cudaStream_t>(stream), canonical);
+                                 shift, heads, static_cast<cudaStream_t>(stream), flags);
+}
+
+int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res, int window,
+                         int shift, int heads, dsg_stream_t stream) {
+  int flags = 0;
+  DSG_TRY(dsg_window_attention_check(bias, mask, batch, res, window, shift, heads, stream, &flags));
+  return dsg_window_attention_flags(qkv, bias, mask, out, batch, res, window, shift, heads, flags, stream);
 }
 
 }  // extern "C"

@@ -80,6 +80,7 @@ class TrainState:
             self.grad = torch.zeros(pos, dtype=F32, device=device)
         self.shapes = {k: tuple(named[k].shape) for k in order}
         self._wviews: Dict[str, torch.Tensor] = {}
+        self.attn_flags: Dict[tuple, int] = {}
         for k in order:
             p = named[k]
             view = self.flat[self.offs[k]: self.offs[k] + p.numel()].view(p.shape)
@@ -359,7 +360,15 @@ class TrainPass:
         bias = o.empty((heads, T, T))
         _nc("dsg_tr_bias_gather", s.w(p + ".attn.relative_position_bias_table").data_ptr(), index.data_ptr(), bias.data_ptr(),
             heads, T, 0, None, o.st)
-        att = native.window_attention(qkv, bias, mask, batch, res, w, shift, heads)
+        # the mask / bias buffer checks synchronise the stream: once per block (first pass), their result is kept
+        fl = s.attn_flags.get((p, batch))
+        if fl is None:
+            got = C.c_int(0)
+            _nc("dsg_window_attention_check", bias.data_ptr(), native.ptr(mask), batch, res, w, shift, heads, o.st, C.byref(got))
+            fl = s.attn_flags[(p, batch)] = got.value
+        att = o.empty((qkv.shape[0], dim), BF16)
+        _nc("dsg_window_attention_flags", qkv.data_ptr(), bias.data_ptr(), native.ptr(mask), att.data_ptr(), batch, res, w, shift,
+            heads, fl, o.st)
         xm = o.gemm(att, s.wb[p + ".attn.proj"], s.w(p + ".attn.proj.bias"), native.EPI_RES_F32, res=xf, out=o.empty(xf.shape))
         y2, _ = o.ln_fwd(xm, s.w(p + ".norm2.weight"), s.w(p + ".norm2.bias"))
         hp = o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_BF16)

@@ -35,7 +35,10 @@ class NodeAdjPrecond(nn.Module):
                 *args, **model_kwargs):
         if args or model_kwargs:
             raise NotImplementedError("NodeAdjPrecond (B200): extra model arguments are not supported")
-        if self.self_condition and np.random.rand() < 0.5:
+        coin = self.__dict__.get("_forced_coin")   # set by GraphedTrainStep, which draws np.random.rand() itself (same stream)
+        if coin is None:
+            coin = self.self_condition and np.random.rand() < 0.5
+        if self.self_condition and coin:
             with torch.no_grad():
                 self_cond_adjs, self_cond_nodes = self.model.denoise(adjs, nodes, node_flags, sigmas,
                                                                      self_cond_adjs, self_cond_nodes)

@@ -96,6 +96,8 @@ _SIGNATURES = {
     "dsg_edm_loss_sums_backward": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_gemm_bf16": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "dsg_window_attention": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    "dsg_window_attention_check": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p, C.POINTER(C.c_int)]),
+    "dsg_window_attention_flags": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]),
     "dsg_gemm_bf16_ex": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p]),
     # training step
     "dsg_tr_ln_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p]),

@@ -161,3 +161,89 @@ class NativeDDP(nn.Module):
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
+
+
+class GraphedTrainStep:
+    """The training iteration of runner/trainer/trainer_node_adj.py:95-178 with everything between the clean batch and the
+    gradients - objective generator, preconditioned denoiser (both self-conditioning outcomes), loss, backward: ~600 kernel
+    launches - replayed as ONE CUDA graph; gradient all-reduce (DDP), optimiser and moving averages follow eagerly (three
+    launches).  The self-conditioning coin is drawn here from the global numpy stream, exactly where NodeAdjPrecond.forward
+    would draw it, and selects one of two captured graphs; the torch CUDA generator advances per replay as in eager mode.
+    Shapes are fixed at the first call."""
+
+    def __init__(self, model, optimizer, ema_helper, train_obj_gen, loss_func, max_grad_norm: float = 10.0, warmup: int = 2):
+        import numpy as np
+        self.np = np
+        self.model, self.opt, self.emas = model, optimizer, ema_helper
+        self.gen, self.loss_func, self.max_grad_norm = train_obj_gen, loss_func, max_grad_norm
+        self.precond = model.module if hasattr(model, "module") else model
+        self.den = find_denoiser(model)
+        self.warmup = warmup
+        self.graphs = {}
+        self.static = None
+        self.pool = None
+
+    def _body(self):
+        adj, node, flags = self.static
+        na, nx, cond, ta, tx, (c_skip, c_out, c_in, c_noise, sigmas, weights) = self.gen.get_input_output(adj, node, flags)
+        for p in self.den.parameters():
+            p.grad = None                      # zero_grad(set_to_none=True): the backward zeroes the flat buffer itself
+        oa, ox = self.precond(adjs=na, nodes=nx, node_flags=flags, sigmas=sigmas)
+        la, ln = self.loss_func(net_pred_a=oa, net_pred_x=ox, net_target_a=ta, net_target_x=tx, net_cond=cond,
+                                adjs_perturbed=na, adjs_gt=adj, x_perturbed=nx, x_gt=node, node_flags=flags,
+                                loss_weight=weights, reduction="none")
+        (la.mean() + ln.mean()).backward()
+        return la.detach(), ln.detach()
+
+    def _capture(self, coin: bool):
+        ts = train_state(self.den, self.static[0].device)
+        group, ts.ddp_group = ts.ddp_group, None      # the all-reduce runs after the replay, outside the graph
+        self.precond.__dict__["_forced_coin"] = coin
+        dev = self.static[0].device
+        rng = torch.cuda.get_rng_state(dev)           # warm-up and capture must not consume the step's noise draws
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self._body()
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                out = self._body()
+            if self.pool is None:
+                self.pool = g.pool()
+        finally:
+            self.precond.__dict__["_forced_coin"] = None
+            ts.ddp_group = group
+            torch.cuda.set_rng_state(rng, dev)
+        self.graphs[coin] = (g, out)
+
+    def __call__(self, adjs_gt, nodes_gt, node_flags):
+        dev = self.gen.dev
+        if self.static is None:
+            self.static = (torch.empty_like(adjs_gt, device=dev), torch.empty_like(nodes_gt, device=dev),
+                           torch.empty_like(node_flags, device=dev))
+        for dst, src in zip(self.static, (adjs_gt, nodes_gt, node_flags)):
+            dst.copy_(src, non_blocking=True)
+        coin = bool(self.precond.self_condition and self.np.random.rand() < 0.5)
+        passes0 = self.precond.raw_passes
+        if coin not in self.graphs:
+            self._capture(coin)                # also leaves valid gradients of this batch? no: replay below produces them
+        g, (la, ln) = self.graphs[coin]
+        g.replay()
+        self.precond.raw_passes = passes0 + (2 if coin else 1)
+        ts = train_state(self.den, self.static[0].device)
+        if ts.ddp_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(ts.grad, op=dist.ReduceOp.AVG, group=ts.ddp_group)
+        if isinstance(self.opt, FusedAdam):
+            self.opt.max_grad_norm = self.max_grad_norm
+        else:
+            nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_grad_norm, norm_type=2)
+        self.opt.step()
+        if self.emas is not None:
+            for ema in self.emas:
+                ema.update()
+        return la, ln

@@ -286,6 +286,12 @@ DSG_API int dsg_proj_ln(const void* att, const void* w, const float* bias, const
  * checks as dsg_model_finalize on every call (synchronous) and then the kernel the denoiser would pick. */
 DSG_API int dsg_window_attention(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
                          int window, int shift, int heads, dsg_stream_t stream);
+/* The two halves of dsg_window_attention: the (stream-synchronising) checks of the mask / bias buffers, once, and the
+ * launch with their result - what a CUDA-graph capture of a training step needs (no synchronisation inside a capture). */
+DSG_API int dsg_window_attention_check(const float* bias, const float* mask, int batch, int res, int window, int shift,
+                                       int heads, dsg_stream_t stream, int* flags_out);
+DSG_API int dsg_window_attention_flags(const void* qkv, const float* bias, const float* mask, void* out, int batch, int res,
+                                       int window, int shift, int heads, int flags, dsg_stream_t stream);
 
 /* out = epilogue(A . W^T) like dsg_gemm_bf16, with (a) split-K: the contraction is cut into `ksplit` slices per output
  * tile, combined by the reduce-add epilogue (epi 2, no bias; out must hold the value to accumulate onto) - the weight
