@@ -181,6 +181,9 @@ def run_native(args, cfg, rank, local_rank, world):
     launches = native.launch_count() - launches0
     with B.ClockSampler(local_rank) as clocks_e2e:
         ms_e2e = timed(step_e2e, args.steps)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     graphs = args.batch * world * args.steps

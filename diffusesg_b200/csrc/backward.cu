@@ -919,7 +919,8 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
   float* sS = reinterpret_cast<float*>(sDO + TP * kQP);
   float* sD = sS + TP * PF;
   float* sAcc = sD + TP * PF;
-  int* sTok = reinterpret_cast<int*>(sAcc + T * T);
+  float* sBias = sAcc + T * T;                    // this head's bias [T][T], loaded once per CTA
+  int* sTok = reinterpret_cast<int*>(sBias + T * T);
   bf16_t* sPb = reinterpret_cast<bf16_t*>(sS);    // P, bf16, row pitch 2 PF
   bf16_t* sDb = reinterpret_cast<bf16_t*>(sD);    // dS
   const int LDB = 2 * PF;
@@ -930,8 +931,8 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
   const int nw = res / w, nW = nw * nw;
   const int total = batch * nW;
   const int item0 = blockIdx.x * items_per_cta, item1 = min(total, item0 + items_per_cta);
-  for (int i = threadIdx.x; i < T * T; i += 256) sAcc[i] = 0.f;
   const float* bh = bias + static_cast<size_t>(h) * T * T;
+  for (int i = threadIdx.x; i < T * T; i += 256) { sAcc[i] = 0.f; sBias[i] = bh[i]; }
   for (int item = item0; item < item1; ++item) {
     const int b = item / nW, win = item - b * nW;
     const int wy = win / nw, wx = win - wy * nw;
@@ -982,33 +983,52 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
         for (int j = lane; j < TP; j += 32) { prow[j] = __float2bfloat16_rn(0.f); dsrow[j] = __float2bfloat16_rn(0.f); }
         continue;
       }
+      // the row lives in registers (<= 4 elements per lane, TP <= 128): scores + bias (+ mask), one max and one sum
+      // reduction, then P and dS go back as bf16 at the start of their own rows - every fp32 read of the row is done by then
+      float sv[4], dv[4];
       float mx = -INFINITY;
-      for (int j = lane; j < T; j += 32) {
-        const float v = srow[j] + bh[i * T + j] + (mk != nullptr ? mk[i * T + j] : 0.f);
-        srow[j] = v;
-        mx = fmaxf(mx, v);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        sv[t] = -INFINITY;
+        dv[t] = 0.f;
+        if (j < T) {
+          sv[t] = srow[j] + sBias[i * T + j] + (mk != nullptr ? mk[i * T + j] : 0.f);
+          dv[t] = drow[j];
+          mx = fmaxf(mx, sv[t]);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
-      for (int j = lane; j < T; j += 32) { const float e = __expf(srow[j] - mx); srow[j] = e; sum += e; }
-      const float inv = 1.0f / warp_sum(sum);
-      float dot = 0.f;
-      for (int j = lane; j < T; j += 32) dot += srow[j] * inv * drow[j];
-      dot = warp_sum(dot);
-      // last pass: P and dS as bf16 at the start of their own rows.  The bf16 element j lies inside the fp32 element j / 2,
-      // which an EARLIER trip of this loop consumed - except in the first trip, where the reads finish before the writes.
-      for (int j0 = 0; j0 < TP; j0 += 32) {
-        const int j = j0 + lane;
-        float pv = 0.f, ds = 0.f;
-        if (j < T) {
-          pv = srow[j] * inv;
-          ds = pv * (drow[j] - dot);
-          sAcc[i * T + j] += ds;
+      float sum = 0.f, dun = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float e = (lane + 32 * t < T) ? __expf(sv[t] - mx) : 0.f;
+        sv[t] = e;
+        sum += e;
+        dun = fmaf(e, dv[t], dun);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        dun += __shfl_xor_sync(0xffffffffu, dun, o);
+      }
+      const float inv = 1.0f / sum;
+      const float dot = dun * inv;
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        if (j < TP) {
+          float pv = 0.f, ds = 0.f;
+          if (j < T) {
+            pv = sv[t] * inv;
+            ds = pv * (dv[t] - dot);
+            sAcc[i * T + j] += ds;
+          }
+          prow[j] = __float2bfloat16_rn(pv);
+          dsrow[j] = __float2bfloat16_rn(ds);
         }
-        __syncwarp();
-        if (j < TP) { prow[j] = __float2bfloat16_rn(pv); dsrow[j] = __float2bfloat16_rn(ds); }
-        __syncwarp();
       }
     }
     __syncthreads();
@@ -1381,7 +1401,7 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   const int T = window * window;
   static const bool fp32_only = getenv("DSG_ATTN_BWD_FP32") != nullptr && getenv("DSG_ATTN_BWD_FP32")[0] == '1';
   const int TP = (T + 15) & ~15, PF = (TP + 16 > 80) ? TP + 16 : 80;
-  const size_t smem_tc = static_cast<size_t>(4) * TP * kQP * 2 + static_cast<size_t>(2) * TP * PF * 4 + static_cast<size_t>(T) * T * 4 + static_cast<size_t>(TP) * 4;
+  const size_t smem_tc = static_cast<size_t>(4) * TP * kQP * 2 + static_cast<size_t>(2) * TP * PF * 4 + static_cast<size_t>(2) * T * T * 4 + static_cast<size_t>(TP) * 4;
   const size_t smem_f32 = (static_cast<size_t>(4) * T * kHdP + 2 * static_cast<size_t>(T) * (T + 1) + static_cast<size_t>(T) * T) * 4 + static_cast<size_t>(T) * 4;
   const bool tc = !fp32_only && smem_tc <= 227 * 1024;
   const size_t smem = tc ? smem_tc : smem_f32;

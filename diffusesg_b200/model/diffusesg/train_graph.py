@@ -374,12 +374,11 @@ class TrainPass:
         hp = o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_BF16)
         h = o.gelu(hp)
         xo = o.gemm(h, s.wb[p + ".mlp.fc2"], s.w(p + ".mlp.fc2.bias"), native.EPI_RES_F32, res=xm, out=o.empty(xm.shape))
+        h_t, _ = o.transpose(h)      # the fc2 weight gradient's token-major operand, written while h is hot; h itself is dropped
         del h
 
         def bwd(dxo):
-            h = o.gelu(hp)
-            dh = self._lin_bwd(p + ".mlp.fc2", dxo, h, dx_epi=native.EPI_BF16)
-            del h
+            dh = self._lin_bwd(p + ".mlp.fc2", dxo, None, dx_epi=native.EPI_BF16, x_t=h_t)
             dhp = o.gelu(hp, dh)
             del dh
             dy2 = self._lin_bwd(p + ".mlp.fc1", dhp, y2)
