@@ -42,30 +42,45 @@ constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default
 // LayerNorm forward (training form): y = (x - mean) * rstd * gamma + beta, one warp per row, two exact passes for
 // the statistics (the row stays in L1).  Writes bf16 (GEMM operand) and / or fp32.
 // ---------------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16_t* __restrict__ y16, float* __restrict__ y32, long long M, int C) {
+  // a lane owns the float4 groups lane + 32 k (k < NV) of every row: the row is read once and stays in registers
   const int lane = threadIdx.x & 31;
   const long long warps = static_cast<long long>(gridDim.x) * 8;
   const int nv = C >> 2;
+  const float invC = 1.0f / C;
   for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < M; row += warps) {
     const float* xr = x + row * C;
+    float4 a[NV];
     float s = 0.f;
-    for (int v = lane; v < nv; v += 32) { const float4 a = ld4(xr + 4 * v); s += (a.x + a.y) + (a.z + a.w); }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
-    for (int v = lane; v < nv; v += 32) {
-      const float4 a = ld4(xr + 4 * v);
-      const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      a[k] = v < nv ? ld4(xr + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (a[k].x + a[k].y) + (a[k].z + a[k].w);
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + kLnEps);
-    for (int v = lane; v < nv; v += 32) {
-      const float4 a = ld4(xr + 4 * v), g = ld4(gamma + 4 * v), b = ld4(beta + 4 * v);
-      const float4 o = make_float4((a.x - mean) * rstd * g.x + b.x, (a.y - mean) * rstd * g.y + b.y,
-                                   (a.z - mean) * rstd * g.z + b.z, (a.w - mean) * rstd * g.w + b.w);
-      if (y16 != nullptr) st4_bf16(y16 + row * C + 4 * v, o);
-      if (y32 != nullptr) st4(y32 + row * C + 4 * v, o);
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (lane + 32 * k < nv) {
+        a[k].x -= mean; a[k].y -= mean; a[k].z -= mean; a[k].w -= mean;
+        q += (a[k].x * a[k].x + a[k].y * a[k].y) + (a[k].z * a[k].z + a[k].w * a[k].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + kLnEps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv) {
+        const float4 g = ld4(gamma + 4 * v), b = ld4(beta + 4 * v);
+        const float4 o = make_float4(a[k].x * rstd * g.x + b.x, a[k].y * rstd * g.y + b.y, a[k].z * rstd * g.z + b.z,
+                                     a[k].w * rstd * g.w + b.w);
+        if (y16 != nullptr) st4_bf16(y16 + row * C + 4 * v, o);
+        if (y32 != nullptr) st4(y32 + row * C + 4 * v, o);
+      }
     }
   }
 }
@@ -1108,26 +1123,39 @@ struct AdamArgs {
   float* ema[8];
 };
 __global__ void __launch_bounds__(256)
-adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n4,
                 const float* __restrict__ gsumsq, AdamArgs a) {
+  // n4 = elements / 4 (the flat buffer is a multiple of 4 floats); every stream is read and written once, 16 bytes at a time
   float clip = 1.f;
   if (gsumsq != nullptr && a.max_norm > 0.f) clip = fminf(1.f, a.max_norm / (sqrtf(*gsumsq) + 1e-6f));
-  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
-    float w = p[i];
+  const float step_size = a.lr / a.bc1, inv_bc2 = 1.0f / a.bc2_sqrt;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    float4 w4 = ld4(p + 4 * i);
+    float w[4] = {w4.x, w4.y, w4.z, w4.w};
     if (m != nullptr) {   // m == NULL: moving averages only
-      float gi = g[i] * clip + a.weight_decay * w;
-      const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
-      const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
-      m[i] = mi;
-      v[i] = vi;
-      w -= (a.lr / a.bc1) * mi / (sqrtf(vi) / a.bc2_sqrt + a.eps);
-      p[i] = w;
+      const float4 g4 = ld4(g + 4 * i), m4 = ld4(m + 4 * i), v4 = ld4(v + 4 * i);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gi = gg[k] * clip + a.weight_decay * w[k];
+        mm[k] = a.beta1 * mm[k] + (1.f - a.beta1) * gi;
+        vv[k] = a.beta2 * vv[k] + (1.f - a.beta2) * gi * gi;
+        w[k] -= step_size * mm[k] / (sqrtf(vv[k]) * inv_bc2 + a.eps);
+      }
+      st4(m + 4 * i, make_float4(mm[0], mm[1], mm[2], mm[3]));
+      st4(v + 4 * i, make_float4(vv[0], vv[1], vv[2], vv[3]));
+      st4(p + 4 * i, make_float4(w[0], w[1], w[2], w[3]));
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (k < a.n_ema) {   // lerp(ema, w, 1 - decay); decay 0 is ema_pytorch's plain copy
-        float* e = a.ema[k];
-        e[i] = a.ema_decay[k] == 0.f ? w : e[i] + (1.f - a.ema_decay[k]) * (w - e[i]);
+        float* e = a.ema[k] + 4 * i;
+        const float d = a.ema_decay[k];
+        const float4 e4 = ld4(e);
+        st4(e, d == 0.f ? make_float4(w[0], w[1], w[2], w[3])
+                        : make_float4(e4.x + (1.f - d) * (w[0] - e4.x), e4.y + (1.f - d) * (w[1] - e4.y),
+                                      e4.z + (1.f - d) * (w[2] - e4.z), e4.w + (1.f - d) * (w[3] - e4.w)));
       }
   }
 }
@@ -1185,8 +1213,17 @@ extern "C" {
 
 int dsg_tr_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, long long M, int C,
                   dsg_stream_t stream) {
-  DSG_REQUIRE(x && gamma && beta && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0, "tr_ln_fwd: bad argument");
-  ln_fwd_kernel<<<grid_for(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, static_cast<bf16_t*>(y_bf16), y_f32, M, C);
+  DSG_REQUIRE(x && gamma && beta && (y_bf16 || y_f32) && M > 0 && C > 0 && C % 4 == 0 && C <= 2048, "tr_ln_fwd: bad argument (C <= 2048)");
+  const unsigned grid = grid_for(M, 8 * 4, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bf16_t* y16 = static_cast<bf16_t*>(y_bf16);
+  const int nvw = (C / 4 + 31) / 32;   // float4 groups per lane
+  if (nvw <= 1) ln_fwd_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
+  else if (nvw <= 2) ln_fwd_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
+  else if (nvw <= 3) ln_fwd_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
+  else if (nvw <= 6) ln_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
+  else if (nvw <= 12) ln_fwd_kernel<12><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
+  else ln_fwd_kernel<16><<<grid, 256, 0, st>>>(x, gamma, beta, y16, y_f32, M, C);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -1450,7 +1487,8 @@ int dsg_tr_adam_ema(float* p, const float* g, float* m, float* v, long long n, c
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   a.n_ema = n_ema;
   for (int k = 0; k < n_ema; ++k) { a.ema[k] = ema[k]; a.ema_decay[k] = ema_decay[k]; }
-  adam_ema_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, gsumsq, a);
+  DSG_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0, "tr_adam_ema: the flat buffers are multiples of 4 floats, 16-byte aligned");
+  adam_ema_kernel<<<grid_for(n / 4, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n / 4, gsumsq, a);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

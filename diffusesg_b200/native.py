@@ -15,7 +15,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libdsg_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_F32 = 0, 1, 2, 3
 

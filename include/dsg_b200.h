@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSG_ABI_VERSION 2
+#define DSG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DSG_API __attribute__((visibility("default")))

@@ -235,7 +235,7 @@ def test_window_attention_backward(batch, res, w, shift, heads):
 # optimiser
 # ---------------------------------------------------------------------------------------------------------
 def test_fused_adam_ema_matches_torch():
-    n = 100003
+    n = 100004                   # the flat buffers are multiples of 4 floats
     g = torch.Generator(device=DEV).manual_seed(3)
     p = torch.randn(n, device=DEV, generator=g)
     ref = p.clone().requires_grad_(True)
@@ -454,3 +454,72 @@ def test_graphed_training_step_matches_eager():
     # Adam turns the last-bit differences of the atomically accumulated gradients into lr-sized differences wherever a
     # gradient is ~ eps (two eager runs differ the same way): 8 steps x lr 1e-3 against weights of std 0.02
     assert _rel(w1, w0) < 5e-3 and _rel(e1, e0) < 5e-3, (_rel(w1, w0), _rel(e1, e0))
+
+
+def test_training_trajectory_matches_the_reference_loop():
+    """Six optimiser steps of the reference's training loop (objective -> preconditioned model with its no-grad
+    self-conditioning pass -> rainbow loss -> backward -> clip 10 -> Adam) on the native path and on the fp32 CPU oracle with
+    torch autograd + torch.optim.Adam, fed the SAME noise draws, sigmas and coins: the loss trajectories coincide and the
+    accumulated weight updates point the same way."""
+    cfg = CONFIGS["tiny"]
+    sd = synthetic_state_dict(cfg, seed=99, stress=True)
+    B, steps, lr = 4, 6, 1e-3
+    adj, node, flags, *_ = synthetic_inputs(cfg, B, seed=3)
+    adj, node = O.mask_pairs(adj.sign(), flags), O.mask_rows(node.clamp(-1, 1), flags)
+    net = _net(cfg, sd).train()
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).train()
+    opt = FusedAdam(model, lr=lr, max_grad_norm=10.0)
+    gen = NodeAdjEDMObjectiveGenerator("edm", "edm", dev=DEV, symmetric_noise=False)
+    loss_fn = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=1.0, objective="edm")
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "attn_mask" not in k else v) for k, v in sd.items()}
+    ref_params = [v for v in leaves.values() if v.is_floating_point() and v.requires_grad]
+    ref_opt = torch.optim.Adam(ref_params, lr=lr)
+
+    def onet(a, x, f, c_noise, sa, sn):
+        return O.denoiser_forward(leaves, img=cfg["img"], embed=cfg["embed"], depths=cfg["depths"], heads=cfg["heads"],
+                                  window=cfg["window"], self_condition=True, adj=a, node=x, flags=f, noise_labels=c_noise,
+                                  sc_adj=sa, sc_node=sn)
+    rng = np.random.RandomState(7)
+    coins = [bool(rng.rand() < 0.5) for _ in range(steps)]
+    assert any(coins) and not all(coins)
+    adj_d, node_d, flags_d = adj.to(DEV), node.to(DEV), flags.to(DEV)
+    got, want = [], []
+    for k in range(steps):
+        torch.manual_seed(100 + k)
+        na, nx, cond, ta, tx, (c_skip, c_out, c_in, c_noise, sigmas, weights) = gen.get_input_output(adj_d, node_d, flags_d)
+        # native
+        model.__dict__["_forced_coin"] = coins[k]
+        opt.zero_grad(set_to_none=True)
+        oa, ox = model(adjs=na, nodes=nx, node_flags=flags_d, sigmas=sigmas)
+        la, ln = loss_fn(net_pred_a=oa, net_pred_x=ox, net_target_a=ta, net_target_x=tx, net_cond=cond, adjs_perturbed=na,
+                         adjs_gt=adj_d, x_perturbed=nx, x_gt=node_d, node_flags=flags_d, loss_weight=weights, reduction="none")
+        (la.mean() + ln.mean()).backward()
+        opt.step()
+        got.append(float(la.mean() + ln.mean()))
+        # reference loop on the oracle (model/precond/precond.py:90-105, trainer_node_adj.py:109-175)
+        na_c, nx_c, sig_c, w_c = na.cpu(), nx.cpu(), sigmas.cpu(), weights.cpu()
+        sa = sn = None
+        if coins[k]:
+            with torch.no_grad():
+                sa, sn = O.precond_forward(onet, na_c, nx_c, flags, sig_c, None, None)
+        da, dn = O.precond_forward(onet, na_c, nx_c, flags, sig_c, sa, sn)
+        ra, rn = T.regression_loss(da, dn, ta.cpu(), tx.cpu(), flags, w_c, 1.0, 1.0, "none")
+        ref_opt.zero_grad(set_to_none=True)
+        (ra.mean() + rn.mean()).backward()
+        torch.nn.utils.clip_grad_norm_(ref_params, max_norm=10.0)
+        ref_opt.step()
+        want.append(float(ra.mean() + rn.mean()))
+    model.__dict__["_forced_coin"] = None
+    print("loss trajectory native", [f"{v:.5f}" for v in got], "reference", [f"{v:.5f}" for v in want])
+    # the loss inherits the bf16 rounding of the forward (F to ~1e-2 per pass, weighted by (sigma^2 + 1/4) / (sigma/2)^2)
+    assert np.allclose(got, want, rtol=1e-2), (got, want)
+    num = den_a = den_b = 0.0
+    for key, p in net.named_parameters():
+        da_ = (p.detach().cpu() - sd[key]).double().flatten()
+        db_ = (leaves[key].detach() - sd[key]).double().flatten()
+        num += float(da_ @ db_)
+        den_a += float(da_ @ da_)
+        den_b += float(db_ @ db_)
+    cos = num / (den_a * den_b) ** 0.5
+    print(f"cosine between the accumulated weight updates: {cos:.4f}")
+    assert cos > 0.9, cos
