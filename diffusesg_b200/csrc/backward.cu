@@ -34,6 +34,16 @@ DSG_DEVICE float4 ld4_bf16(const bf16_t* p) {
   const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
   return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
 }
+DSG_DEVICE void unpack8(const uint4& w, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = __low2float(h[j]); f[2 * j + 1] = __high2float(h[j]); }
+}
+DSG_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+  return w;
+}
 DSG_DEVICE float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default
@@ -242,16 +252,6 @@ film_silu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ v
 DSG_DEVICE float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 DSG_DEVICE float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
-DSG_DEVICE void unpack8(const uint4& w, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { f[2 * j] = __low2float(h[j]); f[2 * j + 1] = __high2float(h[j]); }
-}
-DSG_DEVICE uint4 pack8(const float (&f)[8]) {
-  uint4 w;
-  w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-  return w;
 }
 // n8 = element count / 8; pointers 16-byte aligned
 __global__ void __launch_bounds__(256)
@@ -513,6 +513,59 @@ transpose_colsum_kernel(const T* __restrict__ src, bf16_t* __restrict__ dst, bf1
 #pragma unroll
       for (int k = 0; k < 32; ++k) s += part[k][t];
       atomicAdd(&colsum[c0 + t], s);
+    }
+  }
+}
+
+// Bias gradient and bf16 operand of a weight-gradient GEMM in one pass over dY [M, C] (C % 8 == 0): colsum[c] += sum over
+// rows (columns < scale_cols scaled), cast [M, C] = bf16(dY) when dY is fp32.  A thread owns one 8-column group for a
+// strided run of rows (a warp reads 32 consecutive groups of one row), four rows in flight.
+constexpr int kCsRows = 512;
+template <typename T>
+__global__ void __launch_bounds__(256)
+cast_colsum_kernel(const T* __restrict__ src, bf16_t* __restrict__ cast, float* __restrict__ colsum, long long M, int C,
+                   int scale_cols, float scale) {
+  __shared__ float part[8][256];
+  const int g = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + g) * 8;
+  const bool col_ok = c < C;
+  const long long r_begin = static_cast<long long>(blockIdx.y) * kCsRows, r_end = min(M, r_begin + kCsRows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long r0 = r_begin + rl; r0 < r_end; r0 += 32) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + 8 * u;
+      const bool ok = col_ok && r < r_end;
+      const T* p = src + (ok ? r * C + c : 0);
+      if (sizeof(T) == 2) {
+        uint4 w = *reinterpret_cast<const uint4*>(p);
+        if (!ok) w = make_uint4(0u, 0u, 0u, 0u);
+        unpack8(w, v[u]);
+      } else {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        if (!ok) { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + 8 * u;
+      if (cast != nullptr && col_ok && r < r_end) *reinterpret_cast<uint4*>(cast + r * C + c) = pack8(v[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+  }
+  if (colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[rl][8 * g + j] = acc[j];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+      atomicAdd(&colsum[cc], cc < scale_cols ? t * scale : t);
     }
   }
 }
@@ -1334,6 +1387,25 @@ int dsg_tr_transpose(const void* src, int src_is_bf16, void* dst_t, void* cast, 
   }
   DSG_LAUNCH_CHECK();
   return DSG_OK;
+}
+
+int dsg_tr_cast_colsum(const void* src, int src_is_bf16, void* cast, float* colsum, long long M, int C, int scale_cols,
+                       float scale, dsg_stream_t stream) {
+  DSG_REQUIRE(src && (cast || colsum) && M > 0 && C > 0 && C % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(cast) & 15) == 0, "tr_cast_colsum: bad argument (C %% 8 == 0, 16-byte aligned)");
+  const dim3 grid((C + 255) / 256, static_cast<unsigned>((M + kCsRows - 1) / kCsRows));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_is_bf16)
+    cast_colsum_kernel<bf16_t><<<grid, 256, 0, st>>>(static_cast<const bf16_t*>(src), static_cast<bf16_t*>(cast), colsum, M, C, scale_cols, scale);
+  else
+    cast_colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), static_cast<bf16_t*>(cast), colsum, M, C, scale_cols, scale);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_wgrad(const void* dy, const void* x, float* dw, long long tokens, int n_out, int x_cols, int out_cols, int ksplit,
+                 int scale_rows, float row_scale, dsg_stream_t stream) {
+  return launch_wgrad(dy, x, dw, tokens, n_out, x_cols, out_cols, ksplit, scale_rows, row_scale, static_cast<cudaStream_t>(stream));
 }
 
 int dsg_tr_shuffle2x2(const float* src, float* dst, int B, int H, int W, int C, int to_coarse, dsg_stream_t stream) {

@@ -255,6 +255,20 @@ DSG_DEVICE uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return lo | (hi << 32);
 }
 
+// MN-major operand tile (the non-contracted index is the contiguous one: a weight-gradient GEMM reads dY [tokens, N_out]
+// and X [tokens, K_in] as they lie in memory).  Canonical layout, 128-byte swizzle, in 16-byte units
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)): an atom is 64 MN elements x 8 K rows = what TMA writes for a box of 64 columns
+// (128 B) x 8 rows; K groups of 8 rows are SBO = 1024 B apart, the next 64 MN elements (the next TMA box) LBO bytes.
+DSG_DEVICE uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  const uint64_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16);
+  const uint64_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return lo | (hi << 32);
+}
+// Instruction descriptor: bf16 x bf16 -> fp32, BOTH operands MN-major (bits 15, 16), M=128, N=n.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=n.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);

@@ -46,12 +46,15 @@ static_assert(Cfg<96>::SMEM_BYTES <= 227 * 1024 && Cfg<192>::SMEM_BYTES <= 227 *
 static_assert(Cfg<96, true>::SMEM_BYTES <= 227 * 1024 && Cfg<192, true>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(Cfg<256>::SMEM_BYTES <= 227 * 1024 && Cfg<256, true>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-template <int BN, int EPI, bool PAIR>
+// MNM: both operands MN-major (weight gradients): tmA / tmW describe dY [tokens, N_out] and X [tokens, K_in], a stage holds
+// 2 + BN / 64 TMA boxes of 64 columns x 64 tokens (8 KB each), p.M = N_out, p.N = K_in rounded up to BN, p.K = tokens.
+template <int BN, int EPI, bool PAIR, bool MNM = false>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   using C = Cfg<BN, PAIR>;
   static_assert(!(PAIR && EPI == EPI_ADJ_HEAD), "the adj-head epilogue is single-CTA");
+  static_assert(!MNM || (!PAIR && EPI == EPI_RES_F32 && BN % 64 == 0), "MN-major operands: single-CTA split-K weight gradients");
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   // round up to 1024 bytes (128-byte swizzle atoms) without casting through an integer, so that the compiler
@@ -142,6 +145,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d_pair(sA + s * A_STAGE_BYTES, &tmA, lbar, kb * BK, (m_blk * 2 + static_cast<int>(rank)) * BM);
           else if (lane == 1)
             tma_load_2d_pair(sB + s * C::B_STAGE_BYTES, &tmW, lbar, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+        } else if (MNM) {
+          // one box per lane: 64 output rows / columns (inner, contiguous in memory) x 64 tokens (outer)
+          if (lane == 0) mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          __syncwarp();
+          if (lane < 2) tma_load_2d(sA + s * A_STAGE_BYTES + lane * 8192, &tmA, &full_bar[s], m_blk * BM + lane * 64, kb * BK);
+          else if (lane < 2 + BN / 64)
+            tma_load_2d(sB + s * C::B_STAGE_BYTES + (lane - 2) * 8192, &tmW, &full_bar[s], n_blk * BN + (lane - 2) * 64, kb * BK);
         } else {
           if (lane == 0) mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           __syncwarp();
@@ -154,7 +164,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == kMmaWarp && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (the leader of a pair)
-    constexpr uint32_t idesc = PAIR ? umma_idesc_bf16_pair(BN) : umma_idesc_bf16(BN);
+    constexpr uint32_t idesc = PAIR ? umma_idesc_bf16_pair(BN) : MNM ? umma_idesc_bf16_mn(BN) : umma_idesc_bf16(BN);
+    // K = 16 per MMA: two 8-row groups of the MN-major tile (2 x 1024 B), or 32 bytes inside the K-major swizzle row
+    constexpr uint32_t kstep = MNM ? 128u : 2u;
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
@@ -168,13 +180,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&full_bar[s], ph);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t db = umma_desc_sw128(smem_u32(sB + s * C::B_STAGE_BYTES));
+          const uint64_t da = MNM ? umma_desc_sw128_mn(smem_u32(sA + s * A_STAGE_BYTES), 8192u) : umma_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES));
+          const uint64_t db = MNM ? umma_desc_sw128_mn(smem_u32(sB + s * C::B_STAGE_BYTES), 8192u) : umma_desc_sw128(smem_u32(sB + s * C::B_STAGE_BYTES));
           const int ksteps = min(BK, p.K - kb * BK) / 16;
           for (int k = 0; k < ksteps; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
-            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            else umma_bf16_ss(d_tmem, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) != 0);
           }
           if (PAIR) {
             umma_commit_pair(&empty_bar[s]);
@@ -355,6 +367,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; j += 2) f2_unpack(gelu_erf2(f2_pack(v[j], v[j + 1])), v[j], v[j + 1]);
           }
+          if (MNM) {
+            if (m_blk * BM + r_in_tile < p.scale_rows) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.row_scale;
+            }
+          }
           if (kOutBf16) {
             // 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
             uint8_t* rowp = buf + r_in_tile * 64;
@@ -470,7 +488,51 @@ int launch_pair(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMa
   return DSG_OK;
 }
 
+
+template <int BN>
+int launch_wgrad_t(const CUtensorMap* tmA, const CUtensorMap* tmW, const CUtensorMap* tmO, const GemmParams& p, cudaStream_t st) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI_RES_F32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<BN>::SMEM_BYTES));
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN) * (p.ksplit > 1 ? p.ksplit : 1);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<BN, EPI_RES_F32, false, true><<<grid, gemm_threads(EPI_RES_F32), Cfg<BN>::SMEM_BYTES, st>>>(*tmA, *tmW, *tmO, p);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
 }  // namespace
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes, int box_cols,
+                 int box_rows);
+
+int launch_wgrad(const void* dy, const void* x, float* dw, long long tokens, int n_out, int x_cols, int out_cols, int ksplit,
+                 int scale_rows, float row_scale, cudaStream_t st) {
+  DSG_REQUIRE(dy && x && dw && tokens > 0 && tokens % 16 == 0 && n_out % 8 == 0 && x_cols % 8 == 0 && out_cols > 0 &&
+                  out_cols <= x_cols && (out_cols * 4) % 16 == 0,
+              "wgrad: tokens %lld n_out %d x_cols %d out_cols %d (tokens %% 16, widths %% 8, 16-byte output rows)", tokens,
+              n_out, x_cols, out_cols);
+  const int bn = (x_cols % 192 == 0) ? 192 : 128;
+  CUtensorMap ta, tw, to;
+  if (int rc = make_tmap_2d(&ta, dy, tokens, n_out, 2, 64, 64)) return rc;
+  if (int rc = make_tmap_2d(&tw, x, tokens, x_cols, 2, 64, 64)) return rc;
+  if (int rc = make_tmap_out(&to, dw, n_out, out_cols, EPI_RES_F32)) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = n_out;
+  p.N = (x_cols + bn - 1) / bn * bn;
+  p.K = static_cast<int>(tokens);
+  p.res = dw; p.out = dw; p.ldo = p.N; p.bn = bn;
+  p.scale_rows = scale_rows; p.row_scale = row_scale;
+  const int num_kb = (p.K + BK - 1) / BK;
+  if (ksplit > 1) {
+    const int per = (num_kb + ksplit - 1) / ksplit;
+    p.ksplit = (num_kb + per - 1) / per;
+  }
+  return bn == 192 ? launch_wgrad_t<192>(&ta, &tw, &to, p, st) : launch_wgrad_t<128>(&ta, &tw, &to, p, st);
+}
 
 int make_tmap_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int elem_bytes, int box_cols,
                  int box_rows) {

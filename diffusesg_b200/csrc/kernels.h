@@ -34,6 +34,8 @@ struct GemmParams {
   int ldo;
   int bn;              // tile width: 0 = gemm_block_n(N); 256 needs N % 256 == 0 and a W descriptor with that box
   int ksplit;          // > 1: split the contraction into that many slices per output tile (EPI_RES_F32, no bias)
+  int scale_rows;      // weight-gradient GEMM: output rows < scale_rows are multiplied by row_scale (the q third of qkv)
+  float row_scale;
   // EPI_ADJ_HEAD only
   const float* w2t;    // [96][8]: second layer of the adj read-out MLP, transposed and zero padded
   const float* b2;     // [8]
@@ -53,6 +55,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t col
 // Output descriptor of a GEMM with epilogue `epi`: [rows, cols] bf16 / fp32, box = 32 cols x 128 rows
 // (64-byte swizzle for bf16, 128-byte for fp32).  Not used by EPI_ADJ_HEAD.
 int make_tmap_out(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int epi);
+
+// Weight gradient dW [n_out, out_cols] += dY^T . X with dY [tokens, n_out], X [tokens, x_cols] read as MN-major operands
+// straight from their row-major tensors (no transposes), contraction over the tokens split into `ksplit` slices.
+int launch_wgrad(const void* dy, const void* x, float* dw, long long tokens, int n_out, int x_cols, int out_cols, int ksplit,
+                 int scale_rows, float row_scale, cudaStream_t st);
 
 // N must be a multiple of 96; K a multiple of 32; rows beyond M are neither read as valid nor written.
 // box_rows of the W descriptor must equal gemm_block_n(N).

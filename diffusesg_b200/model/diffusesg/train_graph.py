@@ -22,7 +22,12 @@ import torch
 from ... import native
 from .geometry import block_table
 
+import os
+
 F32, BF16 = torch.float32, torch.bfloat16
+# weight gradients: MN-major tcgen05 operands read straight from the row-major tensors (default), or the first version -
+# token-major transposes + the K-major kernel (DSG_WGRAD_TRANSPOSE=1, kept for A/B runs)
+WGRAD_TRANSPOSE = os.environ.get("DSG_WGRAD_TRANSPOSE") == "1"
 HEAD_DIM = 32
 _BIG_SUFFIXES = (".attn.qkv", ".attn.proj", ".mlp.fc1", ".mlp.fc2", ".downsample.reduction", ".upsample.pre_linear",
                  ".upsample.post_linear")
@@ -214,6 +219,27 @@ class _Ops:
         _nc("dsg_gemm_bf16_ex", dy_t.data_ptr(), x_t.data_ptr(), None, dw.data_ptr(), dw.data_ptr(), n_out, n, mp,
             native.EPI_RES_F32, ksplit, k_in, self.st)
 
+    def wgrad_mn(self, dy16, x16, dw, scale_rows=0, scale=1.0):
+        """dw [N_out, K_in] += dy16 [M, N_out]^T @ x16 [M, x_cols]; both operands bf16 row-major, no transposes."""
+        m, n_out = dy16.shape
+        x_cols = x16.shape[1]
+        out_cols = dw.shape[1]
+        bn = 192 if x_cols % 192 == 0 else 128
+        tiles = ((n_out + 127) // 128) * ((x_cols + bn - 1) // bn)
+        num_kb = (m + 63) // 64
+        ksplit = max(1, min(296 // tiles, num_kb // 4))
+        _nc("dsg_tr_wgrad", dy16.data_ptr(), x16.data_ptr(), dw.data_ptr(), m, n_out, x_cols, out_cols, ksplit, scale_rows,
+            float(scale), self.st)
+
+    def cast_colsum(self, src, colsum=None, cast=False, scale_cols=0, scale=1.0):
+        """colsum [C] += column sums of src [M, C] (columns < scale_cols scaled); returns the bf16 copy when asked."""
+        m, c = src.shape
+        cst = self.empty((m, c), BF16) if cast else None
+        if cst is not None or colsum is not None:
+            _nc("dsg_tr_cast_colsum", src.data_ptr(), int(src.dtype == BF16), native.ptr(cst), native.ptr(colsum), m, c,
+                scale_cols, float(scale), self.st)
+        return cst
+
     def transpose(self, src, colsum=None, cast=False, scale_cols=0, scale=1.0):
         """src [M, C] (fp32 / bf16) -> ([C, Mp] bf16, optional [M, C] bf16 copy); colsum [C] += column sums."""
         m, c = src.shape
@@ -316,29 +342,40 @@ class TrainPass:
         self.tape: List = []
 
     # -- large linears ---------------------------------------------------------------------------------------------
-    def _lin_bwd(self, name, dy, x16, need_dx=True, dx_epi=native.EPI_F32, bias=True, scale_cols=0, x_t=None,
-                 transposed_weight=False):
-        """Gradients of y = x W^T + b into the flat buffer; returns dx.  dy fp32 or bf16 [M, N_out]."""
+    def _lin_bwd(self, name, dy, x16, need_dx=True, dx_epi=native.EPI_F32, bias=True, scale_cols=0, transposed_weight=False):
+        """Gradients of y = x W^T + b into the flat buffer; returns dx.  dy fp32 or bf16 [M, N_out], x16 bf16 [M, K_in]."""
         s, o = self.s, self.o
         db = s.g(name + ".bias") if bias else None
-        dy_t, dy16 = o.transpose(dy, colsum=db, cast=(dy.dtype != BF16 and need_dx), scale_cols=scale_cols,
-                                 scale=HEAD_DIM ** -0.5)
-        if dy.dtype == BF16:
-            dy16 = dy
-        if x_t is None:
-            x_t, _ = o.transpose(x16)
         dw = s.g(name + ".weight")
         dw2 = dw.view(dw.shape[0], -1)
-        if transposed_weight:   # ConvTranspose2d weight [in, out]: y = x W
-            o.wgrad(x_t, dy_t, dw2)
-        elif (dw2.shape[1] * 4) % 16 != 0:
-            # a weight row that is no multiple of 16 bytes (the 26 / 54-channel embeddings) cannot be a TMA destination:
-            # accumulate a zero-padded copy and add its leading columns
-            pad = o.zeros((dw2.shape[0], x_t.shape[0]))
-            o.wgrad(dy_t, x_t, pad)
-            o.copy_cols(pad, 0, dw2, 0, dw2.shape[1], accumulate=True)
+        scale = HEAD_DIM ** -0.5
+        if WGRAD_TRANSPOSE:
+            dy_t, dy16 = o.transpose(dy, colsum=db, cast=(dy.dtype != BF16 and need_dx), scale_cols=scale_cols, scale=scale)
+            if dy.dtype == BF16:
+                dy16 = dy
+            x_t, _ = o.transpose(x16)
+            if transposed_weight:   # ConvTranspose2d weight [in, out]: y = x W
+                o.wgrad(x_t, dy_t, dw2)
+            elif (dw2.shape[1] * 4) % 16 != 0:
+                pad = o.zeros((dw2.shape[0], x_t.shape[0]))
+                o.wgrad(dy_t, x_t, pad)
+                o.copy_cols(pad, 0, dw2, 0, dw2.shape[1], accumulate=True)
+            else:
+                o.wgrad(dy_t, x_t, dw2, k_in=dw2.shape[1])
         else:
-            o.wgrad(dy_t, x_t, dw2, k_in=dw2.shape[1])
+            dy16 = o.cast_colsum(dy, colsum=db, cast=dy.dtype != BF16, scale_cols=scale_cols, scale=scale)
+            if dy.dtype == BF16:
+                dy16 = dy
+            if transposed_weight:   # ConvTranspose2d weight [in, out]: y = x W, so dW = x^T dy
+                o.wgrad_mn(x16, dy16, dw2)
+            elif (dw2.shape[1] * 4) % 16 != 0:
+                # a weight row that is no multiple of 16 bytes (the 26 / 54-channel embeddings) cannot be a TMA destination:
+                # accumulate a zero-padded copy and add its leading columns
+                pad = o.zeros((dw2.shape[0], x16.shape[1]))
+                o.wgrad_mn(dy16, x16, pad)
+                o.copy_cols(pad, 0, dw2, 0, dw2.shape[1], accumulate=True)
+            else:
+                o.wgrad_mn(dy16, x16, dw2, scale_rows=scale_cols, scale=scale)
         if not need_dx:
             return None
         wd = s.wb[name] if transposed_weight else s.wbt[name]   # [K_in, N_out]
@@ -374,11 +411,9 @@ class TrainPass:
         hp = o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_BF16)
         h = o.gelu(hp)
         xo = o.gemm(h, s.wb[p + ".mlp.fc2"], s.w(p + ".mlp.fc2.bias"), native.EPI_RES_F32, res=xm, out=o.empty(xm.shape))
-        h_t, _ = o.transpose(h)      # the fc2 weight gradient's token-major operand, written while h is hot; h itself is dropped
-        del h
 
         def bwd(dxo):
-            dh = self._lin_bwd(p + ".mlp.fc2", dxo, None, dx_epi=native.EPI_BF16, x_t=h_t)
+            dh = self._lin_bwd(p + ".mlp.fc2", dxo, h, dx_epi=native.EPI_BF16)
             dhp = o.gelu(hp, dh)
             del dh
             dy2 = self._lin_bwd(p + ".mlp.fc1", dhp, y2)
@@ -517,7 +552,7 @@ class TrainPass:
         r0 = o.gemm(yf, s.wbt["read_out.0"], s.w("read_out.0.bias"), native.EPI_BF16)
         r1 = o.gemm(r0, s.wb["read_out.1"], s.w("read_out.1.bias"), native.EPI_BF16)
         rep = o.gemm(r1, s.wb["read_out.2"], s.w("read_out.2.bias"), native.EPI_F32)
-        rep_t, rep16 = o.transpose(rep, cast=True)
+        rep16 = o.cast_colsum(rep, cast=True)
         hap = o.gemm(rep16, s.wb["readout_adj_mlp.fc1"], s.w("readout_adj_mlp.fc1.bias"), native.EPI_BF16)
         ha = o.gelu(hap)
         wa2 = s.w("readout_adj_mlp.fc2.weight")
@@ -533,7 +568,7 @@ class TrainPass:
         out_node = o.empty(node.shape)
         _nc("dsg_tr_node_out", tok_n.data_ptr(), flags.data_ptr(), native.ptr(node) if mode == 1 else None, native.ptr(c_skip),
             native.ptr(c_out), out_node.data_ptr(), B, n, cn, 0, o.st)
-        del rep16, tok_a, tok_n
+        del tok_a, tok_n
         x_final = x
 
         def heads_bwd(d_adj, d_node):
@@ -546,7 +581,7 @@ class TrainPass:
             del dha32
             dhap = o.gelu(hap, dha)
             del dha
-            drep = self._lin_bwd("readout_adj_mlp.fc1", dhap, None, x_t=rep_t)
+            drep = self._lin_bwd("readout_adj_mlp.fc1", dhap, rep16)
             dtok_n = o.empty((B * n, cn))
             _nc("dsg_tr_node_out", d_node.data_ptr(), flags.data_ptr(), None, None, native.ptr(c_out), dtok_n.data_ptr(), B, n,
                 cn, 1, o.st)

@@ -110,6 +110,9 @@ _SIGNATURES = {
     "dsg_tr_add_inplace": (C.c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_void_p]),
     "dsg_tr_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,
                                    C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "dsg_tr_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_longlong] + [C.c_int] * 5 + [C.c_float, C.c_void_p]),
+    "dsg_tr_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p]),
     "dsg_tr_shuffle2x2": (C.c_int, [C.c_void_p] * 2 + [C.c_int] * 5 + [C.c_void_p]),
     "dsg_tr_copy_cols": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
                                    C.c_int, C.c_int, C.c_void_p]),

@@ -334,6 +334,16 @@ DSG_API int dsg_tr_add_inplace(float* y, const float* x, long long n, dsg_stream
  * multiplied by `scale` in dst_t and colsum (the q third of qkv runs pre-scaled by head_dim^-1/2, :118). */
 DSG_API int dsg_tr_transpose(const void* src, int src_is_bf16, void* dst_t, void* cast, float* colsum, long long M,
                              long long Mp, int C, int scale_cols, float scale, dsg_stream_t stream);
+/* The weight gradient of an nn.Linear without transposes: dw [n_out, out_cols] += dy^T . x with dy [tokens, n_out] and
+ * x [tokens, x_cols] bf16 row-major, read by TMA as they lie and fed to tcgen05.mma as MN-major operands (the
+ * non-contracted index is the contiguous one); contraction over the tokens in `ksplit` slices combined by the reduce-add
+ * epilogue; rows < scale_rows of dw are multiplied by row_scale (the q third of qkv, :118); out_cols <= x_cols (a zero
+ * padded input).  tokens % 16 == 0, widths % 8 == 0.  dsg_tr_cast_colsum prepares its operand: colsum [C] += column sums
+ * of dy (the bias gradient; columns < scale_cols scaled) and, for an fp32 dy, the bf16 copy. */
+DSG_API int dsg_tr_wgrad(const void* dy, const void* x, float* dw, long long tokens, int n_out, int x_cols, int out_cols,
+                         int ksplit, int scale_rows, float row_scale, dsg_stream_t stream);
+DSG_API int dsg_tr_cast_colsum(const void* src, int src_is_bf16, void* cast, float* colsum, long long M, int C,
+                               int scale_cols, float scale, dsg_stream_t stream);
 /* fine [B, 2H, 2W, C] <-> coarse [B, H, W, 4, C], chunk k = dy + 2 dx: the gather of PatchMerging (:325-329) and the
  * scatter of PatchBreakup (:394-397); to_coarse selects the direction (each is the other's backward). */
 DSG_API int dsg_tr_shuffle2x2(const float* src, float* dst, int B, int H, int W, int C, int to_coarse, dsg_stream_t stream);

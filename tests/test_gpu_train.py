@@ -156,6 +156,42 @@ def test_weight_gradient_split_k(n_out, k_in, M):
     assert _rel(dw, want) < 2e-5, _rel(dw, want)
 
 
+@pytest.mark.parametrize("n_out,x_cols,out_cols,M,scale_rows", [
+    (96, 96, 96, 4096, 0), (288, 96, 96, 20000, 96), (384, 1536, 1536, 8192, 0), (1536, 384, 384, 3008, 0),
+    (96, 96, 60, 5008, 0), (768, 768, 768, 48, 0), (2304, 768, 768, 1024, 768), (96, 384, 384, 524288, 0), (192, 192, 192, 64, 0)])
+def test_weight_gradient_mn_major(n_out, x_cols, out_cols, M, scale_rows):
+    """dW += dY^T X on the tcgen05 kernel with MN-major operands (dY and X read as they lie, no transposes), split-K."""
+    g = torch.Generator(device=DEV).manual_seed(n_out + M)
+    dy = torch.randn(M, n_out, device=DEV, generator=g).to(torch.bfloat16)
+    x = torch.randn(M, x_cols, device=DEV, generator=g).to(torch.bfloat16)
+    if out_cols != x_cols:
+        x[:, out_cols:] = 0
+    o = _ops()
+    dw = torch.full((n_out, out_cols), 0.5, device=DEV)
+    o.wgrad_mn(dy, x, dw, scale_rows=scale_rows, scale=0.25)
+    torch.cuda.synchronize()
+    want = dy.float().t() @ x.float()[:, :out_cols]
+    want[:scale_rows] *= 0.25
+    want += 0.5
+    assert _rel(dw, want) < 2e-5, _rel(dw, want)
+
+
+@pytest.mark.parametrize("M,Cdim,bf16", [(1000, 96, False), (2056, 288, True), (50, 1536, False), (70000, 384, True)])
+def test_cast_colsum(M, Cdim, bf16):
+    g = torch.Generator(device=DEV).manual_seed(M)
+    src = torch.randn(M, Cdim, device=DEV, generator=g)
+    if bf16:
+        src = src.to(torch.bfloat16)
+    colsum = torch.ones(Cdim, device=DEV)
+    o = _ops()
+    cast = o.cast_colsum(src, colsum=colsum, cast=not bf16, scale_cols=40, scale=0.25)
+    ref = src.float().sum(0)
+    ref[:40] *= 0.25
+    assert _rel(colsum - 1, ref) < 1e-4
+    if not bf16:
+        assert torch.equal(cast.float(), src.to(torch.bfloat16).float())
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 512, 96), (100, 9000, 512), (8192, 12, 96), (70000, 6, 96)])
 def test_small_fp32_gemm(M, N, K):
     g = torch.Generator(device=DEV).manual_seed(M + N)
