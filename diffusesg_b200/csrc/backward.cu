@@ -825,7 +825,8 @@ sgemm_kernel(const TA* __restrict__ A, long long sam, long long sak, const TB* _
       float val = acc[r][c];
       if (bias != nullptr && blockIdx.z == 0) val += bias[n];
       float* o = Cm + static_cast<long long>(m) * ldc + n;
-      if (gridDim.z > 1 || accumulate) atomicAdd(o, val);
+      if (gridDim.z > 1) atomicAdd(o, val);     // K slices meet in the output
+      else if (accumulate) *o += val;           // one slice: this CTA is the element's only writer
       else *o = val;
     }
   }
@@ -972,13 +973,16 @@ window_attention_bwd_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __rest
 //   sAcc          fp32 [T][T] dbias accumulator, sTok int [TP]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kQP = 40;
+// TC: compile-time token count of the window (64 for the 8 x 8 windows of the VG geometry: every index expression and
+// loop bound folds); 0 = taken from the window size at run time.
+template <int TC>
 __global__ void __launch_bounds__(256)
 window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ datt, const float* __restrict__ bias,
                                const float* __restrict__ mask, bf16_t* __restrict__ dqkv, float* __restrict__ dbias,
                                int batch, int res, int w, int shift, int heads, int items_per_cta) {
   using namespace nvcuda;
   extern __shared__ __align__(128) unsigned char smraw[];
-  const int T = w * w, TP = (T + 15) & ~15, NT = TP >> 4, C = heads * kHd;
+  const int T = TC ? TC : w * w, TP = (T + 15) & ~15, NT = TP >> 4, C = heads * kHd;
   const int PF = (TP + 16 > 80) ? TP + 16 : 80;
   bf16_t* sQ = reinterpret_cast<bf16_t*>(smraw);
   bf16_t* sK = sQ + TP * kQP;
@@ -1518,7 +1522,8 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   static PerDeviceOnce configured;
   if (configured.first()) {
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int total = batch * (res / window) * (res / window);
   // one atomicAdd pass over dbias per CTA: keep the CTA count near two waves
@@ -1527,8 +1532,12 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   if (ctas_x > total) ctas_x = total;
   const int per = (total + ctas_x - 1) / ctas_x;
   ctas_x = (total + per - 1) / per;
-  if (tc)
-    window_attention_bwd_tc_kernel<<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  if (tc && T == 64)
+    window_attention_bwd_tc_kernel<64><<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
+        res, window, shift, heads, per);
+  else if (tc)
+    window_attention_bwd_tc_kernel<0><<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
         res, window, shift, heads, per);
   else

@@ -307,7 +307,10 @@ class _Ops:
     def sgemm(self, a, a_strides, b, b_strides, m, n, k, bias=None, out=None, accumulate=False, ksplit=1):
         """out [m, n] (+)= sum_k a[m * a_strides[0] + k * a_strides[1]] * b[k * b_strides[0] + n * b_strides[1]]"""
         if out is None:
-            out = self.empty((m, n))
+            ctas = ((m + 63) // 64) * ((n + 63) // 64)
+            if ksplit == 1 and ctas < 148 and k >= 2048:      # few output tiles, long contraction: slices meet by atomicAdd
+                ksplit = max(1, min(k // 512, 296 // ctas))
+            out = self.zeros((m, n)) if ksplit > 1 else self.empty((m, n))
         _nc("dsg_tr_sgemm", a.data_ptr(), int(a.dtype == BF16), a_strides[0], a_strides[1], b.data_ptr(), int(b.dtype == BF16),
             b_strides[0], b_strides[1], native.ptr(bias), out.data_ptr(), out.shape[-1], m, n, k, ksplit,
             int(accumulate or ksplit > 1), self.st)
