@@ -210,36 +210,52 @@ film_silu_fwd_kernel(const float* __restrict__ v, const float* __restrict__ film
   }
 }
 
-// du = dout silu'(u); dv = du (1 + scale); dscale[b, c] += sum_tokens du v; dshift[b, c] += sum_tokens du
+// du = dout silu'(u); dv = du (1 + scale); dscale[b, c] += sum_tokens du v; dshift[b, c] += sum_tokens du.
+// A thread keeps one float4 channel group for a strided run of the chunk's tokens, so the two parameter gradients
+// accumulate in registers; threads of the same group meet in shared memory once per CTA (one atomic per channel per CTA).
+constexpr int kFilmBwdTokens = 128;
 __global__ void __launch_bounds__(256)
 film_silu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ v, const float* __restrict__ film, int ldf,
                      int off, float* __restrict__ dv, float* __restrict__ dfilm, int L, int C) {
   extern __shared__ float sacc[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += 256) sacc[i] = 0.f;
   __syncthreads();
-  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
-  const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kFilmTokens;
-  const int nt = min(kFilmTokens, L - t0);
+  const int chunks = (L + kFilmBwdTokens - 1) / kFilmBwdTokens;
+  const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kFilmBwdTokens;
+  const int nt = min(kFilmBwdTokens, L - t0);
   const float* fs = film + static_cast<size_t>(b) * ldf + off;
   const size_t base = (static_cast<size_t>(b) * L + t0) * C;
   const int nv = C >> 2;
-  for (int i = threadIdx.x; i < nt * nv; i += 256) {
-    const int c = (i % nv) * 4;
-    const size_t o = base + static_cast<size_t>(i / nv) * C + c;
-    const float4 a = ld4(v + o), sc = ld4(fs + c), sh = ld4(fs + C + c), g = ld4(dout + o);
-    const float av[4] = {a.x, a.y, a.z, a.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w},
-                gv[4] = {g.x, g.y, g.z, g.w};
-    float r[4];
+  // groups are walked in passes of 256 threads: thread -> (group g = (pass * 256 + tid) % nv is NOT fixed), so fix it:
+  // rows-per-pass R = 256 / nvp threads share a group, nvp = groups handled per pass
+  const int nvp = nv < 256 ? nv : 256;          // groups per pass
+  const int R = 256 / nvp;                      // token rows in flight per pass
+  const int gl = threadIdx.x % nvp, rl = threadIdx.x / nvp;
+  for (int g0 = 0; g0 < nv; g0 += nvp) {
+    const int g = g0 + gl;
+    if (g >= nv || rl >= R) continue;
+    const int c = 4 * g;
+    const float4 sc = ld4(fs + c), sh = ld4(fs + C + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    float as[4] = {0.f, 0.f, 0.f, 0.f}, ah[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = rl; t < nt; t += R) {
+      const size_t o = base + static_cast<size_t>(t) * C + c;
+      const float4 a = ld4(v + o), gd = ld4(dout + o);
+      const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {gd.x, gd.y, gd.z, gd.w};
+      float r[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float u = fmaf(av[k], scv[k] + 1.f, shv[k]);
-      const float sg = sigmoid_f(u);
-      const float du = gv[k] * sg * (1.f + u * (1.f - sg));
-      r[k] = du * (scv[k] + 1.f);
-      atomicAdd(&sacc[c + k], du * av[k]);
-      atomicAdd(&sacc[C + c + k], du);
+      for (int k = 0; k < 4; ++k) {
+        const float u = fmaf(av[k], scv[k] + 1.f, shv[k]);
+        const float sg = sigmoid_f(u);
+        const float du = gv[k] * sg * (1.f + u * (1.f - sg));
+        r[k] = du * (scv[k] + 1.f);
+        as[k] = fmaf(du, av[k], as[k]);
+        ah[k] += du;
+      }
+      st4(dv + o, make_float4(r[0], r[1], r[2], r[3]));
     }
-    st4(dv + o, make_float4(r[0], r[1], r[2], r[3]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { atomicAdd(&sacc[c + k], as[k]); atomicAdd(&sacc[C + c + k], ah[k]); }
   }
   __syncthreads();
   float* df = dfilm + static_cast<size_t>(b) * ldf + off;
@@ -302,7 +318,10 @@ gelu_f32_kernel(const float* __restrict__ pre, const float* __restrict__ dout, f
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256)
     out[i] = dout == nullptr ? gelu_exact(pre[i]) : dout[i] * gelu_grad(pre[i]);
 }
-// out[c] += sum over rows of src[r, c] (bias gradients of the small fp32 layers)
+// out[c] += sum over rows of src[r, c] (bias gradients of the small fp32 layers): a thread per column for wide matrices;
+// for narrow ones (the c_e = 6 / c_n = 12 wide outputs: a thread per column would leave most of the CTA idle) a flat
+// mapping - thread t walks elements t, t + 256, ... of the CTA's row chunk, coalesced whatever C is - with a private
+// shared-memory accumulator row per thread (no atomics, no contention), reduced once per CTA.
 __global__ void __launch_bounds__(256)
 colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ out, long long M, int C, int rows_per_cta) {
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -310,6 +329,28 @@ colsum_f32_kernel(const float* __restrict__ src, float* __restrict__ out, long l
     float s = 0.f;
     for (long long r = r0; r < r1; ++r) s += src[r * C + c];
     atomicAdd(&out[c], s);
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_narrow_kernel(const float* __restrict__ src, float* __restrict__ out, long long M, int C, int rows_per_cta) {
+  extern __shared__ float priv[];  // [256][C]
+  float* mine = priv + threadIdx.x * C;
+  for (int c = 0; c < C; ++c) mine[c] = 0.f;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const long long n = (r1 - r0) * C;
+  const float* p = src + r0 * C;
+  int c = threadIdx.x % C;
+  const int step = 256 % C;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    mine[c] += p[i];
+    c += step;
+    if (c >= C) c -= C;
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += 256) {
+    float s = 0.f;
+    for (int t = 0; t < 256; ++t) s += priv[t * C + cc];
+    atomicAdd(&out[cc], s);
   }
 }
 // EDM preconditioning coefficients (runner/objectives/edm.py:122-126), sigma_data = 0.5: out = [c_skip | c_out | c_in | c_noise]
@@ -636,26 +677,44 @@ __global__ void __launch_bounds__(256)
 embed_input_kernel(const float* __restrict__ adj, const float* __restrict__ node, const float* __restrict__ sc_adj,
                    const float* __restrict__ sc_node, const uint8_t* __restrict__ flags, const float* __restrict__ c_in,
                    bf16_t* __restrict__ out, int B, int n, int c_e, int c_n, int self_cond, int ld) {
+  // work item = (32 consecutive pixels, one group of 8 output channels): the adjacency planes are read 128 bytes per warp,
+  // every lane writes one 16-byte piece of its pixel's row
+  const int groups = ld >> 3;
   const long long total = static_cast<long long>(B) * n * n;
   const int nn = n * n;
-  for (long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; pix < total; pix += static_cast<long long>(gridDim.x) * 256) {
+  const long long items = ((total + 31) / 32) * groups;
+  const int lane = threadIdx.x & 31;
+  const int ce_all = self_cond ? 2 * c_e : c_e, cn_all = self_cond ? 2 * c_n : c_n;
+  for (long long it = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); it < items; it += static_cast<long long>(gridDim.x) * 8) {
+    const int grp = static_cast<int>(it % groups);
+    const long long pix = (it / groups) * 32 + lane;
+    if (pix >= total) continue;
     const int b = static_cast<int>(pix / nn), ij = static_cast<int>(pix - static_cast<long long>(b) * nn);
     const int i = ij / n, j = ij - i * n;
     const float ci = c_in != nullptr ? c_in[b] : 1.f;
     const bool ok = flags[b * n + i] != 0 && flags[b * n + j] != 0;
-    bf16_t* o = out + pix * ld;
-    int k = 0;
-    if (self_cond) {
-      for (int c = 0; c < c_e; ++c) o[k++] = __float2bfloat16_rn(sc_adj != nullptr ? sc_adj[(static_cast<size_t>(b) * c_e + c) * nn + ij] : 0.f);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = 8 * grp + k;
+      float val = 0.f;
+      if (ch < ce_all) {                                   // adjacency planes: self-conditioning first (:791-794)
+        const bool is_sc = self_cond && ch < c_e;
+        const int c = is_sc ? ch : ch - (self_cond ? c_e : 0);
+        if (is_sc) val = sc_adj != nullptr ? sc_adj[(static_cast<size_t>(b) * c_e + c) * nn + ij] : 0.f;
+        else val = ci * adj[(static_cast<size_t>(b) * c_e + c) * nn + ij];
+      } else if (ch < ce_all + 2 * cn_all) {               // node planes of i, then of j, masked by flag_i & flag_j (:797-800)
+        const int q = ch - ce_all, side = q / cn_all, cc = q - side * cn_all;
+        const size_t nrow = (static_cast<size_t>(b) * n + (side == 0 ? i : j)) * c_n;
+        const bool is_sc = self_cond && cc < c_n;
+        if (ok) {
+          if (is_sc) val = sc_node != nullptr ? sc_node[nrow + cc] : 0.f;
+          else val = ci * node[nrow + cc - (self_cond ? c_n : 0)];
+        }
+      }
+      f[k] = val;
     }
-    for (int c = 0; c < c_e; ++c) o[k++] = __float2bfloat16_rn(ci * adj[(static_cast<size_t>(b) * c_e + c) * nn + ij]);
-    for (int side = 0; side < 2; ++side) {
-      const size_t nrow = (static_cast<size_t>(b) * n + (side == 0 ? i : j)) * c_n;
-      if (self_cond)
-        for (int c = 0; c < c_n; ++c) o[k++] = __float2bfloat16_rn(ok && sc_node != nullptr ? sc_node[nrow + c] : 0.f);
-      for (int c = 0; c < c_n; ++c) o[k++] = __float2bfloat16_rn(ok ? ci * node[nrow + c] : 0.f);
-    }
-    for (; k < ld; ++k) o[k] = __float2bfloat16_rn(0.f);
+    *reinterpret_cast<uint4*>(out + pix * ld + 8 * grp) = pack8(f);
   }
 }
 
@@ -983,7 +1042,10 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
   using namespace nvcuda;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int T = TC ? TC : w * w, TP = (T + 15) & ~15, NT = TP >> 4, C = heads * kHd;
-  const int PF = (TP + 16 > 80) ? TP + 16 : 80;
+  // fp32 pitch of S / dP.  P and dS are re-read as bf16 with a row stride of PF words: PF % 32 == 20 keeps the eight 16-byte
+  // rows of a fragment load on distinct banks (80 gave 4-way conflicts); 10 x 10 windows keep 128 (shared-memory budget)
+  const int PF = TP <= 64 ? 84 : ((TP + 16 > 80) ? TP + 16 : 80);
+  const int ST = TP <= 64 ? 40 : PF / 2;          // first float of the staging half of a row (32-byte aligned, past the bf16 P)
   bf16_t* sQ = reinterpret_cast<bf16_t*>(smraw);
   bf16_t* sK = sQ + TP * kQP;
   bf16_t* sV = sK + TP * kQP;
@@ -996,8 +1058,8 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
   bf16_t* sPb = reinterpret_cast<bf16_t*>(sS);    // P, bf16, row pitch 2 PF
   bf16_t* sDb = reinterpret_cast<bf16_t*>(sD);    // dS
   const int LDB = 2 * PF;
-  float* stV = sS + PF / 2;                       // fp32 staging [TP][32], row pitch PF
-  float* stQ = sD + PF / 2;
+  float* stV = sS + ST;                           // fp32 staging [TP][32], row pitch PF
+  float* stQ = sD + ST;
   float* stK = sS;
   const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = res / w, nW = nw * nw;
@@ -1315,7 +1377,7 @@ int dsg_tr_film_silu_bwd(const float* dout, const float* v, const float* film, i
                          int B, int L, int C, dsg_stream_t stream) {
   DSG_REQUIRE(dout && v && film && dv && dfilm && B > 0 && L > 0 && C % 4 == 0 && off % 4 == 0 && ldf % 4 == 0 && C <= 4096,
               "tr_film_silu_bwd: bad argument");
-  const int chunks = (L + kFilmTokens - 1) / kFilmTokens;
+  const int chunks = (L + kFilmBwdTokens - 1) / kFilmBwdTokens;
   film_silu_bwd_kernel<<<B * chunks, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(dout, v, film, ldf, off, dv, dfilm, L, C);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
@@ -1342,8 +1404,14 @@ int dsg_tr_gelu_f32(const float* pre, const float* dout, float* out, long long n
 
 int dsg_tr_colsum(const float* src, float* out, long long M, int C, dsg_stream_t stream) {
   DSG_REQUIRE(src && out && M > 0 && C > 0, "tr_colsum: bad argument");
-  const int rows = 256;
-  colsum_f32_kernel<<<static_cast<unsigned>((M + rows - 1) / rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, out, M, C, rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C <= 32) {
+    const int rows = 32768 / C;    // ~32 k elements per CTA
+    colsum_narrow_kernel<<<static_cast<unsigned>((M + rows - 1) / rows), 256, 256 * C * sizeof(float), st>>>(src, out, M, C, rows);
+  } else {
+    const int rows = 256;
+    colsum_f32_kernel<<<static_cast<unsigned>((M + rows - 1) / rows), 256, 0, st>>>(src, out, M, C, rows);
+  }
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }
@@ -1436,7 +1504,8 @@ int dsg_tr_embed_input(const float* adj, const float* node, const float* sc_adj,
                        const float* c_in, void* out, int B, int n, int c_e, int c_n, int self_cond, int ld,
                        dsg_stream_t stream) {
   DSG_REQUIRE(adj && node && flags && out && (self_cond ? 2 : 1) * (c_e + 2 * c_n) <= ld, "tr_embed_input: bad argument");
-  embed_input_kernel<<<grid_for(static_cast<long long>(B) * n * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  DSG_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "tr_embed_input: ld %% 8 == 0, 16-byte aligned output");
+  embed_input_kernel<<<grid_for(static_cast<long long>(B) * n * n * (ld / 8), 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       adj, node, sc_adj, sc_node, flags, c_in, static_cast<bf16_t*>(out), B, n, c_e, c_n, self_cond, ld);
   DSG_LAUNCH_CHECK();
   return DSG_OK;
@@ -1513,7 +1582,7 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   DSG_REQUIRE(shift == 0 || mask != nullptr, "tr_window_attention_bwd: shifted windows need the attention mask");
   const int T = window * window;
   static const bool fp32_only = getenv("DSG_ATTN_BWD_FP32") != nullptr && getenv("DSG_ATTN_BWD_FP32")[0] == '1';
-  const int TP = (T + 15) & ~15, PF = (TP + 16 > 80) ? TP + 16 : 80;
+  const int TP = (T + 15) & ~15, PF = TP <= 64 ? 84 : ((TP + 16 > 80) ? TP + 16 : 80);
   const size_t smem_tc = static_cast<size_t>(4) * TP * kQP * 2 + static_cast<size_t>(2) * TP * PF * 4 + static_cast<size_t>(2) * T * T * 4 + static_cast<size_t>(TP) * 4;
   const size_t smem_f32 = (static_cast<size_t>(4) * T * kHdP + 2 * static_cast<size_t>(T) * (T + 1) + static_cast<size_t>(T) * T) * 4 + static_cast<size_t>(T) * 4;
   const bool tc = !fp32_only && smem_tc <= 227 * 1024;

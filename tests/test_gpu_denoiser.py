@@ -563,3 +563,32 @@ def test_kernels_ignore_shared_memory_leftovers(name, batch):
             for (wa, wn), (ga, gn) in zip(want, got):
                 assert torch.isfinite(ga).all() and torch.isfinite(gn).all(), hex(pattern)
                 assert torch.equal(wa, ga) and torch.equal(wn, gn), hex(pattern)
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 6), ("vg", 4), ("coco", 4)])
+def test_sampler_ignores_shared_memory_leftovers(name, batch):
+    """The whole eager sampler path (EDM step kernels with in-kernel noise, padding-skipping schedule, fused decode of the
+    last step) with all shared memory overwritten by a NaN pattern after every launch: bit-identical samples and classes."""
+    cfg = CONFIGS[name]
+    net, _ = build(cfg)
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=True, symmetric_noise=False).eval()
+    _, _, flags, _, _, _ = synthetic_inputs(cfg, batch, seed=9)
+    outs = []
+    for poison in (0, 1):
+        sampler = NodeAdjEDMSampler(num_steps=4, clip_samples=True, clip_samples_min=-1.0, clip_samples_max=1.0,
+                                    clip_samples_scope="x_0", dev=DEV, objective="edm", self_condition=True,
+                                    symmetric_noise=False)
+        sampler.use_graphs = False            # the poison kernel runs on the legacy default stream between eager launches
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)
+        np.random.seed(5)
+        native.lib().dsg_debug_set_smem_poison(0x7fc00000, poison)
+        try:
+            out = sampler.sample_decoded(model, flags.to(DEV), 7, 150, num_node_chan=cfg["c_n"], num_edge_chan=cfg["c_e"],
+                                         return_state=True)
+            torch.cuda.synchronize()
+        finally:
+            native.lib().dsg_debug_set_smem_poison(0, 0)
+        outs.append(out)
+    for x, y in zip(*outs):
+        assert torch.isfinite(y.float()).all() and torch.equal(x, y)
