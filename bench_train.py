@@ -60,9 +60,8 @@ def workload(args, cfg, world):
             "l2": "activations per step (>= 7 GB at batch 128) exceed the 126 MB L2; no flush needed"}
 
 
-def run_reference(args, cfg, rank, world):
-    if rank != 0:
-        return
+def reference_rate(cfg, cpu_batch, steps, warmup):
+    """The unmodified reference's training iteration on all host cores -> dict(rate graphs/s, sec, cores, sample)."""
     from oracle import stage_reference as R
     torch.set_num_threads(os.cpu_count() or 1)
     ref = R.load()
@@ -73,7 +72,7 @@ def run_reference(args, cfg, rank, world):
     loss_fn = ref.NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=1.0, objective="edm")
     opt = torch.optim.Adam(model.parameters(), lr=LR, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
     emas = [[p.detach().clone() for p in model.parameters()] for _ in EMA_COEFS]
-    adj, node, flags = clean_batch(cfg, args.cpu_batch, 1234)
+    adj, node, flags = clean_batch(cfg, cpu_batch, 1234)
     torch.manual_seed(1234)
     np.random.seed(1234)
 
@@ -93,22 +92,28 @@ def run_reference(args, cfg, rank, world):
                     e.lerp_(p, 1 - d)
 
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
         step(i)
-        if i >= args.warmup:
+        if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    rate = args.cpu_batch / sec
-    config = workload(args, cfg, world)
-    config["measured_sample"] = {"batch": args.cpu_batch, "device": "cpu", "world": 1, "sec_per_step": sec}
     sample = (f"the UNMODIFIED reference (oracle/_ref: NodeAdjPrecond(DiffuseSG), objective generator, rainbow loss; "
-              f"torch.optim.Adam; hand-written EMA lerps), fp32, dev=cpu, batch {args.cpu_batch}, {sec:.2f} s per iteration")
-    B.emit({"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              f"torch.optim.Adam; hand-written EMA lerps), fp32, dev=cpu, batch {cpu_batch}, {sec:.2f} s per iteration")
+    return dict(rate=cpu_batch / sec, sec=sec, cores=torch.get_num_threads(), sample=sample)
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    r = reference_rate(cfg, args.cpu_batch, args.steps, args.warmup)
+    config = workload(args, cfg, world)
+    config["measured_sample"] = {"batch": args.cpu_batch, "device": "cpu", "world": 1, "sec_per_step": r["sec"]}
+    B.emit({"impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["sec"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference", "sample": sample},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            "cpu_baseline": {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+            "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def run_native(args, cfg, rank, local_rank, world):
@@ -208,6 +213,9 @@ def run_native(args, cfg, rank, local_rank, world):
                          "note": "whole step per GPU: dense reference flops (forward 13.3 GF/graph, backward 2x, plus the "
                                  "no-grad self-conditioning passes) / step time; peak = " + pk["source"]},
             "loss": float(sum(t.mean() for t in last["loss"]).item())}
+    if world == 1 and not args.no_cpu_baseline:
+        r = reference_rate(cfg, args.cpu_batch, 2, 1)
+        line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
     B.emit(line)
 
 
@@ -223,6 +231,7 @@ def main():
     ap.add_argument("--config", default="vg", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per iteration")
     ap.add_argument("--data-seed", type=int, default=1234, help="seed of the synthetic clean batch (+ rank)")
     args = ap.parse_args()

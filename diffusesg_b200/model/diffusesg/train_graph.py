@@ -342,7 +342,6 @@ class TrainPass:
     def __init__(self, state: TrainState):
         self.s = state
         self.o = _Ops(state.dev)
-        self.tape: List = []
 
     # -- large linears ---------------------------------------------------------------------------------------------
     def _lin_bwd(self, name, dy, x16, need_dx=True, dx_epi=native.EPI_F32, bias=True, scale_cols=0, transposed_weight=False):
@@ -517,7 +516,6 @@ class TrainPass:
         t0 = o.gemm(inp, s.wb["patch_embed.proj"], s.w("patch_embed.proj.bias"), native.EPI_F32)
         _, v0 = o.ln_fwd(t0, s.w("patch_embed.norm.weight"), s.w("patch_embed.norm.bias"), bf16=False, f32=True)
         x = o.film_fwd(v0, film, s.film_off["patch_embed.affine"], B, n * n, E)
-        tape = self.tape
 
         def embed_bwd(dx):
             dv = o.film_bwd(dx, v0, film, s.film_off["patch_embed.affine"], dfilm, B, n * n, E)
