@@ -342,6 +342,7 @@ class TrainPass:
     def __init__(self, state: TrainState):
         self.s = state
         self.o = _Ops(state.dev)
+        self.record = True     # False: a no-grad pass - nothing of the forward is kept, GELU rides in the fc1 epilogue
 
     # -- large linears ---------------------------------------------------------------------------------------------
     def _lin_bwd(self, name, dy, x16, need_dx=True, dx_epi=native.EPI_F32, bias=True, scale_cols=0, transposed_weight=False):
@@ -410,8 +411,11 @@ class TrainPass:
             heads, fl, o.st)
         xm = o.gemm(att, s.wb[p + ".attn.proj"], s.w(p + ".attn.proj.bias"), native.EPI_RES_F32, res=xf, out=o.empty(xf.shape))
         y2, _ = o.ln_fwd(xm, s.w(p + ".norm2.weight"), s.w(p + ".norm2.bias"))
-        hp = o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_BF16)
-        h = o.gelu(hp)
+        if self.record:
+            hp = o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_BF16)   # pre-activation kept for GELU'
+            h = o.gelu(hp)
+        else:
+            hp, h = None, o.gemm(y2, s.wb[p + ".mlp.fc1"], s.w(p + ".mlp.fc1.bias"), native.EPI_GELU_BF16)
         xo = o.gemm(h, s.wb[p + ".mlp.fc2"], s.w(p + ".mlp.fc2.bias"), native.EPI_RES_F32, res=xm, out=o.empty(xm.shape))
 
         def bwd(dxo):
@@ -693,6 +697,7 @@ def run_training_forward(module, mode, adj, node, flags, noise, sc_adj, sc_node)
             # the self-conditioning refresh of a training step (model/precond/precond.py:90-98): same kernels, no tape kept -
             # the fused inference schedule would need its packed weight arena rebuilt after every optimiser step
             tp = TrainPass(st)
+            tp.record = False
             out = tp.forward(mode, adj, node, flags, noise, sc_adj, sc_node)
             del tp
             return out
