@@ -7,8 +7,10 @@
 // (LayerNorm :243/:275, FiLM + SiLU :238-240/:574-576, nn.GELU :15, PatchMerging :314-335, PatchBreakup :374-403,
 // WindowAttention :108-139, the read-out heads :806-825) and model/precond/precond.py:100-105.
 //
-// All kernels are HBM-bound row kernels (one warp per token row, 16-byte accesses) except window_attention_bwd_kernel,
-// which is a CUDA-core fp32 kernel (five T x T x 32 products per window-head from shared memory).
+// All kernels are HBM-bound row kernels (one warp per token row, 16-byte accesses) except the window-attention backward
+// (window_attention_bwd_tc_kernel: warp-level tensor cores, five T x T x 32 products per window-head from shared memory;
+// window_attention_bwd_kernel is its fp32 CUDA-core predecessor, kept behind DSG_ATTN_BWD_FP32=1 as a numerical reference)
+// and the small strided fp32 GEMM for the batch-sized layers.
 #include <math.h>
 #include <mma.h>
 
@@ -49,8 +51,8 @@ DSG_DEVICE float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default
 
 // ---------------------------------------------------------------------------------------------------------
-// LayerNorm forward (training form): y = (x - mean) * rstd * gamma + beta, one warp per row, two exact passes for
-// the statistics (the row stays in L1).  Writes bf16 (GEMM operand) and / or fp32.
+// LayerNorm forward (training form): y = (x - mean) * rstd * gamma + beta, one warp per row held in registers, mean and
+// centred variance as two exact reductions.  Writes bf16 (GEMM operand) and / or fp32.
 // ---------------------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(256)
@@ -824,6 +826,74 @@ node_pool_bwd_kernel(const float* __restrict__ dpooled, const uint8_t* __restric
   }
 }
 
+// Second layer of the adjacency read-out MLP (diffusesg.py:806-809), c_e <= 8 outputs per pixel from `embed` <= 128 hidden
+// channels: far too narrow for a GEMM tile (a 64 x 64 tile would waste 90 % of its work).  One warp per pixel row, a lane
+// owns channels lane + 32 k with the c_e x 4 weights in registers.
+//   forward:  tok[m, c] = b[c] + sum_e h[m, e] w[c, e]
+//   wgrad:    dw[c, e] += sum_m dtok[m, c] h[m, e]   (register accumulators per warp, shared memory per CTA, one atomic per
+//             entry per CTA)
+__global__ void __launch_bounds__(256)
+adj_fc2_fwd_kernel(const bf16_t* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ tok,
+                   long long M, int E, int ce) {
+  const int lane = threadIdx.x & 31;
+  float wv[8][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wv[c][k] = (c < ce && lane + 32 * k < E) ? w[c * E + lane + 32 * k] : 0.f;
+  const float bias = lane < ce ? b[lane] : 0.f;
+  const long long warps = static_cast<long long>(gridDim.x) * 8;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); row < M; row += warps) {
+    float hv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = lane + 32 * k < E ? __bfloat162float(h[row * E + lane + 32 * k]) : 0.f;
+    float mine = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a = fmaf(wv[c][k], hv[k], a);
+      a = warp_sum(a);
+      if (lane == c) mine = a;
+    }
+    if (lane < ce) tok[row * ce + lane] = mine + bias;
+  }
+}
+__global__ void __launch_bounds__(256)
+adj_fc2_wgrad_kernel(const float* __restrict__ dtok, const bf16_t* __restrict__ h, float* __restrict__ dw, long long M, int E,
+                     int ce, int rows_per_cta) {
+  __shared__ float sacc[8 * 128];
+  for (int i = threadIdx.x; i < 8 * 128; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[8][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+  for (long long row = r0 + (threadIdx.x >> 5); row < r1; row += 8) {
+    float hv[4], d[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hv[k] = lane + 32 * k < E ? __bfloat162float(h[row * E + lane + 32 * k]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) d[c] = c < ce ? dtok[row * ce + c] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[c][k] = fmaf(d[c], hv[k], acc[c][k]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(&sacc[c * 128 + lane + 32 * k], acc[c][k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ce * E; i += 256) {
+    const int c = i / E, e = i - c * E;
+    atomicAdd(&dw[i], sacc[c * 128 + e]);
+  }
+}
+
 // sinusoidal noise embedding (PositionalEmbedding, diffusesg.py:507-513): [cos(x f_k) | sin(x f_k)], f_k = 10000^(-k / half)
 __global__ void posemb_kernel(const float* __restrict__ labels, float* __restrict__ out, int B, int embed) {
   const int half = embed / 2;
@@ -1552,6 +1622,20 @@ int dsg_tr_node_pool(const float* rep, const uint8_t* flags, float* pooled, cons
     node_pool_train_kernel<<<static_cast<unsigned>((static_cast<long long>(B) * n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(rep, flags, pooled, B, n, C);
   else
     node_pool_bwd_kernel<<<grid_for(static_cast<long long>(B) * n * n * C / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(dpooled, flags, drep, B, n, C);
+  DSG_LAUNCH_CHECK();
+  return DSG_OK;
+}
+
+int dsg_tr_adj_fc2(const void* h, const float* w, const float* b, float* tok, const float* dtok, float* dw, long long M, int E,
+                   int ce, dsg_stream_t stream) {
+  DSG_REQUIRE(h && M > 0 && E > 0 && E <= 128 && ce > 0 && ce <= 8 && ((w && b && tok) || (dtok && dw)), "tr_adj_fc2: bad argument (embed <= 128, c_e <= 8)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtok == nullptr) {
+    adj_fc2_fwd_kernel<<<grid_for(M, 8 * 8, 8), 256, 0, st>>>(static_cast<const bf16_t*>(h), w, b, tok, M, E, ce);
+  } else {
+    const int rows = 4096;
+    adj_fc2_wgrad_kernel<<<static_cast<unsigned>((M + rows - 1) / rows), 256, 0, st>>>(dtok, static_cast<const bf16_t*>(h), dw, M, E, ce, rows);
+  }
   DSG_LAUNCH_CHECK();
   return DSG_OK;
 }

@@ -561,7 +561,13 @@ class TrainPass:
         hap = o.gemm(rep16, s.wb["readout_adj_mlp.fc1"], s.w("readout_adj_mlp.fc1.bias"), native.EPI_BF16)
         ha = o.gelu(hap)
         wa2 = s.w("readout_adj_mlp.fc2.weight")
-        tok_a = o.sgemm(ha, (E, 1), wa2, (1, E), M, ce, E, bias=s.w("readout_adj_mlp.fc2.bias"))
+        narrow = ce <= 8 and E <= 128     # the dedicated warp-per-pixel kernels; otherwise the generic fp32 GEMM
+        if narrow:
+            tok_a = o.empty((M, ce))
+            _nc("dsg_tr_adj_fc2", ha.data_ptr(), wa2.data_ptr(), s.w("readout_adj_mlp.fc2.bias").data_ptr(), tok_a.data_ptr(),
+                None, None, M, E, ce, o.st)
+        else:
+            tok_a = o.sgemm(ha, (E, 1), wa2, (1, E), M, ce, E, bias=s.w("readout_adj_mlp.fc2.bias"))
         out_adj = o.empty(adj.shape)
         _nc("dsg_tr_adj_out", tok_a.data_ptr(), flags.data_ptr(), native.ptr(adj) if mode == 1 else None, native.ptr(c_skip),
             native.ptr(c_out), out_adj.data_ptr(), B, n, ce, 0, o.st)
@@ -580,7 +586,13 @@ class TrainPass:
             dtok_a = o.empty((M, ce))
             _nc("dsg_tr_adj_out", d_adj.data_ptr(), flags.data_ptr(), None, None, native.ptr(c_out), dtok_a.data_ptr(), B, n,
                 ce, 1, o.st)
-            dha32 = o.linear_small_bwd(dtok_a, ha, wa2, s.g("readout_adj_mlp.fc2.weight"), s.g("readout_adj_mlp.fc2.bias"))
+            if narrow:
+                _nc("dsg_tr_colsum", dtok_a.data_ptr(), s.g("readout_adj_mlp.fc2.bias").data_ptr(), M, ce, o.st)
+                _nc("dsg_tr_adj_fc2", ha.data_ptr(), None, None, None, dtok_a.data_ptr(),
+                    s.g("readout_adj_mlp.fc2.weight").data_ptr(), M, E, ce, o.st)
+                dha32 = o.sgemm(dtok_a, (ce, 1), wa2, (E, 1), M, E, ce)
+            else:
+                dha32 = o.linear_small_bwd(dtok_a, ha, wa2, s.g("readout_adj_mlp.fc2.weight"), s.g("readout_adj_mlp.fc2.bias"))
             dha = o.empty((M, E), BF16)
             o.copy_cols(dha32, 0, dha, 0, E)
             del dha32

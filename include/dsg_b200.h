@@ -362,6 +362,10 @@ DSG_API int dsg_tr_adj_out(const float* in, const uint8_t* flags, const float* x
                            float* out, int B, int n, int c_e, int backward, dsg_stream_t stream);
 DSG_API int dsg_tr_node_out(const float* in, const uint8_t* flags, const float* x_node, const float* c_skip, const float* c_out,
                             float* out, int B, int n, int c_n, int backward, dsg_stream_t stream);
+/* second layer of the adjacency read-out MLP (:806-809), c_e <= 8 outputs from embed <= 128 hidden channels (h bf16):
+ * dtok == NULL: tok [M, c_e] = h w^T + b; else dw [c_e, embed] += dtok^T h (the bias gradient is dsg_tr_colsum of dtok) */
+DSG_API int dsg_tr_adj_fc2(const void* h, const float* w, const float* b, float* tok, const float* dtok, float* dw, long long M,
+                           int E, int ce, dsg_stream_t stream);
 /* masked mean of :812-813: dpooled == NULL: pooled [B n, C] from rep [B n n, C]; else drep += its backward */
 DSG_API int dsg_tr_node_pool(const float* rep, const uint8_t* flags, float* pooled, const float* dpooled, float* drep, int B,
                              int n, int C, dsg_stream_t stream);

@@ -210,6 +210,22 @@ def test_small_fp32_gemm(M, N, K):
     assert _rel(dw2, dy.t() @ xb.float()) < 1e-4
 
 
+@pytest.mark.parametrize("M,E,ce", [(70000, 96, 6), (4099, 96, 3), (513, 128, 8)])
+def test_adj_head_output_layer(M, E, ce):
+    g = torch.Generator(device=DEV).manual_seed(M)
+    h = torch.randn(M, E, device=DEV, generator=g).to(torch.bfloat16)
+    w = torch.randn(ce, E, device=DEV, generator=g) / E ** 0.5
+    b = torch.randn(ce, device=DEV, generator=g)
+    dtok = torch.randn(M, ce, device=DEV, generator=g)
+    tok = torch.empty(M, ce, device=DEV)
+    dw = torch.full((ce, E), 0.25, device=DEV)
+    lib, st = native.lib(), native.stream_ptr(DEV)
+    native.check(lib.dsg_tr_adj_fc2(h.data_ptr(), w.data_ptr(), b.data_ptr(), tok.data_ptr(), None, None, M, E, ce, st), "fwd")
+    native.check(lib.dsg_tr_adj_fc2(h.data_ptr(), None, None, None, dtok.data_ptr(), dw.data_ptr(), M, E, ce, st), "wgrad")
+    assert _rel(tok, h.float() @ w.t() + b) < 1e-5
+    assert _rel(dw - 0.25, dtok.t() @ h.float()) < 1e-4
+
+
 # ---------------------------------------------------------------------------------------------------------
 # window attention backward
 # ---------------------------------------------------------------------------------------------------------
