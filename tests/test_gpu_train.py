@@ -577,3 +577,48 @@ def test_training_trajectory_matches_the_reference_loop():
     cos = num / (den_a * den_b) ** 0.5
     print(f"cosine between the accumulated weight updates: {cos:.4f}")
     assert cos > 0.9, cos
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 4), ("vg", 2)])
+def test_training_gradients_match_reference_goldens(name, batch, golden_dir):
+    """The native forward + backward of one training iteration (model -> rainbow loss -> backward) against gradients the
+    UNMODIFIED reference produced on the same weights and inputs (tests/golden/make_golden_train.py): losses, the norm of
+    every parameter's gradient, and the complete gradient of the tensors the fixture holds."""
+    import os
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"train_grads_{name}.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    adj, node, flags, _, sc_adj, sc_node = synthetic_inputs(cfg, batch, seed=11)
+    sigmas = torch.tensor([0.2, 1.5, 4.0, 0.7, 0.05, 9.0, 0.9, 2.2])[:batch].contiguous()
+    f = flags.float()
+    tgt_adj = adj.sign() * f[:, None, :, None] * f[:, None, None, :]
+    tgt_node = node.clamp(-1, 1) * f[:, :, None]
+    weights = (sigmas ** 2 + 0.25) / (sigmas * 0.5) ** 2
+    net = _net(cfg, sd).train()
+    model = NodeAdjPrecond(precond="edm", model=net, self_condition=False, symmetric_noise=False).train()
+    loss_fn = NodeAdjRainbowLoss(edge_loss_weight=1.0, node_loss_weight=1.0, objective="edm")
+    dev = lambda t: t.to(DEV)
+    oa, ox = model(adjs=dev(adj), nodes=dev(node), node_flags=dev(flags), sigmas=dev(sigmas), self_cond_adjs=dev(sc_adj),
+                   self_cond_nodes=dev(sc_node))
+    la, ln = loss_fn(net_pred_a=oa, net_pred_x=ox, net_target_a=dev(tgt_adj), net_target_x=dev(tgt_node), net_cond=dev(sigmas),
+                     adjs_perturbed=dev(adj), adjs_gt=dev(tgt_adj), x_perturbed=dev(node), x_gt=dev(tgt_node),
+                     node_flags=dev(flags), loss_weight=dev(weights), reduction="none")
+    (la.mean() + ln.mean()).backward()
+    torch.cuda.synchronize()
+    assert np.allclose(la.detach().cpu().numpy(), g["loss_adj"], rtol=3e-2) and np.allclose(ln.detach().cpu().numpy(), g["loss_node"], rtol=3e-2)
+    params = dict(net.named_parameters())
+    norms = g["norms"]
+    big = norms.max()
+    worst = 0.0
+    for k, want in zip(list(g["keys"]), norms):
+        got = float(params[k].grad.double().norm())
+        if want > 1e-3 * big:
+            worst = max(worst, abs(got - want) / want)
+            assert abs(got - want) < 6e-2 * want, (k, got, want)
+    errs = {}
+    for key in g.files:
+        if key.startswith("grad::"):
+            want = torch.from_numpy(g[key])
+            errs[key[6:]] = _rel(params[key[6:]].grad.detach().cpu(), want)
+    print(f"{name}: worst gradient-norm deviation {worst:.2e}; full tensors: " + ", ".join(f"{k} {e:.2e}" for k, e in errs.items()))
+    assert max(errs.values()) < 1e-1 and float(np.mean(list(errs.values()))) < 4e-2, errs

@@ -194,3 +194,42 @@ def test_sampler256_first_snapshot_matches_reference(case, name, golden_dir):
                     assert (got - want).norm() / want.norm() < 1e-5, (i, float((got - want).norm() / want.norm()))
     if steps == 256:
         assert (adjs - torch.from_numpy(g["adjs"])).norm() / torch.from_numpy(g["adjs"]).norm() < 1e-4
+
+
+def _train_case(cfg, batch):
+    """The inputs tests/golden/make_golden_train.py fed the unmodified reference (same construction, restated here)."""
+    adj, node, flags, _, sc_adj, sc_node = synthetic_inputs(cfg, batch, seed=11)
+    sigmas = torch.tensor([0.2, 1.5, 4.0, 0.7, 0.05, 9.0, 0.9, 2.2])[:batch].contiguous()
+    f = flags.float()
+    tgt_adj = adj.sign() * f[:, None, :, None] * f[:, None, None, :]
+    tgt_node = node.clamp(-1, 1) * f[:, :, None]
+    weights = (sigmas ** 2 + 0.25) / (sigmas * 0.5) ** 2
+    return adj, node, flags, sigmas, sc_adj, sc_node, tgt_adj, tgt_node, weights
+
+
+@pytest.mark.parametrize("name,batch", [("tiny", 4), ("vg", 2)])
+def test_training_gradients_match_reference(name, batch, golden_dir):
+    """One training iteration's forward + backward (trainer_node_adj.py:104-173) on the oracle with torch autograd against
+    the gradients the UNMODIFIED reference produced (tests/golden/train_grads_*.npz): pins what the GPU gradient-parity
+    tests of the native backward compare with."""
+    from oracle import train_oracle as T
+    torch.set_num_threads(8)
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(golden_dir, f"train_grads_{name}.npz"))
+    sd = synthetic_state_dict(cfg, seed=1234, stress=True)
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "attn_mask" not in k else v) for k, v in sd.items()}
+    adj, node, flags, sigmas, sc_adj, sc_node, tgt_adj, tgt_node, weights = _train_case(cfg, batch)
+    da, dn = O.precond_forward(_net(cfg, leaves), adj, node, flags, sigmas, sc_adj, sc_node)
+    la, ln = T.regression_loss(da, dn, tgt_adj, tgt_node, flags, weights, 1.0, 1.0, "none")
+    (la.mean() + ln.mean()).backward()
+    assert np.allclose(la.detach().numpy(), g["loss_adj"], rtol=1e-5) and np.allclose(ln.detach().numpy(), g["loss_node"], rtol=1e-5)
+    keys, norms = list(g["keys"]), g["norms"]
+    assert len(keys) == sum(1 for v in leaves.values() if v.is_floating_point() and v.requires_grad)
+    for k, want in zip(keys, norms):
+        got = float(leaves[k].grad.double().norm())
+        assert abs(got - want) <= 2e-4 * max(want, 1e-6 * norms.max()), (k, got, want)
+    for key in g.files:
+        if key.startswith("grad::"):
+            want = torch.from_numpy(g[key])
+            got = leaves[key[6:]].grad
+            assert float((got - want).norm() / want.norm().clamp_min(1e-20)) < 1e-4, key
