@@ -42,12 +42,34 @@ class FusedAdam(torch.optim.Optimizer):
         if len(params) != n_flat:
             raise NotImplementedError("FusedAdam: the model has trainable parameters outside the DiffuseSG denoiser")
         self.max_grad_norm = max_grad_norm
-        with torch.cuda.device(dev):
+        with native.device_guard(dev):
             self.m = torch.zeros_like(self.ts.flat)
             self.v = torch.zeros_like(self.ts.flat)
             self.gsumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.steps = 0
         self.emas: List["NativeEMA"] = []
+
+    # checkpoint / resume (the reference's trainer saves optimizer.state_dict() next to the model): the two moment buffers
+    # are stored per parameter under the parameter's name, so a checkpoint does not depend on the flat layout
+    def state_dict(self):
+        ts = self.ts
+        per = {k: dict(exp_avg=self.m[ts.offs[k]: ts.offs[k] + ts.params[k].numel()].view(ts.shapes[k]).clone(),
+                       exp_avg_sq=self.v[ts.offs[k]: ts.offs[k] + ts.params[k].numel()].view(ts.shapes[k]).clone())
+               for k in ts.order}
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return {"fused_adam": 1, "step": self.steps, "state": per, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        if "fused_adam" not in sd:
+            raise ValueError("FusedAdam.load_state_dict: not a FusedAdam checkpoint")
+        ts = self.ts
+        for k in ts.order:
+            n = ts.params[k].numel()
+            self.m[ts.offs[k]: ts.offs[k] + n].copy_(sd["state"][k]["exp_avg"].reshape(-1))
+            self.v[ts.offs[k]: ts.offs[k] + n].copy_(sd["state"][k]["exp_avg_sq"].reshape(-1))
+        self.steps = int(sd["step"])
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update(saved)
 
     def attach_emas(self, emas):
         self.emas = list(emas or [])

@@ -458,3 +458,29 @@ def test_native_ddp_world_size_2_gloo(tmp_path):
     assert torch.equal(d0["flat"], d1["flat"])                                   # parameters broadcast from rank 0
     assert d0["mid"] == (1.0, 1.5) and d1["mid"] == (2.0, 1.5)                   # read-out range reduced first
     assert float(d0["grad"].min()) == 1.5 == float(d0["grad"].max()) and torch.equal(d0["grad"], d1["grad"])
+
+
+def test_fused_adam_checkpoint_round_trip():
+    """optimizer.state_dict() / load_state_dict(): moments stored per parameter name, step count and lr restored."""
+    from diffusesg_b200.utils.train_utils import FusedAdam
+    m = NodeAdjPrecond(precond="edm", model=_module(CONFIGS["tiny"]), self_condition=True, symmetric_noise=False)
+    opt = FusedAdam(m, lr=3e-4, weight_decay=0.01)
+    torch.manual_seed(0)
+    opt.m.normal_()
+    opt.v.uniform_()
+    opt.steps = 17
+    opt.param_groups[0]["lr"] = 1.5e-4
+    sd = opt.state_dict()
+    assert set(sd["state"]) == {k for k, _ in m.model.named_parameters()}
+    assert sd["state"]["norm.weight"]["exp_avg"].shape == (96,)
+    m2 = NodeAdjPrecond(precond="edm", model=_module(CONFIGS["tiny"]), self_condition=True, symmetric_noise=False)
+    opt2 = FusedAdam(m2, lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.steps == 17 and opt2.param_groups[0]["lr"] == 1.5e-4 and opt2.param_groups[0]["weight_decay"] == 0.01
+    ts, ts2 = opt.ts, opt2.ts
+    for k in ts.order:
+        n = ts.params[k].numel()
+        assert torch.equal(opt2.m[ts2.offs[k]: ts2.offs[k] + n], opt.m[ts.offs[k]: ts.offs[k] + n]), k
+        assert torch.equal(opt2.v[ts2.offs[k]: ts2.offs[k] + n], opt.v[ts.offs[k]: ts.offs[k] + n]), k
+    with pytest.raises(ValueError):
+        opt2.load_state_dict({"state": {}})
