@@ -252,7 +252,7 @@ class GraphedTrainStep:
         coin = bool(self.precond.self_condition and self.np.random.rand() < 0.5)
         passes0 = self.precond.raw_passes
         if coin not in self.graphs:
-            self._capture(coin)                # also leaves valid gradients of this batch? no: replay below produces them
+            self._capture(coin)                # warm-up + capture only; the replay below computes this batch's gradients
         g, (la, ln) = self.graphs[coin]
         g.replay()
         self.precond.raw_passes = passes0 + (2 if coin else 1)
