@@ -683,6 +683,9 @@ class DenoiserTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_adj, d_node):
         tp = ctx.tp
+        if tp is None:
+            raise RuntimeError("DiffuseSG (B200): the training tape is consumed by its first backward (the saved activations "
+                               "are released as it runs); backward(retain_graph=True) twice is not supported")
         ctx.tp = None
         s = tp.s
         s.attach_grads()

@@ -248,6 +248,10 @@ class GraphedTrainStep:
             self.static = (torch.empty_like(adjs_gt, device=dev), torch.empty_like(nodes_gt, device=dev),
                            torch.empty_like(node_flags, device=dev))
         for dst, src in zip(self.static, (adjs_gt, nodes_gt, node_flags)):
+            if dst.shape != src.shape or dst.dtype != src.dtype:
+                raise ValueError(f"GraphedTrainStep: batch of shape {tuple(src.shape)} / {src.dtype}, the graphs were captured "
+                                 f"for {tuple(dst.shape)} / {dst.dtype} (fixed at the first call; use train_one_step for "
+                                 "ragged last batches)")
             dst.copy_(src, non_blocking=True)
         coin = bool(self.precond.self_condition and self.np.random.rand() < 0.5)
         passes0 = self.precond.raw_passes
