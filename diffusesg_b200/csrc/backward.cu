@@ -1177,6 +1177,27 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
     }
     __syncthreads();
     // S = Q K^T and dP = dO V^T
+    if (TC == 64) {
+      // 64 tokens: eight row strips (2 products x 4 row tiles) for eight warps - the A fragments of a strip are loaded once
+      const int which = warp >> 2, ti = warp & 3;
+      const bf16_t* A = which == 0 ? sQ : sDO;
+      const bf16_t* Bt = which == 0 ? sK : sV;
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa[2];
+      wmma::load_matrix_sync(fa[0], A + ti * 16 * kQP, kQP);
+      wmma::load_matrix_sync(fa[1], A + ti * 16 * kQP + 16, kQP);
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        wmma::fragment<wmma::accumulator, 16, 16, 16, float> fc;
+        wmma::fill_fragment(fc, 0.f);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fb;
+          wmma::load_matrix_sync(fb, Bt + tj * 16 * kQP + kk * 16, kQP);
+          wmma::mma_sync(fc, fa[kk], fb, fc);
+        }
+        wmma::store_matrix_sync((which == 0 ? sS : sD) + ti * 16 * PF + tj * 16, fc, PF, wmma::mem_row_major);
+      }
+    } else
     for (int job = warp; job < 2 * NT * NT; job += 8) {
       const int which = job / (NT * NT), tile = job - which * NT * NT;
       const int ti = tile / NT, tj = tile - ti * NT;
@@ -1255,6 +1276,34 @@ window_attention_bwd_tc_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __r
     }
     __syncthreads();
     // dV = P^T dO -> stV, dQ = dS K -> stQ
+    if (TC == 64) {
+      // eight (product, row tile) strips: both 16-column halves of the output share the A fragment of every k step
+      const int which = warp >> 2, tr = warp & 3;
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> fc0, fc1;
+      wmma::fill_fragment(fc0, 0.f);
+      wmma::fill_fragment(fc1, 0.f);
+      const bf16_t* Bm = which == 0 ? sDO : sK;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fb0, fb1;
+        wmma::load_matrix_sync(fb0, Bm + kt * 16 * kQP, kQP);
+        wmma::load_matrix_sync(fb1, Bm + kt * 16 * kQP + 16, kQP);
+        if (which == 0) {
+          wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fa;   // A(j, i) = P[i][j]
+          wmma::load_matrix_sync(fa, sPb + kt * 16 * LDB + tr * 16, LDB);
+          wmma::mma_sync(fc0, fa, fb0, fc0);
+          wmma::mma_sync(fc1, fa, fb1, fc1);
+        } else {
+          wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fa;   // A(i, j) = dS[i][j]
+          wmma::load_matrix_sync(fa, sDb + tr * 16 * LDB + kt * 16, LDB);
+          wmma::mma_sync(fc0, fa, fb0, fc0);
+          wmma::mma_sync(fc1, fa, fb1, fc1);
+        }
+      }
+      float* st = (which == 0 ? stV : stQ) + tr * 16 * PF;
+      wmma::store_matrix_sync(st, fc0, PF, wmma::mem_row_major);
+      wmma::store_matrix_sync(st + 16, fc1, PF, wmma::mem_row_major);
+    } else
     for (int job = warp; job < 2 * NT * 2; job += 8) {
       const int which = job / (NT * 2), tile = job - which * NT * 2;
       const int tr = tile >> 1, td = tile & 1;
@@ -1695,6 +1744,7 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSG_CUDA_CHECK(cudaFuncSetAttribute(window_attention_bwd_tc_kernel<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int total = batch * (res / window) * (res / window);
   // one atomicAdd pass over dbias per CTA: keep the CTA count near two waves
@@ -1705,6 +1755,10 @@ int dsg_tr_window_attention_bwd(const void* qkv, const void* datt, const float* 
   ctas_x = (total + per - 1) / per;
   if (tc && T == 64)
     window_attention_bwd_tc_kernel<64><<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
+        res, window, shift, heads, per);
+  else if (tc && T == 100)   // the 10 x 10 windows of the COCO-Stuff geometry
+    window_attention_bwd_tc_kernel<100><<<dim3(ctas_x, heads), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16_t*>(qkv), static_cast<const bf16_t*>(datt), bias, mask, static_cast<bf16_t*>(dqkv), dbias, batch,
         res, window, shift, heads, per);
   else if (tc)
